@@ -1,0 +1,51 @@
+"""Pins oracle/tnet_oracle.c against the reference's own CPU trainer (oracle/_ref/TNet = unmodified
+src/TNet.cc + TNetLib + KaldiLib, run by tests/golden/make_golden.py --impl cpu) and, when the GPU goldens
+are present, against the reference's GPU trainer TNetCu run on a B200."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from replay import replay_mlp
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _check(g, acc_double, wtol, etol):
+    net, nb, perms = replay_mlp(g, lambda L: O.Net(L, acc_double=acc_double), O.Cache,
+                                lambda s: O.lib.orc_srand48(s))
+    err, frames, correct = net.stats()
+    assert frames == int(g["ref_frames"])                       # bunch slicing / discard rule exact
+    # report line prints 6 significant digits
+    assert abs(err - float(g["ref_err"])) <= etol * abs(float(g["ref_err"]))
+    ref_correct = float(g["ref_correct_pct"]) * frames / 100.0
+    assert abs(correct - ref_correct) <= max(1.0, 0.003 * frames)
+    k = 0
+    for i, L in enumerate(net.layers):
+        if L[0] != "affine":
+            continue
+        Wt, b = net.get_affine(i)
+        rW, rb = g["final_Wt%d" % k], g["final_b%d" % k]
+        # reference writes 6 significant digits (KaldiLib/Matrix.tcc:522-532)
+        np.testing.assert_allclose(Wt, rW, rtol=wtol, atol=wtol * np.abs(rW).max())
+        np.testing.assert_allclose(b, rb, rtol=wtol, atol=wtol * max(1e-3, np.abs(rb).max()))
+        k += 1
+    return correct, ref_correct
+
+
+@pytest.mark.parametrize("case", ["mlp_small", "mlp_norand_wc"])
+@pytest.mark.parametrize("acc_double", [0, 1])
+def test_oracle_vs_reference_cpu_tnet(case, acc_double):
+    g = np.load(os.path.join(GOLD, "cpu_%s.npz" % case))
+    correct, ref_correct = _check(g, acc_double, wtol=2e-5, etol=2e-5)
+    assert correct == round(ref_correct)      # frame-accuracy count exact on these fixtures
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "gpu_mlp_*.npz"))) or [None])
+def test_oracle_vs_reference_gpu_tnetcu(path):
+    if path is None:
+        pytest.skip("GPU goldens not generated yet (tests/golden/make_golden.py --impl gpu on a B200)")
+    g = np.load(path)
+    _check(g, 0, wtol=5e-5, etol=5e-5)
