@@ -1,0 +1,193 @@
+/*
+ * tnet_b200.h — C ABI of libtnetb200.so: the Blackwell (sm_100a) replacement for the bottom seam of
+ * TNet's GPU training path (troylee/nnet-asr).
+ *
+ * What it replaces in the reference (paths relative to /root/reference/src):
+ *   - CuBaseLib/cukernels.h:5-79      the `cudaF_*` extern "C" kernel launchers
+ *   - CuBaseLib/curandkernels.h:8-31  `cudaF_rand / cudaF_gauss_rand / cudaF_binarize_probs`
+ *   - legacy cuBLAS v1 calls: cublasSgemm (CuBaseLib/cumatrix.tcc:363, cumath.cc:105,237),
+ *     cublasSgemv (cumath.cc:334), cublasSger (cumath.cc:358, cumatrix.tcc:384), cublasInit/Shutdown
+ *     (cudevice.cc:60,66)
+ *   - the cudaMallocPitch/cudaMemcpy2D/cudaMemset plumbing of CuMatrix/CuVector
+ *     (cumatrix.tcc:16-190, cuvector.tcc:14-120)
+ *
+ * Differences from the reference seam: operands keep the `(pointer, MatrixDim)` form but the
+ * caller no longer chooses grid/block; every call takes an explicit context (device, stream, math mode,
+ * workspace) and returns an int status instead of relying on cudaGetLastError(); ops that always follow
+ * one another in the reference (bias + GEMM + sigmoid; GEMM + diff-sigmoid; GEMM + momentum/L2 update;
+ * softmax + cross-entropy + frame accuracy) have fused entry points next to the 1:1 ones.
+ *
+ * All matrix pointers are DEVICE pointers to row-major fp32 with leading dimension `stride` (in elements).
+ * For the tensor-core GEMMs `stride` must be a multiple of 4 and the base 16-byte aligned (tnb_malloc_pitch
+ * guarantees a 128-byte pitch).  Nothing here falls back to the CPU: without a CUDA device every compute
+ * entry point returns TNB_ERR_CUDA.
+ */
+#ifndef TNET_B200_H_
+#define TNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Same layout as the reference's MatrixDim (CuBaseLib/cukernels.h:12-16). */
+typedef struct TnbMatrixDim_ {
+  int rows;
+  int cols;
+  int stride;
+} TnbMatrixDim;
+
+typedef struct TnbContext_ TnbContext; /* opaque: device, stream(s), tensor-map cache, counters */
+
+enum {
+  TNB_OK = 0,
+  TNB_ERR_CUDA = 1,     /* CUDA runtime/driver error; text via tnb_last_error() */
+  TNB_ERR_ARG = 2,      /* bad dimension / alignment / null pointer */
+  TNB_ERR_UNSUPPORTED = 3,
+  TNB_ERR_NCCL = 4
+};
+
+/* GEMM arithmetic (north_star: "fp32-equivalent via 3xTF32 as the default, bf16 reported separately") */
+enum {
+  TNB_MATH_3XTF32 = 0, /* split fp32 = hi + lo (tf32 each); acc += lo*hi + hi*lo + hi*hi  (default) */
+  TNB_MATH_TF32 = 1,   /* single tf32 product (operands rounded to 10-bit mantissa) */
+  TNB_MATH_FP32_SIMT = 2 /* plain fp32 FMA on CUDA cores: debug / cross-check path, no tensor cores */
+};
+
+/* ---- context / device (replaces CuDevice, CuBaseLib/cudevice.cc:22-121) -------------------------- */
+const char *tnb_version(void);
+const char *tnb_last_error(void);                       /* thread-local text of the last failure */
+int tnb_device_count(int *count);                       /* TNB_ERR_CUDA when no driver/GPU */
+/* device < 0 : pick the GPU with the largest free-memory ratio (cudevice.cc:27-56). */
+int tnb_ctx_create(TnbContext **ctx, int device);
+int tnb_ctx_destroy(TnbContext *ctx);
+int tnb_ctx_device(TnbContext *ctx, int *device);
+int tnb_ctx_set_math(TnbContext *ctx, int math_mode);
+int tnb_ctx_get_math(TnbContext *ctx, int *math_mode);
+int tnb_ctx_stream(TnbContext *ctx, void **cuda_stream); /* the cudaStream_t every op is enqueued on */
+int tnb_ctx_sync(TnbContext *ctx);                      /* reference semantics: cudaThreadSynchronize() */
+int tnb_ctx_free_memory(TnbContext *ctx, size_t *free_bytes, size_t *total_bytes); /* cudevice.cc:100-118 */
+/* number of kernels of THIS library launched through ctx since creation (graph replays included) */
+int tnb_ctx_launch_count(TnbContext *ctx, unsigned long long *launches);
+
+/* ---- memory (replaces cudaMallocPitch/cudaFree/cudaMemcpy2D/cudaMemset in cumatrix.tcc) ----------- */
+/* rows x cols fp32 (or any 4-byte type), zero-filled like CuMatrix::Init (cumatrix.tcc:16-34);
+ * *stride_elems is a multiple of 32 elements (128 B). */
+int tnb_malloc_pitch(TnbContext *ctx, void **ptr, int *stride_elems, int rows, int cols);
+int tnb_malloc(TnbContext *ctx, void **ptr, size_t bytes); /* zero-filled */
+int tnb_free(TnbContext *ctx, void *ptr);
+int tnb_memset(TnbContext *ctx, void *ptr, int value, size_t bytes);
+/* kind: 0 H2D, 1 D2H, 2 D2D.  Asynchronous on the ctx stream for pinned host memory. */
+int tnb_memcpy2d(TnbContext *ctx, void *dst, size_t dpitch_bytes, const void *src, size_t spitch_bytes,
+                 size_t width_bytes, size_t height, int kind);
+int tnb_memcpy(TnbContext *ctx, void *dst, const void *src, size_t bytes, int kind);
+int tnb_host_alloc(void **ptr, size_t bytes); /* pinned host memory */
+int tnb_host_free(void *ptr);
+
+/* ---- 1:1 replacements of cukernels.h (float instances) ------------------------------------------- */
+int tnb_set_const(TnbContext *ctx, float *mat, float value, TnbMatrixDim d);                 /* cukernels.h:22 */
+int tnb_apply_log(TnbContext *ctx, float *mat, TnbMatrixDim d);                              /* :23 */
+int tnb_scale_cols(TnbContext *ctx, float *mat, const float *scale, TnbMatrixDim d);         /* :26 */
+int tnb_scale_rows(TnbContext *ctx, float *mat, const float *scale, TnbMatrixDim d);         /* :27 */
+int tnb_add_scaled(TnbContext *ctx, float alpha, const float *A, float beta, float *dst, TnbMatrixDim d); /* :28 */
+int tnb_add_scaled_row(TnbContext *ctx, float alpha, const float *row, float beta, float *dst, TnbMatrixDim d); /* :29 */
+int tnb_mul_elem(TnbContext *ctx, float *mat, const float *A, TnbMatrixDim d);               /* :30 */
+int tnb_log_elem(TnbContext *ctx, float *mat, TnbMatrixDim d);                               /* :31 */
+/* vec[c] = alpha * sum_r mat[r,c] + beta * vec[c]; both reference variants (:34-35) collapse into one
+ * deterministic kernel with double partial sums. */
+int tnb_add_col_sum(TnbContext *ctx, float alpha, const float *mat, float beta, float *vec, TnbMatrixDim d);
+int tnb_sigmoid(TnbContext *ctx, float *y, const float *x, TnbMatrixDim d);                  /* :40 */
+int tnb_diff_sigmoid(TnbContext *ctx, float *eout, const float *e, const float *y, TnbMatrixDim d); /* :41 */
+int tnb_softmax(TnbContext *ctx, float *y, const float *x, TnbMatrixDim d);                  /* :38-39 */
+int tnb_expand(TnbContext *ctx, float *y, const float *x, const int *off, TnbMatrixDim d_out, TnbMatrixDim d_in); /* :43 */
+int tnb_rearrange(TnbContext *ctx, float *y, const float *x, const int *copy_from, TnbMatrixDim d_out, TnbMatrixDim d_in); /* :44 */
+/* y[r,:] = x[copy_from[r],:] for r < d_out.rows (= permutation length), cumath.cc:155-174 */
+int tnb_randomize(TnbContext *ctx, float *y, const float *x, const int *copy_from, TnbMatrixDim d_out, TnbMatrixDim d_in); /* :45 */
+/* match[r] = argmax(out[r,:]) == argmax(des[r,:]) with the reference's tie rules (bit-exact):
+ * cols > 256 sequential first-max; cols <= 256 the index tree of _max_id_reduce (cukernels.cu:424-446). */
+int tnb_check_class(TnbContext *ctx, const float *out, const float *des, int *match, TnbMatrixDim d); /* :47-48 */
+
+/* ---- replacements of curandkernels.h (per-element Hybrid-Taus state z1..z4, bit-exact streams) ----- */
+int tnb_rand(TnbContext *ctx, float *mat, unsigned *z1, unsigned *z2, unsigned *z3, unsigned *z4, TnbMatrixDim d);
+int tnb_gauss_rand(TnbContext *ctx, float *mat, unsigned *z1, unsigned *z2, unsigned *z3, unsigned *z4, TnbMatrixDim d);
+int tnb_binarize_probs(TnbContext *ctx, float *states, const float *probs, const float *rnd, TnbMatrixDim d);
+/* fused CuRand::BinarizeProbs (curand.tcc:136-155): states = probs > HybridTaus(z) ? 1 : 0, no tmp matrix */
+int tnb_rand_binarize(TnbContext *ctx, float *states, const float *probs, unsigned *z1, unsigned *z2, unsigned *z3,
+                      unsigned *z4, TnbMatrixDim d);
+/* fused CuRand::AddGaussNoise (curand.tcc:56-60): tgt += gscale * BoxMuller(z) */
+int tnb_add_gauss_noise(TnbContext *ctx, float *tgt, float gscale, unsigned *z1, unsigned *z2, unsigned *z3,
+                        unsigned *z4, TnbMatrixDim d);
+
+/* ---- GEMM: replaces cublasSgemm as called by CuMatrix<float>::Gemm (cumatrix.tcc:335-370) --------- */
+/* Row-major  C[m x n] = alpha * op(A) * op(B) + beta * C ; transa/transb in {'N','T'} exactly as
+ * CuMatrix::Gemm(transa, transb, alpha, A, B, beta) sees them.  tcgen05/TMEM kernel fed by TMA;
+ * arithmetic per tnb_ctx_set_math. */
+int tnb_gemm(TnbContext *ctx, char transa, char transb, int m, int n, int k, float alpha, const float *A, int lda,
+             const float *B, int ldb, float beta, float *C, int ldc);
+/* y = alpha*op(A)[offset rows/cols]*x + beta*y  — CuMath::OffsetGemv (cumath.cc:283-340) */
+int tnb_offset_gemv(TnbContext *ctx, char trans, float alpha, const float *A, TnbMatrixDim dA, const float *x, int dimX,
+                    float beta, float *y, int dimY, int offsetY);
+/* A += alpha * x * y^T  — CuMath::BlasGer / CuMatrix::BlasGer (cumath.cc:344-362) */
+int tnb_ger(TnbContext *ctx, float alpha, const float *x, int dimX, const float *y, int dimY, float *A, TnbMatrixDim dA);
+
+/* ---- fused hot-path ops ----------------------------------------------------------------------------- */
+enum { TNB_ACT_NONE = 0, TNB_ACT_SIGMOID = 1 };
+/* CuBiasedLinearity::PropagateFnc (+ CuSigmoid::PropagateFnc when act = SIGMOID):
+ *   Y[rows x nout] = act( X[rows x nin] * W[nin x nout] + bias )      cuBiasedLinearity.cc:11-16, cuActivation.cc:9-14 */
+int tnb_affine_fwd(TnbContext *ctx, const float *X, TnbMatrixDim dX, const float *W, TnbMatrixDim dW, const float *bias,
+                   float *Y, TnbMatrixDim dY, int act);
+/* CuBiasedLinearity::BackpropagateFnc (+ CuSigmoid::BackpropagateFnc of the layer below when Yprev != NULL):
+ *   Eprev[rows x nin] = (E[rows x nout] * W^T) (.* Yprev .* (1 - Yprev))   cuBiasedLinearity.cc:20-25, cuActivation.cc:17-22 */
+int tnb_affine_bwd_dx(TnbContext *ctx, const float *E, TnbMatrixDim dE, const float *W, TnbMatrixDim dW, const float *Yprev,
+                      TnbMatrixDim dYprev, float *Eprev, TnbMatrixDim dEprev);
+/* weight gradient only:  G[nin x nout] = X^T * E ;  gb[nout] = colsum(E)   (for data-parallel: allreduce G,gb, then
+ * tnb_sgd_update).  gb may be NULL. */
+int tnb_affine_grad(TnbContext *ctx, const float *X, TnbMatrixDim dX, const float *E, TnbMatrixDim dE, float *G,
+                    TnbMatrixDim dG, float *gb);
+/* CuBiasedLinearity::Update (cuBiasedLinearity.cc:44-64) in one pass over the weights:
+ *   corrW = X^T*E + mmt*corrW ; corrb = colsum(E) + mmt*corrb ; W += (-lr/N)*corrW ; b += (-lr/N)*corrb ;
+ *   W += (-lr*wc*(gdf?1:rows))*W        with N = (gdf?rows:1)/(1-mmt), scalars evaluated in float as the reference.
+ * n_frames_global > 0 overrides `rows` in N and in the L2 factor (data-parallel shards of one bunch). */
+int tnb_affine_update(TnbContext *ctx, const float *X, TnbMatrixDim dX, const float *E, TnbMatrixDim dE, float *W,
+                      TnbMatrixDim dW, float *bias, float *corrW, float *corrb, float lr, float mmt, float wc,
+                      int grad_div_frm, int n_frames_global);
+/* the same update given an already summed gradient (after the NCCL allreduce):
+ *   corrW = G + mmt*corrW ; ... as above.  gb/bias/corrb may be NULL together. */
+int tnb_sgd_update(TnbContext *ctx, const float *G, float *W, float *corrW, TnbMatrixDim dW, const float *gb, float *bias,
+                   float *corrb, float lr, float mmt, float wc, int grad_div_frm, int n_frames);
+
+/* Objective accumulators kept on the device (read once per epoch instead of 2 blocking D2H per bunch,
+ * cuObjectiveFunction.cc:61-80).  Layout is ABI. */
+typedef struct TnbObjStats_ {
+  double error;      /* sum of -t*log(max(y,FLT_MIN))  (xent)  or  sum err^2 (mse)  */
+  long long frames;  /* rows evaluated */
+  long long correct; /* rows with argmax(y)==argmax(t) (xent only) */
+} TnbObjStats;
+/* CuSoftmax::PropagateFnc + CuCrossEntropy::Evaluate fused (cuActivation.cc:26-31, cuObjectiveFunction.cc:48-84):
+ *   Y = softmax(A) (Y may be NULL), Err = Y - T, stats += {xent, rows, correct}.  `stats` is a DEVICE pointer. */
+int tnb_softmax_xent(TnbContext *ctx, const float *A, const float *T, float *Y, float *Err, TnbMatrixDim d, TnbObjStats *stats);
+/* CuCrossEntropy::Evaluate on an existing softmax output */
+int tnb_xent_eval(TnbContext *ctx, const float *Y, const float *T, float *Err, TnbMatrixDim d, TnbObjStats *stats);
+/* CuMeanSquareError::Evaluate (cuObjectiveFunction.cc:26-46; no 1/2 factor) */
+int tnb_mse_eval(TnbContext *ctx, const float *Y, const float *T, float *Err, TnbMatrixDim d, TnbObjStats *stats);
+/* dense one-hot targets from class ids (Labels.cc:66,156 builds them on the host): T[r, lab[r]] = 1 else 0 */
+int tnb_onehot(TnbContext *ctx, float *T, const int *labels, TnbMatrixDim d);
+
+/* ---- data-parallel exchange (no counterpart in the reference GPU path; mirrors the CPU trainer's
+ *      gradient reduce, TNetLib/Platform.h:300-335, BiasedLinearity.cc:90-178) ------------------------ */
+#define TNB_NCCL_ID_BYTES 128
+int tnb_comm_unique_id(unsigned char id[TNB_NCCL_ID_BYTES]);             /* rank 0 creates, caller broadcasts */
+int tnb_comm_init(TnbContext *ctx, const unsigned char id[TNB_NCCL_ID_BYTES], int rank, int world);
+int tnb_comm_destroy(TnbContext *ctx);
+int tnb_comm_world(TnbContext *ctx, int *rank, int *world);
+/* in-place sum over ranks of `count` floats, enqueued on the ctx's communication stream after everything
+ * already enqueued on the compute stream; tnb_comm_wait() makes the compute stream wait for it. */
+int tnb_allreduce_sum(TnbContext *ctx, float *buf, size_t count);
+int tnb_comm_wait(TnbContext *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TNET_B200_H_ */

@@ -1,0 +1,87 @@
+// common.cuh — internal definitions shared by the .cu files of libtnetb200.so
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "tnet_b200.h"
+
+namespace tnb {
+
+void set_error(const char *fmt, ...);
+
+#define TNB_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      tnb::set_error("CUDA error %d (%s) at %s:%d: %s", (int)e__, cudaGetErrorString(e__),     \
+                     __FILE__, __LINE__, #call);                                               \
+      return TNB_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define TNB_ARG(cond, msg)                                                                     \
+  do {                                                                                         \
+    if (!(cond)) {                                                                             \
+      tnb::set_error("bad argument at %s:%d: %s (%s)", __FILE__, __LINE__, msg, #cond);        \
+      return TNB_ERR_ARG;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+// after every kernel launch: count it and surface launch-configuration errors
+#define TNB_LAUNCHED(ctx)                                                                      \
+  do {                                                                                         \
+    (ctx)->launches++;                                                                         \
+    cudaError_t e__ = cudaPeekAtLastError();                                                   \
+    if (e__ != cudaSuccess) {                                                                  \
+      cudaGetLastError();                                                                      \
+      tnb::set_error("kernel launch failed %d (%s) at %s:%d", (int)e__,                        \
+                     cudaGetErrorString(e__), __FILE__, __LINE__);                             \
+      return TNB_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+struct TmapKey {
+  const void *ptr;
+  int rows, cols, stride, box_rows, box_cols, swizzle32;
+  bool operator<(const TmapKey &o) const { return memcmp(this, &o, sizeof(TmapKey)) < 0; }
+};
+
+}  // namespace tnb
+
+struct TnbContext_ {
+  int device = 0;
+  int sm_count = 148;
+  int math_mode = TNB_MATH_3XTF32;
+  cudaStream_t stream = nullptr;       // compute stream
+  cudaStream_t comm_stream = nullptr;  // NCCL stream
+  cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
+  unsigned long long launches = 0;
+  std::map<tnb::TmapKey, CUtensorMap> tmaps;  // TMA descriptors keyed by (ptr, dims, box)
+  // scratch for deterministic per-row -> stats reductions
+  float *row_scratch = nullptr;
+  int *row_match = nullptr;
+  int row_cap = 0;
+  // column-sum scratch (bias gradient before the fused update)
+  float *vec_scratch = nullptr;
+  int vec_cap = 0;
+  // data-parallel
+  void *nccl_comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+namespace tnb {
+inline dim3 grid2d(int cols, int rows, int bx, int by) {
+  return dim3((cols + bx - 1) / bx, (rows + by - 1) / by);
+}
+int ensure_row_scratch(TnbContext *ctx, int rows);
+int ensure_vec_scratch(TnbContext *ctx, int n);
+int get_tmap(TnbContext *ctx, const float *ptr, int rows, int cols, int stride, int box_rows,
+             int box_cols, int swizzle32, CUtensorMap *out);
+}  // namespace tnb

@@ -1,0 +1,254 @@
+// ctx.cu — context, device selection, memory plumbing and the TMA descriptor cache.
+// Replaces CuDevice (reference: src/CuBaseLib/cudevice.cc:22-121) and the cudaMallocPitch /
+// cudaMemcpy2D / cudaMemset calls inside CuMatrix/CuVector (src/CuBaseLib/cumatrix.tcc:16-190).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace tnb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int ensure_row_scratch(TnbContext *ctx, int rows) {
+  if (rows <= ctx->row_cap) return TNB_OK;
+  int cap = rows < 1024 ? 1024 : rows;
+  if (ctx->row_scratch) cudaFree(ctx->row_scratch);
+  if (ctx->row_match) cudaFree(ctx->row_match);
+  ctx->row_scratch = nullptr; ctx->row_match = nullptr; ctx->row_cap = 0;
+  TNB_CUDA(cudaMalloc(&ctx->row_scratch, sizeof(float) * (size_t)cap));
+  TNB_CUDA(cudaMalloc(&ctx->row_match, sizeof(int) * (size_t)cap));
+  ctx->row_cap = cap;
+  return TNB_OK;
+}
+
+int ensure_vec_scratch(TnbContext *ctx, int n) {
+  if (n <= ctx->vec_cap) return TNB_OK;
+  int cap = n < 4096 ? 4096 : n;
+  if (ctx->vec_scratch) cudaFree(ctx->vec_scratch);
+  ctx->vec_scratch = nullptr; ctx->vec_cap = 0;
+  TNB_CUDA(cudaMalloc(&ctx->vec_scratch, sizeof(float) * (size_t)cap));
+  ctx->vec_cap = cap;
+  return TNB_OK;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: libtnetb200.so does not link
+// libcuda, so it loads (and exports its symbols) on a machine without a driver.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int load_encode() {
+  if (g_encode) return TNB_OK;
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  TNB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || !fn) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return TNB_ERR_CUDA;
+  }
+  g_encode = (EncodeTiledFn)fn;
+  return TNB_OK;
+}
+
+// 2-D fp32 tensor map over a row-major [rows x cols] matrix with pitch `stride` elements;
+// box = box_rows x box_cols (box_cols*4 == 128 B), OOB elements read as zero.  swizzle32 = 0: 128-byte swizzle with
+// 16-byte atoms (K-major UMMA operands); 1: 128-byte swizzle with 32-byte atoms, the only layout tcgen05 accepts for
+// MN-major 32-bit (tf32) operands (UMMA LayoutType SWIZZLE_128B_BASE32B).
+int get_tmap(TnbContext *ctx, const float *ptr, int rows, int cols, int stride, int box_rows, int box_cols,
+             int swizzle32, CUtensorMap *out) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.rows = rows; key.cols = cols; key.stride = stride;
+  key.box_rows = box_rows; key.box_cols = box_cols; key.swizzle32 = swizzle32;
+  auto it = ctx->tmaps.find(key);
+  if (it != ctx->tmaps.end()) { *out = it->second; return TNB_OK; }
+  int rc = load_encode();
+  if (rc != TNB_OK) return rc;
+  TNB_ARG(((uintptr_t)ptr & 15) == 0, "TMA needs a 16-byte aligned base");
+  TNB_ARG((stride % 4) == 0, "TMA needs a row pitch that is a multiple of 16 bytes");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)stride * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d stride=%d box=%dx%d", (int)r, rows, cols,
+              stride, box_rows, box_cols);
+    return TNB_ERR_CUDA;
+  }
+  if (ctx->tmaps.size() > 8192) ctx->tmaps.clear();
+  ctx->tmaps[key] = m;
+  *out = m;
+  return TNB_OK;
+}
+
+}  // namespace tnb
+
+using namespace tnb;
+
+extern "C" {
+
+const char *tnb_version(void) { return "tnet-b200 0.1 (sm_100a)"; }
+const char *tnb_last_error(void) { return g_err; }
+
+int tnb_device_count(int *count) {
+  TNB_ARG(count != nullptr, "null");
+  *count = 0;
+  TNB_CUDA(cudaGetDeviceCount(count));
+  return TNB_OK;
+}
+
+int tnb_ctx_create(TnbContext **out, int device) {
+  TNB_ARG(out != nullptr, "null");
+  *out = nullptr;
+  int n = 0;
+  TNB_CUDA(cudaGetDeviceCount(&n));
+  if (n <= 0) { set_error("no CUDA device: libtnetb200 has no CPU fallback"); return TNB_ERR_CUDA; }
+  if (device < 0) {
+    // reference: cudevice.cc:27-56 — choose the GPU with the largest free/total memory ratio
+    double best = -1.0;
+    for (int d = 0; d < n; d++) {
+      size_t fr = 0, tot = 0;
+      if (cudaSetDevice(d) != cudaSuccess) continue;
+      if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); continue; }
+      double ratio = tot ? (double)fr / (double)tot : 0.0;
+      if (ratio > best) { best = ratio; device = d; }
+    }
+    if (device < 0) device = 0;
+  }
+  TNB_ARG(device < n, "device index out of range");
+  TNB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  TNB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; libtnetb200 is built for sm_100a only", device, prop.major, prop.minor);
+    return TNB_ERR_UNSUPPORTED;
+  }
+  TnbContext *ctx = new TnbContext_();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  TNB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  TNB_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  TNB_CUDA(cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
+  TNB_CUDA(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
+  *out = ctx;
+  return TNB_OK;
+}
+
+int tnb_ctx_destroy(TnbContext *ctx) {
+  if (!ctx) return TNB_OK;
+  cudaSetDevice(ctx->device);
+  tnb_comm_destroy(ctx);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->row_scratch) cudaFree(ctx->row_scratch);
+  if (ctx->row_match) cudaFree(ctx->row_match);
+  if (ctx->vec_scratch) cudaFree(ctx->vec_scratch);
+  cudaEventDestroy(ctx->ev_compute);
+  cudaEventDestroy(ctx->ev_comm);
+  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->comm_stream);
+  delete ctx;
+  return TNB_OK;
+}
+
+int tnb_ctx_device(TnbContext *ctx, int *device) { TNB_ARG(ctx && device, "null"); *device = ctx->device; return TNB_OK; }
+int tnb_ctx_set_math(TnbContext *ctx, int m) {
+  TNB_ARG(ctx, "null");
+  TNB_ARG(m == TNB_MATH_3XTF32 || m == TNB_MATH_TF32 || m == TNB_MATH_FP32_SIMT, "unknown math mode");
+  ctx->math_mode = m;
+  return TNB_OK;
+}
+int tnb_ctx_get_math(TnbContext *ctx, int *m) { TNB_ARG(ctx && m, "null"); *m = ctx->math_mode; return TNB_OK; }
+int tnb_ctx_stream(TnbContext *ctx, void **s) { TNB_ARG(ctx && s, "null"); *s = (void *)ctx->stream; return TNB_OK; }
+int tnb_ctx_sync(TnbContext *ctx) {
+  TNB_ARG(ctx, "null");
+  TNB_CUDA(cudaStreamSynchronize(ctx->stream));
+  TNB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+  return TNB_OK;
+}
+int tnb_ctx_free_memory(TnbContext *ctx, size_t *fr, size_t *tot) {
+  TNB_ARG(ctx && fr && tot, "null");
+  TNB_CUDA(cudaSetDevice(ctx->device));
+  TNB_CUDA(cudaMemGetInfo(fr, tot));
+  return TNB_OK;
+}
+int tnb_ctx_launch_count(TnbContext *ctx, unsigned long long *n) { TNB_ARG(ctx && n, "null"); *n = ctx->launches; return TNB_OK; }
+
+int tnb_malloc_pitch(TnbContext *ctx, void **ptr, int *stride_elems, int rows, int cols) {
+  TNB_ARG(ctx && ptr && stride_elems, "null");
+  TNB_ARG(rows >= 0 && cols >= 0, "negative dims");
+  int stride = ((cols + 31) / 32) * 32;
+  if (stride == 0) stride = 32;
+  size_t bytes = (size_t)(rows > 0 ? rows : 1) * (size_t)stride * 4;
+  TNB_CUDA(cudaSetDevice(ctx->device));
+  TNB_CUDA(cudaMalloc(ptr, bytes));
+  TNB_CUDA(cudaMemsetAsync(*ptr, 0, bytes, ctx->stream));
+  *stride_elems = stride;
+  return TNB_OK;
+}
+int tnb_malloc(TnbContext *ctx, void **ptr, size_t bytes) {
+  TNB_ARG(ctx && ptr, "null");
+  TNB_CUDA(cudaSetDevice(ctx->device));
+  TNB_CUDA(cudaMalloc(ptr, bytes ? bytes : 4));
+  TNB_CUDA(cudaMemsetAsync(*ptr, 0, bytes ? bytes : 4, ctx->stream));
+  return TNB_OK;
+}
+int tnb_free(TnbContext *ctx, void *ptr) {
+  TNB_ARG(ctx, "null");
+  if (!ptr) return TNB_OK;
+  // drop cached TMA descriptors that point into this allocation
+  for (auto it = ctx->tmaps.begin(); it != ctx->tmaps.end();) {
+    if (it->first.ptr == ptr) it = ctx->tmaps.erase(it); else ++it;
+  }
+  TNB_CUDA(cudaStreamSynchronize(ctx->stream));
+  TNB_CUDA(cudaFree(ptr));
+  return TNB_OK;
+}
+int tnb_memset(TnbContext *ctx, void *ptr, int value, size_t bytes) {
+  TNB_ARG(ctx && ptr, "null");
+  TNB_CUDA(cudaMemsetAsync(ptr, value, bytes, ctx->stream));
+  return TNB_OK;
+}
+static cudaMemcpyKind kind_of(int k) {
+  return k == 0 ? cudaMemcpyHostToDevice : (k == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+}
+int tnb_memcpy2d(TnbContext *ctx, void *dst, size_t dp, const void *src, size_t sp, size_t w, size_t h, int kind) {
+  TNB_ARG(ctx && dst && src, "null");
+  TNB_ARG(kind >= 0 && kind <= 2, "kind");
+  if (w == 0 || h == 0) return TNB_OK;
+  TNB_CUDA(cudaMemcpy2DAsync(dst, dp, src, sp, w, h, kind_of(kind), ctx->stream));
+  if (kind == 1) TNB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TNB_OK;
+}
+int tnb_memcpy(TnbContext *ctx, void *dst, const void *src, size_t bytes, int kind) {
+  TNB_ARG(ctx && dst && src, "null");
+  TNB_ARG(kind >= 0 && kind <= 2, "kind");
+  if (bytes == 0) return TNB_OK;
+  TNB_CUDA(cudaMemcpyAsync(dst, src, bytes, kind_of(kind), ctx->stream));
+  if (kind == 1) TNB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TNB_OK;
+}
+int tnb_host_alloc(void **ptr, size_t bytes) {
+  TNB_ARG(ptr, "null");
+  TNB_CUDA(cudaMallocHost(ptr, bytes ? bytes : 4));
+  return TNB_OK;
+}
+int tnb_host_free(void *ptr) {
+  if (ptr) TNB_CUDA(cudaFreeHost(ptr));
+  return TNB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,410 @@
+// elementwise.cu — HBM-bound kernels of the hot path: the 1:1 replacements of the reference's
+// cukernels.cu elementwise launchers, the column-sum reduction, the cache/splice gathers, the
+// Hybrid-Taus RNG kernels and the fused SGD update.
+//
+// Design: one thread handles 4 consecutive columns of one row with 16-byte accesses whenever the
+// matrix pitch allows it (tnb_malloc_pitch guarantees it), rows are walked by a grid-stride loop and the
+// grid is sized in multiples of the SM count.  Arithmetic keeps the reference's float/double
+// promotions where they are observable (diff-sigmoid's double product, the double column sums).
+#include <float.h>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace tnb {
+
+// ---------------------------------------------------------------------------------------- generic map kernel
+// F: __device__ float op(float dst_old, int row, int col, size_t idx)   — idx = col + row*stride
+template <typename F>
+__global__ void __launch_bounds__(256) map2d_kernel(float *__restrict__ dst, int rows, int cols, int stride, F f) {
+  const int vcols = (cols + 3) >> 2;
+  const long total = (long)rows * vcols;
+  const bool vec = ((stride & 3) == 0) && (((uintptr_t)dst & 15) == 0);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / vcols);
+    const int c = (int)(i % vcols) << 2;
+    const size_t base = (size_t)r * stride + c;
+    if (vec && c + 3 < cols) {
+      float4 v = *(float4 *)(dst + base);
+      v.x = f(v.x, r, c, base); v.y = f(v.y, r, c + 1, base + 1);
+      v.z = f(v.z, r, c + 2, base + 2); v.w = f(v.w, r, c + 3, base + 3);
+      *(float4 *)(dst + base) = v;
+    } else {
+      for (int t = 0; t < 4 && c + t < cols; t++) dst[base + t] = f(dst[base + t], r, c + t, base + t);
+    }
+  }
+}
+
+template <typename F>
+static int launch_map(TnbContext *ctx, float *dst, TnbMatrixDim d, F f) {
+  TNB_ARG(ctx && dst, "null");
+  TNB_ARG(d.rows >= 0 && d.cols >= 0 && d.stride >= d.cols, "dims");
+  if (d.rows == 0 || d.cols == 0) return TNB_OK;
+  long total = (long)d.rows * ((d.cols + 3) / 4);
+  long blocks = (total + 255) / 256;
+  long cap = (long)ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  map2d_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(dst, d.rows, d.cols, d.stride, f);
+  TNB_LAUNCHED(ctx);
+  return TNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------- column sums
+// vec[c] = alpha * sum_r mat[r,c] + beta*vec[c].  Reference: _add_col_sum (double, serial, cukernels.cu:149-164)
+// and _add_col_sum_reduce (float tree, :169-187).  Here: 32 columns per CTA, 8 row-slices per column with double
+// partials, fixed-order combine -> deterministic, and at least as accurate as either reference variant.
+__global__ void __launch_bounds__(256) colsum_kernel(float alpha, const float *__restrict__ mat, float beta, float *vec,
+                                                     int rows, int cols, int stride) {
+  __shared__ double part[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  double s = 0.0;
+  if (c < cols)
+    for (int r = ry; r < rows; r += 8) s += (double)mat[(size_t)r * stride + c];
+  part[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) t += part[k][cx];
+    float b = (beta == 0.0f) ? 0.0f : beta * vec[c];
+    vec[c] = (float)((double)alpha * t + (double)b);
+  }
+}
+
+int launch_colsum(TnbContext *ctx, float alpha, const float *mat, float beta, float *vec, int rows, int cols, int stride) {
+  if (cols == 0) return TNB_OK;
+  colsum_kernel<<<(cols + 31) / 32, 256, 0, ctx->stream>>>(alpha, mat, beta, vec, rows, cols, stride);
+  TNB_LAUNCHED(ctx);
+  return TNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------- gathers
+// _randomize (cukernels.cu:384-393): y[r,:] = x[perm[r],:]   — one warp per row, 16-byte copies
+__global__ void __launch_bounds__(256) gather_rows_kernel(float *__restrict__ y, const float *__restrict__ x,
+                                                          const int *__restrict__ perm, int nrows, int cols, int sy, int sx) {
+  const int wpb = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool vec = ((sy & 3) == 0) && ((sx & 3) == 0) && (((uintptr_t)y & 15) == 0) && (((uintptr_t)x & 15) == 0);
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < nrows; r += gridDim.x * wpb) {
+    const float *src = x + (size_t)perm[r] * sx;
+    float *dst = y + (size_t)r * sy;
+    if (vec) {
+      const int nv = cols >> 2;
+      for (int i = lane; i < nv; i += 32) ((float4 *)dst)[i] = ((const float4 *)src)[i];
+      for (int i = (nv << 2) + lane; i < cols; i += 32) dst[i] = src[i];
+    } else {
+      for (int i = lane; i < cols; i += 32) dst[i] = src[i];
+    }
+  }
+}
+
+// _expand (cukernels.cu:349-361): y[r, k*D + c] = x[clamp(r + off[k]), c] — one CTA per output row block; the
+// D-wide source rows a block touches stay in L1 (each is reused by up to K output rows)
+__global__ void __launch_bounds__(256) expand_kernel(float *__restrict__ y, const float *__restrict__ x,
+                                                     const int *__restrict__ off, int rows, int cols_out, int sy, int rows_in,
+                                                     int cols_in, int sx) {
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    for (int i = threadIdx.x; i < cols_out; i += blockDim.x) {
+      int k = i / cols_in, c = i - k * cols_in;
+      int sr = r + off[k];
+      sr = sr < 0 ? 0 : (sr >= rows_in ? rows_in - 1 : sr);
+      y[(size_t)r * sy + i] = x[(size_t)sr * sx + c];
+    }
+  }
+}
+
+// _rearrange (cukernels.cu:366-379): column gather, +inf for a bad index
+__global__ void __launch_bounds__(256) rearrange_kernel(float *__restrict__ y, const float *__restrict__ x,
+                                                        const int *__restrict__ copy_from, int rows, int cols_out, int sy,
+                                                        int cols_in, int sx) {
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    for (int i = threadIdx.x; i < cols_out; i += blockDim.x) {
+      int sc = copy_from[i];
+      y[(size_t)r * sy + i] = (sc >= 0 && sc < cols_in) ? x[(size_t)r * sx + sc] : __int_as_float(0x7f800000);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) onehot_kernel(float *__restrict__ T, const int *__restrict__ lab, int rows, int cols,
+                                                     int stride) {
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int l = lab[r];
+    for (int i = threadIdx.x; i < cols; i += blockDim.x) T[(size_t)r * stride + i] = (i == l) ? 1.0f : 0.0f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------- Hybrid-Taus RNG
+// curandkernels.cu:15-46.  Integer streams are bit-exact; the uniform is float(2.3283064365387e-10 * (double)u32).
+__device__ __forceinline__ unsigned taus_step(unsigned &z, int S1, int S2, int S3, unsigned M) {
+  unsigned b = (((z << S1) ^ z) >> S2);
+  return z = (((z & M) << S3) ^ b);
+}
+__device__ __forceinline__ unsigned lcg_step(unsigned &z, unsigned A, unsigned C) { return z = (A * z + C); }
+__device__ __forceinline__ float hybrid_taus(unsigned &z1, unsigned &z2, unsigned &z3, unsigned &z4) {
+  float randval;
+  do {
+    randval = (float)(2.3283064365387e-10 * (double)(taus_step(z1, 13, 19, 12, 4294967294U) ^ taus_step(z2, 2, 25, 4, 4294967288U) ^
+                                                     taus_step(z3, 3, 11, 17, 4294967280U) ^ lcg_step(z4, 1664525, 1013904223U)));
+  } while (!(randval > 0.0f && randval < 1.0f));
+  return randval;
+}
+__device__ __forceinline__ float box_muller(unsigned &z1, unsigned &z2, unsigned &z3, unsigned &z4) {
+  // curandkernels.cu:72-82 (T = float): r = sqrt(-2.0*log(u0)) in double then float; sin in float
+  const float M_2PI_F = 6.283185307179586476925286766558;
+  float u0 = hybrid_taus(z1, z2, z3, z4), u1 = hybrid_taus(z1, z2, z3, z4);
+  float r = (float)sqrt(-2.0 * (double)logf(u0));
+  float theta = M_2PI_F * u1;
+  return r * sinf(theta);
+}
+
+// MODE 0: mat = uniform ; 1: mat = gauss ; 2: states = probs > uniform ; 3: mat += gscale*gauss
+template <int MODE>
+__global__ void __launch_bounds__(256) rand_kernel(float *__restrict__ out, const float *__restrict__ probs, float gscale,
+                                                   unsigned *__restrict__ z1, unsigned *__restrict__ z2,
+                                                   unsigned *__restrict__ z3, unsigned *__restrict__ z4, int rows, int cols,
+                                                   int stride) {
+  const long total = (long)rows * cols;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const size_t k = (size_t)r * stride + c;
+    unsigned a = z1[k], b = z2[k], cc = z3[k], d = z4[k];
+    float v;
+    if (MODE == 0 || MODE == 2) v = hybrid_taus(a, b, cc, d); else v = box_muller(a, b, cc, d);
+    z1[k] = a; z2[k] = b; z3[k] = cc; z4[k] = d;
+    if (MODE == 0 || MODE == 1) out[k] = v;
+    else if (MODE == 2) out[k] = (probs[k] > v) ? 1.0f : 0.0f;
+    else out[k] = gscale * v + out[k];
+  }
+}
+
+template <int MODE>
+static int launch_rand(TnbContext *ctx, float *out, const float *probs, float gscale, unsigned *z1, unsigned *z2, unsigned *z3,
+                       unsigned *z4, TnbMatrixDim d) {
+  TNB_ARG(ctx && out && z1 && z2 && z3 && z4, "null");
+  TNB_ARG(d.rows >= 0 && d.cols >= 0 && d.stride >= d.cols, "dims");
+  if (d.rows == 0 || d.cols == 0) return TNB_OK;
+  long total = (long)d.rows * d.cols;
+  long blocks = (total + 255) / 256, cap = (long)ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  rand_kernel<MODE><<<(int)blocks, 256, 0, ctx->stream>>>(out, probs, gscale, z1, z2, z3, z4, d.rows, d.cols, d.stride);
+  TNB_LAUNCHED(ctx);
+  return TNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------- fused SGD update
+// cuBiasedLinearity.cc:55-63 given the summed gradient G:  corr = G + mmt*corr ; W += scale*corr ; W += l2*W
+__global__ void __launch_bounds__(256) sgd_update_kernel(const float *__restrict__ G, float *__restrict__ W,
+                                                         float *__restrict__ corr, int rows, int cols, int stride, float mmt,
+                                                         float scale, float l2) {
+  const int vcols = (cols + 3) >> 2;
+  const long total = (long)rows * vcols;
+  const bool vec = ((stride & 3) == 0) && (((uintptr_t)G & 15) == 0) && (((uintptr_t)W & 15) == 0) && (((uintptr_t)corr & 15) == 0);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / vcols);
+    const int c = (int)(i % vcols) << 2;
+    const size_t base = (size_t)r * stride + c;
+    if (vec && c + 3 < cols) {
+      float4 g = *(const float4 *)(G + base), k = *(float4 *)(corr + base), w = *(float4 *)(W + base);
+      k.x = g.x + mmt * k.x; k.y = g.y + mmt * k.y; k.z = g.z + mmt * k.z; k.w = g.w + mmt * k.w;
+      w.x = scale * k.x + w.x; w.y = scale * k.y + w.y; w.z = scale * k.z + w.z; w.w = scale * k.w + w.w;
+      if (l2 != 0.0f) { w.x = l2 * w.x + w.x; w.y = l2 * w.y + w.y; w.z = l2 * w.z + w.z; w.w = l2 * w.w + w.w; }
+      *(float4 *)(corr + base) = k;
+      *(float4 *)(W + base) = w;
+    } else {
+      for (int t = 0; t < 4 && c + t < cols; t++) {
+        float k = G[base + t] + mmt * corr[base + t];
+        float w = scale * k + W[base + t];
+        if (l2 != 0.0f) w = l2 * w + w;
+        corr[base + t] = k; W[base + t] = w;
+      }
+    }
+  }
+}
+
+// the reference evaluates the update scalars in float (cuBiasedLinearity.cc:44-63)
+static void update_scalars(float lr, float mmt, float wc, int gdf, int rows, float *scale, float *l2) {
+  float N = 1;
+  if (gdf) N = (float)rows;
+  float mmt_gain = (float)(1.0 / (1.0 - mmt));
+  N *= mmt_gain;
+  *scale = -lr / N;
+  *l2 = (float)(-lr * wc * (gdf ? 1.0 : rows));
+}
+
+}  // namespace tnb
+
+using namespace tnb;
+
+#define DIMCHK(d) TNB_ARG((d).rows >= 0 && (d).cols >= 0 && (d).stride >= (d).cols, "dims")
+
+extern "C" {
+
+int tnb_set_const(TnbContext *ctx, float *mat, float value, TnbMatrixDim d) {
+  return launch_map(ctx, mat, d, [=] __device__(float, int, int, size_t) { return value; });
+}
+int tnb_apply_log(TnbContext *ctx, float *mat, TnbMatrixDim d) {
+  return launch_map(ctx, mat, d, [=] __device__(float v, int, int, size_t) { return logf(v); });
+}
+int tnb_scale_cols(TnbContext *ctx, float *mat, const float *scale, TnbMatrixDim d) {
+  TNB_ARG(scale, "null");
+  return launch_map(ctx, mat, d, [=] __device__(float v, int, int c, size_t) { return v * scale[c]; });
+}
+int tnb_scale_rows(TnbContext *ctx, float *mat, const float *scale, TnbMatrixDim d) {
+  TNB_ARG(scale, "null");
+  return launch_map(ctx, mat, d, [=] __device__(float v, int r, int, size_t) { return v * scale[r]; });
+}
+int tnb_add_scaled(TnbContext *ctx, float alpha, const float *A, float beta, float *dst, TnbMatrixDim d) {
+  TNB_ARG(A, "null");
+  // reference reads dst even when beta == 0 (0*NaN = NaN); kept
+  return launch_map(ctx, dst, d, [=] __device__(float v, int, int, size_t i) { return alpha * A[i] + beta * v; });
+}
+int tnb_add_scaled_row(TnbContext *ctx, float alpha, const float *row, float beta, float *dst, TnbMatrixDim d) {
+  TNB_ARG(row, "null");
+  return launch_map(ctx, dst, d, [=] __device__(float v, int, int c, size_t) { return alpha * row[c] + beta * v; });
+}
+int tnb_mul_elem(TnbContext *ctx, float *mat, const float *A, TnbMatrixDim d) {
+  TNB_ARG(A, "null");
+  return launch_map(ctx, mat, d, [=] __device__(float v, int, int, size_t i) { return v * A[i]; });
+}
+int tnb_log_elem(TnbContext *ctx, float *mat, TnbMatrixDim d) {
+  return launch_map(ctx, mat, d, [=] __device__(float v, int, int, size_t) { return logf(v < FLT_MIN ? FLT_MIN : v); });
+}
+int tnb_sigmoid(TnbContext *ctx, float *y, const float *x, TnbMatrixDim d) {
+  TNB_ARG(x, "null");
+  // cukernels.cu:194-206: float exp, double add/divide, rounded to float
+  return launch_map(ctx, y, d, [=] __device__(float, int, int, size_t i) { return (float)(1.0 / (1.0 + (double)expf(-x[i]))); });
+}
+int tnb_diff_sigmoid(TnbContext *ctx, float *eout, const float *e, const float *y, TnbMatrixDim d) {
+  TNB_ARG(e && y, "null");
+  // cukernels.cu:211-217: y*(1.0-y)*e evaluated in double
+  return launch_map(ctx, eout, d, [=] __device__(float, int, int, size_t i) {
+    double yy = (double)y[i];
+    return (float)(yy * (1.0 - yy) * (double)e[i]);
+  });
+}
+
+int tnb_add_col_sum(TnbContext *ctx, float alpha, const float *mat, float beta, float *vec, TnbMatrixDim d) {
+  TNB_ARG(ctx && mat && vec, "null");
+  DIMCHK(d);
+  return launch_colsum(ctx, alpha, mat, beta, vec, d.rows, d.cols, d.stride);
+}
+
+int tnb_expand(TnbContext *ctx, float *y, const float *x, const int *off, TnbMatrixDim d_out, TnbMatrixDim d_in) {
+  TNB_ARG(ctx && y && x && off, "null");
+  DIMCHK(d_out); DIMCHK(d_in);
+  TNB_ARG(d_in.cols > 0 && d_out.cols % d_in.cols == 0, "expand: output cols must be a multiple of input cols");
+  TNB_ARG(d_out.rows == d_in.rows, "expand: rows");
+  if (d_out.rows == 0) return TNB_OK;
+  int blocks = d_out.rows < ctx->sm_count * 8 ? d_out.rows : ctx->sm_count * 8;
+  expand_kernel<<<blocks, 256, 0, ctx->stream>>>(y, x, off, d_out.rows, d_out.cols, d_out.stride, d_in.rows, d_in.cols, d_in.stride);
+  TNB_LAUNCHED(ctx);
+  return TNB_OK;
+}
+int tnb_rearrange(TnbContext *ctx, float *y, const float *x, const int *copy_from, TnbMatrixDim d_out, TnbMatrixDim d_in) {
+  TNB_ARG(ctx && y && x && copy_from, "null");
+  DIMCHK(d_out); DIMCHK(d_in);
+  TNB_ARG(d_out.rows == d_in.rows, "rearrange: rows");
+  if (d_out.rows == 0 || d_out.cols == 0) return TNB_OK;
+  int blocks = d_out.rows < ctx->sm_count * 8 ? d_out.rows : ctx->sm_count * 8;
+  rearrange_kernel<<<blocks, 256, 0, ctx->stream>>>(y, x, copy_from, d_out.rows, d_out.cols, d_out.stride, d_in.cols, d_in.stride);
+  TNB_LAUNCHED(ctx);
+  return TNB_OK;
+}
+int tnb_randomize(TnbContext *ctx, float *y, const float *x, const int *copy_from, TnbMatrixDim d_out, TnbMatrixDim d_in) {
+  TNB_ARG(ctx && y && x && copy_from, "null");
+  DIMCHK(d_out); DIMCHK(d_in);
+  TNB_ARG(d_out.cols == d_in.cols, "randomize: cols");
+  if (d_out.rows == 0 || d_out.cols == 0) return TNB_OK;
+  int blocks = (d_out.rows + 7) / 8;
+  if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+  gather_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(y, x, copy_from, d_out.rows, d_out.cols, d_out.stride, d_in.stride);
+  TNB_LAUNCHED(ctx);
+  return TNB_OK;
+}
+int tnb_onehot(TnbContext *ctx, float *T, const int *labels, TnbMatrixDim d) {
+  TNB_ARG(ctx && T && labels, "null");
+  DIMCHK(d);
+  if (d.rows == 0 || d.cols == 0) return TNB_OK;
+  int blocks = d.rows < ctx->sm_count * 8 ? d.rows : ctx->sm_count * 8;
+  onehot_kernel<<<blocks, 256, 0, ctx->stream>>>(T, labels, d.rows, d.cols, d.stride);
+  TNB_LAUNCHED(ctx);
+  return TNB_OK;
+}
+
+int tnb_rand(TnbContext *ctx, float *mat, unsigned *z1, unsigned *z2, unsigned *z3, unsigned *z4, TnbMatrixDim d) {
+  return launch_rand<0>(ctx, mat, nullptr, 0.0f, z1, z2, z3, z4, d);
+}
+int tnb_gauss_rand(TnbContext *ctx, float *mat, unsigned *z1, unsigned *z2, unsigned *z3, unsigned *z4, TnbMatrixDim d) {
+  return launch_rand<1>(ctx, mat, nullptr, 0.0f, z1, z2, z3, z4, d);
+}
+int tnb_binarize_probs(TnbContext *ctx, float *states, const float *probs, const float *rnd, TnbMatrixDim d) {
+  TNB_ARG(probs && rnd, "null");
+  return launch_map(ctx, states, d, [=] __device__(float, int, int, size_t i) { return (probs[i] > rnd[i]) ? 1.0f : 0.0f; });
+}
+int tnb_rand_binarize(TnbContext *ctx, float *states, const float *probs, unsigned *z1, unsigned *z2, unsigned *z3,
+                      unsigned *z4, TnbMatrixDim d) {
+  TNB_ARG(probs, "null");
+  return launch_rand<2>(ctx, states, probs, 0.0f, z1, z2, z3, z4, d);
+}
+int tnb_add_gauss_noise(TnbContext *ctx, float *tgt, float gscale, unsigned *z1, unsigned *z2, unsigned *z3, unsigned *z4,
+                        TnbMatrixDim d) {
+  return launch_rand<3>(ctx, tgt, nullptr, gscale, z1, z2, z3, z4, d);
+}
+
+int tnb_affine_grad(TnbContext *ctx, const float *X, TnbMatrixDim dX, const float *E, TnbMatrixDim dE, float *G, TnbMatrixDim dG,
+                    float *gb) {
+  TNB_ARG(ctx && X && E && G, "null");
+  TNB_ARG(dX.rows == dE.rows && dG.rows == dX.cols && dG.cols == dE.cols, "dimension mismatch");
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.C = G; ep.ldc = dG.stride; ep.alpha = 1.0f; ep.beta = 0.0f;
+  int rc = launch_gemm(ctx, 'T', 'N', dX.cols, dE.cols, dX.rows, X, dX.stride, E, dE.stride, ep);
+  if (rc != TNB_OK) return rc;
+  if (gb) return launch_colsum(ctx, 1.0f, E, 0.0f, gb, dE.rows, dE.cols, dE.stride);
+  return TNB_OK;
+}
+
+int tnb_affine_update(TnbContext *ctx, const float *X, TnbMatrixDim dX, const float *E, TnbMatrixDim dE, float *W, TnbMatrixDim dW,
+                      float *bias, float *corrW, float *corrb, float lr, float mmt, float wc, int gdf, int n_frames_global) {
+  TNB_ARG(ctx && X && E && W && bias && corrW && corrb, "null");
+  TNB_ARG(dX.rows == dE.rows && dW.rows == dX.cols && dW.cols == dE.cols, "dimension mismatch");
+  const int rows = n_frames_global > 0 ? n_frames_global : dX.rows;
+  float scale, l2;
+  update_scalars(lr, mmt, wc, gdf, rows, &scale, &l2);
+  // corrW = X^T E + mmt*corrW ; W += scale*corrW ; W += l2*W   — all in the dW GEMM epilogue
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.C = corrW; ep.ldc = dW.stride; ep.alpha = 1.0f; ep.beta = mmt;
+  ep.W = W; ep.ldw = dW.stride; ep.w_scale = scale; ep.w_l2 = l2;
+  int rc = launch_gemm(ctx, 'T', 'N', dX.cols, dE.cols, dX.rows, X, dX.stride, E, dE.stride, ep);
+  if (rc != TNB_OK) return rc;
+  // corrb = colsum(E) + mmt*corrb ; b += scale*corrb
+  rc = launch_colsum(ctx, 1.0f, E, mmt, corrb, dE.rows, dE.cols, dE.stride);
+  if (rc != TNB_OK) return rc;
+  TnbMatrixDim dv = {1, dE.cols, dE.cols};
+  return tnb_add_scaled(ctx, scale, corrb, 1.0f, bias, dv);
+}
+
+int tnb_sgd_update(TnbContext *ctx, const float *G, float *W, float *corrW, TnbMatrixDim dW, const float *gb, float *bias,
+                   float *corrb, float lr, float mmt, float wc, int gdf, int n_frames) {
+  TNB_ARG(ctx && G && W && corrW, "null");
+  DIMCHK(dW);
+  float scale, l2;
+  update_scalars(lr, mmt, wc, gdf, n_frames, &scale, &l2);
+  if (dW.rows > 0 && dW.cols > 0) {
+    long total = (long)dW.rows * ((dW.cols + 3) / 4);
+    long blocks = (total + 255) / 256, cap = (long)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    sgd_update_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(G, W, corrW, dW.rows, dW.cols, dW.stride, mmt, scale, l2);
+    TNB_LAUNCHED(ctx);
+  }
+  if (gb) {
+    TNB_ARG(bias && corrb, "null bias");
+    sgd_update_kernel<<<(dW.cols / 4 + 255) / 256 + 1, 256, 0, ctx->stream>>>(gb, bias, corrb, 1, dW.cols, dW.cols, mmt, scale, 0.0f);
+    TNB_LAUNCHED(ctx);
+  }
+  return TNB_OK;
+}
+
+}  // extern "C"

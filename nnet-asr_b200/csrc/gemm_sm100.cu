@@ -1,0 +1,593 @@
+// gemm_sm100.cu — the three CuBiasedLinearity contractions as one hand-written sm_100a kernel family.
+//
+// Replaces cublasSgemm as called from CuMatrix<float>::Gemm (reference: src/CuBaseLib/cumatrix.tcc:335-370):
+//   forward  Y  = X * W            ('N','N')   cuBiasedLinearity.cc:15
+//   dX       Ep = E * W^T          ('N','T')   cuBiasedLinearity.cc:24
+//   dW       cW = X^T * E + m*cW   ('T','N')   cuBiasedLinearity.cc:55
+// and fuses what the reference runs as separate kernels into the epilogue: bias row + sigmoid
+// (cukernels.cu:100-119,194-206), diff-sigmoid (:211-217), momentum / learning-rate / L2 update (:89-95).
+//
+// Design (B200):
+//   * operands stay fp32 in HBM, row-major with a 128-byte pitch; TMA (cp.async.bulk.tensor.2d, 128B swizzle)
+//     stages 128 x 32 (A) and BN x 32 (B) fp32 tiles into shared memory.  Row-major operands that are
+//     contracted over their ROW index (W in forward, X and E in dW) are loaded as MN-major tiles
+//     (32-float column chunks) so no transposed copy ever exists in HBM.
+//   * tcgen05.mma.kind::tf32, M=128, N=BN, K=8 per instruction, accumulator in TMEM (BN columns).
+//   * 3xTF32 (default): converter warps split every staged tile into hi = rna_tf32(x) (in place) and
+//     lo = rna_tf32(x - hi) (second buffer); per K-step the MMA warp issues lo*hi, hi*lo, hi*hi.
+//   * warp roles: warp0 = TMA producer, warp1 = TMEM alloc + MMA issue, warps2-5 = converters, then epilogue
+//     (tcgen05.ld 32x32b -> registers -> fused epilogue -> global).
+//   * every mbarrier spin is bounded: a protocol bug traps instead of hanging the GPU.
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace tnb {
+
+constexpr int BM = 128;
+constexpr int BK = 32;  // fp32 elements per K block = 128 bytes = one swizzle span
+
+
+// ----------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: ~seconds of spinning means the pipeline protocol is broken -> trap (error), never hang
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) { printf("tnb gemm: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout type [61,64): SWIZZLE_128B = 2 (K-major tiles), SWIZZLE_128B_BASE32B = 1 (the only
+// layout tcgen05 takes for MN-major 32-bit operands: 32-byte swizzle atoms, 4-row groups)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+// fp32 -> (hi, lo) tf32 pair.  hi = round-to-nearest tf32, lo = rna_tf32(x - hi) (x - hi is exact in fp32).
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  float r = x - hi;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
+  lo = ((h & 0x7F800000u) == 0x7F800000u) ? 0.0f : __uint_as_float(l);  // inf/nan: keep them in hi only
+}
+
+__device__ __forceinline__ float sigmoidf_ref(float x) {
+  // reference: 1.0/(1.0+exp(-x)) with a float exp and a double divide (cukernels.cu:194-206); the float
+  // evaluation below differs by <= 1 ulp
+  return 1.0f / (1.0f + expf(-x));
+}
+
+template <int BN_, int NTERMS_>
+struct GemmCfg {
+  static constexpr int BN = BN_;
+  static constexpr int A_BYTES = BM * BK * 4;
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (NTERMS_ == 3 ? 2 : 1);
+  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+};
+
+__device__ __forceinline__ float epi_one(const EpiParams &ep, float acc, float cold, float bias, float y) {
+  float o = ep.alpha * acc;
+  if (ep.beta != 0.0f) o += ep.beta * cold;
+  o += bias;
+  if (ep.act == TNB_ACT_SIGMOID) o = sigmoidf_ref(o);
+  if (ep.mulY) o = (y * (1.0f - y)) * o;
+  return o;
+}
+
+// ----------------------------------------------------------------------------------------------- kernel
+// A_MN / B_MN: 0 = K-major tile (operand rows are the M/N index, contraction index contiguous),
+//              1 = MN-major tile (operand rows are the contraction index, M/N index contiguous).
+template <int BN, int A_MN, int B_MN, int NTERMS>
+__global__ void __launch_bounds__(192, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+                    int K, EpiParams ep) {
+  using Cfg = GemmCfg<BN, NTERMS>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = (uint64_t *)(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t *full_bar = bars;
+  uint64_t *conv_bar = bars + STAGES;
+  uint64_t *empty_bar = bars + 2 * STAGES;
+  uint64_t *tmem_full_bar = bars + 3 * STAGES;
+  uint32_t *tmem_ptr_smem = (uint32_t *)(bars + 3 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&conv_bar[s], 4);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto stage_a = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
+  auto stage_b = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+  auto stage_alo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES + Cfg::B_BYTES; };
+  auto stage_blo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES + Cfg::B_BYTES; };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
+        const int k0 = kb * BK;
+        if (A_MN == 0) {
+          tma_load_2d(stage_a(s), &tmA, &full_bar[s], k0, m0);  // box 32(k) x 128(m)
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 32; j++)  // box 32(m) x 32(k), one 4 KB chunk per 32 m
+            tma_load_2d(stage_a(s) + j * (BK * 128), &tmA, &full_bar[s], m0 + 32 * j, k0);
+        }
+        if (B_MN == 0) {
+          tma_load_2d(stage_b(s), &tmB, &full_bar[s], k0, n0);  // box 32(k) x BN(n)
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 32; j++)
+            tma_load_2d(stage_b(s) + j * (BK * 128), &tmB, &full_bar[s], n0 + 32 * j, k0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, a_major [15], b_major [16],
+      // N>>3 [17,23), M>>4 [24,29)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); a K step of 8 floats = +32 B
+      // MN-major: 32-float chunks BK*128 B apart (LBO), 4-k-row swizzle groups 512 B apart (SBO); a K step of 8 rows = +1024 B
+      const uint32_t a_lbo = A_MN ? BK * 128 : 16, b_lbo = B_MN ? BK * 128 : 16;
+      const uint32_t a_sbo = A_MN ? 512 : 1024, b_sbo = B_MN ? 512 : 1024;
+      const uint32_t a_lt = A_MN ? 1 : 2, b_lt = B_MN ? 1 : 2;
+      const uint32_t a_kstep = A_MN ? 1024 : 32, b_kstep = B_MN ? 1024 : 32;
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(NTERMS == 3 ? &conv_bar[s] : &full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(stage_a(s)), b_hi = smem_u32(stage_b(s));
+        const uint32_t a_lo = smem_u32(stage_alo(s)), b_lo = smem_u32(stage_blo(s));
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ks++) {
+          const uint64_t dah = make_desc(a_hi + ks * a_kstep, a_lbo, a_sbo, a_lt);
+          const uint64_t dbh = make_desc(b_hi + ks * b_kstep, b_lbo, b_sbo, b_lt);
+          const uint32_t first = (kb > 0 || ks > 0) ? 1u : 0u;
+          if (NTERMS == 3) {
+            const uint64_t dal = make_desc(a_lo + ks * a_kstep, a_lbo, a_sbo, a_lt);
+            const uint64_t dbl = make_desc(b_lo + ks * b_kstep, b_lbo, b_sbo, b_lt);
+            umma_tf32(tmem_base, dal, dbh, idesc, first);
+            umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+            umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+          } else {
+            umma_tf32(tmem_base, dah, dbh, idesc, first);
+          }
+        }
+        umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ===================== converters (3xTF32) then epilogue =====================
+    const int ct = threadIdx.x - 64;  // 0..127
+    if (NTERMS == 3) {
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        float4 *ah = (float4 *)stage_a(s), *al = (float4 *)stage_alo(s);
+#pragma unroll
+        for (int i = 0; i < Cfg::A_BYTES / 16 / 128; i++) {
+          float4 x = ah[ct + 128 * i], h, l;
+          split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y);
+          split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+          ah[ct + 128 * i] = h; al[ct + 128 * i] = l;
+        }
+        float4 *bh = (float4 *)stage_b(s), *bl = (float4 *)stage_blo(s);
+#pragma unroll
+        for (int i = 0; i < Cfg::B_BYTES / 16 / 128; i++) {
+          float4 x = bh[ct + 128 * i], h, l;
+          split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y);
+          split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+          bh[ct + 128 * i] = h; bl[ct + 128 * i] = l;
+        }
+        fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv_bar[s]);
+      }
+    }
+    // ---- epilogue: TMEM -> registers -> fused ops -> global ----
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < M;
+    const size_t crow = (size_t)row * (size_t)ep.ldc;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; c++) {
+      const int nc0 = n0 + c * 32;
+      if (nc0 >= N) break;
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int n = nc0 + 4 * j;
+          if (n >= N) break;
+          float acc[4] = {__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                          __uint_as_float(v[4 * j + 3])};
+          if (n + 3 < N) {
+            float4 cold = make_float4(0, 0, 0, 0), yv = make_float4(0, 0, 0, 0), bv = make_float4(0, 0, 0, 0);
+            if (ep.beta != 0.0f) cold = *(const float4 *)(ep.C + crow + n);
+            if (ep.bias) bv = *(const float4 *)(ep.bias + n);
+            if (ep.mulY) yv = *(const float4 *)(ep.mulY + (size_t)row * ep.ldy + n);
+            float4 o;
+            o.x = epi_one(ep, acc[0], cold.x, bv.x, yv.x);
+            o.y = epi_one(ep, acc[1], cold.y, bv.y, yv.y);
+            o.z = epi_one(ep, acc[2], cold.z, bv.z, yv.z);
+            o.w = epi_one(ep, acc[3], cold.w, bv.w, yv.w);
+            *(float4 *)(ep.C + crow + n) = o;
+            if (ep.W) {
+              float4 *wp = (float4 *)(ep.W + (size_t)row * ep.ldw + n);
+              float4 w = *wp;
+              w.x = ep.w_scale * o.x + w.x; w.y = ep.w_scale * o.y + w.y;
+              w.z = ep.w_scale * o.z + w.z; w.w = ep.w_scale * o.w + w.w;
+              if (ep.w_l2 != 0.0f) {
+                w.x = ep.w_l2 * w.x + w.x; w.y = ep.w_l2 * w.y + w.y;
+                w.z = ep.w_l2 * w.z + w.z; w.w = ep.w_l2 * w.w + w.w;
+              }
+              *wp = w;
+            }
+          } else {
+            for (int t = 0; t < 4 && n + t < N; t++) {
+              float cold = (ep.beta != 0.0f) ? ep.C[crow + n + t] : 0.0f;
+              float bv = ep.bias ? ep.bias[n + t] : 0.0f;
+              float yv = ep.mulY ? ep.mulY[(size_t)row * ep.ldy + n + t] : 0.0f;
+              float o = epi_one(ep, acc[t], cold, bv, yv);
+              ep.C[crow + n + t] = o;
+              if (ep.W) {
+                float *wp = ep.W + (size_t)row * ep.ldw + n + t;
+                float w = ep.w_scale * o + *wp;
+                if (ep.w_l2 != 0.0f) w = ep.w_l2 * w + w;
+                *wp = w;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- SIMT cross-check
+// plain fp32 FMA GEMM with the same epilogue (TNB_MATH_FP32_SIMT, and shapes the TMA path cannot take)
+template <int TA, int TB>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const float *__restrict__ A, int lda, const float *__restrict__ B,
+                                                        int ldb, int M, int N, int K, EpiParams ep) {
+  __shared__ float As[16][64 + 1];
+  __shared__ float Bs[16][64 + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      int kk, mm;
+      if (TA) { kk = i / 64; mm = i % 64; } else { mm = i / 16; kk = i % 16; }
+      int gm = m0 + mm, gk = k0 + kk;
+      float v = 0.0f;
+      if (gm < M && gk < K) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+      As[kk][mm] = v;
+      int nn;
+      if (TB) { nn = i / 16; kk = i % 16; } else { kk = i / 64; nn = i % 64; }
+      int gn = n0 + nn; gk = k0 + kk;
+      v = 0.0f;
+      if (gn < N && gk < K) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; kk++) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < 4; i++) {
+    int row = m0 + ty * 4 + i;
+    if (row >= M) continue;
+    for (int j = 0; j < 4; j++) {
+      int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      size_t ci = (size_t)row * ep.ldc + n;
+      float cold = (ep.beta != 0.0f) ? ep.C[ci] : 0.0f;
+      float bv = ep.bias ? ep.bias[n] : 0.0f;
+      float yv = ep.mulY ? ep.mulY[(size_t)row * ep.ldy + n] : 0.0f;
+      float o = epi_one(ep, acc[i][j], cold, bv, yv);
+      ep.C[ci] = o;
+      if (ep.W) {
+        float *wp = ep.W + (size_t)row * ep.ldw + n;
+        float w = ep.w_scale * o + *wp;
+        if (ep.w_l2 != 0.0f) w = ep.w_l2 * w + w;
+        *wp = w;
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- host launch
+template <int BN, int A_MN, int B_MN, int NTERMS>
+static int launch_tc(TnbContext *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, int M, int N, int K, const EpiParams &ep) {
+  using Cfg = GemmCfg<BN, NTERMS>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, NTERMS>;
+  static bool attr_set[64] = {};
+  if (!attr_set[ctx->device & 63]) {
+    TNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set[ctx->device & 63] = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  kern<<<grid, 192, Cfg::SMEM_BYTES, ctx->stream>>>(tmA, tmB, M, N, K, ep);
+  TNB_LAUNCHED(ctx);
+  return TNB_OK;
+}
+
+template <int BN, int NTERMS>
+static int launch_tc_major(TnbContext *ctx, int a_mn, int b_mn, const CUtensorMap &tmA, const CUtensorMap &tmB, int M, int N,
+                           int K, const EpiParams &ep) {
+  if (!a_mn && !b_mn) return launch_tc<BN, 0, 0, NTERMS>(ctx, tmA, tmB, M, N, K, ep);
+  if (!a_mn && b_mn) return launch_tc<BN, 0, 1, NTERMS>(ctx, tmA, tmB, M, N, K, ep);
+  if (a_mn && !b_mn) return launch_tc<BN, 1, 0, NTERMS>(ctx, tmA, tmB, M, N, K, ep);
+  return launch_tc<BN, 1, 1, NTERMS>(ctx, tmA, tmB, M, N, K, ep);
+}
+
+// C[M x N] (+epilogue) = op(A) * op(B); A, B row-major as CuMatrix::Gemm receives them.
+int launch_gemm(TnbContext *ctx, char transa, char transb, int M, int N, int K, const float *A, int lda, const float *B,
+                int ldb, const EpiParams &ep) {
+  TNB_ARG(ctx != nullptr, "null ctx");
+  TNB_ARG(M > 0 && N > 0 && K > 0, "empty GEMM");
+  TNB_ARG(A && B && ep.C, "null operand");
+  const int ta = (transa == 'T' || transa == 't'), tb = (transb == 'T' || transb == 't');
+  TNB_ARG(ta || transa == 'N' || transa == 'n', "transa");
+  TNB_ARG(tb || transb == 'N' || transb == 'n', "transb");
+  const bool vec_ok = ((uintptr_t)ep.C % 16 == 0) && (ep.ldc % 4 == 0) && (!ep.bias || (uintptr_t)ep.bias % 16 == 0) &&
+                      (!ep.mulY || ((uintptr_t)ep.mulY % 16 == 0 && ep.ldy % 4 == 0)) &&
+                      (!ep.W || ((uintptr_t)ep.W % 16 == 0 && ep.ldw % 4 == 0));
+  const bool tma_ok = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && vec_ok;
+  if (ctx->math_mode == TNB_MATH_FP32_SIMT || !tma_ok) {
+    if (ctx->math_mode != TNB_MATH_FP32_SIMT && !tma_ok) {
+      set_error("GEMM operands must be 16-byte aligned with a pitch multiple of 4 floats for the tensor-core path");
+      return TNB_ERR_ARG;
+    }
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    if (!ta && !tb) gemm_simt_kernel<0, 0><<<grid, 256, 0, ctx->stream>>>(A, lda, B, ldb, M, N, K, ep);
+    else if (!ta && tb) gemm_simt_kernel<0, 1><<<grid, 256, 0, ctx->stream>>>(A, lda, B, ldb, M, N, K, ep);
+    else if (ta && !tb) gemm_simt_kernel<1, 0><<<grid, 256, 0, ctx->stream>>>(A, lda, B, ldb, M, N, K, ep);
+    else gemm_simt_kernel<1, 1><<<grid, 256, 0, ctx->stream>>>(A, lda, B, ldb, M, N, K, ep);
+    TNB_LAUNCHED(ctx);
+    return TNB_OK;
+  }
+  // operand majors: op(A)=A  -> A is [M x K], contraction contiguous -> K-major ; op(A)=A^T -> A is [K x M] -> MN-major
+  //                 op(B)=B  -> B is [K x N], N contiguous -> MN-major         ; op(B)=B^T -> B is [N x K] -> K-major
+  const int a_mn = ta ? 1 : 0;
+  const int b_mn = tb ? 0 : 1;
+  // tile width: keep >= ~1 wave of CTAs on 148 SMs, prefer wide tiles (less smem traffic per flop)
+  const long tiles128 = (long)((M + BM - 1) / BM) * ((N + 127) / 128);
+  int bn = 128;
+  if (tiles128 >= 2L * ctx->sm_count && N >= 256) bn = 256;
+  else if (tiles128 < ctx->sm_count / 2 || N <= 64) bn = 64;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a_mn) rc = get_tmap(ctx, A, M, K, lda, BM, BK, 0, &tmA);   // rows = m, cols = k, box 128 x 32
+  else rc = get_tmap(ctx, A, K, M, lda, BK, 32, 1, &tmA);         // rows = k, cols = m, box 32 x 32
+  if (rc != TNB_OK) return rc;
+  if (!b_mn) rc = get_tmap(ctx, B, N, K, ldb, bn, BK, 0, &tmB);   // rows = n, cols = k, box BN x 32
+  else rc = get_tmap(ctx, B, K, N, ldb, BK, 32, 1, &tmB);         // rows = k, cols = n, box 32 x 32
+  if (rc != TNB_OK) return rc;
+  const bool three = ctx->math_mode == TNB_MATH_3XTF32;
+  if (bn == 256) return three ? launch_tc_major<256, 3>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep)
+                              : launch_tc_major<256, 1>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep);
+  if (bn == 128) return three ? launch_tc_major<128, 3>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep)
+                              : launch_tc_major<128, 1>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep);
+  return three ? launch_tc_major<64, 3>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep)
+               : launch_tc_major<64, 1>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep);
+}
+
+// ----------------------------------------------------------------------------------------------- gemv / ger
+// reference: CuMath<float>::OffsetGemv (cumath.cc:283-340), used only by CuRecurrent (batch-1, frame-serial)
+__global__ void gemv_n_kernel(float alpha, const float *__restrict__ A, int lda, int row_off, int nrows, int ncols,
+                              const float *__restrict__ x, float beta, float *y) {
+  // y[r] = alpha * sum_c A[row_off + r, c] * x[c] + beta*y[r]   (one warp per row)
+  int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (r >= nrows) return;
+  const float *a = A + (size_t)(row_off + r) * lda;
+  float s = 0.0f;
+  for (int c = lane; c < ncols; c += 32) s = fmaf(a[c], x[c], s);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) y[r] = alpha * s + (beta == 0.0f ? 0.0f : beta * y[r]);
+}
+__global__ void gemv_t_kernel(float alpha, const float *__restrict__ A, int lda, int col_off, int nrows, int ncols,
+                              const float *__restrict__ x, float beta, float *y) {
+  // y[c] = alpha * sum_r A[r, col_off + c] * x[r] + beta*y[c]   (one thread per column, coalesced over c)
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  float s = 0.0f;
+  for (int r = 0; r < nrows; r++) s = fmaf(A[(size_t)r * lda + col_off + c], x[r], s);
+  y[c] = alpha * s + (beta == 0.0f ? 0.0f : beta * y[c]);
+}
+__global__ void ger_kernel(float alpha, const float *__restrict__ x, int dimX, const float *__restrict__ y, int dimY, float *A,
+                           int lda) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int r = blockIdx.y;
+  if (c < dimY && r < dimX) A[(size_t)r * lda + c] += (alpha * x[r]) * y[c];
+}
+
+}  // namespace tnb
+
+using namespace tnb;
+
+extern "C" {
+
+int tnb_gemm(TnbContext *ctx, char transa, char transb, int m, int n, int k, float alpha, const float *A, int lda,
+             const float *B, int ldb, float beta, float *C, int ldc) {
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.C = C; ep.ldc = ldc; ep.alpha = alpha; ep.beta = beta;
+  return launch_gemm(ctx, transa, transb, m, n, k, A, lda, B, ldb, ep);
+}
+
+int tnb_affine_fwd(TnbContext *ctx, const float *X, TnbMatrixDim dX, const float *W, TnbMatrixDim dW, const float *bias,
+                   float *Y, TnbMatrixDim dY, int act) {
+  TNB_ARG(ctx && X && W && bias && Y, "null");
+  TNB_ARG(dX.cols == dW.rows && dY.cols == dW.cols && dY.rows == dX.rows, "dimension mismatch");
+  TNB_ARG(act == TNB_ACT_NONE || act == TNB_ACT_SIGMOID, "act");
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.C = Y; ep.ldc = dY.stride; ep.alpha = 1.0f; ep.beta = 0.0f; ep.bias = bias; ep.act = act;
+  return launch_gemm(ctx, 'N', 'N', dX.rows, dW.cols, dX.cols, X, dX.stride, W, dW.stride, ep);
+}
+
+int tnb_affine_bwd_dx(TnbContext *ctx, const float *E, TnbMatrixDim dE, const float *W, TnbMatrixDim dW, const float *Yprev,
+                      TnbMatrixDim dYprev, float *Eprev, TnbMatrixDim dEprev) {
+  TNB_ARG(ctx && E && W && Eprev, "null");
+  TNB_ARG(dE.cols == dW.cols && dEprev.cols == dW.rows && dEprev.rows == dE.rows, "dimension mismatch");
+  if (Yprev) TNB_ARG(dYprev.rows == dEprev.rows && dYprev.cols == dEprev.cols, "Yprev dims");
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.C = Eprev; ep.ldc = dEprev.stride; ep.alpha = 1.0f; ep.beta = 0.0f;
+  ep.mulY = Yprev; ep.ldy = dYprev.stride;
+  return launch_gemm(ctx, 'N', 'T', dE.rows, dW.rows, dE.cols, E, dE.stride, W, dW.stride, ep);
+}
+
+int tnb_offset_gemv(TnbContext *ctx, char trans, float alpha, const float *A, TnbMatrixDim dA, const float *x, int dimX,
+                    float beta, float *y, int dimY, int offsetY) {
+  TNB_ARG(ctx && A && x && y, "null");
+  if (trans == 'N' || trans == 'n') {
+    // y[dimY] = A[offsetY : offsetY+dimY, :] * x[dA.cols]
+    TNB_ARG(dimX == dA.cols && dA.rows >= dimY + offsetY, "gemv N dims");
+    int wpb = 8;
+    gemv_n_kernel<<<(dimY + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(alpha, A, dA.stride, offsetY, dimY, dA.cols, x, beta, y);
+  } else if (trans == 'T' || trans == 't') {
+    // y[dimY] = A[:, offsetY : offsetY+dimY]^T * x[dA.rows]
+    TNB_ARG(dimX == dA.rows && dA.cols >= dimY + offsetY, "gemv T dims");
+    gemv_t_kernel<<<(dimY + 127) / 128, 128, 0, ctx->stream>>>(alpha, A, dA.stride, offsetY, dA.rows, dimY, x, beta, y);
+  } else {
+    TNB_ARG(false, "trans");
+  }
+  TNB_LAUNCHED(ctx);
+  return TNB_OK;
+}
+
+int tnb_ger(TnbContext *ctx, float alpha, const float *x, int dimX, const float *y, int dimY, float *A, TnbMatrixDim dA) {
+  TNB_ARG(ctx && x && y && A, "null");
+  TNB_ARG(dimX == dA.rows && dimY == dA.cols, "ger dims");
+  dim3 grid((dimY + 255) / 256, dimX);
+  ger_kernel<<<grid, 256, 0, ctx->stream>>>(alpha, x, dimX, y, dimY, A, dA.stride);
+  TNB_LAUNCHED(ctx);
+  return TNB_OK;
+}
+
+}  // extern "C"

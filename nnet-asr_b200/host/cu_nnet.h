@@ -1,0 +1,890 @@
+// cu_nnet.h — the reference's CuTNetLib call surface (CuComponent / CuUpdatableComponent, the layer classes,
+// CuNetwork, CuCache, CuObjectiveFunction) hosted on libtnetb200.so.
+//
+// Reference files mirrored (paths under src/CuTNetLib): cuComponent.h:27-175, cuBiasedLinearity.{h,cc},
+// cuActivation.{h,cc}, cuCRBEDctFeat.h, cuRbm.{h,cc}, cuRecurrent.{h,cc}, cuNetwork.{h,cc}, cuCache.{h,cc},
+// cuObjectiveFunction.{h,cc}.  Class names, virtuals, ownership (a component owns mOutput/mErrorOutput, its
+// inputs are borrowed pointers) and error behaviour (exceptions) are the reference's.
+//
+// B200-first differences, all inside CuNetwork's traversal and invisible to component-level callers:
+//   * <biasedlinearity> followed by <sigmoid> runs as ONE tcgen05 GEMM whose epilogue adds the bias and applies the
+//     sigmoid, writing the sigmoid component's output directly (the affine pre-activation is never materialised);
+//   * dX of an affine layer whose predecessor is a <sigmoid> multiplies by y(1-y) in the GEMM epilogue;
+//   * the weight gradient GEMM applies momentum / learning rate / L2 in its epilogue (single GPU), or is followed by
+//     an NCCL all-reduce and a fused update kernel (data parallel);
+//   * <softmax>'s identity backward copy and the output copy of Propagate() are pointer re-wiring, not copies;
+//   * Xent / correct / frames accumulate on the device and are read when Report()/GetError() is called.
+// SetFusion(false) (or TNB_FUSE=0) restores the component-by-component traversal for debugging and parity tests.
+#ifndef TNETB200_CU_NNET_H_
+#define TNETB200_CU_NNET_H_
+
+#include <algorithm>
+#include <list>
+
+#include "cu_base.h"
+
+namespace TNet {
+
+// =====================================================================================================
+// CuComponent / CuUpdatableComponent
+// =====================================================================================================
+class CuComponent {
+ public:
+  typedef enum {
+    UPDATABLE_COMPONENT = 0x0100, BIASED_LINEARITY, DISCRETE_LINEARITY, SHARED_LINEARITY, SPARSE_LINEARITY, RBM, RBM_SPARSE, RECURRENT,
+    ACT_FUN = 0x0200, SOFTMAX, SIGMOID,
+    OTHER = 0x0400, EXPAND, COPY, TRANSPOSE, BLOCK_LINEARITY, WINDOW, BIAS, LOG, BLOCK_ARRAY, CLUSTER_LINEARITY
+  } ComponentType;
+
+  CuComponent(size_t nInputs, size_t nOutputs, CuComponent *pPred)
+      : mNInputs(nInputs), mNOutputs(nOutputs), mpInput(NULL), mpErrorInput(NULL) {
+    if (pPred != NULL) {  // double link with the predecessor
+      SetInput(pPred->GetOutput());
+      pPred->SetErrorInput(GetErrorOutput());
+    }
+  }
+  virtual ~CuComponent() {}
+
+  virtual ComponentType GetType() const = 0;
+  virtual const char *GetName() const = 0;
+  virtual bool IsUpdatable() const { return false; }
+
+  size_t GetNInputs() const { return mNInputs; }
+  size_t GetNOutputs() const { return mNOutputs; }
+
+  const CuMatrix<BaseFloat> &GetInput() const { if (NULL == mpInput) Error("mpInput is NULL"); return *mpInput; }
+  const CuMatrix<BaseFloat> &GetOutput() const { return mOutput; }
+  const CuMatrix<BaseFloat> &GetErrorInput() const { if (NULL == mpErrorInput) Error("mpErrorInput is NULL"); return *mpErrorInput; }
+  const CuMatrix<BaseFloat> &GetErrorOutput() const { return mErrorOutput; }
+
+  void SetInput(const CuMatrix<BaseFloat> &rInput) { mpInput = &rInput; }
+  void SetErrorInput(const CuMatrix<BaseFloat> &rErrorInput) { mpErrorInput = &rErrorInput; }
+
+  /// forward pass Input -> Output (cuComponent.h:205-218)
+  void Propagate() {
+    mOutput.Init(GetInput().Rows(), GetNOutputs());
+    if (GetNInputs() != GetInput().Cols())
+      KALDI_ERR << "Non-matching INPUT dim!!! Network dim: " << GetNInputs() << " Data dim: " << GetInput().Cols();
+    PropagateFnc(GetInput(), mOutput);
+  }
+  /// backward pass ErrorInput -> ErrorOutput (cuComponent.h:221-235)
+  void Backpropagate() {
+    mErrorOutput.Init(GetErrorInput().Rows(), GetNInputs());
+    if (GetErrorInput().Cols() != mNOutputs) Error("Backpropagate: non-matching error dim");
+    BackpropagateFnc(GetErrorInput(), mErrorOutput);
+  }
+
+  virtual void ReadFromStream(std::istream &) {}
+  virtual void WriteToStream(std::ostream &) {}
+
+  /// network-internal: lets CuNetwork write a fused result straight into this component's buffers
+  CuMatrix<BaseFloat> &MutableOutput() { return mOutput; }
+  CuMatrix<BaseFloat> &MutableErrorOutput() { return mErrorOutput; }
+
+ protected:
+  virtual void PropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) = 0;
+  virtual void BackpropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) = 0;
+
+  size_t mNInputs, mNOutputs;
+  const CuMatrix<BaseFloat> *mpInput;       ///< NOT owned
+  const CuMatrix<BaseFloat> *mpErrorInput;  ///< NOT owned
+  CuMatrix<BaseFloat> mOutput;              ///< owned
+  CuMatrix<BaseFloat> mErrorOutput;         ///< owned
+};
+
+class CuUpdatableComponent : public CuComponent {
+ public:
+  CuUpdatableComponent(size_t nInputs, size_t nOutputs, CuComponent *pPred)
+      : CuComponent(nInputs, nOutputs, pPred), mLearningRate(0.0), mMomentum(0), mWeightcost(0), mGradDivFrm(true) {}
+  virtual bool IsUpdatable() const { return true; }
+  virtual void Update() = 0;
+  void LearnRate(BaseFloat rate) { mLearningRate = rate; }
+  BaseFloat LearnRate() { return mLearningRate; }
+  void Momentum(BaseFloat mmt) { mMomentum = mmt; }
+  BaseFloat Momentum() { return mMomentum; }
+  void Weightcost(BaseFloat cost) { mWeightcost = cost; }
+  BaseFloat Weightcost() { return mWeightcost; }
+  void GradDivFrm(bool div) { mGradDivFrm = div; }
+  bool GradDivFrm() { return mGradDivFrm; }
+
+ protected:
+  BaseFloat mLearningRate, mMomentum, mWeightcost;
+  bool mGradDivFrm;
+};
+
+// =====================================================================================================
+// Activations (cuActivation.{h,cc})
+// =====================================================================================================
+class CuSigmoid : public CuComponent {
+ public:
+  CuSigmoid(size_t nInputs, size_t nOutputs, CuComponent *pPred) : CuComponent(nInputs, nOutputs, pPred) {}
+  ComponentType GetType() const { return SIGMOID; }
+  const char *GetName() const { return "<sigmoid>"; }
+ protected:
+  void PropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) { CuMath<BaseFloat>::Sigmoid(Y, X); }
+  void BackpropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) { CuMath<BaseFloat>::DiffSigmoid(Y, X, mOutput); }
+};
+
+class CuSoftmax : public CuComponent {
+ public:
+  CuSoftmax(size_t nInputs, size_t nOutputs, CuComponent *pPred) : CuComponent(nInputs, nOutputs, pPred) {}
+  ComponentType GetType() const { return SOFTMAX; }
+  const char *GetName() const { return "<softmax>"; }
+ protected:
+  void PropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) { CuMath<BaseFloat>::Softmax(Y, X); }
+  /// X is already dE/d(softmax input) (cuActivation.cc:35-41)
+  void BackpropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) { Y.CopyFrom(X); }
+};
+
+// =====================================================================================================
+// CuBiasedLinearity (cuBiasedLinearity.{h,cc})
+// =====================================================================================================
+class CuBiasedLinearity : public CuUpdatableComponent {
+ public:
+  CuBiasedLinearity(size_t nInputs, size_t nOutputs, CuComponent *pPred)
+      : CuUpdatableComponent(nInputs, nOutputs, pPred), mLinearity(nInputs, nOutputs), mBias(nOutputs),
+        mLinearityCorrection(nInputs, nOutputs), mBiasCorrection(nOutputs), mDpFrames(0) {}
+  ComponentType GetType() const { return BIASED_LINEARITY; }
+  const char *GetName() const { return "<biasedlinearity>"; }
+
+  void PropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) {
+    TNB_CHECK(tnb_affine_fwd(Cx(), X.pCUData(), X.Dim(), mLinearity.pCUData(), mLinearity.Dim(), mBias.pCUData(), Y.pCUData(), Y.Dim(),
+                             TNB_ACT_NONE));
+  }
+  void BackpropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) {
+    TnbMatrixDim none = {0, 0, 0};
+    TNB_CHECK(tnb_affine_bwd_dx(Cx(), X.pCUData(), X.Dim(), mLinearity.pCUData(), mLinearity.Dim(), NULL, none, Y.pCUData(), Y.Dim()));
+  }
+  /// bias + GEMM + sigmoid in one kernel; Y is the following <sigmoid>'s output buffer
+  void PropagateSigmoid(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) {
+    TNB_CHECK(tnb_affine_fwd(Cx(), X.pCUData(), X.Dim(), mLinearity.pCUData(), mLinearity.Dim(), mBias.pCUData(), Y.pCUData(), Y.Dim(),
+                             TNB_ACT_SIGMOID));
+  }
+  /// dX fused with the diff-sigmoid of the <sigmoid> below: Eprev = (E*W^T) .* Yprev .* (1-Yprev)
+  void BackpropagateDiffSigmoid(const CuMatrix<BaseFloat> &E, const CuMatrix<BaseFloat> &Yprev, CuMatrix<BaseFloat> &Eprev) {
+    TNB_CHECK(tnb_affine_bwd_dx(Cx(), E.pCUData(), E.Dim(), mLinearity.pCUData(), mLinearity.Dim(), Yprev.pCUData(), Yprev.Dim(),
+                                Eprev.pCUData(), Eprev.Dim()));
+  }
+  /// cuBiasedLinearity.cc:44-64, fused into the dW GEMM epilogue
+  void Update() {
+    const CuMatrix<BaseFloat> &X = GetInput(), &E = GetErrorInput();
+    TNB_CHECK(tnb_affine_update(Cx(), X.pCUData(), X.Dim(), E.pCUData(), E.Dim(), mLinearity.pCUData(), mLinearity.Dim(), mBias.pCUData(),
+                                mLinearityCorrection.pCUData(), mBiasCorrection.pCUData(), mLearningRate, mMomentum, mWeightcost,
+                                mGradDivFrm ? 1 : 0, 0));
+  }
+  // ---- data-parallel halves of Update(): local gradient, (all-reduce by the network), apply ----
+  void ComputeGradient() {
+    const CuMatrix<BaseFloat> &X = GetInput(), &E = GetErrorInput();
+    if (mGrad.Rows() != mNInputs + 1) mGrad.Init(mNInputs + 1, mNOutputs);  // [dW ; db] contiguous: one all-reduce per layer
+    TnbMatrixDim dG = mLinearity.Dim();
+    TNB_CHECK(tnb_affine_grad(Cx(), X.pCUData(), X.Dim(), E.pCUData(), E.Dim(), mGrad.pCUData(), dG, mGrad.pCURowData(mNInputs)));
+  }
+  float *GradBuffer() { return mGrad.pCUData(); }
+  size_t GradCount() const { return mGrad.Rows() * mGrad.Stride(); }
+  void ApplyGradient(int n_frames_global) {
+    TNB_CHECK(tnb_sgd_update(Cx(), mGrad.pCUData(), mLinearity.pCUData(), mLinearityCorrection.pCUData(), mLinearity.Dim(),
+                             mGrad.pCURowData(mNInputs), mBias.pCUData(), mBiasCorrection.pCUData(), mLearningRate, mMomentum, mWeightcost,
+                             mGradDivFrm ? 1 : 0, n_frames_global));
+  }
+
+  void ReadFromStream(std::istream &rIn) {
+    BfMatrix transpose;  // stored transposed [out x in] (cuBiasedLinearity.cc:70-78)
+    rIn >> transpose;
+    BfVector bias;
+    rIn >> bias;
+    if (transpose.Cols() * transpose.Rows() == 0) Error("Missing linearity matrix in network file");
+    if (bias.Dim() == 0) Error("Missing bias vector in network file");
+    if (transpose.Rows() != GetNOutputs() || transpose.Cols() != GetNInputs() || bias.Dim() != GetNOutputs()) {
+      std::ostringstream os;
+      os << "Wrong dimensionalities of matrix/vector in network file\n"
+         << "Inputs:" << GetNInputs() << "Outputs:" << GetNOutputs() << "\n"
+         << "linearityCols:" << transpose.Rows() << "linearityRows:" << transpose.Cols() << "biasDims:" << bias.Dim() << "\n";
+      Error(os.str());
+    }
+    mLinearity.CopyFrom(BfMatrix(transpose, TRANS));
+    mBias.CopyFrom(bias);
+  }
+  void WriteToStream(std::ostream &rOut) {
+    BfMatrix tmp;
+    mLinearity.CopyTo(tmp);
+    rOut << BfMatrix(tmp, TRANS);
+    BfVector vec;
+    mBias.CopyTo(vec);
+    rOut << vec;
+    rOut << std::endl;
+  }
+  const CuMatrix<BaseFloat> &Linearity() const { return mLinearity; }
+  const CuVector<BaseFloat> &Bias() const { return mBias; }
+
+ protected:
+  CuMatrix<BaseFloat> mLinearity;  ///< [nInputs x nOutputs]
+  CuVector<BaseFloat> mBias;
+  CuMatrix<BaseFloat> mLinearityCorrection;
+  CuVector<BaseFloat> mBiasCorrection;
+  CuMatrix<BaseFloat> mGrad;  ///< data-parallel only: [dW ; db]
+  int mDpFrames;
+};
+
+// =====================================================================================================
+// Feature-transform components (cuCRBEDctFeat.h)
+// =====================================================================================================
+class CuExpand : public CuComponent {
+ public:
+  CuExpand(size_t nInputs, size_t nOutputs, CuComponent *pPred) : CuComponent(nInputs, nOutputs, pPred) {}
+  ComponentType GetType() const { return EXPAND; }
+  const char *GetName() const { return "<expand>"; }
+  void ReadFromStream(std::istream &rIn) { Vector<int> vec; rIn >> vec; mFrameOffset.CopyFrom(vec); }
+  void WriteToStream(std::ostream &rOut) { Vector<int> vec; mFrameOffset.CopyTo(vec); rOut << vec; }
+ protected:
+  void PropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) {
+    if (X.Cols() * mFrameOffset.Dim() != Y.Cols()) Error("<expand>: output dim must be input dim x number of offsets");
+    CuMath<BaseFloat>::Expand(Y, X, mFrameOffset);
+  }
+  void BackpropagateFnc(const CuMatrix<BaseFloat> &, CuMatrix<BaseFloat> &) { Error("BackpropagateFnc Nonsense"); }
+  CuVector<int> mFrameOffset;
+};
+
+class CuCopy : public CuComponent {
+ public:
+  CuCopy(size_t nInputs, size_t nOutputs, CuComponent *pPred) : CuComponent(nInputs, nOutputs, pPred) {}
+  ComponentType GetType() const { return COPY; }
+  const char *GetName() const { return "<copy>"; }
+  void ReadFromStream(std::istream &rIn) { Vector<int> vec; rIn >> vec; vec.Add(-1); mCopyFromIndices.CopyFrom(vec); }  // 1-based on disk
+  void WriteToStream(std::ostream &rOut) { Vector<int> vec; mCopyFromIndices.CopyTo(vec); vec.Add(1); rOut << vec; }
+ protected:
+  void PropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) { CuMath<BaseFloat>::Rearrange(Y, X, mCopyFromIndices); }
+  void BackpropagateFnc(const CuMatrix<BaseFloat> &, CuMatrix<BaseFloat> &) { Error("BackpropagateFnc Nonsense"); }
+  CuVector<int> mCopyFromIndices;
+};
+
+class CuTranspose : public CuComponent {
+ public:
+  CuTranspose(size_t nInputs, size_t nOutputs, CuComponent *pPred) : CuComponent(nInputs, nOutputs, pPred), mContext(0) {}
+  ComponentType GetType() const { return TRANSPOSE; }
+  const char *GetName() const { return "<transpose>"; }
+  void ReadFromStream(std::istream &rIn) {
+    rIn >> std::ws >> mContext;
+    if (GetNInputs() != GetNOutputs()) Error("Input dim must be same as output dim");
+    if (mContext <= 0 || GetNInputs() % mContext != 0) Error("Number of inputs must be divisible by context length");
+    Vector<int> vec(GetNInputs());
+    int channels = (int)GetNInputs() / mContext;
+    for (int i = 0, ch = 0; ch < channels; ch++)
+      for (int idx = ch; idx < (int)GetNInputs(); idx += channels, i++) vec[i] = idx;
+    mCopyFromIndices.CopyFrom(vec);
+  }
+  void WriteToStream(std::ostream &rOut) { rOut << " " << mContext << "\n"; }
+ protected:
+  void PropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) { CuMath<BaseFloat>::Rearrange(Y, X, mCopyFromIndices); }
+  void BackpropagateFnc(const CuMatrix<BaseFloat> &, CuMatrix<BaseFloat> &) { Error("BackpropagateFnc Nonsense"); }
+  int mContext;
+  CuVector<int> mCopyFromIndices;
+};
+
+class CuBlockLinearity : public CuComponent {
+ public:
+  CuBlockLinearity(size_t nInputs, size_t nOutputs, CuComponent *pPred) : CuComponent(nInputs, nOutputs, pPred) {}
+  ComponentType GetType() const { return BLOCK_LINEARITY; }
+  const char *GetName() const { return "<blocklinearity>"; }
+  void PropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) { CuMath<BaseFloat>::BlockLinearity(Y, X, mBlockLinearity); }
+  void BackpropagateFnc(const CuMatrix<BaseFloat> &, CuMatrix<BaseFloat> &) { Error("BackpropagateFnc Not implemented"); }
+  void ReadFromStream(std::istream &rIn) {
+    Matrix<BaseFloat> mat;
+    rIn >> mat;
+    mBlockLinearity.CopyFrom(Matrix<BaseFloat>(mat, TRANS));
+    if ((GetNOutputs() % mBlockLinearity.Cols() != 0) || (GetNInputs() % mBlockLinearity.Rows() != 0) ||
+        ((GetNOutputs() / mBlockLinearity.Cols()) != (GetNInputs() / mBlockLinearity.Rows())))
+      Error("BlockLinearity matrix dimensions must divide IO dims");
+  }
+  void WriteToStream(std::ostream &rOut) { Matrix<BaseFloat> mat; mBlockLinearity.CopyTo(mat); rOut << Matrix<BaseFloat>(mat, TRANS); }
+ private:
+  CuMatrix<BaseFloat> mBlockLinearity;
+};
+
+class CuBias : public CuComponent {
+ public:
+  CuBias(size_t nInputs, size_t nOutputs, CuComponent *pPred) : CuComponent(nInputs, nOutputs, pPred) {}
+  ComponentType GetType() const { return BIAS; }
+  const char *GetName() const { return "<bias>"; }
+  void PropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) { Y.CopyFrom(X); Y.AddScaledRow(1.0, mBias, 1.0); }
+  void BackpropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) { Y.CopyFrom(X); }
+  void ReadFromStream(std::istream &rIn) { Vector<BaseFloat> vec; rIn >> vec; mBias.CopyFrom(vec); }
+  void WriteToStream(std::ostream &rOut) { Vector<BaseFloat> vec; mBias.CopyTo(vec); rOut << vec; }
+ private:
+  CuVector<BaseFloat> mBias;
+};
+
+class CuWindow : public CuComponent {
+ public:
+  CuWindow(size_t nInputs, size_t nOutputs, CuComponent *pPred) : CuComponent(nInputs, nOutputs, pPred) {}
+  ComponentType GetType() const { return WINDOW; }
+  const char *GetName() const { return "<window>"; }
+  void PropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) { Y.CopyFrom(X); Y.ScaleCols(mWindow); }
+  void BackpropagateFnc(const CuMatrix<BaseFloat> &, CuMatrix<BaseFloat> &) { Error("BackpropagateFnc Not implemented"); }
+  void ReadFromStream(std::istream &rIn) { Vector<BaseFloat> vec; rIn >> vec; mWindow.CopyFrom(vec); }
+  void WriteToStream(std::ostream &rOut) { Vector<BaseFloat> vec; mWindow.CopyTo(vec); rOut << vec; }
+ private:
+  CuVector<BaseFloat> mWindow;
+};
+
+class CuLog : public CuComponent {
+ public:
+  CuLog(size_t nInputs, size_t nOutputs, CuComponent *pPred) : CuComponent(nInputs, nOutputs, pPred) {}
+  ComponentType GetType() const { return LOG; }
+  const char *GetName() const { return "<log>"; }
+  void PropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) { Y.CopyFrom(X); Y.ApplyLog(); }
+  void BackpropagateFnc(const CuMatrix<BaseFloat> &, CuMatrix<BaseFloat> &) { Error("BackpropagateFnc Not implemented"); }
+};
+
+// =====================================================================================================
+// CuRbm (cuRbm.{h,cc}) — CD-1 building blocks used by TRbmCu
+// =====================================================================================================
+class CuRbm : public CuUpdatableComponent {
+ public:
+  typedef enum { BERNOULLI, GAUSSIAN } RbmUnitType;
+  CuRbm(size_t nInputs, size_t nOutputs, CuComponent *pPred)
+      : CuUpdatableComponent(nInputs, nOutputs, pPred), mVisHid(nInputs, nOutputs), mVisBias(nInputs), mHidBias(nOutputs),
+        mVisHidCorrection(nInputs, nOutputs), mVisBiasCorrection(nInputs), mHidBiasCorrection(nOutputs), mVisType(BERNOULLI),
+        mHidType(BERNOULLI) {}
+  ComponentType GetType() const { return RBM; }
+  const char *GetName() const { return "<rbm>"; }
+  RbmUnitType VisType() { return mVisType; }
+  RbmUnitType HidType() { return mHidType; }
+
+  /// h = (sigmoid)(v*W + hidbias) — one fused GEMM (cuRbm.cc:15-23)
+  void PropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) {
+    TNB_CHECK(tnb_affine_fwd(Cx(), X.pCUData(), X.Dim(), mVisHid.pCUData(), mVisHid.Dim(), mHidBias.pCUData(), Y.pCUData(), Y.Dim(),
+                             mHidType == BERNOULLI ? TNB_ACT_SIGMOID : TNB_ACT_NONE));
+  }
+  void BackpropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) {
+    if (mHidType == BERNOULLI) {
+      mBackpropErrBuf.Init(X.Rows(), X.Cols());
+      CuMath<BaseFloat>::DiffSigmoid(mBackpropErrBuf, X, GetOutput());
+    } else {
+      mBackpropErrBuf.CopyFrom(X);
+    }
+    Y.Gemm('N', 'T', 1.0, mBackpropErrBuf, mVisHid, 0.0);
+  }
+  /// backprop-style update (cuRbm.cc:40-100)
+  void Update() {
+    if (mHidType == BERNOULLI) {
+      mBackpropErrBuf.Init(GetErrorInput().Rows(), GetErrorInput().Cols());
+      CuMath<BaseFloat>::DiffSigmoid(mBackpropErrBuf, GetErrorInput(), GetOutput());
+    } else {
+      mBackpropErrBuf.CopyFrom(GetErrorInput());
+    }
+    BaseFloat N = 1;
+    if (mGradDivFrm) N = static_cast<BaseFloat>(GetInput().Rows());
+    BaseFloat mmt_gain = static_cast<BaseFloat>(1.0 / (1.0 - mMomentum));
+    N *= mmt_gain;
+    mVisHidCorrection.Gemm('T', 'N', 1.0, GetInput(), mBackpropErrBuf, mMomentum);
+    mHidBiasCorrection.AddColSum(1.0, mBackpropErrBuf, mMomentum);
+    mVisHid.AddScaled(-mLearningRate / N, mVisHidCorrection, 1.0);
+    mHidBias.AddScaled(-mLearningRate / N, mHidBiasCorrection, 1.0);
+    mVisHid.AddScaled(-mLearningRate * mWeightcost, mVisHid, 1.0);
+  }
+  void Propagate(const CuMatrix<BaseFloat> &visProbs, CuMatrix<BaseFloat> &hidProbs) {
+    if (visProbs.Cols() != GetNInputs()) {
+      std::ostringstream os;
+      os << " Nonmatching input dim, needs:" << GetNInputs() << " got:" << visProbs.Cols() << "\n";
+      Error(os.str());
+    }
+    hidProbs.Init(visProbs.Rows(), GetNOutputs());
+    PropagateFnc(visProbs, hidProbs);
+  }
+  /// v' = (sigmoid)(h*W^T + visbias) (cuRbm.cc:118-128): W is read as the K-major operand, no transposed copy
+  void Reconstruct(const CuMatrix<BaseFloat> &hidState, CuMatrix<BaseFloat> &visProbs) {
+    visProbs.Init(hidState.Rows(), mNInputs);
+    visProbs.AddScaledRow(1.0, mVisBias, 0.0);
+    visProbs.Gemm('N', 'T', 1.0, hidState, mVisHid, 1.0);
+    if (mVisType == BERNOULLI) CuMath<BaseFloat>::Sigmoid(visProbs, visProbs);
+  }
+  /// CD-1 update (cuRbm.cc:131-174)
+  void RbmUpdate(const CuMatrix<BaseFloat> &pos_vis, const CuMatrix<BaseFloat> &pos_hid, const CuMatrix<BaseFloat> &neg_vis,
+                 const CuMatrix<BaseFloat> &neg_hid) {
+    if (!(pos_vis.Rows() == pos_hid.Rows() && pos_vis.Rows() == neg_vis.Rows() && pos_vis.Rows() == neg_hid.Rows() &&
+          pos_vis.Cols() == neg_vis.Cols() && pos_hid.Cols() == neg_hid.Cols() && pos_vis.Cols() == mNInputs && pos_hid.Cols() == mNOutputs))
+      Error("RbmUpdate: non-matching dimensions");
+    BaseFloat N = static_cast<BaseFloat>(pos_vis.Rows());
+    mVisHidCorrection.Gemm('T', 'N', -mLearningRate / N, neg_vis, neg_hid, mMomentum);
+    mVisHidCorrection.Gemm('T', 'N', +mLearningRate / N, pos_vis, pos_hid, 1.0);
+    mVisHidCorrection.AddScaled(-mLearningRate * mWeightcost, mVisHid, 1.0);
+    mVisHid.AddScaled(1.0, mVisHidCorrection, 1.0);
+    mVisBiasCorrection.AddColSum(-mLearningRate / N, neg_vis, mMomentum);
+    mVisBiasCorrection.AddColSum(+mLearningRate / N, pos_vis, 1.0);
+    mVisBias.AddScaled(1.0, mVisBiasCorrection, 1.0);
+    mHidBiasCorrection.AddColSum(-mLearningRate / N, neg_hid, mMomentum);
+    mHidBiasCorrection.AddColSum(+mLearningRate / N, pos_hid, 1.0);
+    mHidBias.AddScaled(1.0, mHidBiasCorrection, 1.0);
+  }
+  void ReadFromStream(std::istream &rIn) {
+    std::string str;
+    rIn >> std::ws >> str;
+    if (str == "bern") mVisType = BERNOULLI; else if (str == "gauss") mVisType = GAUSSIAN; else Error(std::string("Invalid unit type: ") + str);
+    rIn >> std::ws >> str;
+    if (str == "bern") mHidType = BERNOULLI; else if (str == "gauss") mHidType = GAUSSIAN; else Error(std::string("Invalid unit type: ") + str);
+    BfMatrix transpose;
+    rIn >> transpose;
+    if (transpose.Rows() != GetNOutputs() || transpose.Cols() != GetNInputs()) Error("<rbm>: wrong weight matrix dimensions");
+    mVisHid.CopyFrom(BfMatrix(transpose, TRANS));
+    BfVector bias;
+    rIn >> bias; mVisBias.CopyFrom(bias);
+    rIn >> bias; mHidBias.CopyFrom(bias);
+  }
+  void WriteToStream(std::ostream &rOut) {
+    rOut << (mVisType == BERNOULLI ? " bern " : " gauss ");
+    rOut << (mHidType == BERNOULLI ? " bern\n" : " gauss\n");
+    BfMatrix tmp;
+    mVisHid.CopyTo(tmp);
+    rOut << BfMatrix(tmp, TRANS);
+    BfVector vec;
+    mVisBias.CopyTo(vec); rOut << vec; rOut << std::endl;
+    mHidBias.CopyTo(vec); rOut << vec; rOut << std::endl;
+  }
+ protected:
+  CuMatrix<BaseFloat> mVisHid;
+  CuVector<BaseFloat> mVisBias, mHidBias;
+  CuMatrix<BaseFloat> mVisHidCorrection;
+  CuVector<BaseFloat> mVisBiasCorrection, mHidBiasCorrection;
+  CuMatrix<BaseFloat> mBackpropErrBuf;
+  RbmUnitType mVisType, mHidType;
+};
+
+// =====================================================================================================
+// CuRecurrent (cuRecurrent.{h,cc}) — Elman layer, one frame per call, truncated BPTT in Update()
+// =====================================================================================================
+class CuRecurrent : public CuUpdatableComponent {
+ public:
+  CuRecurrent(size_t nInputs, size_t nOutputs, CuComponent *pPred)
+      : CuUpdatableComponent(nInputs, nOutputs, pPred), mLinearity(nInputs + nOutputs, nOutputs), mBias(nOutputs),
+        mLinearityCorrection(nInputs + nOutputs, nOutputs), mBiasCorrection(nOutputs), mBpttOrder(0) {}
+  ComponentType GetType() const { return RECURRENT; }
+  const char *GetName() const { return "<recurrent>"; }
+  void BpttOrder(int ord) {
+    mBpttOrder = ord;
+    mInputHistory.Init(ord + 1, GetNInputs() + GetNOutputs());
+    mHistTmp.Init(ord + 1, GetNInputs() + GetNOutputs());
+    mDiffSigm.Init(1, GetNOutputs()); mErrPrev.Init(1, GetNOutputs());
+  }
+  void ClearHistory() {
+    mInputHistory.SetConst(0.0);
+    if (mOutput.MSize() > 0) mOutput.SetConst(0.0);
+  }
+  void PropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) {
+    if (X.Rows() != 1 || Y.Rows() != 1) Error("<recurrent> processes one frame per call");
+    if (mInputHistory.Rows() == 0) Error("Bptt order was not set");
+    const size_t H = mInputHistory.Rows(), K = mInputHistory.Cols();
+    // shift the history down by one row (persistent scratch: no per-frame allocation)
+    mHistTmp.CopyRows(H - 1, 0, mInputHistory, 0);
+    mInputHistory.CopyRows(H - 1, 0, mHistTmp, 1);
+    // row 0 = [x_t ; y_{t-1}]
+    TNB_CHECK(tnb_memcpy(Cx(), mInputHistory.pCUData(), X.pCUData(), sizeof(BaseFloat) * X.Cols(), 2));
+    TNB_CHECK(tnb_memcpy(Cx(), mInputHistory.pCUData() + X.Cols(), Y.pCUData(), sizeof(BaseFloat) * Y.Cols(), 2));
+    Y.AddScaledRow(1.0, mBias, 0.0);
+    CuMath<BaseFloat>::OffsetGemv('T', 1.0, mLinearity, mInputHistory.pCUData(), K, 1.0, Y.pCUData(), Y.Cols(), 0);
+    CuMath<BaseFloat>::Sigmoid(Y, Y);
+  }
+  void BackpropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) {
+    if (X.Rows() != 1 || Y.Rows() != 1) Error("<recurrent> processes one frame per call");
+    CuMath<BaseFloat>::DiffSigmoid(mDiffSigm, X, GetOutput());
+    // accumulates into Y with beta = 1 as the reference does (cuRecurrent.cc:81)
+    CuMath<BaseFloat>::OffsetGemv('N', 1.0, mLinearity, mDiffSigm.pCUData(), mDiffSigm.Cols(), 1.0, Y.pCUData(), Y.Cols(), 0);
+  }
+  void Update() {
+    const size_t K = mInputHistory.Cols(), H = GetNOutputs();
+    CuMath<BaseFloat>::DiffSigmoid(mDiffSigm, GetErrorInput(), GetOutput());
+    mLinearityCorrection.SetConst(0.0);
+    CuMath<BaseFloat>::BlasGer(-mLearningRate, mInputHistory.pCURowData(0), K, mDiffSigm.pCUData(), H, mLinearityCorrection);
+    mBiasCorrection.AddColSum(-mLearningRate, mDiffSigm, mMomentum);
+    TnbMatrixDim drow = {1, (int)H, (int)mInputHistory.Stride()};
+    for (int i = 1; i <= mBpttOrder; i++) {
+      CuMath<BaseFloat>::OffsetGemv('N', 1.0, mLinearity, mDiffSigm.pCUData(), H, 0.0, mErrPrev.pCUData(), H, GetInput().Cols());
+      // diff-sigmoid with the activations of the history frame (they sit in row i-1, columns nInputs..)
+      TNB_CHECK(tnb_diff_sigmoid(Cx(), mDiffSigm.pCUData(), mErrPrev.pCUData(), mInputHistory.pCURowData(i - 1) + GetInput().Cols(), drow));
+      CuMath<BaseFloat>::BlasGer(-mLearningRate, mInputHistory.pCURowData(i), K, mDiffSigm.pCUData(), H, mLinearityCorrection);
+      mBiasCorrection.AddColSum(-mLearningRate, mDiffSigm, 1.0);
+    }
+    mLinearityCorrection.AddScaled(-mLearningRate * mWeightcost, mLinearity, 1.0);
+    mLinearity.AddScaled(1.0, mLinearityCorrection, 1.0);
+    mBias.AddScaled(1.0, mBiasCorrection, 1.0);
+  }
+  void ReadFromStream(std::istream &rIn) {
+    BfMatrix transpose;
+    rIn >> transpose;
+    if (transpose.Rows() != GetNOutputs() || transpose.Cols() != GetNInputs() + GetNOutputs()) Error("<recurrent>: wrong weight matrix dimensions");
+    mLinearity.CopyFrom(BfMatrix(transpose, TRANS));
+    BfVector bias;
+    rIn >> bias;
+    mBias.CopyFrom(bias);
+  }
+  void WriteToStream(std::ostream &rOut) {
+    BfMatrix tmp;
+    mLinearity.CopyTo(tmp);
+    rOut << BfMatrix(tmp, TRANS);
+    BfVector vec;
+    mBias.CopyTo(vec);
+    rOut << vec;
+    rOut << std::endl;
+  }
+ protected:
+  CuMatrix<BaseFloat> mLinearity;
+  CuVector<BaseFloat> mBias;
+  CuMatrix<BaseFloat> mLinearityCorrection;
+  CuVector<BaseFloat> mBiasCorrection;
+  CuMatrix<BaseFloat> mInputHistory, mHistTmp, mDiffSigm, mErrPrev;
+  int mBpttOrder;
+};
+
+// =====================================================================================================
+// Objective functions (cuObjectiveFunction.{h,cc})
+// =====================================================================================================
+class CuObjectiveFunction {
+ public:
+  typedef enum { OBJ_FUN_I = 0x0300, MEAN_SQUARE_ERROR, CROSS_ENTROPY } ObjFunType;
+  static CuObjectiveFunction *Factory(ObjFunType type);
+  CuObjectiveFunction() : mpStats(NULL) {
+    void *p = NULL;
+    TNB_CHECK(tnb_malloc(Cx(), &p, sizeof(TnbObjStats)));  // zero-filled
+    mpStats = (TnbObjStats *)p;
+  }
+  virtual ~CuObjectiveFunction() { if (mpStats) tnb_free(Cx(), mpStats); }
+  virtual ObjFunType GetTypeId() = 0;
+  virtual const char *GetTypeLabel() = 0;
+  virtual void Evaluate(const CuMatrix<BaseFloat> &rNetOutput, const CuMatrix<BaseFloat> &rDesired, CuMatrix<BaseFloat> &rNetError) = 0;
+  double GetError() { return Read().error; }
+  size_t GetFrames() { return (size_t)Read().frames; }
+  size_t GetCorrect() { return (size_t)Read().correct; }
+  virtual std::string Report() = 0;
+  TnbObjStats *DeviceStats() { return mpStats; }
+  /// data parallel: fold the other ranks' totals into this one (cf. MergeStats, src/TNetLib/ObjFun.cc:214-228)
+  void AddStats(double error, long long frames, long long correct) {
+    TnbObjStats st = Read();
+    st.error += error; st.frames += frames; st.correct += correct;
+    TNB_CHECK(tnb_memcpy(Cx(), mpStats, &st, sizeof(st), 0));
+    CuDevice::Instantiate().Sync();
+  }
+ protected:
+  TnbObjStats Read() {
+    TnbObjStats st;
+    TNB_CHECK(tnb_memcpy(Cx(), &st, mpStats, sizeof(st), 1));
+    return st;
+  }
+  TnbObjStats *mpStats;  ///< device-resident accumulators
+};
+
+class CuMeanSquareError : public CuObjectiveFunction {
+ public:
+  ObjFunType GetTypeId() { return MEAN_SQUARE_ERROR; }
+  const char *GetTypeLabel() { return "<mean_square_error>"; }
+  void Evaluate(const CuMatrix<BaseFloat> &rNetOutput, const CuMatrix<BaseFloat> &rDesired, CuMatrix<BaseFloat> &rNetError) {
+    if (rDesired.Cols() != rNetOutput.Cols() || rDesired.Rows() != rNetOutput.Rows()) Error("Non-matching dimensions of network output with training targets!!!");
+    rNetError.Init(rNetOutput.Rows(), rNetOutput.Cols());
+    TNB_CHECK(tnb_mse_eval(Cx(), rNetOutput.pCUData(), rDesired.pCUData(), rNetError.pCUData(), rNetOutput.Dim(), mpStats));
+  }
+  std::string Report() {
+    TnbObjStats st = Read();
+    std::ostringstream ss;
+    ss << "Mse:" << st.error << " frames:" << (size_t)st.frames << " err/frm:" << st.error / st.frames << "\n";
+    return ss.str();
+  }
+};
+
+class CuCrossEntropy : public CuObjectiveFunction {
+ public:
+  ObjFunType GetTypeId() { return CROSS_ENTROPY; }
+  const char *GetTypeLabel() { return "<cross_entropy>"; }
+  void Evaluate(const CuMatrix<BaseFloat> &rNetOutput, const CuMatrix<BaseFloat> &rDesired, CuMatrix<BaseFloat> &rNetError) {
+    if (rDesired.Cols() != rNetOutput.Cols()) {
+      std::ostringstream os;
+      os << "Non-matching dimensions of network output with training targets!!!" << " Netoutput:" << rNetOutput.Cols()
+         << " Targets:" << rDesired.Cols();
+      Error(os.str());
+    }
+    rNetError.Init(rNetOutput.Rows(), rNetOutput.Cols());
+    TNB_CHECK(tnb_xent_eval(Cx(), rNetOutput.pCUData(), rDesired.pCUData(), rNetError.pCUData(), rNetOutput.Dim(), mpStats));
+  }
+  /// softmax + Evaluate in one kernel, from the pre-softmax activations (used by CuNetwork::PropagateEvaluate)
+  void EvaluateFromActivations(const CuMatrix<BaseFloat> &rAct, const CuMatrix<BaseFloat> &rDesired, CuMatrix<BaseFloat> &rSoftmaxOut,
+                               CuMatrix<BaseFloat> &rNetError) {
+    if (rDesired.Cols() != rAct.Cols()) Error("Non-matching dimensions of network output with training targets!!!");
+    rSoftmaxOut.Init(rAct.Rows(), rAct.Cols());
+    rNetError.Init(rAct.Rows(), rAct.Cols());
+    TNB_CHECK(tnb_softmax_xent(Cx(), rAct.pCUData(), rDesired.pCUData(), rSoftmaxOut.pCUData(), rNetError.pCUData(), rAct.Dim(), mpStats));
+  }
+  /// byte-compatible with cuObjectiveFunction.h:132-144 (tools/train/training_scheduler.sh greps it)
+  std::string Report() {
+    TnbObjStats st = Read();
+    std::ostringstream ss;
+    ss << "Xent:" << st.error << " frames:" << (size_t)st.frames << " err/frm:" << st.error / st.frames << " correct["
+       << 100.0 * st.correct / st.frames << "%]" << "\n";
+    return ss.str();
+  }
+};
+
+inline CuObjectiveFunction *CuObjectiveFunction::Factory(ObjFunType type) {
+  switch (type) {
+    case MEAN_SQUARE_ERROR: return new CuMeanSquareError;
+    case CROSS_ENTROPY: return new CuCrossEntropy;
+    default: Error("Unknown ObjFun type");
+  }
+  return NULL;
+}
+
+// =====================================================================================================
+// CuNetwork (cuNetwork.{h,cc})
+// =====================================================================================================
+class CuNetwork {
+  typedef std::vector<CuComponent *> LayeredType;
+ public:
+  CuNetwork() : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1) {
+    const char *e = getenv("TNB_FUSE");
+    if (e && atoi(e) == 0) mFuse = false;
+  }
+  explicit CuNetwork(std::istream &rIn)
+      : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1) {
+    ReadNetwork(rIn);
+  }
+  ~CuNetwork() {
+    for (LayeredType::iterator it = mNetComponents.begin(); it != mNetComponents.end(); ++it) delete *it;
+    mNetComponents.clear();
+  }
+  void AddLayer(CuComponent *layer) {
+    if (mNetComponents.size() > 0) {
+      if (GetNOutputs() != layer->GetNInputs()) Error("Nonmatching dims");
+      layer->SetInput(mNetComponents.back()->GetOutput());
+      mNetComponents.back()->SetErrorInput(layer->GetErrorOutput());
+    }
+    mNetComponents.push_back(layer);
+  }
+  int Layers() { return (int)mNetComponents.size(); }
+  CuComponent &Layer(int i) { return *mNetComponents[i]; }
+
+  void SetFusion(bool on) { mFuse = on; }
+  /// data parallel over `world` ranks: Update() becomes gradient -> all-reduce -> apply (N uses rows*world)
+  void SetDataParallel(int world) { mWorld = world; }
+
+  /// forward the data to the output (cuNetwork.h:137-165)
+  void Propagate(const CuMatrix<BaseFloat> &in, CuMatrix<BaseFloat> &out) {
+    if (mNetComponents.size() == 0) { out.CopyFrom(in); return; }
+    ForwardTo(in, mNetComponents.size());
+    out.CopyFrom(mNetComponents.back()->GetOutput());
+  }
+  /// Propagate + CuCrossEntropy::Evaluate with the final <softmax> fused into the objective kernel; the network
+  /// output stays in Layer(last).GetOutput() (no copy).  Falls back to Propagate+Evaluate for any other tail.
+  void PropagateEvaluate(const CuMatrix<BaseFloat> &in, const CuMatrix<BaseFloat> &desired, CuObjectiveFunction &obj,
+                         CuMatrix<BaseFloat> &globerr) {
+    size_t n = mNetComponents.size();
+    CuCrossEntropy *xent = dynamic_cast<CuCrossEntropy *>(&obj);
+    if (mFuse && xent && n >= 2 && mNetComponents[n - 1]->GetType() == CuComponent::SOFTMAX) {
+      ForwardTo(in, n - 1);
+      xent->EvaluateFromActivations(mNetComponents[n - 2]->GetOutput(), desired, mNetComponents[n - 1]->MutableOutput(), globerr);
+    } else {
+      if (n == 0) Error("PropagateEvaluate on an empty network");
+      ForwardTo(in, n);
+      obj.Evaluate(mNetComponents.back()->GetOutput(), desired, globerr);
+    }
+  }
+
+  /// backpropagate the error while updating weights (cuNetwork.h:170-194)
+  void Backpropagate(const CuMatrix<BaseFloat> &globerr) {
+    if (mNetComponents.size() == 0) return;
+    const int n = (int)mNetComponents.size();
+    mNetComponents.back()->SetErrorInput(globerr);
+    std::vector<CuBiasedLinearity *> pending;  // data parallel: layers whose gradient is in flight
+    for (int i = n - 1; i >= 0; i--) {
+      CuComponent *c = mNetComponents[i];
+      if (c != mpPropagErrorStopper) {
+        bool done = false;
+        if (mFuse) {
+          // <softmax> backward is the identity: hand globerr to the layer below instead of copying it
+          if (c->GetType() == CuComponent::SOFTMAX && i > 0) {
+            mNetComponents[i - 1]->SetErrorInput(c->GetErrorInput());
+            done = true;
+          }
+          // affine dX fused with the diff-sigmoid of the <sigmoid> right below it
+          if (!done && c->GetType() == CuComponent::BIASED_LINEARITY && i > 0 && mNetComponents[i - 1]->GetType() == CuComponent::SIGMOID &&
+              mNetComponents[i - 1] != mpPropagErrorStopper) {
+            CuComponent *sig = mNetComponents[i - 1];
+            CuMatrix<BaseFloat> &eprev = sig->MutableErrorOutput();
+            eprev.Init(c->GetErrorInput().Rows(), sig->GetNInputs());
+            static_cast<CuBiasedLinearity *>(c)->BackpropagateDiffSigmoid(c->GetErrorInput(), sig->GetOutput(), eprev);
+            done = true;
+          }
+          // ... in which case the <sigmoid> itself has nothing left to do
+          if (!done && c->GetType() == CuComponent::SIGMOID && i + 1 < n && mNetComponents[i + 1]->GetType() == CuComponent::BIASED_LINEARITY &&
+              mNetComponents[i + 1] != mpPropagErrorStopper)
+            done = true;
+        }
+        if (!done) c->Backpropagate();
+      }
+      if (c->IsUpdatable()) {
+        CuUpdatableComponent &rComp = dynamic_cast<CuUpdatableComponent &>(*c);
+        if (rComp.LearnRate() > 0.0f) {
+          if (mWorld > 1 && c->GetType() == CuComponent::BIASED_LINEARITY) {
+            CuBiasedLinearity *lin = static_cast<CuBiasedLinearity *>(c);
+            lin->ComputeGradient();
+            TNB_CHECK(tnb_allreduce_sum(Cx(), lin->GradBuffer(), lin->GradCount()));  // overlaps the layers below
+            pending.push_back(lin);
+          } else {
+            rComp.Update();
+          }
+        }
+      }
+      if (mpPropagErrorStopper == c) break;
+    }
+    if (!pending.empty()) {
+      TNB_CHECK(tnb_comm_wait(Cx()));
+      for (size_t k = 0; k < pending.size(); k++) pending[k]->ApplyGradient((int)pending[k]->GetInput().Rows() * mWorld);
+    }
+    // restore the wiring the fused softmax step changed
+    if (mFuse && n >= 2 && mNetComponents[n - 1]->GetType() == CuComponent::SOFTMAX)
+      mNetComponents[n - 2]->SetErrorInput(mNetComponents[n - 1]->GetErrorOutput());
+  }
+
+  void ReadNetwork(const char *pSrc) {
+    std::ifstream in(pSrc);
+    if (!in.good()) Error(std::string("Error, cannot read model: ") + pSrc);
+    ReadNetwork(in);
+    in.close();
+  }
+  void WriteNetwork(const char *pDst) {
+    std::ofstream out(pDst);
+    if (!out.good()) Error(std::string("Error, cannot write model: ") + pDst);
+    WriteNetwork(out);
+    out.close();
+  }
+  void ReadNetwork(std::istream &rIn) {
+    CuComponent *pComp;
+    while (NULL != (pComp = ComponentFactory(rIn))) mNetComponents.push_back(pComp);
+  }
+  void WriteNetwork(std::ostream &rOut) {
+    for (LayeredType::iterator it = mNetComponents.begin(); it != mNetComponents.end(); ++it) ComponentDumper(rOut, **it);
+  }
+
+  size_t GetNInputs() const { return mNetComponents.empty() ? 0 : mNetComponents.front()->GetNInputs(); }
+  size_t GetNOutputs() const { return mNetComponents.empty() ? 0 : mNetComponents.back()->GetNOutputs(); }
+
+  /// learn rate with per-layer factors "a:b:c" or "a,b,c"; also selects the backprop stopper (cuNetwork.cc:80-135)
+  void SetLearnRate(BaseFloat learnRate, const char *pLearnRateFactors = NULL) {
+    std::list<BaseFloat> lr_factors;
+    if (NULL != pLearnRateFactors) {
+      std::string str(pLearnRateFactors);
+      for (size_t p = 0; p < str.size(); p++) if (str[p] == ':' || str[p] == ',') str[p] = ' ';
+      std::istringstream is(str);
+      BaseFloat f;
+      while (is >> f) lr_factors.push_back(f);
+    }
+    BaseFloat scale = 1.0f;
+    mGlobLearnRate = learnRate;
+    mpLearnRateFactors = pLearnRateFactors;
+    mpPropagErrorStopper = NULL;
+    bool stopper_given = false;
+    for (LayeredType::iterator it = mNetComponents.begin(); it != mNetComponents.end(); ++it) {
+      if ((*it)->IsUpdatable()) {
+        if (NULL != pLearnRateFactors) {
+          if (!(lr_factors.size() > 0)) Error("Too few learninig rate scale factors");
+          scale = lr_factors.front();
+          lr_factors.pop_front();
+        }
+        dynamic_cast<CuUpdatableComponent *>(*it)->LearnRate(learnRate * scale);
+        if (!stopper_given && (learnRate * scale > 0.0)) { mpPropagErrorStopper = *it; stopper_given = true; }
+      }
+    }
+    if (lr_factors.size() > 0) Error("Too much learninig rate scale factors");
+  }
+  BaseFloat GetLearnRate() { return mGlobLearnRate; }
+  void PrintLearnRate() {
+    std::cout << "Learning rate: global " << mGlobLearnRate;
+    std::cout << " components' ";
+    for (size_t i = 0; i < mNetComponents.size(); i++)
+      if (mNetComponents[i]->IsUpdatable()) std::cout << " " << dynamic_cast<CuUpdatableComponent *>(mNetComponents[i])->LearnRate();
+    std::cout << "\n" << std::flush;
+  }
+  void SetMomentum(BaseFloat momentum) { ForUpdatable(&CuUpdatableComponent::Momentum, momentum); }
+  void SetWeightcost(BaseFloat weightcost) { ForUpdatable(&CuUpdatableComponent::Weightcost, weightcost); }
+  void SetL1(BaseFloat) {}  ///< only <sparselinearity> uses it (cuNetwork.cc:186-196); the flag is accepted
+  void SetGradDivFrm(bool div) {
+    for (LayeredType::iterator it = mNetComponents.begin(); it != mNetComponents.end(); ++it)
+      if ((*it)->IsUpdatable()) dynamic_cast<CuUpdatableComponent *>(*it)->GradDivFrm(div);
+  }
+  void SetTempBasisDir(const char *pDir) { mpTempBasisDir = pDir; }
+
+ private:
+  CuNetwork(CuNetwork &);
+  CuNetwork &operator=(CuNetwork &);
+  void ForUpdatable(void (CuUpdatableComponent::*setter)(BaseFloat), BaseFloat v) {
+    for (LayeredType::iterator it = mNetComponents.begin(); it != mNetComponents.end(); ++it)
+      if ((*it)->IsUpdatable()) (dynamic_cast<CuUpdatableComponent *>(*it)->*setter)(v);
+  }
+  /// run layers [0, upto)
+  void ForwardTo(const CuMatrix<BaseFloat> &in, size_t upto) {
+    if (in.Cols() != GetNInputs()) {
+      std::ostringstream os;
+      os << "Nonmatching dims" << " data dim is: " << in.Cols() << " network needs: " << GetNInputs();
+      Error(os.str());
+    }
+    mNetComponents.front()->SetInput(in);
+    for (size_t i = 0; i < upto; i++) {
+      CuComponent *c = mNetComponents[i];
+      if (mFuse && c->GetType() == CuComponent::BIASED_LINEARITY && i + 1 < upto && mNetComponents[i + 1]->GetType() == CuComponent::SIGMOID) {
+        CuComponent *sig = mNetComponents[i + 1];
+        if (c->GetNInputs() != c->GetInput().Cols())
+          KALDI_ERR << "Non-matching INPUT dim!!! Network dim: " << c->GetNInputs() << " Data dim: " << c->GetInput().Cols();
+        CuMatrix<BaseFloat> &y = sig->MutableOutput();
+        y.Init(c->GetInput().Rows(), sig->GetNOutputs());
+        static_cast<CuBiasedLinearity *>(c)->PropagateSigmoid(c->GetInput(), y);
+        i++;  // the <sigmoid> is done
+      } else {
+        c->Propagate();
+      }
+    }
+  }
+  CuComponent *ComponentFactory(std::istream &rIn);
+  void ComponentDumper(std::ostream &rOut, CuComponent &rComp);
+
+  LayeredType mNetComponents;
+  CuComponent *mpPropagErrorStopper;
+  BaseFloat mGlobLearnRate;
+  const char *mpLearnRateFactors;
+  const char *mpTempBasisDir;
+  bool mFuse;
+  int mWorld;
+};
+
+// =====================================================================================================
+// CuCache (cuCache.{h,cc})
+// =====================================================================================================
+class CuCache {
+  typedef enum { EMPTY, INTAKE, FULL, EXHAUST } State;
+ public:
+  CuCache() : mState(EMPTY), mIntakePos(0), mExhaustPos(0), mCachesize(0), mBunchsize(0), mDiscarded(0), mRandomized(false), mTrace(0) {}
+  void Init(size_t cachesize, size_t bunchsize) {
+    if (bunchsize == 0 || (cachesize % bunchsize) != 0) Error("Non divisible cachesize by bunchsize");
+    mCachesize = cachesize; mBunchsize = bunchsize;
+    mState = EMPTY; mIntakePos = 0; mExhaustPos = 0; mRandomized = false;
+  }
+  void AddData(const CuMatrix<BaseFloat> &rFeatures, const CuMatrix<BaseFloat> &rDesired);
+  void Randomize();
+  void GetBunch(CuMatrix<BaseFloat> &rFeatures, CuMatrix<BaseFloat> &rDesired);
+  bool Full() { return (mState == FULL); }
+  bool Empty() { return (mState == EMPTY || mIntakePos < mBunchsize); }
+  int Discarded() { return mDiscarded; }
+  void Trace(int trace) { mTrace = trace; }
+  /// the permutation of the last Randomize() (host copy; for parity tests)
+  const Vector<int> &LastPermutation() const { return mLastPerm; }
+  size_t IntakePos() const { return mIntakePos; }
+
+ private:
+  static long int GenerateRandom(int max) { return lrand48() % max; }
+  State mState;
+  size_t mIntakePos, mExhaustPos, mCachesize, mBunchsize;
+  int mDiscarded;
+  CuMatrix<BaseFloat> mFeatures, mFeaturesRandom, mFeaturesLeftover;
+  CuMatrix<BaseFloat> mDesired, mDesiredRandom, mDesiredLeftover;
+  CuVector<int> mCuRandMask;
+  Vector<int> mLastPerm;
+  bool mRandomized;
+  int mTrace;
+};
+
+}  // namespace TNet
+#endif

@@ -1,0 +1,186 @@
+// tnet_base.h — host-side containers, errors, timer and the text formats of TNet's network files.
+//
+// Mirrors the interface of the reference's KaldiLib pieces the GPU trainers use (reference paths under src/):
+//   Matrix<T>/Vector<T> text I/O        KaldiLib/Matrix.tcc:522-600, Vector.tcc:527-571  ("m rows cols" / "v dim")
+//   Error()/Warning()/KALDI_ERR          KaldiLib/Error.h:54-112
+//   Timer                                KaldiLib/Timer.h:54-75
+// Only the formats and the call surface are kept; the containers are plain row-major std::vector storage
+// (no BLAS on the host: every contraction of the hot path runs on the GPU).
+#ifndef TNETB200_BASE_H_
+#define TNETB200_BASE_H_
+
+#include <sys/time.h>
+
+#include <cassert>
+#include <cctype>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace TNet {
+
+typedef float BaseFloat;
+
+class MyException : public std::runtime_error {
+ public:
+  explicit MyException(const std::string &what) : std::runtime_error(what) {}
+};
+
+inline void Error(const std::string &msg) { throw MyException("ERROR: " + msg); }
+inline void Warning(const std::string &msg) { std::cerr << "WARNING: " << msg << std::endl; }
+inline void TraceLog(const std::string &msg) { std::cout << "INFO: " << msg << std::endl; }
+
+// KALDI_ERR << "text" << value;   throws at the end of the full expression
+class ErrStream {
+ public:
+  ErrStream(const char *file, int line) { os_ << file << ":" << line << " "; }
+  ~ErrStream() noexcept(false) { throw MyException("ERROR: " + os_.str()); }
+  template <typename T>
+  ErrStream &operator<<(const T &v) { os_ << v; return *this; }
+ private:
+  std::ostringstream os_;
+};
+#define KALDI_ERR ::TNet::ErrStream(__FILE__, __LINE__)
+
+class Timer {
+ public:
+  void Start() { gettimeofday(&t0_, 0); }
+  void End() { gettimeofday(&t1_, 0); }
+  double Val() const { return (t1_.tv_sec - t0_.tv_sec) + 1e-6 * (t1_.tv_usec - t0_.tv_usec); }
+ private:
+  struct timeval t0_, t1_;
+};
+
+inline bool IsBigEndian() {
+  const int a = 1;
+  return *reinterpret_cast<const char *>(&a) != 1;
+}
+
+enum MatrixTransposeType { NO_TRANS, TRANS };
+
+template <typename T>
+class Vector {
+ public:
+  Vector() {}
+  explicit Vector(size_t dim) : d_(dim, T()) {}
+  size_t Dim() const { return d_.size(); }
+  void Init(size_t dim) { d_.assign(dim, T()); }
+  T *pData() { return d_.data(); }
+  const T *pData() const { return d_.data(); }
+  T &operator[](size_t i) { return d_[i]; }
+  const T &operator[](size_t i) const { return d_[i]; }
+  void Add(T v) { for (auto &x : d_) x += v; }
+  // double accumulator, result cast to T (KaldiLib/Vector.tcc:266-278)
+  T Sum() const { double s = 0.0; for (const auto &x : d_) s += x; return (T)s; }
+ private:
+  std::vector<T> d_;
+};
+
+template <typename T>
+class Matrix {
+ public:
+  Matrix() : r_(0), c_(0) {}
+  Matrix(size_t rows, size_t cols) : r_(0), c_(0) { Init(rows, cols); }
+  Matrix(const Matrix<T> &src, MatrixTransposeType tr) : r_(0), c_(0) {
+    if (tr == TRANS) {
+      Init(src.Cols(), src.Rows());
+      for (size_t i = 0; i < r_; i++) for (size_t j = 0; j < c_; j++) (*this)(i, j) = src(j, i);
+    } else { *this = src; }
+  }
+  size_t Rows() const { return r_; }
+  size_t Cols() const { return c_; }
+  size_t Stride() const { return c_; }
+  void Init(size_t rows, size_t cols, bool = true) { r_ = rows; c_ = cols; d_.assign(rows * cols, T()); }
+  void Destroy() { r_ = c_ = 0; d_.clear(); }
+  T *pData() { return d_.data(); }
+  const T *pData() const { return d_.data(); }
+  T *pRowData(size_t r) { return d_.data() + r * c_; }
+  const T *pRowData(size_t r) const { return d_.data() + r * c_; }
+  T &operator()(size_t r, size_t c) { return d_[r * c_ + c]; }
+  const T &operator()(size_t r, size_t c) const { return d_[r * c_ + c]; }
+  // NaN/Inf guard used by the trainers on every feature matrix (TNetCu.cc:386)
+  void CheckData(const std::string &name = "") const {
+    for (size_t i = 0; i < d_.size(); i++)
+      if (std::isnan((double)d_[i]) || std::isinf((double)d_[i])) {
+        std::ostringstream os;
+        os << "Invalid value: " << d_[i] << " in matrix " << name << " at row " << i / (c_ ? c_ : 1) << " col " << i % (c_ ? c_ : 1);
+        Error(os.str());
+      }
+  }
+ private:
+  size_t r_, c_;
+  std::vector<T> d_;
+};
+
+typedef Matrix<BaseFloat> BfMatrix;
+typedef Vector<BaseFloat> BfVector;
+
+// ---- text format -------------------------------------------------------------------------------------
+// numbers are read with strtod semantics on whitespace-separated tokens (also accepts "inf"/"nan")
+template <typename T>
+inline bool ReadNumber(std::istream &in, T &v) {
+  std::string tok;
+  if (!(in >> tok)) return false;
+  char *end = 0;
+  double d = std::strtod(tok.c_str(), &end);
+  if (end == tok.c_str() || *end != '\0') return false;
+  v = (T)d;
+  return true;
+}
+
+template <typename T>
+std::istream &operator>>(std::istream &in, Matrix<T> &m) {
+  in >> std::ws;
+  if (in.peek() == 'm') {
+    in.get();
+    long long r = -1, c = -1;
+    in >> r >> c;
+    if (in.fail() || r < 0 || c < 0) throw std::runtime_error("Failed to read matrix from stream: no size\n");
+    if (m.Rows() != (size_t)r || m.Cols() != (size_t)c) m.Init(r, c);
+  }
+  for (size_t i = 0; i < m.Rows(); i++)
+    for (size_t j = 0; j < m.Cols(); j++)
+      if (!ReadNumber(in, m(i, j))) throw std::runtime_error("Failed to read matrix from stream");
+  return in;
+}
+template <typename T>
+std::ostream &operator<<(std::ostream &out, const Matrix<T> &m) {
+  out << "m " << m.Rows() << ' ' << m.Cols() << '\n';
+  for (size_t i = 0; i < m.Rows(); i++) {
+    for (size_t j = 0; j < m.Cols(); j++) out << m(i, j) << ' ';
+    out << '\n';
+  }
+  if (out.fail()) throw std::runtime_error("Failed to write matrix to stream");
+  return out;
+}
+template <typename T>
+std::istream &operator>>(std::istream &in, Vector<T> &v) {
+  in >> std::ws;
+  if (in.peek() == 'v') {
+    in.get();
+    long long n = -1;
+    in >> n;
+    if (in.fail() || n < 0) throw std::runtime_error("Failed to read vector from stream: no size");
+    if (v.Dim() != (size_t)n) v.Init(n);
+  }
+  for (size_t i = 0; i < v.Dim(); i++)
+    if (!ReadNumber(in, v[i])) throw std::runtime_error("Failed to read vector from stream");
+  return in;
+}
+template <typename T>
+std::ostream &operator<<(std::ostream &out, const Vector<T> &v) {
+  out << "v " << v.Dim() << "  ";
+  for (size_t i = 0; i < v.Dim(); i++) out << v[i] << ' ';
+  if (out.fail()) throw std::runtime_error("Failed to write vector to stream");
+  return out;
+}
+
+}  // namespace TNet
+#endif

@@ -1,0 +1,181 @@
+"""ctypes binding of the C ABI declared in include/tnet_b200.h (libtnetb200.so).
+
+Used by tests/ and bench.py to call the product exactly the way a foreign-language host would: plain
+pointers and sizes.  There is no CPU fallback: when the library (or a GPU) is missing, everything raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+LIB_PATH = os.path.join(ROOT, "nnet-asr_b200", "lib", "libtnetb200.so")
+
+OK = 0
+MATH_3XTF32, MATH_TF32, MATH_FP32_SIMT = 0, 1, 2
+ACT_NONE, ACT_SIGMOID = 0, 1
+H2D, D2H, D2D = 0, 1, 2
+
+
+class MatrixDim(C.Structure):
+    _fields_ = [("rows", C.c_int), ("cols", C.c_int), ("stride", C.c_int)]
+
+
+class ObjStats(C.Structure):
+    _fields_ = [("error", C.c_double), ("frames", C.c_longlong), ("correct", C.c_longlong)]
+
+
+class TnbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TnbError("libtnetb200.so is not built (%s): run __graft_entry__.build()" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.tnb_version.restype = C.c_char_p
+        _lib.tnb_last_error.restype = C.c_char_p
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        raise TnbError("tnb error %d: %s" % (rc, lib().tnb_last_error().decode()))
+
+
+def declared_symbols():
+    """All function names declared in include/tnet_b200.h."""
+    import re
+    txt = open(os.path.join(ROOT, "include", "tnet_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(tnb_[a-z0-9_]+)\s*\(", txt)))
+
+
+class Context:
+    def __init__(self, device=0, math=MATH_3XTF32):
+        self.h = C.c_void_p()
+        check(lib().tnb_ctx_create(C.byref(self.h), C.c_int(device)))
+        self.set_math(math)
+
+    def set_math(self, m):
+        check(lib().tnb_ctx_set_math(self.h, C.c_int(m)))
+
+    def sync(self):
+        check(lib().tnb_ctx_sync(self.h))
+
+    def stream(self):
+        s = C.c_void_p()
+        check(lib().tnb_ctx_stream(self.h, C.byref(s)))
+        return s.value
+
+    def launches(self):
+        n = C.c_ulonglong()
+        check(lib().tnb_ctx_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def close(self):
+        if self.h:
+            lib().tnb_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DMat:
+    """Pitched fp32 (or int32/uint32) device matrix owned through tnb_malloc_pitch / tnb_free."""
+
+    def __init__(self, ctx, rows, cols, dtype=np.float32):
+        self.ctx, self.rows, self.cols, self.dtype = ctx, int(rows), int(cols), np.dtype(dtype)
+        assert self.dtype.itemsize == 4
+        self.ptr = C.c_void_p()
+        st = C.c_int()
+        check(lib().tnb_malloc_pitch(ctx.h, C.byref(self.ptr), C.byref(st), C.c_int(self.rows), C.c_int(self.cols)))
+        self.stride = st.value
+
+    @classmethod
+    def from_numpy(cls, ctx, a):
+        a = np.ascontiguousarray(a)
+        if a.ndim == 1:
+            a = a.reshape(1, -1)
+        m = cls(ctx, a.shape[0], a.shape[1], a.dtype)
+        m.upload(a)
+        return m
+
+    @property
+    def dim(self):
+        return MatrixDim(self.rows, self.cols, self.stride)
+
+    def row_view_dim(self, rows):
+        return MatrixDim(rows, self.cols, self.stride)
+
+    def p(self, ctype=C.c_float):
+        return C.cast(self.ptr, C.POINTER(ctype))
+
+    def row_ptr(self, r, ctype=C.c_float):
+        return C.cast(C.c_void_p(self.ptr.value + 4 * r * self.stride), C.POINTER(ctype))
+
+    def upload(self, a):
+        a = np.ascontiguousarray(a, dtype=self.dtype).reshape(self.rows, self.cols)
+        if self.rows == 0 or self.cols == 0:
+            return
+        check(lib().tnb_memcpy2d(self.ctx.h, self.ptr, C.c_size_t(self.stride * 4), a.ctypes.data_as(C.c_void_p),
+                                 C.c_size_t(self.cols * 4), C.c_size_t(self.cols * 4), C.c_size_t(self.rows), C.c_int(H2D)))
+        self.ctx.sync()  # pageable source
+
+    def download(self):
+        a = np.empty((self.rows, self.cols), dtype=self.dtype)
+        if self.rows == 0 or self.cols == 0:
+            return a
+        check(lib().tnb_memcpy2d(self.ctx.h, a.ctypes.data_as(C.c_void_p), C.c_size_t(self.cols * 4), self.ptr,
+                                 C.c_size_t(self.stride * 4), C.c_size_t(self.cols * 4), C.c_size_t(self.rows), C.c_int(D2H)))
+        return a
+
+    def free(self):
+        if self.ptr:
+            lib().tnb_free(self.ctx.h, self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.free()
+        except Exception:
+            pass
+
+
+class DStats:
+    """Device-resident TnbObjStats."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.ptr = C.c_void_p()
+        check(lib().tnb_malloc(ctx.h, C.byref(self.ptr), C.c_size_t(C.sizeof(ObjStats))))
+
+    def p(self):
+        return C.cast(self.ptr, C.POINTER(ObjStats))
+
+    def read(self):
+        st = ObjStats()
+        check(lib().tnb_memcpy(self.ctx.h, C.byref(st), self.ptr, C.c_size_t(C.sizeof(ObjStats)), C.c_int(D2H)))
+        return st.error, st.frames, st.correct
+
+    def reset(self):
+        check(lib().tnb_memset(self.ctx.h, self.ptr, C.c_int(0), C.c_size_t(C.sizeof(ObjStats))))
+
+
+def gemm(ctx, ta, tb, alpha, A, B, beta, Cm):
+    """Cm (DMat) = alpha*op(A)*op(B) + beta*Cm with CuMatrix::Gemm argument meaning."""
+    m, n = Cm.rows, Cm.cols
+    k = A.rows if ta in "Tt" else A.cols
+    check(lib().tnb_gemm(ctx.h, C.c_char(ta.encode()), C.c_char(tb.encode()), C.c_int(m), C.c_int(n), C.c_int(k),
+                         C.c_float(alpha), A.p(), C.c_int(A.stride), B.p(), C.c_int(B.stride), C.c_float(beta), Cm.p(),
+                         C.c_int(Cm.stride)))

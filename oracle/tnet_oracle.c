@@ -135,14 +135,17 @@ static float max_reduce_tree(float *buffer, int n) {
   return buffer[0];
 }
 
-/* cukernels.cu:424-446 _max_id_reduce : index tree, left slot kept on ties */
+/* cukernels.cu:424-446 _max_id_reduce : index tree, left slot kept on ties.
+ * Upstream, an unpaired slot compares temp = -1e20 and, if its value is below -1e20, copies
+ * idx[t+halfPoint] which was never written (undefined behaviour).  Defined inputs (softmax
+ * outputs, one-hot targets) never go there; the restatement leaves an unpaired slot unchanged. */
 static int max_id_reduce_tree(const float *val, int *idx, int n) {
   int nTotalThreads = n;
   while (nTotalThreads > 1) {
     int halfPoint = ((1 + nTotalThreads) >> 1);
     for (int t = 0; t < halfPoint; t++) {
-      float temp = -1e20;
-      if (t + halfPoint < nTotalThreads) temp = val[idx[t + halfPoint]];
+      if (t + halfPoint >= nTotalThreads) continue;
+      float temp = val[idx[t + halfPoint]];
       if (temp > val[idx[t]]) idx[t] = idx[t + halfPoint];
     }
     nTotalThreads = ((1 + nTotalThreads) >> 1);

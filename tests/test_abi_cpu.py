@@ -1,0 +1,46 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads without a GPU or NCCL and exports every
+symbol include/tnet_b200.h declares; compute entry points fail loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import subprocess
+
+import pytest
+
+from tnet_b200 import abi
+
+
+def test_library_is_built():
+    assert os.path.exists(abi.LIB_PATH), "run `python -c 'import __graft_entry__ as g; g.build()'`"
+
+
+def test_exports_every_declared_symbol():
+    lib = abi.lib()
+    names = abi.declared_symbols()
+    assert len(names) >= 55
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_no_link_time_dependency_on_driver_or_nccl_or_oracle():
+    out = subprocess.check_output(["ldd", abi.LIB_PATH], text=True)
+    for forbidden in ("libcuda.so", "libnccl", "libcublas", "tnet_oracle"):
+        assert forbidden not in out, out
+
+
+def test_fails_loudly_without_gpu():
+    lib = abi.lib()
+    n = C.c_int(-1)
+    rc = lib.tnb_device_count(C.byref(n))
+    if rc == abi.OK and n.value > 0:
+        pytest.skip("a GPU is visible")
+    h = C.c_void_p()
+    rc = lib.tnb_ctx_create(C.byref(h), C.c_int(0))
+    assert rc != abi.OK and not h.value
+    assert lib.tnb_last_error().decode() != ""
+
+
+def test_matrixdim_layout_matches_reference():
+    # reference: CuBaseLib/cukernels.h:12-16  struct { int rows; int cols; int stride; }
+    assert C.sizeof(abi.MatrixDim) == 12
+    assert [f[0] for f in abi.MatrixDim._fields_] == ["rows", "cols", "stride"]
+    assert C.sizeof(abi.ObjStats) == 24

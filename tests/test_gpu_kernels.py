@@ -1,0 +1,395 @@
+"""Kernel-level parity: every C-ABI compute entry point of libtnetb200.so against oracle/tnet_oracle.c on the same
+seeded inputs.  Integer / index work is bit-exact; floating point is held to the tolerance written at each test."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle_lib as O
+from tnet_b200 import abi
+
+L = None
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    global L
+    L = abi.lib()
+    c = abi.Context(0)
+    yield c
+    c.close()
+
+
+def rng(seed):
+    return np.random.default_rng(seed)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+# 3xTF32 tolerance: error per product <= ~2^-21 relative + the tensor core's fp32 accumulation (truncating adds, one per
+# K=8 instruction, which grows like sqrt(K) exactly as an fp32 SGEMM's rounding does); measured against the
+# double-accumulated oracle and scaled by sum_k |a||b| (the forward error bound's natural scale).
+def tol3x(K):
+    return max(2e-6, 8e-8 * np.sqrt(K))     # = 2^-24 * 1.35 * sqrt(K): fp32-SGEMM-equivalent
+
+GEMM_SHAPES = [
+    # (ta, tb, M, N, K)
+    ("N", "N", 256, 1024, 351),    # config A forward, layer 1  (K tail 351 = 10*32+31)
+    ("N", "N", 256, 135, 1024),    # config A forward, layer 2  (N tail)
+    ("N", "T", 256, 1024, 135),    # config A dX (K tail 135)
+    ("T", "N", 351, 1024, 256),    # config A dW layer 1 (M tail)
+    ("T", "N", 1024, 135, 256),    # config A dW layer 2
+    ("N", "N", 1024, 2048, 429),   # config C forward first layer
+    ("N", "T", 1024, 2048, 3000),  # config C dX last layer (K tail 3000 = 93*32+24)
+    ("T", "N", 2048, 3000, 1024),  # config C dW last layer -> BN=256 path
+    ("N", "N", 1, 7, 5),           # degenerate tiny
+    ("T", "T", 130, 70, 45),       # the 4th operand-major combination
+    ("N", "N", 128, 64, 32),       # exactly one tile, BN=64
+]
+
+
+def _gemm_case(ctx, ta, tb, M, N, K, math, alpha=1.0, beta=0.0, seed=0):
+    r = rng(seed)
+    A = r.standard_normal((K, M) if ta == "T" else (M, K)).astype(np.float32)
+    B = r.standard_normal((N, K) if tb == "T" else (K, N)).astype(np.float32)
+    C0 = r.standard_normal((M, N)).astype(np.float32)
+    ctx.set_math(math)
+    dA, dB, dC = abi.DMat.from_numpy(ctx, A), abi.DMat.from_numpy(ctx, B), abi.DMat.from_numpy(ctx, C0)
+    abi.gemm(ctx, ta, tb, alpha, dA, dB, beta, dC)
+    got = dC.download()
+    ref = O.gemm(ta, tb, alpha, A, B, beta, C0, acc_double=1)
+    opA = A.T if ta == "T" else A
+    opB = B.T if tb == "T" else B
+    scale = np.abs(opA).astype(np.float64) @ np.abs(opB).astype(np.float64) * abs(alpha) + abs(beta) * np.abs(C0)
+    return got, ref, scale
+
+
+@pytest.mark.parametrize("ta,tb,M,N,K", GEMM_SHAPES)
+def test_gemm_3xtf32_vs_oracle(ctx, ta, tb, M, N, K):
+    got, ref, scale = _gemm_case(ctx, ta, tb, M, N, K, abi.MATH_3XTF32)
+    err = np.abs(got.astype(np.float64) - ref) / (scale + 1e-30)
+    assert err.max() < tol3x(K), err.max()
+
+
+@pytest.mark.parametrize("ta,tb,M,N,K", GEMM_SHAPES[:5] + GEMM_SHAPES[8:])
+def test_gemm_tf32_vs_oracle(ctx, ta, tb, M, N, K):
+    got, ref, scale = _gemm_case(ctx, ta, tb, M, N, K, abi.MATH_TF32)
+    err = np.abs(got.astype(np.float64) - ref) / (scale + 1e-30)
+    assert err.max() < 2e-3, err.max()      # single tf32: 2^-10 per operand
+
+
+@pytest.mark.parametrize("ta,tb,M,N,K", [GEMM_SHAPES[0], GEMM_SHAPES[2], GEMM_SHAPES[3], GEMM_SHAPES[9]])
+def test_gemm_simt_vs_oracle(ctx, ta, tb, M, N, K):
+    got, ref, scale = _gemm_case(ctx, ta, tb, M, N, K, abi.MATH_FP32_SIMT)
+    err = np.abs(got.astype(np.float64) - ref) / (scale + 1e-30)
+    assert err.max() < 1e-6, err.max()
+
+
+def test_gemm_alpha_beta(ctx):
+    got, ref, scale = _gemm_case(ctx, "T", "N", 200, 300, 96, abi.MATH_3XTF32, alpha=-0.37, beta=0.9, seed=3)
+    err = np.abs(got.astype(np.float64) - ref) / (scale + 1e-30)
+    assert err.max() < 2e-6
+
+
+def test_gemm_linearity_full_size(ctx):
+    """Size-independent property at config C's largest layer: G(a*X1 + X2) == a*G(X1) + G(X2) up to rounding."""
+    r = rng(11)
+    M, K, N = 1024, 2048, 3000
+    X1 = r.standard_normal((M, K)).astype(np.float32)
+    X2 = r.standard_normal((M, K)).astype(np.float32)
+    W = (0.1 * r.standard_normal((K, N))).astype(np.float32)
+    ctx.set_math(abi.MATH_3XTF32)
+    dW = abi.DMat.from_numpy(ctx, W)
+    outs = []
+    for X in (X1, X2, (2.0 * X1 + X2).astype(np.float32)):
+        dX = abi.DMat.from_numpy(ctx, X)
+        dY = abi.DMat(ctx, M, N)
+        abi.gemm(ctx, "N", "N", 1.0, dX, dW, 0.0, dY)
+        outs.append(dY.download().astype(np.float64))
+    lin = 2.0 * outs[0] + outs[1]
+    assert np.abs(outs[2] - lin).max() < 2e-4 * np.abs(lin).max()
+
+
+def test_affine_fwd_bias_sigmoid(ctx):
+    r = rng(5)
+    rows, nin, nout = 300, 351, 1024
+    X = r.standard_normal((rows, nin)).astype(np.float32)
+    W = (0.1 * r.standard_normal((nin, nout))).astype(np.float32)
+    b = r.standard_normal(nout).astype(np.float32)
+    ctx.set_math(abi.MATH_3XTF32)
+    dX, dW, db = abi.DMat.from_numpy(ctx, X), abi.DMat.from_numpy(ctx, W), abi.DMat.from_numpy(ctx, b)
+    dY = abi.DMat(ctx, rows, nout)
+    for act in (abi.ACT_NONE, abi.ACT_SIGMOID):
+        abi.check(L.tnb_affine_fwd(ctx.h, dX.p(), dX.dim, dW.p(), dW.dim, db.p(), dY.p(), dY.dim, C.c_int(act)))
+        got = dY.download()
+        pre = O.gemm("N", "N", 1.0, X, W, 1.0, np.tile(b, (rows, 1)), acc_double=1)
+        ref = O.sigmoid(pre) if act else pre
+        np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5 if not act else 2e-6)
+
+
+def test_affine_bwd_dx_diffsigmoid(ctx):
+    r = rng(6)
+    rows, nin, nout = 260, 1024, 135
+    E = r.standard_normal((rows, nout)).astype(np.float32)
+    W = (0.1 * r.standard_normal((nin, nout))).astype(np.float32)
+    Yp = r.random((rows, nin)).astype(np.float32)
+    dE, dW, dYp = abi.DMat.from_numpy(ctx, E), abi.DMat.from_numpy(ctx, W), abi.DMat.from_numpy(ctx, Yp)
+    dEp = abi.DMat(ctx, rows, nin)
+    abi.check(L.tnb_affine_bwd_dx(ctx.h, dE.p(), dE.dim, dW.p(), dW.dim, dYp.p(), dYp.dim, dEp.p(), dEp.dim))
+    got = dEp.download()
+    ref = O.diff_sigmoid(O.gemm("N", "T", 1.0, E, W, 0.0, np.zeros((rows, nin), np.float32), acc_double=1), Yp)
+    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-6)
+    abi.check(L.tnb_affine_bwd_dx(ctx.h, dE.p(), dE.dim, dW.p(), dW.dim, None, dYp.dim, dEp.p(), dEp.dim))
+    ref2 = O.gemm("N", "T", 1.0, E, W, 0.0, np.zeros((rows, nin), np.float32), acc_double=1)
+    np.testing.assert_allclose(dEp.download(), ref2, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("rows,nin,nout,mmt,wc,gdf", [(256, 351, 1024, 0.0, 0.0, 1), (640, 200, 135, 0.5, 1e-4, 1),
+                                                      (128, 64, 300, 0.9, 1e-3, 0)])
+def test_affine_update_vs_oracle(ctx, rows, nin, nout, mmt, wc, gdf):
+    """CuBiasedLinearity::Update fused in the dW epilogue == oracle restatement of cuBiasedLinearity.cc:44-64."""
+    r = rng(7)
+    X = r.standard_normal((rows, nin)).astype(np.float32)
+    E = (0.1 * r.standard_normal((rows, nout))).astype(np.float32)
+    W = (0.1 * r.standard_normal((nin, nout))).astype(np.float32)
+    b = r.standard_normal(nout).astype(np.float32)
+    cW = (0.01 * r.standard_normal((nin, nout))).astype(np.float32)
+    cb = (0.01 * r.standard_normal(nout)).astype(np.float32)
+    lr = 0.05
+    dX, dE, dW, db, dcW, dcb = [abi.DMat.from_numpy(ctx, a) for a in (X, E, W, b, cW, cb)]
+    abi.check(L.tnb_affine_update(ctx.h, dX.p(), dX.dim, dE.p(), dE.dim, dW.p(), dW.dim, db.p(), dcW.p(), dcb.p(),
+                                  C.c_float(lr), C.c_float(mmt), C.c_float(wc), C.c_int(gdf), C.c_int(0)))
+    W2, b2, cW2, cb2 = W.copy(), b.copy(), cW.copy(), cb.copy()
+    O.lib.orc_affine_update(O.P(X), nin, O.P(E), nout, O.P(W2), nout, O.P(b2), O.P(cW2), nout, O.P(cb2), rows, nin, nout,
+                            O.cf(lr), O.cf(mmt), O.cf(wc), gdf, 1)
+    np.testing.assert_allclose(dcW.download(), cW2, rtol=1e-5, atol=1e-5 * np.abs(cW2).max())
+    np.testing.assert_allclose(dW.download(), W2, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(dcb.download()[0], cb2, rtol=1e-5, atol=1e-5 * np.abs(cb2).max())
+    np.testing.assert_allclose(db.download()[0], b2, rtol=1e-5, atol=1e-6)
+
+
+def test_affine_grad_plus_sgd_update_equals_fused(ctx):
+    """Data-parallel path (grad -> [allreduce] -> tnb_sgd_update) gives the fused single-GPU result."""
+    r = rng(8)
+    rows, nin, nout = 192, 100, 260
+    X = r.standard_normal((rows, nin)).astype(np.float32)
+    E = (0.1 * r.standard_normal((rows, nout))).astype(np.float32)
+    W = (0.1 * r.standard_normal((nin, nout))).astype(np.float32)
+    b = r.standard_normal(nout).astype(np.float32)
+    z = np.zeros_like
+    dX, dE = abi.DMat.from_numpy(ctx, X), abi.DMat.from_numpy(ctx, E)
+    W1, b1, c1, cb1 = [abi.DMat.from_numpy(ctx, a) for a in (W, b, z(W), z(b))]
+    W2, b2, c2, cb2 = [abi.DMat.from_numpy(ctx, a) for a in (W, b, z(W), z(b))]
+    G, gb = abi.DMat(ctx, nin, nout), abi.DMat(ctx, 1, nout)
+    args = (C.c_float(0.1), C.c_float(0.5), C.c_float(1e-4), C.c_int(1))
+    for _ in range(2):
+        abi.check(L.tnb_affine_update(ctx.h, dX.p(), dX.dim, dE.p(), dE.dim, W1.p(), W1.dim, b1.p(), c1.p(), cb1.p(), *args, C.c_int(0)))
+        abi.check(L.tnb_affine_grad(ctx.h, dX.p(), dX.dim, dE.p(), dE.dim, G.p(), G.dim, gb.p()))
+        abi.check(L.tnb_sgd_update(ctx.h, G.p(), W2.p(), c2.p(), W2.dim, gb.p(), b2.p(), cb2.p(), *args, C.c_int(rows)))
+    np.testing.assert_allclose(W1.download(), W2.download(), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(b1.download(), b2.download(), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(c1.download(), c2.download(), rtol=1e-6, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+def _mat(ctx, a):
+    return abi.DMat.from_numpy(ctx, a)
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (7, 13), (256, 351), (100, 3000)])
+def test_elementwise_ops(ctx, rows, cols):
+    r = rng(rows * 1000 + cols)
+    x = r.standard_normal((rows, cols)).astype(np.float32)
+    y = r.standard_normal((rows, cols)).astype(np.float32)
+    # sigmoid / diff_sigmoid  (device expf vs libm expf: <= 2 ulp)
+    dx, dy = _mat(ctx, x), abi.DMat(ctx, rows, cols)
+    abi.check(L.tnb_sigmoid(ctx.h, dy.p(), dx.p(), dx.dim))
+    s = dy.download()
+    np.testing.assert_allclose(s, O.sigmoid(x), rtol=6e-7, atol=1e-9)
+    de = _mat(ctx, y)
+    dout = abi.DMat(ctx, rows, cols)
+    abi.check(L.tnb_diff_sigmoid(ctx.h, dout.p(), de.p(), dy.p(), dy.dim))
+    assert np.array_equal(dout.download(), O.diff_sigmoid(y, s))          # same inputs -> bit-exact (double product)
+    # add_scaled / add_scaled_row / mul_elem / scale_cols / scale_rows / set_const
+    d1 = _mat(ctx, x)
+    abi.check(L.tnb_add_scaled(ctx.h, C.c_float(-1.5), de.p(), C.c_float(0.25), d1.p(), d1.dim))
+    np.testing.assert_allclose(d1.download(), np.float32(-1.5) * y + np.float32(0.25) * x, rtol=1e-6, atol=1e-6)
+    row = r.standard_normal(cols).astype(np.float32)
+    drow = _mat(ctx, row)
+    d2 = _mat(ctx, x)
+    abi.check(L.tnb_add_scaled_row(ctx.h, C.c_float(1.0), drow.p(), C.c_float(0.0), d2.p(), d2.dim))
+    assert np.array_equal(d2.download(), np.tile(row, (rows, 1)))
+    d3 = _mat(ctx, x)
+    abi.check(L.tnb_mul_elem(ctx.h, d3.p(), de.p(), d3.dim))
+    assert np.array_equal(d3.download(), x * y)
+    d4 = _mat(ctx, x)
+    abi.check(L.tnb_scale_cols(ctx.h, d4.p(), drow.p(), d4.dim))
+    assert np.array_equal(d4.download(), x * row[None, :])
+    rs = r.standard_normal(rows).astype(np.float32)
+    drs = _mat(ctx, rs)
+    d5 = _mat(ctx, x)
+    abi.check(L.tnb_scale_rows(ctx.h, d5.p(), drs.p(), d5.dim))
+    assert np.array_equal(d5.download(), x * rs[:, None])
+    abi.check(L.tnb_set_const(ctx.h, d5.p(), C.c_float(3.25), d5.dim))
+    assert np.array_equal(d5.download(), np.full((rows, cols), 3.25, np.float32))
+    # log_elem floors at FLT_MIN
+    p = np.abs(x)
+    p[0, 0] = 0.0
+    d6 = _mat(ctx, p)
+    abi.check(L.tnb_log_elem(ctx.h, d6.p(), d6.dim))
+    ref = p.copy()
+    O.lib.orc_log_elem(O.P(ref), rows, cols, cols)
+    np.testing.assert_allclose(d6.download(), ref, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 5), (256, 135), (512, 256), (1024, 3000), (513, 33)])
+def test_add_col_sum(ctx, rows, cols):
+    r = rng(rows + cols)
+    m = r.standard_normal((rows, cols)).astype(np.float32)
+    v = r.standard_normal(cols).astype(np.float32)
+    dm, dv = _mat(ctx, m), _mat(ctx, v)
+    abi.check(L.tnb_add_col_sum(ctx.h, C.c_float(-0.5), dm.p(), C.c_float(0.75), dv.p(), dm.dim))
+    ref = O.add_col_sum(-0.5, m, 0.75, v)      # reference picks float-tree or double-serial by shape
+    # float tree (rows<=512 & cols<=256) carries ~sqrt(rows) ulp; double-serial is exact to 1 ulp
+    np.testing.assert_allclose(dv.download()[0], ref, rtol=1e-5, atol=2e-5)
+    exact = (-0.5 * m.astype(np.float64).sum(0) + 0.75 * v).astype(np.float32)
+    np.testing.assert_allclose(dv.download()[0], exact, rtol=3e-7, atol=1e-7)
+
+
+def test_gathers_bit_exact(ctx):
+    r = rng(21)
+    # randomize (cache shuffle): permutation shorter than the cache (partial last fill)
+    x = r.standard_normal((500, 351)).astype(np.float32)
+    perm = r.permutation(431).astype(np.int32)
+    dx, dp = _mat(ctx, x), _mat(ctx, perm)
+    dy = abi.DMat(ctx, 500, 351)
+    abi.check(L.tnb_randomize(ctx.h, dy.p(), dx.p(), dp.p(C.c_int), abi.MatrixDim(431, 351, dy.stride), abi.MatrixDim(431, 351, dx.stride)))
+    got = dy.download()
+    assert np.array_equal(got[:431], O.randomize(x, perm)[:431])
+    assert not got[431:].any()                                       # rows beyond the permutation untouched
+    # expand (splice) with edge clamping, 39 x 9 and 39 x 11
+    for ctxw in (4, 5):
+        f = r.standard_normal((77, 39)).astype(np.float32)
+        offs = np.arange(-ctxw, ctxw + 1, dtype=np.int32)
+        df, do = _mat(ctx, f), _mat(ctx, offs)
+        dz = abi.DMat(ctx, 77, 39 * len(offs))
+        abi.check(L.tnb_expand(ctx.h, dz.p(), df.p(), do.p(C.c_int), dz.dim, df.dim))
+        assert np.array_equal(dz.download(), O.expand(f, offs))
+    # rearrange with an out-of-range index -> +inf
+    cf = np.array([3, 0, 38, -1, 39, 7], dtype=np.int32)
+    dcf = _mat(ctx, cf)
+    dr = abi.DMat(ctx, 77, len(cf))
+    abi.check(L.tnb_rearrange(ctx.h, dr.p(), df.p(), dcf.p(C.c_int), dr.dim, df.dim))
+    assert np.array_equal(dr.download(), O.rearrange(f, cf))
+    # onehot
+    lab = r.integers(0, 300, 64).astype(np.int32)
+    dl = _mat(ctx, lab)
+    dt = abi.DMat(ctx, 64, 300)
+    abi.check(L.tnb_onehot(ctx.h, dt.p(), dl.p(C.c_int), dt.dim))
+    ref = np.zeros((64, 300), np.float32)
+    ref[np.arange(64), lab] = 1
+    assert np.array_equal(dt.download(), ref)
+
+
+# ------------------------------------------------------------------------------------------------ objective
+def _onehot(r, rows, cols):
+    t = np.zeros((rows, cols), np.float32)
+    t[np.arange(rows), r.integers(0, cols, rows)] = 1.0
+    return t
+
+
+@pytest.mark.parametrize("rows,cols", [(256, 135), (64, 256), (1024, 3000), (3, 257), (5, 1), (700, 10)])
+def test_softmax_xent_vs_oracle(ctx, rows, cols):
+    r = rng(rows * 7 + cols)
+    a = (3.0 * r.standard_normal((rows, cols))).astype(np.float32)
+    t = _onehot(r, rows, cols)
+    da, dt = _mat(ctx, a), _mat(ctx, t)
+    dy, de = abi.DMat(ctx, rows, cols), abi.DMat(ctx, rows, cols)
+    st = abi.DStats(ctx)
+    abi.check(L.tnb_softmax_xent(ctx.h, da.p(), dt.p(), dy.p(), de.p(), da.dim, st.p()))
+    y = dy.download()
+    yref = O.softmax(a)
+    np.testing.assert_allclose(y, yref, rtol=3e-6, atol=1e-9)        # float exp vs the reference's double exp/sum
+    assert np.array_equal(de.download(), y - t)                       # err = y - t on the kernel's own y: exact
+    # frame accuracy: bit-exact against the oracle's tie rules evaluated on the SAME y
+    err, frames, correct = st.read()
+    assert frames == rows
+    assert correct == int(O.check_class(y, t).sum())
+    _, xref, _, _ = O.xent_evaluate(y, t)
+    assert abs(err - xref) <= 2e-6 * abs(xref) + 1e-6
+    # standalone softmax and xent_eval entry points
+    dy2 = abi.DMat(ctx, rows, cols)
+    abi.check(L.tnb_softmax(ctx.h, dy2.p(), da.p(), da.dim))
+    assert np.array_equal(dy2.download(), y)
+    st2 = abi.DStats(ctx)
+    de2 = abi.DMat(ctx, rows, cols)
+    abi.check(L.tnb_xent_eval(ctx.h, dy.p(), dt.p(), de2.p(), dy.dim, st2.p()))
+    e2, f2, c2 = st2.read()
+    assert (f2, c2) == (frames, correct) and abs(e2 - err) <= 1e-9 * abs(err) + 1e-12
+    # stats accumulate across calls
+    abi.check(L.tnb_xent_eval(ctx.h, dy.p(), dt.p(), de2.p(), dy.dim, st2.p()))
+    e3, f3, c3 = st2.read()
+    assert (f3, c3) == (2 * frames, 2 * correct)
+
+
+@pytest.mark.parametrize("cols", [2, 3, 135, 255, 256, 257, 1000])
+def test_check_class_ties_bit_exact(ctx, cols):
+    """Collisions: quantised outputs force many exact ties; both tie rules (index tree <=256, first-max >256)."""
+    r = rng(cols)
+    rows = 300
+    out = r.integers(0, 4, (rows, cols)).astype(np.float32)
+    des = r.integers(0, 3, (rows, cols)).astype(np.float32)
+    out[0, :] = 0.0                       # all-equal row
+    if cols > 256:                        # (for cols <= 256 values below -1e20 are undefined behaviour upstream)
+        out[1, :] = -1e30                 # nothing beats the -1e20 floor -> id stays -1 / -2
+        des[1, :] = -1e30
+    out[2, 0] = np.nan
+    dout, ddes = _mat(ctx, out), _mat(ctx, des)
+    dm = abi.DMat(ctx, 1, rows, np.int32)
+    abi.check(L.tnb_check_class(ctx.h, dout.p(), ddes.p(), dm.p(C.c_int), dout.dim))
+    assert np.array_equal(dm.download()[0], O.check_class(out, des))
+
+
+def test_mse_eval(ctx):
+    r = rng(31)
+    y = r.standard_normal((128, 429)).astype(np.float32)
+    t = r.standard_normal((128, 429)).astype(np.float32)
+    dy, dt, de = _mat(ctx, y), _mat(ctx, t), abi.DMat(ctx, 128, 429)
+    st = abi.DStats(ctx)
+    abi.check(L.tnb_mse_eval(ctx.h, dy.p(), dt.p(), de.p(), dy.dim, st.p()))
+    eref, mref, fref = O.mse_evaluate(y, t)
+    assert np.array_equal(de.download(), eref)
+    err, frames, _ = st.read()
+    assert frames == fref and abs(err - mref) <= 2e-6 * mref
+
+
+# ------------------------------------------------------------------------------------------------ RNG
+def test_hybrid_taus_streams_bit_exact(ctx):
+    rows, cols = 37, 211
+    z = O.rand_seed(4242, rows, cols)
+    dz = [_mat(ctx, a) for a in z]
+    zo = [a.copy() for a in z]
+    dm = abi.DMat(ctx, rows, cols)
+    for _ in range(3):
+        abi.check(L.tnb_rand(ctx.h, dm.p(), *[d.p(C.c_uint) for d in dz], dm.dim))
+        ref = O.rand_uniform(zo)
+        assert np.array_equal(dm.download(), ref)
+    for d, a in zip(dz, zo):
+        assert np.array_equal(d.download(), a)                        # generator state advanced identically
+    probs = rng(1).random((rows, cols)).astype(np.float32)
+    dp, ds = _mat(ctx, probs), abi.DMat(ctx, rows, cols)
+    abi.check(L.tnb_rand_binarize(ctx.h, ds.p(), dp.p(), *[d.p(C.c_uint) for d in dz], ds.dim))
+    assert np.array_equal(ds.download(), O.binarize(probs, O.rand_uniform(zo)))
+    abi.check(L.tnb_gauss_rand(ctx.h, dm.p(), *[d.p(C.c_uint) for d in dz], dm.dim))
+    g = O.rand_gauss(zo)
+    np.testing.assert_allclose(dm.download(), g, rtol=2e-6, atol=2e-6)  # device logf/sinf vs libm
+    for d, a in zip(dz, zo):
+        assert np.array_equal(d.download(), a)
+
+
+def test_launch_counter(ctx):
+    n0 = ctx.launches()
+    d = abi.DMat(ctx, 8, 8)
+    abi.check(L.tnb_set_const(ctx.h, d.p(), C.c_float(1.0), d.dim))
+    assert ctx.launches() == n0 + 1
