@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py — training frames/s of TNet's bunch hot path (forward, softmax+xent, backward, SGD update) on B200.
+
+  python bench.py --gpus N --steps K --warmup W            this repo's CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...   the reference's own CPU trainer (oracle/_ref/TNet) on host cores
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): deep DNN 429-2048x6-3000 sigmoid/softmax,
+bunch 1024 PER GPU, synthetic N(0,1) features and uniform labels, random-init weights (W~0.1*N(0,1), hidden bias
+U[-4.1,-3.9]), learning rate 0.008 / momentum 0.5 / weightcost 1e-6, GRADDIVFRM on.  A step = one bunch: CuCache::GetBunch
+row window, forward, fused softmax+cross-entropy+accuracy, backward, momentum/L2 update.  Data parallel: every rank owns
+its rows of the (N x 1024)-frame global bunch, per-layer [dW|db] is summed with NCCL, N in the update rule is the global
+frame count ("scaling": "weak").
+
+One JSON line on stdout (rank 0).  `value` = frames/s with the training set resident in HBM; `e2e` = the same through
+the host-buffer entry point (pinned host features + int labels copied H2D every step, statistics read back D2H every
+step); `roofline` = algorithmic GEMM flops / CUDA-event time of the tcgen05 GEMM launches inside the timed region;
+`cpu_baseline` = the reference CPU trainer on a bounded sample of the same workload (rank 0, N=1 only).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "nnet-asr_b200", "python"))
+
+DIMS = [429, 2048, 2048, 2048, 2048, 2048, 2048, 3000]
+BUNCH = 1024
+RAW_DIM, CTX = 39, 5
+LR, MMT, WC = 0.008, 0.5, 1e-6
+RESIDENT_BUNCHES = 16
+WORKLOAD = "deep DNN 429-2048x6-3000 sigmoid/softmax, bunch 1024 per GPU (BASELINE configs[2])"
+
+
+def flops_per_frame(dims):
+    """6*sum(in*out) - 2*in_1*out_1 (no dX for the first trainable layer)."""
+    s = sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+    return 6 * s - 2 * dims[0] * dims[1]
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_sustained=d.get("bf16_tflops_sustained", 1388.8), bf16_burst=d.get("bf16_tflops", 1648.3),
+                    hbm=d.get("hbm_gbs", 6552.6), source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_sustained=1400.0, bf16_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile(mode="w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        rows = [r for r in rows if len(r) >= 9 and r[0].strip() == str(self.idx)]
+        if not rows:
+            return out
+        sm = sorted(float(r[1]) for r in rows if r[1].replace(".", "").isdigit())
+        if sm:
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = float(rows[0][2])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for k, n in enumerate(names):
+            if any(r[5 + k].strip().lower() == "active" for r in rows):
+                out["reasons"].append(n)
+        out["power_w_max"] = max((float(r[3]) for r in rows if re.match(r"^[0-9.]+$", r[3])), default=None)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ reference CPU arm
+def write_reference_dataset(d, n_frames, utt_len=256, seed=20240607):
+    """Files the reference trainers read: HTK features (raw 39-dim), <expand> +-5 transform, MLF, label map, SCP and the
+    429-2048x6-3000 network (tools/init/gen_mlp_init.py --gauss --negbias statistics)."""
+    from tnet_b200 import formats as F
+    rng = np.random.default_rng(seed)
+    utts = F.gen_utterances(max(1, n_frames // utt_len), utt_len, RAW_DIM, DIMS[-1], rng, vary_len=False)
+    paths = F.write_dataset(d, utts, DIMS[-1], CTX)
+    net = os.path.join(d, "init.nnet")
+    with open(net, "w") as f:           # numpy's C-level text writer: ~300 MB of weights in a few seconds
+        for l in range(len(DIMS) - 1):
+            nin, nout = DIMS[l], DIMS[l + 1]
+            last = l == len(DIMS) - 2
+            f.write("<biasedlinearity> %d %d\nm %d %d\n" % (nout, nin, nout, nin))
+            f.flush()
+            (0.1 * rng.standard_normal(nout * nin)).astype(np.float32).tofile(f, sep=" ", format="%.6g")
+            f.write("\nv %d\n" % nout)
+            f.flush()
+            b = np.zeros(nout, np.float32) if last else (rng.random(nout) / 5.0 - 4.1).astype(np.float32)
+            b.tofile(f, sep=" ", format="%.6g")
+            f.write("\n<%s> %d %d\n" % ("softmax" if last else "sigmoid", nout, nout))
+    paths["net"] = net
+    return paths
+
+
+def run_reference_tnet(paths, d, threads, n_utts_scp=None):
+    exe = os.path.join(ROOT, "oracle", "_ref", "TNet")
+    scp = paths["scp"]
+    if n_utts_scp is not None:
+        scp = os.path.join(d, "sub_%d.scp" % n_utts_scp)
+        open(scp, "w").write("\n".join(paths["files"][:n_utts_scp]) + "\n")
+    cmd = [exe, "-H", paths["net"], "-I", paths["mlf"], "-L", "*/", "-X", "lab", "-S", scp, "-m", paths["labelmap"],
+           "-n", repr(LR / BUNCH),      # the CPU trainer has no 1/N: the schedulers divide lr by the bunch size
+           "--TARGETMMF=" + os.path.join(d, "out.nnet"), "--BUNCHSIZE=%d" % BUNCH, "--CACHESIZE=%d" % (BUNCH * 4),
+           "--RANDOMIZE=TRUE", "--SEED=123", "--FEATURETRANSFORM=" + paths["transform"], "--STARTFRMEXT=%d" % CTX,
+           "--ENDFRMEXT=%d" % CTX, "--WEIGHTCOST=%g" % WC, "--THREADS=%d" % threads]
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")
+    t0 = time.perf_counter()
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    wall = time.perf_counter() - t0
+    if res.returncode != 0:
+        raise RuntimeError("reference TNet failed:\n" + res.stdout[-2000:])
+    m = re.search(r"frames:(\d+)", res.stdout)
+    return wall, int(m.group(1)) if m else 0
+
+
+def cpu_reference_throughput(bunches_a, bunches_b, threads=None):
+    """frames/s of the reference CPU trainer on config C, from the SLOPE between two runs of different length so that the
+    fixed cost of parsing/writing the 28M-weight text network (inside TNet's own timer) drops out."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "TNet")
+    if not os.path.exists(exe):
+        raise RuntimeError("oracle/_ref/TNet is not built (run __graft_entry__.build() where /root/reference exists)")
+    ncpu = os.cpu_count() or 1
+    if threads is None:
+        threads = 1
+        while threads * 2 <= min(ncpu, 32):
+            threads *= 2
+    utt_len = 256
+    d = tempfile.mkdtemp(prefix="tnet_cpu_")
+    try:
+        need = max(bunches_a, bunches_b) * BUNCH
+        paths = write_reference_dataset(d, need, utt_len)
+        per = BUNCH // utt_len
+        ta, fa = run_reference_tnet(paths, d, threads, bunches_a * per)
+        tb, fb = run_reference_tnet(paths, d, threads, bunches_b * per)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    if fb <= fa or tb <= ta:
+        raise RuntimeError("reference runs did not scale: %s frames in %.1fs vs %s in %.1fs" % (fa, ta, fb, tb))
+    fps = (fb - fa) / (tb - ta)
+    return fps, threads, "reference TNet --THREADS=%d, slope between %d and %d frames of config C (%.1fs, %.1fs wall)" % (
+        threads, fa, fb, ta, tb)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = max(1, min(args.steps, 12))     # bounded sample: each CPU step is one 1024-frame bunch
+    try:
+        fps, threads, sample = cpu_reference_throughput(2, 2 + steps)
+    except Exception as e:  # the oracle always exists; a failure here is an error, not "unavailable"
+        print(json.dumps({"impl": "reference", "error": str(e)[:300]}))
+        return 1
+    line = {
+        "impl": "reference", "metric": "training_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": 2, "ms_per_step": 1000.0 * BUNCH / fps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "bunch": BUNCH, "note": "CPU reference trains ONE 1024-frame bunch per step on host cores"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ this repo's arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--math", default="3xtf32", choices=["3xtf32", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from tnet_b200 import abi, host
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    host.select_gpu(local)
+    host.set_math(abi.MATH_3XTF32 if args.math == "3xtf32" else abi.MATH_TF32)
+    L, H = abi.lib(), host.hlib()
+    ctx = host.ctx_handle()
+
+    # ---- data-parallel communicator of the library (NCCL id exchanged through torch.distributed) ----
+    if world > 1:
+        idbuf = (C.c_ubyte * 128)()
+        if rank == 0:
+            abi.check(L.tnb_comm_unique_id(idbuf))
+        t = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        idbuf = (C.c_ubyte * 128)(*t.cpu().tolist())
+        abi.check(L.tnb_comm_init(ctx, idbuf, C.c_int(rank), C.c_int(world)))
+
+    net = host.Net(dims=DIMS, seed=1)
+    net.set_hyper(LR, mmt=MMT, wc=WC, gdf=True)
+    if world > 1:
+        net.set_data_parallel(world)
+
+    rng = np.random.default_rng(20240607 + rank)
+    rows = RESIDENT_BUNCHES * BUNCH
+    X = rng.standard_normal((rows, DIMS[0])).astype(np.float32)
+    lab = rng.integers(0, DIMS[-1], rows).astype(np.int32)
+    net.load_resident(X, lab)
+
+    stream = torch.cuda.ExternalStream(host_stream(L, ctx), device=torch.device("cuda", local))
+
+    def barrier():
+        host.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    net.train_resident(BUNCH, 0, args.warmup)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = host.launches()
+    abi.check(L.tnb_ctx_profile_begin(ctx))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    net.train_resident(BUNCH, args.warmup, args.steps)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    gms, gl, gfl = C.c_double(), C.c_ulonglong(), C.c_double()
+    abi.check(L.tnb_ctx_profile_end(ctx, C.byref(gms), C.byref(gl), C.byref(gfl)))
+    launches = host.launches() - l0
+    clocks = sampler.stop() if rank == 0 else {}
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    frames = args.steps * BUNCH * world
+    value = frames / (ms / 1000.0)
+
+    # ---- end to end: pinned host buffers in, statistics out, every step ----
+    xb = torch.empty((BUNCH, DIMS[0]), dtype=torch.float32).pin_memory()
+    lb = torch.empty((BUNCH,), dtype=torch.int32).pin_memory()
+    xb.copy_(torch.from_numpy(X[:BUNCH]))
+    lb.copy_(torch.from_numpy(lab[:BUNCH]))
+    xp, lp = C.cast(xb.data_ptr(), C.POINTER(C.c_float)), C.cast(lb.data_ptr(), C.POINTER(C.c_int))
+
+    def e2e_step():
+        host.hcheck(H.tnh_net_train_bunch_labels(net.h, xp, lp, C.c_int(BUNCH), C.c_int(0)))
+        return net.stats()          # D2H read of {xent, frames, correct}: synchronises the step
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_value = frames / e2e_s
+
+    if rank == 0:
+        pk = measured_peaks()
+        fpf = flops_per_frame(DIMS)
+        gemm_tflops = (gfl.value / (gms.value / 1000.0)) / 1e12 if gms.value > 0 else 0.0
+        passes = 3 if args.math == "3xtf32" else 1
+        line = {
+            "metric": "training_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32x3" if args.math == "3xtf32" else "tf32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "dims": DIMS, "bunch_per_gpu": BUNCH, "global_bunch": BUNCH * world,
+                       "parallelism": "dp%d" % world, "learn_rate": LR, "momentum": MMT, "weightcost": WC,
+                       "l2_note": "no L2 flush: weights+corrections (224 MB) and activations exceed the 126 MB L2 every step",
+                       "flops_per_frame": fpf, "gemm_math": args.math},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": BUNCH * DIMS[0] * 4 + BUNCH * 4,
+                    "d2h_bytes_per_step": 24},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": gemm_tflops / pk["bf16_sustained"], "traffic": None,
+                         "kernel": "gemm_tcgen05_kernel (all GEMM launches of the timed region, CUDA events)",
+                         "gemm_ms_per_step": gms.value / args.steps, "gemm_launches": int(gl.value),
+                         "issued_tf32_tflops": gemm_tflops * passes,
+                         "frac_issued_of_tf32_peak": gemm_tflops * passes / (pk["bf16_sustained"] / 2.0),
+                         "peak_source": pk["source"] + "; tf32 dense peak taken as bf16/2",
+                         "step_tflops": fpf * value / world / 1e12},
+            "final_stats": {"xent_per_frame": st[0] / max(1, st[1]), "frames": st[1]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                fps, threads, sample = cpu_reference_throughput(2, 6)
+                line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "reference", "sample": sample}
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % str(e)[:200]}
+        print(json.dumps(line))
+    if world > 1:
+        abi.check(L.tnb_comm_destroy(ctx))
+        dist.destroy_process_group()
+    return 0
+
+
+def host_stream(L, ctx):
+    s = C.c_void_p()
+    from tnet_b200 import abi
+    abi.check(L.tnb_ctx_stream(ctx, C.byref(s)))
+    return s.value
+
+
+if __name__ == "__main__":
+    sys.exit(main())

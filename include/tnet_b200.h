@@ -72,6 +72,12 @@ int tnb_ctx_free_memory(TnbContext *ctx, size_t *free_bytes, size_t *total_bytes
 /* number of kernels of THIS library launched through ctx since creation (graph replays included) */
 int tnb_ctx_launch_count(TnbContext *ctx, unsigned long long *launches);
 
+/* Per-kernel device timing of the GEMM launches (CUDA events on the ctx stream around every tcgen05 GEMM launched
+ * between begin and end): total milliseconds, launch count and algorithmic flops (2*M*N*K per launch).  This is what
+ * bench.py's roofline object is computed from. */
+int tnb_ctx_profile_begin(TnbContext *ctx);
+int tnb_ctx_profile_end(TnbContext *ctx, double *gemm_ms, unsigned long long *gemm_launches, double *gemm_flops);
+
 /* ---- memory (replaces cudaMallocPitch/cudaFree/cudaMemcpy2D/cudaMemset in cumatrix.tcc) ----------- */
 /* rows x cols fp32 (or any 4-byte type), zero-filled like CuMatrix::Init (cumatrix.tcc:16-34);
  * *stride_elems is a multiple of 32 elements (128 B). */

@@ -71,6 +71,11 @@ struct TnbContext_ {
   // column-sum scratch (bias gradient before the fused update)
   float *vec_scratch = nullptr;
   int vec_cap = 0;
+  // GEMM profiling (tnb_ctx_profile_begin/end)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;  // start/stop pairs
+  size_t prof_used = 0;
+  double prof_flops = 0.0;
   // data-parallel
   void *nccl_comm = nullptr;
   int rank = 0, world = 1;

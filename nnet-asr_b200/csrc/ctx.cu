@@ -156,6 +156,7 @@ int tnb_ctx_destroy(TnbContext *ctx) {
   if (ctx->row_scratch) cudaFree(ctx->row_scratch);
   if (ctx->row_match) cudaFree(ctx->row_match);
   if (ctx->vec_scratch) cudaFree(ctx->vec_scratch);
+  for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_compute);
   cudaEventDestroy(ctx->ev_comm);
   cudaStreamDestroy(ctx->stream);
@@ -186,6 +187,30 @@ int tnb_ctx_free_memory(TnbContext *ctx, size_t *fr, size_t *tot) {
   return TNB_OK;
 }
 int tnb_ctx_launch_count(TnbContext *ctx, unsigned long long *n) { TNB_ARG(ctx && n, "null"); *n = ctx->launches; return TNB_OK; }
+
+int tnb_ctx_profile_begin(TnbContext *ctx) {
+  TNB_ARG(ctx, "null");
+  ctx->profiling = true;
+  ctx->prof_used = 0;
+  ctx->prof_flops = 0.0;
+  return TNB_OK;
+}
+int tnb_ctx_profile_end(TnbContext *ctx, double *gemm_ms, unsigned long long *gemm_launches, double *gemm_flops) {
+  TNB_ARG(ctx && gemm_ms && gemm_launches && gemm_flops, "null");
+  ctx->profiling = false;
+  TNB_CUDA(cudaStreamSynchronize(ctx->stream));
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+    float t = 0.0f;
+    TNB_CUDA(cudaEventElapsedTime(&t, ctx->prof_events[i], ctx->prof_events[i + 1]));
+    ms += t;
+  }
+  *gemm_ms = ms;
+  *gemm_launches = ctx->prof_used / 2;
+  *gemm_flops = ctx->prof_flops;
+  ctx->prof_used = 0;
+  return TNB_OK;
+}
 
 int tnb_malloc_pitch(TnbContext *ctx, void **ptr, int *stride_elems, int rows, int cols) {
   TNB_ARG(ctx && ptr && stride_elems, "null");

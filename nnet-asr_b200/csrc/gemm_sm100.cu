@@ -429,7 +429,21 @@ static int launch_tc(TnbContext *ctx, const CUtensorMap &tmA, const CUtensorMap 
     attr_set[ctx->device & 63] = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->profiling) {
+    while (ctx->prof_events.size() < ctx->prof_used + 2) {
+      cudaEvent_t e;
+      TNB_CUDA(cudaEventCreate(&e));
+      ctx->prof_events.push_back(e);
+    }
+    e0 = ctx->prof_events[ctx->prof_used];
+    e1 = ctx->prof_events[ctx->prof_used + 1];
+    ctx->prof_used += 2;
+    ctx->prof_flops += 2.0 * (double)M * (double)N * (double)K;
+    TNB_CUDA(cudaEventRecord(e0, ctx->stream));
+  }
   kern<<<grid, 192, Cfg::SMEM_BYTES, ctx->stream>>>(tmA, tmB, M, N, K, ep);
+  if (e1) TNB_CUDA(cudaEventRecord(e1, ctx->stream));
   TNB_LAUNCHED(ctx);
   return TNB_OK;
 }

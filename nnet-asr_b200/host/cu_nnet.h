@@ -213,6 +213,12 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     rOut << vec;
     rOut << std::endl;
   }
+  /// set the parameters from host memory; Wt is the on-disk layout [nOutputs x nInputs]
+  void SetParams(const BfMatrix &Wt, const BfVector &bias) {
+    if (Wt.Rows() != GetNOutputs() || Wt.Cols() != GetNInputs() || bias.Dim() != GetNOutputs()) Error("SetParams: wrong dimensions");
+    mLinearity.CopyFrom(BfMatrix(Wt, TRANS));
+    mBias.CopyFrom(bias);
+  }
   const CuMatrix<BaseFloat> &Linearity() const { return mLinearity; }
   const CuVector<BaseFloat> &Bias() const { return mBias; }
 

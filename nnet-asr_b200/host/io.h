@@ -1,0 +1,471 @@
+// io.h — the file-side call surface the trainers' main() functions use: option parsing, feature lists and labels.
+//
+// Mirrors (formats, flag grammar and error behaviour only — reference paths under src/KaldiLib):
+//   UserInterface      UserInterface.cc:121-267 (option map "-X fmt KEY", --KEY=VAL, -C config, -A, key normalisation),
+//                      :466-490 (GetParam prefix stripping), :567-585 (GetBool), CheckCommandLineParamUse
+//   FeatureRepository  Features.cc: SCP entries "logical=physical[first,last]", HTK 12-byte header, byte swapping
+//                      (NATURALREADORDER), STARTFRMEXT / ENDFRMEXT frame replication (:776-849)
+//   LabelRepository    Labels.cc:44-227 (MLF records, time -> frame rounding, output label map, one-hot rows)
+// Not built (outside the hot path, reported as errors when requested): compressed (_C) / CRC HTK files, derivative
+// expansion (TARGETKIND with _D/_A/_T), CMEAN/VARSCALE normalisation files.
+#ifndef TNETB200_IO_H_
+#define TNETB200_IO_H_
+
+#include <stdint.h>
+#include <strings.h>
+
+#include <map>
+
+#include "tnet_base.h"
+
+namespace TNet {
+
+// ------------------------------------------------------------------------------------------ UserInterface
+class UserInterface {
+ public:
+  struct ValueRecord {
+    std::string mValue;
+    char mOption;
+    bool mRead;
+  };
+
+  static std::string NormalizeKey(const char *name) {
+    std::string key;
+    for (const char *p = name; *p; ++p)
+      if (*p != '-' && *p != '_') key.push_back((char)toupper(*p));
+    return key;
+  }
+  void InsertConfigParam(const char *pParamName, const char *value, int optionChar) {
+    ValueRecord &r = mMap[NormalizeKey(pParamName)];
+    r.mValue = value;
+    r.mRead = false;
+    r.mOption = (char)optionChar;
+  }
+  /// "KEY = VALUE" lines, '#' comments
+  void ReadConfig(const char *pFileName) {
+    std::ifstream in(pFileName);
+    if (!in.good()) throw std::runtime_error(std::string("Cannot open input config file ") + pFileName);
+    std::string line;
+    int line_no = 0;
+    while (std::getline(in, line)) {
+      line_no++;
+      size_t hash = line.find('#');
+      if (hash != std::string::npos) line.erase(hash);
+      size_t b = line.find_first_not_of(" \t\r");
+      if (b == std::string::npos) continue;
+      size_t eq = line.find('=');
+      if (eq == std::string::npos) {
+        std::ostringstream os;
+        os << "Character '=' expected (" << pFileName << ":" << line_no << ")";
+        throw std::runtime_error(os.str());
+      }
+      std::string key = Trim(line.substr(0, eq)), val = Trim(line.substr(eq + 1));
+      if (val.size() >= 2 && (val[0] == '"' || val[0] == '\'') && val[val.size() - 1] == val[0]) val = val.substr(1, val.size() - 2);
+      InsertConfigParam(key.c_str(), val.c_str(), 'C');
+    }
+  }
+  /// pOptionMapping: " -x fmt KEY[=VAL]" entries; fmt 'n' = flag, 'r'/'l'/'o' = takes an argument ('l' accumulates a list)
+  int ParseOptions(int argc, char *argv[], const char *pOptionMapping, const char *pToolName) {
+    struct Opt { char fmt; std::string key, val; };
+    std::map<char, Opt> opts;
+    {
+      std::istringstream is(pOptionMapping);
+      std::string tok;
+      while (is >> tok) {
+        if (tok.size() != 2 || tok[0] != '-') throw std::runtime_error("Fatal: malformed option map");
+        Opt o;
+        std::string fmt, key;
+        if (!(is >> fmt >> key)) throw std::runtime_error("Fatal: Unexpected end of optionMap string");
+        o.fmt = fmt[0];
+        size_t eq = key.find('=');
+        o.key = key.substr(0, eq);
+        o.val = eq == std::string::npos ? "TRUE" : key.substr(eq + 1);
+        opts[tok[1]] = o;
+      }
+    }
+    auto is_option = [](const char *s) { return s[0] == '-' && (isalpha((unsigned char)s[1]) || s[1] == '-'); };
+    for (int i = 1; i < argc; i++) {  // -A : echo the command line
+      if (!strcmp(argv[i], "--")) break;
+      if (!strcmp(argv[i], "-A")) {
+        for (int k = 0; k < argc; k++) {
+          if (strchr(argv[k], ' ') || strchr(argv[k], '*')) std::cout << '\'' << argv[k] << '\'' << " "; else std::cout << argv[k] << " ";
+        }
+        std::cout << std::endl;
+        break;
+      }
+    }
+    for (int i = 1; i < argc; i++) {  // -C config files first
+      if (!strcmp(argv[i], "--")) break;
+      if (argv[i][0] != '-' || argv[i][1] != 'C') continue;
+      if (argv[i][2] != '\0') ReadConfig(argv[i] + 2);
+      else if (i + 1 < argc && !is_option(argv[i + 1])) ReadConfig(argv[++i]);
+      else throw std::runtime_error("Config file name expected after option '-C'");
+    }
+    for (int i = 1; i < argc; i++) {  // --KEY=VAL
+      if (!strcmp(argv[i], "--")) break;
+      if (argv[i][0] != '-' || argv[i][1] != '-') continue;
+      std::string s(argv[i] + 2);
+      size_t eq = s.find('=');
+      if (eq == std::string::npos) throw std::runtime_error(std::string("Character '=' expected after option '") + argv[i] + "'");
+      InsertConfigParam((std::string(pToolName) + ":" + s.substr(0, eq)).c_str(), s.substr(eq + 1).c_str(), '-');
+    }
+    int optind = 1;
+    std::map<char, bool> seen;
+    for (; optind < argc && is_option(argv[optind]); optind++) {
+      char opt = argv[optind][1];
+      const char *optarg = argv[optind][2] != '\0' ? argv[optind] + 2 : NULL;
+      if (opt == '-' && !optarg) return optind + 1;
+      if (opt == '-') continue;
+      if (opt == 'C') { if (!optarg) optind++; continue; }
+      if (opt == 'A') continue;
+      std::map<char, Opt>::iterator it = opts.find(opt);
+      if (it == opts.end()) throw std::runtime_error(std::string("Invalid command line option '-") + opt + "'");
+      std::string param = std::string(pToolName) + ":" + it->second.key;
+      if (it->second.fmt == 'n') {
+        if (optarg) throw std::runtime_error(std::string("Unexpected argument '") + optarg + "' after option '-" + opt + "'");
+        InsertConfigParam(param.c_str(), it->second.val.c_str(), opt);
+      } else {
+        if (!optarg) {
+          if (optind + 1 == argc || is_option(argv[optind + 1]))
+            throw std::runtime_error(std::string("Argument 1 of option '-") + opt + "' expected");
+          optarg = argv[++optind];
+        }
+        std::string v(optarg);
+        if (it->second.fmt == 'l' && seen[opt]) v = std::string(GetStr(param.c_str(), "")) + "," + v;
+        seen[opt] = true;
+        InsertConfigParam(param.c_str(), v.c_str(), opt);
+      }
+    }
+    for (int i = optind; i < argc; i++)
+      if (is_option(argv[i])) throw std::runtime_error(std::string("No option expected after first non-option argument '") + argv[optind] + "'");
+    return optind;
+  }
+  /// try the full name, then strip everything up to each ':' in turn (UserInterface.cc:466-490)
+  ValueRecord *GetParam(const char *pParamName) {
+    std::string name = NormalizeKeepColon(pParamName);
+    const char *p = name.c_str();
+    while (true) {
+      std::map<std::string, ValueRecord>::iterator it = mMap.find(p);
+      if (it != mMap.end()) { it->second.mRead = true; return &it->second; }
+      p = strchr(p, ':');
+      if (!p) return NULL;
+      p++;
+    }
+  }
+  const char *GetStr(const char *name, const char *dflt) { ValueRecord *v = GetParam(name); return v ? v->mValue.c_str() : dflt; }
+  long GetInt(const char *name, long dflt) {
+    ValueRecord *v = GetParam(name);
+    if (!v) return dflt;
+    char *end;
+    long r = strtol(v->mValue.c_str(), &end, 0);
+    if (v->mValue.empty() || *end) throw std::runtime_error(std::string("Integer number expected for ") + name + " but found '" + v->mValue + "'");
+    return r;
+  }
+  float GetFlt(const char *name, float dflt) {
+    ValueRecord *v = GetParam(name);
+    if (!v) return dflt;
+    char *end;
+    double r = strtod(v->mValue.c_str(), &end);
+    if (v->mValue.empty() || *end) throw std::runtime_error(std::string("Decimal number expected for ") + name + " but found '" + v->mValue + "'");
+    return (float)r;
+  }
+  bool GetBool(const char *name, bool dflt) {
+    ValueRecord *v = GetParam(name);
+    if (!v) return dflt;
+    const char *val = v->mValue.c_str();
+    if (!strcasecmp(val, "TRUE") || !strcmp(val, "T")) return true;
+    if (strcasecmp(val, "FALSE") && strcmp(val, "F"))
+      throw std::runtime_error(std::string("TRUE or FALSE expected for ") + name + " but found '" + val + "'");
+    return false;
+  }
+  /// unknown / unused command line parameters are an error (TNetCu.cc:261)
+  void CheckCommandLineParamUse() {
+    for (std::map<std::string, ValueRecord>::iterator it = mMap.begin(); it != mMap.end(); ++it) {
+      if (!it->second.mRead && it->second.mOption != 'C') {
+        std::string what = it->second.mOption == '-' ? std::string("Unexpected command line parameter ") + it->first
+                                                     : std::string("Ignoring option '-") + it->second.mOption + "'";
+        if (it->second.mOption == '-') throw std::runtime_error(what);
+        Warning(what);
+      }
+    }
+  }
+  void PrintConfig(std::ostream &out) {
+    out << "Configuration Parameters[" << mMap.size() << "]\n";
+    for (std::map<std::string, ValueRecord>::iterator it = mMap.begin(); it != mMap.end(); ++it)
+      out << (it->second.mRead ? " " : "#") << std::setw0(it->first) << " = " << it->second.mValue << "   # -" << it->second.mOption << "\n";
+  }
+
+ private:
+  static std::string Trim(const std::string &s) {
+    size_t b = s.find_first_not_of(" \t\r"), e = s.find_last_not_of(" \t\r");
+    return b == std::string::npos ? std::string() : s.substr(b, e - b + 1);
+  }
+  static std::string NormalizeKeepColon(const char *name) {
+    std::string key;
+    for (const char *p = name; *p; ++p)
+      if (*p != '-' && *p != '_') key.push_back((char)toupper(*p));
+    return key;
+  }
+  std::map<std::string, ValueRecord> mMap;
+};
+
+}  // namespace TNet
+
+// tiny helper so PrintConfig compiles without <iomanip> gymnastics
+namespace std {
+inline const std::string &setw0(const std::string &s) { return s; }
+}
+
+namespace TNet {
+
+/// dir/base.ext from an input name (Common.cc:118-180): dir and ext replace the input's, "/./" keeps the tail as base
+inline void MakeHtkFileName(char *pOut, const char *inFileName, const char *out_dir, const char *out_ext) {
+  if (!strcmp(inFileName, "-")) { strcpy(pOut, "-"); return; }
+  const char *base = strrchr(inFileName, '/');
+  base = base ? base + 1 : inFileName;
+  const char *bend = NULL;
+  if (out_ext) bend = strrchr(base, '.');
+  if (!bend) bend = base + strlen(base);
+  const char *keep = strstr(inFileName, "/./");
+  if (keep) base = keep + 3;
+  std::string out;
+  if (out_dir) {
+    if (*out_dir) { out += out_dir; out += "/"; }
+    out.append(base, bend - base);
+  } else {
+    out.append(inFileName, bend - inFileName);
+  }
+  if (out_ext && *out_ext) { out += "."; out += out_ext; }
+  strcpy(pOut, out.c_str());
+}
+
+// ------------------------------------------------------------------------------------------ FeatureRepository
+struct HtkHeader {
+  int32_t mNSamples;
+  int32_t mSamplePeriod;
+  int16_t mSampleSize;
+  uint16_t mSampleKind;
+};
+
+class FeatureRepository {
+ public:
+  struct FileRecord {
+    std::string mLogical, mPhysical;
+    int mFirst, mLast;  // -1 = whole file
+    const std::string &Logical() const { return mLogical; }
+    const std::string &Physical() const { return mPhysical; }
+  };
+  FeatureRepository() : mSwap(true), mStartExt(0), mEndExt(0), mTrace(0), mPos(0) { memset(&mHeader, 0, sizeof(mHeader)); }
+
+  void Init(bool swap, int extLeft, int extRight, int targetKind, int derivOrder, int *pDerivWinLen, const char *pCmnPath, const char *pCmnMask,
+            const char *pCvnPath, const char *pCvnMask, const char *pCvgFile) {
+    (void)pDerivWinLen; (void)pCmnPath; (void)pCvnPath;
+    mSwap = swap; mStartExt = extLeft; mEndExt = extRight;
+    if (derivOrder > 0 || (targetKind & 0x3F00 & ~0)) {
+      if (derivOrder > 0) Error("TARGETKIND with derivatives (_D/_A/_T) is not built into the B200 hot path");
+    }
+    if (pCmnMask || pCvnMask || pCvgFile) Error("CMEAN/VARSCALE normalisation files are not built into the B200 hot path (use a <bias>/<window> transform)");
+  }
+  void Trace(int t) { mTrace = t; }
+  void AddFile(const std::string &entry) { mFiles.push_back(ParseEntry(entry)); }
+  void AddFileList(const char *pFileName) {
+    std::ifstream in(pFileName);
+    if (!in.good()) Error(std::string("Cannot open script file ") + pFileName);
+    std::string line;
+    while (std::getline(in, line)) {
+      size_t b = line.find_first_not_of(" \t\r"), e = line.find_last_not_of(" \t\r");
+      if (b == std::string::npos) continue;
+      AddFile(line.substr(b, e - b + 1));
+    }
+  }
+  size_t QueueSize() const { return mFiles.size(); }
+  void Rewind() { mPos = 0; }
+  void MoveNext() { mPos++; }
+  bool EndOfList() const { return mPos >= mFiles.size(); }
+  const FileRecord &Current() const { return mFiles[mPos]; }
+  const HtkHeader &CurrentHeader() const { return mHeader; }
+
+  /// read the current file; STARTFRMEXT/ENDFRMEXT rows replicate the first/last frame
+  void ReadFullMatrix(Matrix<BaseFloat> &rMatrix) {
+    const FileRecord &rec = Current();
+    FILE *f = fopen(rec.mPhysical.c_str(), "rb");
+    if (!f) Error(std::string("Cannot open feature file: '") + rec.mPhysical + "'");
+    unsigned char hb[12];
+    if (fread(hb, 1, 12, f) != 12) { fclose(f); Error(std::string("Invalid HTK header in feature file: '") + rec.mPhysical + "'"); }
+    HtkHeader h;
+    memcpy(&h.mNSamples, hb, 4); memcpy(&h.mSamplePeriod, hb + 4, 4); memcpy(&h.mSampleSize, hb + 8, 2); memcpy(&h.mSampleKind, hb + 10, 2);
+    if (mSwap) { h.mNSamples = Swap32(h.mNSamples); h.mSamplePeriod = Swap32(h.mSamplePeriod); h.mSampleSize = (int16_t)Swap16((uint16_t)h.mSampleSize); h.mSampleKind = Swap16(h.mSampleKind); }
+    if (h.mSampleKind & 02000) { fclose(f); Error(std::string("Compressed (_C) HTK files are not built into the B200 hot path: ") + rec.mPhysical); }
+    if (h.mNSamples <= 0 || h.mSampleSize <= 0 || h.mSampleSize % 4 != 0) { fclose(f); Error(std::string("Invalid HTK header in feature file: '") + rec.mPhysical + "'"); }
+    const int dim = h.mSampleSize / 4;
+    int first = rec.mFirst < 0 ? 0 : rec.mFirst, last = rec.mLast < 0 ? h.mNSamples - 1 : rec.mLast;
+    if (first > last || last >= h.mNSamples) { fclose(f); Error(std::string("Frame range out of file: ") + rec.mLogical); }
+    const int n = last - first + 1;
+    std::vector<float> buf((size_t)n * dim);
+    fseek(f, 12 + (long)first * h.mSampleSize, SEEK_SET);
+    if (fread(buf.data(), 4, buf.size(), f) != buf.size()) { fclose(f); Error(std::string("Cannot read feature file: '") + rec.mPhysical + "'"); }
+    fclose(f);
+    if (mSwap) {
+      uint32_t *u = reinterpret_cast<uint32_t *>(buf.data());
+      for (size_t i = 0; i < buf.size(); i++) u[i] = (uint32_t)Swap32((int32_t)u[i]);
+    }
+    rMatrix.Init(n + mStartExt + mEndExt, dim);
+    for (int r = 0; r < n + mStartExt + mEndExt; r++) {
+      int src = r - mStartExt;
+      src = src < 0 ? 0 : (src >= n ? n - 1 : src);
+      memcpy(rMatrix.pRowData(r), buf.data() + (size_t)src * dim, sizeof(float) * dim);
+    }
+    mHeader = h;
+    mHeader.mNSamples = n;
+    if (mTrace & 1) std::cout << "[" << rec.mLogical << " " << n << "frm]" << std::flush;
+  }
+  static int ReadParmKind(const char *str, bool) {
+    static const char *names[] = {"WAVEFORM", "LPC", "LPREFC", "LPCEPSTRA", "LPDELCEP", "IREFC", "MFCC", "FBANK", "MELSPEC", "USER", "DISCRETE", "PLP", "ANON"};
+    std::string s(str);
+    size_t us = s.find('_');
+    std::string base = s.substr(0, us);
+    int kind = -1;
+    for (int i = 0; i < 13; i++)
+      if (!strcasecmp(base.c_str(), names[i])) kind = i == 12 ? 0x3F : i;
+    if (kind < 0) return -1;
+    while (us != std::string::npos) {
+      size_t nx = s.find('_', us + 1);
+      std::string q = s.substr(us + 1, nx == std::string::npos ? std::string::npos : nx - us - 1);
+      if (q == "E") kind |= 0100; else if (q == "N") kind |= 0200; else if (q == "D") kind |= 0400; else if (q == "A") kind |= 01000;
+      else if (q == "C") kind |= 02000; else if (q == "Z") kind |= 04000; else if (q == "K") kind |= 010000; else if (q == "0") kind |= 020000;
+      else if (q == "V") kind |= 040000; else if (q == "T") kind |= 0100000; else return -1;
+      us = nx;
+    }
+    return kind;
+  }
+
+ private:
+  static int32_t Swap32(int32_t v) { uint32_t u = (uint32_t)v; return (int32_t)((u >> 24) | ((u >> 8) & 0xFF00) | ((u << 8) & 0xFF0000) | (u << 24)); }
+  static uint16_t Swap16(uint16_t v) { return (uint16_t)((v >> 8) | (v << 8)); }
+  static FileRecord ParseEntry(const std::string &e) {
+    FileRecord r;
+    r.mFirst = r.mLast = -1;
+    std::string s = e;
+    size_t eq = s.find('=');
+    if (eq != std::string::npos) { r.mLogical = s.substr(0, eq); s = s.substr(eq + 1); }
+    size_t lb = s.rfind('[');
+    if (lb != std::string::npos && !s.empty() && s[s.size() - 1] == ']') {
+      int a = -1, b = -1;
+      if (sscanf(s.c_str() + lb, "[%d,%d]", &a, &b) == 2) { r.mFirst = a; r.mLast = b; s = s.substr(0, lb); }
+    }
+    r.mPhysical = s;
+    if (r.mLogical.empty()) r.mLogical = s;
+    return r;
+  }
+  bool mSwap;
+  int mStartExt, mEndExt, mTrace;
+  std::vector<FileRecord> mFiles;
+  size_t mPos;
+  HtkHeader mHeader;
+};
+
+// ------------------------------------------------------------------------------------------ LabelRepository
+class LabelRepository {
+ public:
+  LabelRepository() : mTrace(0) {}
+  void Trace(int t) { mTrace = t; }
+  void Init(const char *pLabelMlfFile, const char *pOutputLabelMapFile, const char *pLabelDir, const char *pLabelExt) {
+    (void)pLabelDir;
+    mExt = pLabelExt ? pLabelExt : "lab";
+    ReadOutputLabelMap(pOutputLabelMapFile);
+    std::ifstream in(pLabelMlfFile);
+    if (!in.good()) Error(std::string("Cannot open Label MLF file: ") + pLabelMlfFile);
+    std::string line, key;
+    bool in_rec = false;
+    while (std::getline(in, line)) {
+      if (!line.empty() && line[line.size() - 1] == '\r') line.erase(line.size() - 1);
+      if (!in_rec) {
+        if (line.empty() || line[0] == '#') continue;
+        if (line[0] == '"') {
+          size_t q = line.rfind('"');
+          key = BaseKey(line.substr(1, q > 0 ? q - 1 : std::string::npos));
+          mRecords[key].clear();
+          in_rec = true;
+        }
+      } else {
+        if (line == ".") { in_rec = false; continue; }
+        mRecords[key].push_back(line);
+      }
+    }
+  }
+  size_t NOutputs() const { return mLabelMap.size(); }
+
+  /// per-frame class ids (-1 = unlabelled); times are divided by sourceRate with round-half-up (Labels.cc:111-112)
+  void GenLabelIds(std::vector<int> &ids, size_t nFrames, size_t sourceRate, const char *pFeatureLogical) {
+    if (nFrames < 1) KALDI_ERR << "Number of frames:" << nFrames << " is lower than 1!!!\n" << pFeatureLogical;
+    std::map<std::string, std::vector<std::string> >::iterator rec = mRecords.find(BaseKey(pFeatureLogical));
+    if (rec == mRecords.end()) Error(std::string("Cannot open label MLF record: ") + BaseKey(pFeatureLogical) + "." + mExt);
+    ids.assign(nFrames, -1);
+    size_t trunc_frames = 0;
+    for (size_t l = 0; l < rec->second.size(); l++) {
+      const std::string &line = rec->second[l];
+      if (line.empty() || line[0] == '#') continue;
+      std::istringstream iss(line);
+      unsigned long long beg, end;
+      std::string state;
+      if (!(iss >> beg)) KALDI_ERR << "Cannot parse column 1 (begin)\nline: " << line << "\nfile: " << pFeatureLogical << "\n";
+      if (!(iss >> end)) KALDI_ERR << "Cannot parse column 2 (end)\nline: " << line << "\nfile: " << pFeatureLogical << "\n";
+      if (!(iss >> state)) KALDI_ERR << "Cannot parse column 3 (state_tag)\nline: " << line << "\nfile: " << pFeatureLogical << "\n";
+      beg = (beg + sourceRate / 2) / sourceRate;
+      end = (end + sourceRate / 2) / sourceRate;
+      std::map<std::string, int>::iterator it = mLabelMap.find(state);
+      if (it == mLabelMap.end()) Error(std::string("Unknown state tag: '") + state + "' file:'" + pFeatureLogical);
+      for (unsigned long long fr = beg; fr < end; fr++) {
+        if (fr >= nFrames) { trunc_frames++; continue; }
+        if (ids[fr] != -1) {
+          std::ostringstream os;
+          os << "Frame already assigned to other state, " << " file: " << pFeatureLogical << " frame: " << fr << " nframes: " << nFrames
+             << " previously assigned to: (" << ids[fr] << ") now should be assigned to: " << state << "(" << it->second << ")\n";
+          Error(os.str());
+        }
+        ids[fr] = it->second;
+      }
+    }
+    if (trunc_frames > 10) {
+      std::ostringstream os;
+      os << "Truncated frames: " << trunc_frames << " Check sourcerate in features and validity of labels\n";
+      Warning(os.str());
+    }
+  }
+  /// dense one-hot rows, as the reference builds them on the host (Labels.cc:44-190)
+  void GenDesiredMatrix(BfMatrix &rDesired, size_t nFrames, size_t sourceRate, const char *pFeatureLogical) {
+    std::vector<int> ids;
+    GenLabelIds(ids, nFrames, sourceRate, pFeatureLogical);
+    rDesired.Init(nFrames, mLabelMap.size());
+    for (size_t i = 0; i < nFrames; i++)
+      if (ids[i] >= 0) rDesired(i, ids[i]) = 1.0f;
+  }
+
+ private:
+  void ReadOutputLabelMap(const char *file) {
+    std::ifstream in(file);
+    if (!in.good()) Error(std::string("Cannot open OutputLabelMapFile: ") + file);
+    std::string tag;
+    int i = 0;
+    while (in >> tag) {
+      if (mLabelMap.find(tag) != mLabelMap.end()) Error(std::string("Duplicate tag in OutputLabelMapFile: ") + tag);
+      mLabelMap[tag] = i++;
+    }
+    if (mLabelMap.empty()) Error(std::string("Empty OutputLabelMapFile: ") + file);
+  }
+  /// records are matched on the file's base name without directory and extension ("*/utt.lab" patterns)
+  static std::string BaseKey(const std::string &name) {
+    size_t sl = name.rfind('/');
+    std::string b = sl == std::string::npos ? name : name.substr(sl + 1);
+    size_t dot = b.rfind('.');
+    if (dot != std::string::npos) b.erase(dot);
+    return b;
+  }
+  std::map<std::string, std::vector<std::string> > mRecords;
+  std::map<std::string, int> mLabelMap;
+  std::string mExt;
+  int mTrace;
+};
+
+}  // namespace TNet
+#endif

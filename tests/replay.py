@@ -54,3 +54,40 @@ def replay_mlp(g, make_net, make_cache, srand48, cv=False):
             net.train_bunch(Fb, Db, cv)
             nb += 1
     return net, nb, perms
+
+
+def replay_rbm(g, make_rbm, make_cache, srand48):
+    """TRbmCu main loop (src/TRbmCu.cc:255-356).  make_rbm(Wt, vb, hb, vis_gauss, hid_gauss, bunch, lr, mmt, wc) must seed
+    its generator from lrand48() at construction (after srand48)."""
+    ctx, bunch, cache, seed, vis_gauss, hid_gauss = [int(v) for v in g["cfg"]]
+    lr, mmt, wc = [float(v) for v in g["hyper"]]
+    srand48(seed)
+    rbm = make_rbm(g["init_Wt"], g["init_vb"], g["init_hb"], vis_gauss, hid_gauss, bunch, lr, mmt, wc)
+    cache = (cache // bunch) * bunch
+    c = make_cache(cache, bunch)
+    it = iter(utterances(g))
+    pending = next(it, None)
+    nb = 0
+    while pending is not None:
+        while not c.full() and pending is not None:
+            c.add(pending[0], np.zeros((pending[0].shape[0], 1), np.float32))   # "fake the labels" TRbmCu.cc:313
+            pending = next(it, None)
+        c.randomize()
+        while not c.empty():
+            Fb, _ = c.get_bunch()
+            rbm.cd1(Fb)
+            nb += 1
+    return rbm, nb
+
+
+def rnn_layers(g, prefix="init"):
+    ctx, bptt, nin, H, n_out = [int(v) for v in g["cfg"]]
+    return [("recurrent", g[prefix + "_Wr"], g[prefix + "_br"], nin), ("affine", g[prefix + "_Wo"], g[prefix + "_bo"]), ("softmax", n_out)]
+
+
+def rnn_utterances(g):
+    ctx = int(g["cfg"][0])
+    pos = 0
+    for T in g["lengths"]:
+        yield F.splice(g["feats"][pos:pos + T], ctx), g["labels"][pos:pos + T].astype(np.int32)
+        pos += T
