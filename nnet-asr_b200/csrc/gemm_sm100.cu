@@ -13,9 +13,11 @@
 //     contracted over their ROW index (W in forward, X and E in dW) are loaded as MN-major tiles
 //     (32-float column chunks) so no transposed copy ever exists in HBM.
 //   * tcgen05.mma.kind::tf32, M=128, N=BN, K=8 per instruction, accumulator in TMEM (BN columns).
-//   * 3xTF32 (default): converter warps split every staged tile into hi = rna_tf32(x) (in place) and
-//     lo = rna_tf32(x - hi) (second buffer); per K-step the MMA warp issues lo*hi, hi*lo, hi*hi.
-//   * warp roles: warp0 = TMA producer, warp1 = TMEM alloc + MMA issue, warps2-5 = converters, then epilogue
+//   * 3xTF32 (default): the tensor core reads fp32 words as tf32 by TRUNCATION (measured on B200: tools/probe_tf32.py,
+//     profiles/r01_tf32_probe.txt), so the staged fp32 tile itself is the `hi` operand; converter warps only write
+//     lo = rna_tf32(x - trunc_tf32(x)) into a second buffer (x - trunc(x) is exact in fp32).  Per K-step the MMA warp
+//     issues lo*hi, hi*lo, hi*hi.
+//   * warp roles: warp0 = TMA producer, warp1 = TMEM alloc + MMA issue, warps2-9 = converters, then epilogue
 //     (tcgen05.ld 32x32b -> registers -> fused epilogue -> global).
 //   * every mbarrier spin is bounded: a protocol bug traps instead of hanging the GPU.
 #include "common.cuh"
@@ -25,6 +27,9 @@ namespace tnb {
 
 constexpr int BM = 128;
 constexpr int BK = 32;  // fp32 elements per K block = 128 bytes = one swizzle span
+constexpr int CONV_WARPS = 8;                       // converter / epilogue warps
+constexpr int CONV_THREADS = CONV_WARPS * 32;
+constexpr int GEMM_THREADS = 64 + CONV_THREADS;     // + TMA warp + MMA warp
 
 
 // ----------------------------------------------------------------------------------------------- PTX
@@ -111,14 +116,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-// fp32 -> (hi, lo) tf32 pair.  hi = round-to-nearest tf32, lo = rna_tf32(x - hi) (x - hi is exact in fp32).
-__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  float r = x - hi;
+// low part of the 3xTF32 split: hi is what the tensor core sees when it reads x (the top 19 bits), lo = rna_tf32(x - hi).
+// Inf/NaN stay in hi only.
+__device__ __forceinline__ float lo_tf32(float x) {
+  const uint32_t u = __float_as_uint(x);
+  const float r = x - __uint_as_float(u & 0xFFFFE000u);
+  uint32_t l;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
-  lo = ((h & 0x7F800000u) == 0x7F800000u) ? 0.0f : __uint_as_float(l);  // inf/nan: keep them in hi only
+  return ((u & 0x7F800000u) == 0x7F800000u) ? 0.0f : __uint_as_float(l);
 }
 
 __device__ __forceinline__ float sigmoidf_ref(float x) {
@@ -152,7 +157,7 @@ __device__ __forceinline__ float epi_one(const EpiParams &ep, float acc, float c
 // A_MN / B_MN: 0 = K-major tile (operand rows are the M/N index, contraction index contiguous),
 //              1 = MN-major tile (operand rows are the contraction index, M/N index contiguous).
 template <int BN, int A_MN, int B_MN, int NTERMS>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                     int K, EpiParams ep) {
   using Cfg = GemmCfg<BN, NTERMS>;
@@ -177,7 +182,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < STAGES; s++) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&conv_bar[s], 4);
+      mbar_init(&conv_bar[s], CONV_WARPS);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
@@ -262,27 +267,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
   } else {
     // ===================== converters (3xTF32) then epilogue =====================
-    const int ct = threadIdx.x - 64;  // 0..127
+    const int ct = threadIdx.x - 64;  // 0..CONV_THREADS-1
     if (NTERMS == 3) {
       for (int kb = 0; kb < num_kb; kb++) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
-        float4 *ah = (float4 *)stage_a(s), *al = (float4 *)stage_alo(s);
+        // A and B tiles are contiguous ([A_hi][B_hi] -> [A_lo][B_lo]): one linear pass, 16 B per thread per step
+        const float4 *src = (const float4 *)stage_a(s);
+        float4 *dst = (float4 *)stage_alo(s);
+        constexpr int NV = (Cfg::A_BYTES + Cfg::B_BYTES) / 16;
 #pragma unroll
-        for (int i = 0; i < Cfg::A_BYTES / 16 / 128; i++) {
-          float4 x = ah[ct + 128 * i], h, l;
-          split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y);
-          split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
-          ah[ct + 128 * i] = h; al[ct + 128 * i] = l;
-        }
-        float4 *bh = (float4 *)stage_b(s), *bl = (float4 *)stage_blo(s);
-#pragma unroll
-        for (int i = 0; i < Cfg::B_BYTES / 16 / 128; i++) {
-          float4 x = bh[ct + 128 * i], h, l;
-          split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y);
-          split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
-          bh[ct + 128 * i] = h; bl[ct + 128 * i] = l;
+        for (int i = 0; i < NV / CONV_THREADS; i++) {
+          const float4 x = src[ct + CONV_THREADS * i];
+          float4 l;
+          l.x = lo_tf32(x.x); l.y = lo_tf32(x.y); l.z = lo_tf32(x.z); l.w = lo_tf32(x.w);
+          dst[ct + CONV_THREADS * i] = l;
         }
         fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
@@ -292,12 +292,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ---- epilogue: TMEM -> registers -> fused ops -> global ----
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int q = warp & 3;              // TMEM lane quarter this warp may read
+    const int chalf = (warp - 2) >> 2;   // two warps share a quarter: even / odd 32-column chunks
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < M;
     const size_t crow = (size_t)row * (size_t)ep.ldc;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; c++) {
+    for (int c = chalf; c < BN / 32; c += CONV_WARPS / 4) {
       const int nc0 = n0 + c * 32;
       if (nc0 >= N) break;
       uint32_t v[32];
@@ -442,7 +443,7 @@ static int launch_tc(TnbContext *ctx, const CUtensorMap &tmA, const CUtensorMap 
     ctx->prof_flops += 2.0 * (double)M * (double)N * (double)K;
     TNB_CUDA(cudaEventRecord(e0, ctx->stream));
   }
-  kern<<<grid, 192, Cfg::SMEM_BYTES, ctx->stream>>>(tmA, tmB, M, N, K, ep);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(tmA, tmB, M, N, K, ep);
   if (e1) TNB_CUDA(cudaEventRecord(e1, ctx->stream));
   TNB_LAUNCHED(ctx);
   return TNB_OK;

@@ -192,7 +192,7 @@ class UserInterface {
   void PrintConfig(std::ostream &out) {
     out << "Configuration Parameters[" << mMap.size() << "]\n";
     for (std::map<std::string, ValueRecord>::iterator it = mMap.begin(); it != mMap.end(); ++it)
-      out << (it->second.mRead ? " " : "#") << std::setw0(it->first) << " = " << it->second.mValue << "   # -" << it->second.mOption << "\n";
+      out << (it->second.mRead ? " " : "#") << it->first << " = " << it->second.mValue << "   # -" << it->second.mOption << "\n";
   }
 
  private:
@@ -208,15 +208,6 @@ class UserInterface {
   }
   std::map<std::string, ValueRecord> mMap;
 };
-
-}  // namespace TNet
-
-// tiny helper so PrintConfig compiles without <iomanip> gymnastics
-namespace std {
-inline const std::string &setw0(const std::string &s) { return s; }
-}
-
-namespace TNet {
 
 /// dir/base.ext from an input name (Common.cc:118-180): dir and ext replace the input's, "/./" keeps the tail as base
 inline void MakeHtkFileName(char *pOut, const char *inFileName, const char *out_dir, const char *out_ext) {
