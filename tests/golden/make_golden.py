@@ -68,7 +68,7 @@ def pack_layers(prefix, layers, out):
             k += 1
 
 
-def run_mlp(case, cfg, impl, workdir):
+def run_mlp(case, cfg, impl, workdir, exe=None, save=True):
     rng = np.random.default_rng(cfg["seed"] + 1000)
     utts = F.gen_utterances(cfg["n_utt"], cfg["n_frames"], cfg["raw_dim"], cfg["n_out"], rng)
     paths = F.write_dataset(workdir, utts, cfg["n_out"], cfg["ctx"])
@@ -78,7 +78,8 @@ def run_mlp(case, cfg, impl, workdir):
     F.write_mlp(init, layers)
     layers = F.read_mlp(init)  # exactly what the binaries parse
     final = os.path.join(workdir, "final.nnet")
-    exe = os.path.join(REF, "TNet" if impl == "cpu" else "TNetCu")
+    if exe is None:
+        exe = os.path.join(REF, "TNet" if impl == "cpu" else "TNetCu")
     cmd = [exe, "-H", init, "-I", paths["mlf"], "-L", "*/", "-X", "lab", "-S", paths["scp"], "-m", paths["labelmap"],
            "-n", repr(cfg["lr"]), "--TARGETMMF=" + final, "--BUNCHSIZE=%d" % cfg["bunch"], "--CACHESIZE=%d" % cfg["cache"],
            "--RANDOMIZE=" + _b(cfg["randomize"]), "--SEED=%d" % cfg["seed"], "--FEATURETRANSFORM=" + paths["transform"],
@@ -92,6 +93,8 @@ def run_mlp(case, cfg, impl, workdir):
         raise RuntimeError("reference failed:\n" + res.stdout[-3000:])
     rep = parse_report(res.stdout)
     out_layers = F.read_mlp(final)
+    if not save:
+        return rep, out_layers, res.stdout
     names = list(utts.keys())
     data = dict(
         feats=np.concatenate([utts[n][0] for n in names]), labels=np.concatenate([utts[n][1] for n in names]),
@@ -119,7 +122,7 @@ RNN_CASES = {
 }
 
 
-def run_rbm(case, cfg, workdir):
+def run_rbm(case, cfg, workdir, exe=None, save=True):
     rng = np.random.default_rng(cfg["seed"] + 1000)
     utts = F.gen_utterances(cfg["n_utt"], cfg["n_frames"], cfg["raw_dim"], 4, rng)
     if cfg["vistype"] == "bern":  # visible probabilities in (0,1)
@@ -134,7 +137,7 @@ def run_rbm(case, cfg, workdir):
     F.write_mlp(init, [("rbm", cfg["vistype"], cfg["hidtype"], Wt, vb, hb)])
     L0 = F.read_mlp(init)[0]
     final = os.path.join(workdir, "final.rbm")
-    cmd = [os.path.join(REF, "TRbmCu"), "-H", init, "-S", paths["scp"], "-n", repr(cfg["lr"]), "--TARGETMMF=" + final,
+    cmd = [exe or os.path.join(REF, "TRbmCu"), "-H", init, "-S", paths["scp"], "-n", repr(cfg["lr"]), "--TARGETMMF=" + final,
            "--BUNCHSIZE=%d" % cfg["bunch"], "--CACHESIZE=%d" % cfg["cache"], "--RANDOMIZE=TRUE", "--SEED=%d" % cfg["seed"],
            "--FEATURETRANSFORM=" + paths["transform"], "--STARTFRMEXT=%d" % cfg["ctx"], "--ENDFRMEXT=%d" % cfg["ctx"],
            "--MOMENTUM=" + repr(cfg["mmt"]), "--WEIGHTCOST=" + repr(cfg["wc"])]
@@ -143,6 +146,8 @@ def run_rbm(case, cfg, workdir):
         raise RuntimeError("reference failed:\n" + res.stdout[-3000:])
     rep = parse_report(res.stdout)
     LF = F.read_mlp(final)[0]
+    if not save:
+        return rep, LF, res.stdout
     names = list(utts.keys())
     np.savez_compressed(
         os.path.join(OUT, "gpu_%s.npz" % case),
@@ -154,7 +159,7 @@ def run_rbm(case, cfg, workdir):
     print("gpu %s: %s" % (case, rep))
 
 
-def run_rnn(case, cfg, workdir):
+def run_rnn(case, cfg, workdir, exe=None, save=True):
     rng = np.random.default_rng(cfg["seed"] + 1000)
     utts = F.gen_utterances(cfg["n_utt"], cfg["n_frames"], cfg["raw_dim"], cfg["n_out"], rng)
     paths = F.write_dataset(workdir, utts, cfg["n_out"], cfg["ctx"])
@@ -169,7 +174,7 @@ def run_rnn(case, cfg, workdir):
     F.write_mlp(init, [("recurrent", Wr, br, nin), ("affine", Wo, bo), ("softmax", cfg["n_out"])])
     L = F.read_mlp(init)
     final = os.path.join(workdir, "final.rnn")
-    cmd = [os.path.join(REF, "TRecurrentCu"), "-H", init, "-I", paths["mlf"], "-L", "*/", "-X", "lab", "-S", paths["scp"],
+    cmd = [exe or os.path.join(REF, "TRecurrentCu"), "-H", init, "-I", paths["mlf"], "-L", "*/", "-X", "lab", "-S", paths["scp"],
            "-m", paths["labelmap"], "-n", repr(cfg["lr"]), "--TARGETMMF=" + final, "--BPTT=%d" % cfg["bptt"],
            "--FEATURETRANSFORM=" + paths["transform"], "--STARTFRMEXT=%d" % cfg["ctx"], "--ENDFRMEXT=%d" % cfg["ctx"]]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -177,6 +182,8 @@ def run_rnn(case, cfg, workdir):
         raise RuntimeError("reference failed:\n" + res.stdout[-3000:])
     rep = parse_report(res.stdout)
     LF = F.read_mlp(final)
+    if not save:
+        return rep, LF, res.stdout
     names = list(utts.keys())
     np.savez_compressed(
         os.path.join(OUT, "gpu_%s.npz" % case),

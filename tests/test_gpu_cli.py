@@ -1,0 +1,62 @@
+"""Drop-in binaries: nnet-asr_b200/bin/{TNetCu,TRbmCu,TRecurrentCu} run with the reference's command lines on the
+files the goldens were produced from, and must reproduce what the reference binaries wrote (network file, report line)."""
+import importlib.util
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "nnet-asr_b200", "bin")
+GOLD = os.path.join(ROOT, "tests", "golden")
+spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+MG = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(MG)
+
+
+@pytest.mark.parametrize("case", ["mlp_small", "mlp_mmt_wide", "mlp_bigbunch"])
+def test_tnetcu_binary_reproduces_reference(case):
+    g = np.load(os.path.join(GOLD, "gpu_%s.npz" % case))
+    with tempfile.TemporaryDirectory() as d:
+        rep, layers, out = MG.run_mlp(case, MG.MLP_CASES[case], "gpu", d, exe=os.path.join(BIN, "TNetCu"), save=False)
+    assert "===== TNET TRAINING STARTED =====" in out and "[FPS:" in out and "-- TR Xent:" in out
+    assert rep["frames"] == int(g["ref_frames"])
+    assert abs(rep["err"] - float(g["ref_err"])) <= 1e-4 * abs(float(g["ref_err"]))
+    assert abs(rep["correct_pct"] - float(g["ref_correct_pct"])) <= 0.2
+    k = 0
+    for L in layers:
+        if L[0] == "affine":
+            rW = g["final_Wt%d" % k]
+            np.testing.assert_allclose(L[1], rW, rtol=2e-4, atol=2e-4 * np.abs(rW).max())
+            k += 1
+
+
+def test_trbmcu_binary_reproduces_reference():
+    g = np.load(os.path.join(GOLD, "gpu_rbm_gb.npz"))
+    with tempfile.TemporaryDirectory() as d:
+        rep, LF, out = MG.run_rbm("rbm_gb", MG.RBM_CASES["rbm_gb"], d, exe=os.path.join(BIN, "TRbmCu"), save=False)
+    assert "===== TRbmCu FINISHED" in out
+    assert rep["frames"] == int(g["ref_frames"])
+    assert abs(rep["err"] - float(g["ref_err"])) <= 2e-4 * abs(float(g["ref_err"]))
+    np.testing.assert_allclose(LF[3], g["final_Wt"], rtol=2e-4, atol=2e-4 * np.abs(g["final_Wt"]).max())
+
+
+def test_trecurrentcu_binary_reproduces_reference():
+    g = np.load(os.path.join(GOLD, "gpu_rnn_small.npz"))
+    with tempfile.TemporaryDirectory() as d:
+        rep, LF, out = MG.run_rnn("rnn_small", MG.RNN_CASES["rnn_small"], d, exe=os.path.join(BIN, "TRecurrentCu"), save=False)
+    assert rep["frames"] == int(g["ref_frames"])
+    assert abs(rep["err"] - float(g["ref_err"])) <= 2e-4 * abs(float(g["ref_err"]))
+    np.testing.assert_allclose(LF[0][1], g["final_Wr"], rtol=3e-4, atol=3e-4 * np.abs(g["final_Wr"]).max())
+
+
+def test_cli_errors_like_the_reference():
+    import subprocess
+    exe = os.path.join(BIN, "TNetCu")
+    r = subprocess.run([exe, "--BOGUSFLAG=1", "-H", "/nonexistent"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Exception thrown" in r.stderr
+    r = subprocess.run([exe, "-n", "0.1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Source MMF must be specified" in r.stderr

@@ -1,0 +1,132 @@
+"""CPU-side tests of the host logic that needs no device: option grammar of the drop-in binaries (they must fail before
+touching the GPU), the text formats, and the data-parallel arithmetic (2 gloo ranks against the single-process oracle)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from tnet_b200 import formats as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "nnet-asr_b200", "bin")
+
+
+def _run(args):
+    return subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+
+
+@pytest.mark.parametrize("exe", ["TNetCu", "TRbmCu", "TRecurrentCu"])
+def test_binaries_exist_and_reject_bad_flags(exe):
+    p = os.path.join(BIN, exe)
+    assert os.path.exists(p), "run __graft_entry__.build()"
+    r = _run([p, "-Z", "1"])
+    assert r.returncode == 1 and "Invalid command line option '-Z'" in r.stderr
+    r = _run([p, "--SEED"])
+    assert r.returncode == 1 and "Character '=' expected" in r.stderr
+    r = _run([p, "--RANDOMIZE=MAYBE", "-H", "x"])
+    assert r.returncode == 1 and "TRUE or FALSE expected" in r.stderr
+
+
+def test_unused_long_option_is_an_error():
+    # reference: ui.CheckCommandLineParamUse() (TNetCu.cc:261)
+    r = _run([os.path.join(BIN, "TNetCu"), "--NOSUCHPARAM=3", "-H", "x"])
+    assert r.returncode == 1 and "NOSUCHPARAM" in r.stderr
+
+
+def test_no_cpu_fallback_in_binaries(tmp_path):
+    """With valid options and files but no GPU the trainer must fail loudly, not train on the CPU."""
+    import ctypes as C
+    from tnet_b200 import abi
+    n = C.c_int(0)
+    if abi.lib().tnb_device_count(C.byref(n)) == abi.OK and n.value > 0:
+        pytest.skip("a GPU is visible")
+    r = np.random.default_rng(0)
+    net = str(tmp_path / "a.nnet")
+    F.write_mlp(net, F.gen_mlp_init([6, 4, 3], r))
+    res = _run([os.path.join(BIN, "TNetCu"), "-H", net, "-S", "/dev/null", "-I", "/dev/null", "-m", "/dev/null"])
+    assert res.returncode == 1 and "CUDA" in res.stderr
+
+
+def test_network_text_format_roundtrip(tmp_path):
+    r = np.random.default_rng(1)
+    layers = [("expand", 13, [-2, -1, 0, 1, 2])] + F.gen_mlp_init([65, 8, 4], r) + []
+    p = str(tmp_path / "n.nnet")
+    F.write_mlp(p, layers)
+    back = F.read_mlp(p)
+    assert [l[0] for l in back] == ["expand", "affine", "sigmoid", "affine", "softmax"]
+    assert np.array_equal(back[1][1], layers[1][1]) and np.array_equal(back[0][2], np.array([-2, -1, 0, 1, 2]))
+    x = r.standard_normal((7, 13)).astype(np.float32)
+    assert np.array_equal(F.splice(x, 2), O.expand(x, np.arange(-2, 3, dtype=np.int32)))   # away from... incl. edge clamping
+
+
+def test_htk_roundtrip(tmp_path):
+    r = np.random.default_rng(2)
+    x = r.standard_normal((11, 39)).astype(np.float32)
+    p = str(tmp_path / "a.fea")
+    F.write_htk(p, x)
+    y, period, kind = F.read_htk(p)
+    assert np.array_equal(x, y) and period == 100000 and kind == F.HTK_USER
+
+
+DP_WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
+import oracle_lib as O
+from tnet_b200 import formats as F
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+r = np.random.default_rng(5)
+dims, B = [20, 16, 7], 64
+layers = F.gen_mlp_init(dims, r)
+X = r.standard_normal((B, dims[0])).astype(np.float32)
+T = np.zeros((B, dims[-1]), np.float32); T[np.arange(B), r.integers(0, dims[-1], B)] = 1
+lr, mmt, wc = 0.1, 0.5, 1e-3
+# what CuNetwork::Backpropagate does per rank in data-parallel mode: local rows, gradient, all-reduce, update with N = global rows
+rows = slice(rank * B // world, (rank + 1) * B // world)
+net = O.Net(layers, acc_double=1)
+net.set_hyper(0.0)                       # lr 0: forward/backward only, no update inside the oracle
+Xl, Tl = X[rows], T[rows]
+W = [O.f32(layers[0][1]).T.copy(), O.f32(layers[2][1]).T.copy()]
+b = [O.f32(layers[0][2]).copy(), O.f32(layers[2][2]).copy()]
+cW = [np.zeros_like(W[0]), np.zeros_like(W[1])]; cb = [np.zeros_like(b[0]), np.zeros_like(b[1])]
+for step in range(2):
+    cur = [("affine", W[0].T.copy(), b[0]), ("sigmoid", dims[1]), ("affine", W[1].T.copy(), b[1]), ("softmax", dims[2])]
+    n = O.Net(cur, acc_double=1); n.set_hyper(0.0)
+    y = n.propagate(Xl)
+    h = n.layer_out(1, Xl.shape[0])
+    e2, _, _, _ = O.xent_evaluate(y, Tl)
+    e1 = O.diff_sigmoid(O.gemm("N", "T", 1.0, e2, W[1], 0.0, np.zeros((Xl.shape[0], dims[1]), np.float32), 1), h)
+    grads = [(O.gemm("T", "N", 1.0, Xl, e1, 0.0, np.zeros_like(W[0]), 1), e1.astype(np.float64).sum(0).astype(np.float32)),
+             (O.gemm("T", "N", 1.0, h, e2, 0.0, np.zeros_like(W[1]), 1), e2.astype(np.float64).sum(0).astype(np.float32))]
+    for k, (gW, gb) in enumerate(grads):
+        tW, tb = torch.from_numpy(gW.copy()), torch.from_numpy(gb.copy())
+        dist.all_reduce(tW); dist.all_reduce(tb)
+        N = np.float32(B) * np.float32(1.0 / (1.0 - mmt))
+        cW[k] = tW.numpy() + np.float32(mmt) * cW[k]; cb[k] = tb.numpy() + np.float32(mmt) * cb[k]
+        W[k] = W[k] + np.float32(-lr / N) * cW[k]; b[k] = b[k] + np.float32(-lr / N) * cb[k]
+        W[k] = W[k] + np.float32(-lr * wc) * W[k]
+if rank == 0:
+    ref = O.Net(layers, acc_double=1); ref.set_hyper(lr, mmt=mmt, wc=wc, gdf=True)
+    ref.train_bunch(X, T); ref.train_bunch(X, T)
+    for k, i in enumerate((0, 2)):
+        Wt, bb = ref.get_affine(i)
+        np.testing.assert_allclose(W[k].T, Wt, rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(b[k], bb, rtol=2e-5, atol=1e-6)
+    print("DP_OK")
+dist.destroy_process_group()
+"""
+
+
+def test_data_parallel_arithmetic_two_gloo_ranks(tmp_path):
+    """N>1 semantics on CPU: rows of the bunch split over 2 ranks, per-layer gradient all-reduce (gloo), update with the
+    GLOBAL frame count == the single-process oracle on the whole bunch."""
+    script = tmp_path / "dp_worker.py"
+    script.write_text(DP_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29517", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", str(script), os.path.join(ROOT, "tests"), os.path.join(ROOT, "nnet-asr_b200", "python")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "DP_OK" in r.stdout, r.stdout[-3000:]
