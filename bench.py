@@ -67,7 +67,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -200,7 +200,7 @@ def reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--math", default="3xtf32", choices=["3xtf32", "tf32"])
@@ -258,11 +258,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ----
-    net.train_resident(BUNCH, 0, args.warmup)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()             # clocks are sampled from the warm-up to the end of the timed region
+    net.train_resident(BUNCH, 0, args.warmup)
+    barrier()
     l0 = host.launches()
     abi.check(L.tnb_ctx_profile_begin(ctx))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

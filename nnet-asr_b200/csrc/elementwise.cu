@@ -53,28 +53,48 @@ static int launch_map(TnbContext *ctx, float *dst, TnbMatrixDim d, F f) {
 // vec[c] = alpha * sum_r mat[r,c] + beta*vec[c].  Reference: _add_col_sum (double, serial, cukernels.cu:149-164)
 // and _add_col_sum_reduce (float tree, :169-187).  Here: 32 columns per CTA, 8 row-slices per column with double
 // partials, fixed-order combine -> deterministic, and at least as accurate as either reference variant.
-__global__ void __launch_bounds__(256) colsum_kernel(float alpha, const float *__restrict__ mat, float beta, float *vec,
-                                                     int rows, int cols, int stride) {
-  __shared__ double part[8][33];
+// phase 1: grid (cols/32, S): CTA (bx, by) sums rows [by*chunk, (by+1)*chunk) of 32 columns into part[by][col] (double)
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float *__restrict__ mat, double *__restrict__ part, int rows, int cols,
+                                                             int stride, int chunk) {
+  __shared__ double sm[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
+  const int r0 = blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
   double s = 0.0;
   if (c < cols)
-    for (int r = ry; r < rows; r += 8) s += (double)mat[(size_t)r * stride + c];
-  part[ry][cx] = s;
+    for (int r = r0 + ry; r < r1; r += 8) s += (double)mat[(size_t)r * stride + c];
+  sm[ry][cx] = s;
   __syncthreads();
   if (ry == 0 && c < cols) {
     double t = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) t += part[k][cx];
-    float b = (beta == 0.0f) ? 0.0f : beta * vec[c];
-    vec[c] = (float)((double)alpha * t + (double)b);
+    for (int k = 0; k < 8; k++) t += sm[k][cx];
+    part[(size_t)blockIdx.y * cols + c] = t;
   }
+}
+// phase 2: fixed-order combine of the S partials
+__global__ void __launch_bounds__(256) colsum_final_kernel(float alpha, const double *__restrict__ part, float beta, float *vec, int cols, int S) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double t = 0.0;
+  for (int k = 0; k < S; k++) t += part[(size_t)k * cols + c];
+  float b = (beta == 0.0f) ? 0.0f : beta * vec[c];
+  vec[c] = (float)((double)alpha * t + (double)b);
 }
 
 int launch_colsum(TnbContext *ctx, float alpha, const float *mat, float beta, float *vec, int rows, int cols, int stride) {
   if (cols == 0) return TNB_OK;
-  colsum_kernel<<<(cols + 31) / 32, 256, 0, ctx->stream>>>(alpha, mat, beta, vec, rows, cols, stride);
+  const int cb = (cols + 31) / 32;
+  int S = (2 * ctx->sm_count + cb - 1) / cb;  // ~2 CTAs per SM in phase 1
+  if (S > (rows + 63) / 64) S = (rows + 63) / 64;
+  if (S < 1) S = 1;
+  const int chunk = (rows + S - 1) / S;
+  int rc = ensure_vec_scratch(ctx, 2 * S * cols);  // doubles
+  if (rc != TNB_OK) return rc;
+  double *part = (double *)ctx->vec_scratch;
+  colsum_partial_kernel<<<dim3(cb, S), 256, 0, ctx->stream>>>(mat, part, rows, cols, stride, chunk);
+  TNB_LAUNCHED(ctx);
+  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, ctx->stream>>>(alpha, part, beta, vec, cols, S);
   TNB_LAUNCHED(ctx);
   return TNB_OK;
 }

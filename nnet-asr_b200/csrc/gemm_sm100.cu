@@ -188,7 +188,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_smem, BN);
+  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : (BN <= 256 ? 256 : 512)));
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -355,7 +356,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -488,11 +489,25 @@ int launch_gemm(TnbContext *ctx, char transa, char transb, int M, int N, int K, 
   //                 op(B)=B  -> B is [K x N], N contiguous -> MN-major         ; op(B)=B^T -> B is [N x K] -> K-major
   const int a_mn = ta ? 1 : 0;
   const int b_mn = tb ? 0 : 1;
-  // tile width: keep >= ~1 wave of CTAs on 148 SMs, prefer wide tiles (less smem traffic per flop)
-  const long tiles128 = (long)((M + BM - 1) / BM) * ((N + 127) / 128);
+  // tile width BN in {64,128,192,256}: minimise waves(BN) * tile_time(BN).  tile_time is the shared-memory-bandwidth model of
+  // DESIGN.md 3.1 (bytes through smem per K block: TMA fill + converter read/write + operand reads of the MMAs, 128 B/clk) plus a
+  // fixed prologue and an epilogue proportional to BN.
+  const bool three = ctx->math_mode == TNB_MATH_3XTF32;
+  const int num_kb = (K + BK - 1) / BK;
   int bn = 128;
-  if (tiles128 >= 2L * ctx->sm_count && N >= 256) bn = 256;
-  else if (tiles128 < ctx->sm_count / 2 || N <= 64) bn = 64;
+  double best = 1e300;
+  const int cands[4] = {64, 128, 192, 256};
+  for (int ci = 0; ci < 4; ci++) {
+    const int c = cands[ci];
+    if (c > 64 && N <= c / 2) continue;  // do not pad N by more than 2x
+    const long tiles = (long)((M + BM - 1) / BM) * ((N + c - 1) / c);
+    const long waves = (tiles + ctx->sm_count - 1) / ctx->sm_count;
+    const double smem_bytes = three ? (96.0 * 1024 + 768.0 * c) : (32.0 * 1024 + 256.0 * c);
+    double t = num_kb * smem_bytes / 128.0 + 4000.0 + 30.0 * c;
+    if (c >= 192 && three) t *= 1.05;  // only 2 pipeline stages fit
+    const double cost = waves * t;
+    if (cost < best * 0.999) { best = cost; bn = c; }
+  }
   CUtensorMap tmA, tmB;
   int rc;
   if (!a_mn) rc = get_tmap(ctx, A, M, K, lda, BM, BK, 0, &tmA);   // rows = m, cols = k, box 128 x 32
@@ -501,9 +516,10 @@ int launch_gemm(TnbContext *ctx, char transa, char transb, int M, int N, int K, 
   if (!b_mn) rc = get_tmap(ctx, B, N, K, ldb, bn, BK, 0, &tmB);   // rows = n, cols = k, box BN x 32
   else rc = get_tmap(ctx, B, K, N, ldb, BK, 32, 1, &tmB);         // rows = k, cols = n, box 32 x 32
   if (rc != TNB_OK) return rc;
-  const bool three = ctx->math_mode == TNB_MATH_3XTF32;
   if (bn == 256) return three ? launch_tc_major<256, 3>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep)
                               : launch_tc_major<256, 1>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep);
+  if (bn == 192) return three ? launch_tc_major<192, 3>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep)
+                              : launch_tc_major<192, 1>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep);
   if (bn == 128) return three ? launch_tc_major<128, 3>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep)
                               : launch_tc_major<128, 1>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep);
   return three ? launch_tc_major<64, 3>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep)
