@@ -62,29 +62,73 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     if (++spins > (1u << 26)) { printf("tnb gemm: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
   }
 }
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
+  // default .release.cta semantics (what CUTLASS' ClusterBarrier::arrive(cta) issues): the staged data never crosses the CTA
+  // boundary through the generic proxy — each SM's tensor core reads its own smem after the local fence.proxy.async — so only
+  // the ordering travels.  A .release.cluster here costs MEMBAR.ALL.GPU per arrive (measured: pair mode slower than 1 CTA).
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c_inner, int c_outer) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  if (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+  if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
 }
+template <int CG>
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
+// completion of all MMAs issued so far by this thread -> arrive on `bar` (in both CTAs of the pair when CG == 2)
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  if (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  } else {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+  }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -132,11 +176,14 @@ __device__ __forceinline__ float sigmoidf_ref(float x) {
   return 1.0f / (1.0f + expf(-x));
 }
 
-template <int BN_, int NTERMS_>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile: each CTA
+// stages its own 128 rows of A and HALF of the B tile (BN/2), the pair's tensor cores read both halves.
+template <int BN_, int NTERMS_, int CG_>
 struct GemmCfg {
   static constexpr int BN = BN_;
+  static constexpr int BH = BN_ / CG_;  // B rows (n) staged by one CTA
   static constexpr int A_BYTES = BM * BK * 4;
-  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int B_BYTES = BH * BK * 4;
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (NTERMS_ == 3 ? 2 : 1);
   static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -156,11 +203,12 @@ __device__ __forceinline__ float epi_one(const EpiParams &ep, float acc, float c
 // ----------------------------------------------------------------------------------------------- kernel
 // A_MN / B_MN: 0 = K-major tile (operand rows are the M/N index, contraction index contiguous),
 //              1 = MN-major tile (operand rows are the contraction index, M/N index contiguous).
-template <int BN, int A_MN, int B_MN, int NTERMS>
+template <int BN, int A_MN, int B_MN, int NTERMS, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                     int K, EpiParams ep) {
-  using Cfg = GemmCfg<BN, NTERMS>;
+  using Cfg = GemmCfg<BN, NTERMS, CG>;
+  constexpr int BH = Cfg::BH;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -173,25 +221,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM;
-  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.x * BM;  // consecutive CTAs (a pair when CG == 2) take consecutive 128-row blocks of the same N tile
+  const int n0 = blockIdx.y * BN;
   const int num_kb = (K + BK - 1) / BK;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader: issues the MMAs of the pair
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < STAGES; s++) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&conv_bar[s], CONV_WARPS);
+      // arrivals per phase: every converter warp (3xTF32) or one forwarding warp (single pass) of each CTA of the pair
+      mbar_init(&conv_bar[s], (NTERMS == 3 ? CONV_WARPS : 1) * CG);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : (BN <= 256 ? 256 : 512)));
-  if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  if (warp == 1) tmem_alloc<CG>(tmem_ptr_smem, TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();  // the peer's barriers must exist before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -216,23 +266,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < BM / 32; j++)  // box 32(m) x 32(k), one 4 KB chunk per 32 m
             tma_load_2d(stage_a(s) + j * (BK * 128), &tmA, &full_bar[s], m0 + 32 * j, k0);
         }
+        const int nb = n0 + (int)rank * BH;  // this CTA's part of the B tile
         if (B_MN == 0) {
-          tma_load_2d(stage_b(s), &tmB, &full_bar[s], k0, n0);  // box 32(k) x BN(n)
+          tma_load_2d(stage_b(s), &tmB, &full_bar[s], k0, nb);  // box 32(k) x BH(n)
         } else {
 #pragma unroll
-          for (int j = 0; j < BN / 32; j++)
-            tma_load_2d(stage_b(s) + j * (BK * 128), &tmB, &full_bar[s], n0 + 32 * j, k0);
+          for (int j = 0; j < BH / 32; j++)
+            tma_load_2d(stage_b(s) + j * (BK * 128), &tmB, &full_bar[s], nb + 32 * j, k0);
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (leader CTA only in pair mode) =====================
+    if (lane == 0 && rank == 0) {
       // instruction descriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, a_major [15], b_major [16],
       // N>>3 [17,23), M>>4 [24,29)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
       // K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); a K step of 8 floats = +32 B
       // MN-major: 32-float chunks BK*128 B apart (LBO), 4-k-row swizzle groups 512 B apart (SBO); a K step of 8 rows = +1024 B
       const uint32_t a_lbo = A_MN ? BK * 128 : 16, b_lbo = B_MN ? BK * 128 : 16;
@@ -242,7 +293,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int kb = 0; kb < num_kb; kb++) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(NTERMS == 3 ? &conv_bar[s] : &full_bar[s], ph);
+        mbar_wait((NTERMS == 3 || CG == 2) ? &conv_bar[s] : &full_bar[s], ph);
         tc_fence_after();
         const uint32_t a_hi = smem_u32(stage_a(s)), b_hi = smem_u32(stage_b(s));
         const uint32_t a_lo = smem_u32(stage_alo(s)), b_lo = smem_u32(stage_blo(s));
@@ -254,40 +305,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (NTERMS == 3) {
             const uint64_t dal = make_desc(a_lo + ks * a_kstep, a_lbo, a_sbo, a_lt);
             const uint64_t dbl = make_desc(b_lo + ks * b_kstep, b_lbo, b_sbo, b_lt);
-            umma_tf32(tmem_base, dal, dbh, idesc, first);
-            umma_tf32(tmem_base, dah, dbl, idesc, 1u);
-            umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+            umma_tf32<CG>(tmem_base, dal, dbh, idesc, first);
+            umma_tf32<CG>(tmem_base, dah, dbl, idesc, 1u);
+            umma_tf32<CG>(tmem_base, dah, dbh, idesc, 1u);
           } else {
-            umma_tf32(tmem_base, dah, dbh, idesc, first);
+            umma_tf32<CG>(tmem_base, dah, dbh, idesc, first);
           }
         }
-        umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
+        umma_commit<CG>(&empty_bar[s]);  // smem slot (of both CTAs) reusable once these MMAs have read it
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
+      umma_commit<CG>(tmem_full_bar);  // accumulator complete (in both CTAs' TMEM)
     }
     __syncwarp();
   } else {
     // ===================== converters (3xTF32) then epilogue =====================
     const int ct = threadIdx.x - 64;  // 0..CONV_THREADS-1
-    if (NTERMS == 3) {
+    // pair mode: these warps also forward "my stage has landed" to the leader's barrier (one warp is enough without conversion)
+    if (NTERMS == 3 || (CG == 2 && warp == 2)) {
       for (int kb = 0; kb < num_kb; kb++) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        // A and B tiles are contiguous ([A_hi][B_hi] -> [A_lo][B_lo]): one linear pass, 16 B per thread per step
-        const float4 *src = (const float4 *)stage_a(s);
-        float4 *dst = (float4 *)stage_alo(s);
-        constexpr int NV = (Cfg::A_BYTES + Cfg::B_BYTES) / 16;
+        mbar_wait(&full_bar[s], ph);  // all lanes poll (a single polling lane + __syncwarp measured 1.5x slower)
+        if (NTERMS == 3) {
+          // A and B tiles are contiguous ([A_hi][B_hi] -> [A_lo][B_lo]): one linear pass, 16 B per thread per step
+          const float4 *src = (const float4 *)stage_a(s);
+          float4 *dst = (float4 *)stage_alo(s);
+          constexpr int NV = (Cfg::A_BYTES + Cfg::B_BYTES) / 16;
+          static_assert(NV % CONV_THREADS == 0, "tile bytes must split evenly over the converter threads");
 #pragma unroll
-        for (int i = 0; i < NV / CONV_THREADS; i++) {
-          const float4 x = src[ct + CONV_THREADS * i];
-          float4 l;
-          l.x = lo_tf32(x.x); l.y = lo_tf32(x.y); l.z = lo_tf32(x.z); l.w = lo_tf32(x.w);
-          dst[ct + CONV_THREADS * i] = l;
+          for (int i = 0; i < NV / CONV_THREADS; i++) {
+            const float4 x = src[ct + CONV_THREADS * i];
+            float4 l;
+            l.x = lo_tf32(x.x); l.y = lo_tf32(x.y); l.z = lo_tf32(x.z); l.w = lo_tf32(x.w);
+            dst[ct + CONV_THREADS * i] = l;
+          }
+          fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         }
-        fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&conv_bar[s]);
+        if (lane == 0) { if (CG == 2) mbar_arrive_remote(&conv_bar[s], 0); else mbar_arrive(&conv_bar[s]); }
       }
     }
     // ---- epilogue: TMEM -> registers -> fused ops -> global ----
@@ -353,10 +408,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc<CG>(tmem_base, TMEM_COLS);
   }
 }
 
@@ -421,16 +476,17 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float *__restrict_
 }
 
 // ----------------------------------------------------------------------------------------------- host launch
-template <int BN, int A_MN, int B_MN, int NTERMS>
+template <int BN, int A_MN, int B_MN, int NTERMS, int CG>
 static int launch_tc(TnbContext *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, int M, int N, int K, const EpiParams &ep) {
-  using Cfg = GemmCfg<BN, NTERMS>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, NTERMS>;
+  using Cfg = GemmCfg<BN, NTERMS, CG>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, NTERMS, CG>;
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
     TNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set[ctx->device & 63] = true;
   }
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  int mtiles = (M + BM - 1) / BM;
+  if (CG == 2) mtiles = (mtiles + 1) & ~1;  // whole pairs; a pair's second CTA may be entirely out of range (zero-filled by TMA)
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->profiling) {
     while (ctx->prof_events.size() < ctx->prof_used + 2) {
@@ -444,19 +500,39 @@ static int launch_tc(TnbContext *ctx, const CUtensorMap &tmA, const CUtensorMap 
     ctx->prof_flops += 2.0 * (double)M * (double)N * (double)K;
     TNB_CUDA(cudaEventRecord(e0, ctx->stream));
   }
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(tmA, tmB, M, N, K, ep);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(mtiles, (N + BN - 1) / BN);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TNB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, M, N, K, ep));
   if (e1) TNB_CUDA(cudaEventRecord(e1, ctx->stream));
   TNB_LAUNCHED(ctx);
   return TNB_OK;
 }
 
-template <int BN, int NTERMS>
+template <int BN, int NTERMS, int CG>
 static int launch_tc_major(TnbContext *ctx, int a_mn, int b_mn, const CUtensorMap &tmA, const CUtensorMap &tmB, int M, int N,
                            int K, const EpiParams &ep) {
-  if (!a_mn && !b_mn) return launch_tc<BN, 0, 0, NTERMS>(ctx, tmA, tmB, M, N, K, ep);
-  if (!a_mn && b_mn) return launch_tc<BN, 0, 1, NTERMS>(ctx, tmA, tmB, M, N, K, ep);
-  if (a_mn && !b_mn) return launch_tc<BN, 1, 0, NTERMS>(ctx, tmA, tmB, M, N, K, ep);
-  return launch_tc<BN, 1, 1, NTERMS>(ctx, tmA, tmB, M, N, K, ep);
+  if (!a_mn && !b_mn) return launch_tc<BN, 0, 0, NTERMS, CG>(ctx, tmA, tmB, M, N, K, ep);
+  if (!a_mn && b_mn) return launch_tc<BN, 0, 1, NTERMS, CG>(ctx, tmA, tmB, M, N, K, ep);
+  if (a_mn && !b_mn) return launch_tc<BN, 1, 0, NTERMS, CG>(ctx, tmA, tmB, M, N, K, ep);
+  return launch_tc<BN, 1, 1, NTERMS, CG>(ctx, tmA, tmB, M, N, K, ep);
+}
+
+template <int BN, int CG>
+static int launch_tc_terms(TnbContext *ctx, bool three, int a_mn, int b_mn, const CUtensorMap &tmA, const CUtensorMap &tmB, int M,
+                           int N, int K, const EpiParams &ep) {
+  return three ? launch_tc_major<BN, 3, CG>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep)
+               : launch_tc_major<BN, 1, CG>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep);
 }
 
 // C[M x N] (+epilogue) = op(A) * op(B); A, B row-major as CuMatrix::Gemm receives them.
@@ -489,41 +565,56 @@ int launch_gemm(TnbContext *ctx, char transa, char transb, int M, int N, int K, 
   //                 op(B)=B  -> B is [K x N], N contiguous -> MN-major         ; op(B)=B^T -> B is [N x K] -> K-major
   const int a_mn = ta ? 1 : 0;
   const int b_mn = tb ? 0 : 1;
-  // tile width BN in {64,128,192,256}: minimise waves(BN) * tile_time(BN).  tile_time is the shared-memory-bandwidth model of
-  // DESIGN.md 3.1 (bytes through smem per K block: TMA fill + converter read/write + operand reads of the MMAs, 128 B/clk) plus a
-  // fixed prologue and an epilogue proportional to BN.
+  // Tile choice over {1 CTA, CTA pair} x BN: minimise waves * tile_time.  tile_time is the shared-memory-bandwidth model of
+  // DESIGN.md 3.1 — bytes through one SM's smem per K block (TMA fill + converter read/write + operand reads of the MMAs, at
+  // 128 B/clk) — plus a fixed prologue and an epilogue proportional to BN.  A pair stages only half of B per SM.
   const bool three = ctx->math_mode == TNB_MATH_3XTF32;
   const int num_kb = (K + BK - 1) / BK;
-  int bn = 128;
+  int bn = 128, cg = 1;
   double best = 1e300;
+  static int force_cg = -1;
+  if (force_cg < 0) { const char *e = getenv("TNB_GEMM_CG"); force_cg = e ? atoi(e) : 0; }  // 1 / 2 force a mode (debugging)
   const int cands[4] = {64, 128, 192, 256};
-  for (int ci = 0; ci < 4; ci++) {
-    const int c = cands[ci];
-    if (c > 64 && N <= c / 2) continue;  // do not pad N by more than 2x
-    const long tiles = (long)((M + BM - 1) / BM) * ((N + c - 1) / c);
-    const long waves = (tiles + ctx->sm_count - 1) / ctx->sm_count;
-    const double smem_bytes = three ? (96.0 * 1024 + 768.0 * c) : (32.0 * 1024 + 256.0 * c);
-    double t = num_kb * smem_bytes / 128.0 + 4000.0 + 30.0 * c;
-    if (c >= 192 && three) t *= 1.05;  // only 2 pipeline stages fit
-    const double cost = waves * t;
-    if (cost < best * 0.999) { best = cost; bn = c; }
+  for (int g = 1; g <= 2; g++) {
+    if (force_cg && g != force_cg) continue;
+    if (g == 2 && M <= BM && !force_cg) continue;  // a pair needs two 128-row blocks
+    if (g == 2 && !three && !force_cg) continue;   // single-pass tf32 is L2/latency-bound: pairs measured 4 % slower there
+    for (int ci = 0; ci < 4; ci++) {
+      const int c = cands[ci];
+      if (g == 2 && c == 64) continue;
+      if (c > 64 && N <= c / 2) continue;  // do not pad N by more than 2x
+      int mt = (M + BM - 1) / BM;
+      if (g == 2) mt = (mt + 1) & ~1;
+      const long ctas = (long)mt * ((N + c - 1) / c);
+      const long waves = (ctas + ctx->sm_count - 1) / ctx->sm_count;
+      const double a_b = 16.0 * 1024, b_b = 128.0 * c / g;        // staged bytes per K block
+      const double mma_reads = (three ? 12.0 : 4.0) * (4096.0 + 32.0 * c / g);
+      const double smem_bytes = (three ? 3.0 : 1.0) * (a_b + b_b) + mma_reads;
+      const int stage_bytes = (int)((a_b + b_b) * (three ? 2 : 1));
+      double t = num_kb * smem_bytes / 128.0 + 4000.0 + 30.0 * c;
+      if ((196 * 1024) / stage_bytes < 3) t *= 1.05;  // only 2 pipeline stages fit
+      const double cost = waves * t;
+      if (cost < best * 0.999) { best = cost; bn = c; cg = g; }
+    }
   }
+  const int bh = bn / cg;  // B rows staged per CTA = TMA box height of a K-major B
   CUtensorMap tmA, tmB;
   int rc;
   if (!a_mn) rc = get_tmap(ctx, A, M, K, lda, BM, BK, 0, &tmA);   // rows = m, cols = k, box 128 x 32
   else rc = get_tmap(ctx, A, K, M, lda, BK, 32, 1, &tmA);         // rows = k, cols = m, box 32 x 32
   if (rc != TNB_OK) return rc;
-  if (!b_mn) rc = get_tmap(ctx, B, N, K, ldb, bn, BK, 0, &tmB);   // rows = n, cols = k, box BN x 32
+  if (!b_mn) rc = get_tmap(ctx, B, N, K, ldb, bh, BK, 0, &tmB);   // rows = n, cols = k, box BH x 32
   else rc = get_tmap(ctx, B, K, N, ldb, BK, 32, 1, &tmB);         // rows = k, cols = n, box 32 x 32
   if (rc != TNB_OK) return rc;
-  if (bn == 256) return three ? launch_tc_major<256, 3>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep)
-                              : launch_tc_major<256, 1>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep);
-  if (bn == 192) return three ? launch_tc_major<192, 3>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep)
-                              : launch_tc_major<192, 1>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep);
-  if (bn == 128) return three ? launch_tc_major<128, 3>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep)
-                              : launch_tc_major<128, 1>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep);
-  return three ? launch_tc_major<64, 3>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep)
-               : launch_tc_major<64, 1>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep);
+  if (cg == 2) {
+    if (bn == 256) return launch_tc_terms<256, 2>(ctx, three, a_mn, b_mn, tmA, tmB, M, N, K, ep);
+    if (bn == 192) return launch_tc_terms<192, 2>(ctx, three, a_mn, b_mn, tmA, tmB, M, N, K, ep);
+    return launch_tc_terms<128, 2>(ctx, three, a_mn, b_mn, tmA, tmB, M, N, K, ep);
+  }
+  if (bn == 256) return launch_tc_terms<256, 1>(ctx, three, a_mn, b_mn, tmA, tmB, M, N, K, ep);
+  if (bn == 192) return launch_tc_terms<192, 1>(ctx, three, a_mn, b_mn, tmA, tmB, M, N, K, ep);
+  if (bn == 128) return launch_tc_terms<128, 1>(ctx, three, a_mn, b_mn, tmA, tmB, M, N, K, ep);
+  return launch_tc_terms<64, 1>(ctx, three, a_mn, b_mn, tmA, tmB, M, N, K, ep);
 }
 
 // ----------------------------------------------------------------------------------------------- gemv / ger
