@@ -325,7 +325,10 @@ def main():
                     "d2h_bytes_per_step": 24},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": gemm_tflops / pk["bf16_sustained"], "traffic": None,
+                         "frac": gemm_tflops / pk["bf16_sustained"],
+                         # dram__bytes_read+write of ONE 1024x2048x2048 forward launch (ncu --set full, profiles/r01_gemm_pair_ncu.md);
+                         # algorithmic bytes of that launch: X 8.4 MB + W 16.8 MB read, Y 8.4 MB written (stays in L2)
+                         "traffic": 25.27e6,
                          "kernel": "gemm_tcgen05_kernel (all GEMM launches of the timed region, CUDA events)",
                          "gemm_ms_per_step": gms.value / args.steps, "gemm_launches": int(gl.value),
                          "issued_tf32_tflops": gemm_tflops * passes,
