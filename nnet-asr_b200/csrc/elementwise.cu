@@ -53,40 +53,69 @@ static int launch_map(TnbContext *ctx, float *dst, TnbMatrixDim d, F f) {
 // vec[c] = alpha * sum_r mat[r,c] + beta*vec[c].  Reference: _add_col_sum (double, serial, cukernels.cu:149-164)
 // and _add_col_sum_reduce (float tree, :169-187).  Here: 32 columns per CTA, 8 row-slices per column with double
 // partials, fixed-order combine -> deterministic, and at least as accurate as either reference variant.
-// phase 1: grid (cols/32, S): CTA (bx, by) sums rows [by*chunk, (by+1)*chunk) of 32 columns into part[by][col] (double)
+// phase 1: grid (ceil(cols/128), S): CTA (bx, by) sums rows [by*chunk, (by+1)*chunk) of 128 columns into part[by][col] (double).
+// 32 column groups of 4 (one 16-byte load per thread and row) x 8 row lanes; two rows in flight per thread.
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float *__restrict__ mat, double *__restrict__ part, int rows, int cols,
                                                              int stride, int chunk) {
-  __shared__ double sm[8][33];
+  __shared__ double sm[8][129];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
+  const int c = blockIdx.x * 128 + cx * 4;
   const int r0 = blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
-  double s = 0.0;
-  if (c < cols)
-    for (int r = r0 + ry; r < r1; r += 8) s += (double)mat[(size_t)r * stride + c];
-  sm[ry][cx] = s;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+  const bool vec = ((stride & 3) == 0) && (((uintptr_t)mat & 15) == 0) && (c + 3 < cols);
+  if (vec) {
+    int r = r0 + ry;
+    for (; r + 8 < r1; r += 16) {
+      const float4 a = *(const float4 *)(mat + (size_t)r * stride + c);
+      const float4 b = *(const float4 *)(mat + (size_t)(r + 8) * stride + c);
+      s0 += a.x; s1 += a.y; s2 += a.z; s3 += a.w;
+      t0 += b.x; t1 += b.y; t2 += b.z; t3 += b.w;
+    }
+    for (; r < r1; r += 8) {
+      const float4 a = *(const float4 *)(mat + (size_t)r * stride + c);
+      s0 += a.x; s1 += a.y; s2 += a.z; s3 += a.w;
+    }
+  } else {
+    for (int r = r0 + ry; r < r1; r += 8) {
+      const float *p = mat + (size_t)r * stride + c;
+      if (c < cols) s0 += p[0];
+      if (c + 1 < cols) s1 += p[1];
+      if (c + 2 < cols) s2 += p[2];
+      if (c + 3 < cols) s3 += p[3];
+    }
+  }
+  sm[ry][cx * 4 + 0] = s0 + t0; sm[ry][cx * 4 + 1] = s1 + t1; sm[ry][cx * 4 + 2] = s2 + t2; sm[ry][cx * 4 + 3] = s3 + t3;
   __syncthreads();
-  if (ry == 0 && c < cols) {
-    double t = 0.0;
+  if (threadIdx.x < 128) {
+    const int cc = blockIdx.x * 128 + threadIdx.x;
+    if (cc < cols) {
+      double t = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) t += sm[k][cx];
-    part[(size_t)blockIdx.y * cols + c] = t;
+      for (int k = 0; k < 8; k++) t += sm[k][threadIdx.x];
+      part[(size_t)blockIdx.y * cols + cc] = t;
+    }
   }
 }
-// phase 2: fixed-order combine of the S partials
-__global__ void __launch_bounds__(256) colsum_final_kernel(float alpha, const double *__restrict__ part, float beta, float *vec, int cols, int S) {
+// phase 2: fixed-order combine of the S partials.  With `upd` != NULL the vector is a momentum buffer and the bias update of
+// CuBiasedLinearity::Update (cuBiasedLinearity.cc:56-59) is applied in the same pass: vec = sum + beta*vec ; upd += scale*vec.
+__global__ void __launch_bounds__(256) colsum_final_kernel(float alpha, const double *__restrict__ part, float beta, float *vec, int cols, int S,
+                                                           float *upd, float scale) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   double t = 0.0;
   for (int k = 0; k < S; k++) t += part[(size_t)k * cols + c];
   float b = (beta == 0.0f) ? 0.0f : beta * vec[c];
-  vec[c] = (float)((double)alpha * t + (double)b);
+  const float v = (float)((double)alpha * t + (double)b);
+  vec[c] = v;
+  if (upd) upd[c] = scale * v + upd[c];
 }
 
-int launch_colsum(TnbContext *ctx, float alpha, const float *mat, float beta, float *vec, int rows, int cols, int stride) {
+int launch_colsum_update(TnbContext *ctx, float alpha, const float *mat, float beta, float *vec, int rows, int cols, int stride, float *upd,
+                         float scale) {
   if (cols == 0) return TNB_OK;
-  const int cb = (cols + 31) / 32;
+  const int cb = (cols + 127) / 128;
   int S = (2 * ctx->sm_count + cb - 1) / cb;  // ~2 CTAs per SM in phase 1
-  if (S > (rows + 63) / 64) S = (rows + 63) / 64;
+  if (S > (rows + 31) / 32) S = (rows + 31) / 32;
   if (S < 1) S = 1;
   const int chunk = (rows + S - 1) / S;
   int rc = ensure_vec_scratch(ctx, 2 * S * cols);  // doubles
@@ -94,9 +123,12 @@ int launch_colsum(TnbContext *ctx, float alpha, const float *mat, float beta, fl
   double *part = (double *)ctx->vec_scratch;
   colsum_partial_kernel<<<dim3(cb, S), 256, 0, ctx->stream>>>(mat, part, rows, cols, stride, chunk);
   TNB_LAUNCHED(ctx);
-  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, ctx->stream>>>(alpha, part, beta, vec, cols, S);
+  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, ctx->stream>>>(alpha, part, beta, vec, cols, S, upd, scale);
   TNB_LAUNCHED(ctx);
   return TNB_OK;
+}
+int launch_colsum(TnbContext *ctx, float alpha, const float *mat, float beta, float *vec, int rows, int cols, int stride) {
+  return launch_colsum_update(ctx, alpha, mat, beta, vec, rows, cols, stride, nullptr, 0.0f);
 }
 
 // ---------------------------------------------------------------------------------------- gathers
@@ -399,11 +431,8 @@ int tnb_affine_update(TnbContext *ctx, const float *X, TnbMatrixDim dX, const fl
   ep.W = W; ep.ldw = dW.stride; ep.w_scale = scale; ep.w_l2 = l2;
   int rc = launch_gemm(ctx, 'T', 'N', dX.cols, dE.cols, dX.rows, X, dX.stride, E, dE.stride, ep);
   if (rc != TNB_OK) return rc;
-  // corrb = colsum(E) + mmt*corrb ; b += scale*corrb
-  rc = launch_colsum(ctx, 1.0f, E, mmt, corrb, dE.rows, dE.cols, dE.stride);
-  if (rc != TNB_OK) return rc;
-  TnbMatrixDim dv = {1, dE.cols, dE.cols};
-  return tnb_add_scaled(ctx, scale, corrb, 1.0f, bias, dv);
+  // corrb = colsum(E) + mmt*corrb ; b += scale*corrb   (one reduction + one combine/update kernel)
+  return launch_colsum_update(ctx, 1.0f, E, mmt, corrb, dE.rows, dE.cols, dE.stride, bias, scale);
 }
 
 int tnb_sgd_update(TnbContext *ctx, const float *G, float *W, float *corrW, TnbMatrixDim dW, const float *gb, float *bias,

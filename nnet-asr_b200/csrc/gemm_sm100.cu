@@ -170,6 +170,15 @@ __device__ __forceinline__ float lo_tf32(float x) {
   return ((u & 0x7F800000u) == 0x7F800000u) ? 0.0f : __uint_as_float(l);
 }
 
+// Pipeline tracing (compile with -DTNB_GEMM_TRACE): CTA (0,0) records clock64() at every hand-off of the mainloop
+// ([event][k block]) and at entry / setup / epilogue start / epilogue end / exit ([1][0..4]); tools/dbg_timeline.py prints it.
+// This is how the per-K-block costs quoted in DESIGN.md 3.1 were measured.
+#ifdef TNB_GEMM_TRACE
+__device__ long long g_dbg_ts[8 * 256];
+#define DBG_TS(ev, kb) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (kb) < 256) g_dbg_ts[(ev) * 256 + (kb)] = clock64(); } while (0)
+#else
+#define DBG_TS(ev, kb) do { } while (0)
+#endif
 __device__ __forceinline__ float sigmoidf_ref(float x) {
   // reference: 1.0/(1.0+exp(-x)) with a float exp and a double divide (cukernels.cu:194-206); the float
   // evaluation below differs by <= 1 ulp
@@ -221,6 +230,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) DBG_TS(1, 0);
   const int m0 = blockIdx.x * BM;  // consecutive CTAs (a pair when CG == 2) take consecutive 128-row blocks of the same N tile
   const int n0 = blockIdx.y * BN;
   const int num_kb = (K + BK - 1) / BK;
@@ -243,6 +253,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();  // the peer's barriers must exist before any remote arrive / multicast commit
   tc_fence_after();
+  if (threadIdx.x == 0) DBG_TS(1, 1);
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   auto stage_a = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
@@ -257,6 +268,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
+        DBG_TS(0, kb);
         mbar_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
         const int k0 = kb * BK;
         if (A_MN == 0) {
@@ -294,6 +306,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait((NTERMS == 3 || CG == 2) ? &conv_bar[s] : &full_bar[s], ph);
+        DBG_TS(4, kb);
         tc_fence_after();
         const uint32_t a_hi = smem_u32(stage_a(s)), b_hi = smem_u32(stage_b(s));
         const uint32_t a_lo = smem_u32(stage_alo(s)), b_lo = smem_u32(stage_blo(s));
@@ -313,6 +326,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         umma_commit<CG>(&empty_bar[s]);  // smem slot (of both CTAs) reusable once these MMAs have read it
+        DBG_TS(5, kb);
       }
       umma_commit<CG>(tmem_full_bar);  // accumulator complete (in both CTAs' TMEM)
     }
@@ -320,12 +334,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     // ===================== converters (3xTF32) then epilogue =====================
     const int ct = threadIdx.x - 64;  // 0..CONV_THREADS-1
+    // The fused epilogue re-reads C (momentum buffer, beta != 0) and W: pull this CTA's tiles of both into L2 now, so that the
+    // epilogue, which all CTAs reach at the same time, is served from L2 instead of queueing on HBM.
+    if (ep.beta != 0.0f || ep.W) {
+      for (int i = ct; i < BM * (BN / 32); i += CONV_THREADS) {
+        const int r = m0 + i / (BN / 32), cc = n0 + (i % (BN / 32)) * 32;
+        if (r < M && cc < N) {
+          if (ep.beta != 0.0f) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.C + (size_t)r * ep.ldc + cc));
+          if (ep.W) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.W + (size_t)r * ep.ldw + cc));
+        }
+      }
+    }
     // pair mode: these warps also forward "my stage has landed" to the leader's barrier (one warp is enough without conversion)
     if (NTERMS == 3 || (CG == 2 && warp == 2)) {
       for (int kb = 0; kb < num_kb; kb++) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);  // all lanes poll (a single polling lane + __syncwarp measured 1.5x slower)
+        if (threadIdx.x == 64) DBG_TS(2, kb);
         if (NTERMS == 3) {
           // A and B tiles are contiguous ([A_hi][B_hi] -> [A_lo][B_lo]): one linear pass, 16 B per thread per step
           const float4 *src = (const float4 *)stage_a(s);
@@ -343,29 +369,43 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         __syncwarp();
         if (lane == 0) { if (CG == 2) mbar_arrive_remote(&conv_bar[s], 0); else mbar_arrive(&conv_bar[s]); }
+        if (threadIdx.x == 64) DBG_TS(3, kb);
       }
     }
-    // ---- epilogue: TMEM -> registers -> fused ops -> global ----
+    // ---- epilogue: TMEM -> registers -> smem transpose -> fused ops with COALESCED global accesses ----
+    // tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns).  Storing from that layout makes each warp
+    // instruction touch 32 different 128-byte lines; going through a padded 32x36 smem tile per warp re-maps lanes so that
+    // 8 consecutive lanes cover one 128-byte row segment (4 lines per instruction instead of 32) for every array the fused
+    // epilogue reads or writes (C, C_old, bias, Yprev, W).  The stage buffers are free once tmem_full has fired.
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) DBG_TS(1, 2);
     const int q = warp & 3;              // TMEM lane quarter this warp may read
     const int chalf = (warp - 2) >> 2;   // two warps share a quarter: even / odd 32-column chunks
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < M;
-    const size_t crow = (size_t)row * (size_t)ep.ldc;
+    float *scratch = (float *)smem + (warp - 2) * (32 * 36);
+    const int cg4 = (lane & 7) * 4;      // column offset of this lane inside the 32-column chunk
+    const int r8 = lane >> 3;            // row offset (0..3) inside a group of 4 rows
 #pragma unroll 1
     for (int c = chalf; c < BN / 32; c += CONV_WARPS / 4) {
       const int nc0 = n0 + c * 32;
       if (nc0 >= N) break;
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      if (row_ok) {
+      float4 *srow = (float4 *)(scratch + lane * 36);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const int n = nc0 + 4 * j;
-          if (n >= N) break;
-          float acc[4] = {__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                          __uint_as_float(v[4 * j + 3])};
+      for (int j = 0; j < 8; j++)
+        srow[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                              __uint_as_float(v[4 * j + 3]));
+      __syncwarp();
+      const int n = nc0 + cg4;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int r = r8 + 4 * k;
+        const int row = m0 + q * 32 + r;
+        const float4 a4 = *(const float4 *)(scratch + r * 36 + cg4);
+        if (row < M && n < N) {
+          const float acc[4] = {a4.x, a4.y, a4.z, a4.w};
+          const size_t crow = (size_t)row * (size_t)ep.ldc;
           if (n + 3 < N) {
             float4 cold = make_float4(0, 0, 0, 0), yv = make_float4(0, 0, 0, 0), bv = make_float4(0, 0, 0, 0);
             if (ep.beta != 0.0f) cold = *(const float4 *)(ep.C + crow + n);
@@ -405,10 +445,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+      __syncwarp();  // the next chunk overwrites the scratch tile
     }
+    if (threadIdx.x == 64) DBG_TS(1, 3);
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (threadIdx.x == 0) DBG_TS(1, 4);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<CG>(tmem_base, TMEM_COLS);
@@ -575,12 +618,15 @@ int launch_gemm(TnbContext *ctx, char transa, char transb, int M, int N, int K, 
   static int force_cg = -1;
   if (force_cg < 0) { const char *e = getenv("TNB_GEMM_CG"); force_cg = e ? atoi(e) : 0; }  // 1 / 2 force a mode (debugging)
   const int cands[4] = {64, 128, 192, 256};
+  static int force_bn = -1;
+  if (force_bn < 0) { const char *e = getenv("TNB_GEMM_BN"); force_bn = e ? atoi(e) : 0; }
   for (int g = 1; g <= 2; g++) {
     if (force_cg && g != force_cg) continue;
     if (g == 2 && M <= BM && !force_cg) continue;  // a pair needs two 128-row blocks
     if (g == 2 && !three && !force_cg) continue;   // single-pass tf32 is L2/latency-bound: pairs measured 4 % slower there
     for (int ci = 0; ci < 4; ci++) {
       const int c = cands[ci];
+      if (force_bn && c != force_bn) continue;
       if (g == 2 && c == 64) continue;
       if (c > 64 && N <= c / 2) continue;  // do not pad N by more than 2x
       int mt = (M + BM - 1) / BM;
@@ -713,3 +759,8 @@ int tnb_ger(TnbContext *ctx, float alpha, const float *x, int dimX, const float 
 }
 
 }  // extern "C"
+
+#ifdef TNB_GEMM_TRACE
+// read back the pipeline timestamps (tracing builds only; not part of the ABI)
+extern "C" int tnb_dbg_read_ts(long long *out) { return cudaMemcpyFromSymbol(out, tnb::g_dbg_ts, sizeof(long long) * 8 * 256) == cudaSuccess ? 0 : 1; }
+#endif
