@@ -71,6 +71,12 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta) 
   // the ordering travels.  A .release.cluster here costs MEMBAR.ALL.GPU per arrive (measured: pair mode slower than 1 CTA).
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
+// 16-byte store into the shared memory of CTA `cta` of the cluster (same offset as the local address `p`)
+__device__ __forceinline__ void st_remote_f4(float *p, uint32_t cta, float4 v) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(p)), "r"(cta));
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -121,11 +127,10 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 }
 // completion of all MMAs issued so far by this thread -> arrive on `bar` (in both CTAs of the pair when CG == 2)
 template <int CG>
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+__device__ __forceinline__ void umma_commit(uint64_t *bar, uint16_t mask = 3) {
   if (CG == 1) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
   } else {
-    const uint16_t mask = 3;
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
   }
@@ -212,7 +217,10 @@ __device__ __forceinline__ float epi_one(const EpiParams &ep, float acc, float c
 // ----------------------------------------------------------------------------------------------- kernel
 // A_MN / B_MN: 0 = K-major tile (operand rows are the M/N index, contraction index contiguous),
 //              1 = MN-major tile (operand rows are the contraction index, M/N index contiguous).
-template <int BN, int A_MN, int B_MN, int NTERMS, int CG>
+// SPLIT = 2 (pair mode only): a cluster of 4 = two pairs working on the SAME 256 x BN tile, each over half of the K blocks; after
+// the mainloop the pairs swap half of their accumulator columns through distributed shared memory and each finishes (adds,
+// fused epilogue, store) the half it keeps.  Lets a 1024-row bunch use the MMA-bound 256 x 256 tile on 128 SMs.
+template <int BN, int A_MN, int B_MN, int NTERMS, int CG, int SPLIT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                     int K, EpiParams ep) {
@@ -231,10 +239,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) DBG_TS(1, 0);
-  const int m0 = blockIdx.x * BM;  // consecutive CTAs (a pair when CG == 2) take consecutive 128-row blocks of the same N tile
+  static_assert(SPLIT == 1 || CG == 2, "split-K is built on CTA pairs");
+  const uint32_t crank = (CG * SPLIT > 1) ? cluster_ctarank() : 0u;  // rank in the cluster of CG*SPLIT CTAs
+  const uint32_t rank = crank & (CG - 1);    // rank in the pair: 0 = leader (issues the MMAs of the pair)
+  const uint32_t split = crank / CG;         // which half of the K blocks this pair accumulates
+  // consecutive CTAs (a pair when CG == 2) take consecutive 128-row blocks of the same N tile; with SPLIT the next pair repeats them
+  const int m0 = (int)(blockIdx.x / (CG * SPLIT)) * (BM * CG) + (int)rank * BM;
   const int n0 = blockIdx.y * BN;
-  const int num_kb = (K + BK - 1) / BK;
-  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader: issues the MMAs of the pair
+  const int total_kb = (K + BK - 1) / BK;
+  const int kb_begin = (SPLIT == 1) ? 0 : (int)split * ((total_kb + 1) / 2);
+  const int num_kb = (SPLIT == 1) ? total_kb : (split == 0 ? (total_kb + 1) / 2 : total_kb / 2);
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -251,7 +265,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : (BN <= 256 ? 256 : 512)));
   if (warp == 1) tmem_alloc<CG>(tmem_ptr_smem, TMEM_COLS);
   tc_fence_before();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();  // the peer's barriers must exist before any remote arrive / multicast commit
+  if (CG * SPLIT > 1) cluster_sync_all(); else __syncthreads();  // the peer's barriers must exist before any remote arrive / multicast commit
   tc_fence_after();
   if (threadIdx.x == 0) DBG_TS(1, 1);
   const uint32_t tmem_base = *tmem_ptr_smem;
@@ -270,7 +284,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&empty_bar[s], ph ^ 1);
         DBG_TS(0, kb);
         mbar_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
-        const int k0 = kb * BK;
+        const int k0 = (kb_begin + kb) * BK;
         if (A_MN == 0) {
           tma_load_2d(stage_a(s), &tmA, &full_bar[s], k0, m0);  // box 32(k) x 128(m)
         } else {
@@ -325,10 +339,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             umma_tf32<CG>(tmem_base, dah, dbh, idesc, first);
           }
         }
-        umma_commit<CG>(&empty_bar[s]);  // smem slot (of both CTAs) reusable once these MMAs have read it
+        umma_commit<CG>(&empty_bar[s], (uint16_t)(3u << crank));  // smem slot (of both CTAs of the pair) reusable once these MMAs have read it
         DBG_TS(5, kb);
       }
-      umma_commit<CG>(tmem_full_bar);  // accumulator complete (in both CTAs' TMEM)
+      umma_commit<CG>(tmem_full_bar, (uint16_t)(3u << crank));  // accumulator complete (in both CTAs' TMEM)
     }
     __syncwarp();
   } else {
@@ -368,25 +382,55 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         }
         __syncwarp();
-        if (lane == 0) { if (CG == 2) mbar_arrive_remote(&conv_bar[s], 0); else mbar_arrive(&conv_bar[s]); }
+        if (lane == 0) { if (CG == 2) mbar_arrive_remote(&conv_bar[s], crank & ~1u); else mbar_arrive(&conv_bar[s]); }
         if (threadIdx.x == 64) DBG_TS(3, kb);
       }
     }
-    // ---- epilogue: TMEM -> registers -> smem transpose -> fused ops with COALESCED global accesses ----
-    // tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns).  Storing from that layout makes each warp
-    // instruction touch 32 different 128-byte lines; going through a padded 32x36 smem tile per warp re-maps lanes so that
-    // 8 consecutive lanes cover one 128-byte row segment (4 lines per instruction instead of 32) for every array the fused
-    // epilogue reads or writes (C, C_old, bias, Yprev, W).  The stage buffers are free once tmem_full has fired.
+  }
+
+  // ---- epilogue: TMEM -> registers -> smem transpose -> fused ops with COALESCED global accesses ----
+  // tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns).  Storing from that layout makes each warp
+  // instruction touch 32 different 128-byte lines; going through a padded 32x36 smem tile per warp re-maps lanes so that
+  // 8 consecutive lanes cover one 128-byte row segment (4 lines per instruction instead of 32) for every array the fused
+  // epilogue reads or writes (C, C_old, bias, Yprev, W).  The stage buffers are free once tmem_full has fired.
+  const int q = warp & 3;              // TMEM lane quarter this warp may read
+  const int chalf = (warp - 2) >> 2;   // two warps share a quarter: even / odd 32-column chunks
+  constexpr int HALFC = BN / 64;       // 32-column chunks per half tile (split-K)
+  constexpr int RS = BN / 2 + 4;       // row pitch (floats) of the split-K receive buffer: 16-byte aligned, conflict-free
+  float *scratch = (float *)smem + (warp >= 2 ? warp - 2 : 0) * (32 * 36);
+  float *recv = (float *)smem + CONV_WARPS * (32 * 36);  // [128][RS] floats, behind the per-warp transpose tiles
+  if (warp >= 2) {
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (threadIdx.x == 64) DBG_TS(1, 2);
-    const int q = warp & 3;              // TMEM lane quarter this warp may read
-    const int chalf = (warp - 2) >> 2;   // two warps share a quarter: even / odd 32-column chunks
-    float *scratch = (float *)smem + (warp - 2) * (32 * 36);
+  }
+  if (SPLIT == 2) {
+    cluster_sync_all();  // every pair of the cluster has finished its MMAs: all four CTAs' stage buffers are free
+    if (warp >= 2) {
+      // send the half of the accumulator columns the OTHER pair finishes to the CTA holding the same rows there
+      const uint32_t partner = crank ^ 2u;
+      float *dst_row = recv + (q * 32 + lane) * RS;
+#pragma unroll 1
+      for (int ci = chalf; ci < HALFC; ci += CONV_WARPS / 4) {
+        const int c = (1 - (int)split) * HALFC + ci;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          st_remote_f4(dst_row + ci * 32 + 4 * j, partner,
+                       make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                   __uint_as_float(v[4 * j + 3])));
+      }
+    }
+    cluster_sync_all();  // the partner's half has landed in my receive buffer
+  }
+  if (warp >= 2) {
     const int cg4 = (lane & 7) * 4;      // column offset of this lane inside the 32-column chunk
     const int r8 = lane >> 3;            // row offset (0..3) inside a group of 4 rows
+    const int nchunks = (SPLIT == 2) ? HALFC : BN / 32;
 #pragma unroll 1
-    for (int c = chalf; c < BN / 32; c += CONV_WARPS / 4) {
+    for (int ci = chalf; ci < nchunks; ci += CONV_WARPS / 4) {
+      const int c = (SPLIT == 2) ? (int)split * HALFC + ci : ci;
       const int nc0 = n0 + c * 32;
       if (nc0 >= N) break;
       uint32_t v[32];
@@ -402,7 +446,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int k = 0; k < 8; k++) {
         const int r = r8 + 4 * k;
         const int row = m0 + q * 32 + r;
-        const float4 a4 = *(const float4 *)(scratch + r * 36 + cg4);
+        float4 a4 = *(const float4 *)(scratch + r * 36 + cg4);
+        if (SPLIT == 2) {  // other K half, computed by the partner pair (a + b is commutative: both halves of the tile agree)
+          const float4 p4 = *(const float4 *)(recv + (q * 32 + r) * RS + ci * 32 + cg4);
+          a4.x += p4.x; a4.y += p4.y; a4.z += p4.z; a4.w += p4.w;
+        }
         if (row < M && n < N) {
           const float acc[4] = {a4.x, a4.y, a4.z, a4.w};
           const size_t crow = (size_t)row * (size_t)ep.ldc;
@@ -450,7 +498,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (threadIdx.x == 64) DBG_TS(1, 3);
   }
   tc_fence_before();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (CG * SPLIT > 1) cluster_sync_all(); else __syncthreads();
   if (threadIdx.x == 0) DBG_TS(1, 4);
   if (warp == 1) {
     tc_fence_after();
@@ -519,10 +567,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float *__restrict_
 }
 
 // ----------------------------------------------------------------------------------------------- host launch
-template <int BN, int A_MN, int B_MN, int NTERMS, int CG>
+template <int BN, int A_MN, int B_MN, int NTERMS, int CG, int SPLIT>
 static int launch_tc(TnbContext *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, int M, int N, int K, const EpiParams &ep) {
   using Cfg = GemmCfg<BN, NTERMS, CG>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, NTERMS, CG>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, NTERMS, CG, SPLIT>;
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
     TNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -545,13 +593,13 @@ static int launch_tc(TnbContext *ctx, const CUtensorMap &tmA, const CUtensorMap 
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(mtiles, (N + BN - 1) / BN);
+  cfg.gridDim = dim3(mtiles * SPLIT, (N + BN - 1) / BN);  // split-K: each pair of row blocks appears once per K half
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.x = CG * SPLIT;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -562,13 +610,13 @@ static int launch_tc(TnbContext *ctx, const CUtensorMap &tmA, const CUtensorMap 
   return TNB_OK;
 }
 
-template <int BN, int NTERMS, int CG>
+template <int BN, int NTERMS, int CG, int SPLIT = 1>
 static int launch_tc_major(TnbContext *ctx, int a_mn, int b_mn, const CUtensorMap &tmA, const CUtensorMap &tmB, int M, int N,
                            int K, const EpiParams &ep) {
-  if (!a_mn && !b_mn) return launch_tc<BN, 0, 0, NTERMS, CG>(ctx, tmA, tmB, M, N, K, ep);
-  if (!a_mn && b_mn) return launch_tc<BN, 0, 1, NTERMS, CG>(ctx, tmA, tmB, M, N, K, ep);
-  if (a_mn && !b_mn) return launch_tc<BN, 1, 0, NTERMS, CG>(ctx, tmA, tmB, M, N, K, ep);
-  return launch_tc<BN, 1, 1, NTERMS, CG>(ctx, tmA, tmB, M, N, K, ep);
+  if (!a_mn && !b_mn) return launch_tc<BN, 0, 0, NTERMS, CG, SPLIT>(ctx, tmA, tmB, M, N, K, ep);
+  if (!a_mn && b_mn) return launch_tc<BN, 0, 1, NTERMS, CG, SPLIT>(ctx, tmA, tmB, M, N, K, ep);
+  if (a_mn && !b_mn) return launch_tc<BN, 1, 0, NTERMS, CG, SPLIT>(ctx, tmA, tmB, M, N, K, ep);
+  return launch_tc<BN, 1, 1, NTERMS, CG, SPLIT>(ctx, tmA, tmB, M, N, K, ep);
 }
 
 template <int BN, int CG>
@@ -576,6 +624,44 @@ static int launch_tc_terms(TnbContext *ctx, bool three, int a_mn, int b_mn, cons
                            int N, int K, const EpiParams &ep) {
   return three ? launch_tc_major<BN, 3, CG>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep)
                : launch_tc_major<BN, 1, CG>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep);
+}
+
+// How many CTAs of a cluster launch can be resident at once (clusters must sit inside one GPC, so this can be below the SM count).
+static int cluster_capacity(TnbContext *ctx, int cluster) {
+  static int cap[64][5] = {};
+  int &c = cap[ctx->device & 63][cluster];
+  if (c == 0) {
+    c = ctx->sm_count - ctx->sm_count % cluster;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(cluster * 64, 1);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    cudaError_t e;
+    if (cluster == 4) {
+      using Cfg = GemmCfg<256, 3, 2>;
+      auto kern = gemm_tcgen05_kernel<256, 0, 0, 3, 2, 2>;
+      cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+      e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    } else {
+      using Cfg = GemmCfg<256, 3, 2>;
+      auto kern = gemm_tcgen05_kernel<256, 0, 0, 3, 2, 1>;
+      cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+      e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    }
+    if (e == cudaSuccess && n > 0) c = n * cluster; else cudaGetLastError();
+    if (getenv("TNB_GEMM_DEBUG")) fprintf(stderr, "[tnb] cluster size %d: %d co-resident CTAs\n", cluster, c);
+  }
+  return c;
 }
 
 // C[M x N] (+epilogue) = op(A) * op(B); A, B row-major as CuMatrix::Gemm receives them.
@@ -613,8 +699,10 @@ int launch_gemm(TnbContext *ctx, char transa, char transb, int M, int N, int K, 
   // 128 B/clk) — plus a fixed prologue and an epilogue proportional to BN.  A pair stages only half of B per SM.
   const bool three = ctx->math_mode == TNB_MATH_3XTF32;
   const int num_kb = (K + BK - 1) / BK;
-  int bn = 128, cg = 1;
+  int bn = 128, cg = 1, split = 1;
   double best = 1e300;
+  static int force_split = -1;
+  if (force_split < 0) { const char *e = getenv("TNB_GEMM_SPLIT"); force_split = e ? atoi(e) : 0; }  // 1 / 2 force (debugging)
   static int force_cg = -1;
   if (force_cg < 0) { const char *e = getenv("TNB_GEMM_CG"); force_cg = e ? atoi(e) : 0; }  // 1 / 2 force a mode (debugging)
   const int cands[4] = {64, 128, 192, 256};
@@ -631,16 +719,23 @@ int launch_gemm(TnbContext *ctx, char transa, char transb, int M, int N, int K, 
       if (c > 64 && N <= c / 2) continue;  // do not pad N by more than 2x
       int mt = (M + BM - 1) / BM;
       if (g == 2) mt = (mt + 1) & ~1;
-      const long ctas = (long)mt * ((N + c - 1) / c);
-      const long waves = (ctas + ctx->sm_count - 1) / ctx->sm_count;
       const double a_b = 16.0 * 1024, b_b = 128.0 * c / g;        // staged bytes per K block
       const double mma_reads = (three ? 12.0 : 4.0) * (4096.0 + 32.0 * c / g);
       const double smem_bytes = (three ? 3.0 : 1.0) * (a_b + b_b) + mma_reads;
       const int stage_bytes = (int)((a_b + b_b) * (three ? 2 : 1));
-      double t = num_kb * smem_bytes / 128.0 + 4000.0 + 30.0 * c;
-      if ((196 * 1024) / stage_bytes < 3) t *= 1.05;  // only 2 pipeline stages fit
-      const double cost = waves * t;
-      if (cost < best * 0.999) { best = cost; bn = c; cg = g; }
+      for (int sp = 1; sp <= 2; sp++) {
+        // split-K: two pairs share one output tile, each over half of K, and swap half an accumulator through DSMEM at the end
+        if (force_split == 1 && sp == 2) continue;
+        if (force_split == 2 && sp == 1 && g == 2 && three && c != 64 && num_kb >= 8) continue;
+        if (sp == 2 && (g != 2 || !three || c == 64 || num_kb < 8)) continue;
+        const long ctas = (long)mt * ((N + c - 1) / c) * sp;
+        const long cap = (g * sp == 1) ? ctx->sm_count : cluster_capacity(ctx, g * sp);
+        const long waves = (ctas + cap - 1) / cap;
+        double t = ((num_kb + sp - 1) / sp) * smem_bytes / 128.0 + 4000.0 + 30.0 * c / sp + (sp == 2 ? 2500.0 + 8.0 * c : 0.0);
+        if ((196 * 1024) / stage_bytes < 3) t *= 1.05;  // only 2 pipeline stages fit
+        const double cost = waves * t;
+        if (cost < best * 0.999) { best = cost; bn = c; cg = g; split = sp; }
+      }
     }
   }
   const int bh = bn / cg;  // B rows staged per CTA = TMA box height of a K-major B
@@ -652,6 +747,13 @@ int launch_gemm(TnbContext *ctx, char transa, char transb, int M, int N, int K, 
   if (!b_mn) rc = get_tmap(ctx, B, N, K, ldb, bh, BK, 0, &tmB);   // rows = n, cols = k, box BH x 32
   else rc = get_tmap(ctx, B, K, N, ldb, BK, 32, 1, &tmB);         // rows = k, cols = n, box 32 x 32
   if (rc != TNB_OK) return rc;
+  if (getenv("TNB_GEMM_DEBUG"))
+    fprintf(stderr, "[tnb] gemm %c%c M=%d N=%d K=%d -> BN=%d CG=%d SPLIT=%d\n", transa, transb, M, N, K, bn, cg, split);
+  if (split == 2) {  // 3xTF32 CTA pairs only
+    if (bn == 256) return launch_tc_major<256, 3, 2, 2>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep);
+    if (bn == 192) return launch_tc_major<192, 3, 2, 2>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep);
+    return launch_tc_major<128, 3, 2, 2>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep);
+  }
   if (cg == 2) {
     if (bn == 256) return launch_tc_terms<256, 2>(ctx, three, a_mn, b_mn, tmA, tmB, M, N, K, ep);
     if (bn == 192) return launch_tc_terms<192, 2>(ctx, three, a_mn, b_mn, tmA, tmB, M, N, K, ep);
