@@ -181,8 +181,15 @@ __device__ __forceinline__ float lo_tf32(float x) {
 #ifdef TNB_GEMM_TRACE
 __device__ long long g_dbg_ts[8 * 256];
 #define DBG_TS(ev, kb) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (kb) < 256) g_dbg_ts[(ev) * 256 + (kb)] = clock64(); } while (0)
+// every CTA also records %globaltimer at entry / epilogue start / exit and its SM id ([cta][4]): launch skew and tail of the grid
+__device__ long long g_dbg_cta[4 * 1024];
+__device__ __forceinline__ long long dbg_gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ int dbg_smid() { int t; asm volatile("mov.u32 %0, %%smid;" : "=r"(t)); return t; }
+#define DBG_CTA(slot) do { const int cta_ = blockIdx.y * gridDim.x + blockIdx.x; if (cta_ < 1024) { \
+  g_dbg_cta[cta_ * 4 + (slot)] = dbg_gtime(); if ((slot) == 0) g_dbg_cta[cta_ * 4 + 3] = dbg_smid(); } } while (0)
 #else
 #define DBG_TS(ev, kb) do { } while (0)
+#define DBG_CTA(slot) do { } while (0)
 #endif
 __device__ __forceinline__ float sigmoidf_ref(float x) {
   // reference: 1.0/(1.0+exp(-x)) with a float exp and a double divide (cukernels.cu:194-206); the float
@@ -238,7 +245,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) DBG_TS(1, 0);
+  if (threadIdx.x == 0) { DBG_TS(1, 0); DBG_CTA(0); }
   static_assert(SPLIT == 1 || CG == 2, "split-K is built on CTA pairs");
   const uint32_t crank = (CG * SPLIT > 1) ? cluster_ctarank() : 0u;  // rank in the cluster of CG*SPLIT CTAs
   const uint32_t rank = crank & (CG - 1);    // rank in the pair: 0 = leader (issues the MMAs of the pair)
@@ -402,7 +409,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp >= 2) {
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    if (threadIdx.x == 64) DBG_TS(1, 2);
+    if (threadIdx.x == 64) { DBG_TS(1, 2); DBG_CTA(1); }
   }
   if (SPLIT == 2) {
     cluster_sync_all();  // every pair of the cluster has finished its MMAs: all four CTAs' stage buffers are free
@@ -499,7 +506,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   if (CG * SPLIT > 1) cluster_sync_all(); else __syncthreads();
-  if (threadIdx.x == 0) DBG_TS(1, 4);
+  if (threadIdx.x == 0) { DBG_TS(1, 4); DBG_CTA(2); }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<CG>(tmem_base, TMEM_COLS);
@@ -865,4 +872,5 @@ int tnb_ger(TnbContext *ctx, float alpha, const float *x, int dimX, const float 
 #ifdef TNB_GEMM_TRACE
 // read back the pipeline timestamps (tracing builds only; not part of the ABI)
 extern "C" int tnb_dbg_read_ts(long long *out) { return cudaMemcpyFromSymbol(out, tnb::g_dbg_ts, sizeof(long long) * 8 * 256) == cudaSuccess ? 0 : 1; }
+extern "C" int tnb_dbg_read_cta(long long *out) { return cudaMemcpyFromSymbol(out, tnb::g_dbg_cta, sizeof(long long) * 4 * 1024) == cudaSuccess ? 0 : 1; }
 #endif
