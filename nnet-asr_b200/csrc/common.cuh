@@ -73,6 +73,7 @@ struct TnbContext_ {
   int vec_cap = 0;
   // GEMM profiling (tnb_ctx_profile_begin/end)
   bool profiling = false;
+  bool pdl = true;  // programmatic dependent launch between consecutive GEMMs (TNB_PDL=0 disables)
   std::vector<cudaEvent_t> prof_events;  // start/stop pairs
   size_t prof_used = 0;
   double prof_flops = 0.0;

@@ -2,6 +2,7 @@
 // Replaces CuDevice (reference: src/CuBaseLib/cudevice.cc:22-121) and the cudaMallocPitch /
 // cudaMemcpy2D / cudaMemset calls inside CuMatrix/CuVector (src/CuBaseLib/cumatrix.tcc:16-190).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -138,6 +139,7 @@ int tnb_ctx_create(TnbContext **out, int device) {
     return TNB_ERR_UNSUPPORTED;
   }
   TnbContext *ctx = new TnbContext_();
+  { const char *e = getenv("TNB_PDL"); if (e && atoi(e) == 0) ctx->pdl = false; }
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   TNB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));

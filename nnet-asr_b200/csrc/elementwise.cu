@@ -428,7 +428,7 @@ int tnb_affine_update(TnbContext *ctx, const float *X, TnbMatrixDim dX, const fl
   EpiParams ep;
   memset(&ep, 0, sizeof(ep));
   ep.C = corrW; ep.ldc = dW.stride; ep.alpha = 1.0f; ep.beta = mmt;
-  ep.W = W; ep.ldw = dW.stride; ep.w_scale = scale; ep.w_l2 = l2;
+  ep.W = W; ep.ldw = dW.stride; ep.w_scale = scale; ep.w_l2 = l2; ep.mode = EPI_UPD;
   int rc = launch_gemm(ctx, 'T', 'N', dX.cols, dE.cols, dX.rows, X, dX.stride, E, dE.stride, ep);
   if (rc != TNB_OK) return rc;
   // corrb = colsum(E) + mmt*corrb ; b += scale*corrb   (one reduction + one combine/update kernel)

@@ -12,7 +12,42 @@ struct EpiParams {
   const float *mulY; int ldy;   // out *= y*(1-y)              (CuSigmoid::BackpropagateFnc)
   float *W; int ldw;            // fused SGD: W += w_scale*out ; W += w_l2*W
   float w_scale, w_l2;
+  int mode;                     // EPI_*: which specialised epilogue the fused entry point asks for (EPI_GENERIC = any combination)
 };
+
+// Specialised epilogues (template parameter of the kernel).  The generic one evaluates every field of EpiParams at run time; the
+// three fused layer ops get compact code paths whose global reads are issued in one batch before the accumulator is touched.
+enum { EPI_GENERIC = 0, EPI_FWD = 1 /* C = act(acc + bias) */, EPI_DX = 2 /* C = acc .* y(1-y) */,
+       EPI_UPD = 3 /* C = acc + beta*C ; W += s*C ; W += l2*W */ };
+
+__device__ __forceinline__ float sigmoidf_ref(float x) {
+  // reference: 1.0/(1.0+exp(-x)) with a float exp and a double divide (cukernels.cu:194-206); the float
+  // evaluation below differs by <= 1 ulp
+  return 1.0f / (1.0f + expf(-x));
+}
+
+__device__ __forceinline__ float epi_one(const EpiParams &ep, float acc, float cold, float bias, float y) {
+  float o = ep.alpha * acc;
+  if (ep.beta != 0.0f) o += ep.beta * cold;
+  o += bias;
+  if (ep.act == TNB_ACT_SIGMOID) o = sigmoidf_ref(o);
+  if (ep.mulY) o = (y * (1.0f - y)) * o;
+  return o;
+}
+
+constexpr int BM = 128;  // rows of the output tile one CTA owns
+constexpr int BK = 32;   // fp32 elements per K block = 128 bytes = one swizzle span
+constexpr int CONV_WARPS = 8;                       // converter / epilogue warps
+constexpr int CONV_THREADS = CONV_WARPS * 32;
+constexpr int GEMM_THREADS = 64 + CONV_THREADS;     // + TMA warp + MMA warp
+
+// Defined in gemm_kernel.cuh and explicitly instantiated, tile shape by tile shape, in the gemm_inst_*.cu translation units.
+// BN: tile width; NTERMS: 3 = 3xTF32, 1 = single tf32 pass; CG: CTAs per tile (2 = tcgen05 cta_group::2 pair); SPLIT: split-K factor.
+template <int BN, int NTERMS, int CG, int SPLIT>
+int launch_tc_major(TnbContext *ctx, int a_mn, int b_mn, const CUtensorMap &tmA, const CUtensorMap &tmB, int M, int N, int K,
+                    const EpiParams &ep);
+template <int BN, int NTERMS, int CG, int SPLIT>
+int tc_max_active_clusters(int *clusters);
 
 // C[M x N] (+epilogue) = op(A) * op(B); A, B row-major exactly as CuMatrix::Gemm receives them
 // (reference: src/CuBaseLib/cumatrix.tcc:335-370).

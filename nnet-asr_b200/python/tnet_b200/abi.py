@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-LIB_PATH = os.path.join(ROOT, "nnet-asr_b200", "lib", "libtnetb200.so")
+# TNB_LIB_DIR: developer override used by tools/dbg_*.py to load the tracing build (make TRACE=1 LIBDIR=...)
+LIB_PATH = os.path.join(os.environ.get("TNB_LIB_DIR") or os.path.join(ROOT, "nnet-asr_b200", "lib"), "libtnetb200.so")
 
 OK = 0
 MATH_3XTF32, MATH_TF32, MATH_FP32_SIMT = 0, 1, 2
