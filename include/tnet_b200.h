@@ -53,7 +53,9 @@ enum {
 enum {
   TNB_MATH_3XTF32 = 0, /* split fp32 = hi + lo (tf32 each); acc += lo*hi + hi*lo + hi*hi  (default) */
   TNB_MATH_TF32 = 1,   /* single tf32 product (operands rounded to 10-bit mantissa) */
-  TNB_MATH_FP32_SIMT = 2 /* plain fp32 FMA on CUDA cores: debug / cross-check path, no tensor cores */
+  TNB_MATH_FP32_SIMT = 2, /* plain fp32 FMA on CUDA cores: debug / cross-check path, no tensor cores */
+  TNB_MATH_BF16 = 3    /* operands rounded to bf16 (RN), products accumulated in fp32 (TMEM); weights, activations, errors and
+                          momentum buffers stay fp32.  Reported separately from the fp32-equivalent default. */
 };
 
 /* ---- context / device (replaces CuDevice, CuBaseLib/cudevice.cc:22-121) -------------------------- */
@@ -82,6 +84,8 @@ int tnb_ctx_profile_end(TnbContext *ctx, double *gemm_ms, unsigned long long *ge
 /* rows x cols fp32 (or any 4-byte type), zero-filled like CuMatrix::Init (cumatrix.tcc:16-34);
  * *stride_elems is a multiple of 32 elements (128 B). */
 int tnb_malloc_pitch(TnbContext *ctx, void **ptr, int *stride_elems, int rows, int cols);
+/* rows x cols 2-byte elements (bf16 twins of fp32 matrices, TNB_MATH_BF16), zero-filled; *stride_elems is a multiple of 64. */
+int tnb_malloc_pitch16(TnbContext *ctx, void **ptr, int *stride_elems, int rows, int cols);
 int tnb_malloc(TnbContext *ctx, void **ptr, size_t bytes); /* zero-filled */
 int tnb_free(TnbContext *ctx, void *ptr);
 int tnb_memset(TnbContext *ctx, void *ptr, int value, size_t bytes);
@@ -163,6 +167,25 @@ int tnb_affine_update(TnbContext *ctx, const float *X, TnbMatrixDim dX, const fl
  *   corrW = G + mmt*corrW ; ... as above.  gb/bias/corrb may be NULL together. */
 int tnb_sgd_update(TnbContext *ctx, const float *G, float *W, float *corrW, TnbMatrixDim dW, const float *gb, float *bias,
                    float *corrb, float lr, float mmt, float wc, int grad_div_frm, int n_frames);
+
+/* ---- TNB_MATH_BF16 with resident bf16 twins -----------------------------------------------------------
+ * In bf16 mode every entry point above still takes fp32 arrays (operands are rounded into context scratch per call).  The hot
+ * path avoids that conversion by keeping a bf16 twin next to each fp32 matrix a GEMM reads: the three fused layer ops below
+ * READ twins (X16, W16, E16: row-major bf16 bit patterns, pitch in elements, 16-byte aligned, pitch a multiple of 8) and WRITE
+ * the twin of what they produce (Y16, Eprev16, W16; may be NULL) from the same fp32 value they store.  Arithmetic and fp32
+ * results are identical to the fp32-array entry points in bf16 mode. */
+int tnb_to_bf16(TnbContext *ctx, uint16_t *dst, int dst_stride, const float *src, TnbMatrixDim d); /* dst = bf16_rn(src); pad columns zeroed */
+int tnb_affine_fwd_bf16(TnbContext *ctx, const uint16_t *X16, int ldx16, TnbMatrixDim dX, const uint16_t *W16, int ldw16,
+                        TnbMatrixDim dW, const float *bias, float *Y, TnbMatrixDim dY, uint16_t *Y16, int ldy16, int act);
+int tnb_affine_bwd_dx_bf16(TnbContext *ctx, const uint16_t *E16, int lde16, TnbMatrixDim dE, const uint16_t *W16, int ldw16,
+                           TnbMatrixDim dW, const float *Yprev, TnbMatrixDim dYprev, float *Eprev, TnbMatrixDim dEprev,
+                           uint16_t *Eprev16, int ldep16);
+/* E (fp32) is read for the bias gradient (column sums stay fp32/double as in the default mode) */
+int tnb_affine_grad_bf16(TnbContext *ctx, const uint16_t *X16, int ldx16, TnbMatrixDim dX, const uint16_t *E16, int lde16,
+                         const float *E, TnbMatrixDim dE, float *G, TnbMatrixDim dG, float *gb);
+int tnb_affine_update_bf16(TnbContext *ctx, const uint16_t *X16, int ldx16, TnbMatrixDim dX, const uint16_t *E16, int lde16,
+                           const float *E, TnbMatrixDim dE, float *W, TnbMatrixDim dW, uint16_t *W16, int ldw16, float *bias,
+                           float *corrW, float *corrb, float lr, float mmt, float wc, int grad_div_frm, int n_frames_global);
 
 /* Objective accumulators kept on the device (read once per epoch instead of 2 blocking D2H per bunch,
  * cuObjectiveFunction.cc:61-80).  Layout is ABI. */

@@ -71,6 +71,9 @@ struct TnbContext_ {
   // column-sum scratch (bias gradient before the fused update)
   float *vec_scratch = nullptr;
   int vec_cap = 0;
+  // bf16 copies of fp32 GEMM operands for the generic entry points in TNB_MATH_BF16 (slot 0 = A, 1 = B)
+  uint16_t *bf16_scratch[2] = {nullptr, nullptr};
+  size_t bf16_cap[2] = {0, 0};
   // GEMM profiling (tnb_ctx_profile_begin/end)
   bool profiling = false;
   bool pdl = true;  // programmatic dependent launch between consecutive GEMMs (TNB_PDL=0 disables)
@@ -88,6 +91,6 @@ inline dim3 grid2d(int cols, int rows, int bx, int by) {
 }
 int ensure_row_scratch(TnbContext *ctx, int rows);
 int ensure_vec_scratch(TnbContext *ctx, int n);
-int get_tmap(TnbContext *ctx, const float *ptr, int rows, int cols, int stride, int box_rows,
-             int box_cols, int swizzle32, CUtensorMap *out);
+int get_tmap(TnbContext *ctx, const void *ptr, int rows, int cols, int stride, int box_rows,
+             int box_cols, int swizzle32, CUtensorMap *out, int elem_bytes = 4);
 }  // namespace tnb

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "gemm.cuh"
 
 namespace tnb {
 
@@ -64,24 +65,26 @@ static int load_encode() {
 // box = box_rows x box_cols (box_cols*4 == 128 B), OOB elements read as zero.  swizzle32 = 0: 128-byte swizzle with
 // 16-byte atoms (K-major UMMA operands); 1: 128-byte swizzle with 32-byte atoms, the only layout tcgen05 accepts for
 // MN-major 32-bit (tf32) operands (UMMA LayoutType SWIZZLE_128B_BASE32B).
-int get_tmap(TnbContext *ctx, const float *ptr, int rows, int cols, int stride, int box_rows, int box_cols,
-             int swizzle32, CUtensorMap *out) {
+// elem_bytes = 2: the same over a bf16 matrix (box_cols = 64, plain 128-byte swizzle for both operand majors).
+int get_tmap(TnbContext *ctx, const void *ptr, int rows, int cols, int stride, int box_rows, int box_cols,
+             int swizzle32, CUtensorMap *out, int elem_bytes) {
   TmapKey key;
   memset(&key, 0, sizeof(key));
   key.ptr = ptr; key.rows = rows; key.cols = cols; key.stride = stride;
-  key.box_rows = box_rows; key.box_cols = box_cols; key.swizzle32 = swizzle32;
+  key.box_rows = box_rows; key.box_cols = box_cols; key.swizzle32 = swizzle32 | (elem_bytes << 8);
   auto it = ctx->tmaps.find(key);
   if (it != ctx->tmaps.end()) { *out = it->second; return TNB_OK; }
   int rc = load_encode();
   if (rc != TNB_OK) return rc;
   TNB_ARG(((uintptr_t)ptr & 15) == 0, "TMA needs a 16-byte aligned base");
-  TNB_ARG((stride % 4) == 0, "TMA needs a row pitch that is a multiple of 16 bytes");
+  TNB_ARG(elem_bytes == 4 || elem_bytes == 2, "element size");
+  TNB_ARG(((size_t)stride * elem_bytes) % 16 == 0, "TMA needs a row pitch that is a multiple of 16 bytes");
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)stride * sizeof(float)};
+  cuuint64_t gstr[1] = {(cuuint64_t)stride * (cuuint64_t)elem_bytes};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
-  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, gdim, gstr, box, estr,
+  CUresult r = g_encode(&m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE,
                         swizzle32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -94,6 +97,22 @@ int get_tmap(TnbContext *ctx, const float *ptr, int rows, int cols, int stride, 
   ctx->tmaps[key] = m;
   *out = m;
   return TNB_OK;
+}
+
+// bf16 copy of an fp32 GEMM operand in ctx-owned scratch (generic entry points in TNB_MATH_BF16).  Stream order makes the
+// reuse safe: the conversion kernel is an ordinary launch, so it starts only after the GEMM that read the slot has completed.
+int bf16_scratch(TnbContext *ctx, int slot, const float *src, int rows, int cols, int stride, uint16_t **out, int *out_stride) {
+  const int st = ((cols + 63) / 64) * 64;
+  const size_t need = (size_t)rows * (size_t)st;
+  if (need > ctx->bf16_cap[slot]) {
+    if (ctx->bf16_scratch[slot]) { TNB_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->bf16_scratch[slot]); }
+    ctx->bf16_scratch[slot] = nullptr; ctx->bf16_cap[slot] = 0;
+    TNB_CUDA(cudaMalloc(&ctx->bf16_scratch[slot], need * 2));
+    ctx->bf16_cap[slot] = need;
+  }
+  *out = ctx->bf16_scratch[slot];
+  *out_stride = st;
+  return launch_to_bf16(ctx, *out, st, src, rows, cols, stride);
 }
 
 }  // namespace tnb
@@ -158,6 +177,7 @@ int tnb_ctx_destroy(TnbContext *ctx) {
   if (ctx->row_scratch) cudaFree(ctx->row_scratch);
   if (ctx->row_match) cudaFree(ctx->row_match);
   if (ctx->vec_scratch) cudaFree(ctx->vec_scratch);
+  for (int i = 0; i < 2; i++) if (ctx->bf16_scratch[i]) cudaFree(ctx->bf16_scratch[i]);
   for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_compute);
   cudaEventDestroy(ctx->ev_comm);
@@ -170,7 +190,7 @@ int tnb_ctx_destroy(TnbContext *ctx) {
 int tnb_ctx_device(TnbContext *ctx, int *device) { TNB_ARG(ctx && device, "null"); *device = ctx->device; return TNB_OK; }
 int tnb_ctx_set_math(TnbContext *ctx, int m) {
   TNB_ARG(ctx, "null");
-  TNB_ARG(m == TNB_MATH_3XTF32 || m == TNB_MATH_TF32 || m == TNB_MATH_FP32_SIMT, "unknown math mode");
+  TNB_ARG(m == TNB_MATH_3XTF32 || m == TNB_MATH_TF32 || m == TNB_MATH_FP32_SIMT || m == TNB_MATH_BF16, "unknown math mode");
   ctx->math_mode = m;
   return TNB_OK;
 }
@@ -220,6 +240,18 @@ int tnb_malloc_pitch(TnbContext *ctx, void **ptr, int *stride_elems, int rows, i
   int stride = ((cols + 31) / 32) * 32;
   if (stride == 0) stride = 32;
   size_t bytes = (size_t)(rows > 0 ? rows : 1) * (size_t)stride * 4;
+  TNB_CUDA(cudaSetDevice(ctx->device));
+  TNB_CUDA(cudaMalloc(ptr, bytes));
+  TNB_CUDA(cudaMemsetAsync(*ptr, 0, bytes, ctx->stream));
+  *stride_elems = stride;
+  return TNB_OK;
+}
+int tnb_malloc_pitch16(TnbContext *ctx, void **ptr, int *stride_elems, int rows, int cols) {
+  TNB_ARG(ctx && ptr && stride_elems, "null");
+  TNB_ARG(rows >= 0 && cols >= 0, "negative dims");
+  int stride = ((cols + 63) / 64) * 64;  // 128-byte pitch
+  if (stride == 0) stride = 64;
+  size_t bytes = (size_t)(rows > 0 ? rows : 1) * (size_t)stride * 2;
   TNB_CUDA(cudaSetDevice(ctx->device));
   TNB_CUDA(cudaMalloc(ptr, bytes));
   TNB_CUDA(cudaMemsetAsync(*ptr, 0, bytes, ctx->stream));

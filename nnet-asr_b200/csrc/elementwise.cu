@@ -6,6 +6,7 @@
 // matrix pitch allows it (tnb_malloc_pitch guarantees it), rows are walked by a grid-stride loop and the
 // grid is sized in multiples of the SM count.  Arithmetic keeps the reference's float/double
 // promotions where they are observable (diff-sigmoid's double product, the double column sums).
+#include <cuda_bf16.h>
 #include <float.h>
 
 #include "common.cuh"
@@ -284,6 +285,47 @@ static void update_scalars(float lr, float mmt, float wc, int gdf, int rows, flo
   *l2 = (float)(-lr * wc * (gdf ? 1.0 : rows));
 }
 
+// ---------------------------------------------------------------------------------------- fp32 -> bf16 (TNB_MATH_BF16 operands)
+// one thread converts 8 consecutive columns: two 16-byte loads, one 16-byte store; columns between `cols` and the pitch are
+// written as zeros so that a later TMA box never reads uninitialised padding as NaN
+__global__ void __launch_bounds__(256) to_bf16_kernel(uint16_t *__restrict__ dst, int dst_stride, const float *__restrict__ src,
+                                                      int rows, int cols, int src_stride) {
+  const int vcols = dst_stride >> 3;
+  const long total = (long)rows * vcols;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / vcols), c = (int)(i % vcols) << 3;
+    const float *sp = src + (size_t)r * src_stride + c;
+    float v[8];
+    if (c + 7 < cols && ((src_stride & 3) == 0) && (((uintptr_t)src & 15) == 0)) {
+      const float4 a = *(const float4 *)sp, b = *(const float4 *)(sp + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; t++) v[t] = (c + t < cols) ? sp[t] : 0.0f;
+    }
+    uint4 o;
+    __nv_bfloat162 p;
+    p = __floats2bfloat162_rn(v[0], v[1]); o.x = *(const uint32_t *)&p;
+    p = __floats2bfloat162_rn(v[2], v[3]); o.y = *(const uint32_t *)&p;
+    p = __floats2bfloat162_rn(v[4], v[5]); o.z = *(const uint32_t *)&p;
+    p = __floats2bfloat162_rn(v[6], v[7]); o.w = *(const uint32_t *)&p;
+    *(uint4 *)(dst + (size_t)r * dst_stride + c) = o;
+  }
+}
+
+int launch_to_bf16(TnbContext *ctx, uint16_t *dst, int dst_stride, const float *src, int rows, int cols, int src_stride) {
+  TNB_ARG(ctx && dst && src, "null");
+  TNB_ARG(rows >= 0 && cols >= 0 && dst_stride >= cols && src_stride >= cols, "dims");
+  TNB_ARG((dst_stride % 8) == 0 && ((uintptr_t)dst % 16) == 0, "bf16 arrays need a 16-byte aligned base and a pitch multiple of 8");
+  if (rows == 0 || cols == 0) return TNB_OK;
+  const long total = (long)rows * (dst_stride >> 3);
+  long blocks = (total + 255) / 256, cap = (long)ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  to_bf16_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(dst, dst_stride, src, rows, cols, src_stride);
+  TNB_LAUNCHED(ctx);
+  return TNB_OK;
+}
+
 }  // namespace tnb
 
 using namespace tnb;
@@ -404,6 +446,10 @@ int tnb_add_gauss_noise(TnbContext *ctx, float *tgt, float gscale, unsigned *z1,
   return launch_rand<3>(ctx, tgt, nullptr, gscale, z1, z2, z3, z4, d);
 }
 
+int tnb_to_bf16(TnbContext *ctx, uint16_t *dst, int dst_stride, const float *src, TnbMatrixDim d) {
+  return launch_to_bf16(ctx, dst, dst_stride, src, d.rows, d.cols, d.stride);
+}
+
 int tnb_affine_grad(TnbContext *ctx, const float *X, TnbMatrixDim dX, const float *E, TnbMatrixDim dE, float *G, TnbMatrixDim dG,
                     float *gb) {
   TNB_ARG(ctx && X && E && G, "null");
@@ -432,6 +478,37 @@ int tnb_affine_update(TnbContext *ctx, const float *X, TnbMatrixDim dX, const fl
   int rc = launch_gemm(ctx, 'T', 'N', dX.cols, dE.cols, dX.rows, X, dX.stride, E, dE.stride, ep);
   if (rc != TNB_OK) return rc;
   // corrb = colsum(E) + mmt*corrb ; b += scale*corrb   (one reduction + one combine/update kernel)
+  return launch_colsum_update(ctx, 1.0f, E, mmt, corrb, dE.rows, dE.cols, dE.stride, bias, scale);
+}
+
+int tnb_affine_grad_bf16(TnbContext *ctx, const uint16_t *X16, int ldx16, TnbMatrixDim dX, const uint16_t *E16, int lde16,
+                         const float *E, TnbMatrixDim dE, float *G, TnbMatrixDim dG, float *gb) {
+  TNB_ARG(ctx && X16 && E16 && G, "null");
+  TNB_ARG(dX.rows == dE.rows && dG.rows == dX.cols && dG.cols == dE.cols, "dimension mismatch");
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.C = G; ep.ldc = dG.stride; ep.alpha = 1.0f; ep.beta = 0.0f;
+  int rc = launch_gemm_bf16(ctx, 'T', 'N', dX.cols, dE.cols, dX.rows, X16, ldx16, E16, lde16, ep);
+  if (rc != TNB_OK) return rc;
+  if (gb) { TNB_ARG(E, "the bias gradient is summed from the fp32 error"); return launch_colsum(ctx, 1.0f, E, 0.0f, gb, dE.rows, dE.cols, dE.stride); }
+  return TNB_OK;
+}
+
+int tnb_affine_update_bf16(TnbContext *ctx, const uint16_t *X16, int ldx16, TnbMatrixDim dX, const uint16_t *E16, int lde16,
+                           const float *E, TnbMatrixDim dE, float *W, TnbMatrixDim dW, uint16_t *W16, int ldw16, float *bias,
+                           float *corrW, float *corrb, float lr, float mmt, float wc, int gdf, int n_frames_global) {
+  TNB_ARG(ctx && X16 && E16 && E && W && bias && corrW && corrb, "null");
+  TNB_ARG(dX.rows == dE.rows && dW.rows == dX.cols && dW.cols == dE.cols, "dimension mismatch");
+  const int rows = n_frames_global > 0 ? n_frames_global : dX.rows;
+  float scale, l2;
+  update_scalars(lr, mmt, wc, gdf, rows, &scale, &l2);
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.C = corrW; ep.ldc = dW.stride; ep.alpha = 1.0f; ep.beta = mmt;
+  ep.W = W; ep.ldw = dW.stride; ep.w_scale = scale; ep.w_l2 = l2; ep.mode = EPI_UPD;
+  ep.W16 = W16; ep.ldw16 = ldw16;
+  int rc = launch_gemm_bf16(ctx, 'T', 'N', dX.cols, dE.cols, dX.rows, X16, ldx16, E16, lde16, ep);
+  if (rc != TNB_OK) return rc;
   return launch_colsum_update(ctx, 1.0f, E, mmt, corrb, dE.rows, dE.cols, dE.stride, bias, scale);
 }
 

@@ -12,6 +12,8 @@ struct EpiParams {
   const float *mulY; int ldy;   // out *= y*(1-y)              (CuSigmoid::BackpropagateFnc)
   float *W; int ldw;            // fused SGD: W += w_scale*out ; W += w_l2*W
   float w_scale, w_l2;
+  uint16_t *C16; int ldc16;     // optional bf16 copy of the stored output (TNB_MATH_BF16 shadows)
+  uint16_t *W16; int ldw16;     // optional bf16 copy of the updated weights
   int mode;                     // EPI_*: which specialised epilogue the fused entry point asks for (EPI_GENERIC = any combination)
 };
 
@@ -42,7 +44,7 @@ constexpr int CONV_THREADS = CONV_WARPS * 32;
 constexpr int GEMM_THREADS = 64 + CONV_THREADS;     // + TMA warp + MMA warp
 
 // Defined in gemm_kernel.cuh and explicitly instantiated, tile shape by tile shape, in the gemm_inst_*.cu translation units.
-// BN: tile width; NTERMS: 3 = 3xTF32, 1 = single tf32 pass; CG: CTAs per tile (2 = tcgen05 cta_group::2 pair); SPLIT: split-K factor.
+// BN: tile width; NTERMS: 3 = 3xTF32, 1 = single tf32 pass, 16 = bf16 operands (16-bit arrays in HBM); CG: CTAs per tile (2 = tcgen05 cta_group::2 pair); SPLIT: split-K factor.
 template <int BN, int NTERMS, int CG, int SPLIT>
 int launch_tc_major(TnbContext *ctx, int a_mn, int b_mn, const CUtensorMap &tmA, const CUtensorMap &tmB, int M, int N, int K,
                     const EpiParams &ep);
@@ -53,5 +55,12 @@ int tc_max_active_clusters(int *clusters);
 // (reference: src/CuBaseLib/cumatrix.tcc:335-370).
 int launch_gemm(TnbContext *ctx, char transa, char transb, int M, int N, int K, const float *A, int lda, const float *B,
                 int ldb, const EpiParams &ep);
+// the same contraction with bf16 operands (row-major bf16 arrays, pitch in elements a multiple of 8; TMA + kind::f16 MMA)
+int launch_gemm_bf16(TnbContext *ctx, char transa, char transb, int M, int N, int K, const uint16_t *A, int lda,
+                     const uint16_t *B, int ldb, const EpiParams &ep);
+// A16 = bf16_rn(A) for a [rows x cols] fp32 matrix (elementwise.cu)
+int launch_to_bf16(TnbContext *ctx, uint16_t *dst, int dst_stride, const float *src, int rows, int cols, int src_stride);
+// ctx-owned bf16 scratch copies of fp32 operands (generic entry points in TNB_MATH_BF16): slot 0 / 1
+int bf16_scratch(TnbContext *ctx, int slot, const float *src, int rows, int cols, int stride, uint16_t **out, int *out_stride);
 
 }  // namespace tnb

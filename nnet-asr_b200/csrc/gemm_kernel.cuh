@@ -2,6 +2,8 @@
 // Included by gemm_sm100.cu (dispatcher) and by the gemm_inst_*.cu translation units that instantiate groups of tile shapes
 // (split so that `make -j` compiles them in parallel).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -84,6 +86,25 @@ template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
   else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+// kind::f16 (bf16 operands, fp32 accumulate): M x N x 16 per instruction
+template <int CG>
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 template <int CG>
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -199,6 +220,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   using Cfg = GemmCfg<BN, NTERMS, CG>;
   constexpr int BH = Cfg::BH;
   constexpr int STAGES = Cfg::STAGES;
+  // NTERMS == 16: bf16 operands in HBM (TNB_MATH_BF16).  A 128-byte smem row then holds 64 elements instead of 32, so a K block
+  // is 64 deep and an MN-major chunk 64 wide; the stage geometry IN BYTES is the same as for fp32/tf32.
+  constexpr bool BF = (NTERMS == 16);
+  constexpr int BKE = BF ? 64 : 32;   // elements per K block (one 128-byte swizzle span)
+  constexpr int CW = BF ? 64 : 32;    // M/N elements per 128-byte row of an MN-major chunk
+  constexpr int CHUNK_BYTES = BKE * 128;
+  static_assert(!B_MN || BH % CW == 0, "an MN-major B tile is staged in whole 128-byte chunks");
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t *bars = (uint64_t *)(smem + STAGES * Cfg::STAGE_BYTES);
@@ -221,7 +249,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // consecutive CTAs (a pair when CG == 2) take consecutive 128-row blocks of the same N tile; with SPLIT the next pair repeats them
   const int m0 = (int)(blockIdx.x / (CG * SPLIT)) * (BM * CG) + (int)rank * BM;
   const int n0 = blockIdx.y * BN;
-  const int total_kb = (K + BK - 1) / BK;
+  const int total_kb = (K + BKE - 1) / BKE;
   const int kb_begin = (SPLIT == 1) ? 0 : (int)split * ((total_kb + 1) / 2);
   const int num_kb = (SPLIT == 1) ? total_kb : (split == 0 ? (total_kb + 1) / 2 : total_kb / 2);
 
@@ -261,21 +289,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&empty_bar[s], ph ^ 1);
         DBG_TS(0, kb);
         mbar_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
-        const int k0 = (kb_begin + kb) * BK;
+        const int k0 = (kb_begin + kb) * BKE;
         if (A_MN == 0) {
           tma_load_2d(stage_a(s), &tmA, &full_bar[s], k0, m0);  // box 32(k) x 128(m)
         } else {
 #pragma unroll
-          for (int j = 0; j < BM / 32; j++)  // box 32(m) x 32(k), one 4 KB chunk per 32 m
-            tma_load_2d(stage_a(s) + j * (BK * 128), &tmA, &full_bar[s], m0 + 32 * j, k0);
+          for (int j = 0; j < BM / CW; j++)  // box CW(m) x BKE(k): one chunk of 128-byte rows per CW m
+            tma_load_2d(stage_a(s) + j * CHUNK_BYTES, &tmA, &full_bar[s], m0 + CW * j, k0);
         }
         const int nb = n0 + (int)rank * BH;  // this CTA's part of the B tile
         if (B_MN == 0) {
           tma_load_2d(stage_b(s), &tmB, &full_bar[s], k0, nb);  // box 32(k) x BH(n)
         } else {
 #pragma unroll
-          for (int j = 0; j < BH / 32; j++)
-            tma_load_2d(stage_b(s) + j * (BK * 128), &tmB, &full_bar[s], nb + 32 * j, k0);
+          for (int j = 0; j < BH / CW; j++)
+            tma_load_2d(stage_b(s) + j * CHUNK_BYTES, &tmB, &full_bar[s], nb + CW * j, k0);
         }
       }
     }
@@ -285,14 +313,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0 && rank == 0) {
       // instruction descriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, a_major [15], b_major [16],
       // N>>3 [17,23), M>>4 [24,29)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) |
+      // (bf16: A = B = 1, kind::f16)
+      constexpr uint32_t FMT = BF ? 1u : 2u;
+      const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
-      // K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); a K step of 8 floats = +32 B
-      // MN-major: 32-float chunks BK*128 B apart (LBO), 4-k-row swizzle groups 512 B apart (SBO); a K step of 8 rows = +1024 B
-      const uint32_t a_lbo = A_MN ? BK * 128 : 16, b_lbo = B_MN ? BK * 128 : 16;
-      const uint32_t a_sbo = A_MN ? 512 : 1024, b_sbo = B_MN ? 512 : 1024;
-      const uint32_t a_lt = A_MN ? 1 : 2, b_lt = B_MN ? 1 : 2;
-      const uint32_t a_kstep = A_MN ? 1024 : 32, b_kstep = B_MN ? 1024 : 32;
+      // K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); a K step (8 floats / 16 bf16) = +32 B
+      // MN-major fp32: 32-float chunks CHUNK_BYTES apart (LBO), 4-k-row swizzle groups 512 B apart (SBO), layout SWIZZLE_128B_BASE32B;
+      //                a K step of 8 rows = +1024 B
+      // MN-major bf16: 64-element chunks CHUNK_BYTES apart (LBO), 8-k-row swizzle groups 1024 B apart (SBO), layout SWIZZLE_128B;
+      //                a K step of 16 rows = +2048 B
+      constexpr uint32_t MN_SBO = BF ? 1024 : 512, MN_LT = BF ? 2 : 1, MN_KSTEP = BF ? 2048 : 1024;
+      const uint32_t a_lbo = A_MN ? CHUNK_BYTES : 16, b_lbo = B_MN ? CHUNK_BYTES : 16;
+      const uint32_t a_sbo = A_MN ? MN_SBO : 1024, b_sbo = B_MN ? MN_SBO : 1024;
+      const uint32_t a_lt = A_MN ? MN_LT : 2, b_lt = B_MN ? MN_LT : 2;
+      const uint32_t a_kstep = A_MN ? MN_KSTEP : 32, b_kstep = B_MN ? MN_KSTEP : 32;
       for (int kb = 0; kb < num_kb; kb++) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -312,6 +346,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             umma_tf32<CG>(tmem_base, dal, dbh, idesc, first);
             umma_tf32<CG>(tmem_base, dah, dbl, idesc, 1u);
             umma_tf32<CG>(tmem_base, dah, dbh, idesc, 1u);
+          } else if (BF) {
+            umma_bf16<CG>(tmem_base, dah, dbh, idesc, first);
           } else {
             umma_tf32<CG>(tmem_base, dah, dbh, idesc, first);
           }
@@ -384,6 +420,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int r8 = lane >> 3;            // row offset (0..3) inside a group of 4 rows
   const int nchunks = (SPLIT == 2) ? HALFC : BN / 32;
   const int row0 = m0 + q * 32 + r8;   // this lane's rows: row0 + 4k, k = 0..7
+  // optional bf16 twins of the outputs (TNB_MATH_BF16: the next GEMM reads these instead of converting the fp32 arrays)
+  auto st16 = [&](uint16_t *base, int ld, int row, int n, const float4 &o) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+    uint2 u;
+    u.x = *(const uint32_t *)&lo; u.y = *(const uint32_t *)&hi;
+    *(uint2 *)(base + (size_t)row * ld + n) = u;
+  };
   float4 pa[8], pb[8];                 // prefetched epilogue operands of the current chunk: EPI_DX: pa = y ; EPI_UPD: pa = C_old, pb = W
   auto chunk_col = [&](int ci) { return n0 + ((SPLIT == 2) ? (int)split * HALFC + ci : ci) * 32 + cg4; };
   auto prefetch_chunk = [&](int ci) {
@@ -465,7 +508,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const float4 a4 = acc_at(k);
             float4 o = make_float4(a4.x + bv.x, a4.y + bv.y, a4.z + bv.z, a4.w + bv.w);
             if (sig) { o.x = sigmoidf_ref(o.x); o.y = sigmoidf_ref(o.y); o.z = sigmoidf_ref(o.z); o.w = sigmoidf_ref(o.w); }
-            if (row < M) *(float4 *)(ep.C + (size_t)row * ep.ldc + n) = o;
+            if (row < M) {
+              *(float4 *)(ep.C + (size_t)row * ep.ldc + n) = o;
+              if (ep.C16) st16(ep.C16, ep.ldc16, row, n, o);
+            }
           }
         } else if (EPI == EPI_DX) {
 #pragma unroll
@@ -478,6 +524,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               o.x = (y.x * (1.0f - y.x)) * a4.x; o.y = (y.y * (1.0f - y.y)) * a4.y;
               o.z = (y.z * (1.0f - y.z)) * a4.z; o.w = (y.w * (1.0f - y.w)) * a4.w;
               *(float4 *)(ep.C + (size_t)row * ep.ldc + n) = o;
+              if (ep.C16) st16(ep.C16, ep.ldc16, row, n, o);
             }
           }
         } else if (EPI == EPI_UPD) {
@@ -502,6 +549,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 w.z = ep.w_l2 * w.z + w.z; w.w = ep.w_l2 * w.w + w.w;
               }
               *(float4 *)(ep.W + (size_t)row * ep.ldw + n) = w;
+              if (ep.W16) st16(ep.W16, ep.ldw16, row, n, w);
             }
           }
         } else {
@@ -520,6 +568,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               o.z = epi_one(ep, a4.z, cold.z, bv.z, yv.z);
               o.w = epi_one(ep, a4.w, cold.w, bv.w, yv.w);
               *(float4 *)(ep.C + crow + n) = o;
+              if (ep.C16) st16(ep.C16, ep.ldc16, row, n, o);
               if (ep.W) {
                 float4 *wp = (float4 *)(ep.W + (size_t)row * ep.ldw + n);
                 float4 w = *wp;
@@ -530,6 +579,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   w.z = ep.w_l2 * w.z + w.z; w.w = ep.w_l2 * w.w + w.w;
                 }
                 *wp = w;
+                if (ep.W16) st16(ep.W16, ep.ldw16, row, n, w);
               }
             }
           }
@@ -549,11 +599,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             float yv = ep.mulY ? ep.mulY[(size_t)row * ep.ldy + n + t] : 0.0f;
             float o = epi_one(ep, acc[t], cold, bs, yv);
             ep.C[crow + n + t] = o;
+            if (ep.C16) ep.C16[(size_t)row * ep.ldc16 + n + t] = __bfloat16_as_ushort(__float2bfloat16_rn(o));
             if (ep.W) {
               float *wp = ep.W + (size_t)row * ep.ldw + n + t;
               float w = ep.w_scale * o + *wp;
               if (ep.w_l2 != 0.0f) w = ep.w_l2 * w + w;
               *wp = w;
+              if (ep.W16) ep.W16[(size_t)row * ep.ldw16 + n + t] = __bfloat16_as_ushort(__float2bfloat16_rn(w));
             }
           }
         }

@@ -108,6 +108,17 @@ int launch_gemm(TnbContext *ctx, char transa, char transb, int M, int N, int K, 
   const int ta = (transa == 'T' || transa == 't'), tb = (transb == 'T' || transb == 't');
   TNB_ARG(ta || transa == 'N' || transa == 'n', "transa");
   TNB_ARG(tb || transb == 'N' || transb == 'n', "transb");
+  if (ctx->math_mode == TNB_MATH_BF16) {
+    // fp32 operands in bf16 mode: round both to bf16 in ctx scratch, then the bf16 tensor-core path (the fused layer ops have
+    // *_bf16 entry points that take resident bf16 twins instead)
+    uint16_t *a16 = nullptr, *b16 = nullptr;
+    int lda16 = 0, ldb16 = 0;
+    int rc = bf16_scratch(ctx, 0, A, ta ? K : M, ta ? M : K, lda, &a16, &lda16);
+    if (rc != TNB_OK) return rc;
+    rc = bf16_scratch(ctx, 1, B, tb ? N : K, tb ? K : N, ldb, &b16, &ldb16);
+    if (rc != TNB_OK) return rc;
+    return launch_gemm_bf16(ctx, transa, transb, M, N, K, a16, lda16, b16, ldb16, ep);
+  }
   const bool vec_ok = ((uintptr_t)ep.C % 16 == 0) && (ep.ldc % 4 == 0) && (!ep.bias || (uintptr_t)ep.bias % 16 == 0) &&
                       (!ep.mulY || ((uintptr_t)ep.mulY % 16 == 0 && ep.ldy % 4 == 0)) &&
                       (!ep.W || ((uintptr_t)ep.W % 16 == 0 && ep.ldw % 4 == 0));
@@ -196,6 +207,77 @@ int launch_gemm(TnbContext *ctx, char transa, char transb, int M, int N, int K, 
   return TNB_ERR_UNSUPPORTED;
 }
 
+// ----------------------------------------------------------------------------------------------- bf16 operands
+// Same kernel family with NTERMS = 16: 64-deep K blocks of bf16, tcgen05.mma kind::f16, no converter warps.  Tile choice: the
+// MMA needs 2*BN cycles per K block (4 instructions of 128 x BN x 16 per SM at 8192 flop/clk), the operand fetch
+// (16 KB + 128 B * BH per CTA and K block) arrives at about 42 B/clk/SM when every SM pulls from L2 at once (LTS cap / 148).
+int launch_gemm_bf16(TnbContext *ctx, char transa, char transb, int M, int N, int K, const uint16_t *A, int lda,
+                     const uint16_t *B, int ldb, const EpiParams &ep) {
+  TNB_ARG(ctx != nullptr, "null ctx");
+  TNB_ARG(M > 0 && N > 0 && K > 0, "empty GEMM");
+  TNB_ARG(A && B && ep.C, "null operand");
+  const int ta = (transa == 'T' || transa == 't'), tb = (transb == 'T' || transb == 't');
+  TNB_ARG(ta || transa == 'N' || transa == 'n', "transa");
+  TNB_ARG(tb || transb == 'N' || transb == 'n', "transb");
+  TNB_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && (lda % 8 == 0) && (ldb % 8 == 0),
+          "bf16 operands must be 16-byte aligned with a pitch multiple of 8 elements");
+  TNB_ARG(((uintptr_t)ep.C % 16 == 0) && (ep.ldc % 4 == 0) && (!ep.bias || (uintptr_t)ep.bias % 16 == 0) &&
+              (!ep.mulY || ((uintptr_t)ep.mulY % 16 == 0 && ep.ldy % 4 == 0)) && (!ep.W || ((uintptr_t)ep.W % 16 == 0 && ep.ldw % 4 == 0)) &&
+              (!ep.C16 || ((uintptr_t)ep.C16 % 8 == 0 && ep.ldc16 % 4 == 0)) && (!ep.W16 || ((uintptr_t)ep.W16 % 8 == 0 && ep.ldw16 % 4 == 0)),
+          "epilogue arrays must be 16-byte aligned with a pitch multiple of 4 elements");
+  const int a_mn = ta ? 1 : 0, b_mn = tb ? 0 : 1;
+  const int num_kb = (K + 63) / 64;
+  static int force_bn = -1, force_cg = -1, force_split = -1;
+  if (force_bn < 0) { const char *e = getenv("TNB_GEMM_BN"); force_bn = e ? atoi(e) : 0; }
+  if (force_cg < 0) { const char *e = getenv("TNB_GEMM_CG"); force_cg = e ? atoi(e) : 0; }
+  if (force_split < 0) { const char *e = getenv("TNB_GEMM_SPLIT"); force_split = e ? atoi(e) : 0; }
+  int bn = 128, cg = 1, split = 1;
+  double best = 1e300;
+  const int cands[3] = {64, 128, 256};
+  for (int g = 1; g <= 2; g++) {
+    if (force_cg && g != force_cg) continue;
+    if (g == 2 && M <= BM && !force_cg) continue;
+    for (int ci = 0; ci < 3; ci++) {
+      const int c = cands[ci];
+      if (force_bn && c != force_bn) continue;
+      if (g == 2 && c == 64) continue;
+      if (c > 64 && N <= c / 2) continue;
+      int mt = (M + BM - 1) / BM;
+      if (g == 2) mt = (mt + 1) & ~1;
+      const double fetch = (16384.0 + 128.0 * c / g) / 42.0, mma = 2.0 * c;
+      for (int sp = 1; sp <= 2; sp++) {
+        if (force_split == 1 && sp == 2) continue;
+        if (sp == 2 && (g != 2 || num_kb < 8)) continue;
+        if (force_split == 2 && sp == 1 && g == 2 && num_kb >= 8) continue;
+        const long ctas = (long)mt * ((N + c - 1) / c) * sp;
+        const long cap = (g * sp == 1) ? ctx->sm_count : cluster_capacity(ctx, g * sp);
+        const long waves = (ctas + cap - 1) / cap;
+        const double t = ((num_kb + sp - 1) / sp) * (fetch > mma ? fetch : mma) + 4000.0 + 30.0 * c / sp + (sp == 2 ? 2500.0 + 8.0 * c : 0.0);
+        const double cost = waves * t;
+        if (cost < best * 0.999) { best = cost; bn = c; cg = g; split = sp; }
+      }
+    }
+  }
+  const int bh = bn / cg;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a_mn) rc = get_tmap(ctx, A, M, K, lda, BM, 64, 0, &tmA, 2);   // rows = m, cols = k, box 128 x 64
+  else rc = get_tmap(ctx, A, K, M, lda, 64, 64, 0, &tmA, 2);         // rows = k, cols = m, box 64 x 64
+  if (rc != TNB_OK) return rc;
+  if (!b_mn) rc = get_tmap(ctx, B, N, K, ldb, bh, 64, 0, &tmB, 2);   // rows = n, cols = k, box BH x 64
+  else rc = get_tmap(ctx, B, K, N, ldb, 64, 64, 0, &tmB, 2);         // rows = k, cols = n, box 64 x 64
+  if (rc != TNB_OK) return rc;
+  if (getenv("TNB_GEMM_DEBUG"))
+    fprintf(stderr, "[tnb] gemm bf16 %c%c M=%d N=%d K=%d -> BN=%d CG=%d SPLIT=%d\n", transa, transb, M, N, K, bn, cg, split);
+#define TNB_TRY(BN_, CG_, SP_) \
+  if (bn == BN_ && cg == CG_ && split == SP_) return launch_tc_major<BN_, 16, CG_, SP_>(ctx, a_mn, b_mn, tmA, tmB, M, N, K, ep);
+  TNB_TRY(256, 2, 2) TNB_TRY(128, 2, 2) TNB_TRY(256, 2, 1) TNB_TRY(128, 2, 1)
+  TNB_TRY(256, 1, 1) TNB_TRY(128, 1, 1) TNB_TRY(64, 1, 1)
+#undef TNB_TRY
+  set_error("no bf16 GEMM instance for BN=%d CG=%d SPLIT=%d", bn, cg, split);
+  return TNB_ERR_UNSUPPORTED;
+}
+
 // ----------------------------------------------------------------------------------------------- gemv / ger
 // reference: CuMath<float>::OffsetGemv (cumath.cc:283-340), used only by CuRecurrent (batch-1, frame-serial)
 __global__ void gemv_n_kernel(float alpha, const float *__restrict__ A, int lda, int row_off, int nrows, int ncols,
@@ -262,6 +344,33 @@ int tnb_affine_bwd_dx(TnbContext *ctx, const float *E, TnbMatrixDim dE, const fl
   ep.mulY = Yprev; ep.ldy = dYprev.stride;
   if (Yprev) ep.mode = EPI_DX;
   return launch_gemm(ctx, 'N', 'T', dE.rows, dW.rows, dE.cols, E, dE.stride, W, dW.stride, ep);
+}
+
+int tnb_affine_fwd_bf16(TnbContext *ctx, const uint16_t *X16, int ldx16, TnbMatrixDim dX, const uint16_t *W16, int ldw16,
+                        TnbMatrixDim dW, const float *bias, float *Y, TnbMatrixDim dY, uint16_t *Y16, int ldy16, int act) {
+  TNB_ARG(ctx && X16 && W16 && bias && Y, "null");
+  TNB_ARG(dX.cols == dW.rows && dY.cols == dW.cols && dY.rows == dX.rows, "dimension mismatch");
+  TNB_ARG(act == TNB_ACT_NONE || act == TNB_ACT_SIGMOID, "act");
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.C = Y; ep.ldc = dY.stride; ep.alpha = 1.0f; ep.beta = 0.0f; ep.bias = bias; ep.act = act; ep.mode = EPI_FWD;
+  ep.C16 = Y16; ep.ldc16 = ldy16;
+  return launch_gemm_bf16(ctx, 'N', 'N', dX.rows, dW.cols, dX.cols, X16, ldx16, W16, ldw16, ep);
+}
+
+int tnb_affine_bwd_dx_bf16(TnbContext *ctx, const uint16_t *E16, int lde16, TnbMatrixDim dE, const uint16_t *W16, int ldw16,
+                           TnbMatrixDim dW, const float *Yprev, TnbMatrixDim dYprev, float *Eprev, TnbMatrixDim dEprev,
+                           uint16_t *Eprev16, int ldep16) {
+  TNB_ARG(ctx && E16 && W16 && Eprev, "null");
+  TNB_ARG(dE.cols == dW.cols && dEprev.cols == dW.rows && dEprev.rows == dE.rows, "dimension mismatch");
+  if (Yprev) TNB_ARG(dYprev.rows == dEprev.rows && dYprev.cols == dEprev.cols, "Yprev dims");
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.C = Eprev; ep.ldc = dEprev.stride; ep.alpha = 1.0f; ep.beta = 0.0f;
+  ep.mulY = Yprev; ep.ldy = dYprev.stride;
+  if (Yprev) ep.mode = EPI_DX;
+  ep.C16 = Eprev16; ep.ldc16 = ldep16;
+  return launch_gemm_bf16(ctx, 'N', 'T', dE.rows, dW.rows, dE.cols, E16, lde16, W16, ldw16, ep);
 }
 
 int tnb_offset_gemv(TnbContext *ctx, char trans, float alpha, const float *A, TnbMatrixDim dA, const float *x, int dimX,

@@ -54,6 +54,7 @@ class CuDevice {
     return mCtx;
   }
   void SetMath(int mode) { mMath = mode; if (mCtx) TNB_CHECK(tnb_ctx_set_math(mCtx, mode)); }
+  int Math() { int m = 0; TNB_CHECK(tnb_ctx_get_math(Ctx(), &m)); return m; }
   void Sync() { TNB_CHECK(tnb_ctx_sync(Ctx())); }
   void AccuProfile(const std::string &key, double time) { mProfile[key] += time; }
   void PrintProfile() {
@@ -75,7 +76,7 @@ class CuDevice {
     const char *e = getenv("TNB_DEVICE");
     if (e) mSelected = atoi(e);
     const char *m = getenv("TNB_MATH");
-    if (m) mMath = !strcmp(m, "tf32") ? TNB_MATH_TF32 : (!strcmp(m, "simt") ? TNB_MATH_FP32_SIMT : TNB_MATH_3XTF32);
+    if (m) mMath = !strcmp(m, "tf32") ? TNB_MATH_TF32 : (!strcmp(m, "simt") ? TNB_MATH_FP32_SIMT : (!strcmp(m, "bf16") ? TNB_MATH_BF16 : TNB_MATH_3XTF32));
   }
   CuDevice(const CuDevice &);
   TnbContext *mCtx;
@@ -92,8 +93,11 @@ template <typename T> class CuVector;
 template <typename T>
 class CuMatrix {
  public:
-  CuMatrix() : mRows(0), mCols(0), mStride(0), mCap(0), mpCUData(NULL) {}
-  CuMatrix(size_t rows, size_t cols) : mRows(0), mCols(0), mStride(0), mCap(0), mpCUData(NULL) { Init(rows, cols); }
+  CuMatrix() : mRows(0), mCols(0), mStride(0), mCap(0), mpCUData(NULL), mpTwin(NULL), mTwinCap(0), mTwinStride(0), mTwinValid(false) {}
+  CuMatrix(size_t rows, size_t cols)
+      : mRows(0), mCols(0), mStride(0), mCap(0), mpCUData(NULL), mpTwin(NULL), mTwinCap(0), mTwinStride(0), mTwinValid(false) {
+    Init(rows, cols);
+  }
   ~CuMatrix() { Destroy(); }
 
   size_t Rows() const { return mRows; }
@@ -101,15 +105,32 @@ class CuMatrix {
   size_t Stride() const { return mStride; }
   TnbMatrixDim Dim() const { TnbMatrixDim d = {(int)mRows, (int)mCols, (int)mStride}; return d; }
   const T *pCUData() const { return mpCUData; }
-  T *pCUData() { return mpCUData; }
+  T *pCUData() { mTwinValid = false; return mpCUData; }  // a mutable pointer may be written through: the bf16 twin goes stale
   const T *pCURowData(size_t r) const { assert(r < mRows); return mpCUData + r * mStride; }
-  T *pCURowData(size_t r) { assert(r < mRows); return mpCUData + r * mStride; }
+  T *pCURowData(size_t r) { assert(r < mRows); mTwinValid = false; return mpCUData + r * mStride; }
   size_t MSize() const { return mRows * mStride * sizeof(T); }
+
+  // ---- bf16 twin (TNB_MATH_BF16): a 16-bit copy of this matrix that the tensor-core GEMMs read instead of converting the fp32
+  // array on every call.  Every mutating method and every mutable-pointer access marks it stale; Twin() refreshes a stale
+  // twin with one conversion kernel; the fused GEMM epilogues that write the fp32 values and their twin together call
+  // TwinForWrite() AFTER taking the mutable fp32 pointer.
+  const uint16_t *Twin() const {
+    AllocTwin();
+    if (!mTwinValid) {
+      TNB_CHECK(tnb_to_bf16(Cx(), mpTwin, (int)mTwinStride, (const float *)mpCUData, Dim()));
+      mTwinValid = true;
+    }
+    return mpTwin;
+  }
+  uint16_t *TwinForWrite() { AllocTwin(); mTwinValid = true; return mpTwin; }
+  int TwinStride() const { return (int)mTwinStride; }
+  bool TwinValid() const { return mTwinValid; }
 
   /// (re)allocate; contents are zeroed only when the dimensions change (cumatrix.tcc:16-34)
   CuMatrix<T> &Init(size_t rows, size_t cols) {
     static_assert(sizeof(T) == 4, "4-byte elements");
     if (mRows == rows && mCols == cols) return *this;
+    mTwinValid = false;
     size_t stride = ((cols + 31) / 32) * 32;
     if (stride == 0) stride = 32;
     size_t need = (rows ? rows : 1) * stride;
@@ -129,18 +150,25 @@ class CuMatrix {
   }
   void Destroy() {
     if (mpCUData) tnb_free(Cx(), mpCUData);
+    if (mpTwin) tnb_free(Cx(), mpTwin);
     mpCUData = NULL;
-    mRows = mCols = mStride = mCap = 0;
+    mpTwin = NULL;
+    mRows = mCols = mStride = mCap = mTwinCap = mTwinStride = 0;
+    mTwinValid = false;
   }
 
   CuMatrix<T> &CopyFrom(const CuMatrix<T> &src) {
     Init(src.Rows(), src.Cols());
+    mTwinValid = false;
+
     TNB_CHECK(tnb_memcpy2d(Cx(), mpCUData, mStride * sizeof(T), src.pCUData(), src.Stride() * sizeof(T), src.Cols() * sizeof(T),
                            src.Rows(), 2));
     return *this;
   }
   CuMatrix<T> &CopyFrom(const Matrix<T> &src) {
     Init(src.Rows(), src.Cols());
+    mTwinValid = false;
+
     TNB_CHECK(tnb_memcpy2d(Cx(), mpCUData, mStride * sizeof(T), src.pData(), src.Stride() * sizeof(T), src.Cols() * sizeof(T),
                            src.Rows(), 0));
     CuDevice::Instantiate().Sync();  // pageable source must stay valid until the copy is done
@@ -156,6 +184,7 @@ class CuMatrix {
     assert(rowCnt + srcOri <= src.Rows());
     assert(rowCnt + dstOri <= Rows());
     assert(Cols() == src.Cols());
+    mTwinValid = false;
     TNB_CHECK(tnb_memcpy2d(Cx(), mpCUData + dstOri * mStride, mStride * sizeof(T), src.pCUData() + srcOri * src.Stride(),
                            src.Stride() * sizeof(T), src.Cols() * sizeof(T), rowCnt, 2));
   }
@@ -163,18 +192,20 @@ class CuMatrix {
     assert(colCnt + srcOri <= src.Cols());
     assert(colCnt + dstOri <= Cols());
     assert(Rows() == src.Rows());
+    mTwinValid = false;
     TNB_CHECK(tnb_memcpy2d(Cx(), mpCUData + dstOri, mStride * sizeof(T), src.pCUData() + srcOri, src.Stride() * sizeof(T),
                            colCnt * sizeof(T), Rows(), 2));
   }
-  void SetZero() { if (mpCUData) TNB_CHECK(tnb_memset(Cx(), mpCUData, 0, MSize())); }
+  void SetZero() { mTwinValid = false; if (mpCUData) TNB_CHECK(tnb_memset(Cx(), mpCUData, 0, MSize())); }
 
   // ---- math (float only, as in the reference's specialisations cumatrix.tcc:194-420) ----
-  void SetConst(T v) { TNB_CHECK(tnb_set_const(Cx(), mpCUData, v, Dim())); }
-  void ApplyLog() { TNB_CHECK(tnb_apply_log(Cx(), mpCUData, Dim())); }
+  void SetConst(T v) { mTwinValid = false; TNB_CHECK(tnb_set_const(Cx(), mpCUData, v, Dim())); }
+  void ApplyLog() { mTwinValid = false; TNB_CHECK(tnb_apply_log(Cx(), mpCUData, Dim())); }
   void ScaleCols(const CuVector<T> &scale);
   void ScaleRows(const CuVector<T> &scale);
   void AddScaled(T alpha, const CuMatrix<T> &A, T beta) {
     assert(A.Rows() == Rows() && A.Cols() == Cols() && A.Stride() == Stride());
+    mTwinValid = false;
     TNB_CHECK(tnb_add_scaled(Cx(), alpha, A.pCUData(), beta, mpCUData, Dim()));
   }
   void AddScaledRow(T alpha, const CuVector<T> &row, T beta);
@@ -185,23 +216,43 @@ class CuMatrix {
     size_t n = (transb == 'T' || transb == 't') ? B.Rows() : B.Cols();
     size_t k1 = (transb == 'T' || transb == 't') ? B.Cols() : B.Rows();
     if (m != Rows() || n != Cols() || k != k1) Error("Gemm: non-matching dimensions");
+    mTwinValid = false;
     TNB_CHECK(tnb_gemm(Cx(), transa, transb, (int)m, (int)n, (int)k, alpha, A.pCUData(), (int)A.Stride(), B.pCUData(),
                        (int)B.Stride(), beta, mpCUData, (int)mStride));
   }
   void BlasGer(T alpha, const CuVector<T> &x, const CuVector<T> &y);
   void MulElem(const CuMatrix<T> &A) {
     assert(A.Rows() == Rows() && A.Cols() == Cols() && A.Stride() == Stride());
+    mTwinValid = false;
     TNB_CHECK(tnb_mul_elem(Cx(), mpCUData, A.pCUData(), Dim()));
   }
-  void LogElem() { TNB_CHECK(tnb_log_elem(Cx(), mpCUData, Dim())); }
+  void LogElem() { mTwinValid = false; TNB_CHECK(tnb_log_elem(Cx(), mpCUData, Dim())); }
   void Print() const { Matrix<T> m; CopyTo(m); std::cout << m; }
   void CheckData() const { Matrix<T> m; CopyTo(m); m.CheckData(); }
 
  private:
   CuMatrix(const CuMatrix<T> &);
   CuMatrix<T> &operator=(const CuMatrix<T> &);
+  void AllocTwin() const {
+    static_assert(sizeof(T) == 4, "4-byte elements");
+    const size_t st = ((mCols + 63) / 64) * 64, need = (mRows ? mRows : 1) * (st ? st : 64);
+    if (need > mTwinCap || st != mTwinStride) {
+      if (mpTwin) tnb_free(Cx(), mpTwin);
+      mpTwin = NULL;
+      void *p = NULL;
+      int got = 0;
+      TNB_CHECK(tnb_malloc_pitch16(Cx(), &p, &got, (int)mRows, (int)mCols));
+      mpTwin = (uint16_t *)p;
+      mTwinCap = need;
+      mTwinStride = (size_t)got;
+      mTwinValid = false;
+    }
+  }
   size_t mRows, mCols, mStride, mCap;
   T *mpCUData;
+  mutable uint16_t *mpTwin;
+  mutable size_t mTwinCap, mTwinStride;
+  mutable bool mTwinValid;
 };
 
 /// Device vector (reference: cuvector.h:14-85)
@@ -273,11 +324,13 @@ class CuVector {
 template <typename T>
 inline void CuMatrix<T>::ScaleCols(const CuVector<T> &scale) {
   assert(scale.Dim() == Cols());
+  mTwinValid = false;
   TNB_CHECK(tnb_scale_cols(Cx(), mpCUData, scale.pCUData(), Dim()));
 }
 template <typename T>
 inline void CuMatrix<T>::ScaleRows(const CuVector<T> &scale) {
   assert(scale.Dim() == Rows());
+  mTwinValid = false;
   TNB_CHECK(tnb_scale_rows(Cx(), mpCUData, scale.pCUData(), Dim()));
 }
 template <typename T>
@@ -287,11 +340,13 @@ inline void CuMatrix<T>::AddScaledRow(T alpha, const CuVector<T> &row, T beta) {
     os << "Non matching dimensions: Cols:" << Cols() << " VectorDim:" << row.Dim();
     Error(os.str());
   }
+  mTwinValid = false;
   TNB_CHECK(tnb_add_scaled_row(Cx(), alpha, row.pCUData(), beta, mpCUData, Dim()));
 }
 template <typename T>
 inline void CuMatrix<T>::BlasGer(T alpha, const CuVector<T> &x, const CuVector<T> &y) {
   assert(x.Dim() == Rows() && y.Dim() == Cols());
+  mTwinValid = false;
   TNB_CHECK(tnb_ger(Cx(), alpha, x.pCUData(), (int)x.Dim(), y.pCUData(), (int)y.Dim(), mpCUData, Dim()));
 }
 

@@ -147,27 +147,57 @@ class CuBiasedLinearity : public CuUpdatableComponent {
   ComponentType GetType() const { return BIASED_LINEARITY; }
   const char *GetName() const { return "<biasedlinearity>"; }
 
-  void PropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) {
-    TNB_CHECK(tnb_affine_fwd(Cx(), X.pCUData(), X.Dim(), mLinearity.pCUData(), mLinearity.Dim(), mBias.pCUData(), Y.pCUData(), Y.Dim(),
-                             TNB_ACT_NONE));
+  // In TNB_MATH_BF16 every GEMM below reads the bf16 twins of its operands (CuMatrix::Twin(): resident, refreshed only when
+  // stale) and writes the twin of its result from the epilogue, so that no conversion pass runs between the layers.
+  static bool Bf16() { return CuDevice::Instantiate().Math() == TNB_MATH_BF16; }
+  void Forward(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y, int act) {
+    const CuMatrix<BaseFloat> &W = mLinearity;
+    if (Bf16()) {
+      const uint16_t *x16 = X.Twin(), *w16 = W.Twin();
+      float *y = Y.pCUData();
+      uint16_t *y16 = Y.TwinForWrite();
+      TNB_CHECK(tnb_affine_fwd_bf16(Cx(), x16, X.TwinStride(), X.Dim(), w16, W.TwinStride(), W.Dim(), mBias.pCUData(), y, Y.Dim(), y16,
+                                    Y.TwinStride(), act));
+    } else {
+      TNB_CHECK(tnb_affine_fwd(Cx(), X.pCUData(), X.Dim(), W.pCUData(), W.Dim(), mBias.pCUData(), Y.pCUData(), Y.Dim(), act));
+    }
   }
-  void BackpropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) {
-    TnbMatrixDim none = {0, 0, 0};
-    TNB_CHECK(tnb_affine_bwd_dx(Cx(), X.pCUData(), X.Dim(), mLinearity.pCUData(), mLinearity.Dim(), NULL, none, Y.pCUData(), Y.Dim()));
-  }
+  void PropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) { Forward(X, Y, TNB_ACT_NONE); }
+  void BackpropagateFnc(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) { BackpropagateDiffSigmoid(X, NULL, Y); }
   /// bias + GEMM + sigmoid in one kernel; Y is the following <sigmoid>'s output buffer
-  void PropagateSigmoid(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) {
-    TNB_CHECK(tnb_affine_fwd(Cx(), X.pCUData(), X.Dim(), mLinearity.pCUData(), mLinearity.Dim(), mBias.pCUData(), Y.pCUData(), Y.Dim(),
-                             TNB_ACT_SIGMOID));
-  }
+  void PropagateSigmoid(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y) { Forward(X, Y, TNB_ACT_SIGMOID); }
   /// dX fused with the diff-sigmoid of the <sigmoid> below: Eprev = (E*W^T) .* Yprev .* (1-Yprev)
   void BackpropagateDiffSigmoid(const CuMatrix<BaseFloat> &E, const CuMatrix<BaseFloat> &Yprev, CuMatrix<BaseFloat> &Eprev) {
-    TNB_CHECK(tnb_affine_bwd_dx(Cx(), E.pCUData(), E.Dim(), mLinearity.pCUData(), mLinearity.Dim(), Yprev.pCUData(), Yprev.Dim(),
-                                Eprev.pCUData(), Eprev.Dim()));
+    BackpropagateDiffSigmoid(E, &Yprev, Eprev);
+  }
+  void BackpropagateDiffSigmoid(const CuMatrix<BaseFloat> &E, const CuMatrix<BaseFloat> *pYprev, CuMatrix<BaseFloat> &Eprev) {
+    const CuMatrix<BaseFloat> &W = mLinearity;
+    TnbMatrixDim none = {0, 0, 0};
+    const float *yp = pYprev ? pYprev->pCUData() : NULL;
+    const TnbMatrixDim dyp = pYprev ? pYprev->Dim() : none;
+    if (Bf16()) {
+      const uint16_t *e16 = E.Twin(), *w16 = W.Twin();
+      float *ep = Eprev.pCUData();
+      uint16_t *ep16 = Eprev.TwinForWrite();
+      TNB_CHECK(tnb_affine_bwd_dx_bf16(Cx(), e16, E.TwinStride(), E.Dim(), w16, W.TwinStride(), W.Dim(), yp, dyp, ep, Eprev.Dim(), ep16,
+                                       Eprev.TwinStride()));
+    } else {
+      TNB_CHECK(tnb_affine_bwd_dx(Cx(), E.pCUData(), E.Dim(), W.pCUData(), W.Dim(), yp, dyp, Eprev.pCUData(), Eprev.Dim()));
+    }
   }
   /// cuBiasedLinearity.cc:44-64, fused into the dW GEMM epilogue
   void Update() {
     const CuMatrix<BaseFloat> &X = GetInput(), &E = GetErrorInput();
+    if (Bf16()) {
+      const uint16_t *x16 = X.Twin(), *e16 = E.Twin();
+      mLinearity.Twin();  // allocate (and fill on first use) so that the epilogue can keep it current from here on
+      float *w = mLinearity.pCUData();
+      uint16_t *w16 = mLinearity.TwinForWrite();
+      TNB_CHECK(tnb_affine_update_bf16(Cx(), x16, X.TwinStride(), X.Dim(), e16, E.TwinStride(), E.pCUData(), E.Dim(), w, mLinearity.Dim(),
+                                       w16, mLinearity.TwinStride(), mBias.pCUData(), mLinearityCorrection.pCUData(),
+                                       mBiasCorrection.pCUData(), mLearningRate, mMomentum, mWeightcost, mGradDivFrm ? 1 : 0, 0));
+      return;
+    }
     TNB_CHECK(tnb_affine_update(Cx(), X.pCUData(), X.Dim(), E.pCUData(), E.Dim(), mLinearity.pCUData(), mLinearity.Dim(), mBias.pCUData(),
                                 mLinearityCorrection.pCUData(), mBiasCorrection.pCUData(), mLearningRate, mMomentum, mWeightcost,
                                 mGradDivFrm ? 1 : 0, 0));
@@ -177,6 +207,12 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     const CuMatrix<BaseFloat> &X = GetInput(), &E = GetErrorInput();
     if (mGrad.Rows() != mNInputs + 1) mGrad.Init(mNInputs + 1, mNOutputs);  // [dW ; db] contiguous: one all-reduce per layer
     TnbMatrixDim dG = mLinearity.Dim();
+    if (Bf16()) {
+      const uint16_t *x16 = X.Twin(), *e16 = E.Twin();
+      TNB_CHECK(tnb_affine_grad_bf16(Cx(), x16, X.TwinStride(), X.Dim(), e16, E.TwinStride(), E.pCUData(), E.Dim(), mGrad.pCUData(), dG,
+                                     mGrad.pCURowData(mNInputs)));
+      return;
+    }
     TNB_CHECK(tnb_affine_grad(Cx(), X.pCUData(), X.Dim(), E.pCUData(), E.Dim(), mGrad.pCUData(), dG, mGrad.pCURowData(mNInputs)));
   }
   float *GradBuffer() { return mGrad.pCUData(); }

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.a
 LIB_PATH = os.path.join(os.environ.get("TNB_LIB_DIR") or os.path.join(ROOT, "nnet-asr_b200", "lib"), "libtnetb200.so")
 
 OK = 0
-MATH_3XTF32, MATH_TF32, MATH_FP32_SIMT = 0, 1, 2
+MATH_3XTF32, MATH_TF32, MATH_FP32_SIMT, MATH_BF16 = 0, 1, 2, 3
 ACT_NONE, ACT_SIGMOID = 0, 1
 H2D, D2H, D2D = 0, 1, 2
 
@@ -139,6 +139,56 @@ class DMat:
         check(lib().tnb_memcpy2d(self.ctx.h, a.ctypes.data_as(C.c_void_p), C.c_size_t(self.cols * 4), self.ptr,
                                  C.c_size_t(self.stride * 4), C.c_size_t(self.cols * 4), C.c_size_t(self.rows), C.c_int(D2H)))
         return a
+
+    def free(self):
+        if self.ptr:
+            lib().tnb_free(self.ctx.h, self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.free()
+        except Exception:
+            pass
+
+
+def bf16_round(a):
+    """fp32 -> nearest-even bf16, returned as fp32 (what __float2bfloat16_rn keeps); finite inputs."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32).reshape(np.shape(a))
+
+
+class DMat16:
+    """Pitched bf16 device matrix (tnb_malloc_pitch16): the twin a TNB_MATH_BF16 GEMM reads instead of the fp32 array."""
+
+    def __init__(self, ctx, rows, cols):
+        self.ctx, self.rows, self.cols = ctx, int(rows), int(cols)
+        self.ptr = C.c_void_p()
+        st = C.c_int()
+        check(lib().tnb_malloc_pitch16(ctx.h, C.byref(self.ptr), C.byref(st), C.c_int(self.rows), C.c_int(self.cols)))
+        self.stride = st.value
+
+    @classmethod
+    def from_fp32(cls, ctx, dmat):
+        m = cls(ctx, dmat.rows, dmat.cols)
+        check(lib().tnb_to_bf16(ctx.h, m.p(), C.c_int(m.stride), dmat.p(), dmat.dim))
+        return m
+
+    def p(self):
+        return C.cast(self.ptr, C.POINTER(C.c_uint16))
+
+    def download_bits(self, full_pitch=False):
+        w = self.stride if full_pitch else self.cols
+        a = np.empty((self.rows, w), dtype=np.uint16)
+        check(lib().tnb_memcpy2d(self.ctx.h, a.ctypes.data_as(C.c_void_p), C.c_size_t(w * 2), self.ptr, C.c_size_t(self.stride * 2),
+                                 C.c_size_t(w * 2), C.c_size_t(self.rows), C.c_int(D2H)))
+        return a
+
+    def download(self):
+        """values as fp32"""
+        return (self.download_bits().astype(np.uint32) << 16).view(np.float32)
 
     def free(self):
         if self.ptr:
