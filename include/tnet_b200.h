@@ -163,6 +163,19 @@ int tnb_affine_grad(TnbContext *ctx, const float *X, TnbMatrixDim dX, const floa
 int tnb_affine_update(TnbContext *ctx, const float *X, TnbMatrixDim dX, const float *E, TnbMatrixDim dE, float *W,
                       TnbMatrixDim dW, float *bias, float *corrW, float *corrb, float lr, float mmt, float wc,
                       int grad_div_frm, int n_frames_global);
+/* bias == NULL && corrb == NULL in tnb_affine_update (and its _bf16 twin): weight half only.  The bias halves of several layers
+ * are then applied together by tnb_bias_update_batch — same arithmetic per layer, two launches for the whole stack instead of two
+ * per layer (CuNetwork::Backpropagate defers them to the end of the pass; nothing reads a bias during backpropagation):
+ *   corrb = colsum(E) + mmt*corrb ; b += (-lr/N)*corrb        with N as in tnb_affine_update */
+#define TNB_MAX_BIAS_JOBS 16
+typedef struct TnbBiasJob_ {
+  const float *E;      /* error at the layer's output [rows x nout] */
+  TnbMatrixDim dE;
+  float *bias, *corrb; /* [nout] */
+  float lr, mmt;
+  int grad_div_frm, n_frames_global;
+} TnbBiasJob;
+int tnb_bias_update_batch(TnbContext *ctx, const TnbBiasJob *jobs, int n);
 /* the same update given an already summed gradient (after the NCCL allreduce):
  *   corrW = G + mmt*corrW ; ... as above.  gb/bias/corrb may be NULL together. */
 int tnb_sgd_update(TnbContext *ctx, const float *G, float *W, float *corrW, TnbMatrixDim dW, const float *gb, float *bias,

@@ -132,6 +132,68 @@ int launch_colsum(TnbContext *ctx, float alpha, const float *mat, float beta, fl
   return launch_colsum_update(ctx, alpha, mat, beta, vec, rows, cols, stride, nullptr, 0.0f);
 }
 
+// The bias halves of several CuBiasedLinearity::Update calls in ONE pair of launches (blockIdx.z = layer): in a deep net the
+// seven per-layer pairs cost more in launch gaps than in work.  Same arithmetic and summation order per layer as above.
+struct BiasBatch {
+  int n;
+  struct { const float *E; int rows, cols, stride, S, chunk; long part_off; float *corrb, *bias; float mmt, scale; } j[TNB_MAX_BIAS_JOBS];
+};
+__global__ void __launch_bounds__(256) colsum_partial_batch_kernel(const __grid_constant__ BiasBatch b, double *part) {
+  const auto &j = b.j[blockIdx.z];
+  if ((int)blockIdx.x * 128 >= j.cols || (int)blockIdx.y >= j.S) return;
+  __shared__ double sm[8][129];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + cx * 4;
+  const int r0 = blockIdx.y * j.chunk, r1 = min(j.rows, r0 + j.chunk);
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+  const float *mat = j.E;
+  const int stride = j.stride, cols = j.cols;
+  const bool vec = ((stride & 3) == 0) && (((uintptr_t)mat & 15) == 0) && (c + 3 < cols);
+  if (vec) {
+    int r = r0 + ry;
+    for (; r + 8 < r1; r += 16) {
+      const float4 a = *(const float4 *)(mat + (size_t)r * stride + c);
+      const float4 bb = *(const float4 *)(mat + (size_t)(r + 8) * stride + c);
+      s0 += a.x; s1 += a.y; s2 += a.z; s3 += a.w;
+      t0 += bb.x; t1 += bb.y; t2 += bb.z; t3 += bb.w;
+    }
+    for (; r < r1; r += 8) {
+      const float4 a = *(const float4 *)(mat + (size_t)r * stride + c);
+      s0 += a.x; s1 += a.y; s2 += a.z; s3 += a.w;
+    }
+  } else {
+    for (int r = r0 + ry; r < r1; r += 8) {
+      const float *p = mat + (size_t)r * stride + c;
+      if (c < cols) s0 += p[0];
+      if (c + 1 < cols) s1 += p[1];
+      if (c + 2 < cols) s2 += p[2];
+      if (c + 3 < cols) s3 += p[3];
+    }
+  }
+  sm[ry][cx * 4 + 0] = s0 + t0; sm[ry][cx * 4 + 1] = s1 + t1; sm[ry][cx * 4 + 2] = s2 + t2; sm[ry][cx * 4 + 3] = s3 + t3;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int cc = blockIdx.x * 128 + threadIdx.x;
+    if (cc < cols) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) t += sm[k][threadIdx.x];
+      part[j.part_off + (size_t)blockIdx.y * cols + cc] = t;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) colsum_final_batch_kernel(const __grid_constant__ BiasBatch b, const double *__restrict__ part) {
+  const auto &j = b.j[blockIdx.y];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= j.cols) return;
+  double t = 0.0;
+  for (int k = 0; k < j.S; k++) t += part[j.part_off + (size_t)k * j.cols + c];
+  const float bb = (j.mmt == 0.0f) ? 0.0f : j.mmt * j.corrb[c];
+  const float v = (float)(t + (double)bb);
+  j.corrb[c] = v;
+  j.bias[c] = j.scale * v + j.bias[c];
+}
+
 // ---------------------------------------------------------------------------------------- gathers
 // _randomize (cukernels.cu:384-393): y[r,:] = x[perm[r],:]   — one warp per row, 16-byte copies
 __global__ void __launch_bounds__(256) gather_rows_kernel(float *__restrict__ y, const float *__restrict__ x,
@@ -465,7 +527,7 @@ int tnb_affine_grad(TnbContext *ctx, const float *X, TnbMatrixDim dX, const floa
 
 int tnb_affine_update(TnbContext *ctx, const float *X, TnbMatrixDim dX, const float *E, TnbMatrixDim dE, float *W, TnbMatrixDim dW,
                       float *bias, float *corrW, float *corrb, float lr, float mmt, float wc, int gdf, int n_frames_global) {
-  TNB_ARG(ctx && X && E && W && bias && corrW && corrb, "null");
+  TNB_ARG(ctx && X && E && W && corrW && ((bias && corrb) || (!bias && !corrb)), "null");
   TNB_ARG(dX.rows == dE.rows && dW.rows == dX.cols && dW.cols == dE.cols, "dimension mismatch");
   const int rows = n_frames_global > 0 ? n_frames_global : dX.rows;
   float scale, l2;
@@ -476,9 +538,46 @@ int tnb_affine_update(TnbContext *ctx, const float *X, TnbMatrixDim dX, const fl
   ep.C = corrW; ep.ldc = dW.stride; ep.alpha = 1.0f; ep.beta = mmt;
   ep.W = W; ep.ldw = dW.stride; ep.w_scale = scale; ep.w_l2 = l2; ep.mode = EPI_UPD;
   int rc = launch_gemm(ctx, 'T', 'N', dX.cols, dE.cols, dX.rows, X, dX.stride, E, dE.stride, ep);
-  if (rc != TNB_OK) return rc;
+  if (rc != TNB_OK || !bias) return rc;
   // corrb = colsum(E) + mmt*corrb ; b += scale*corrb   (one reduction + one combine/update kernel)
   return launch_colsum_update(ctx, 1.0f, E, mmt, corrb, dE.rows, dE.cols, dE.stride, bias, scale);
+}
+
+int tnb_bias_update_batch(TnbContext *ctx, const TnbBiasJob *jobs, int n) {
+  TNB_ARG(ctx && (jobs || n == 0), "null");
+  TNB_ARG(n >= 0 && n <= TNB_MAX_BIAS_JOBS, "between 0 and TNB_MAX_BIAS_JOBS jobs per call");
+  if (n == 0) return TNB_OK;
+  BiasBatch b;
+  memset(&b, 0, sizeof(b));
+  b.n = n;
+  long off = 0;
+  int max_cb = 1, max_S = 1, max_cols = 1;
+  for (int i = 0; i < n; i++) {
+    const TnbBiasJob &q = jobs[i];
+    TNB_ARG(q.E && q.bias && q.corrb, "null");
+    TNB_ARG(q.dE.rows >= 0 && q.dE.cols >= 0 && q.dE.stride >= q.dE.cols, "dims");
+    const int cb = (q.dE.cols + 127) / 128;
+    int S = (2 * ctx->sm_count + cb * n - 1) / (cb * n);  // ~2 CTAs per SM over the whole batch
+    if (S > (q.dE.rows + 31) / 32) S = (q.dE.rows + 31) / 32;
+    if (S < 1) S = 1;
+    float scale, l2;
+    update_scalars(q.lr, q.mmt, 0.0f, q.grad_div_frm, q.n_frames_global > 0 ? q.n_frames_global : q.dE.rows, &scale, &l2);
+    auto &j = b.j[i];
+    j.E = q.E; j.rows = q.dE.rows; j.cols = q.dE.cols; j.stride = q.dE.stride; j.S = S; j.chunk = (q.dE.rows + S - 1) / S;
+    j.part_off = off; j.corrb = q.corrb; j.bias = q.bias; j.mmt = q.mmt; j.scale = scale;
+    off += (long)S * q.dE.cols;
+    if (cb > max_cb) max_cb = cb;
+    if (S > max_S) max_S = S;
+    if (q.dE.cols > max_cols) max_cols = q.dE.cols;
+  }
+  int rc = ensure_vec_scratch(ctx, (int)(2 * off));  // doubles
+  if (rc != TNB_OK) return rc;
+  double *part = (double *)ctx->vec_scratch;
+  colsum_partial_batch_kernel<<<dim3(max_cb, max_S, n), 256, 0, ctx->stream>>>(b, part);
+  TNB_LAUNCHED(ctx);
+  colsum_final_batch_kernel<<<dim3((max_cols + 255) / 256, n), 256, 0, ctx->stream>>>(b, part);
+  TNB_LAUNCHED(ctx);
+  return TNB_OK;
 }
 
 int tnb_affine_grad_bf16(TnbContext *ctx, const uint16_t *X16, int ldx16, TnbMatrixDim dX, const uint16_t *E16, int lde16,
@@ -497,7 +596,7 @@ int tnb_affine_grad_bf16(TnbContext *ctx, const uint16_t *X16, int ldx16, TnbMat
 int tnb_affine_update_bf16(TnbContext *ctx, const uint16_t *X16, int ldx16, TnbMatrixDim dX, const uint16_t *E16, int lde16,
                            const float *E, TnbMatrixDim dE, float *W, TnbMatrixDim dW, uint16_t *W16, int ldw16, float *bias,
                            float *corrW, float *corrb, float lr, float mmt, float wc, int gdf, int n_frames_global) {
-  TNB_ARG(ctx && X16 && E16 && E && W && bias && corrW && corrb, "null");
+  TNB_ARG(ctx && X16 && E16 && W && corrW && ((bias && corrb && E) || (!bias && !corrb)), "null");
   TNB_ARG(dX.rows == dE.rows && dW.rows == dX.cols && dW.cols == dE.cols, "dimension mismatch");
   const int rows = n_frames_global > 0 ? n_frames_global : dX.rows;
   float scale, l2;
@@ -508,7 +607,7 @@ int tnb_affine_update_bf16(TnbContext *ctx, const uint16_t *X16, int ldx16, TnbM
   ep.W = W; ep.ldw = dW.stride; ep.w_scale = scale; ep.w_l2 = l2; ep.mode = EPI_UPD;
   ep.W16 = W16; ep.ldw16 = ldw16;
   int rc = launch_gemm_bf16(ctx, 'T', 'N', dX.cols, dE.cols, dX.rows, X16, ldx16, E16, lde16, ep);
-  if (rc != TNB_OK) return rc;
+  if (rc != TNB_OK || !bias) return rc;
   return launch_colsum_update(ctx, 1.0f, E, mmt, corrb, dE.rows, dE.cols, dE.stride, bias, scale);
 }
 

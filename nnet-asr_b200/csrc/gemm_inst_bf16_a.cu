@@ -6,3 +6,5 @@ TNB_GEMM_INSTANTIATE(64, 16, 1, 1)
 TNB_GEMM_INSTANTIATE(128, 16, 1, 1)
 TNB_GEMM_INSTANTIATE(256, 16, 1, 1)
 }  // namespace tnb
+
+TNB_GEMM_TRACE_READERS(bf16_a)

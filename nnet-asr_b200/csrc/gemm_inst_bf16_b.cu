@@ -7,3 +7,5 @@ TNB_GEMM_INSTANTIATE(256, 16, 2, 1)
 TNB_GEMM_INSTANTIATE(128, 16, 2, 2)
 TNB_GEMM_INSTANTIATE(256, 16, 2, 2)
 }  // namespace tnb
+
+TNB_GEMM_TRACE_READERS(bf16_b)

@@ -7,3 +7,5 @@ TNB_GEMM_INSTANTIATE(128, 3, 1, 1)
 TNB_GEMM_INSTANTIATE(192, 3, 1, 1)
 TNB_GEMM_INSTANTIATE(256, 3, 1, 1)
 }  // namespace tnb
+
+TNB_GEMM_TRACE_READERS(cg1_3x)

@@ -6,3 +6,5 @@ TNB_GEMM_INSTANTIATE(128, 3, 2, 1)
 TNB_GEMM_INSTANTIATE(192, 3, 2, 1)
 TNB_GEMM_INSTANTIATE(256, 3, 2, 1)
 }  // namespace tnb
+
+TNB_GEMM_TRACE_READERS(cg2)

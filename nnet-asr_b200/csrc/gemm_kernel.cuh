@@ -452,7 +452,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (threadIdx.x == 64) { DBG_TS(1, 2); DBG_CTA(1); }
   }
   if (SPLIT == 2) {
+    if (threadIdx.x == 64) DBG_TS(7, 0);
     cluster_sync_all();  // every pair of the cluster has finished its MMAs: all four CTAs' stage buffers are free
+    if (threadIdx.x == 64) DBG_TS(7, 1);
     if (warp >= 2) {
       // send the half of the accumulator columns the OTHER pair finishes to the CTA holding the same rows there
       const uint32_t partner = crank ^ 2u;
@@ -469,7 +471,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                    __uint_as_float(v[4 * j + 3])));
       }
     }
+    if (threadIdx.x == 64) DBG_TS(7, 2);
     cluster_sync_all();  // the partner's half has landed in my receive buffer
+    if (threadIdx.x == 64) DBG_TS(7, 3);
   }
   if (warp >= 2) {
 #pragma unroll 1
@@ -477,18 +481,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int c = (SPLIT == 2) ? (int)split * HALFC + ci : ci;
       if (n0 + c * 32 >= N) break;
       if (ci != chalf) prefetch_chunk(ci);
+      if (threadIdx.x == 64) DBG_TS(6, 4 * (ci / 2) + 0);
       const int n = chunk_col(ci);
       const bool vec = n + 3 < N;
       float4 bv = make_float4(0, 0, 0, 0);
       if ((EPI == EPI_FWD || EPI == EPI_GENERIC) && ep.bias && vec) bv = *(const float4 *)(ep.bias + n);
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      if (threadIdx.x == 64) DBG_TS(6, 4 * (ci / 2) + 1);
       float4 *srow = (float4 *)(scratch + lane * 36);
 #pragma unroll
       for (int j = 0; j < 8; j++)
         srow[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                               __uint_as_float(v[4 * j + 3]));
       __syncwarp();
+      if (threadIdx.x == 64) DBG_TS(6, 4 * (ci / 2) + 2);
       // accumulator value (both K halves when split) of this lane's 4 columns in row r8 + 4k
       auto acc_at = [&](int k) {
         const int r = r8 + 4 * k;
@@ -502,7 +509,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (vec) {
         if (EPI == EPI_FWD) {
           const bool sig = ep.act == TNB_ACT_SIGMOID;
-#pragma unroll 2
+#pragma unroll
           for (int k = 0; k < 8; k++) {
             const int row = row0 + 4 * k;
             const float4 a4 = acc_at(k);
@@ -553,7 +560,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         } else {
-#pragma unroll 2
+#pragma unroll 4
           for (int k = 0; k < 8; k++) {
             const int row = row0 + 4 * k;
             const float4 a4 = acc_at(k);
@@ -567,6 +574,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               o.y = epi_one(ep, a4.y, cold.y, bv.y, yv.y);
               o.z = epi_one(ep, a4.z, cold.z, bv.z, yv.z);
               o.w = epi_one(ep, a4.w, cold.w, bv.w, yv.w);
+#ifdef TNB_GEMM_TRACE
+              if (ep.alpha == -77.0f) { asm volatile("" ::"f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)); continue; }  // probe: epilogue without its stores
+#endif
               *(float4 *)(ep.C + crow + n) = o;
               if (ep.C16) st16(ep.C16, ep.ldc16, row, n, o);
               if (ep.W) {
@@ -610,6 +620,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+      if (threadIdx.x == 64) DBG_TS(6, 4 * (ci / 2) + 3);
       __syncwarp();  // the next chunk overwrites the scratch tile
     }
     if (threadIdx.x == 64) DBG_TS(1, 3);
@@ -709,6 +720,20 @@ int tc_max_active_clusters(int *clusters) {
   if (e != cudaSuccess) { cudaGetLastError(); *clusters = 0; return TNB_ERR_CUDA; }
   return TNB_OK;
 }
+
+// Tracing builds: device globals are private to a translation unit, so every instantiation unit exports its own readers
+// (tnb_dbg_read_ts_<tag>, tnb_dbg_read_cta_<tag>); tools/dbg_*.py pick the unit whose buffers hold the latest timestamps.
+#ifdef TNB_GEMM_TRACE
+#define TNB_GEMM_TRACE_READERS(tag)                                                                                              \
+  extern "C" int tnb_dbg_read_ts_##tag(long long *out) {                                                                         \
+    return cudaMemcpyFromSymbol(out, tnb::g_dbg_ts, sizeof(long long) * 8 * 256) == cudaSuccess ? 0 : 1;                         \
+  }                                                                                                                              \
+  extern "C" int tnb_dbg_read_cta_##tag(long long *out) {                                                                        \
+    return cudaMemcpyFromSymbol(out, tnb::g_dbg_cta, sizeof(long long) * 4 * 1024) == cudaSuccess ? 0 : 1;                       \
+  }
+#else
+#define TNB_GEMM_TRACE_READERS(tag)
+#endif
 
 #define TNB_GEMM_INSTANTIATE(BN, NTERMS, CG, SPLIT)                                                                              \
   template int launch_tc_major<BN, NTERMS, CG, SPLIT>(TnbContext *, int, int, const CUtensorMap &, const CUtensorMap &, int, int, \

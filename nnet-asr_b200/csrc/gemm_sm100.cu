@@ -402,9 +402,3 @@ int tnb_ger(TnbContext *ctx, float alpha, const float *x, int dimX, const float 
 }
 
 }  // extern "C"
-
-#ifdef TNB_GEMM_TRACE
-// read back the pipeline timestamps (tracing builds only; not part of the ABI)
-extern "C" int tnb_dbg_read_ts(long long *out) { return cudaMemcpyFromSymbol(out, tnb::g_dbg_ts, sizeof(long long) * 8 * 256) == cudaSuccess ? 0 : 1; }
-extern "C" int tnb_dbg_read_cta(long long *out) { return cudaMemcpyFromSymbol(out, tnb::g_dbg_cta, sizeof(long long) * 4 * 1024) == cudaSuccess ? 0 : 1; }
-#endif

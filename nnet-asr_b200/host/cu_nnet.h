@@ -186,21 +186,28 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     }
   }
   /// cuBiasedLinearity.cc:44-64, fused into the dW GEMM epilogue
-  void Update() {
+  void Update() { Update(NULL); }
+  /// pDeferredBias != NULL: only the weight half runs now; the bias half (which nothing reads before the next forward pass) is
+  /// described in *pDeferredBias for CuNetwork to apply together with the other layers' (tnb_bias_update_batch)
+  void Update(TnbBiasJob *pDeferredBias) {
     const CuMatrix<BaseFloat> &X = GetInput(), &E = GetErrorInput();
+    float *bias = pDeferredBias ? NULL : mBias.pCUData(), *corrb = pDeferredBias ? NULL : mBiasCorrection.pCUData();
+    if (pDeferredBias) {
+      TnbBiasJob j = {E.pCUData(), E.Dim(), mBias.pCUData(), mBiasCorrection.pCUData(), mLearningRate, mMomentum, mGradDivFrm ? 1 : 0, 0};
+      *pDeferredBias = j;
+    }
     if (Bf16()) {
       const uint16_t *x16 = X.Twin(), *e16 = E.Twin();
       mLinearity.Twin();  // allocate (and fill on first use) so that the epilogue can keep it current from here on
       float *w = mLinearity.pCUData();
       uint16_t *w16 = mLinearity.TwinForWrite();
       TNB_CHECK(tnb_affine_update_bf16(Cx(), x16, X.TwinStride(), X.Dim(), e16, E.TwinStride(), E.pCUData(), E.Dim(), w, mLinearity.Dim(),
-                                       w16, mLinearity.TwinStride(), mBias.pCUData(), mLinearityCorrection.pCUData(),
-                                       mBiasCorrection.pCUData(), mLearningRate, mMomentum, mWeightcost, mGradDivFrm ? 1 : 0, 0));
+                                       w16, mLinearity.TwinStride(), bias, mLinearityCorrection.pCUData(), corrb, mLearningRate, mMomentum,
+                                       mWeightcost, mGradDivFrm ? 1 : 0, 0));
       return;
     }
-    TNB_CHECK(tnb_affine_update(Cx(), X.pCUData(), X.Dim(), E.pCUData(), E.Dim(), mLinearity.pCUData(), mLinearity.Dim(), mBias.pCUData(),
-                                mLinearityCorrection.pCUData(), mBiasCorrection.pCUData(), mLearningRate, mMomentum, mWeightcost,
-                                mGradDivFrm ? 1 : 0, 0));
+    TNB_CHECK(tnb_affine_update(Cx(), X.pCUData(), X.Dim(), E.pCUData(), E.Dim(), mLinearity.pCUData(), mLinearity.Dim(), bias,
+                                mLinearityCorrection.pCUData(), corrb, mLearningRate, mMomentum, mWeightcost, mGradDivFrm ? 1 : 0, 0));
   }
   // ---- data-parallel halves of Update(): local gradient, (all-reduce by the network), apply ----
   void ComputeGradient() {
@@ -732,6 +739,7 @@ class CuNetwork {
     const int n = (int)mNetComponents.size();
     mNetComponents.back()->SetErrorInput(globerr);
     std::vector<CuBiasedLinearity *> pending;  // data parallel: layers whose gradient is in flight
+    std::vector<TnbBiasJob> bias_jobs;         // fused schedule: bias halves of the updates, applied together after the last layer
     for (int i = n - 1; i >= 0; i--) {
       CuComponent *c = mNetComponents[i];
       if (c != mpPropagErrorStopper) {
@@ -766,6 +774,9 @@ class CuNetwork {
             lin->ComputeGradient();
             TNB_CHECK(tnb_allreduce_sum(Cx(), lin->GradBuffer(), lin->GradCount()));  // overlaps the layers below
             pending.push_back(lin);
+          } else if (mFuse && c->GetType() == CuComponent::BIASED_LINEARITY) {
+            bias_jobs.push_back(TnbBiasJob());
+            static_cast<CuBiasedLinearity *>(c)->Update(&bias_jobs.back());
           } else {
             rComp.Update();
           }
@@ -773,6 +784,8 @@ class CuNetwork {
       }
       if (mpPropagErrorStopper == c) break;
     }
+    for (size_t k = 0; k < bias_jobs.size(); k += TNB_MAX_BIAS_JOBS)
+      TNB_CHECK(tnb_bias_update_batch(Cx(), &bias_jobs[k], (int)std::min<size_t>(TNB_MAX_BIAS_JOBS, bias_jobs.size() - k)));
     if (!pending.empty()) {
       TNB_CHECK(tnb_comm_wait(Cx()));
       for (size_t k = 0; k < pending.size(); k++) pending[k]->ApplyGradient((int)pending[k]->GetInput().Rows() * mWorld);

@@ -2,24 +2,49 @@ import ctypes as C, os, sys, numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "nnet-asr_b200", "python"))
 from tnet_b200 import abi
-ctx = abi.Context(0, abi.MATH_3XTF32 if len(sys.argv) < 2 or sys.argv[1] == "3x" else abi.MATH_TF32)
+ctx = abi.Context(0, {"3x": abi.MATH_3XTF32, "tf32": abi.MATH_TF32, "bf16": abi.MATH_BF16}[sys.argv[1] if len(sys.argv) > 1 else "3x"])
 r = np.random.default_rng(0)
 ta, tb, M, N, K = (sys.argv[2], sys.argv[3], int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])) if len(sys.argv) > 6 else ("N", "N", 1024, 2048, 2048)
 A = r.standard_normal((K, M) if ta == "T" else (M, K)).astype(np.float32); B = r.standard_normal((N, K) if tb == "T" else (K, N)).astype(np.float32)
 dA, dB, dC = abi.DMat.from_numpy(ctx, A), abi.DMat.from_numpy(ctx, B), abi.DMat(ctx, M, N)
 import time
+OP = os.environ.get("DBG_OP", "gemm")   # gemm | fwd | dx | upd : the fused layer ops use M as rows, K/N as nin/nout of the shape given
+L = abi.lib()
+if OP != "gemm":
+    rows, nin, nout = (M, K, N) if OP == "fwd" else ((M, N, K) if OP == "dx" else (K, M, N))
+    X = abi.DMat.from_numpy(ctx, r.random((rows, nin)).astype(np.float32)); E = abi.DMat.from_numpy(ctx, (0.01 * r.standard_normal((rows, nout))).astype(np.float32))
+    W = abi.DMat.from_numpy(ctx, (0.1 * r.standard_normal((nin, nout))).astype(np.float32)); cW = abi.DMat(ctx, nin, nout)
+    b = abi.DMat.from_numpy(ctx, np.zeros(nout, np.float32)); cb = abi.DMat(ctx, 1, nout); Y = abi.DMat(ctx, rows, nout); Ep = abi.DMat(ctx, rows, nin)
+def run():
+    if OP == "gemm":
+        abi.gemm(ctx, ta, tb, float(os.environ.get("DBG_ALPHA", "1.0")), dA, dB, 0.0, dC)
+    elif OP == "fwd":
+        abi.check(L.tnb_affine_fwd(ctx.h, X.p(), X.dim, W.p(), W.dim, b.p(), Y.p(), Y.dim, C.c_int(abi.ACT_SIGMOID)))
+    elif OP == "dx":
+        abi.check(L.tnb_affine_bwd_dx(ctx.h, E.p(), E.dim, W.p(), W.dim, X.p(), X.dim, Ep.p(), Ep.dim))
+    else:
+        abi.check(L.tnb_affine_update(ctx.h, X.p(), X.dim, E.p(), E.dim, W.p(), W.dim, b.p(), cW.p(), cb.p(), C.c_float(0.008), C.c_float(0.5), C.c_float(1e-6), C.c_int(1), C.c_int(0)))
 for _ in range(3):
-    abi.gemm(ctx, ta, tb, 1.0, dA, dB, 0.0, dC)
+    run()
 ctx.sync()
 t = time.perf_counter()
 for _ in range(20):
-    abi.gemm(ctx, ta, tb, 1.0, dA, dB, 0.0, dC)
+    run()
 ctx.sync()
 print("kernel wall (20 back-to-back): %.1f us each" % ((time.perf_counter() - t) / 20 * 1e6))
 ts = np.zeros(8 * 256, np.int64)
-abi.lib().tnb_dbg_read_ts(ts.ctypes.data_as(C.c_void_p))
-nkb = min(64, (K + 31) // 32)
-ts = ts.reshape(8, 256)[:, :nkb]
+best = None
+for tag in ("cg1_3x", "cg1_1x", "cg2", "split", "bf16_a", "bf16_b"):   # one trace buffer per instantiation unit: take the latest
+    t_ = np.zeros(8 * 256, np.int64)
+    getattr(abi.lib(), "tnb_dbg_read_ts_" + tag)(t_.ctypes.data_as(C.c_void_p))
+    if best is None or t_.max() > best.max():
+        best = t_
+ts = best
+BKE = 64 if len(sys.argv) > 1 and sys.argv[1] == "bf16" else 32
+nkb = min(64, (K + BKE - 1) // BKE)
+if os.environ.get("DBG_SPLIT"): nkb //= 2
+raw = ts.reshape(8, 256)
+ts = raw[:, :nkb]
 t0 = ts[0, 0]
 e=ts[1]; print("entry->setup %d, setup->first empty_seen %d, last commit->epilogue start %d, epilogue %d, epilogue end->final sync %d, TOTAL entry->final %d cycles" % (e[1]-e[0], ts[0,0]-e[1], e[2]-ts[5,nkb-1], e[3]-e[2], e[4]-e[3], e[4]-e[0]))
 names = ["prod:empty_seen", "-", "conv:full_seen", "conv:arrived", "mma:conv_seen", "mma:committed"]
@@ -31,3 +56,14 @@ print("full_seen - empty_seen (TMA latency incl. issue):", (ts[2, 8:nkb-2] - ts[
 print("arrived - full_seen (conversion):", (ts[3, 8:nkb-2] - ts[2, 8:nkb-2]).mean())
 print("mma conv_seen - conv arrived:", (ts[4, 8:nkb-2] - ts[3, 8:nkb-2]).mean())
 print("mma committed - conv_seen (issue):", (ts[5, 8:nkb-2] - ts[4, 8:nkb-2]).mean())
+
+ep = raw[6, :16]
+print("epilogue of warp 2, per 32-column chunk (cycles): tmem_ld, smem transpose, fused ops + stores")
+for i in range(4):
+    a = ep[4 * i:4 * i + 4]
+    if a[0] > 0 and a[3] > a[0]:
+        print("  chunk %d: start +%d  tmem_ld %d  transpose %d  ops+stores %d" % (i, a[0] - raw[1, 2], a[1] - a[0], a[2] - a[1], a[3] - a[2]))
+
+x = raw[7, :4]
+if x[0] > 0 and x[3] > x[0] and os.environ.get("DBG_SPLIT"):
+    print("split-K exchange (cycles): first cluster sync %d, tmem_ld + remote stores %d, second cluster sync %d" % (x[1] - x[0], x[2] - x[1], x[3] - x[2]))
