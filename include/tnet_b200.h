@@ -94,6 +94,18 @@ int tnb_memcpy2d(TnbContext *ctx, void *dst, size_t dpitch_bytes, const void *sr
                  size_t width_bytes, size_t height, int kind);
 int tnb_memcpy(TnbContext *ctx, void *dst, const void *src, size_t bytes, int kind);
 int tnb_host_alloc(void **ptr, size_t bytes); /* pinned host memory */
+/* ---- streams and events (the reference copies synchronously on the default stream: cumatrix.tcc:68-118).  A host that wants
+ * its transfers to overlap the training step enqueues them on the context's copy stream and orders the two streams with
+ * events; nothing below blocks the host except tnb_event_sync. */
+enum { TNB_STREAM_COMPUTE = 0, TNB_STREAM_COPY = 1 };
+int tnb_memcpy2d_on(TnbContext *ctx, int stream_id, void *dst, size_t dpitch_bytes, const void *src, size_t spitch_bytes,
+                    size_t width_bytes, size_t height, int kind); /* host side must be pinned; never synchronises */
+int tnb_memcpy_on(TnbContext *ctx, int stream_id, void *dst, const void *src, size_t bytes, int kind);
+int tnb_event_create(TnbContext *ctx, void **event);
+int tnb_event_destroy(TnbContext *ctx, void *event);
+int tnb_event_record(TnbContext *ctx, void *event, int stream_id);      /* after everything enqueued so far on that stream */
+int tnb_stream_wait_event(TnbContext *ctx, int stream_id, void *event); /* device-side wait */
+int tnb_event_sync(TnbContext *ctx, void *event);                       /* host-side wait */
 int tnb_host_free(void *ptr);
 
 /* ---- 1:1 replacements of cukernels.h (float instances) ------------------------------------------- */

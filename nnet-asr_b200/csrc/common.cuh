@@ -61,6 +61,7 @@ struct TnbContext_ {
   int math_mode = TNB_MATH_3XTF32;
   cudaStream_t stream = nullptr;       // compute stream
   cudaStream_t comm_stream = nullptr;  // NCCL stream
+  cudaStream_t copy_stream = nullptr;  // host<->device transfers that overlap compute (TNB_STREAM_COPY)
   cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
   unsigned long long launches = 0;
   std::map<tnb::TmapKey, CUtensorMap> tmaps;  // TMA descriptors keyed by (ptr, dims, box)

@@ -163,6 +163,7 @@ int tnb_ctx_create(TnbContext **out, int device) {
   ctx->sm_count = prop.multiProcessorCount;
   TNB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   TNB_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  TNB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   TNB_CUDA(cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
   TNB_CUDA(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
   *out = ctx;
@@ -183,6 +184,7 @@ int tnb_ctx_destroy(TnbContext *ctx) {
   cudaEventDestroy(ctx->ev_comm);
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->comm_stream);
+  cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
   return TNB_OK;
 }
@@ -200,6 +202,7 @@ int tnb_ctx_sync(TnbContext *ctx) {
   TNB_ARG(ctx, "null");
   TNB_CUDA(cudaStreamSynchronize(ctx->stream));
   TNB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+  TNB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
   return TNB_OK;
 }
 int tnb_ctx_free_memory(TnbContext *ctx, size_t *fr, size_t *tot) {
@@ -300,6 +303,51 @@ int tnb_memcpy(TnbContext *ctx, void *dst, const void *src, size_t bytes, int ki
   if (kind == 1) TNB_CUDA(cudaStreamSynchronize(ctx->stream));
   return TNB_OK;
 }
+// ---- streams and events: what a host needs to overlap its transfers with the training step ----
+static cudaStream_t stream_of(TnbContext *ctx, int id) { return id == TNB_STREAM_COPY ? ctx->copy_stream : ctx->stream; }
+int tnb_memcpy2d_on(TnbContext *ctx, int stream_id, void *dst, size_t dp, const void *src, size_t sp, size_t w, size_t h, int kind) {
+  TNB_ARG(ctx && dst && src, "null");
+  TNB_ARG(kind >= 0 && kind <= 2 && (stream_id == TNB_STREAM_COMPUTE || stream_id == TNB_STREAM_COPY), "kind / stream");
+  if (w == 0 || h == 0) return TNB_OK;
+  TNB_CUDA(cudaMemcpy2DAsync(dst, dp, src, sp, w, h, kind_of(kind), stream_of(ctx, stream_id)));
+  return TNB_OK;
+}
+int tnb_memcpy_on(TnbContext *ctx, int stream_id, void *dst, const void *src, size_t bytes, int kind) {
+  TNB_ARG(ctx && dst && src, "null");
+  TNB_ARG(kind >= 0 && kind <= 2 && (stream_id == TNB_STREAM_COMPUTE || stream_id == TNB_STREAM_COPY), "kind / stream");
+  if (bytes == 0) return TNB_OK;
+  TNB_CUDA(cudaMemcpyAsync(dst, src, bytes, kind_of(kind), stream_of(ctx, stream_id)));
+  return TNB_OK;
+}
+int tnb_event_create(TnbContext *ctx, void **ev) {
+  TNB_ARG(ctx && ev, "null");
+  cudaEvent_t e;
+  TNB_CUDA(cudaSetDevice(ctx->device));
+  TNB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  *ev = (void *)e;
+  return TNB_OK;
+}
+int tnb_event_destroy(TnbContext *ctx, void *ev) {
+  TNB_ARG(ctx, "null");
+  if (ev) TNB_CUDA(cudaEventDestroy((cudaEvent_t)ev));
+  return TNB_OK;
+}
+int tnb_event_record(TnbContext *ctx, void *ev, int stream_id) {
+  TNB_ARG(ctx && ev && (stream_id == TNB_STREAM_COMPUTE || stream_id == TNB_STREAM_COPY), "null / stream");
+  TNB_CUDA(cudaEventRecord((cudaEvent_t)ev, stream_of(ctx, stream_id)));
+  return TNB_OK;
+}
+int tnb_stream_wait_event(TnbContext *ctx, int stream_id, void *ev) {
+  TNB_ARG(ctx && ev && (stream_id == TNB_STREAM_COMPUTE || stream_id == TNB_STREAM_COPY), "null / stream");
+  TNB_CUDA(cudaStreamWaitEvent(stream_of(ctx, stream_id), (cudaEvent_t)ev, 0));
+  return TNB_OK;
+}
+int tnb_event_sync(TnbContext *ctx, void *ev) {
+  TNB_ARG(ctx && ev, "null");
+  TNB_CUDA(cudaEventSynchronize((cudaEvent_t)ev));
+  return TNB_OK;
+}
+
 int tnb_host_alloc(void **ptr, size_t bytes) {
   TNB_ARG(ptr, "null");
   TNB_CUDA(cudaMallocHost(ptr, bytes ? bytes : 4));

@@ -34,8 +34,23 @@ struct TnhNet_ {
   // resident training set
   CuMatrix<BaseFloat> res_feats;
   CuVector<int> res_labels;
-  TnhNet_() : obj(NULL) {}
-  ~TnhNet_() { delete obj; }
+  // pipelined submission (tnh_net_submit_bunch_labels / tnh_net_collect): two input slots
+  struct Slot {
+    CuMatrix<BaseFloat> feats;
+    CuVector<int> labels;
+    void *ready, *used, *done;  // H2D landed (copy stream) / step no longer reads the slot / statistics copied back
+    TnbObjStats *stats_host;    // pinned
+    Slot() : ready(NULL), used(NULL), done(NULL), stats_host(NULL) {}
+  } slot[2];
+  unsigned long long submitted, collected;
+  TnhNet_() : obj(NULL), submitted(0), collected(0) {}
+  ~TnhNet_() {
+    delete obj;
+    for (int i = 0; i < 2; i++) {
+      if (slot[i].ready) { tnb_event_destroy(Cx(), slot[i].ready); tnb_event_destroy(Cx(), slot[i].used); tnb_event_destroy(Cx(), slot[i].done); }
+      if (slot[i].stats_host) tnb_host_free(slot[i].stats_host);
+    }
+  }
   void Step(bool cv) {  // TNetCu.cc:431-438 with the softmax fused into the objective
     net.PropagateEvaluate(feats, labs, *obj, globerr);
     if (!cv) net.Backpropagate(globerr);
@@ -181,6 +196,50 @@ int tnh_net_train_bunch_labels(TnhNet *h, const float *x, const int *lab, int ro
   h->labs.Init(rows, h->net.GetNOutputs());
   TNB_CHECK(tnb_onehot(Cx(), h->labs.pCUData(), h->labels.pCUData(), h->labs.Dim()));
   h->Step(cv != 0);
+  TNH_CATCH
+}
+int tnh_net_submit_bunch_labels(TnhNet *h, const float *x, const int *lab, int rows, int cv) {
+  TNH_TRY
+  if (h->submitted - h->collected >= 2) Error("two submissions are already in flight: collect one first");
+  TnhNet_::Slot &s = h->slot[h->submitted & 1];
+  const int nin = (int)h->net.GetNInputs();
+  if (!s.ready) {
+    TNB_CHECK(tnb_event_create(Cx(), &s.ready));
+    TNB_CHECK(tnb_event_create(Cx(), &s.used));
+    TNB_CHECK(tnb_event_create(Cx(), &s.done));
+    void *p = NULL;
+    TNB_CHECK(tnb_host_alloc(&p, sizeof(TnbObjStats)));
+    s.stats_host = (TnbObjStats *)p;
+    TNB_CHECK(tnb_event_record(Cx(), s.used, TNB_STREAM_COMPUTE));
+  }
+  if ((int)s.feats.Rows() != rows || (int)s.feats.Cols() != nin) {
+    s.feats.Init(rows, nin);   // (re)allocation and zero-fill run on the compute stream: the copy must not overtake them
+    s.labels.Init(rows);
+    TNB_CHECK(tnb_event_record(Cx(), s.used, TNB_STREAM_COMPUTE));
+  }
+  TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_COPY, s.used));  // the step that last read this slot (two submissions ago) is done
+  TNB_CHECK(tnb_memcpy2d_on(Cx(), TNB_STREAM_COPY, s.feats.pCUData(), s.feats.Stride() * sizeof(float), x, (size_t)nin * sizeof(float),
+                            (size_t)nin * sizeof(float), rows, 0));
+  TNB_CHECK(tnb_memcpy_on(Cx(), TNB_STREAM_COPY, s.labels.pCUData(), lab, sizeof(int) * (size_t)rows, 0));
+  TNB_CHECK(tnb_event_record(Cx(), s.ready, TNB_STREAM_COPY));
+  TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_COMPUTE, s.ready));
+  h->labs.Init(rows, h->net.GetNOutputs());
+  TNB_CHECK(tnb_onehot(Cx(), h->labs.pCUData(), s.labels.pCUData(), h->labs.Dim()));
+  h->net.PropagateEvaluate(s.feats, h->labs, *h->obj, h->globerr);
+  if (!cv) h->net.Backpropagate(h->globerr);
+  TNB_CHECK(tnb_event_record(Cx(), s.used, TNB_STREAM_COMPUTE));
+  TNB_CHECK(tnb_memcpy_on(Cx(), TNB_STREAM_COMPUTE, s.stats_host, h->obj->DeviceStats(), sizeof(TnbObjStats), 1));
+  TNB_CHECK(tnb_event_record(Cx(), s.done, TNB_STREAM_COMPUTE));
+  h->submitted++;
+  TNH_CATCH
+}
+int tnh_net_collect(TnhNet *h, double *e, long long *f, long long *c) {
+  TNH_TRY
+  if (h->collected >= h->submitted) Error("nothing in flight");
+  TnhNet_::Slot &s = h->slot[h->collected & 1];
+  TNB_CHECK(tnb_event_sync(Cx(), s.done));
+  *e = s.stats_host->error; *f = s.stats_host->frames; *c = s.stats_host->correct;
+  h->collected++;
   TNH_CATCH
 }
 int tnh_net_stats(TnhNet *h, double *e, long long *f, long long *c) {

@@ -137,6 +137,15 @@ class Net:
     def train_resident(self, bunch, first, n, cv=False):
         hcheck(hlib().tnh_net_train_resident(self.h, C.c_int(bunch), C.c_int(first), C.c_int(n), C.c_int(int(cv))))
 
+    def submit_bunch_labels(self, x_ptr, lab_ptr, rows, cv=False):
+        """pipelined step from PINNED host buffers (ctypes pointers); pair with collect()"""
+        hcheck(hlib().tnh_net_submit_bunch_labels(self.h, x_ptr, lab_ptr, C.c_int(rows), C.c_int(int(cv))))
+
+    def collect(self):
+        e = C.c_double(); fr = C.c_longlong(); co = C.c_longlong()
+        hcheck(hlib().tnh_net_collect(self.h, C.byref(e), C.byref(fr), C.byref(co)))
+        return e.value, fr.value, co.value
+
     def stats(self):
         e = C.c_double(); fr = C.c_longlong(); co = C.c_longlong()
         hcheck(hlib().tnh_net_stats(self.h, C.byref(e), C.byref(fr), C.byref(co)))
@@ -274,6 +283,15 @@ class Rbm:
             os.unlink(name)
         return L[3], L[4], L[5]
 
+    def submit_bunch_labels(self, x_ptr, lab_ptr, rows, cv=False):
+        """pipelined step from PINNED host buffers (ctypes pointers); pair with collect()"""
+        hcheck(hlib().tnh_net_submit_bunch_labels(self.h, x_ptr, lab_ptr, C.c_int(rows), C.c_int(int(cv))))
+
+    def collect(self):
+        e = C.c_double(); fr = C.c_longlong(); co = C.c_longlong()
+        hcheck(hlib().tnh_net_collect(self.h, C.byref(e), C.byref(fr), C.byref(co)))
+        return e.value, fr.value, co.value
+
     def stats(self):
         e = C.c_double(); fr = C.c_longlong()
         hcheck(hlib().tnh_rbm_stats(self.h, C.byref(e), C.byref(fr)))
@@ -310,6 +328,15 @@ class Rnn:
             return F.read_mlp(name)
         finally:
             os.unlink(name)
+
+    def submit_bunch_labels(self, x_ptr, lab_ptr, rows, cv=False):
+        """pipelined step from PINNED host buffers (ctypes pointers); pair with collect()"""
+        hcheck(hlib().tnh_net_submit_bunch_labels(self.h, x_ptr, lab_ptr, C.c_int(rows), C.c_int(int(cv))))
+
+    def collect(self):
+        e = C.c_double(); fr = C.c_longlong(); co = C.c_longlong()
+        hcheck(hlib().tnh_net_collect(self.h, C.byref(e), C.byref(fr), C.byref(co)))
+        return e.value, fr.value, co.value
 
     def stats(self):
         e = C.c_double(); fr = C.c_longlong(); co = C.c_longlong()

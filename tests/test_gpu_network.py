@@ -227,3 +227,50 @@ def test_rnn_bptt_matches_reference_trecurrentcu():
     np.testing.assert_allclose(L[0][1], g["final_Wr"], rtol=3e-4, atol=3e-4 * np.abs(g["final_Wr"]).max())
     np.testing.assert_allclose(L[0][2], g["final_br"], rtol=3e-4, atol=3e-4 * max(1e-3, np.abs(g["final_br"]).max()))
     np.testing.assert_allclose(L[1][1], g["final_Wo"], rtol=3e-4, atol=3e-4 * np.abs(g["final_Wo"]).max())
+
+
+def test_pipelined_submit_collect_equals_blocking_steps():
+    """tnh_net_submit_bunch_labels / tnh_net_collect (H2D on the copy stream, one submission in flight) train exactly like the
+    blocking tnh_net_train_bunch_labels: same statistics after every bunch, same final weights (bit-exact: same kernels, same
+    order, only the transfer schedule differs)."""
+    import ctypes as C
+    from tnet_b200 import formats as F
+    dims, bunch, steps = [39, 64, 48, 20], 96, 6
+    r = np.random.default_rng(5)
+    layers = F.gen_mlp_init(dims, r)
+    xs = r.standard_normal((steps, bunch, dims[0])).astype(np.float32)
+    labs = r.integers(0, dims[-1], (steps, bunch)).astype(np.int32)
+    L, H = abi.lib(), host.hlib()
+    # pinned staging buffers, one per step (a submission's buffers must stay untouched until it is collected)
+    px, pl = C.c_void_p(), C.c_void_p()
+    abi.check(L.tnb_host_alloc(C.byref(px), C.c_size_t(xs.nbytes)))
+    abi.check(L.tnb_host_alloc(C.byref(pl), C.c_size_t(labs.nbytes)))
+    C.memmove(px, xs.ctypes.data, xs.nbytes)
+    C.memmove(pl, labs.ctypes.data, labs.nbytes)
+    xp = lambda i: C.cast(C.c_void_p(px.value + i * bunch * dims[0] * 4), C.POINTER(C.c_float))
+    lp = lambda i: C.cast(C.c_void_p(pl.value + i * bunch * 4), C.POINTER(C.c_int))
+    try:
+        host.set_math(abi.MATH_3XTF32)
+        a = host.Net(layers)
+        b = host.Net(layers)
+        for n in (a, b):
+            n.set_hyper(0.1, mmt=0.5, wc=1e-4, gdf=True)
+        ref = []
+        for i in range(steps):
+            host.hcheck(H.tnh_net_train_bunch_labels(a.h, xp(i), lp(i), C.c_int(bunch), C.c_int(0)))
+            ref.append(a.stats())
+        got = []
+        b.submit_bunch_labels(xp(0), lp(0), bunch)
+        for i in range(1, steps):
+            b.submit_bunch_labels(xp(i), lp(i), bunch)
+            got.append(b.collect())
+        got.append(b.collect())
+        assert got == ref
+        for la, lb in zip(a.get_layers(), b.get_layers()):
+            if la[0] == "affine":
+                assert np.array_equal(la[1], lb[1]) and np.array_equal(la[2], lb[2])
+        with pytest.raises(Exception):
+            b.collect()             # nothing in flight
+    finally:
+        L.tnb_host_free(px)
+        L.tnb_host_free(pl)
