@@ -210,6 +210,10 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner does) go to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -353,7 +357,8 @@ def main():
                 line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "reference", "sample": sample}
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % str(e)[:200]}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         abi.check(L.tnb_comm_destroy(ctx))
         dist.destroy_process_group()

@@ -97,7 +97,7 @@ int tnb_host_alloc(void **ptr, size_t bytes); /* pinned host memory */
 /* ---- streams and events (the reference copies synchronously on the default stream: cumatrix.tcc:68-118).  A host that wants
  * its transfers to overlap the training step enqueues them on the context's copy stream and orders the two streams with
  * events; nothing below blocks the host except tnb_event_sync. */
-enum { TNB_STREAM_COMPUTE = 0, TNB_STREAM_COPY = 1 };
+enum { TNB_STREAM_COMPUTE = 0, TNB_STREAM_COPY = 1, TNB_STREAM_COMM = 2 /* the collectives' stream: tnb_sgd_update_batch_on only */ };
 int tnb_memcpy2d_on(TnbContext *ctx, int stream_id, void *dst, size_t dpitch_bytes, const void *src, size_t spitch_bytes,
                     size_t width_bytes, size_t height, int kind); /* host side must be pinned; never synchronises */
 int tnb_memcpy_on(TnbContext *ctx, int stream_id, void *dst, const void *src, size_t bytes, int kind);
@@ -183,7 +183,7 @@ int tnb_affine_update(TnbContext *ctx, const float *X, TnbMatrixDim dX, const fl
 typedef struct TnbBiasJob_ {
   const float *E;      /* error at the layer's output [rows x nout] */
   TnbMatrixDim dE;
-  float *bias, *corrb; /* [nout] */
+  float *bias, *corrb; /* [nout]; bias == NULL: gradient only, corrb[c] = colsum(E)[c] (summed over ranks before it is applied) */
   float lr, mmt;
   int grad_div_frm, n_frames_global;
 } TnbBiasJob;
@@ -212,6 +212,24 @@ int tnb_affine_update_bf16(TnbContext *ctx, const uint16_t *X16, int ldx16, TnbM
                            const float *E, TnbMatrixDim dE, float *W, TnbMatrixDim dW, uint16_t *W16, int ldw16, float *bias,
                            float *corrW, float *corrb, float lr, float mmt, float wc, int grad_div_frm, int n_frames_global);
 
+/* tnb_sgd_update for several layers in one launch (the data-parallel step applies them after the last all-reduce); W16/ldw16:
+ * optional bf16 twin of W to refresh (NULL otherwise). */
+typedef struct TnbSgdJob_ {
+  const float *G;
+  float *W, *corrW;
+  TnbMatrixDim dW;
+  const float *gb;       /* may be NULL together with bias, corrb */
+  float *bias, *corrb;
+  float lr, mmt, wc;
+  int grad_div_frm, n_frames;
+  uint16_t *W16;
+  int ldw16;
+} TnbSgdJob;
+int tnb_sgd_update_batch(TnbContext *ctx, const TnbSgdJob *jobs, int n); /* n <= TNB_MAX_BIAS_JOBS */
+/* the same enqueued on the communication stream (TNB_STREAM_COMM), i.e. behind the all-reduce that produced G and next to the
+ * backward GEMMs of the layers below; tnb_comm_wait() orders the compute stream behind it */
+int tnb_sgd_update_batch_on(TnbContext *ctx, int stream_id, const TnbSgdJob *jobs, int n);
+
 /* Objective accumulators kept on the device (read once per epoch instead of 2 blocking D2H per bunch,
  * cuObjectiveFunction.cc:61-80).  Layout is ABI. */
 typedef struct TnbObjStats_ {
@@ -239,6 +257,14 @@ int tnb_comm_world(TnbContext *ctx, int *rank, int *world);
 /* in-place sum over ranks of `count` floats, enqueued on the ctx's communication stream after everything
  * already enqueued on the compute stream; tnb_comm_wait() makes the compute stream wait for it. */
 int tnb_allreduce_sum(TnbContext *ctx, float *buf, size_t count);
+/* One layer's data-parallel update, enqueued on the communication stream behind everything already on the compute stream:
+ * reduce-scatter G over the ranks (rank r receives the sum of rows [r*rows_pad/world, (r+1)*rows_pad/world)), apply
+ * CuBiasedLinearity::Update to those rows of W/corrW, all-gather the updated rows of W; the bias gradient gb[ncols] is all-reduced
+ * and applied by every rank.  G, W and corrW must have capacity for rows_pad rows (a multiple of the world size, >= dW.rows; the
+ * rows beyond dW.rows of G must be zero).  tnb_comm_wait() afterwards makes the compute stream wait for it.  With a single rank
+ * it is tnb_sgd_update. */
+int tnb_dp_update(TnbContext *ctx, float *G, float *W, float *corrW, TnbMatrixDim dW, int rows_pad, float *gb, float *bias,
+                  float *corrb, float lr, float mmt, float wc, int grad_div_frm, int n_frames_global);
 int tnb_comm_wait(TnbContext *ctx);
 
 #ifdef __cplusplus

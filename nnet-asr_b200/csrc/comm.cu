@@ -9,6 +9,7 @@
 // libnccl is resolved with dlopen at first use: libtnetb200.so has no link-time dependency on it, so the library
 // loads (and every symbol of include/tnet_b200.h is exported) on machines without NCCL.
 #include <dlfcn.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -21,6 +22,8 @@ enum { kNcclFloat = 7, kNcclSum = 0 };  // ncclFloat32, ncclSum (nccl.h enums, s
 static int (*p_GetUniqueId)(NcclUniqueId *) = nullptr;
 static int (*p_CommInitRank)(NcclComm *, int, NcclUniqueId, int) = nullptr;
 static int (*p_AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+static int (*p_ReduceScatter)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+static int (*p_AllGather)(const void *, void *, size_t, int, NcclComm, cudaStream_t) = nullptr;
 static int (*p_CommDestroy)(NcclComm) = nullptr;
 static const char *(*p_GetErrorString)(int) = nullptr;
 
@@ -32,9 +35,11 @@ static int load_nccl() {
   p_GetUniqueId = (int (*)(NcclUniqueId *))dlsym(h, "ncclGetUniqueId");
   p_CommInitRank = (int (*)(NcclComm *, int, NcclUniqueId, int))dlsym(h, "ncclCommInitRank");
   p_AllReduce = (int (*)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t))dlsym(h, "ncclAllReduce");
+  p_ReduceScatter = (int (*)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t))dlsym(h, "ncclReduceScatter");
+  p_AllGather = (int (*)(const void *, void *, size_t, int, NcclComm, cudaStream_t))dlsym(h, "ncclAllGather");
   p_CommDestroy = (int (*)(NcclComm))dlsym(h, "ncclCommDestroy");
   p_GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
-  if (!p_GetUniqueId || !p_CommInitRank || !p_AllReduce || !p_CommDestroy) {
+  if (!p_GetUniqueId || !p_CommInitRank || !p_AllReduce || !p_CommDestroy || !p_ReduceScatter || !p_AllGather) {
     p_AllReduce = nullptr;
     set_error("libnccl is missing required symbols");
     return TNB_ERR_NCCL;
@@ -70,6 +75,11 @@ int tnb_comm_unique_id(unsigned char id[TNB_NCCL_ID_BYTES]) {
 int tnb_comm_init(TnbContext *ctx, const unsigned char id[TNB_NCCL_ID_BYTES], int rank, int world) {
   TNB_ARG(ctx && id, "null");
   TNB_ARG(world >= 1 && rank >= 0 && rank < world, "rank/world");
+  // The backward GEMMs occupy 128 of the 148 SMs with CTAs that need a whole SM each; a collective launched next to them must
+  // fit into the SMs that are left, or the next GEMM loses a wave waiting for the collective's CTAs to leave.  Measured on two
+  // B200 (profiles/r01_dp_notes.md): NCCL moves ~21 GB/s of all-reduce algorithm bandwidth per CTA; 24 CTAs gave the best step
+  // time (16: -1.5 %, 32: -4 %).  An explicit NCCL_MAX_CTAS wins.
+  setenv("NCCL_MAX_CTAS", "24", 0);
   int rc = load_nccl();
   if (rc != TNB_OK) return rc;
   TNB_CUDA(cudaSetDevice(ctx->device));
@@ -110,6 +120,46 @@ int tnb_allreduce_sum(TnbContext *ctx, float *buf, size_t count) {
   TNB_CUDA(cudaEventRecord(ctx->ev_compute, ctx->stream));
   TNB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_compute, 0));
   TNB_NCCL(p_AllReduce(buf, buf, count, kNcclFloat, kNcclSum, (NcclComm)ctx->nccl_comm, ctx->comm_stream));
+  return TNB_OK;
+}
+
+// One layer's data-parallel update, entirely on the communication stream so that it overlaps the backward GEMMs of the layers
+// below: reduce-scatter the local gradient (every rank receives the sum of ITS block of weight rows), apply
+// CuBiasedLinearity::Update to that block only, all-gather the updated rows.  Compared with all-reduce + full update on every
+// rank the bytes on the wire are the same, the update's HBM traffic (5 passes over the weights) is divided by the world size and
+// nothing is left to do after the last layer but to wait.  This is the reference CPU trainer's scheme — every thread updates
+// its slice of the rows from the summed gradient (TNetLib/BiasedLinearity.cc:133-178) — with NCCL collectives.
+int tnb_dp_update(TnbContext *ctx, float *G, float *W, float *corrW, TnbMatrixDim dW, int rows_pad, float *gb, float *bias,
+                  float *corrb, float lr, float mmt, float wc, int gdf, int n_frames_global) {
+  TNB_ARG(ctx && G && W && corrW, "null");
+  TNB_ARG((gb && bias && corrb) || (!gb && !bias && !corrb), "bias arguments go together");
+  TNB_ARG(dW.rows > 0 && dW.cols > 0 && dW.stride >= dW.cols && n_frames_global > 0, "dims");
+  const int world = ctx->world;
+  TNB_ARG(rows_pad >= dW.rows && rows_pad % world == 0, "rows_pad must be a multiple of the world size, at least dW.rows");
+  float scale, l2;
+  update_scalars(lr, mmt, wc, gdf, n_frames_global, &scale, &l2);
+  cudaStream_t cs = world > 1 ? ctx->comm_stream : ctx->stream;
+  if (world > 1) {
+    TNB_ARG(ctx->nccl_comm != nullptr, "communicator not initialised");
+    TNB_CUDA(cudaEventRecord(ctx->ev_compute, ctx->stream));  // the gradient GEMM (and everything before it) is the producer
+    TNB_CUDA(cudaStreamWaitEvent(cs, ctx->ev_compute, 0));
+  }
+  const int shard = rows_pad / world;
+  const size_t shard_elems = (size_t)shard * (size_t)dW.stride;
+  const size_t off = (size_t)ctx->rank * shard_elems;
+  if (world > 1) {
+    TNB_NCCL(p_ReduceScatter(G, G + off, shard_elems, kNcclFloat, kNcclSum, (NcclComm)ctx->nccl_comm, cs));
+    if (gb) TNB_NCCL(p_AllReduce(gb, gb, (size_t)dW.cols, kNcclFloat, kNcclSum, (NcclComm)ctx->nccl_comm, cs));
+  }
+  int my_rows = dW.rows - ctx->rank * shard;   // rows of the logical matrix inside this rank's block
+  if (my_rows > shard) my_rows = shard;
+  int rc = launch_sgd_update(ctx, cs, G + off, W + off, corrW + off, my_rows, dW.cols, dW.stride, mmt, scale, l2);
+  if (rc != TNB_OK) return rc;
+  if (gb) {  // the bias is tiny: every rank applies the same update to its own copy
+    rc = launch_sgd_update(ctx, cs, gb, bias, corrb, 1, dW.cols, dW.cols, mmt, scale, 0.0f);
+    if (rc != TNB_OK) return rc;
+  }
+  if (world > 1) TNB_NCCL(p_AllGather(W + off, W, shard_elems, kNcclFloat, (NcclComm)ctx->nccl_comm, cs));
   return TNB_OK;
 }
 

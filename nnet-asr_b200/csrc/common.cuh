@@ -90,6 +90,11 @@ namespace tnb {
 inline dim3 grid2d(int cols, int rows, int bx, int by) {
   return dim3((cols + bx - 1) / bx, (rows + by - 1) / by);
 }
+// the reference evaluates the update scalars in float (cuBiasedLinearity.cc:44-63): W += scale*corr ; W += l2*W
+void update_scalars(float lr, float mmt, float wc, int gdf, int rows, float *scale, float *l2);
+// corr = G + mmt*corr ; W += scale*corr ; W += l2*W over a [rows x cols] block, on the given stream
+int launch_sgd_update(TnbContext *ctx, cudaStream_t stream, const float *G, float *W, float *corr, int rows, int cols, int stride,
+                      float mmt, float scale, float l2);
 int ensure_row_scratch(TnbContext *ctx, int rows);
 int ensure_vec_scratch(TnbContext *ctx, int n);
 int get_tmap(TnbContext *ctx, const void *ptr, int rows, int cols, int stride, int box_rows,

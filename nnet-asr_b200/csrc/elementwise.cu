@@ -8,6 +8,7 @@
 // promotions where they are observable (diff-sigmoid's double product, the double column sums).
 #include <cuda_bf16.h>
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm.cuh"
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(256) colsum_final_batch_kernel(const __grid_co
   if (c >= j.cols) return;
   double t = 0.0;
   for (int k = 0; k < j.S; k++) t += part[j.part_off + (size_t)k * j.cols + c];
+  if (!j.bias) { j.corrb[c] = (float)t; return; }  // gradient only (data parallel: summed over the ranks before it is applied)
   const float bb = (j.mmt == 0.0f) ? 0.0f : j.mmt * j.corrb[c];
   const float v = (float)(t + (double)bb);
   j.corrb[c] = v;
@@ -338,13 +340,73 @@ __global__ void __launch_bounds__(256) sgd_update_kernel(const float *__restrict
 }
 
 // the reference evaluates the update scalars in float (cuBiasedLinearity.cc:44-63)
-static void update_scalars(float lr, float mmt, float wc, int gdf, int rows, float *scale, float *l2) {
+// the same for several parameter arrays in one launch (blockIdx.y = array): the data-parallel step applies all layers' updates
+// after the last all-reduce, where seven pairs of launches cost more in gaps than in bandwidth.  Optionally refreshes the bf16
+// twin of the updated weights (TNB_MATH_BF16).
+struct SgdBatch {
+  int n;
+  struct { const float *G; float *W, *corr; uint16_t *W16; int rows, cols, stride, ldw16; float mmt, scale, l2; } j[2 * TNB_MAX_BIAS_JOBS];
+};
+__global__ void __launch_bounds__(256) sgd_update_batch_kernel(const __grid_constant__ SgdBatch b) {
+  const auto &j = b.j[blockIdx.y];
+  const int vcols = (j.cols + 3) >> 2;
+  const long total = (long)j.rows * vcols;
+  const bool vec = ((j.stride & 3) == 0) && (((uintptr_t)j.G & 15) == 0) && (((uintptr_t)j.W & 15) == 0) && (((uintptr_t)j.corr & 15) == 0);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / vcols);
+    const int c = (int)(i % vcols) << 2;
+    const size_t base = (size_t)r * j.stride + c;
+    if (vec && c + 3 < j.cols) {
+      float4 g = *(const float4 *)(j.G + base), k = *(float4 *)(j.corr + base), w = *(float4 *)(j.W + base);
+      k.x = g.x + j.mmt * k.x; k.y = g.y + j.mmt * k.y; k.z = g.z + j.mmt * k.z; k.w = g.w + j.mmt * k.w;
+      w.x = j.scale * k.x + w.x; w.y = j.scale * k.y + w.y; w.z = j.scale * k.z + w.z; w.w = j.scale * k.w + w.w;
+      if (j.l2 != 0.0f) { w.x = j.l2 * w.x + w.x; w.y = j.l2 * w.y + w.y; w.z = j.l2 * w.z + w.z; w.w = j.l2 * w.w + w.w; }
+      *(float4 *)(j.corr + base) = k;
+      *(float4 *)(j.W + base) = w;
+      if (j.W16) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y), hi = __floats2bfloat162_rn(w.z, w.w);
+        uint2 u;
+        u.x = *(const uint32_t *)&lo; u.y = *(const uint32_t *)&hi;
+        *(uint2 *)(j.W16 + (size_t)r * j.ldw16 + c) = u;
+      }
+    } else {
+      for (int t = 0; t < 4 && c + t < j.cols; t++) {
+        float k = j.G[base + t] + j.mmt * j.corr[base + t];
+        float w = j.scale * k + j.W[base + t];
+        if (j.l2 != 0.0f) w = j.l2 * w + w;
+        j.corr[base + t] = k; j.W[base + t] = w;
+        if (j.W16) j.W16[(size_t)r * j.ldw16 + c + t] = __bfloat16_as_ushort(__float2bfloat16_rn(w));
+      }
+    }
+  }
+}
+
+void update_scalars(float lr, float mmt, float wc, int gdf, int rows, float *scale, float *l2) {
   float N = 1;
   if (gdf) N = (float)rows;
   float mmt_gain = (float)(1.0 / (1.0 - mmt));
   N *= mmt_gain;
   *scale = -lr / N;
   *l2 = (float)(-lr * wc * (gdf ? 1.0 : rows));
+}
+
+int launch_sgd_update(TnbContext *ctx, cudaStream_t stream, const float *G, float *W, float *corr, int rows, int cols, int stride,
+                      float mmt, float scale, float l2) {
+  if (rows <= 0 || cols <= 0) return TNB_OK;
+  long total = (long)rows * ((cols + 3) / 4);
+  long blocks = (total + 255) / 256, cap = (long)ctx->sm_count * 8;
+  // On the communication stream the update runs next to the backward GEMMs, whose CTAs need a whole SM each (196 KB of shared
+  // memory, most of the register file): a few CTAs that fit into the SMs the GEMM grid leaves free, instead of a device-wide grid
+  // that would stand in the way of the next GEMM's CTAs.
+  if (stream != ctx->stream) {
+    static int side_ctas = -1;
+    if (side_ctas < 0) { const char *e = getenv("TNB_DP_UPDATE_CTAS"); side_ctas = e ? atoi(e) : 32; }
+    cap = side_ctas;
+  }
+  if (blocks > cap) blocks = cap;
+  sgd_update_kernel<<<(int)blocks, 256, 0, stream>>>(G, W, corr, rows, cols, stride, mmt, scale, l2);
+  TNB_LAUNCHED(ctx);
+  return TNB_OK;
 }
 
 // ---------------------------------------------------------------------------------------- fp32 -> bf16 (TNB_MATH_BF16 operands)
@@ -554,7 +616,7 @@ int tnb_bias_update_batch(TnbContext *ctx, const TnbBiasJob *jobs, int n) {
   int max_cb = 1, max_S = 1, max_cols = 1;
   for (int i = 0; i < n; i++) {
     const TnbBiasJob &q = jobs[i];
-    TNB_ARG(q.E && q.bias && q.corrb, "null");
+    TNB_ARG(q.E && q.corrb, "null");
     TNB_ARG(q.dE.rows >= 0 && q.dE.cols >= 0 && q.dE.stride >= q.dE.cols, "dims");
     const int cb = (q.dE.cols + 127) / 128;
     int S = (2 * ctx->sm_count + cb * n - 1) / (cb * n);  // ~2 CTAs per SM over the whole batch
@@ -611,23 +673,54 @@ int tnb_affine_update_bf16(TnbContext *ctx, const uint16_t *X16, int ldx16, TnbM
   return launch_colsum_update(ctx, 1.0f, E, mmt, corrb, dE.rows, dE.cols, dE.stride, bias, scale);
 }
 
+int tnb_sgd_update_batch(TnbContext *ctx, const TnbSgdJob *jobs, int n) { return tnb_sgd_update_batch_on(ctx, TNB_STREAM_COMPUTE, jobs, n); }
+
+int tnb_sgd_update_batch_on(TnbContext *ctx, int stream_id, const TnbSgdJob *jobs, int n) {
+  TNB_ARG(ctx && (jobs || n == 0), "null");
+  TNB_ARG(stream_id == TNB_STREAM_COMPUTE || stream_id == TNB_STREAM_COMM, "compute or communication stream");
+  TNB_ARG(n >= 0 && n <= TNB_MAX_BIAS_JOBS, "between 0 and TNB_MAX_BIAS_JOBS jobs per call");
+  if (n == 0) return TNB_OK;
+  SgdBatch b;
+  memset(&b, 0, sizeof(b));
+  long max_total = 1;
+  for (int i = 0; i < n; i++) {
+    const TnbSgdJob &q = jobs[i];
+    TNB_ARG(q.G && q.W && q.corrW, "null");
+    TNB_ARG((q.gb && q.bias && q.corrb) || (!q.gb && !q.bias && !q.corrb), "bias arguments go together");
+    TNB_ARG(q.dW.rows >= 0 && q.dW.cols >= 0 && q.dW.stride >= q.dW.cols, "dims");
+    TNB_ARG(!q.W16 || ((uintptr_t)q.W16 % 8 == 0 && q.ldw16 % 4 == 0 && q.ldw16 >= q.dW.cols), "bf16 twin alignment");
+    float scale, l2;
+    update_scalars(q.lr, q.mmt, q.wc, q.grad_div_frm, q.n_frames, &scale, &l2);
+    auto &w = b.j[b.n++];
+    w.G = q.G; w.W = q.W; w.corr = q.corrW; w.W16 = q.W16; w.ldw16 = q.ldw16;
+    w.rows = q.dW.rows; w.cols = q.dW.cols; w.stride = q.dW.stride; w.mmt = q.mmt; w.scale = scale; w.l2 = l2;
+    const long total = (long)q.dW.rows * ((q.dW.cols + 3) / 4);
+    if (total > max_total) max_total = total;
+    if (q.gb) {
+      auto &v = b.j[b.n++];
+      v.G = q.gb; v.W = q.bias; v.corr = q.corrb; v.W16 = nullptr; v.ldw16 = 0;
+      v.rows = 1; v.cols = q.dW.cols; v.stride = q.dW.cols; v.mmt = q.mmt; v.scale = scale; v.l2 = 0.0f;
+    }
+  }
+  long blocks = (max_total + 255) / 256, cap = ((long)ctx->sm_count * 8 + b.n - 1) / b.n;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  sgd_update_batch_kernel<<<dim3((unsigned)blocks, (unsigned)b.n), 256, 0, stream_id == TNB_STREAM_COMM ? ctx->comm_stream : ctx->stream>>>(b);
+  TNB_LAUNCHED(ctx);
+  return TNB_OK;
+}
+
 int tnb_sgd_update(TnbContext *ctx, const float *G, float *W, float *corrW, TnbMatrixDim dW, const float *gb, float *bias,
                    float *corrb, float lr, float mmt, float wc, int gdf, int n_frames) {
   TNB_ARG(ctx && G && W && corrW, "null");
   DIMCHK(dW);
   float scale, l2;
   update_scalars(lr, mmt, wc, gdf, n_frames, &scale, &l2);
-  if (dW.rows > 0 && dW.cols > 0) {
-    long total = (long)dW.rows * ((dW.cols + 3) / 4);
-    long blocks = (total + 255) / 256, cap = (long)ctx->sm_count * 8;
-    if (blocks > cap) blocks = cap;
-    sgd_update_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(G, W, corrW, dW.rows, dW.cols, dW.stride, mmt, scale, l2);
-    TNB_LAUNCHED(ctx);
-  }
+  int rc = launch_sgd_update(ctx, ctx->stream, G, W, corrW, dW.rows, dW.cols, dW.stride, mmt, scale, l2);
+  if (rc != TNB_OK) return rc;
   if (gb) {
     TNB_ARG(bias && corrb, "null bias");
-    sgd_update_kernel<<<(dW.cols / 4 + 255) / 256 + 1, 256, 0, ctx->stream>>>(gb, bias, corrb, 1, dW.cols, dW.cols, mmt, scale, 0.0f);
-    TNB_LAUNCHED(ctx);
+    return launch_sgd_update(ctx, ctx->stream, gb, bias, corrb, 1, dW.cols, dW.cols, mmt, scale, 0.0f);
   }
   return TNB_OK;
 }

@@ -148,6 +148,22 @@ class CuMatrix {
     mRows = rows; mCols = cols; mStride = stride;
     return *this;
   }
+  /// keep the logical dimensions and the contents, but make the allocation large enough for `rows` rows (the extra rows are
+  /// zero): the data-parallel update shards the weight rows over the ranks in equal blocks (tnb_dp_update)
+  void ReserveRows(size_t rows) {
+    const size_t need = rows * mStride;
+    if (need <= mCap) return;
+    void *p = NULL;
+    int st = 0;
+    TNB_CHECK(tnb_malloc_pitch(Cx(), &p, &st, (int)rows, (int)mCols));  // zero-filled
+    assert((size_t)st == mStride);
+    if (mpCUData) {
+      TNB_CHECK(tnb_memcpy(Cx(), p, mpCUData, mRows * mStride * sizeof(T), 2));
+      tnb_free(Cx(), mpCUData);
+    }
+    mpCUData = (T *)p;
+    mCap = need;
+  }
   void Destroy() {
     if (mpCUData) tnb_free(Cx(), mpCUData);
     if (mpTwin) tnb_free(Cx(), mpTwin);

@@ -143,7 +143,7 @@ class CuBiasedLinearity : public CuUpdatableComponent {
  public:
   CuBiasedLinearity(size_t nInputs, size_t nOutputs, CuComponent *pPred)
       : CuUpdatableComponent(nInputs, nOutputs, pPred), mLinearity(nInputs, nOutputs), mBias(nOutputs),
-        mLinearityCorrection(nInputs, nOutputs), mBiasCorrection(nOutputs), mDpFrames(0) {}
+        mLinearityCorrection(nInputs, nOutputs), mBiasCorrection(nOutputs), mDpFrames(0), mRowsPad(0) {}
   ComponentType GetType() const { return BIASED_LINEARITY; }
   const char *GetName() const { return "<biasedlinearity>"; }
 
@@ -210,23 +210,48 @@ class CuBiasedLinearity : public CuUpdatableComponent {
                                 mLinearityCorrection.pCUData(), corrb, mLearningRate, mMomentum, mWeightcost, mGradDivFrm ? 1 : 0, 0));
   }
   // ---- data-parallel halves of Update(): local gradient, (all-reduce by the network), apply ----
-  void ComputeGradient() {
+  /// rows of the weight matrix rounded up to a multiple of the world size: the ranks own equal blocks of rows in the update
+  void PrepareDataParallel(int world) {
+    mRowsPad = ((mNInputs + world - 1) / world) * world;
+    mLinearity.ReserveRows(mRowsPad);
+    mLinearityCorrection.ReserveRows(mRowsPad);
+    mGrad.Init(mRowsPad + 1, mNOutputs);  // [dW (padded rows stay zero) ; db]
+  }
+  void ComputeGradient(bool with_bias = true) {
     const CuMatrix<BaseFloat> &X = GetInput(), &E = GetErrorInput();
-    if (mGrad.Rows() != mNInputs + 1) mGrad.Init(mNInputs + 1, mNOutputs);  // [dW ; db] contiguous: one all-reduce per layer
+    if (mRowsPad == 0) PrepareDataParallel(1);
     TnbMatrixDim dG = mLinearity.Dim();
+    float *gb = with_bias ? mGrad.pCURowData(mRowsPad) : NULL;
     if (Bf16()) {
       const uint16_t *x16 = X.Twin(), *e16 = E.Twin();
-      TNB_CHECK(tnb_affine_grad_bf16(Cx(), x16, X.TwinStride(), X.Dim(), e16, E.TwinStride(), E.pCUData(), E.Dim(), mGrad.pCUData(), dG,
-                                     mGrad.pCURowData(mNInputs)));
+      TNB_CHECK(tnb_affine_grad_bf16(Cx(), x16, X.TwinStride(), X.Dim(), e16, E.TwinStride(), E.pCUData(), E.Dim(), mGrad.pCUData(), dG, gb));
       return;
     }
-    TNB_CHECK(tnb_affine_grad(Cx(), X.pCUData(), X.Dim(), E.pCUData(), E.Dim(), mGrad.pCUData(), dG, mGrad.pCURowData(mNInputs)));
+    TNB_CHECK(tnb_affine_grad(Cx(), X.pCUData(), X.Dim(), E.pCUData(), E.Dim(), mGrad.pCUData(), dG, gb));
+  }
+  /// reduce-scatter + this rank's block of the update + all-gather, on the communication stream (tnb_dp_update)
+  void DataParallelUpdate(int n_frames_global) {
+    TNB_CHECK(tnb_dp_update(Cx(), mGrad.pCUData(), mLinearity.pCUData(), mLinearityCorrection.pCUData(), mLinearity.Dim(), (int)mRowsPad,
+                            mGrad.pCURowData(mRowsPad), mBias.pCUData(), mBiasCorrection.pCUData(), mLearningRate, mMomentum, mWeightcost,
+                            mGradDivFrm ? 1 : 0, n_frames_global));
+  }
+  /// all-reduce schedule: description of this layer's update from the summed gradient, for tnb_sgd_update_batch
+  TnbSgdJob GradientJob(int n_frames_global) {
+    TnbSgdJob j;
+    memset(&j, 0, sizeof(j));
+    j.G = mGrad.pCUData(); j.dW = mLinearity.Dim(); j.gb = mGrad.pCURowData(mRowsPad);
+    j.corrW = mLinearityCorrection.pCUData(); j.bias = mBias.pCUData(); j.corrb = mBiasCorrection.pCUData();
+    j.lr = mLearningRate; j.mmt = mMomentum; j.wc = mWeightcost; j.grad_div_frm = mGradDivFrm ? 1 : 0; j.n_frames = n_frames_global;
+    if (Bf16()) mLinearity.Twin();           // allocate / fill once; kept current by the update kernel from here on
+    j.W = mLinearity.pCUData();               // (marks the twin stale ...)
+    if (Bf16()) { j.W16 = mLinearity.TwinForWrite(); j.ldw16 = mLinearity.TwinStride(); }  // (... and this hands it to the kernel)
+    return j;
   }
   float *GradBuffer() { return mGrad.pCUData(); }
   size_t GradCount() const { return mGrad.Rows() * mGrad.Stride(); }
   void ApplyGradient(int n_frames_global) {
     TNB_CHECK(tnb_sgd_update(Cx(), mGrad.pCUData(), mLinearity.pCUData(), mLinearityCorrection.pCUData(), mLinearity.Dim(),
-                             mGrad.pCURowData(mNInputs), mBias.pCUData(), mBiasCorrection.pCUData(), mLearningRate, mMomentum, mWeightcost,
+                             mGrad.pCURowData(mRowsPad), mBias.pCUData(), mBiasCorrection.pCUData(), mLearningRate, mMomentum, mWeightcost,
                              mGradDivFrm ? 1 : 0, n_frames_global));
   }
 
@@ -272,6 +297,7 @@ class CuBiasedLinearity : public CuUpdatableComponent {
   CuVector<BaseFloat> mBiasCorrection;
   CuMatrix<BaseFloat> mGrad;  ///< data-parallel only: [dW ; db]
   int mDpFrames;
+  size_t mRowsPad;
 };
 
 // =====================================================================================================
@@ -684,12 +710,12 @@ inline CuObjectiveFunction *CuObjectiveFunction::Factory(ObjFunType type) {
 class CuNetwork {
   typedef std::vector<CuComponent *> LayeredType;
  public:
-  CuNetwork() : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1) {
+  CuNetwork() : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mDpShard(false) {
     const char *e = getenv("TNB_FUSE");
     if (e && atoi(e) == 0) mFuse = false;
   }
   explicit CuNetwork(std::istream &rIn)
-      : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1) {
+      : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mDpShard(false) {
     ReadNetwork(rIn);
   }
   ~CuNetwork() {
@@ -709,7 +735,13 @@ class CuNetwork {
 
   void SetFusion(bool on) { mFuse = on; }
   /// data parallel over `world` ranks: Update() becomes gradient -> all-reduce -> apply (N uses rows*world)
-  void SetDataParallel(int world) { mWorld = world; }
+  void SetDataParallel(int world) {
+    mWorld = world;
+    const char *e = getenv("TNB_DP_MODE");
+    mDpShard = e && !strcmp(e, "shard");
+    for (size_t i = 0; i < mNetComponents.size(); i++)
+      if (mNetComponents[i]->GetType() == CuComponent::BIASED_LINEARITY) static_cast<CuBiasedLinearity *>(mNetComponents[i])->PrepareDataParallel(world);
+  }
 
   /// forward the data to the output (cuNetwork.h:137-165)
   void Propagate(const CuMatrix<BaseFloat> &in, CuMatrix<BaseFloat> &out) {
@@ -771,8 +803,15 @@ class CuNetwork {
         if (rComp.LearnRate() > 0.0f) {
           if (mWorld > 1 && c->GetType() == CuComponent::BIASED_LINEARITY) {
             CuBiasedLinearity *lin = static_cast<CuBiasedLinearity *>(c);
-            lin->ComputeGradient();
-            TNB_CHECK(tnb_allreduce_sum(Cx(), lin->GradBuffer(), lin->GradCount()));  // overlaps the layers below
+            if (mDpShard) lin->ComputeGradient();
+            if (mDpShard) lin->DataParallelUpdate((int)lin->GetInput().Rows() * mWorld);  // reduce-scatter / update / all-gather
+            else {
+              // all-reduce of the weight gradient on the communication stream: overlaps the backward GEMMs of the layers below.
+              // (Measured on 2 B200: the collectives are the critical path of the step, so nothing else is queued behind them —
+              // running each layer's update on that stream as well cost 7 % — and the updates follow in one launch at the end.)
+              lin->ComputeGradient();
+              TNB_CHECK(tnb_allreduce_sum(Cx(), lin->GradBuffer(), lin->GradCount()));  // [dW ; db] in one exchange
+            }
             pending.push_back(lin);
           } else if (mFuse && c->GetType() == CuComponent::BIASED_LINEARITY) {
             bias_jobs.push_back(TnbBiasJob());
@@ -787,8 +826,17 @@ class CuNetwork {
     for (size_t k = 0; k < bias_jobs.size(); k += TNB_MAX_BIAS_JOBS)
       TNB_CHECK(tnb_bias_update_batch(Cx(), &bias_jobs[k], (int)std::min<size_t>(TNB_MAX_BIAS_JOBS, bias_jobs.size() - k)));
     if (!pending.empty()) {
-      TNB_CHECK(tnb_comm_wait(Cx()));
-      for (size_t k = 0; k < pending.size(); k++) pending[k]->ApplyGradient((int)pending[k]->GetInput().Rows() * mWorld);
+      if (!mDpShard) {
+        TNB_CHECK(tnb_comm_wait(Cx()));
+        // every rank applies all layers' updates (weights and biases) from the summed gradients in one launch.  (Also tried on
+        // 2 B200 and slower: a separate batched bias exchange at the end of the pass — its small all-reduce is pure exposed latency.)
+        std::vector<TnbSgdJob> upd;
+        for (size_t k = 0; k < pending.size(); k++) upd.push_back(pending[k]->GradientJob((int)pending[k]->GetInput().Rows() * mWorld));
+        for (size_t k = 0; k < upd.size(); k += TNB_MAX_BIAS_JOBS)
+          TNB_CHECK(tnb_sgd_update_batch(Cx(), &upd[k], (int)std::min<size_t>(TNB_MAX_BIAS_JOBS, upd.size() - k)));
+      } else {
+        TNB_CHECK(tnb_comm_wait(Cx()));  // the next forward pass reads the gathered weights
+      }
     }
     // restore the wiring the fused softmax step changed
     if (mFuse && n >= 2 && mNetComponents[n - 1]->GetType() == CuComponent::SOFTMAX)
@@ -903,6 +951,7 @@ class CuNetwork {
   const char *mpTempBasisDir;
   bool mFuse;
   int mWorld;
+  bool mDpShard;  ///< data-parallel schedule: false = all-reduce + batched update (default), true = tnb_dp_update (TNB_DP_MODE=shard)
 };
 
 // =====================================================================================================

@@ -36,34 +36,41 @@ lab = r.integers(0, dims[-1], (steps, B)).astype(np.int32)
 T = np.zeros((steps, B, dims[-1]), np.float32)
 for s in range(steps):
     T[s, np.arange(B), lab[s]] = 1
-net = host.Net(layers)
-net.set_hyper(0.5, mmt=0.5, wc=1e-4, gdf=True)
-net.set_data_parallel(world)
-rows = slice(rank * B // world, (rank + 1) * B // world)
-for s in range(steps):
-    net.train_bunch(X[s, rows], T[s, rows])
-e, fr, co = net.stats()
-tot = torch.tensor([e, fr, co], dtype=torch.float64, device="cuda")
-dist.all_reduce(tot)
-got = net.get_layers()
-ok = True
+for mode in ("allreduce", "shard"):      # both data-parallel schedules of CuNetwork::Backpropagate (TNB_DP_MODE)
+    for mname, math in (("3xtf32", abi.MATH_3XTF32), ("bf16", abi.MATH_BF16)):
+        os.environ["TNB_DP_MODE"] = mode
+        host.set_math(math)
+        net = host.Net(layers)
+        net.set_hyper(0.5, mmt=0.5, wc=1e-4, gdf=True)
+        net.set_data_parallel(world)
+        rows = slice(rank * B // world, (rank + 1) * B // world)
+        for s in range(steps):
+            net.train_bunch(X[s, rows], T[s, rows])
+        e, fr, co = net.stats()
+        tot = torch.tensor([e, fr, co], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tot)
+        got = net.get_layers()
+        ok = True
+        if rank == 0:
+            ref = host.Net(layers)
+            ref.set_hyper(0.5, mmt=0.5, wc=1e-4, gdf=True)
+            for s in range(steps):
+                ref.train_bunch(X[s], T[s])
+            re_, rfr, rco = ref.stats()
+            want = ref.get_layers()
+            for a, b in zip(got, want):
+                if a[0] == "affine":
+                    np.testing.assert_allclose(a[1], b[1], rtol=2e-4, atol=2e-5 * np.abs(b[1]).max())
+                    np.testing.assert_allclose(a[2], b[2], rtol=2e-4, atol=2e-5 * max(1e-2, np.abs(b[2]).max()))
+            assert int(tot[1].item()) == rfr and abs(tot[0].item() - re_) <= 1e-4 * abs(re_) and abs(int(tot[2].item()) - rco) <= 2, (tot, re_, rfr, rco)
+            print("dp ok: schedule=%s math=%s world=%d xent=%.4f frames=%d" % (mode, mname, world, tot[0].item(), int(tot[1].item())), flush=True)
+        # every rank must hold the same weights
+        chk = torch.tensor([float(np.abs(got[0][1]).sum())], dtype=torch.float64, device="cuda")
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert lo.item() == hi.item(), "ranks diverged"
+host.set_math(abi.MATH_3XTF32)
 if rank == 0:
-    ref = host.Net(layers)
-    ref.set_hyper(0.5, mmt=0.5, wc=1e-4, gdf=True)
-    for s in range(steps):
-        ref.train_bunch(X[s], T[s])
-    re_, rfr, rco = ref.stats()
-    want = ref.get_layers()
-    for a, b in zip(got, want):
-        if a[0] == "affine":
-            np.testing.assert_allclose(a[1], b[1], rtol=2e-4, atol=2e-5 * np.abs(b[1]).max())
-            np.testing.assert_allclose(a[2], b[2], rtol=2e-4, atol=2e-5 * max(1e-2, np.abs(b[2]).max()))
-    assert int(tot[1].item()) == rfr and abs(tot[0].item() - re_) <= 1e-4 * abs(re_) and abs(int(tot[2].item()) - rco) <= 2, (tot, re_, rfr, rco)
-    print("DP_EQUIV_OK world=%d xent=%.4f frames=%d" % (world, tot[0].item(), int(tot[1].item())))
-# every rank must hold the same weights
-chk = torch.tensor([float(np.abs(got[0][1]).sum())], dtype=torch.float64, device="cuda")
-lo, hi = chk.clone(), chk.clone()
-dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-assert lo.item() == hi.item(), "ranks diverged"
+    print("DP_EQUIV_OK world=%d" % world)
 abi.check(L.tnb_comm_destroy(ctx))
 dist.destroy_process_group()
