@@ -231,6 +231,72 @@ __global__ void __launch_bounds__(256) expand_kernel(float *__restrict__ y, cons
   }
 }
 
+// The same through shared memory: a CTA owns a block of R consecutive output rows, stages the window of input rows they can
+// touch (R + max(off) - min(off) rows, clamped at the ends exactly like the per-element rule) with coalesced loads, and writes
+// the K-fold wider output rows with 16-byte stores from a per-CTA lookup table (output column -> window offset).  Each input
+// row is read from HBM once per row block instead of K times, and the stores — (K-1)/K of the traffic — are full lines.
+// R is chosen in the kernel from the fixed window budget because the offsets live in device memory; when the offsets span
+// more rows than the budget holds, the CTA falls back to the direct rule above.
+constexpr int EXPAND_SMEM_BYTES = 44 * 1024;
+__global__ void __launch_bounds__(256) expand_smem_kernel(float *__restrict__ y, const float *__restrict__ x, const int *__restrict__ off,
+                                                          int rows, int cols_out, int sy, int rows_in, int cols_in, int sx) {
+  extern __shared__ int esm[];
+  int *lut = esm;                              // [cols_out]: (off[k] - min_off) * cols_in + c
+  float *win = (float *)(esm + cols_out);      // [R + span][cols_in]
+  const int K = cols_out / cols_in;
+  int mn = off[0], mxo = off[0];
+  for (int k = 1; k < K; k++) { const int o = off[k]; mn = o < mn ? o : mn; mxo = o > mxo ? o : mxo; }
+  const int span = mxo - mn;
+  const int budget_rows = (EXPAND_SMEM_BYTES - 4 * cols_out) / (4 * cols_in);
+  const int R = budget_rows - span;
+  if (R < 8) {  // window does not fit: direct rule
+    for (int r = blockIdx.x; r < rows; r += gridDim.x)
+      for (int i = threadIdx.x; i < cols_out; i += blockDim.x) {
+        const int k = i / cols_in, c = i - k * cols_in;
+        int sr = r + off[k];
+        sr = sr < 0 ? 0 : (sr >= rows_in ? rows_in - 1 : sr);
+        y[(size_t)r * sy + i] = x[(size_t)sr * sx + c];
+      }
+    return;
+  }
+  for (int i = threadIdx.x; i < cols_out; i += blockDim.x) {
+    const int k = i / cols_in, c = i - k * cols_in;
+    lut[i] = (off[k] - mn) * cols_in + c;
+  }
+  const bool vec = ((sy & 3) == 0) && (((uintptr_t)y & 15) == 0);
+  const int nq = cols_out >> 2;
+  for (int r0 = blockIdx.x * R; r0 < rows; r0 += gridDim.x * R) {
+    const int nr = (rows - r0 < R) ? rows - r0 : R;
+    __syncthreads();  // lut ready / previous block's window consumed
+    for (int idx = threadIdx.x; idx < (nr + span) * cols_in; idx += blockDim.x) {
+      const int w = idx / cols_in, c = idx - w * cols_in;
+      int sr = r0 + mn + w;
+      sr = sr < 0 ? 0 : (sr >= rows_in ? rows_in - 1 : sr);
+      win[idx] = x[(size_t)sr * sx + c];
+    }
+    __syncthreads();
+    if (vec) {
+      for (int idx = threadIdx.x; idx < nr * nq; idx += blockDim.x) {
+        const int rr = idx / nq, q = idx - rr * nq;
+        const float *wr = win + rr * cols_in;
+        float4 v;
+        v.x = wr[lut[4 * q]]; v.y = wr[lut[4 * q + 1]]; v.z = wr[lut[4 * q + 2]]; v.w = wr[lut[4 * q + 3]];
+        *(float4 *)(y + (size_t)(r0 + rr) * sy + 4 * q) = v;
+      }
+      const int tail = cols_out - 4 * nq;
+      for (int idx = threadIdx.x; idx < nr * tail; idx += blockDim.x) {
+        const int rr = idx / tail, i = 4 * nq + (idx - rr * tail);
+        y[(size_t)(r0 + rr) * sy + i] = win[rr * cols_in + lut[i]];
+      }
+    } else {
+      for (int idx = threadIdx.x; idx < nr * cols_out; idx += blockDim.x) {
+        const int rr = idx / cols_out, i = idx - rr * cols_out;
+        y[(size_t)(r0 + rr) * sy + i] = win[rr * cols_in + lut[i]];
+      }
+    }
+  }
+}
+
 // _rearrange (cukernels.cu:366-379): column gather, +inf for a bad index
 __global__ void __launch_bounds__(256) rearrange_kernel(float *__restrict__ y, const float *__restrict__ x,
                                                         const int *__restrict__ copy_from, int rows, int cols_out, int sy,
@@ -515,7 +581,17 @@ int tnb_expand(TnbContext *ctx, float *y, const float *x, const int *off, TnbMat
   TNB_ARG(d_out.rows == d_in.rows, "expand: rows");
   if (d_out.rows == 0) return TNB_OK;
   int blocks = d_out.rows < ctx->sm_count * 8 ? d_out.rows : ctx->sm_count * 8;
-  expand_kernel<<<blocks, 256, 0, ctx->stream>>>(y, x, off, d_out.rows, d_out.cols, d_out.stride, d_in.rows, d_in.cols, d_in.stride);
+  if (d_in.cols > 0 && d_out.cols % d_in.cols == 0 && 4 * d_out.cols + 16 * 4 * d_in.cols <= EXPAND_SMEM_BYTES) {
+    // shared-memory version: at most 5 CTAs per SM (44 KB each), row blocks walked by a grid-stride loop
+    const int rb = (EXPAND_SMEM_BYTES - 4 * d_out.cols) / (4 * d_in.cols);  // upper bound of rows per block
+    int nb = (d_out.rows + (rb > 16 ? rb / 2 : 8) - 1) / (rb > 16 ? rb / 2 : 8);
+    if (nb > ctx->sm_count * 5) nb = ctx->sm_count * 5;
+    if (nb < 1) nb = 1;
+    expand_smem_kernel<<<nb, 256, EXPAND_SMEM_BYTES, ctx->stream>>>(y, x, off, d_out.rows, d_out.cols, d_out.stride, d_in.rows, d_in.cols,
+                                                                    d_in.stride);
+  } else {
+    expand_kernel<<<blocks, 256, 0, ctx->stream>>>(y, x, off, d_out.rows, d_out.cols, d_out.stride, d_in.rows, d_in.cols, d_in.stride);
+  }
   TNB_LAUNCHED(ctx);
   return TNB_OK;
 }

@@ -43,7 +43,8 @@ inline void SelectMath(UserInterface &ui, const char *sname) {
   if (!strcasecmp(math, "3xtf32")) CuDevice::Instantiate().SetMath(TNB_MATH_3XTF32);
   else if (!strcasecmp(math, "tf32")) CuDevice::Instantiate().SetMath(TNB_MATH_TF32);
   else if (!strcasecmp(math, "simt")) CuDevice::Instantiate().SetMath(TNB_MATH_FP32_SIMT);
-  else throw std::runtime_error(std::string("Invalid MATH '") + math + "' (3xtf32, tf32, simt)");
+  else if (!strcasecmp(math, "bf16")) CuDevice::Instantiate().SetMath(TNB_MATH_BF16);
+  else throw std::runtime_error(std::string("Invalid MATH '") + math + "' (3xtf32, tf32, bf16, simt)");
 }
 
 inline long SeedOrTime(long seed) {

@@ -276,6 +276,16 @@ def test_gathers_bit_exact(ctx):
         dz = abi.DMat(ctx, 77, 39 * len(offs))
         abi.check(L.tnb_expand(ctx.h, dz.p(), df.p(), do.p(C.c_int), dz.dim, df.dim))
         assert np.array_equal(dz.download(), O.expand(f, offs))
+    # splice across many row blocks of the shared-memory kernel, with unsorted / strided offsets (example 01 uses 23 x 51), a span
+    # wider than the window budget (direct-rule fallback), a single-row utterance and an utterance shorter than the context
+    for T, D, offs in ((5000, 39, np.arange(-5, 6)), (1234, 23, np.arange(-25, 26)), (300, 13, np.array([7, -3, 0, 0, -40, 2])),
+                       (400, 40, np.array([-300, 0, 300])), (1, 39, np.arange(-4, 5)), (3, 39, np.arange(-5, 6)), (64, 351, np.array([0]))):
+        f2 = r.standard_normal((T, D)).astype(np.float32)
+        offs = offs.astype(np.int32)
+        df2, do2 = _mat(ctx, f2), _mat(ctx, offs)
+        dz2 = abi.DMat(ctx, T, D * len(offs))
+        abi.check(L.tnb_expand(ctx.h, dz2.p(), df2.p(), do2.p(C.c_int), dz2.dim, df2.dim))
+        assert np.array_equal(dz2.download(), O.expand(f2, offs)), (T, D, offs)
     # rearrange with an out-of-range index -> +inf
     cf = np.array([3, 0, 38, -1, 39, 7], dtype=np.int32)
     dcf = _mat(ctx, cf)
