@@ -97,7 +97,13 @@ int tnb_host_alloc(void **ptr, size_t bytes); /* pinned host memory */
 /* ---- streams and events (the reference copies synchronously on the default stream: cumatrix.tcc:68-118).  A host that wants
  * its transfers to overlap the training step enqueues them on the context's copy stream and orders the two streams with
  * events; nothing below blocks the host except tnb_event_sync. */
-enum { TNB_STREAM_COMPUTE = 0, TNB_STREAM_COPY = 1, TNB_STREAM_COMM = 2 /* the collectives' stream: tnb_sgd_update_batch_on only */ };
+enum {
+  TNB_STREAM_COMPUTE = 0, /* every entry point without a stream argument */
+  TNB_STREAM_COPY = 1,    /* host<->device transfers */
+  TNB_STREAM_COMM = 2,    /* the collectives (tnb_allreduce_sum, tnb_dp_update) */
+  TNB_STREAM_AUX = 3,     /* side streams for small kernels that run next to the compute stream's GEMMs: the data-parallel step */
+  TNB_STREAM_AUX2 = 4     /*   puts the bias-gradient column sums on one and the per-layer updates on the other */
+};
 int tnb_memcpy2d_on(TnbContext *ctx, int stream_id, void *dst, size_t dpitch_bytes, const void *src, size_t spitch_bytes,
                     size_t width_bytes, size_t height, int kind); /* host side must be pinned; never synchronises */
 int tnb_memcpy_on(TnbContext *ctx, int stream_id, void *dst, const void *src, size_t bytes, int kind);
@@ -188,6 +194,8 @@ typedef struct TnbBiasJob_ {
   int grad_div_frm, n_frames_global;
 } TnbBiasJob;
 int tnb_bias_update_batch(TnbContext *ctx, const TnbBiasJob *jobs, int n);
+/* the same on another stream of the context, with its own reduction scratch (may run next to compute-stream column sums) */
+int tnb_bias_update_batch_on(TnbContext *ctx, int stream_id, const TnbBiasJob *jobs, int n);
 /* the same update given an already summed gradient (after the NCCL allreduce):
  *   corrW = G + mmt*corrW ; ... as above.  gb/bias/corrb may be NULL together. */
 int tnb_sgd_update(TnbContext *ctx, const float *G, float *W, float *corrW, TnbMatrixDim dW, const float *gb, float *bias,
@@ -226,8 +234,8 @@ typedef struct TnbSgdJob_ {
   int ldw16;
 } TnbSgdJob;
 int tnb_sgd_update_batch(TnbContext *ctx, const TnbSgdJob *jobs, int n); /* n <= TNB_MAX_BIAS_JOBS */
-/* the same enqueued on the communication stream (TNB_STREAM_COMM), i.e. behind the all-reduce that produced G and next to the
- * backward GEMMs of the layers below; tnb_comm_wait() orders the compute stream behind it */
+/* the same enqueued on another stream of the context (next to the backward GEMMs of the layers below); the caller orders it
+ * behind the all-reduce that produced G and the compute stream behind it with events */
 int tnb_sgd_update_batch_on(TnbContext *ctx, int stream_id, const TnbSgdJob *jobs, int n);
 
 /* Objective accumulators kept on the device (read once per epoch instead of 2 blocking D2H per bunch,
@@ -257,6 +265,9 @@ int tnb_comm_world(TnbContext *ctx, int *rank, int *world);
 /* in-place sum over ranks of `count` floats, enqueued on the ctx's communication stream after everything
  * already enqueued on the compute stream; tnb_comm_wait() makes the compute stream wait for it. */
 int tnb_allreduce_sum(TnbContext *ctx, float *buf, size_t count);
+/* the same, additionally ordered behind `event` (e.g. a bias gradient computed on a side stream into the same buffer); `done`, if
+ * not NULL, is recorded on the communication stream behind the all-reduce (a side stream can then apply the update) */
+int tnb_allreduce_sum_ev(TnbContext *ctx, float *buf, size_t count, void *event, void *done);
 /* One layer's data-parallel update, enqueued on the communication stream behind everything already on the compute stream:
  * reduce-scatter G over the ranks (rank r receives the sum of rows [r*rows_pad/world, (r+1)*rows_pad/world)), apply
  * CuBiasedLinearity::Update to those rows of W/corrW, all-gather the updated rows of W; the bias gradient gb[ncols] is all-reduced

@@ -112,14 +112,20 @@ int tnb_comm_world(TnbContext *ctx, int *rank, int *world) {
   return TNB_OK;
 }
 
-int tnb_allreduce_sum(TnbContext *ctx, float *buf, size_t count) {
+int tnb_allreduce_sum(TnbContext *ctx, float *buf, size_t count) { return tnb_allreduce_sum_ev(ctx, buf, count, nullptr, nullptr); }
+
+int tnb_allreduce_sum_ev(TnbContext *ctx, float *buf, size_t count, void *event, void *done) {
   TNB_ARG(ctx && buf, "null");
-  if (ctx->world == 1 || count == 0) return TNB_OK;  // single rank: the sum is the buffer itself
-  TNB_ARG(ctx->nccl_comm != nullptr, "communicator not initialised");
-  // comm stream waits for everything enqueued so far on the compute stream (the producer of buf)
+  if (count == 0) return TNB_OK;
+  // comm stream waits for everything enqueued so far on the compute stream (the producer of buf) and for `event`
   TNB_CUDA(cudaEventRecord(ctx->ev_compute, ctx->stream));
   TNB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_compute, 0));
-  TNB_NCCL(p_AllReduce(buf, buf, count, kNcclFloat, kNcclSum, (NcclComm)ctx->nccl_comm, ctx->comm_stream));
+  if (event) TNB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, (cudaEvent_t)event, 0));
+  if (ctx->world > 1) {  // single rank: the sum is the buffer itself
+    TNB_ARG(ctx->nccl_comm != nullptr, "communicator not initialised");
+    TNB_NCCL(p_AllReduce(buf, buf, count, kNcclFloat, kNcclSum, (NcclComm)ctx->nccl_comm, ctx->comm_stream));
+  }
+  if (done) TNB_CUDA(cudaEventRecord((cudaEvent_t)done, ctx->comm_stream));
   return TNB_OK;
 }
 

@@ -62,6 +62,8 @@ struct TnbContext_ {
   cudaStream_t stream = nullptr;       // compute stream
   cudaStream_t comm_stream = nullptr;  // NCCL stream
   cudaStream_t copy_stream = nullptr;  // host<->device transfers that overlap compute (TNB_STREAM_COPY)
+  cudaStream_t aux_stream = nullptr;   // small kernels next to the compute stream's GEMMs (TNB_STREAM_AUX)
+  cudaStream_t aux2_stream = nullptr;  // (TNB_STREAM_AUX2)
   cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
   unsigned long long launches = 0;
   std::map<tnb::TmapKey, CUtensorMap> tmaps;  // TMA descriptors keyed by (ptr, dims, box)
@@ -72,6 +74,8 @@ struct TnbContext_ {
   // column-sum scratch (bias gradient before the fused update)
   float *vec_scratch = nullptr;
   int vec_cap = 0;
+  float *vec_scratch_side = nullptr;   // the same for column sums enqueued on another stream (they may run concurrently)
+  int vec_cap_side = 0;
   // bf16 copies of fp32 GEMM operands for the generic entry points in TNB_MATH_BF16 (slot 0 = A, 1 = B)
   uint16_t *bf16_scratch[2] = {nullptr, nullptr};
   size_t bf16_cap[2] = {0, 0};
@@ -97,6 +101,8 @@ int launch_sgd_update(TnbContext *ctx, cudaStream_t stream, const float *G, floa
                       float mmt, float scale, float l2);
 int ensure_row_scratch(TnbContext *ctx, int rows);
 int ensure_vec_scratch(TnbContext *ctx, int n);
+int ensure_vec_scratch_side(TnbContext *ctx, int n);
+cudaStream_t stream_of(TnbContext *ctx, int stream_id);  // TNB_STREAM_* -> cudaStream_t (nullptr for an unknown id)
 int get_tmap(TnbContext *ctx, const void *ptr, int rows, int cols, int stride, int box_rows,
              int box_cols, int swizzle32, CUtensorMap *out, int elem_bytes = 4);
 }  // namespace tnb

@@ -30,6 +30,27 @@ int ensure_row_scratch(TnbContext *ctx, int rows) {
   return TNB_OK;
 }
 
+int ensure_vec_scratch_side(TnbContext *ctx, int n) {
+  if (n <= ctx->vec_cap_side) return TNB_OK;
+  int cap = n < 4096 ? 4096 : n;
+  if (ctx->vec_scratch_side) { TNB_CUDA(cudaDeviceSynchronize()); cudaFree(ctx->vec_scratch_side); }
+  ctx->vec_scratch_side = nullptr; ctx->vec_cap_side = 0;
+  TNB_CUDA(cudaMalloc(&ctx->vec_scratch_side, sizeof(float) * (size_t)cap));
+  ctx->vec_cap_side = cap;
+  return TNB_OK;
+}
+
+cudaStream_t stream_of(TnbContext *ctx, int id) {
+  switch (id) {
+    case TNB_STREAM_COMPUTE: return ctx->stream;
+    case TNB_STREAM_COPY: return ctx->copy_stream;
+    case TNB_STREAM_COMM: return ctx->comm_stream;
+    case TNB_STREAM_AUX: return ctx->aux_stream;
+    case TNB_STREAM_AUX2: return ctx->aux2_stream;
+    default: return nullptr;
+  }
+}
+
 int ensure_vec_scratch(TnbContext *ctx, int n) {
   if (n <= ctx->vec_cap) return TNB_OK;
   int cap = n < 4096 ? 4096 : n;
@@ -164,6 +185,8 @@ int tnb_ctx_create(TnbContext **out, int device) {
   TNB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   TNB_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
   TNB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  TNB_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+  TNB_CUDA(cudaStreamCreateWithFlags(&ctx->aux2_stream, cudaStreamNonBlocking));
   TNB_CUDA(cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
   TNB_CUDA(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
   *out = ctx;
@@ -185,6 +208,9 @@ int tnb_ctx_destroy(TnbContext *ctx) {
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->comm_stream);
   cudaStreamDestroy(ctx->copy_stream);
+  cudaStreamDestroy(ctx->aux_stream);
+  cudaStreamDestroy(ctx->aux2_stream);
+  if (ctx->vec_scratch_side) cudaFree(ctx->vec_scratch_side);
   delete ctx;
   return TNB_OK;
 }
@@ -203,6 +229,8 @@ int tnb_ctx_sync(TnbContext *ctx) {
   TNB_CUDA(cudaStreamSynchronize(ctx->stream));
   TNB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
   TNB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  TNB_CUDA(cudaStreamSynchronize(ctx->aux_stream));
+  TNB_CUDA(cudaStreamSynchronize(ctx->aux2_stream));
   return TNB_OK;
 }
 int tnb_ctx_free_memory(TnbContext *ctx, size_t *fr, size_t *tot) {
@@ -304,17 +332,16 @@ int tnb_memcpy(TnbContext *ctx, void *dst, const void *src, size_t bytes, int ki
   return TNB_OK;
 }
 // ---- streams and events: what a host needs to overlap its transfers with the training step ----
-static cudaStream_t stream_of(TnbContext *ctx, int id) { return id == TNB_STREAM_COPY ? ctx->copy_stream : ctx->stream; }
 int tnb_memcpy2d_on(TnbContext *ctx, int stream_id, void *dst, size_t dp, const void *src, size_t sp, size_t w, size_t h, int kind) {
   TNB_ARG(ctx && dst && src, "null");
-  TNB_ARG(kind >= 0 && kind <= 2 && (stream_id == TNB_STREAM_COMPUTE || stream_id == TNB_STREAM_COPY), "kind / stream");
+  TNB_ARG(kind >= 0 && kind <= 2 && stream_of(ctx, stream_id) != nullptr, "kind / stream");
   if (w == 0 || h == 0) return TNB_OK;
   TNB_CUDA(cudaMemcpy2DAsync(dst, dp, src, sp, w, h, kind_of(kind), stream_of(ctx, stream_id)));
   return TNB_OK;
 }
 int tnb_memcpy_on(TnbContext *ctx, int stream_id, void *dst, const void *src, size_t bytes, int kind) {
   TNB_ARG(ctx && dst && src, "null");
-  TNB_ARG(kind >= 0 && kind <= 2 && (stream_id == TNB_STREAM_COMPUTE || stream_id == TNB_STREAM_COPY), "kind / stream");
+  TNB_ARG(kind >= 0 && kind <= 2 && stream_of(ctx, stream_id) != nullptr, "kind / stream");
   if (bytes == 0) return TNB_OK;
   TNB_CUDA(cudaMemcpyAsync(dst, src, bytes, kind_of(kind), stream_of(ctx, stream_id)));
   return TNB_OK;
@@ -333,12 +360,12 @@ int tnb_event_destroy(TnbContext *ctx, void *ev) {
   return TNB_OK;
 }
 int tnb_event_record(TnbContext *ctx, void *ev, int stream_id) {
-  TNB_ARG(ctx && ev && (stream_id == TNB_STREAM_COMPUTE || stream_id == TNB_STREAM_COPY), "null / stream");
+  TNB_ARG(ctx && ev && stream_of(ctx, stream_id) != nullptr, "null / stream");
   TNB_CUDA(cudaEventRecord((cudaEvent_t)ev, stream_of(ctx, stream_id)));
   return TNB_OK;
 }
 int tnb_stream_wait_event(TnbContext *ctx, int stream_id, void *ev) {
-  TNB_ARG(ctx && ev && (stream_id == TNB_STREAM_COMPUTE || stream_id == TNB_STREAM_COPY), "null / stream");
+  TNB_ARG(ctx && ev && stream_of(ctx, stream_id) != nullptr, "null / stream");
   TNB_CUDA(cudaStreamWaitEvent(stream_of(ctx, stream_id), (cudaEvent_t)ev, 0));
   return TNB_OK;
 }

@@ -681,8 +681,12 @@ int tnb_affine_update(TnbContext *ctx, const float *X, TnbMatrixDim dX, const fl
   return launch_colsum_update(ctx, 1.0f, E, mmt, corrb, dE.rows, dE.cols, dE.stride, bias, scale);
 }
 
-int tnb_bias_update_batch(TnbContext *ctx, const TnbBiasJob *jobs, int n) {
+int tnb_bias_update_batch(TnbContext *ctx, const TnbBiasJob *jobs, int n) { return tnb_bias_update_batch_on(ctx, TNB_STREAM_COMPUTE, jobs, n); }
+
+int tnb_bias_update_batch_on(TnbContext *ctx, int stream_id, const TnbBiasJob *jobs, int n) {
   TNB_ARG(ctx && (jobs || n == 0), "null");
+  cudaStream_t st = stream_of(ctx, stream_id);
+  TNB_ARG(st != nullptr, "stream");
   TNB_ARG(n >= 0 && n <= TNB_MAX_BIAS_JOBS, "between 0 and TNB_MAX_BIAS_JOBS jobs per call");
   if (n == 0) return TNB_OK;
   BiasBatch b;
@@ -708,12 +712,13 @@ int tnb_bias_update_batch(TnbContext *ctx, const TnbBiasJob *jobs, int n) {
     if (S > max_S) max_S = S;
     if (q.dE.cols > max_cols) max_cols = q.dE.cols;
   }
-  int rc = ensure_vec_scratch(ctx, (int)(2 * off));  // doubles
+  const bool side = st != ctx->stream;
+  int rc = side ? ensure_vec_scratch_side(ctx, (int)(2 * off)) : ensure_vec_scratch(ctx, (int)(2 * off));  // doubles
   if (rc != TNB_OK) return rc;
-  double *part = (double *)ctx->vec_scratch;
-  colsum_partial_batch_kernel<<<dim3(max_cb, max_S, n), 256, 0, ctx->stream>>>(b, part);
+  double *part = (double *)(side ? ctx->vec_scratch_side : ctx->vec_scratch);
+  colsum_partial_batch_kernel<<<dim3(max_cb, max_S, n), 256, 0, st>>>(b, part);
   TNB_LAUNCHED(ctx);
-  colsum_final_batch_kernel<<<dim3((max_cols + 255) / 256, n), 256, 0, ctx->stream>>>(b, part);
+  colsum_final_batch_kernel<<<dim3((max_cols + 255) / 256, n), 256, 0, st>>>(b, part);
   TNB_LAUNCHED(ctx);
   return TNB_OK;
 }
@@ -753,7 +758,7 @@ int tnb_sgd_update_batch(TnbContext *ctx, const TnbSgdJob *jobs, int n) { return
 
 int tnb_sgd_update_batch_on(TnbContext *ctx, int stream_id, const TnbSgdJob *jobs, int n) {
   TNB_ARG(ctx && (jobs || n == 0), "null");
-  TNB_ARG(stream_id == TNB_STREAM_COMPUTE || stream_id == TNB_STREAM_COMM, "compute or communication stream");
+  TNB_ARG(stream_of(ctx, stream_id) != nullptr, "stream");
   TNB_ARG(n >= 0 && n <= TNB_MAX_BIAS_JOBS, "between 0 and TNB_MAX_BIAS_JOBS jobs per call");
   if (n == 0) return TNB_OK;
   SgdBatch b;
@@ -779,9 +784,12 @@ int tnb_sgd_update_batch_on(TnbContext *ctx, int stream_id, const TnbSgdJob *job
     }
   }
   long blocks = (max_total + 255) / 256, cap = ((long)ctx->sm_count * 8 + b.n - 1) / b.n;
+  // next to the compute stream's GEMMs (whose CTAs take most of an SM's registers): one small CTA per SM fits beside a GEMM CTA,
+  // a device-filling grid would keep the next GEMM's CTAs waiting for a free SM
+  if (stream_of(ctx, stream_id) != ctx->stream) cap = (ctx->sm_count + b.n - 1) / b.n;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  sgd_update_batch_kernel<<<dim3((unsigned)blocks, (unsigned)b.n), 256, 0, stream_id == TNB_STREAM_COMM ? ctx->comm_stream : ctx->stream>>>(b);
+  sgd_update_batch_kernel<<<dim3((unsigned)blocks, (unsigned)b.n), 256, 0, stream_of(ctx, stream_id)>>>(b);
   TNB_LAUNCHED(ctx);
   return TNB_OK;
 }

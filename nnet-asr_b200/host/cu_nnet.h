@@ -143,7 +143,10 @@ class CuBiasedLinearity : public CuUpdatableComponent {
  public:
   CuBiasedLinearity(size_t nInputs, size_t nOutputs, CuComponent *pPred)
       : CuUpdatableComponent(nInputs, nOutputs, pPred), mLinearity(nInputs, nOutputs), mBias(nOutputs),
-        mLinearityCorrection(nInputs, nOutputs), mBiasCorrection(nOutputs), mDpFrames(0), mRowsPad(0) {}
+        mLinearityCorrection(nInputs, nOutputs), mBiasCorrection(nOutputs), mDpFrames(0), mRowsPad(0), mEvE(NULL), mEvB(NULL), mEvAR(NULL), mEvDone(NULL) {}
+  ~CuBiasedLinearity() {
+    if (mEvE) { tnb_event_destroy(Cx(), mEvE); tnb_event_destroy(Cx(), mEvB); tnb_event_destroy(Cx(), mEvAR); tnb_event_destroy(Cx(), mEvDone); }
+  }
   ComponentType GetType() const { return BIASED_LINEARITY; }
   const char *GetName() const { return "<biasedlinearity>"; }
 
@@ -247,6 +250,29 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     if (Bf16()) { j.W16 = mLinearity.TwinForWrite(); j.ldw16 = mLinearity.TwinStride(); }  // (... and this hands it to the kernel)
     return j;
   }
+  /// all-reduce schedule, one layer: the bias gradient (column sums of E) on a side stream, the weight gradient GEMM on the
+  /// compute stream, the all-reduce of [dW ; db] on the communication stream behind both, the update on a second side stream behind
+  /// the all-reduce.  Only the GEMM stays on the compute stream's critical path; *pDone is recorded behind the update.
+  void DataParallelExchange(int n_frames_global, void **pDone) {
+    if (mRowsPad == 0) PrepareDataParallel(1);
+    if (!mEvE) {
+      TNB_CHECK(tnb_event_create(Cx(), &mEvE)); TNB_CHECK(tnb_event_create(Cx(), &mEvB));
+      TNB_CHECK(tnb_event_create(Cx(), &mEvAR)); TNB_CHECK(tnb_event_create(Cx(), &mEvDone));
+    }
+    const CuMatrix<BaseFloat> &E = GetErrorInput();
+    TNB_CHECK(tnb_event_record(Cx(), mEvE, TNB_STREAM_COMPUTE));        // E (and the previous bunch's use of the buffers) is done
+    TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_AUX, mEvE));
+    TnbBiasJob bj = {E.pCUData(), E.Dim(), NULL, mGrad.pCURowData(mRowsPad), 0.0f, 0.0f, 0, 0};  // gradient only
+    TNB_CHECK(tnb_bias_update_batch_on(Cx(), TNB_STREAM_AUX, &bj, 1));
+    TNB_CHECK(tnb_event_record(Cx(), mEvB, TNB_STREAM_AUX));
+    ComputeGradient(false);
+    TNB_CHECK(tnb_allreduce_sum_ev(Cx(), mGrad.pCUData(), GradCount(), mEvB, mEvAR));
+    TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_AUX2, mEvAR));
+    TnbSgdJob job = GradientJob(n_frames_global);
+    TNB_CHECK(tnb_sgd_update_batch_on(Cx(), TNB_STREAM_AUX2, &job, 1));
+    TNB_CHECK(tnb_event_record(Cx(), mEvDone, TNB_STREAM_AUX2));
+    *pDone = mEvDone;
+  }
   float *GradBuffer() { return mGrad.pCUData(); }
   size_t GradCount() const { return mGrad.Rows() * mGrad.Stride(); }
   void ApplyGradient(int n_frames_global) {
@@ -298,6 +324,7 @@ class CuBiasedLinearity : public CuUpdatableComponent {
   CuMatrix<BaseFloat> mGrad;  ///< data-parallel only: [dW ; db]
   int mDpFrames;
   size_t mRowsPad;
+  void *mEvE, *mEvB, *mEvAR, *mEvDone;  ///< data-parallel stream ordering (created on first use)
 };
 
 // =====================================================================================================
@@ -771,6 +798,7 @@ class CuNetwork {
     const int n = (int)mNetComponents.size();
     mNetComponents.back()->SetErrorInput(globerr);
     std::vector<CuBiasedLinearity *> pending;  // data parallel: layers whose gradient is in flight
+    std::vector<void *> dp_done;               // data parallel, all-reduce schedule: one event per layer, behind its update
     std::vector<TnbBiasJob> bias_jobs;         // fused schedule: bias halves of the updates, applied together after the last layer
     for (int i = n - 1; i >= 0; i--) {
       CuComponent *c = mNetComponents[i];
@@ -806,11 +834,9 @@ class CuNetwork {
             if (mDpShard) lin->ComputeGradient();
             if (mDpShard) lin->DataParallelUpdate((int)lin->GetInput().Rows() * mWorld);  // reduce-scatter / update / all-gather
             else {
-              // all-reduce of the weight gradient on the communication stream: overlaps the backward GEMMs of the layers below.
-              // (Measured on 2 B200: the collectives are the critical path of the step, so nothing else is queued behind them —
-              // running each layer's update on that stream as well cost 7 % — and the updates follow in one launch at the end.)
-              lin->ComputeGradient();
-              TNB_CHECK(tnb_allreduce_sum(Cx(), lin->GradBuffer(), lin->GradCount()));  // [dW ; db] in one exchange
+              void *done = NULL;
+              lin->DataParallelExchange((int)lin->GetInput().Rows() * mWorld, &done);
+              dp_done.push_back(done);
             }
             pending.push_back(lin);
           } else if (mFuse && c->GetType() == CuComponent::BIASED_LINEARITY) {
@@ -827,13 +853,8 @@ class CuNetwork {
       TNB_CHECK(tnb_bias_update_batch(Cx(), &bias_jobs[k], (int)std::min<size_t>(TNB_MAX_BIAS_JOBS, bias_jobs.size() - k)));
     if (!pending.empty()) {
       if (!mDpShard) {
-        TNB_CHECK(tnb_comm_wait(Cx()));
-        // every rank applies all layers' updates (weights and biases) from the summed gradients in one launch.  (Also tried on
-        // 2 B200 and slower: a separate batched bias exchange at the end of the pass — its small all-reduce is pure exposed latency.)
-        std::vector<TnbSgdJob> upd;
-        for (size_t k = 0; k < pending.size(); k++) upd.push_back(pending[k]->GradientJob((int)pending[k]->GetInput().Rows() * mWorld));
-        for (size_t k = 0; k < upd.size(); k += TNB_MAX_BIAS_JOBS)
-          TNB_CHECK(tnb_sgd_update_batch(Cx(), &upd[k], (int)std::min<size_t>(TNB_MAX_BIAS_JOBS, upd.size() - k)));
+        // the next forward pass reads the new weights: order the compute stream behind every layer's update (aux stream)
+        for (size_t k = 0; k < dp_done.size(); k++) TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_COMPUTE, dp_done[k]));
       } else {
         TNB_CHECK(tnb_comm_wait(Cx()));  // the next forward pass reads the gathered weights
       }

@@ -310,6 +310,27 @@ class FeatureRepository {
     mHeader.mNSamples = n;
     if (mTrace & 1) std::cout << "[" << rec.mLogical << " " << n << "frm]" << std::flush;
   }
+  /// write an uncompressed HTK parameter file in the byte order the reader was configured with (Features.cc:485-495,1481-1550)
+  bool WriteFeatureMatrix(const Matrix<BaseFloat> &rMatrix, const std::string &filename, int targetKind, int samplePeriod) {
+    FILE *f = fopen(filename.c_str(), "wb");
+    if (!f) { Error(std::string("Cannot create file:") + filename); return false; }
+    int32_t n = (int32_t)rMatrix.Rows(), per = (int32_t)samplePeriod;
+    int16_t size = (int16_t)(rMatrix.Cols() * sizeof(float));
+    uint16_t kind = (uint16_t)targetKind;
+    if (mSwap) { n = Swap32(n); per = Swap32(per); size = (int16_t)Swap16((uint16_t)size); kind = Swap16(kind); }
+    unsigned char hb[12];
+    memcpy(hb, &n, 4); memcpy(hb + 4, &per, 4); memcpy(hb + 8, &size, 2); memcpy(hb + 10, &kind, 2);
+    bool ok = fwrite(hb, 1, 12, f) == 12;
+    std::vector<uint32_t> row(rMatrix.Cols());
+    for (size_t r = 0; ok && r < rMatrix.Rows(); r++) {
+      memcpy(row.data(), rMatrix.pRowData(r), sizeof(float) * rMatrix.Cols());
+      if (mSwap) for (size_t c = 0; c < row.size(); c++) row[c] = (uint32_t)Swap32((int32_t)row[c]);
+      ok = fwrite(row.data(), 4, row.size(), f) == row.size();
+    }
+    fclose(f);
+    if (!ok) Error(std::string("Cannot write to file:") + filename);
+    return ok;
+  }
   static int ReadParmKind(const char *str, bool) {
     static const char *names[] = {"WAVEFORM", "LPC", "LPREFC", "LPCEPSTRA", "LPDELCEP", "IREFC", "MFCC", "FBANK", "MELSPEC", "USER", "DISCRETE", "PLP", "ANON"};
     std::string s(str);

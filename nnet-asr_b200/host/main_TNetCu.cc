@@ -127,7 +127,8 @@ int main(int argc, char *argv[]) try {
   if (!strcasecmp(math, "3xtf32")) CuDevice::Instantiate().SetMath(TNB_MATH_3XTF32);
   else if (!strcasecmp(math, "tf32")) CuDevice::Instantiate().SetMath(TNB_MATH_TF32);
   else if (!strcasecmp(math, "simt")) CuDevice::Instantiate().SetMath(TNB_MATH_FP32_SIMT);
-  else throw std::runtime_error(std::string("Invalid MATH '") + math + "' (3xtf32, tf32, simt)");
+  else if (!strcasecmp(math, "bf16")) CuDevice::Instantiate().SetMath(TNB_MATH_BF16);
+  else throw std::runtime_error(std::string("Invalid MATH '") + math + "' (3xtf32, tf32, bf16, simt)");
   bool fuse = ui.GetBool(SNAME ":FUSE", true);
 
   if (ui.GetBool(SNAME ":PRINTCONFIG", false)) { std::cout << std::endl; ui.PrintConfig(std::cout); std::cout << std::endl; }

@@ -3,6 +3,7 @@
 # from the sources where they lie under /root/reference into oracle/_ref/.
 #
 #   oracle/_ref/TNet          CPU trainer   (src/TNet.cc + KaldiLib + TNetLib)   -> cpu baseline + oracle pin
+#   oracle/_ref/TFeaCat       CPU forward-only tool (src/TFeaCat.cc, same libs)  -> golden for the TFeaCatCu drop-in
 #   oracle/_ref/TNetCu        GPU trainer   (src/TNetCu.cc + CuBaseLib + CuTNetLib, legacy cuBLAS) -> golden on B200
 #   oracle/_ref/TRbmCu, TRecurrentCu        same libs
 #
@@ -43,6 +44,12 @@ build_cpu() {
   wait
   g++ -o "$OUT/TNet" "${objs[@]}" "$OBLAS" -lpthread -Wl,--disable-new-dtags -Wl,-rpath,"$OBLAS_DIR"
   echo "built $OUT/TNet"
+  # forward-only tool of the CPU library (src/TFeaCat.cc): golden vectors for the TFeaCatCu drop-in
+  g++ $CXXF $INC -c "$REF/src/TFeaCat.cc" -o "$WORK/cpu/TFeaCat.o"
+  local lobjs=()
+  for o in "${objs[@]}"; do case "$o" in */TNet.o) ;; *) lobjs+=("$o");; esac; done
+  g++ -o "$OUT/TFeaCat" "$WORK/cpu/TFeaCat.o" "${lobjs[@]}" "$OBLAS" -lpthread -Wl,--disable-new-dtags -Wl,-rpath,"$OBLAS_DIR"
+  echo "built $OUT/TFeaCat"
 }
 
 build_gpu() {

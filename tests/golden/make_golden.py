@@ -196,6 +196,44 @@ def run_rnn(case, cfg, workdir, exe=None, save=True):
     print("gpu %s: %s" % (case, rep))
 
 
+# forward-only tool: name -> dict(raw_dim, ctx, hidden[], n_out, n_utt, n_frames, seed, log)
+FEACAT_CASES = {
+    "feacat_post": dict(raw_dim=13, ctx=3, hidden=[48, 40], n_out=300, n_utt=6, n_frames=70, seed=31, log=False),
+    "feacat_logpost": dict(raw_dim=13, ctx=2, hidden=[32], n_out=20, n_utt=5, n_frames=50, seed=32, log=True),
+}
+
+
+def run_feacat(case, cfg, workdir, exe=None, save=True):
+    """reference CPU TFeaCat (src/TFeaCat.cc) / our TFeaCatCu on the same files: per-utterance output features"""
+    rng = np.random.default_rng(cfg["seed"] + 3000)
+    utts = F.gen_utterances(cfg["n_utt"], cfg["n_frames"], cfg["raw_dim"], cfg["n_out"], rng)
+    paths = F.write_dataset(workdir, utts, cfg["n_out"], cfg["ctx"])
+    dims = [cfg["raw_dim"] * (2 * cfg["ctx"] + 1)] + cfg["hidden"] + [cfg["n_out"]]
+    layers = F.gen_mlp_init(dims, rng, negbias=False)
+    init = os.path.join(workdir, "init.nnet")
+    F.write_mlp(init, layers)
+    layers = F.read_mlp(init)
+    outdir = os.path.join(workdir, "out")
+    os.makedirs(outdir, exist_ok=True)
+    if exe is None:
+        exe = os.path.join(REF, "TFeaCat")
+    cmd = [exe, "-H", init, "-S", paths["scp"], "-l", outdir, "-y", "post", "--FEATURETRANSFORM=" + paths["transform"],
+           "--STARTFRMEXT=%d" % cfg["ctx"], "--ENDFRMEXT=%d" % cfg["ctx"], "--LOGPOSTERIOR=" + _b(cfg["log"])]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("TFeaCat failed:\n" + res.stdout[-3000:])
+    names = list(utts.keys())
+    outs = [F.read_htk(os.path.join(outdir, os.path.splitext(os.path.basename(f))[0] + ".post"))[0] for f in paths["files"]]
+    if not save:
+        return outs, res.stdout
+    data = dict(feats=np.concatenate([utts[n][0] for n in names]), lengths=np.array([utts[n][0].shape[0] for n in names], dtype=np.int32),
+                dims=np.array(dims, dtype=np.int32), cfg=np.array([cfg["ctx"], int(cfg["log"])], dtype=np.int64),
+                ref_out=np.concatenate(outs))
+    pack_layers("init", layers, data)
+    np.savez_compressed(os.path.join(OUT, "cpu_%s.npz" % case), **data)
+    print("cpu %s: %d utterances, output %s" % (case, len(outs), data["ref_out"].shape))
+
+
 def main():
     global OUT
     ap = argparse.ArgumentParser()
@@ -209,6 +247,10 @@ def main():
             continue
         with tempfile.TemporaryDirectory() as d:
             run_mlp(case, cfg, a.impl, d)
+    if a.impl == "cpu":
+        for case, cfg in FEACAT_CASES.items():
+            with tempfile.TemporaryDirectory() as d:
+                run_feacat(case, cfg, d)
     if a.impl == "gpu":
         for case, cfg in RBM_CASES.items():
             with tempfile.TemporaryDirectory() as d:

@@ -1,4 +1,4 @@
-"""Drop-in binaries: nnet-asr_b200/bin/{TNetCu,TRbmCu,TRecurrentCu} run with the reference's command lines on the
+"""Drop-in binaries: nnet-asr_b200/bin/{TNetCu,TRbmCu,TRecurrentCu,TFeaCatCu} run with the reference's command lines on the
 files the goldens were produced from, and must reproduce what the reference binaries wrote (network file, report line)."""
 import importlib.util
 import os
@@ -51,6 +51,21 @@ def test_trecurrentcu_binary_reproduces_reference():
     assert rep["frames"] == int(g["ref_frames"])
     assert abs(rep["err"] - float(g["ref_err"])) <= 2e-4 * abs(float(g["ref_err"]))
     np.testing.assert_allclose(LF[0][1], g["final_Wr"], rtol=3e-4, atol=3e-4 * np.abs(g["final_Wr"]).max())
+
+
+@pytest.mark.parametrize("case", ["feacat_post", "feacat_logpost"])
+def test_tfeacatcu_binary_reproduces_reference(case):
+    """bin/TFeaCatCu with the reference's command line on the files the golden was produced from == the features the unmodified
+    reference CPU tool TFeaCat wrote (3xTF32 forward vs the CPU's fp32 BLAS: 2e-5 relative; log-posteriors 2e-5 absolute)."""
+    g = np.load(os.path.join(GOLD, "cpu_%s.npz" % case))
+    with tempfile.TemporaryDirectory() as d:
+        outs, _ = MG.run_feacat(case, MG.FEACAT_CASES[case], d, exe=os.path.join(BIN, "TFeaCatCu"), save=False)
+    got = np.concatenate(outs)
+    assert got.shape == g["ref_out"].shape
+    if int(g["cfg"][1]):
+        np.testing.assert_allclose(got, g["ref_out"], rtol=2e-5, atol=2e-5)
+    else:
+        np.testing.assert_allclose(got, g["ref_out"], rtol=2e-5, atol=1e-9)
 
 
 def test_cli_errors_like_the_reference():

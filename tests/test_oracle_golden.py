@@ -49,3 +49,18 @@ def test_oracle_vs_reference_gpu_tnetcu(path):
         pytest.skip("GPU goldens not generated yet (tests/golden/make_golden.py --impl gpu on a B200)")
     g = np.load(path)
     _check(g, 0, wtol=5e-5, etol=5e-5)
+
+
+@pytest.mark.parametrize("case", ["feacat_post", "feacat_logpost"])
+def test_oracle_forward_vs_reference_cpu_tfeacat(case):
+    """Forward-only pin: the oracle's Propagate on the golden inputs == what the unmodified reference CPU tool TFeaCat wrote
+    (posteriors, or log-posteriors with --LOGPOSTERIOR=TRUE), utterance by utterance."""
+    from replay import fixture_layers, utterances
+    g = np.load(os.path.join(GOLD, "cpu_%s.npz" % case))
+    net = O.Net(fixture_layers(g), acc_double=1)
+    got = np.concatenate([net.propagate(f) for f, _ in utterances(g)])
+    if int(g["cfg"][1]):
+        got = np.log(got.astype(np.float64)).astype(np.float32)      # TFeaCat.cc: static_cast<BaseFloat>(log(x))
+        np.testing.assert_allclose(got, g["ref_out"], rtol=2e-5, atol=2e-5)
+    else:
+        np.testing.assert_allclose(got, g["ref_out"], rtol=2e-5, atol=1e-9)
