@@ -22,6 +22,8 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <algorithm>
+#include <thread>
 #include <vector>
 
 namespace TNet {
@@ -123,14 +125,26 @@ typedef Matrix<BaseFloat> BfMatrix;
 typedef Vector<BaseFloat> BfVector;
 
 // ---- text format -------------------------------------------------------------------------------------
-// numbers are read with strtod semantics on whitespace-separated tokens (also accepts "inf"/"nan")
+// Same text as the reference (KaldiLib/Matrix.tcc:522-600, Vector.tcc:527-571: `ostream << float` at the default precision of 6
+// = printf's %g), produced and parsed fast enough that a 28M-weight network does not dominate a short run: numbers are
+// scanned straight from the stream buffer with strtod semantics (also "inf"/"nan"), large matrices are formatted row block by
+// row block on several threads and written in order.
 template <typename T>
 inline bool ReadNumber(std::istream &in, T &v) {
-  std::string tok;
-  if (!(in >> tok)) return false;
+  std::streambuf *sb = in.rdbuf();
+  int ch = sb->sgetc();
+  while (ch != std::char_traits<char>::eof() && (ch == ' ' || ch == '\n' || ch == '\t' || ch == '\r' || ch == '\f' || ch == '\v')) ch = sb->snextc();
+  if (ch == std::char_traits<char>::eof()) { in.setstate(std::ios::eofbit | std::ios::failbit); return false; }
+  char tok[64];
+  int n = 0;
+  while (ch != std::char_traits<char>::eof() && !(ch == ' ' || ch == '\n' || ch == '\t' || ch == '\r' || ch == '\f' || ch == '\v')) {
+    if (n < 63) tok[n++] = (char)ch; else return false;
+    ch = sb->snextc();
+  }
+  tok[n] = '\0';
   char *end = 0;
-  double d = std::strtod(tok.c_str(), &end);
-  if (end == tok.c_str() || *end != '\0') return false;
+  double d = std::strtod(tok, &end);
+  if (end == tok || *end != '\0') return false;
   v = (T)d;
   return true;
 }
@@ -145,17 +159,49 @@ std::istream &operator>>(std::istream &in, Matrix<T> &m) {
     if (in.fail() || r < 0 || c < 0) throw std::runtime_error("Failed to read matrix from stream: no size\n");
     if (m.Rows() != (size_t)r || m.Cols() != (size_t)c) m.Init(r, c);
   }
-  for (size_t i = 0; i < m.Rows(); i++)
-    for (size_t j = 0; j < m.Cols(); j++)
-      if (!ReadNumber(in, m(i, j))) throw std::runtime_error("Failed to read matrix from stream");
+  T *p = m.pData();
+  const size_t total = m.Rows() * m.Cols();
+  for (size_t i = 0; i < total; i++)
+    if (!ReadNumber(in, p[i])) throw std::runtime_error("Failed to read matrix from stream");
   return in;
+}
+// rows [r0, r1) of m as text, one row per line, every number followed by a blank
+template <typename T>
+inline void FormatRows(const Matrix<T> &m, size_t r0, size_t r1, std::string &out) {
+  out.clear();
+  out.reserve((r1 - r0) * m.Cols() * 12);
+  char buf[48];
+  for (size_t i = r0; i < r1; i++) {
+    const T *row = m.pRowData(i);
+    for (size_t j = 0; j < m.Cols(); j++) {
+      int n = snprintf(buf, sizeof(buf), "%g ", (double)row[j]);
+      out.append(buf, (size_t)n);
+    }
+    out.push_back('\n');
+  }
 }
 template <typename T>
 std::ostream &operator<<(std::ostream &out, const Matrix<T> &m) {
   out << "m " << m.Rows() << ' ' << m.Cols() << '\n';
-  for (size_t i = 0; i < m.Rows(); i++) {
-    for (size_t j = 0; j < m.Cols(); j++) out << m(i, j) << ' ';
-    out << '\n';
+  const size_t total = m.Rows() * m.Cols();
+  unsigned nthr = std::thread::hardware_concurrency();
+  if (nthr > 16) nthr = 16;
+  if (total < (1u << 18) || nthr < 2 || m.Rows() < 2 * nthr) {
+    std::string s;
+    FormatRows(m, 0, m.Rows(), s);
+    out.write(s.data(), (std::streamsize)s.size());
+  } else {
+    // blocks of rows, `nthr` at a time, written in order (bounded memory: a block is ~rows/(4*nthr) rows of text)
+    const size_t nblk = 4 * nthr, per = (m.Rows() + nblk - 1) / nblk;
+    std::vector<std::string> txt(nthr);
+    for (size_t b0 = 0; b0 < nblk; b0 += nthr) {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nthr && b0 + t < nblk; t++) {
+        const size_t r0 = std::min(m.Rows(), (b0 + t) * per), r1 = std::min(m.Rows(), (b0 + t + 1) * per);
+        th.emplace_back([&m, &txt, t, r0, r1]() { FormatRows(m, r0, r1, txt[t]); });
+      }
+      for (size_t t = 0; t < th.size(); t++) { th[t].join(); out.write(txt[t].data(), (std::streamsize)txt[t].size()); }
+    }
   }
   if (out.fail()) throw std::runtime_error("Failed to write matrix to stream");
   return out;
