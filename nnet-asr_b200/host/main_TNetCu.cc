@@ -70,7 +70,7 @@ int main(int argc, char *argv[]) try {
   FeatureRepository feature_repo;
   LabelRepository label_repo;
   Timer timer, timer_frontend;
-  double time_frontend = 0.0;
+  double time_frontend = 0.0, time_read = 0.0, time_xform = 0.0, time_labels = 0.0, time_cache = 0.0, time_write = 0.0;
 
   if (argc == 1) usage(argv[0]);
   int args_parsed = ui.ParseOptions(argc, argv, p_option_string, SNAME);
@@ -204,19 +204,24 @@ int main(int argc, char *argv[]) try {
     timer_frontend.Start();
     while (!cache.Full() && !feature_repo.EndOfList()) {
       Matrix<BaseFloat> feats_host;
+      Timer t_part;
+      t_part.Start();
       feature_repo.ReadFullMatrix(feats_host);
       feats_host.CheckData(feature_repo.Current().Logical());
+      t_part.End(); time_read += t_part.Val(); t_part.Start();
       feats_original.CopyFrom(feats_host);
       transform_network.Propagate(feats_original, feats_expanded);
       int rows = (int)feats_expanded.Rows() - start_frm_ext - end_frm_ext;
       if (rows < 1) Error(std::string("Utterance shorter than the frame extension: ") + feature_repo.Current().Logical());
       feats_trim.Init(rows, feats_expanded.Cols());
       feats_trim.CopyRows(rows, start_frm_ext, feats_expanded, 0);
+      t_part.End(); time_xform += t_part.Val(); t_part.Start();
       // labels: class ids go to the device (4 bytes/frame instead of 4*nOutputs) and are expanded to one-hot rows there
       std::vector<int> ids;
       label_repo.GenLabelIds(ids, rows, feature_repo.CurrentHeader().mSamplePeriod, feature_repo.Current().Logical().c_str());
       Vector<int> ids_host(rows);
       for (int i = 0; i < rows; i++) ids_host[i] = ids[i];
+      t_part.End(); time_labels += t_part.Val(); t_part.Start();
       label_ids.CopyFrom(ids_host);
       labs_cu.Init(rows, label_repo.NOutputs());
       TNB_CHECK(tnb_onehot(Cx(), labs_cu.pCUData(), label_ids.pCUData(), labs_cu.Dim()));
@@ -227,6 +232,7 @@ int main(int argc, char *argv[]) try {
         Error(os.str());
       }
       cache.AddData(feats_trim, labs_cu);
+      t_part.End(); time_cache += t_part.Val();
       feature_repo.MoveNext();
     }
     timer_frontend.End();
@@ -243,6 +249,8 @@ int main(int argc, char *argv[]) try {
   }
   if (trace & 1) TraceLog("Training finished");
 
+  Timer t_write;
+  t_write.Start();
   if (!cross_validate) {
     char p_trg_mmf_file[4096];
     if (NULL != p_targetmmf) {
@@ -254,12 +262,15 @@ int main(int argc, char *argv[]) try {
       network.WriteNetwork(p_trg_mmf_file);
     }
   }
+  t_write.End();
+  time_write = t_write.Val();
   size_t frames = p_obj_function->GetFrames();  // reads the device accumulators (synchronises)
   timer.End();
   std::cout << "===== TNET " << (cross_validate ? "CROSSVALIDATION" : "TRAINING") << " FINISHED ( " << timer.Val() << "s ) "
             << "[FPS:" << frames / timer.Val() << ",RT:" << 1.0f / (frames / timer.Val() / 100.0f) << "] =====" << std::endl;
   std::cout << "-- " << (cross_validate ? "CV " : "TR ") << p_obj_function->Report();
-  if (trace & 4) std::cout << "\n== PROFILE ==\nT-fe: " << time_frontend << "\nkernel launches: " << CuDevice::Instantiate().Launches() << std::endl;
+  if (trace & 4) std::cout << "\n== PROFILE ==\nT-fe: " << time_frontend << " (read+check " << time_read << ", H2D+transform " << time_xform << ", labels "
+                           << time_labels << ", one-hot+cache " << time_cache << ")\nT-write(sync+network file): " << time_write << "\nkernel launches: " << CuDevice::Instantiate().Launches() << std::endl;
   delete p_obj_function;
   return 0;
 } catch (std::exception &rExc) {

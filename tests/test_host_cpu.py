@@ -130,3 +130,15 @@ def test_data_parallel_arithmetic_two_gloo_ranks(tmp_path):
                         "--master-port", "29517", str(script), os.path.join(ROOT, "tests"), os.path.join(ROOT, "nnet-asr_b200", "python")],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "DP_OK" in r.stdout, r.stdout[-3000:]
+
+
+def test_fast_text_reader_writer_matches_ostream_format(tmp_path):
+    """tests/cpp/test_text_io.cc: the threaded %g writer is byte-identical to the reference's `ostream << float` loop and the
+    stream-buffer scanner reads what strtod reads (incl. inf/nan/denormals, truncated and malformed input)."""
+    import subprocess
+    exe = str(tmp_path / "test_text_io")
+    src = os.path.join(ROOT, "tests", "cpp", "test_text_io.cc")
+    inc = os.path.join(ROOT, "nnet-asr_b200", "host")
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-pthread", "-I", inc, "-o", exe, src])
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode == 0 and "TEXT_IO_OK" in r.stdout, r.stderr
