@@ -121,7 +121,9 @@ int tnb_allreduce_sum_ev(TnbContext *ctx, float *buf, size_t count, void *event,
   TNB_CUDA(cudaEventRecord(ctx->ev_compute, ctx->stream));
   TNB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_compute, 0));
   if (event) TNB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, (cudaEvent_t)event, 0));
-  if (ctx->world > 1) {  // single rank: the sum is the buffer itself
+  static int skip = -1;  // TNB_DP_SKIP_COMM=1: timing experiment only (the data-parallel step without its collectives; results are wrong)
+  if (skip < 0) { const char *e = getenv("TNB_DP_SKIP_COMM"); skip = (e && atoi(e) != 0) ? 1 : 0; }
+  if (ctx->world > 1 && !skip) {  // single rank: the sum is the buffer itself
     TNB_ARG(ctx->nccl_comm != nullptr, "communicator not initialised");
     TNB_NCCL(p_AllReduce(buf, buf, count, kNcclFloat, kNcclSum, (NcclComm)ctx->nccl_comm, ctx->comm_stream));
   }

@@ -183,7 +183,13 @@ int tnb_ctx_create(TnbContext **out, int device) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   TNB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  TNB_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  {
+    // TNB_COMM_PRIORITY=1: collectives on the highest-priority stream (their few CTAs are placed before a waiting GEMM wave)
+    const char *e = getenv("TNB_COMM_PRIORITY");
+    int lo = 0, hi = 0;
+    TNB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    TNB_CUDA(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, (e && atoi(e) != 0) ? hi : 0));
+  }
   TNB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   TNB_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
   TNB_CUDA(cudaStreamCreateWithFlags(&ctx->aux2_stream, cudaStreamNonBlocking));

@@ -282,6 +282,7 @@ int tnh_net_train_resident(TnhNet *h, int bunch, int first, int n, int cv) {
     TNB_CHECK(tnb_onehot(Cx(), h->labs.pCUData(), h->res_labels.pCUData() + r0, h->labs.Dim()));
     h->Step(cv != 0);
   }
+  h->net.WaitDataParallel();  // the last bunch's exchange belongs to this call (stream order; the host does not block)
   TNH_CATCH
 }
 

@@ -143,7 +143,7 @@ class CuBiasedLinearity : public CuUpdatableComponent {
  public:
   CuBiasedLinearity(size_t nInputs, size_t nOutputs, CuComponent *pPred)
       : CuUpdatableComponent(nInputs, nOutputs, pPred), mLinearity(nInputs, nOutputs), mBias(nOutputs),
-        mLinearityCorrection(nInputs, nOutputs), mBiasCorrection(nOutputs), mDpFrames(0), mRowsPad(0), mEvE(NULL), mEvB(NULL), mEvAR(NULL), mEvDone(NULL) {}
+        mLinearityCorrection(nInputs, nOutputs), mBiasCorrection(nOutputs), mDpFrames(0), mRowsPad(0), mEvE(NULL), mEvB(NULL), mEvAR(NULL), mEvDone(NULL), mDpPending(false) {}
   ~CuBiasedLinearity() {
     if (mEvE) { tnb_event_destroy(Cx(), mEvE); tnb_event_destroy(Cx(), mEvB); tnb_event_destroy(Cx(), mEvAR); tnb_event_destroy(Cx(), mEvDone); }
   }
@@ -154,6 +154,7 @@ class CuBiasedLinearity : public CuUpdatableComponent {
   // stale) and writes the twin of its result from the epilogue, so that no conversion pass runs between the layers.
   static bool Bf16() { return CuDevice::Instantiate().Math() == TNB_MATH_BF16; }
   void Forward(const CuMatrix<BaseFloat> &X, CuMatrix<BaseFloat> &Y, int act) {
+    WaitDataParallel();
     const CuMatrix<BaseFloat> &W = mLinearity;
     if (Bf16()) {
       const uint16_t *x16 = X.Twin(), *w16 = W.Twin();
@@ -174,6 +175,7 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     BackpropagateDiffSigmoid(E, &Yprev, Eprev);
   }
   void BackpropagateDiffSigmoid(const CuMatrix<BaseFloat> &E, const CuMatrix<BaseFloat> *pYprev, CuMatrix<BaseFloat> &Eprev) {
+    WaitDataParallel();
     const CuMatrix<BaseFloat> &W = mLinearity;
     TnbMatrixDim none = {0, 0, 0};
     const float *yp = pYprev ? pYprev->pCUData() : NULL;
@@ -193,6 +195,7 @@ class CuBiasedLinearity : public CuUpdatableComponent {
   /// pDeferredBias != NULL: only the weight half runs now; the bias half (which nothing reads before the next forward pass) is
   /// described in *pDeferredBias for CuNetwork to apply together with the other layers' (tnb_bias_update_batch)
   void Update(TnbBiasJob *pDeferredBias) {
+    WaitDataParallel();
     const CuMatrix<BaseFloat> &X = GetInput(), &E = GetErrorInput();
     float *bias = pDeferredBias ? NULL : mBias.pCUData(), *corrb = pDeferredBias ? NULL : mBiasCorrection.pCUData();
     if (pDeferredBias) {
@@ -250,10 +253,9 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     if (Bf16()) { j.W16 = mLinearity.TwinForWrite(); j.ldw16 = mLinearity.TwinStride(); }  // (... and this hands it to the kernel)
     return j;
   }
-  /// all-reduce schedule, one layer: the bias gradient (column sums of E) on a side stream, the weight gradient GEMM on the
-  /// compute stream, the all-reduce of [dW ; db] on the communication stream behind both, the update on a second side stream behind
-  /// the all-reduce.  Only the GEMM stays on the compute stream's critical path; *pDone is recorded behind the update.
-  void DataParallelExchange(int n_frames_global, void **pDone) {
+  /// all-reduce schedule, one layer, first half: the bias gradient (column sums of E) on a side stream, the weight gradient
+  /// GEMM on the compute stream.  Only the GEMM stays on the compute stream's critical path.
+  void DataParallelGradient() {
     if (mRowsPad == 0) PrepareDataParallel(1);
     if (!mEvE) {
       TNB_CHECK(tnb_event_create(Cx(), &mEvE)); TNB_CHECK(tnb_event_create(Cx(), &mEvB));
@@ -266,12 +268,23 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     TNB_CHECK(tnb_bias_update_batch_on(Cx(), TNB_STREAM_AUX, &bj, 1));
     TNB_CHECK(tnb_event_record(Cx(), mEvB, TNB_STREAM_AUX));
     ComputeGradient(false);
+  }
+  /// second half: the all-reduce of [dW ; db] on the communication stream behind both, the update on a second side stream behind
+  /// the all-reduce.  Nothing waits for it here: whoever touches the parameters next does (WaitDataParallel), which lets the
+  /// exchange of this bunch run into the forward pass of the next one.
+  void DataParallelReduceUpdate(int n_frames_global) {
     TNB_CHECK(tnb_allreduce_sum_ev(Cx(), mGrad.pCUData(), GradCount(), mEvB, mEvAR));
     TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_AUX2, mEvAR));
     TnbSgdJob job = GradientJob(n_frames_global);
     TNB_CHECK(tnb_sgd_update_batch_on(Cx(), TNB_STREAM_AUX2, &job, 1));
     TNB_CHECK(tnb_event_record(Cx(), mEvDone, TNB_STREAM_AUX2));
-    *pDone = mEvDone;
+    mDpPending = true;
+  }
+  /// order the compute stream behind this layer's outstanding data-parallel update (no host synchronisation)
+  void WaitDataParallel() const {
+    if (!mDpPending) return;
+    TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_COMPUTE, mEvDone));
+    mDpPending = false;
   }
   float *GradBuffer() { return mGrad.pCUData(); }
   size_t GradCount() const { return mGrad.Rows() * mGrad.Stride(); }
@@ -282,6 +295,7 @@ class CuBiasedLinearity : public CuUpdatableComponent {
   }
 
   void ReadFromStream(std::istream &rIn) {
+    WaitDataParallel();
     BfMatrix transpose;  // stored transposed [out x in] (cuBiasedLinearity.cc:70-78)
     rIn >> transpose;
     BfVector bias;
@@ -299,6 +313,7 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     mBias.CopyFrom(bias);
   }
   void WriteToStream(std::ostream &rOut) {
+    WaitDataParallel();
     BfMatrix tmp;
     mLinearity.CopyTo(tmp);
     rOut << BfMatrix(tmp, TRANS);
@@ -309,12 +324,13 @@ class CuBiasedLinearity : public CuUpdatableComponent {
   }
   /// set the parameters from host memory; Wt is the on-disk layout [nOutputs x nInputs]
   void SetParams(const BfMatrix &Wt, const BfVector &bias) {
+    WaitDataParallel();
     if (Wt.Rows() != GetNOutputs() || Wt.Cols() != GetNInputs() || bias.Dim() != GetNOutputs()) Error("SetParams: wrong dimensions");
     mLinearity.CopyFrom(BfMatrix(Wt, TRANS));
     mBias.CopyFrom(bias);
   }
-  const CuMatrix<BaseFloat> &Linearity() const { return mLinearity; }
-  const CuVector<BaseFloat> &Bias() const { return mBias; }
+  const CuMatrix<BaseFloat> &Linearity() const { WaitDataParallel(); return mLinearity; }
+  const CuVector<BaseFloat> &Bias() const { WaitDataParallel(); return mBias; }
 
  protected:
   CuMatrix<BaseFloat> mLinearity;  ///< [nInputs x nOutputs]
@@ -325,6 +341,7 @@ class CuBiasedLinearity : public CuUpdatableComponent {
   int mDpFrames;
   size_t mRowsPad;
   void *mEvE, *mEvB, *mEvAR, *mEvDone;  ///< data-parallel stream ordering (created on first use)
+  mutable bool mDpPending;              ///< an update of this layer is in flight on the side streams
 };
 
 // =====================================================================================================
@@ -737,12 +754,12 @@ inline CuObjectiveFunction *CuObjectiveFunction::Factory(ObjFunType type) {
 class CuNetwork {
   typedef std::vector<CuComponent *> LayeredType;
  public:
-  CuNetwork() : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mDpShard(false) {
+  CuNetwork() : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false) {
     const char *e = getenv("TNB_FUSE");
     if (e && atoi(e) == 0) mFuse = false;
   }
   explicit CuNetwork(std::istream &rIn)
-      : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mDpShard(false) {
+      : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false) {
     ReadNetwork(rIn);
   }
   ~CuNetwork() {
@@ -761,11 +778,26 @@ class CuNetwork {
   CuComponent &Layer(int i) { return *mNetComponents[i]; }
 
   void SetFusion(bool on) { mFuse = on; }
+  /// order the compute stream behind every outstanding data-parallel update (stream order only; callers that time or end a
+  /// run of bunches use it so that the last bunch's exchange is inside what they measure)
+  void WaitDataParallel() {
+    for (size_t i = 0; i < mNetComponents.size(); i++)
+      if (mNetComponents[i]->GetType() == CuComponent::BIASED_LINEARITY) static_cast<CuBiasedLinearity *>(mNetComponents[i])->WaitDataParallel();
+  }
   /// data parallel over `world` ranks: Update() becomes gradient -> all-reduce -> apply (N uses rows*world)
   void SetDataParallel(int world) {
     mWorld = world;
     const char *e = getenv("TNB_DP_MODE");
     mDpShard = e && !strcmp(e, "shard");
+    // default: with L >= 6 updatable layers the top one and the bottom two exchange at once, the middle ones late (measured on
+    // 2 B200, config C, ms per bunch: no deferral 1.311, 1:5 1.244, 2:5 1.261, 3:5 1.288, 2:6 1.305);
+    // TNB_DP_DEFER=begin:end overrides (0:0 = plain top-to-bottom order)
+    int nupd = 0;
+    for (size_t i = 0; i < mNetComponents.size(); i++) nupd += mNetComponents[i]->GetType() == CuComponent::BIASED_LINEARITY;
+    mDpDeferBegin = mDpDeferEnd = 0;
+    if (nupd >= 6) { mDpDeferBegin = 1; mDpDeferEnd = nupd - 2; }
+    const char *d = getenv("TNB_DP_DEFER");
+    if (d) { int a = 0, b = 0; if (sscanf(d, "%d:%d", &a, &b) == 2) { mDpDeferBegin = a; mDpDeferEnd = b; } }
     for (size_t i = 0; i < mNetComponents.size(); i++)
       if (mNetComponents[i]->GetType() == CuComponent::BIASED_LINEARITY) static_cast<CuBiasedLinearity *>(mNetComponents[i])->PrepareDataParallel(world);
   }
@@ -798,7 +830,7 @@ class CuNetwork {
     const int n = (int)mNetComponents.size();
     mNetComponents.back()->SetErrorInput(globerr);
     std::vector<CuBiasedLinearity *> pending;  // data parallel: layers whose gradient is in flight
-    std::vector<void *> dp_done;               // data parallel, all-reduce schedule: one event per layer, behind its update
+    std::vector<CuBiasedLinearity *> deferred; // data parallel, all-reduce schedule: layers whose exchange is issued after the lowest layer's
     std::vector<TnbBiasJob> bias_jobs;         // fused schedule: bias halves of the updates, applied together after the last layer
     for (int i = n - 1; i >= 0; i--) {
       CuComponent *c = mNetComponents[i];
@@ -834,9 +866,14 @@ class CuNetwork {
             if (mDpShard) lin->ComputeGradient();
             if (mDpShard) lin->DataParallelUpdate((int)lin->GetInput().Rows() * mWorld);  // reduce-scatter / update / all-gather
             else {
-              void *done = NULL;
-              lin->DataParallelExchange((int)lin->GetInput().Rows() * mWorld, &done);
-              dp_done.push_back(done);
+              // Gradient now; exchange + update now or deferred.  The collectives are the step's critical path and the lowest
+              // layer's gradient, which the next forward pass needs FIRST, is the last one to exist: the middle layers'
+              // exchanges are therefore issued after the lowest layers', in forward order, and run into the next bunch's
+              // forward pass (every layer's forward waits only for its own update, CuBiasedLinearity::WaitDataParallel).
+              lin->DataParallelGradient();
+              const int k = (int)pending.size();
+              if (k >= mDpDeferBegin && k < mDpDeferEnd) deferred.push_back(lin);
+              else lin->DataParallelReduceUpdate((int)lin->GetInput().Rows() * mWorld);
             }
             pending.push_back(lin);
           } else if (mFuse && c->GetType() == CuComponent::BIASED_LINEARITY) {
@@ -851,14 +888,9 @@ class CuNetwork {
     }
     for (size_t k = 0; k < bias_jobs.size(); k += TNB_MAX_BIAS_JOBS)
       TNB_CHECK(tnb_bias_update_batch(Cx(), &bias_jobs[k], (int)std::min<size_t>(TNB_MAX_BIAS_JOBS, bias_jobs.size() - k)));
-    if (!pending.empty()) {
-      if (!mDpShard) {
-        // the next forward pass reads the new weights: order the compute stream behind every layer's update (aux stream)
-        for (size_t k = 0; k < dp_done.size(); k++) TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_COMPUTE, dp_done[k]));
-      } else {
-        TNB_CHECK(tnb_comm_wait(Cx()));  // the next forward pass reads the gathered weights
-      }
-    }
+    for (size_t k = deferred.size(); k-- > 0;)  // bottom-most deferred layer first: the order the next forward pass needs them
+      deferred[k]->DataParallelReduceUpdate((int)deferred[k]->GetInput().Rows() * mWorld);
+    if (!pending.empty() && mDpShard) TNB_CHECK(tnb_comm_wait(Cx()));  // the next forward pass reads the gathered weights
     // restore the wiring the fused softmax step changed
     if (mFuse && n >= 2 && mNetComponents[n - 1]->GetType() == CuComponent::SOFTMAX)
       mNetComponents[n - 2]->SetErrorInput(mNetComponents[n - 1]->GetErrorOutput());
@@ -972,6 +1004,7 @@ class CuNetwork {
   const char *mpTempBasisDir;
   bool mFuse;
   int mWorld;
+  int mDpDeferBegin, mDpDeferEnd;  ///< all-reduce schedule: updatable layers [begin, end), counted from the top, exchange late
   bool mDpShard;  ///< data-parallel schedule: false = all-reduce + batched update (default), true = tnb_dp_update (TNB_DP_MODE=shard)
 };
 
