@@ -133,6 +133,9 @@ int tnb_expand(TnbContext *ctx, float *y, const float *x, const int *off, TnbMat
 int tnb_rearrange(TnbContext *ctx, float *y, const float *x, const int *copy_from, TnbMatrixDim d_out, TnbMatrixDim d_in); /* :44 */
 /* y[r,:] = x[copy_from[r],:] for r < d_out.rows (= permutation length), cumath.cc:155-174 */
 int tnb_randomize(TnbContext *ctx, float *y, const float *x, const int *copy_from, TnbMatrixDim d_out, TnbMatrixDim d_in); /* :45 */
+/* sum[c] += sum_r X[r,c] ; sumsq[c] += sum_r (float)(X[r,c]*X[r,c]); sum/sumsq: DEVICE doubles [cols], accumulated across calls
+ * (the global mean/variance statistics TNormCu.cc:268-272 gathers on the host after copying every utterance back) */
+int tnb_accum_moments(TnbContext *ctx, const float *X, TnbMatrixDim d, double *sum, double *sumsq);
 /* match[r] = argmax(out[r,:]) == argmax(des[r,:]) with the reference's tie rules (bit-exact):
  * cols > 256 sequential first-max; cols <= 256 the index tree of _max_id_reduce (cukernels.cu:424-446). */
 int tnb_check_class(TnbContext *ctx, const float *out, const float *des, int *match, TnbMatrixDim d); /* :47-48 */

@@ -196,6 +196,32 @@ __global__ void __launch_bounds__(256) colsum_final_batch_kernel(const __grid_co
   j.bias[c] = j.scale * v + j.bias[c];
 }
 
+// ---------------------------------------------------------------------------------------- first / second moments (TNormCu)
+// sum[c] += sum_r x[r,c] ; sumsq[c] += sum_r (float)(x[r,c]*x[r,c])  in double (TNormCu.cc:268-272 accumulates float products into
+// double vectors on the host after a D2H copy of every utterance).  One CTA per 128 columns x row slice, double atomics at the end:
+// the accumulators are doubles, so the order of the additions moves the result by ~1e-16 relative.
+__global__ void __launch_bounds__(256) moments_kernel(const float *__restrict__ x, int rows, int cols, int stride, int chunk,
+                                                      double *__restrict__ sum, double *__restrict__ sumsq) {
+  __shared__ double s1[8][33], s2[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const int r0 = blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
+  double a = 0.0, b = 0.0;
+  if (c < cols)
+    for (int r = r0 + ry; r < r1; r += 8) {
+      const float v = x[(size_t)r * stride + c];
+      a += (double)v;
+      b += (double)(v * v);
+    }
+  s1[ry][cx] = a; s2[ry][cx] = b;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    for (int k = 1; k < 8; k++) { a += s1[k][cx]; b += s2[k][cx]; }
+    atomicAdd(&sum[c], a);
+    atomicAdd(&sumsq[c], b);
+  }
+}
+
 // ---------------------------------------------------------------------------------------- gathers
 // _randomize (cukernels.cu:384-393): y[r,:] = x[perm[r],:]   — one warp per row, 16-byte copies
 __global__ void __launch_bounds__(256) gather_rows_kernel(float *__restrict__ y, const float *__restrict__ x,
@@ -644,6 +670,19 @@ int tnb_rand_binarize(TnbContext *ctx, float *states, const float *probs, unsign
 int tnb_add_gauss_noise(TnbContext *ctx, float *tgt, float gscale, unsigned *z1, unsigned *z2, unsigned *z3, unsigned *z4,
                         TnbMatrixDim d) {
   return launch_rand<3>(ctx, tgt, nullptr, gscale, z1, z2, z3, z4, d);
+}
+
+int tnb_accum_moments(TnbContext *ctx, const float *X, TnbMatrixDim d, double *sum, double *sumsq) {
+  TNB_ARG(ctx && X && sum && sumsq, "null");
+  DIMCHK(d);
+  if (d.rows == 0 || d.cols == 0) return TNB_OK;
+  const int cb = (d.cols + 31) / 32;
+  int S = (2 * ctx->sm_count + cb - 1) / cb;
+  if (S > (d.rows + 63) / 64) S = (d.rows + 63) / 64;
+  if (S < 1) S = 1;
+  moments_kernel<<<dim3(cb, S), 256, 0, ctx->stream>>>(X, d.rows, d.cols, d.stride, (d.rows + S - 1) / S, sum, sumsq);
+  TNB_LAUNCHED(ctx);
+  return TNB_OK;
 }
 
 int tnb_to_bf16(TnbContext *ctx, uint16_t *dst, int dst_stride, const float *src, TnbMatrixDim d) {

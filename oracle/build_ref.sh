@@ -4,6 +4,7 @@
 #
 #   oracle/_ref/TNet          CPU trainer   (src/TNet.cc + KaldiLib + TNetLib)   -> cpu baseline + oracle pin
 #   oracle/_ref/TFeaCat       CPU forward-only tool (src/TFeaCat.cc, same libs)  -> golden for the TFeaCatCu drop-in
+#   oracle/_ref/TNorm         CPU mean/variance estimator (src/TNorm.cc)         -> golden for the TNormCu drop-in
 #   oracle/_ref/TNetCu        GPU trainer   (src/TNetCu.cc + CuBaseLib + CuTNetLib, legacy cuBLAS) -> golden on B200
 #   oracle/_ref/TRbmCu, TRecurrentCu        same libs
 #
@@ -50,6 +51,10 @@ build_cpu() {
   for o in "${objs[@]}"; do case "$o" in */TNet.o) ;; *) lobjs+=("$o");; esac; done
   g++ -o "$OUT/TFeaCat" "$WORK/cpu/TFeaCat.o" "${lobjs[@]}" "$OBLAS" -lpthread -Wl,--disable-new-dtags -Wl,-rpath,"$OBLAS_DIR"
   echo "built $OUT/TFeaCat"
+  # global mean/variance estimator of the CPU library (src/TNorm.cc): golden vectors for the TNormCu drop-in
+  g++ $CXXF $INC -c "$REF/src/TNorm.cc" -o "$WORK/cpu/TNorm.o"
+  g++ -o "$OUT/TNorm" "$WORK/cpu/TNorm.o" "${lobjs[@]}" "$OBLAS" -lpthread -Wl,--disable-new-dtags -Wl,-rpath,"$OBLAS_DIR"
+  echo "built $OUT/TNorm"
 }
 
 build_gpu() {

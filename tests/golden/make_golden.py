@@ -234,6 +234,39 @@ def run_feacat(case, cfg, workdir, exe=None, save=True):
     print("cpu %s: %d utterances, output %s" % (case, len(outs), data["ref_out"].shape))
 
 
+NORM_CASES = {"norm_splice": dict(raw_dim=13, ctx=3, n_utt=9, n_frames=80, seed=41)}
+
+
+def run_norm(case, cfg, workdir, exe=None, save=True):
+    """reference CPU TNorm (src/TNorm.cc) / our TNormCu: global mean/variance of the spliced features -> <bias> + <window>"""
+    rng = np.random.default_rng(cfg["seed"] + 4000)
+    utts = F.gen_utterances(cfg["n_utt"], cfg["n_frames"], cfg["raw_dim"], 4, rng)
+    utts = {k: ((v[0] * rng.uniform(0.2, 3.0, cfg["raw_dim"]) + rng.uniform(-2, 2, cfg["raw_dim"])).astype(np.float32), v[1]) for k, v in utts.items()}
+    paths = F.write_dataset(workdir, utts, 4, cfg["ctx"])
+    target = os.path.join(workdir, "norm.transf")
+    cmd = [exe or os.path.join(REF, "TNorm"), "-H", paths["transform"], "-S", paths["scp"], "--TARGETMMF=" + target,
+           "--STARTFRMEXT=%d" % cfg["ctx"], "--ENDFRMEXT=%d" % cfg["ctx"]]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("TNorm failed:\n" + res.stdout[-3000:])
+    tk = open(target).read().split()
+    assert tk[0] == "<bias>" and tk[3] == "v"
+    dim = int(tk[1])
+    bias = np.array(tk[5:5 + dim], dtype=np.float64)
+    w0 = 5 + dim
+    assert tk[w0] == "<window>" and tk[w0 + 3] == "v"
+    window = np.array(tk[w0 + 5:w0 + 5 + dim], dtype=np.float64)
+    m = re.search(r"frames: (\d+)", res.stdout)
+    frames = int(m.group(1)) if m else -1
+    if not save:
+        return bias, window, frames, res.stdout
+    names = list(utts.keys())
+    np.savez_compressed(os.path.join(OUT, "cpu_%s.npz" % case), feats=np.concatenate([utts[n][0] for n in names]),
+                        lengths=np.array([utts[n][0].shape[0] for n in names], dtype=np.int32), cfg=np.array([cfg["ctx"]], dtype=np.int64),
+                        ref_bias=bias, ref_window=window, ref_frames=np.int64(frames))
+    print("cpu %s: dim %d frames %d" % (case, dim, frames))
+
+
 def main():
     global OUT
     ap = argparse.ArgumentParser()
@@ -248,6 +281,9 @@ def main():
         with tempfile.TemporaryDirectory() as d:
             run_mlp(case, cfg, a.impl, d)
     if a.impl == "cpu":
+        for case, cfg in NORM_CASES.items():
+            with tempfile.TemporaryDirectory() as d:
+                run_norm(case, cfg, d)
         for case, cfg in FEACAT_CASES.items():
             with tempfile.TemporaryDirectory() as d:
                 run_feacat(case, cfg, d)

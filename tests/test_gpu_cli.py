@@ -1,4 +1,4 @@
-"""Drop-in binaries: nnet-asr_b200/bin/{TNetCu,TRbmCu,TRecurrentCu,TFeaCatCu} run with the reference's command lines on the
+"""Drop-in binaries: nnet-asr_b200/bin/{TNetCu,TRbmCu,TRecurrentCu,TFeaCatCu,TNormCu} run with the reference's command lines on the
 files the goldens were produced from, and must reproduce what the reference binaries wrote (network file, report line)."""
 import importlib.util
 import os
@@ -66,6 +66,17 @@ def test_tfeacatcu_binary_reproduces_reference(case):
         np.testing.assert_allclose(got, g["ref_out"], rtol=2e-5, atol=2e-5)
     else:
         np.testing.assert_allclose(got, g["ref_out"], rtol=2e-5, atol=1e-9)
+
+
+def test_tnormcu_binary_reproduces_reference():
+    """bin/TNormCu with the reference's command line == the <bias>/<window> transform the unmodified reference CPU tool TNorm
+    wrote for the same files (6 printed digits), same frame count quirk."""
+    g = np.load(os.path.join(GOLD, "cpu_norm_splice.npz"))
+    with tempfile.TemporaryDirectory() as d:
+        bias, window, frames, out = MG.run_norm("norm_splice", MG.NORM_CASES["norm_splice"], d, exe=os.path.join(BIN, "TNormCu"), save=False)
+    assert "===== TNormCu FINISHED" in out and frames == int(g["ref_frames"])
+    np.testing.assert_allclose(bias, g["ref_bias"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(window, g["ref_window"], rtol=2e-5)
 
 
 def test_cli_errors_like_the_reference():

@@ -64,3 +64,23 @@ def test_oracle_forward_vs_reference_cpu_tfeacat(case):
         np.testing.assert_allclose(got, g["ref_out"], rtol=2e-5, atol=2e-5)
     else:
         np.testing.assert_allclose(got, g["ref_out"], rtol=2e-5, atol=1e-9)
+
+
+def test_tnorm_restatement_vs_reference_cpu_tnorm():
+    """Pins the normalisation estimator's arithmetic (TNorm.cc / TNormCu.cc:268-328) against the unmodified reference CPU tool:
+    float products accumulated in double over the TRIMMED spliced frames, divided by a frame count that INCLUDES the replicated
+    extension rows (TNormCu.cc:292), bias = -mean, window = 1/sqrt(E[x^2] - mean^2)."""
+    from replay import utterances
+    g = np.load(os.path.join(GOLD, "cpu_norm_splice.npz"))
+    ctx = int(g["cfg"][0])
+    first = second = 0.0
+    frames = 0
+    for f, _ in utterances(g):
+        first = first + f.astype(np.float64).sum(0)
+        second = second + (f * f).astype(np.float64).sum(0)       # float product, double accumulation
+        frames += f.shape[0] + 2 * ctx
+    assert frames == int(g["ref_frames"])
+    mean = first / frames
+    var = second / frames - mean * mean
+    np.testing.assert_allclose(-mean, g["ref_bias"], rtol=1e-5, atol=1e-6)      # the tool prints 6 significant digits
+    np.testing.assert_allclose(1.0 / np.sqrt(var), g["ref_window"], rtol=1e-5)
