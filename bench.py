@@ -340,9 +340,10 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": gemm_tflops / pk["bf16_sustained"],
-                         # dram__bytes_read+write of ONE 1024x2048x2048 forward launch (ncu --set full, profiles/r01_gemm_pair_ncu.md);
-                         # algorithmic bytes of that launch: X 8.4 MB + W 16.8 MB read, Y 8.4 MB written (stays in L2)
-                         "traffic": 25.27e6,
+                         # dram__bytes_read+write of ONE 1024x2048x2048 forward launch (ncu --set full, profiles/r01_ncu_fwd.md and
+                         # r01_ncu_fwd_bf16.md); algorithmic bytes of that launch: X 8.4 MB + W 16.8 MB read in fp32 (half in bf16),
+                         # Y 8.4 MB written (stays in L2)
+                         "traffic": 12.63e6 if args.math == "bf16" else 25.22e6,
                          "kernel": "gemm_tcgen05_kernel (every GEMM launch of K steps, one CUDA event pair per launch)",
                          "gemm_ms_per_step": gms.value / args.steps, "gemm_launches": int(gl.value),
                          "issued_tflops": gemm_tflops * passes,

@@ -18,8 +18,9 @@
  * softmax + cross-entropy + frame accuracy) have fused entry points next to the 1:1 ones.
  *
  * All matrix pointers are DEVICE pointers to row-major fp32 with leading dimension `stride` (in elements).
- * For the tensor-core GEMMs `stride` must be a multiple of 4 and the base 16-byte aligned (tnb_malloc_pitch
- * guarantees a 128-byte pitch).  Nothing here falls back to the CPU: without a CUDA device every compute
+ * The tensor-core GEMMs need `stride` to be a multiple of 4 and every base 16-byte aligned (tnb_malloc_pitch
+ * guarantees a 128-byte pitch); GEMMs on views that are not (column blocks at odd offsets, CuMath::OffsetGemm) run on a
+ * plain fp32 FMA kernel on the GPU.  Nothing here falls back to the CPU: without a CUDA device every compute
  * entry point returns TNB_ERR_CUDA.
  */
 #ifndef TNET_B200_H_

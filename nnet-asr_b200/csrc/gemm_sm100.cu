@@ -108,6 +108,23 @@ int launch_gemm(TnbContext *ctx, char transa, char transb, int M, int N, int K, 
   const int ta = (transa == 'T' || transa == 't'), tb = (transb == 'T' || transb == 't');
   TNB_ARG(ta || transa == 'N' || transa == 'n', "transa");
   TNB_ARG(tb || transb == 'N' || transb == 'n', "transb");
+  const bool vec_ok = ((uintptr_t)ep.C % 16 == 0) && (ep.ldc % 4 == 0) && (!ep.bias || (uintptr_t)ep.bias % 16 == 0) &&
+                      (!ep.mulY || ((uintptr_t)ep.mulY % 16 == 0 && ep.ldy % 4 == 0)) &&
+                      (!ep.W || ((uintptr_t)ep.W % 16 == 0 && ep.ldw % 4 == 0));
+  const bool tma_ok = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && vec_ok;
+  if (ctx->math_mode == TNB_MATH_FP32_SIMT || !tma_ok) {
+    // Sub-matrix views at column offsets that are not multiples of 4 floats cannot be described to TMA (16-byte alignment):
+    // CuMath::OffsetGemm / <blocklinearity> slice a [T x 51*23] matrix into 51-column blocks (cumath.cc:88-113, example 01's
+    // Hamm_dct_norm).  Those GEMMs are tiny feature-transform work; they run on the plain fp32 FMA kernel in every math mode
+    // (exact fp32 products, i.e. at least as accurate as the tensor-core modes).
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    if (!ta && !tb) gemm_simt_kernel<0, 0><<<grid, 256, 0, ctx->stream>>>(A, lda, B, ldb, M, N, K, ep);
+    else if (!ta && tb) gemm_simt_kernel<0, 1><<<grid, 256, 0, ctx->stream>>>(A, lda, B, ldb, M, N, K, ep);
+    else if (ta && !tb) gemm_simt_kernel<1, 0><<<grid, 256, 0, ctx->stream>>>(A, lda, B, ldb, M, N, K, ep);
+    else gemm_simt_kernel<1, 1><<<grid, 256, 0, ctx->stream>>>(A, lda, B, ldb, M, N, K, ep);
+    TNB_LAUNCHED(ctx);
+    return TNB_OK;
+  }
   if (ctx->math_mode == TNB_MATH_BF16) {
     // fp32 operands in bf16 mode: round both to bf16 in ctx scratch, then the bf16 tensor-core path (the fused layer ops have
     // *_bf16 entry points that take resident bf16 twins instead)
@@ -118,23 +135,6 @@ int launch_gemm(TnbContext *ctx, char transa, char transb, int M, int N, int K, 
     rc = bf16_scratch(ctx, 1, B, tb ? N : K, tb ? K : N, ldb, &b16, &ldb16);
     if (rc != TNB_OK) return rc;
     return launch_gemm_bf16(ctx, transa, transb, M, N, K, a16, lda16, b16, ldb16, ep);
-  }
-  const bool vec_ok = ((uintptr_t)ep.C % 16 == 0) && (ep.ldc % 4 == 0) && (!ep.bias || (uintptr_t)ep.bias % 16 == 0) &&
-                      (!ep.mulY || ((uintptr_t)ep.mulY % 16 == 0 && ep.ldy % 4 == 0)) &&
-                      (!ep.W || ((uintptr_t)ep.W % 16 == 0 && ep.ldw % 4 == 0));
-  const bool tma_ok = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && vec_ok;
-  if (ctx->math_mode == TNB_MATH_FP32_SIMT || !tma_ok) {
-    if (ctx->math_mode != TNB_MATH_FP32_SIMT && !tma_ok) {
-      set_error("GEMM operands must be 16-byte aligned with a pitch multiple of 4 floats for the tensor-core path");
-      return TNB_ERR_ARG;
-    }
-    dim3 grid((N + 63) / 64, (M + 63) / 64);
-    if (!ta && !tb) gemm_simt_kernel<0, 0><<<grid, 256, 0, ctx->stream>>>(A, lda, B, ldb, M, N, K, ep);
-    else if (!ta && tb) gemm_simt_kernel<0, 1><<<grid, 256, 0, ctx->stream>>>(A, lda, B, ldb, M, N, K, ep);
-    else if (ta && !tb) gemm_simt_kernel<1, 0><<<grid, 256, 0, ctx->stream>>>(A, lda, B, ldb, M, N, K, ep);
-    else gemm_simt_kernel<1, 1><<<grid, 256, 0, ctx->stream>>>(A, lda, B, ldb, M, N, K, ep);
-    TNB_LAUNCHED(ctx);
-    return TNB_OK;
   }
   // operand majors: op(A)=A  -> A is [M x K], contraction contiguous -> K-major ; op(A)=A^T -> A is [K x M] -> MN-major
   //                 op(B)=B  -> B is [K x N], N contiguous -> MN-major         ; op(B)=B^T -> B is [N x K] -> K-major

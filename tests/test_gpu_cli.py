@@ -79,6 +79,37 @@ def test_tnormcu_binary_reproduces_reference():
     np.testing.assert_allclose(window, g["ref_window"], rtol=2e-5)
 
 
+def test_example01_real_data_dropin_matches_reference_trainers():
+    """BASELINE configs[0] on the reference's own example data (first 30 utterances of examples/01test...: real 23-dim features, the
+    real Hamm_dct_norm chain <expand 51><transpose><window><blocklinearity><bias><window>, MLF with 135 phone-state names, 598-1024-135,
+    bunch 960, the example's run_test.GPU.sh flags): bin/TNetCu == what the unmodified reference CPU trainer TNet produced
+    (tests/golden/make_example01.py), and == the unmodified reference TNetCu binary run here on the same files when it is present."""
+    spec1 = importlib.util.spec_from_file_location("make_example01", os.path.join(GOLD, "make_example01.py"))
+    EX = importlib.util.module_from_spec(spec1)
+    spec1.loader.exec_module(EX)
+    g = np.load(os.path.join(GOLD, "cpu_example01.npz"))
+    rep, layers, out = EX.run(os.path.join(BIN, "TNetCu"), g, gpu=True)
+    assert rep["frames"] == int(g["ref_frames"]) == 12480
+    assert abs(rep["err"] - float(g["ref_err"])) <= 1e-4 * abs(float(g["ref_err"]))
+    assert abs(rep["correct_pct"] - float(g["ref_correct_pct"])) <= 0.1
+    # final weights: 5e-4 of the layer's largest weight.  This run has no 1/N (GRADDIVFRM=F with bunch 960, lr 0.008 as in the
+    # example): one bunch moves the output weights by up to 0.1, so rounding differences between the CPU's BLAS and the tensor
+    # cores show up in the 4th digit of a handful of weights (3 of 138240 beyond 2e-4) while Xent and accuracy agree to 1e-4.
+    def close(a, b):
+        np.testing.assert_allclose(a, b, rtol=5e-4, atol=5e-4 * np.abs(b).max())
+    close(layers[0][1][::8], g["final_Wt0_rows8"])
+    close(layers[2][1], g["final_Wt1"])
+    close(layers[2][2], g["final_b1"])
+    ref_gpu = os.path.join(ROOT, "oracle", "_ref", "TNetCu")
+    if os.path.exists(ref_gpu):
+        rrep, rlayers, _ = EX.run(ref_gpu, g, gpu=True)
+        assert rrep["frames"] == rep["frames"]
+        assert abs(rep["err"] - rrep["err"]) <= 1e-4 * abs(rrep["err"])
+        assert abs(rep["correct_pct"] - rrep["correct_pct"]) <= 0.05
+        close(layers[0][1], rlayers[0][1])
+        close(layers[2][1], rlayers[2][1])
+
+
 def test_cli_errors_like_the_reference():
     import subprocess
     exe = os.path.join(BIN, "TNetCu")

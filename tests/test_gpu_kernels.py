@@ -86,6 +86,31 @@ def test_gemm_simt_vs_oracle(ctx, ta, tb, M, N, K):
     assert err.max() < 1e-6, err.max()
 
 
+def test_gemm_on_unaligned_column_blocks(ctx):
+    """CuMath::OffsetGemm / <blocklinearity> (cumath.cc:88-113): GEMMs on 51-column blocks of a wide matrix, i.e. operand and result
+    pointers that are not 16-byte aligned.  TMA cannot describe them; they run on the fp32 FMA kernel in every math mode."""
+    r = rng(17)
+    T, nb, k, m = 300, 23, 51, 26
+    X = r.standard_normal((T, nb * k)).astype(np.float32)
+    B = r.standard_normal((k, m)).astype(np.float32)
+    dX, dB, dY = abi.DMat.from_numpy(ctx, X), abi.DMat.from_numpy(ctx, B), abi.DMat(ctx, T, nb * m)
+    # blocks whose offsets happen to be 16-byte aligned (every 4th here) still take the tensor-core path of the mode
+    for math, tol in ((abi.MATH_3XTF32, 1e-5), (abi.MATH_BF16, 0.2), (abi.MATH_TF32, 0.03)):
+        ctx.set_math(math)
+        for i in range(nb):
+            pa = C.cast(C.c_void_p(dX.ptr.value + 4 * i * k), C.POINTER(C.c_float))
+            pc = C.cast(C.c_void_p(dY.ptr.value + 4 * i * m), C.POINTER(C.c_float))
+            abi.check(L.tnb_gemm(ctx.h, C.c_char(b"N"), C.c_char(b"N"), C.c_int(T), C.c_int(m), C.c_int(k), C.c_float(1.0), pa, C.c_int(dX.stride),
+                                 dB.p(), C.c_int(dB.stride), C.c_float(0.0), pc, C.c_int(dY.stride)))
+        ref = np.concatenate([X[:, i * k:(i + 1) * k].astype(np.float64) @ B.astype(np.float64) for i in range(nb)], axis=1)
+        got = dY.download()
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=tol)
+        una = [i for i in range(nb) if (4 * i * k) % 16 or (4 * i * m) % 16]      # fp32 FMA kernel in every mode
+        for i in una:
+            np.testing.assert_allclose(got[:, i * m:(i + 1) * m], ref[:, i * m:(i + 1) * m], rtol=1e-5, atol=1e-5)
+    ctx.set_math(abi.MATH_3XTF32)
+
+
 def test_gemm_alpha_beta(ctx):
     got, ref, scale = _gemm_case(ctx, "T", "N", 200, 300, 96, abi.MATH_3XTF32, alpha=-0.37, beta=0.9, seed=3)
     err = np.abs(got.astype(np.float64) - ref) / (scale + 1e-30)
