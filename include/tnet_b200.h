@@ -95,6 +95,14 @@ int tnb_memcpy2d(TnbContext *ctx, void *dst, size_t dpitch_bytes, const void *sr
                  size_t width_bytes, size_t height, int kind);
 int tnb_memcpy(TnbContext *ctx, void *dst, const void *src, size_t bytes, int kind);
 int tnb_host_alloc(void **ptr, size_t bytes); /* pinned host memory */
+/* ---- CUDA graphs: record a launch-bound sequence of calls once, replay it (TRecurrentCu: ~115 small kernels per frame).
+ * Between begin and end every call on the compute stream is captured instead of executed; do not allocate, synchronise or copy
+ * to/from pageable host memory there (run the sequence once eagerly first so that every buffer and scratch exists). */
+int tnb_graph_begin(TnbContext *ctx);
+int tnb_graph_end(TnbContext *ctx, void **graph);
+int tnb_graph_launch(TnbContext *ctx, void *graph);   /* counts the graph's kernels in tnb_ctx_launch_count */
+int tnb_graph_destroy(TnbContext *ctx, void *graph);
+
 /* ---- streams and events (the reference copies synchronously on the default stream: cumatrix.tcc:68-118).  A host that wants
  * its transfers to overlap the training step enqueues them on the context's copy stream and orders the two streams with
  * events; nothing below blocks the host except tnb_event_sync. */

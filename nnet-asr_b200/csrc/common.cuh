@@ -66,6 +66,8 @@ struct TnbContext_ {
   cudaStream_t aux2_stream = nullptr;  // (TNB_STREAM_AUX2)
   cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
   unsigned long long launches = 0;
+  bool capturing = false;                   // between tnb_graph_begin and tnb_graph_end
+  unsigned long long capture_base = 0;      // launch counter at tnb_graph_begin
   std::map<tnb::TmapKey, CUtensorMap> tmaps;  // TMA descriptors keyed by (ptr, dims, box)
   // scratch for deterministic per-row -> stats reductions
   float *row_scratch = nullptr;

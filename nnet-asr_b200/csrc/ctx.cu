@@ -337,6 +337,44 @@ int tnb_memcpy(TnbContext *ctx, void *dst, const void *src, size_t bytes, int ki
   if (kind == 1) TNB_CUDA(cudaStreamSynchronize(ctx->stream));
   return TNB_OK;
 }
+// ---- CUDA graphs: a launch-bound sequence of entry points (TRecurrentCu issues ~115 small kernels per frame) recorded once and
+// replayed.  Between begin and end every tnb_* call on the compute stream is captured instead of executed; calls that allocate,
+// synchronise or copy to/from pageable host memory must not be made there.  PDL attributes are left out of captured launches.
+struct TnbGraph { cudaGraphExec_t exec; unsigned long long kernels; };
+int tnb_graph_begin(TnbContext *ctx) {
+  TNB_ARG(ctx && !ctx->capturing, "null / already capturing");
+  TNB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  ctx->capturing = true;
+  ctx->capture_base = ctx->launches;
+  return TNB_OK;
+}
+int tnb_graph_end(TnbContext *ctx, void **graph) {
+  TNB_ARG(ctx && graph && ctx->capturing, "null / not capturing");
+  ctx->capturing = false;
+  cudaGraph_t g = nullptr;
+  TNB_CUDA(cudaStreamEndCapture(ctx->stream, &g));
+  TnbGraph *t = new TnbGraph();
+  t->kernels = ctx->launches - ctx->capture_base;
+  ctx->launches = ctx->capture_base;  // nothing has run yet
+  cudaError_t e = cudaGraphInstantiate(&t->exec, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) { delete t; set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return TNB_ERR_CUDA; }
+  *graph = t;
+  return TNB_OK;
+}
+int tnb_graph_launch(TnbContext *ctx, void *graph) {
+  TNB_ARG(ctx && graph && !ctx->capturing, "null / capturing");
+  TnbGraph *t = (TnbGraph *)graph;
+  TNB_CUDA(cudaGraphLaunch(t->exec, ctx->stream));
+  ctx->launches += t->kernels;
+  return TNB_OK;
+}
+int tnb_graph_destroy(TnbContext *ctx, void *graph) {
+  TNB_ARG(ctx, "null");
+  if (graph) { TnbGraph *t = (TnbGraph *)graph; cudaGraphExecDestroy(t->exec); delete t; }
+  return TNB_OK;
+}
+
 // ---- streams and events: what a host needs to overlap its transfers with the training step ----
 int tnb_memcpy2d_on(TnbContext *ctx, int stream_id, void *dst, size_t dp, const void *src, size_t sp, size_t w, size_t h, int kind) {
   TNB_ARG(ctx && dst && src, "null");

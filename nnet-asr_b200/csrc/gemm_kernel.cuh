@@ -672,7 +672,7 @@ static int launch_tc(TnbContext *ctx, const CUtensorMap &tmA, const CUtensorMap 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (ctx->pdl && !ctx->profiling) {
+  if (ctx->pdl && !ctx->profiling && !ctx->capturing) {
     // programmatic dependent launch: this grid may be scheduled while the previous kernel of the stream is still running; the
     // kernel orders itself behind it with griddepcontrol.wait before its first global access
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;

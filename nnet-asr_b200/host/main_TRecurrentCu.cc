@@ -57,6 +57,7 @@ int main(int argc, char *argv[]) try {
   int gpu_select = ui.GetInt(SNAME ":GPUSELECT", -1);
   if (gpu_select >= 0) CuDevice::Instantiate().SelectGPU(gpu_select);
   SelectMath(ui, SNAME);
+  bool use_graph = ui.GetBool(SNAME ":GRAPH", true);  // replay the per-frame launch sequence as a CUDA graph
   if (ui.GetBool(SNAME ":PRINTCONFIG", false)) { std::cout << std::endl; ui.PrintConfig(std::cout); std::cout << std::endl; }
   if (ui.GetBool(SNAME ":PRINTVERSION", false)) std::cout << std::endl << "======= TRecurrentCu (B200) =======" << std::endl << std::endl;
   ui.CheckCommandLineParamUse();
@@ -82,7 +83,8 @@ int main(int argc, char *argv[]) try {
 
   timer.Start();
   std::cout << (cross_validate ? "===== TRecurrentCu CROSSVAL STARTED =====" : "===== TRecurrentCu TRAINING STARTED =====") << std::endl;
-  int frames = 0;
+  int frames = 0, eager_frames = 0;
+  void *graph = NULL;
   CuMatrix<BaseFloat> feats, targets, feats_original, feats_expanded;
   CuMatrix<BaseFloat> input_row, output_row, target_row, error_row;
   CuVector<int> label_ids;
@@ -105,9 +107,24 @@ int main(int argc, char *argv[]) try {
     for (size_t frm = 0; frm < feats.Rows(); frm++) {
       input_row.CopyRows(1, frm, feats, 0);
       target_row.CopyRows(1, frm, targets, 0);
-      network.Propagate(input_row, output_row);
-      p_obj_function->Evaluate(output_row, target_row, error_row);
-      if (!cross_validate) network.Backpropagate(error_row);
+      // One frame = ~115 small dependent launches on fixed buffers (forward GEMV, objective, BPTT chain of GEMV + rank-1 updates,
+      // weight update): after two eager frames have created every buffer, scratch and TMA descriptor, the sequence is recorded
+      // into a CUDA graph once and replayed for every further frame of the run (--GRAPH=FALSE keeps the eager schedule).
+      if (graph) {
+        TNB_CHECK(tnb_graph_launch(Cx(), graph));
+      } else if (use_graph && eager_frames >= 2) {
+        TNB_CHECK(tnb_graph_begin(Cx()));
+        network.Propagate(input_row, output_row);
+        p_obj_function->Evaluate(output_row, target_row, error_row);
+        if (!cross_validate) network.Backpropagate(error_row);
+        TNB_CHECK(tnb_graph_end(Cx(), &graph));
+        TNB_CHECK(tnb_graph_launch(Cx(), graph));
+      } else {
+        network.Propagate(input_row, output_row);
+        p_obj_function->Evaluate(output_row, target_row, error_row);
+        if (!cross_validate) network.Backpropagate(error_row);
+        eager_frames++;
+      }
     }
     frames += (int)feats.Rows();
     std::cout << "." << std::flush;
@@ -118,6 +135,7 @@ int main(int argc, char *argv[]) try {
     else Error("forgot to specify --TARGETMMF argument");
   }
   CuDevice::Instantiate().Sync();
+  if (graph) tnb_graph_destroy(Cx(), graph);
   timer.End();
   std::cout << std::endl;
   std::cout << "===== TRecurrentCu FINISHED ( " << timer.Val() << "s ) " << "[FPS:" << float(frames) / timer.Val() << ",RT:"
