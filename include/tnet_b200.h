@@ -172,6 +172,16 @@ int tnb_offset_gemv(TnbContext *ctx, char trans, float alpha, const float *A, Tn
 /* A += alpha * x * y^T  — CuMath::BlasGer / CuMatrix::BlasGer (cumath.cc:344-362) */
 int tnb_ger(TnbContext *ctx, float alpha, const float *x, int dimX, const float *y, int dimY, float *A, TnbMatrixDim dA);
 
+/* CuRecurrent::Update fused (cuRecurrent.cc:92-153; W is [(nin + H) x H], the last H rows are the recurrent weights):
+ * tnb_rnn_bptt_step: one step of the BPTT chain — d_out = diffsigmoid(W[nin.., :] * d_prev, y_hist) and bcorr += -lr * d_out — in one
+ *   launch (the reference: OffsetGemv + DiffSigmoid + BlasGer + AddColSum per step);
+ * tnb_rnn_apply: W += sum_i (-lr * hist[i]) (x) d[i] + (-lr*wc) * W over the stored steps i = 0..nsteps-1, summed in the reference's
+ *   order, in one pass over W (the reference: SetConst + nsteps BlasGer + 2 AddScaled). */
+int tnb_rnn_bptt_step(TnbContext *ctx, const float *W, TnbMatrixDim dW, int nin, const float *d_prev, const float *y_hist, float *d_out,
+                      float *bcorr, float lr);
+int tnb_rnn_apply(TnbContext *ctx, float *W, TnbMatrixDim dW, const float *hist, int ld_hist, const float *d, int ld_d, int nsteps, float lr,
+                  float wc);
+
 /* ---- fused hot-path ops ----------------------------------------------------------------------------- */
 enum { TNB_ACT_NONE = 0, TNB_ACT_SIGMOID = 1 };
 /* CuBiasedLinearity::PropagateFnc (+ CuSigmoid::PropagateFnc when act = SIGMOID):

@@ -308,11 +308,79 @@ __global__ void ger_kernel(float alpha, const float *__restrict__ x, int dimX, c
   if (c < dimY && r < dimX) A[(size_t)r * lda + c] += (alpha * x[r]) * y[c];
 }
 
+// ---- CuRecurrent::Update, fused (cuRecurrent.cc:92-153) --------------------------------------------------------------------
+// One step of the BPTT chain in ONE launch instead of five (gemv, diff-sigmoid, rank-1 update, two column-sum kernels):
+//   e[r]    = sum_c W[nin + r, c] * d_prev[c]                    (OffsetGemv 'N' on the recurrent rows, warp per row as gemv_n_kernel)
+//   d[r]    = (float)(y[r] * (1 - y[r]) * e[r])  in double        (DiffSigmoid with the history frame's activations)
+//   bcorr[r] = (float)(-lr * d[r] + bcorr[r])    in double        (AddColSum(-lr, d, 1.0) of a one-row matrix)
+// The rank-1 updates of all steps are applied together by rnn_apply_kernel from the stored d vectors.
+__global__ void __launch_bounds__(256) rnn_bptt_step_kernel(const float *__restrict__ W, int ldw, int nin, int H, const float *__restrict__ d_prev,
+                                                            const float *__restrict__ y, float *__restrict__ d_out, float *__restrict__ bcorr,
+                                                            float neg_lr) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= H) return;
+  const float *a = W + (size_t)(nin + r) * ldw;
+  float s = 0.0f;
+  for (int c = lane; c < H; c += 32) s = fmaf(a[c], d_prev[c], s);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    const double yy = (double)y[r];
+    const float d = (float)(yy * (1.0 - yy) * (double)s);
+    d_out[r] = d;
+    bcorr[r] = (float)((double)neg_lr * (double)d + (double)bcorr[r]);
+  }
+}
+// W[k,h] += sum_i (-lr * hist[i][k]) * d[i][h] + (-lr*wc) * W[k,h], the sum in the order of the reference's sequence of rank-1
+// updates into a zeroed correction matrix (i = 0 .. nsteps-1), then corr += l2*W, then W += corr: one pass over W instead of
+// nsteps + 3 (BlasGer x nsteps, SetConst, AddScaled x 2).
+__global__ void __launch_bounds__(256) rnn_apply_kernel(float *__restrict__ W, int ldw, int K, int H, const float *__restrict__ hist, int ldh,
+                                                        const float *__restrict__ d, int ldd, int nsteps, float neg_lr, float l2) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int k = blockIdx.y;
+  if (c >= H || k >= K) return;
+  float corr[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  for (int i = 0; i < nsteps; i++) {
+    const float t = neg_lr * hist[(size_t)i * ldh + k];
+    const float *di = d + (size_t)i * ldd + c;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (c + j < H) corr[j] = fmaf(t, di[j], corr[j]);
+  }
+  float *w = W + (size_t)k * ldw + c;
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+    if (c + j < H) {
+      const float cj = fmaf(l2, w[j], corr[j]);  // corr = l2*W + 1*corr
+      w[j] = cj + w[j];                          // W = 1*corr + 1*W
+    }
+}
+
 }  // namespace tnb
 
 using namespace tnb;
 
 extern "C" {
+
+int tnb_rnn_bptt_step(TnbContext *ctx, const float *W, TnbMatrixDim dW, int nin, const float *d_prev, const float *y_hist, float *d_out,
+                      float *bcorr, float lr) {
+  TNB_ARG(ctx && W && d_prev && y_hist && d_out && bcorr, "null");
+  const int H = dW.cols;
+  TNB_ARG(nin >= 0 && dW.rows == nin + H && dW.stride >= H, "W must be [(nin + H) x H]");
+  rnn_bptt_step_kernel<<<(H + 7) / 8, 256, 0, ctx->stream>>>(W, dW.stride, nin, H, d_prev, y_hist, d_out, bcorr, -lr);
+  TNB_LAUNCHED(ctx);
+  return TNB_OK;
+}
+
+int tnb_rnn_apply(TnbContext *ctx, float *W, TnbMatrixDim dW, const float *hist, int ld_hist, const float *d, int ld_d, int nsteps, float lr,
+                  float wc) {
+  TNB_ARG(ctx && W && hist && d, "null");
+  TNB_ARG(nsteps >= 1 && dW.rows > 0 && dW.cols > 0 && ld_hist >= dW.rows && ld_d >= dW.cols, "dims");
+  dim3 grid(((dW.cols + 3) / 4 + 255) / 256, dW.rows);
+  rnn_apply_kernel<<<grid, 256, 0, ctx->stream>>>(W, dW.stride, dW.rows, dW.cols, hist, ld_hist, d, ld_d, nsteps, -lr, -lr * wc);
+  TNB_LAUNCHED(ctx);
+  return TNB_OK;
+}
 
 int tnb_gemm(TnbContext *ctx, char transa, char transb, int m, int n, int k, float alpha, const float *A, int lda,
              const float *B, int ldb, float beta, float *C, int ldc) {

@@ -583,6 +583,7 @@ class CuRecurrent : public CuUpdatableComponent {
     mInputHistory.Init(ord + 1, GetNInputs() + GetNOutputs());
     mHistTmp.Init(ord + 1, GetNInputs() + GetNOutputs());
     mDiffSigm.Init(1, GetNOutputs()); mErrPrev.Init(1, GetNOutputs());
+    mDiffs.Init(ord + 1, GetNOutputs());
   }
   void ClearHistory() {
     mInputHistory.SetConst(0.0);
@@ -608,22 +609,19 @@ class CuRecurrent : public CuUpdatableComponent {
     // accumulates into Y with beta = 1 as the reference does (cuRecurrent.cc:81)
     CuMath<BaseFloat>::OffsetGemv('N', 1.0, mLinearity, mDiffSigm.pCUData(), mDiffSigm.Cols(), 1.0, Y.pCUData(), Y.Cols(), 0);
   }
+  /// cuRecurrent.cc:92-153.  Same arithmetic per element as the reference's sequence of calls; the BPTT chain runs one fused
+  /// launch per step (tnb_rnn_bptt_step) and the rank-1 updates of all steps are applied in one pass over W (tnb_rnn_apply).
   void Update() {
-    const size_t K = mInputHistory.Cols(), H = GetNOutputs();
-    CuMath<BaseFloat>::DiffSigmoid(mDiffSigm, GetErrorInput(), GetOutput());
-    mLinearityCorrection.SetConst(0.0);
-    CuMath<BaseFloat>::BlasGer(-mLearningRate, mInputHistory.pCURowData(0), K, mDiffSigm.pCUData(), H, mLinearityCorrection);
-    mBiasCorrection.AddColSum(-mLearningRate, mDiffSigm, mMomentum);
-    TnbMatrixDim drow = {1, (int)H, (int)mInputHistory.Stride()};
-    for (int i = 1; i <= mBpttOrder; i++) {
-      CuMath<BaseFloat>::OffsetGemv('N', 1.0, mLinearity, mDiffSigm.pCUData(), H, 0.0, mErrPrev.pCUData(), H, GetInput().Cols());
-      // diff-sigmoid with the activations of the history frame (they sit in row i-1, columns nInputs..)
-      TNB_CHECK(tnb_diff_sigmoid(Cx(), mDiffSigm.pCUData(), mErrPrev.pCUData(), mInputHistory.pCURowData(i - 1) + GetInput().Cols(), drow));
-      CuMath<BaseFloat>::BlasGer(-mLearningRate, mInputHistory.pCURowData(i), K, mDiffSigm.pCUData(), H, mLinearityCorrection);
-      mBiasCorrection.AddColSum(-mLearningRate, mDiffSigm, 1.0);
-    }
-    mLinearityCorrection.AddScaled(-mLearningRate * mWeightcost, mLinearity, 1.0);
-    mLinearity.AddScaled(1.0, mLinearityCorrection, 1.0);
+    const size_t H = GetNOutputs(), nin = GetInput().Cols();
+    // step 0: d_0 = diffsigmoid(error, output) ; bcorr = -lr*d_0 + mmt*bcorr
+    TnbMatrixDim drow = {1, (int)H, (int)mDiffs.Stride()};
+    TNB_CHECK(tnb_diff_sigmoid(Cx(), mDiffs.pCUData(), GetErrorInput().pCUData(), GetOutput().pCUData(), drow));
+    TNB_CHECK(tnb_add_col_sum(Cx(), -mLearningRate, mDiffs.pCUData(), mMomentum, mBiasCorrection.pCUData(), drow));
+    for (int i = 1; i <= mBpttOrder; i++)   // d_i from d_{i-1} and the activations of history frame i-1 (columns nin.. of its row)
+      TNB_CHECK(tnb_rnn_bptt_step(Cx(), mLinearity.pCUData(), mLinearity.Dim(), (int)nin, mDiffs.pCURowData(i - 1),
+                                  mInputHistory.pCURowData(i - 1) + nin, mDiffs.pCURowData(i), mBiasCorrection.pCUData(), mLearningRate));
+    TNB_CHECK(tnb_rnn_apply(Cx(), mLinearity.pCUData(), mLinearity.Dim(), mInputHistory.pCUData(), (int)mInputHistory.Stride(), mDiffs.pCUData(),
+                            (int)mDiffs.Stride(), mBpttOrder + 1, mLearningRate, mWeightcost));
     mBias.AddScaled(1.0, mBiasCorrection, 1.0);
   }
   void ReadFromStream(std::istream &rIn) {
@@ -650,6 +648,7 @@ class CuRecurrent : public CuUpdatableComponent {
   CuMatrix<BaseFloat> mLinearityCorrection;
   CuVector<BaseFloat> mBiasCorrection;
   CuMatrix<BaseFloat> mInputHistory, mHistTmp, mDiffSigm, mErrPrev;
+  CuMatrix<BaseFloat> mDiffs;  ///< [(bptt + 1) x nOutputs]: the back-propagated error of every BPTT step of the current frame
   int mBpttOrder;
 };
 
