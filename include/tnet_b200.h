@@ -70,6 +70,9 @@ int tnb_ctx_device(TnbContext *ctx, int *device);
 int tnb_ctx_set_math(TnbContext *ctx, int math_mode);
 int tnb_ctx_get_math(TnbContext *ctx, int *math_mode);
 int tnb_ctx_stream(TnbContext *ctx, void **cuda_stream); /* the cudaStream_t every op is enqueued on */
+/* make the entry points that take no stream argument enqueue on another stream of the context (TNB_STREAM_COMPUTE restores the
+ * default).  The host mirror uses it to run a layer's weight-gradient GEMM next to the dX chain of the layers below. */
+int tnb_ctx_use_stream(TnbContext *ctx, int stream_id);
 int tnb_ctx_sync(TnbContext *ctx);                      /* reference semantics: cudaThreadSynchronize() */
 int tnb_ctx_free_memory(TnbContext *ctx, size_t *free_bytes, size_t *total_bytes); /* cudevice.cc:100-118 */
 /* number of kernels of THIS library launched through ctx since creation (graph replays included) */

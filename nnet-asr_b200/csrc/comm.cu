@@ -118,7 +118,7 @@ int tnb_allreduce_sum_ev(TnbContext *ctx, float *buf, size_t count, void *event,
   TNB_ARG(ctx && buf, "null");
   if (count == 0) return TNB_OK;
   // comm stream waits for everything enqueued so far on the compute stream (the producer of buf) and for `event`
-  TNB_CUDA(cudaEventRecord(ctx->ev_compute, ctx->stream));
+  TNB_CUDA(cudaEventRecord(ctx->ev_compute, ctx->main_stream));
   TNB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_compute, 0));
   if (event) TNB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, (cudaEvent_t)event, 0));
   static int skip = -1;  // TNB_DP_SKIP_COMM=1: timing experiment only (the data-parallel step without its collectives; results are wrong)
@@ -146,10 +146,10 @@ int tnb_dp_update(TnbContext *ctx, float *G, float *W, float *corrW, TnbMatrixDi
   TNB_ARG(rows_pad >= dW.rows && rows_pad % world == 0, "rows_pad must be a multiple of the world size, at least dW.rows");
   float scale, l2;
   update_scalars(lr, mmt, wc, gdf, n_frames_global, &scale, &l2);
-  cudaStream_t cs = world > 1 ? ctx->comm_stream : ctx->stream;
+  cudaStream_t cs = world > 1 ? ctx->comm_stream : ctx->main_stream;
   if (world > 1) {
     TNB_ARG(ctx->nccl_comm != nullptr, "communicator not initialised");
-    TNB_CUDA(cudaEventRecord(ctx->ev_compute, ctx->stream));  // the gradient GEMM (and everything before it) is the producer
+    TNB_CUDA(cudaEventRecord(ctx->ev_compute, ctx->main_stream));  // the gradient GEMM (and everything before it) is the producer
     TNB_CUDA(cudaStreamWaitEvent(cs, ctx->ev_compute, 0));
   }
   const int shard = rows_pad / world;
@@ -175,7 +175,7 @@ int tnb_comm_wait(TnbContext *ctx) {
   TNB_ARG(ctx, "null");
   if (ctx->world == 1) return TNB_OK;
   TNB_CUDA(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
-  TNB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+  TNB_CUDA(cudaStreamWaitEvent(ctx->main_stream, ctx->ev_comm, 0));
   return TNB_OK;
 }
 

@@ -59,7 +59,8 @@ struct TnbContext_ {
   int device = 0;
   int sm_count = 148;
   int math_mode = TNB_MATH_3XTF32;
-  cudaStream_t stream = nullptr;       // compute stream
+  cudaStream_t stream = nullptr;       // the stream entry points without a stream argument enqueue on (tnb_ctx_use_stream; default: main_stream)
+  cudaStream_t main_stream = nullptr;  // TNB_STREAM_COMPUTE
   cudaStream_t comm_stream = nullptr;  // NCCL stream
   cudaStream_t copy_stream = nullptr;  // host<->device transfers that overlap compute (TNB_STREAM_COPY)
   cudaStream_t aux_stream = nullptr;   // small kernels next to the compute stream's GEMMs (TNB_STREAM_AUX)

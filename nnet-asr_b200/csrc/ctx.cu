@@ -42,7 +42,7 @@ int ensure_vec_scratch_side(TnbContext *ctx, int n) {
 
 cudaStream_t stream_of(TnbContext *ctx, int id) {
   switch (id) {
-    case TNB_STREAM_COMPUTE: return ctx->stream;
+    case TNB_STREAM_COMPUTE: return ctx->main_stream;
     case TNB_STREAM_COPY: return ctx->copy_stream;
     case TNB_STREAM_COMM: return ctx->comm_stream;
     case TNB_STREAM_AUX: return ctx->aux_stream;
@@ -182,7 +182,8 @@ int tnb_ctx_create(TnbContext **out, int device) {
   { const char *e = getenv("TNB_PDL"); if (e && atoi(e) == 0) ctx->pdl = false; }
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  TNB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  TNB_CUDA(cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->main_stream;
   {
     // TNB_COMM_PRIORITY=1: collectives on the highest-priority stream (their few CTAs are placed before a waiting GEMM wave)
     const char *e = getenv("TNB_COMM_PRIORITY");
@@ -203,7 +204,7 @@ int tnb_ctx_destroy(TnbContext *ctx) {
   if (!ctx) return TNB_OK;
   cudaSetDevice(ctx->device);
   tnb_comm_destroy(ctx);
-  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->main_stream);
   if (ctx->row_scratch) cudaFree(ctx->row_scratch);
   if (ctx->row_match) cudaFree(ctx->row_match);
   if (ctx->vec_scratch) cudaFree(ctx->vec_scratch);
@@ -211,7 +212,7 @@ int tnb_ctx_destroy(TnbContext *ctx) {
   for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_compute);
   cudaEventDestroy(ctx->ev_comm);
-  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->main_stream);
   cudaStreamDestroy(ctx->comm_stream);
   cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->aux_stream);
@@ -229,10 +230,17 @@ int tnb_ctx_set_math(TnbContext *ctx, int m) {
   return TNB_OK;
 }
 int tnb_ctx_get_math(TnbContext *ctx, int *m) { TNB_ARG(ctx && m, "null"); *m = ctx->math_mode; return TNB_OK; }
-int tnb_ctx_stream(TnbContext *ctx, void **s) { TNB_ARG(ctx && s, "null"); *s = (void *)ctx->stream; return TNB_OK; }
+int tnb_ctx_stream(TnbContext *ctx, void **s) { TNB_ARG(ctx && s, "null"); *s = (void *)ctx->main_stream; return TNB_OK; }
+int tnb_ctx_use_stream(TnbContext *ctx, int stream_id) {
+  TNB_ARG(ctx && !ctx->capturing, "null / capturing");
+  cudaStream_t st = stream_of(ctx, stream_id);
+  TNB_ARG(st != nullptr && stream_id != TNB_STREAM_COMM, "stream");
+  ctx->stream = st;
+  return TNB_OK;
+}
 int tnb_ctx_sync(TnbContext *ctx) {
   TNB_ARG(ctx, "null");
-  TNB_CUDA(cudaStreamSynchronize(ctx->stream));
+  TNB_CUDA(cudaStreamSynchronize(ctx->main_stream));
   TNB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
   TNB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
   TNB_CUDA(cudaStreamSynchronize(ctx->aux_stream));

@@ -286,6 +286,14 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_COMPUTE, mEvDone));
     mDpPending = false;
   }
+  /// events for running this layer's update GEMM on a side stream (created on first use)
+  void SideStreamEvents(void **pDx, void **pUpd) {
+    if (!mEvE) {
+      TNB_CHECK(tnb_event_create(Cx(), &mEvE)); TNB_CHECK(tnb_event_create(Cx(), &mEvB));
+      TNB_CHECK(tnb_event_create(Cx(), &mEvAR)); TNB_CHECK(tnb_event_create(Cx(), &mEvDone));
+    }
+    *pDx = mEvE; *pUpd = mEvDone;
+  }
   float *GradBuffer() { return mGrad.pCUData(); }
   size_t GradCount() const { return mGrad.Rows() * mGrad.Stride(); }
   void ApplyGradient(int n_frames_global) {
@@ -753,12 +761,12 @@ inline CuObjectiveFunction *CuObjectiveFunction::Factory(ObjFunType type) {
 class CuNetwork {
   typedef std::vector<CuComponent *> LayeredType;
  public:
-  CuNetwork() : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false) {
+  CuNetwork() : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mBwdStreams(BwdStreamsDefault()), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false) {
     const char *e = getenv("TNB_FUSE");
     if (e && atoi(e) == 0) mFuse = false;
   }
   explicit CuNetwork(std::istream &rIn)
-      : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false) {
+      : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mBwdStreams(BwdStreamsDefault()), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false) {
     ReadNetwork(rIn);
   }
   ~CuNetwork() {
@@ -776,6 +784,7 @@ class CuNetwork {
   int Layers() { return (int)mNetComponents.size(); }
   CuComponent &Layer(int i) { return *mNetComponents[i]; }
 
+  static int BwdStreamsDefault() { const char *e = getenv("TNB_BWD_STREAMS"); return e ? atoi(e) : 1; }
   void SetFusion(bool on) { mFuse = on; }
   /// order the compute stream behind every outstanding data-parallel update (stream order only; callers that time or end a
   /// run of bunches use it so that the last bunch's exchange is inside what they measure)
@@ -830,6 +839,7 @@ class CuNetwork {
     mNetComponents.back()->SetErrorInput(globerr);
     std::vector<CuBiasedLinearity *> pending;  // data parallel: layers whose gradient is in flight
     std::vector<CuBiasedLinearity *> deferred; // data parallel, all-reduce schedule: layers whose exchange is issued after the lowest layer's
+    std::vector<void *> side_done;             // fused schedule on two streams: one event per layer, behind its update GEMM
     std::vector<TnbBiasJob> bias_jobs;         // fused schedule: bias halves of the updates, applied together after the last layer
     for (int i = n - 1; i >= 0; i--) {
       CuComponent *c = mNetComponents[i];
@@ -877,7 +887,22 @@ class CuNetwork {
             pending.push_back(lin);
           } else if (mFuse && c->GetType() == CuComponent::BIASED_LINEARITY) {
             bias_jobs.push_back(TnbBiasJob());
-            static_cast<CuBiasedLinearity *>(c)->Update(&bias_jobs.back());
+            CuBiasedLinearity *lin = static_cast<CuBiasedLinearity *>(c);
+            if (mBwdStreams == 2) {
+              // the weight-gradient GEMM (+ fused update) of this layer only needs E and X, which exist: it runs on a side stream next
+              // to the dX GEMMs of the layers below (their CTAs fill the SMs the other kernel leaves free or has finished with)
+              void *ev_dx = NULL, *ev_upd = NULL;
+              lin->SideStreamEvents(&ev_dx, &ev_upd);
+              TNB_CHECK(tnb_event_record(Cx(), ev_dx, TNB_STREAM_COMPUTE));   // dX of this layer has read W; E of this layer exists
+              TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_AUX, ev_dx));
+              TNB_CHECK(tnb_ctx_use_stream(Cx(), TNB_STREAM_AUX));
+              lin->Update(&bias_jobs.back());
+              TNB_CHECK(tnb_ctx_use_stream(Cx(), TNB_STREAM_COMPUTE));
+              TNB_CHECK(tnb_event_record(Cx(), ev_upd, TNB_STREAM_AUX));
+              side_done.push_back(ev_upd);
+            } else {
+              lin->Update(&bias_jobs.back());
+            }
           } else {
             rComp.Update();
           }
@@ -885,6 +910,7 @@ class CuNetwork {
       }
       if (mpPropagErrorStopper == c) break;
     }
+    for (size_t k = 0; k < side_done.size(); k++) TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_COMPUTE, side_done[k]));
     for (size_t k = 0; k < bias_jobs.size(); k += TNB_MAX_BIAS_JOBS)
       TNB_CHECK(tnb_bias_update_batch(Cx(), &bias_jobs[k], (int)std::min<size_t>(TNB_MAX_BIAS_JOBS, bias_jobs.size() - k)));
     for (size_t k = deferred.size(); k-- > 0;)  // bottom-most deferred layer first: the order the next forward pass needs them
@@ -1003,6 +1029,7 @@ class CuNetwork {
   const char *mpTempBasisDir;
   bool mFuse;
   int mWorld;
+  int mBwdStreams;                 ///< fused single-GPU schedule: 2 = weight-gradient GEMMs on a side stream (TNB_BWD_STREAMS)
   int mDpDeferBegin, mDpDeferEnd;  ///< all-reduce schedule: updatable layers [begin, end), counted from the top, exchange late
   bool mDpShard;  ///< data-parallel schedule: false = all-reduce + batched update (default), true = tnb_dp_update (TNB_DP_MODE=shard)
 };
