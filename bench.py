@@ -354,7 +354,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                fps, threads, sample = cpu_reference_throughput(2, 6)
+                fps, threads, sample = cpu_reference_throughput(2, 10)
                 line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "reference", "sample": sample}
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % str(e)[:200]}
