@@ -293,6 +293,8 @@ int tnb_allreduce_sum(TnbContext *ctx, float *buf, size_t count);
 /* the same, additionally ordered behind `event` (e.g. a bias gradient computed on a side stream into the same buffer); `done`, if
  * not NULL, is recorded on the communication stream behind the all-reduce (a side stream can then apply the update) */
 int tnb_allreduce_sum_ev(TnbContext *ctx, float *buf, size_t count, void *event, void *done);
+/* n buffers in one NCCL launch (ncclGroupStart/End): ordered behind the compute stream and the given events, `done` recorded behind it */
+int tnb_allreduce_sum_multi(TnbContext *ctx, float *const *bufs, const size_t *counts, int n, void *const *events, int n_events, void *done);
 /* One layer's data-parallel update, enqueued on the communication stream behind everything already on the compute stream:
  * reduce-scatter G over the ranks (rank r receives the sum of rows [r*rows_pad/world, (r+1)*rows_pad/world)), apply
  * CuBiasedLinearity::Update to those rows of W/corrW, all-gather the updated rows of W; the bias gradient gb[ncols] is all-reduced

@@ -280,6 +280,12 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     TNB_CHECK(tnb_event_record(Cx(), mEvDone, TNB_STREAM_AUX2));
     mDpPending = true;
   }
+  /// pieces of the second half for a GROUP of layers exchanged in one NCCL launch (CuNetwork's deferred layers)
+  void *BiasGradientEvent() { return mEvB; }
+  void MarkDataParallelUpdateEnqueued() {  // the group's batched update has just been enqueued on the update stream
+    TNB_CHECK(tnb_event_record(Cx(), mEvDone, TNB_STREAM_AUX2));
+    mDpPending = true;
+  }
   /// order the compute stream behind this layer's outstanding data-parallel update (no host synchronisation)
   void WaitDataParallel() const {
     if (!mDpPending) return;
@@ -761,15 +767,16 @@ inline CuObjectiveFunction *CuObjectiveFunction::Factory(ObjFunType type) {
 class CuNetwork {
   typedef std::vector<CuComponent *> LayeredType;
  public:
-  CuNetwork() : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mBwdStreams(BwdStreamsDefault()), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false) {
+  CuNetwork() : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mEvGroup(NULL), mDpGroup(false), mBwdStreams(BwdStreamsDefault()), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false) {
     const char *e = getenv("TNB_FUSE");
     if (e && atoi(e) == 0) mFuse = false;
   }
   explicit CuNetwork(std::istream &rIn)
-      : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mBwdStreams(BwdStreamsDefault()), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false) {
+      : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mEvGroup(NULL), mDpGroup(false), mBwdStreams(BwdStreamsDefault()), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false) {
     ReadNetwork(rIn);
   }
   ~CuNetwork() {
+    if (mEvGroup) tnb_event_destroy(Cx(), mEvGroup);
     for (LayeredType::iterator it = mNetComponents.begin(); it != mNetComponents.end(); ++it) delete *it;
     mNetComponents.clear();
   }
@@ -804,6 +811,12 @@ class CuNetwork {
     for (size_t i = 0; i < mNetComponents.size(); i++) nupd += mNetComponents[i]->GetType() == CuComponent::BIASED_LINEARITY;
     mDpDeferBegin = mDpDeferEnd = 0;
     if (nupd >= 6) { mDpDeferBegin = 1; mDpDeferEnd = nupd - 2; }
+    // one NCCL launch for the deferred layers pays a call's fixed latency once (8 ranks: ~50 us of a 16.8 MB layer's 101 us) but
+    // holds their updates until the whole group is through.  Measured slower on both 2 ranks (1.340 vs 1.237 ms per bunch) and
+    // 8 ranks (1.560 vs 1.496 ms): off unless TNB_DP_GROUP=1
+    mDpGroup = false;
+    const char *gr = getenv("TNB_DP_GROUP");
+    if (gr) mDpGroup = atoi(gr) != 0;
     const char *d = getenv("TNB_DP_DEFER");
     if (d) { int a = 0, b = 0; if (sscanf(d, "%d:%d", &a, &b) == 2) { mDpDeferBegin = a; mDpDeferEnd = b; } }
     for (size_t i = 0; i < mNetComponents.size(); i++)
@@ -913,8 +926,29 @@ class CuNetwork {
     for (size_t k = 0; k < side_done.size(); k++) TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_COMPUTE, side_done[k]));
     for (size_t k = 0; k < bias_jobs.size(); k += TNB_MAX_BIAS_JOBS)
       TNB_CHECK(tnb_bias_update_batch(Cx(), &bias_jobs[k], (int)std::min<size_t>(TNB_MAX_BIAS_JOBS, bias_jobs.size() - k)));
-    for (size_t k = deferred.size(); k-- > 0;)  // bottom-most deferred layer first: the order the next forward pass needs them
-      deferred[k]->DataParallelReduceUpdate((int)deferred[k]->GetInput().Rows() * mWorld);
+    if (!mDpGroup) {
+      for (size_t k = deferred.size(); k-- > 0;)  // bottom-most deferred layer first: the order the next forward pass needs them
+        deferred[k]->DataParallelReduceUpdate((int)deferred[k]->GetInput().Rows() * mWorld);
+    } else if (!deferred.empty()) {
+      // the deferred layers go out together: one NCCL launch for all of them (a call's fixed latency is paid once), one update
+      // launch behind it, bottom-most layer first
+      if (!mEvGroup) TNB_CHECK(tnb_event_create(Cx(), &mEvGroup));
+      std::vector<float *> bufs;
+      std::vector<size_t> counts;
+      std::vector<void *> evs;
+      std::vector<TnbSgdJob> jobs;
+      for (size_t k = deferred.size(); k-- > 0;) {
+        bufs.push_back(deferred[k]->GradBuffer());
+        counts.push_back(deferred[k]->GradCount());
+        evs.push_back(deferred[k]->BiasGradientEvent());
+      }
+      TNB_CHECK(tnb_allreduce_sum_multi(Cx(), bufs.data(), counts.data(), (int)bufs.size(), evs.data(), (int)evs.size(), mEvGroup));
+      TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_AUX2, mEvGroup));
+      for (size_t k = deferred.size(); k-- > 0;) jobs.push_back(deferred[k]->GradientJob((int)deferred[k]->GetInput().Rows() * mWorld));
+      for (size_t k = 0; k < jobs.size(); k += TNB_MAX_BIAS_JOBS)
+        TNB_CHECK(tnb_sgd_update_batch_on(Cx(), TNB_STREAM_AUX2, &jobs[k], (int)std::min<size_t>(TNB_MAX_BIAS_JOBS, jobs.size() - k)));
+      for (size_t k = 0; k < deferred.size(); k++) deferred[k]->MarkDataParallelUpdateEnqueued();
+    }
     if (!pending.empty() && mDpShard) TNB_CHECK(tnb_comm_wait(Cx()));  // the next forward pass reads the gathered weights
     // restore the wiring the fused softmax step changed
     if (mFuse && n >= 2 && mNetComponents[n - 1]->GetType() == CuComponent::SOFTMAX)
@@ -1029,6 +1063,8 @@ class CuNetwork {
   const char *mpTempBasisDir;
   bool mFuse;
   int mWorld;
+  void *mEvGroup;                  ///< data parallel: behind the grouped all-reduce of the deferred layers
+  bool mDpGroup;                   ///< deferred layers in one NCCL launch (TNB_DP_GROUP=1; measured slower, off by default)
   int mBwdStreams;                 ///< fused single-GPU schedule: 2 = weight-gradient GEMMs on a side stream (TNB_BWD_STREAMS)
   int mDpDeferBegin, mDpDeferEnd;  ///< all-reduce schedule: updatable layers [begin, end), counted from the top, exchange late
   bool mDpShard;  ///< data-parallel schedule: false = all-reduce + batched update (default), true = tnb_dp_update (TNB_DP_MODE=shard)
