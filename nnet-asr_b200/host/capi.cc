@@ -66,7 +66,7 @@ struct TnhCache_ {
 
 struct TnhRbm_ {
   CuNetwork net;
-  CuRbm *rbm;
+  CuRbmBase *rbm;
   CuRand<BaseFloat> *rnd;
   CuMeanSquareError mse;
   CuMatrix<BaseFloat> pos_vis, pos_hid, neg_vis, neg_hid, dummy_labs, dummy_err;
@@ -74,7 +74,7 @@ struct TnhRbm_ {
   ~TnhRbm_() { delete rnd; }
   void Step() {  // TRbmCu.cc:326-354
     rbm->Propagate(pos_vis, pos_hid);
-    if (rbm->HidType() == CuRbm::BERNOULLI) {
+    if (rbm->HidType() == CuRbmBase::BERNOULLI) {
       rnd->BinarizeProbs(pos_hid, neg_hid);
     } else {
       neg_hid.CopyFrom(pos_hid);
@@ -343,8 +343,9 @@ int tnh_rbm_read(TnhRbm **out, const char *file, int bunchsize, float lr, float 
   try {
     h->net.ReadNetwork(file);
     if (h->net.Layers() != 1) Error(std::string("Number of layers must be 1") + file);
-    if (h->net.Layer(0).GetType() != CuComponent::RBM) Error(std::string("Layer must be RBM") + file);
-    h->rbm = dynamic_cast<CuRbm *>(&h->net.Layer(0));
+    if (h->net.Layer(0).GetType() != CuComponent::RBM && h->net.Layer(0).GetType() != CuComponent::RBM_SPARSE)
+      Error(std::string("Layer must be RBM") + file);
+    h->rbm = dynamic_cast<CuRbmBase *>(&h->net.Layer(0));
     h->rbm->LearnRate(lr); h->rbm->Momentum(mmt); h->rbm->Weightcost(wc);
     // the generator is seeded from lrand48() right here, i.e. after srand48(seed) and before any cache shuffle
     h->rnd = new CuRand<BaseFloat>(bunchsize, h->rbm->GetNOutputs());

@@ -9,6 +9,7 @@
 #ifndef TNETB200_CU_BASE_H_
 #define TNETB200_CU_BASE_H_
 
+#include <algorithm>
 #include <map>
 
 #include "tnet_b200.h"
@@ -390,6 +391,43 @@ class CuMath {
     for (int i = 0; i < blocks; i++)
       TNB_CHECK(tnb_gemm(Cx(), 'N', 'N', n, m, k, 1.0f, X.pCUData() + i * k, (int)X.Stride(), block_transf.pCUData(),
                          (int)block_transf.Stride(), 0.0f, Y.pCUData() + i * m, (int)Y.Stride()));
+  }
+  /// C[:, offC:] = alpha * op(A[:, offA:]) * op(B[:, offB:]) + beta * C[:, offC:] on sub-blocks addressed by a column offset into
+  /// the operands' first rows (cumath.cc:210-244).  The extents are those of B clipped to C: k = min(op(B) rows, op(A) cols),
+  /// columns = min(op(B) cols, C cols), rows = min(op(A) rows, C rows) — the callers rely on the clipping (<sharedlinearity>
+  /// passes the whole input matrix with the weight block's extents).  Upstream's row clip reads `n<C.Rows() ? m : C.Rows()`,
+  /// a slip that never triggers in its callers (op(A) always has at least C's rows); the plain minimum is taken here.
+  static void OffsetGemm(char transA, char transB, T alpha, const CuMatrix<T> &A, const CuMatrix<T> &B, T beta, CuMatrix<T> &C, int offA,
+                         int offB, int offC) {
+    const bool ta = (transA == 'T' || transA == 't'), tb = (transB == 'T' || transB == 't');
+    size_t cols = tb ? B.Rows() : B.Cols();
+    size_t rows = ta ? A.Cols() : A.Rows();
+    size_t k = tb ? B.Cols() : B.Rows();
+    const size_t k1 = ta ? A.Rows() : A.Cols();
+    k = std::min(k, k1);
+    cols = std::min(cols, C.Cols());
+    rows = std::min(rows, C.Rows());
+    TNB_CHECK(tnb_gemm(Cx(), transA, transB, (int)rows, (int)cols, (int)k, alpha, A.pCUData() + offA, (int)A.Stride(), B.pCUData() + offB,
+                       (int)B.Stride(), beta, C.pCUData() + offC, (int)C.Stride()));
+  }
+  /// out = [in in in ...] (cumath.cc:366-384: the splice kernel on a one-row matrix with all-zero offsets)
+  static void VecExpand(const CuVector<T> &in, CuVector<T> &out) {
+    assert(in.Dim() > 0 && out.Dim() % in.Dim() == 0);
+    CuVector<int> offsets(out.Dim() / in.Dim());
+    offsets.SetZero();
+    VecExpand(in, out, offsets);
+  }
+  /// the same with a caller-kept all-zero offset vector of out.Dim()/in.Dim() entries (no allocation per call)
+  static void VecExpand(const CuVector<T> &in, CuVector<T> &out, const CuVector<int> &offsets) {
+    assert(in.Dim() > 0 && out.Dim() == in.Dim() * offsets.Dim());
+    TnbMatrixDim din = {1, (int)in.Dim(), (int)in.Dim()}, dout = {1, (int)out.Dim(), (int)out.Dim()};
+    TNB_CHECK(tnb_expand(Cx(), out.pCUData(), in.pCUData(), offsets.pCUData(), dout, din));
+  }
+  /// out = alpha * (sum of the out.Dim()-long pieces of in) + beta * out (cumath.cc:388-404: `in` read as [pieces x out.Dim()])
+  static void VecAddColSum(T alpha, const CuVector<T> &in, T beta, CuVector<T> &out) {
+    assert(out.Dim() > 0 && in.Dim() % out.Dim() == 0);
+    TnbMatrixDim d = {(int)(in.Dim() / out.Dim()), (int)out.Dim(), (int)out.Dim()};
+    TNB_CHECK(tnb_add_col_sum(Cx(), alpha, in.pCUData(), beta, out.pCUData(), d));
   }
   static void Expand(CuMatrix<T> &Y, const CuMatrix<T> &X, const CuVector<int> &frameOffsets) {
     assert(Y.Rows() == X.Rows() && X.Cols() * frameOffsets.Dim() == Y.Cols());

@@ -15,8 +15,9 @@ const TagEntry kTags[] = {
     {"<softmax>", CuComponent::SOFTMAX},                  {"<sigmoid>", CuComponent::SIGMOID},   {"<expand>", CuComponent::EXPAND},
     {"<copy>", CuComponent::COPY},                        {"<transpose>", CuComponent::TRANSPOSE}, {"<blocklinearity>", CuComponent::BLOCK_LINEARITY},
     {"<bias>", CuComponent::BIAS},                        {"<window>", CuComponent::WINDOW},     {"<log>", CuComponent::LOG},
+    {"<sharedlinearity>", CuComponent::SHARED_LINEARITY}, {"<discretelinearity>", CuComponent::DISCRETE_LINEARITY}, {"<rbmsparse>", CuComponent::RBM_SPARSE},
 };
-const char *kOutOfScope[] = {"<discretelinearity>", "<sharedlinearity>", "<sparselinearity>", "<rbmsparse>", "<blockarray>", "<clusterlinearity>"};
+const char *kOutOfScope[] = {"<sparselinearity>", "<blockarray>", "<clusterlinearity>"};
 }  // namespace
 
 CuComponent *CuNetwork::ComponentFactory(std::istream &rIn) {
@@ -56,6 +57,9 @@ CuComponent *CuNetwork::ComponentFactory(std::istream &rIn) {
     case CuComponent::BIAS: pRet = new CuBias(nInputs, nOutputs, pPred); break;
     case CuComponent::WINDOW: pRet = new CuWindow(nInputs, nOutputs, pPred); break;
     case CuComponent::LOG: pRet = new CuLog(nInputs, nOutputs, pPred); break;
+    case CuComponent::SHARED_LINEARITY: pRet = new CuSharedLinearity(nInputs, nOutputs, pPred); break;
+    case CuComponent::DISCRETE_LINEARITY: pRet = new CuDiscreteLinearity(nInputs, nOutputs, pPred); break;
+    case CuComponent::RBM_SPARSE: pRet = new CuRbmSparse(nInputs, nOutputs, pPred); break;
     default: Error(std::string("Unknown Component tag:") + componentTag);
   }
   try {

@@ -471,11 +471,24 @@ class CuLog : public CuComponent {
 // =====================================================================================================
 // CuRbm (cuRbm.{h,cc}) — CD-1 building blocks used by TRbmCu
 // =====================================================================================================
-class CuRbm : public CuUpdatableComponent {
+/// what TRbmCu's loop needs from an RBM layer (cuRbm.h:15-45): implemented by CuRbm and CuRbmSparse
+class CuRbmBase : public CuUpdatableComponent {
  public:
   typedef enum { BERNOULLI, GAUSSIAN } RbmUnitType;
+  CuRbmBase(size_t nInputs, size_t nOutputs, CuComponent *pPred) : CuUpdatableComponent(nInputs, nOutputs, pPred) {}
+  virtual void Propagate(const CuMatrix<BaseFloat> &visProbs, CuMatrix<BaseFloat> &hidProbs) = 0;
+  virtual void Reconstruct(const CuMatrix<BaseFloat> &hidState, CuMatrix<BaseFloat> &visProbs) = 0;
+  virtual void RbmUpdate(const CuMatrix<BaseFloat> &pos_vis, const CuMatrix<BaseFloat> &pos_hid, const CuMatrix<BaseFloat> &neg_vis,
+                         const CuMatrix<BaseFloat> &neg_hid) = 0;
+  virtual RbmUnitType VisType() = 0;
+  virtual RbmUnitType HidType() = 0;
+  using CuComponent::Propagate;  // the no-argument network-internal form stays visible next to the RBM one
+};
+
+class CuRbm : public CuRbmBase {
+ public:
   CuRbm(size_t nInputs, size_t nOutputs, CuComponent *pPred)
-      : CuUpdatableComponent(nInputs, nOutputs, pPred), mVisHid(nInputs, nOutputs), mVisBias(nInputs), mHidBias(nOutputs),
+      : CuRbmBase(nInputs, nOutputs, pPred), mVisHid(nInputs, nOutputs), mVisBias(nInputs), mHidBias(nOutputs),
         mVisHidCorrection(nInputs, nOutputs), mVisBiasCorrection(nInputs), mHidBiasCorrection(nOutputs), mVisType(BERNOULLI),
         mHidType(BERNOULLI) {}
   ComponentType GetType() const { return RBM; }
@@ -581,6 +594,10 @@ class CuRbm : public CuUpdatableComponent {
   CuMatrix<BaseFloat> mBackpropErrBuf;
   RbmUnitType mVisType, mHidType;
 };
+
+}  // namespace TNet
+#include "cu_nnet_ext.h"  // CuSharedLinearity, CuDiscreteLinearity, CuRbmSparse
+namespace TNet {
 
 // =====================================================================================================
 // CuRecurrent (cuRecurrent.{h,cc}) — Elman layer, one frame per call, truncated BPTT in Update()

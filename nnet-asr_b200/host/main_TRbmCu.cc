@@ -52,8 +52,9 @@ int main(int argc, char *argv[]) try {
   if (NULL != p_source_mmf_file) network.ReadNetwork(p_source_mmf_file);
   else Error("Source MMF must be specified [-H]");
   if (network.Layers() != 1) Error(std::string("Number of layers must be 1") + p_source_mmf_file);
-  if (network.Layer(0).GetType() != CuComponent::RBM) Error(std::string("Layer must be RBM") + p_source_mmf_file);
-  CuRbm &rbm = dynamic_cast<CuRbm &>(network.Layer(0));
+  if (network.Layer(0).GetType() != CuComponent::RBM && network.Layer(0).GetType() != CuComponent::RBM_SPARSE)
+    Error(std::string("Layer must be RBM") + p_source_mmf_file);
+  CuRbmBase &rbm = dynamic_cast<CuRbmBase &>(network.Layer(0));
 
   feature_repo.Init(fp.swap_features, fp.start_frm_ext, fp.end_frm_ext, fp.target_kind, fp.deriv_order, NULL, NULL, fp.cmn_mask, NULL, fp.cvn_mask, fp.cvg_file);
   if (NULL != p_script) feature_repo.AddFileList(p_script);
@@ -92,7 +93,7 @@ int main(int argc, char *argv[]) try {
     while (!cache.Empty()) {
       cache.GetBunch(pos_vis, dummy_labs);
       rbm.Propagate(pos_vis, pos_hid);
-      if (rbm.HidType() == CuRbm::BERNOULLI) {
+      if (rbm.HidType() == CuRbmBase::BERNOULLI) {
         cu_rand.BinarizeProbs(pos_hid, neg_hid);
       } else {
         neg_hid.CopyFrom(pos_hid);

@@ -37,7 +37,10 @@ def write_vector(f, v, fmt="%.9g"):
 def write_mlp(path, layers):
     """layers: list of ('affine', Wt[out x in], b) | ('sigmoid', n) | ('softmax', n)
     | ('expand', dim_in, offsets) | ('bias', v) | ('window', v)
-    | ('rbm', vistype, hidtype, Wt[hid x vis], visbias, hidbias) | ('recurrent', Wt[out x (in+out)], b, nin)"""
+    | ('rbm', vistype, hidtype, Wt[hid x vis], visbias, hidbias) | ('recurrent', Wt[out x (in+out)], b, nin)
+    | ('shared', ninst, Wt[out/ninst x in/ninst], b[out/ninst])      <sharedlinearity>, cuSharedLinearity.cc:98-178
+    | ('discrete', [Wt_i[out_i x in_i], ...], b[sum out_i])           <discretelinearity>, cuDiscreteLinearity.cc:80-157
+    | ('rbmsparse', vistype, hidtype, Wt, visbias, hidbias, sparsity_cost)   <rbmsparse>, cuRbmSparse.cc:171-236"""
     with open(path, "w") as f:
         for L in layers:
             kind = L[0]
@@ -74,6 +77,28 @@ def write_mlp(path, layers):
                 write_matrix(f, Wt)
                 write_vector(f, b)
                 f.write("\n")
+            elif kind == "shared":
+                _, ninst, Wt, b = L
+                f.write("<sharedlinearity> %d %d\n%d\n" % (Wt.shape[0] * ninst, Wt.shape[1] * ninst, ninst))
+                write_matrix(f, Wt)
+                write_vector(f, b)
+                f.write("\n")
+            elif kind == "discrete":
+                _, blocks, b = L
+                f.write("<discretelinearity> %d %d\n%d\n" % (sum(B.shape[0] for B in blocks), sum(B.shape[1] for B in blocks), len(blocks)))
+                for B in blocks:
+                    write_matrix(f, B)
+                write_vector(f, b)
+                f.write("\n")
+            elif kind == "rbmsparse":
+                _, vt, ht, Wt, vb, hb, cost = L
+                f.write("<rbmsparse> %d %d\n" % (Wt.shape[0], Wt.shape[1]))
+                f.write(" %s  %s\n" % (vt, ht))
+                write_matrix(f, Wt)
+                write_vector(f, vb)
+                f.write("\n")
+                write_vector(f, hb)
+                f.write("\n%.9g\n" % cost)
             else:
                 raise ValueError(kind)
 
@@ -110,7 +135,32 @@ def _read_vector(tk, dtype=np.float32):
 
 def read_mlp(path):
     """Parse a network text file back into the `layers` structure of write_mlp."""
-    tk = _Tok(open(path).read())
+    return read_mlp_text(open(path).read())
+
+
+def layer_dims(L):
+    """(n_inputs, n_outputs) of one entry of the `layers` structure."""
+    k = L[0]
+    if k == "affine":
+        return L[1].shape[1], L[1].shape[0]
+    if k == "shared":
+        return L[2].shape[1] * L[1], L[2].shape[0] * L[1]
+    if k == "discrete":
+        return sum(B.shape[1] for B in L[1]), sum(B.shape[0] for B in L[1])
+    if k in ("rbm", "rbmsparse"):
+        return L[3].shape[1], L[3].shape[0]
+    if k == "recurrent":
+        return L[3], L[1].shape[0]
+    if k == "expand":
+        return L[1], L[1] * len(L[2])
+    if k in ("bias", "window"):
+        return len(L[1]), len(L[1])
+    return L[1], L[1]
+
+
+def read_mlp_text(text):
+    """The same from the file's contents (the golden fixtures keep whole network files as strings)."""
+    tk = _Tok(text)
     layers = []
     while tk.peek() is not None:
         tag = tk.next().lower()
@@ -138,6 +188,22 @@ def read_mlp(path):
             Wt = _read_matrix(tk)
             b = _read_vector(tk)
             layers.append(("recurrent", Wt, b, nin))
+        elif tag == "<sharedlinearity>":
+            ninst = int(tk.next())
+            Wt = _read_matrix(tk)
+            b = _read_vector(tk)
+            assert Wt.shape == (nout // ninst, nin // ninst)
+            layers.append(("shared", ninst, Wt, b))
+        elif tag == "<discretelinearity>":
+            nblocks = int(tk.next())
+            blocks = [_read_matrix(tk) for _ in range(nblocks)]
+            layers.append(("discrete", blocks, _read_vector(tk)))
+        elif tag == "<rbmsparse>":
+            vt, ht = tk.next(), tk.next()
+            Wt = _read_matrix(tk)
+            vb = _read_vector(tk)
+            hb = _read_vector(tk)
+            layers.append(("rbmsparse", vt, ht, Wt, vb, hb, float(tk.next())))
         else:
             raise ValueError("unsupported tag " + tag)
     return layers

@@ -70,10 +70,7 @@ def srand48(seed):
     hlib().tnh_srand48(int(seed))
 
 
-def _layer_dims(L):
-    if L[0] == "affine":
-        return L[1].shape[1], L[1].shape[0]
-    return L[1], L[1]
+_layer_dims = F.layer_dims
 
 
 class Net:
@@ -248,10 +245,15 @@ class Cache:
 
 
 class Rbm:
-    def __init__(self, Wt, vb, hb, vis_gauss, hid_gauss, bunch, lr, mmt, wc):
+    def __init__(self, Wt, vb, hb, vis_gauss, hid_gauss, bunch, lr, mmt, wc, sparse_cost=None):
+        """sparse_cost != None: the layer is written as <rbmsparse> with that sparsity cost (CuRbmSparse)"""
         with tempfile.NamedTemporaryFile(suffix=".rbm", delete=False) as t:
             name = t.name
-        F.write_mlp(name, [("rbm", "gauss" if vis_gauss else "bern", "gauss" if hid_gauss else "bern", f32(Wt), f32(vb), f32(hb))])
+        units = ("gauss" if vis_gauss else "bern", "gauss" if hid_gauss else "bern")
+        if sparse_cost is None:
+            F.write_mlp(name, [("rbm",) + units + (f32(Wt), f32(vb), f32(hb))])
+        else:
+            F.write_mlp(name, [("rbmsparse",) + units + (f32(Wt), f32(vb), f32(hb), float(sparse_cost))])
         self.h = C.c_void_p()
         try:
             hcheck(hlib().tnh_rbm_read(C.byref(self.h), name.encode(), C.c_int(bunch), C.c_float(lr), C.c_float(mmt), C.c_float(wc)))

@@ -406,6 +406,111 @@ void orc_affine_update(const float *X, int ldx, const float *E, int lde, float *
 }
 
 /* ------------------------------------------------------------------------- */
+/* CuMath::OffsetGemm (cumath.cc:210-244): GEMM on sub-blocks addressed by a    */
+/* column offset into each operand; extents clipped to op(B) and C.  With the  */
+/* row-major layout an offset is a pointer bump, the leading dimensions stay.  */
+/* ------------------------------------------------------------------------- */
+static void offset_gemm(char ta, char tb, int rows, int cols, int k, float alpha, const float *A,
+                        int lda, int offA, const float *B, int ldb, int offB, float beta, float *C,
+                        int ldc, int offC, int acc_double) {
+  orc_gemm(ta, tb, rows, cols, k, alpha, A + offA, lda, B + offB, ldb, beta, C + offC, ldc, acc_double);
+}
+
+/* ------------------------------------------------------------------------- */
+/* CuSharedLinearity (cuSharedLinearity.cc): W [bi x bo] (bi = nin/K,          */
+/* bo = nout/K) shared by the K column blocks of the input; bias [bo]          */
+/* ------------------------------------------------------------------------- */
+
+/* cuSharedLinearity.cc:9-25 PropagateFnc; VecExpand = cumath.cc:366-384 (bias tiled K times) */
+void orc_shared_fwd(const float *X, int ldx, const float *W, const float *bias, float *Y, int ldy,
+                    int rows, int bi, int bo, int K, int acc_double) {
+  float *bexp = (float *)malloc(sizeof(float) * (size_t)bo * K);
+  for (int i = 0; i < bo * K; i++) bexp[i] = bias[i % bo];
+  orc_add_scaled_row(1.0f, bexp, 0.0f, Y, rows, bo * K, ldy);
+  for (int i = 0; i < K; i++)
+    offset_gemm('N', 'N', rows, bo, bi, 1.0f, X, ldx, i * bi, W, bo, 0, 1.0f, Y, ldy, i * bo, acc_double);
+  free(bexp);
+}
+
+/* cuSharedLinearity.cc:28-36 BackpropagateFnc */
+void orc_shared_bwd(const float *E, int lde, const float *W, float *Eprev, int ldp, int rows, int bi,
+                    int bo, int K, int acc_double) {
+  for (int i = 0; i < K; i++)
+    offset_gemm('N', 'T', rows, bi, bo, 1.0f, E, lde, i * bo, W, bo, 0, 0.0f, Eprev, ldp, i * bi, acc_double);
+}
+
+/* cuSharedLinearity.cc:62-93 Update ("#if 1 new implementation"); VecAddColSum = cumath.cc:388-404,
+ * which always launches the serial double-accumulator kernel on the [K x bo] view */
+void orc_shared_update(const float *X, int ldx, const float *E, int lde, float *W, float *bias,
+                       float *corrW, float *corrb, int rows, int bi, int bo, int K, float lr,
+                       float mmt, float wc, int grad_div_frm, int acc_double) {
+  float N = 1;
+  if (grad_div_frm) N = (float)rows;
+  float mmt_gain = (float)(1.0 / (1.0 - mmt));
+  N *= mmt_gain;
+  N *= (float)K;
+  for (int i = 0; i < K; i++)
+    offset_gemm('T', 'N', bi, bo, rows, 1.0f, X, ldx, i * bi, E, lde, i * bo, (i == 0) ? mmt : 1.0f,
+                corrW, bo, 0, acc_double);
+  float *cexp = (float *)calloc((size_t)bo * K, sizeof(float));
+  orc_add_col_sum(1.0f, E, 0.0f, cexp, rows, bo * K, lde);
+  orc_add_col_sum_serial(1.0f, cexp, mmt, corrb, K, bo, bo);
+  free(cexp);
+  orc_add_scaled(-lr / N, corrW, 1.0f, W, bi, bo, bo);
+  orc_add_scaled(-lr / N, corrb, 1.0f, bias, 1, bo, bo);
+  orc_add_scaled(-lr * wc, W, 1.0f, W, bi, bo, bo);
+}
+
+/* ------------------------------------------------------------------------- */
+/* CuDiscreteLinearity (cuDiscreteLinearity.cc): block-diagonal affine layer;  */
+/* block i is Wb[i] [bin[i] x bout[i]], one bias over all outputs             */
+/* ------------------------------------------------------------------------- */
+
+/* cuDiscreteLinearity.cc:7-25 PropagateFnc */
+void orc_discrete_fwd(const float *X, int ldx, float *const *Wb, const int *bin, const int *bout,
+                      int nblocks, const float *bias, float *Y, int ldy, int rows, int nout,
+                      int acc_double) {
+  orc_add_scaled_row(1.0f, bias, 0.0f, Y, rows, nout, ldy);
+  int oi = 0, oo = 0;
+  for (int i = 0; i < nblocks; i++) {
+    offset_gemm('N', 'N', rows, bout[i], bin[i], 1.0f, X, ldx, oi, Wb[i], bout[i], 0, 1.0f, Y, ldy, oo, acc_double);
+    oi += bin[i]; oo += bout[i];
+  }
+}
+
+/* cuDiscreteLinearity.cc:28-41 BackpropagateFnc */
+void orc_discrete_bwd(const float *E, int lde, float *const *Wb, const int *bin, const int *bout,
+                      int nblocks, float *Eprev, int ldp, int rows, int acc_double) {
+  int oi = 0, oo = 0;
+  for (int i = 0; i < nblocks; i++) {
+    offset_gemm('N', 'T', rows, bin[i], bout[i], 1.0f, E, lde, oi, Wb[i], bout[i], 0, 0.0f, Eprev, ldp, oo, acc_double);
+    oi += bout[i]; oo += bin[i];
+  }
+}
+
+/* cuDiscreteLinearity.cc:44-76 Update */
+void orc_discrete_update(const float *X, int ldx, const float *E, int lde, float **Wb, float **corrWb,
+                         const int *bin, const int *bout, int nblocks, float *bias, float *corrb,
+                         int rows, int nout, float lr, float mmt, float wc, int grad_div_frm,
+                         int acc_double) {
+  float N = 1;
+  if (grad_div_frm) N = (float)rows;
+  float mmt_gain = (float)(1.0 / (1.0 - mmt));
+  N *= mmt_gain;
+  int oi = 0, oo = 0;
+  for (int i = 0; i < nblocks; i++) {
+    offset_gemm('T', 'N', bin[i], bout[i], rows, 1.0f, X, ldx, oi, E, lde, oo, mmt, corrWb[i], bout[i], 0, acc_double);
+    oi += bin[i]; oo += bout[i];
+  }
+  for (int i = 0; i < nblocks; i++) {
+    orc_add_scaled(-lr / N, corrWb[i], 1.0f, Wb[i], bin[i], bout[i], bout[i]);
+    orc_add_scaled(-lr * wc, Wb[i], 1.0f, Wb[i], bin[i], bout[i], bout[i]);
+  }
+  orc_add_col_sum(1.0f, E, mmt, corrb, rows, nout, lde);
+  orc_add_scaled(-lr / N, corrb, 1.0f, bias, 1, nout, nout);
+}
+
+/* ------------------------------------------------------------------------- */
 /* Objective functions (cuObjectiveFunction.cc)                               */
 /* ------------------------------------------------------------------------- */
 typedef struct {
@@ -653,11 +758,14 @@ void orc_binarize_probs(float *states, const float *probs, const float *rnd, int
 /* MLP network trainer: CuNetwork::Propagate / Backpropagate                  */
 /* (cuNetwork.h:137-194) + TNetCu.cc:427-441 bunch loop                       */
 /* ------------------------------------------------------------------------- */
-enum { ORC_AFFINE = 0, ORC_SIGMOID = 1, ORC_SOFTMAX = 2 };
+enum { ORC_AFFINE = 0, ORC_SIGMOID = 1, ORC_SOFTMAX = 2, ORC_SHARED = 3, ORC_DISCRETE = 4 };
 
 typedef struct {
   int type, nin, nout;
-  float *W, *b, *corrW, *corrb; /* affine only; W [nin x nout] */
+  float *W, *b, *corrW, *corrb; /* affine: W [nin x nout]; shared: W [nin/K x nout/K], b [nout/K]; discrete: b only */
+  int K;                        /* shared: instances; discrete: blocks */
+  float **Wb, **corrWb;         /* discrete: block i [bin[i] x bout[i]] */
+  int *bin, *bout;
   float lr, mmt, wc;
   int gdf;
   float *out, *eout; /* [rows x nout], [rows x nin] */
@@ -697,8 +805,49 @@ void orc_net_add_affine(OrcNet *h, int nin, int nout, const float *Wt, const flo
     for (int i = 0; i < nin; i++) l->W[IDX(i, o, nout)] = Wt[IDX(o, i, nin)];
   memcpy(l->b, b, sizeof(float) * (size_t)nout);
 }
+/* Wt [nout/K x nin/K] on-disk layout (cuSharedLinearity.cc:112-121) */
+void orc_net_add_shared(OrcNet *h, int nin, int nout, int K, const float *Wt, const float *b) {
+  OrcLayer *l = net_push(h, ORC_SHARED, nin, nout);
+  int bi = nin / K, bo = nout / K;
+  l->K = K;
+  l->W = (float *)malloc(sizeof(float) * (size_t)bi * bo);
+  l->b = (float *)malloc(sizeof(float) * (size_t)bo);
+  l->corrW = (float *)calloc((size_t)bi * bo, sizeof(float));
+  l->corrb = (float *)calloc((size_t)bo, sizeof(float));
+  for (int o = 0; o < bo; o++)
+    for (int i = 0; i < bi; i++) l->W[IDX(i, o, bo)] = Wt[IDX(o, i, bi)];
+  memcpy(l->b, b, sizeof(float) * (size_t)bo);
+}
+/* blocks concatenated in Wt_all, each in on-disk layout [bout[i] x bin[i]] (cuDiscreteLinearity.cc:91-105) */
+void orc_net_add_discrete(OrcNet *h, int nblocks, const int *bin, const int *bout, const float *Wt_all,
+                          const float *b) {
+  int nin = 0, nout = 0;
+  for (int i = 0; i < nblocks; i++) { nin += bin[i]; nout += bout[i]; }
+  OrcLayer *l = net_push(h, ORC_DISCRETE, nin, nout);
+  l->K = nblocks;
+  l->bin = (int *)malloc(sizeof(int) * (size_t)nblocks);
+  l->bout = (int *)malloc(sizeof(int) * (size_t)nblocks);
+  l->Wb = (float **)calloc((size_t)nblocks, sizeof(float *));
+  l->corrWb = (float **)calloc((size_t)nblocks, sizeof(float *));
+  const float *src = Wt_all;
+  for (int k = 0; k < nblocks; k++) {
+    l->bin[k] = bin[k]; l->bout[k] = bout[k];
+    l->Wb[k] = (float *)malloc(sizeof(float) * (size_t)bin[k] * bout[k]);
+    l->corrWb[k] = (float *)calloc((size_t)bin[k] * bout[k], sizeof(float));
+    for (int o = 0; o < bout[k]; o++)
+      for (int i = 0; i < bin[k]; i++) l->Wb[k][IDX(i, o, bout[k])] = src[IDX(o, i, bin[k])];
+    src += (size_t)bin[k] * bout[k];
+  }
+  l->b = (float *)malloc(sizeof(float) * (size_t)nout);
+  l->corrb = (float *)calloc((size_t)nout, sizeof(float));
+  memcpy(l->b, b, sizeof(float) * (size_t)nout);
+}
 void orc_net_add_sigmoid(OrcNet *h, int n) { net_push(h, ORC_SIGMOID, n, n); }
 void orc_net_add_softmax(OrcNet *h, int n) { net_push(h, ORC_SOFTMAX, n, n); }
+
+static int layer_updatable(const OrcLayer *l) {
+  return l->type == ORC_AFFINE || l->type == ORC_SHARED || l->type == ORC_DISCRETE;
+}
 
 /* cuNetwork.cc:80-135 SetLearnRate (factors==NULL => scale 1) + SetMomentum etc. */
 void orc_net_set_hyper(OrcNet *h, float lr, const float *factors, int nfactors, float mmt, float wc,
@@ -707,7 +856,7 @@ void orc_net_set_hyper(OrcNet *h, float lr, const float *factors, int nfactors, 
   h->stopper = -1;
   for (int i = 0; i < h->n; i++) {
     OrcLayer *l = &h->L[i];
-    if (l->type != ORC_AFFINE) continue;
+    if (!layer_updatable(l)) continue;
     float scale = 1.0f;
     if (factors && k < nfactors) scale = factors[k];
     k++;
@@ -735,6 +884,14 @@ void orc_net_propagate(OrcNet *h, const float *X, int rows, float *out) {
         orc_affine_fwd(in, l->nin, l->W, l->nout, l->b, l->out, l->nout, rows, l->nin, l->nout,
                        h->acc_double);
         break;
+      case ORC_SHARED:
+        orc_shared_fwd(in, l->nin, l->W, l->b, l->out, l->nout, rows, l->nin / l->K, l->nout / l->K, l->K,
+                       h->acc_double);
+        break;
+      case ORC_DISCRETE:
+        orc_discrete_fwd(in, l->nin, l->Wb, l->bin, l->bout, l->K, l->b, l->out, l->nout, rows, l->nout,
+                         h->acc_double);
+        break;
       case ORC_SIGMOID: orc_sigmoid(l->out, in, rows, l->nout, l->nout); break;
       case ORC_SOFTMAX: orc_softmax(l->out, in, rows, l->nout, l->nout); break;
     }
@@ -755,6 +912,13 @@ void orc_net_backpropagate(OrcNet *h, const float *X, const float *globerr, int 
           orc_affine_bwd(ein, l->nout, l->W, l->nout, l->eout, l->nin, rows, l->nin, l->nout,
                          h->acc_double);
           break;
+        case ORC_SHARED:
+          orc_shared_bwd(ein, l->nout, l->W, l->eout, l->nin, rows, l->nin / l->K, l->nout / l->K, l->K,
+                         h->acc_double);
+          break;
+        case ORC_DISCRETE:
+          orc_discrete_bwd(ein, l->nout, l->Wb, l->bin, l->bout, l->K, l->eout, l->nin, rows, h->acc_double);
+          break;
         case ORC_SIGMOID: /* cuActivation.cc:17-22 */
           orc_diff_sigmoid(l->eout, ein, l->out, rows, l->nout, l->nout);
           break;
@@ -767,6 +931,12 @@ void orc_net_backpropagate(OrcNet *h, const float *X, const float *globerr, int 
       orc_affine_update(in, l->nin, ein, l->nout, l->W, l->nout, l->b, l->corrW, l->nout, l->corrb,
                         rows, l->nin, l->nout, l->lr, l->mmt, l->wc, l->gdf, h->acc_double);
     }
+    if (l->type == ORC_SHARED && l->lr > 0.0f)
+      orc_shared_update(in, l->nin, ein, l->nout, l->W, l->b, l->corrW, l->corrb, rows, l->nin / l->K,
+                        l->nout / l->K, l->K, l->lr, l->mmt, l->wc, l->gdf, h->acc_double);
+    if (l->type == ORC_DISCRETE && l->lr > 0.0f)
+      orc_discrete_update(in, l->nin, ein, l->nout, l->Wb, l->corrWb, l->bin, l->bout, l->K, l->b, l->corrb,
+                          rows, l->nout, l->lr, l->mmt, l->wc, l->gdf, h->acc_double);
     if (i == h->stopper) break;
     ein = l->eout;
   }
@@ -795,6 +965,25 @@ void orc_net_get_affine(OrcNet *h, int layer, float *Wt, float *b) {
     for (int i = 0; i < l->nin; i++) Wt[IDX(o, i, l->nin)] = l->W[IDX(i, o, l->nout)];
   memcpy(b, l->b, sizeof(float) * (size_t)l->nout);
 }
+/* shared: Wt [nout/K x nin/K], b [nout/K] */
+void orc_net_get_shared(OrcNet *h, int layer, float *Wt, float *b) {
+  OrcLayer *l = &h->L[layer];
+  int bi = l->nin / l->K, bo = l->nout / l->K;
+  for (int o = 0; o < bo; o++)
+    for (int i = 0; i < bi; i++) Wt[IDX(o, i, bi)] = l->W[IDX(i, o, bo)];
+  memcpy(b, l->b, sizeof(float) * (size_t)bo);
+}
+/* discrete: the blocks concatenated, each [bout[i] x bin[i]]; b [nout] */
+void orc_net_get_discrete(OrcNet *h, int layer, float *Wt_all, float *b) {
+  OrcLayer *l = &h->L[layer];
+  float *dst = Wt_all;
+  for (int k = 0; k < l->K; k++) {
+    for (int o = 0; o < l->bout[k]; o++)
+      for (int i = 0; i < l->bin[k]; i++) dst[IDX(o, i, l->bin[k])] = l->Wb[k][IDX(i, o, l->bout[k])];
+    dst += (size_t)l->bin[k] * l->bout[k];
+  }
+  memcpy(b, l->b, sizeof(float) * (size_t)l->nout);
+}
 const float *orc_net_layer_out(OrcNet *h, int layer) { return h->L[layer].out; }
 const float *orc_net_layer_eout(OrcNet *h, int layer) { return h->L[layer].eout; }
 const float *orc_net_err(OrcNet *h) { return h->err; }
@@ -803,6 +992,9 @@ void orc_net_free(OrcNet *h) {
   for (int i = 0; i < h->n; i++) {
     OrcLayer *l = &h->L[i];
     free(l->W); free(l->b); free(l->corrW); free(l->corrb); free(l->out); free(l->eout);
+    if (l->type == ORC_DISCRETE)
+      for (int k = 0; k < l->K; k++) { free(l->Wb[k]); free(l->corrWb[k]); }
+    free(l->Wb); free(l->corrWb); free(l->bin); free(l->bout);
   }
   free(h->L); free(h->err); free(h);
 }
@@ -817,6 +1009,10 @@ typedef struct {
   float lr, mmt, wc;
   int acc_double;
   OrcObjStats st;
+  /* CuRbmSparse (cuRbmSparse.h:64-70,92-105): off unless orc_rbm_set_sparse() was called */
+  int sparse;
+  float sp_prior, sp_lambda, sp_cost;
+  float *sp_q, *sp_qcur, *vis_mean;
 } OrcRbm;
 
 /* Wt on-disk [nhid x nvis] (cuRbm.cc:198-207) */
@@ -836,9 +1032,18 @@ OrcRbm *orc_rbm_new(int nvis, int nhid, int vis_gauss, int hid_gauss, const floa
   r->chb = (float *)calloc(nhid, sizeof(float));
   return r;
 }
+/* cuRbmSparse.h:92-105 constructor defaults (prior 1e-4, lambda 0.95); the cost comes from the file (cuRbmSparse.cc:198-199) */
+void orc_rbm_set_sparse(OrcRbm *r, float cost) {
+  r->sparse = 1; r->sp_prior = 0.0001f; r->sp_lambda = 0.95f; r->sp_cost = cost;
+  r->sp_q = (float *)malloc(sizeof(float) * r->nhid);
+  r->sp_qcur = (float *)calloc(r->nhid, sizeof(float));
+  r->vis_mean = (float *)calloc(r->nvis, sizeof(float));
+  for (int h = 0; h < r->nhid; h++) r->sp_q[h] = r->sp_prior;
+}
 void orc_rbm_free(OrcRbm *r) {
   if (!r) return;
-  free(r->W); free(r->vb); free(r->hb); free(r->cW); free(r->cvb); free(r->chb); free(r);
+  free(r->W); free(r->vb); free(r->hb); free(r->cW); free(r->cvb); free(r->chb);
+  free(r->sp_q); free(r->sp_qcur); free(r->vis_mean); free(r);
 }
 /* cuRbm.cc:15-23 PropagateFnc / :104-115 Propagate */
 void orc_rbm_propagate(OrcRbm *r, const float *vis, float *hid, int rows) {
@@ -861,15 +1066,27 @@ void orc_rbm_update(OrcRbm *r, const float *pos_vis, const float *pos_hid, const
                     const float *neg_hid, int rows) {
   float N = (float)rows;
   int V = r->nvis, H = r->nhid;
+  const int sp = r->sparse && !r->hid_gauss;
+  if (sp) { /* cuRbmSparse.cc:139-145 : q = lambda*q + (1-lambda)*mean(pos_hid); qcur = q - prior; mean visible */
+    orc_add_col_sum((float)(1.0 / rows), pos_hid, 0.0f, r->sp_qcur, rows, H, H);
+    orc_add_scaled((float)(1.0 - r->sp_lambda), r->sp_qcur, r->sp_lambda, r->sp_q, 1, H, H);
+    orc_set_const(r->sp_qcur, -r->sp_prior, 1, H, H);
+    orc_add_scaled(1.0f, r->sp_q, 1.0f, r->sp_qcur, 1, H, H);
+    orc_add_col_sum((float)(1.0 / rows), pos_vis, 0.0f, r->vis_mean, rows, V, V);
+  }
   orc_gemm('T', 'N', V, H, rows, -r->lr / N, neg_vis, V, neg_hid, H, r->mmt, r->cW, H, r->acc_double);
   orc_gemm('T', 'N', V, H, rows, +r->lr / N, pos_vis, V, pos_hid, H, 1.0f, r->cW, H, r->acc_double);
   orc_add_scaled(-r->lr * r->wc, r->W, 1.0f, r->cW, V, H, H);
+  if (sp) /* cuRbmSparse.cc:151-153 : cW += -cost * vis_mean * qcur^T (cublasSger) */
+    for (int v = 0; v < V; v++)
+      for (int h = 0; h < H; h++) r->cW[IDX(v, h, H)] += -r->sp_cost * r->vis_mean[v] * r->sp_qcur[h];
   orc_add_scaled(1.0f, r->cW, 1.0f, r->W, V, H, H);
   orc_add_col_sum(-r->lr / N, neg_vis, r->mmt, r->cvb, rows, V, V);
   orc_add_col_sum(+r->lr / N, pos_vis, 1.0f, r->cvb, rows, V, V);
   orc_add_scaled(1.0f, r->cvb, 1.0f, r->vb, 1, V, V);
   orc_add_col_sum(-r->lr / N, neg_hid, r->mmt, r->chb, rows, H, H);
   orc_add_col_sum(+r->lr / N, pos_hid, 1.0f, r->chb, rows, H, H);
+  if (sp) orc_add_scaled(-r->sp_cost, r->sp_qcur, 1.0f, r->chb, 1, H, H); /* cuRbmSparse.cc:162-164 */
   orc_add_scaled(1.0f, r->chb, 1.0f, r->hb, 1, H, H);
 }
 /* TRbmCu.cc:326-354 : one CD-1 bunch.  z1..z4 are the [rows x nhid] RNG state

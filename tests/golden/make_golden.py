@@ -110,12 +110,82 @@ def run_mlp(case, cfg, impl, workdir, exe=None, save=True):
     print("%s %s: %s" % (impl, case, rep))
 
 
+# --------------------------------------------------------------------------- networks with the OffsetGemm layers
+# first layer: ("shared", bo) = <sharedlinearity> with one instance per spliced frame (2*ctx+1 instances of raw_dim -> bo), or
+# ("discrete", [(in_i, out_i), ...]) = <discretelinearity>; then <sigmoid>, <biasedlinearity> to n_out, <softmax>.
+NET_CASES = {
+    # CPU-comparable rule (TNetLib/SharedLinearity.cc:222-258: W -= lr/K * dW, no momentum, no 1/N, no L2)
+    "net_shared": dict(raw_dim=13, ctx=2, first=("shared", 8), n_out=10, n_utt=20, n_frames=90, bunch=64, cache=512,
+                       lr=0.02, mmt=0.0, wc=0.0, gdf=False, seed=61, randomize=True),
+    "net_shared_mmt": dict(raw_dim=13, ctx=3, first=("shared", 6), n_out=12, n_utt=20, n_frames=100, bunch=128, cache=768,
+                           lr=0.8, mmt=0.5, wc=1e-4, gdf=True, seed=62, randomize=True),
+    "net_discrete": dict(raw_dim=13, ctx=2, first=("discrete", [(26, 12), (39, 20)]), n_out=10, n_utt=20, n_frames=100, bunch=64,
+                         cache=512, lr=0.6, mmt=0.5, wc=1e-4, gdf=True, seed=63, randomize=True),
+}
+NET_GPU_ONLY = {"net_shared_mmt", "net_discrete"}
+
+
+def build_net(cfg, rng):
+    nin = cfg["raw_dim"] * (2 * cfg["ctx"] + 1)
+    kind, arg = cfg["first"]
+    if kind == "shared":
+        K = 2 * cfg["ctx"] + 1
+        first = ("shared", K, (0.1 * rng.standard_normal((arg, nin // K))).astype(np.float32), rng.uniform(-4.1, -3.9, arg).astype(np.float32))
+        nhid = arg * K
+    else:
+        assert sum(b[0] for b in arg) == nin
+        nhid = sum(b[1] for b in arg)
+        first = ("discrete", [(0.1 * rng.standard_normal((o, i))).astype(np.float32) for i, o in arg], rng.uniform(-4.1, -3.9, nhid).astype(np.float32))
+    top = ("affine", (0.1 * rng.standard_normal((cfg["n_out"], nhid))).astype(np.float32), np.zeros(cfg["n_out"], np.float32))
+    return [first, ("sigmoid", nhid), top, ("softmax", cfg["n_out"])]
+
+
+def run_net(case, cfg, impl, workdir, exe=None, save=True):
+    """Like run_mlp for an arbitrary layer list; the fixture keeps the initial and final network FILES as text."""
+    rng = np.random.default_rng(cfg["seed"] + 1000)
+    utts = F.gen_utterances(cfg["n_utt"], cfg["n_frames"], cfg["raw_dim"], cfg["n_out"], rng)
+    paths = F.write_dataset(workdir, utts, cfg["n_out"], cfg["ctx"])
+    init = os.path.join(workdir, "init.nnet")
+    F.write_mlp(init, build_net(cfg, rng))
+    final = os.path.join(workdir, "final.nnet")
+    if exe is None:
+        exe = os.path.join(REF, "TNet" if impl == "cpu" else "TNetCu")
+    cmd = [exe, "-H", init, "-I", paths["mlf"], "-L", "*/", "-X", "lab", "-S", paths["scp"], "-m", paths["labelmap"],
+           "-n", repr(cfg["lr"]), "--TARGETMMF=" + final, "--BUNCHSIZE=%d" % cfg["bunch"], "--CACHESIZE=%d" % cfg["cache"],
+           "--RANDOMIZE=" + _b(cfg["randomize"]), "--SEED=%d" % cfg["seed"], "--FEATURETRANSFORM=" + paths["transform"],
+           "--STARTFRMEXT=%d" % cfg["ctx"], "--ENDFRMEXT=%d" % cfg["ctx"], "--WEIGHTCOST=" + repr(cfg["wc"])]
+    if impl == "cpu":
+        cmd += ["--THREADS=1"]
+    else:
+        cmd += ["--MOMENTUM=" + repr(cfg["mmt"]), "--GRADDIVFRM=" + _b(cfg["gdf"])]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("reference failed:\n" + res.stdout[-3000:])
+    rep = parse_report(res.stdout)
+    if not save:
+        return rep, F.read_mlp(final), res.stdout
+    names = list(utts.keys())
+    np.savez_compressed(
+        os.path.join(OUT, "%s_%s.npz" % (impl, case)),
+        feats=np.concatenate([utts[n][0] for n in names]), labels=np.concatenate([utts[n][1] for n in names]),
+        lengths=np.array([utts[n][0].shape[0] for n in names], dtype=np.int32),
+        dims=np.array([cfg["raw_dim"] * (2 * cfg["ctx"] + 1), cfg["n_out"]], dtype=np.int32),
+        cfg=np.array([cfg["ctx"], cfg["bunch"], cfg["cache"], cfg["seed"], int(cfg["randomize"]), int(cfg["gdf"])], dtype=np.int64),
+        hyper=np.array([cfg["lr"], cfg["mmt"], cfg["wc"]], dtype=np.float64),
+        init_net=np.frombuffer(open(init, "rb").read(), dtype=np.uint8), final_net=np.frombuffer(open(final, "rb").read(), dtype=np.uint8),
+        ref_err=np.float64(rep["err"]), ref_frames=np.int64(rep["frames"]), ref_correct_pct=np.float64(rep["correct_pct"]))
+    print("%s %s: %s" % (impl, case, rep))
+
+
 # --------------------------------------------------------------------------- RBM (TRbmCu) / recurrent (TRecurrentCu)
 RBM_CASES = {
     "rbm_gb": dict(raw_dim=13, ctx=1, nhid=32, vistype="gauss", hidtype="bern", n_utt=12, n_frames=100, bunch=32, cache=256,
                    lr=0.001, mmt=0.5, wc=2e-4, seed=11),
     "rbm_bb": dict(raw_dim=13, ctx=1, nhid=24, vistype="bern", hidtype="bern", n_utt=12, n_frames=100, bunch=32, cache=256,
                    lr=0.1, mmt=0.5, wc=2e-4, seed=12),
+    # <rbmsparse> (cuRbmSparse.cc): the file carries the sparsity cost; large enough here for the penalty to move the weights
+    "rbm_sparse_bb": dict(raw_dim=13, ctx=1, nhid=24, vistype="bern", hidtype="bern", n_utt=12, n_frames=100, bunch=32, cache=256,
+                          lr=0.1, mmt=0.5, wc=2e-4, seed=13, sparse_cost=0.01),
 }
 RNN_CASES = {
     "rnn_small": dict(raw_dim=13, ctx=1, nhid=20, n_out=8, n_utt=6, n_frames=40, bptt=4, lr=0.05, seed=21),
@@ -134,7 +204,11 @@ def run_rbm(case, cfg, workdir, exe=None, save=True):
     vb = np.zeros(nvis, np.float32)
     hb = (rng.random(cfg["nhid"]) / 5.0 - 0.1).astype(np.float32)
     init = os.path.join(workdir, "init.rbm")
-    F.write_mlp(init, [("rbm", cfg["vistype"], cfg["hidtype"], Wt, vb, hb)])
+    cost = cfg.get("sparse_cost")
+    if cost is None:
+        F.write_mlp(init, [("rbm", cfg["vistype"], cfg["hidtype"], Wt, vb, hb)])
+    else:
+        F.write_mlp(init, [("rbmsparse", cfg["vistype"], cfg["hidtype"], Wt, vb, hb, cost)])
     L0 = F.read_mlp(init)[0]
     final = os.path.join(workdir, "final.rbm")
     cmd = [exe or os.path.join(REF, "TRbmCu"), "-H", init, "-S", paths["scp"], "-n", repr(cfg["lr"]), "--TARGETMMF=" + final,
@@ -155,6 +229,7 @@ def run_rbm(case, cfg, workdir, exe=None, save=True):
         cfg=np.array([cfg["ctx"], cfg["bunch"], cfg["cache"], cfg["seed"], int(cfg["vistype"] == "gauss"), int(cfg["hidtype"] == "gauss")], np.int64),
         hyper=np.array([cfg["lr"], cfg["mmt"], cfg["wc"]], np.float64),
         init_Wt=L0[3], init_vb=L0[4], init_hb=L0[5], final_Wt=LF[3], final_vb=LF[4], final_hb=LF[5],
+        sparse_cost=np.float64(-1.0 if cost is None else cost),
         ref_err=np.float64(rep["err"]), ref_frames=np.int64(rep["frames"]))
     print("gpu %s: %s" % (case, rep))
 
@@ -272,28 +347,42 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--impl", choices=["cpu", "gpu"], required=True)
     ap.add_argument("--out", default=OUT)
+    ap.add_argument("--only", default=None, help="regular expression: generate only the cases whose name matches")
     a = ap.parse_args()
     OUT = a.out
     os.makedirs(OUT, exist_ok=True)
+
+    def want(case):
+        return a.only is None or re.search(a.only, case) is not None
+
     for case, cfg in MLP_CASES.items():
-        if a.impl == "cpu" and case in GPU_ONLY:
+        if (a.impl == "cpu" and case in GPU_ONLY) or not want(case):
             continue
         with tempfile.TemporaryDirectory() as d:
             run_mlp(case, cfg, a.impl, d)
+    for case, cfg in NET_CASES.items():
+        if (a.impl == "cpu" and case in NET_GPU_ONLY) or not want(case):
+            continue
+        with tempfile.TemporaryDirectory() as d:
+            run_net(case, cfg, a.impl, d)
     if a.impl == "cpu":
         for case, cfg in NORM_CASES.items():
-            with tempfile.TemporaryDirectory() as d:
-                run_norm(case, cfg, d)
+            if want(case):
+                with tempfile.TemporaryDirectory() as d:
+                    run_norm(case, cfg, d)
         for case, cfg in FEACAT_CASES.items():
-            with tempfile.TemporaryDirectory() as d:
-                run_feacat(case, cfg, d)
+            if want(case):
+                with tempfile.TemporaryDirectory() as d:
+                    run_feacat(case, cfg, d)
     if a.impl == "gpu":
         for case, cfg in RBM_CASES.items():
-            with tempfile.TemporaryDirectory() as d:
-                run_rbm(case, cfg, d)
+            if want(case):
+                with tempfile.TemporaryDirectory() as d:
+                    run_rbm(case, cfg, d)
         for case, cfg in RNN_CASES.items():
-            with tempfile.TemporaryDirectory() as d:
-                run_rnn(case, cfg, d)
+            if want(case):
+                with tempfile.TemporaryDirectory() as d:
+                    run_rnn(case, cfg, d)
 
 
 if __name__ == "__main__":

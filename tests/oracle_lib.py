@@ -5,9 +5,12 @@ Builds the library on first use if it is missing (gcc is available here and on t
 import ctypes as C
 import os
 import subprocess
+import sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "nnet-asr_b200", "python"))
+from tnet_b200 import formats as F  # noqa: E402  (file-format helpers only: layer tuple shapes)
 _SO = os.path.join(ROOT, "oracle", "_build", "libtnet_oracle.so")
 
 fp = C.POINTER(C.c_float)
@@ -181,6 +184,15 @@ class Net:
             if L[0] == "affine":
                 Wt, b = f32(L[1]), f32(L[2])
                 lib.orc_net_add_affine(self.h, ci(Wt.shape[1]), ci(Wt.shape[0]), P(Wt), P(b))
+            elif L[0] == "shared":
+                K, Wt, b = int(L[1]), f32(L[2]), f32(L[3])
+                lib.orc_net_add_shared(self.h, ci(Wt.shape[1] * K), ci(Wt.shape[0] * K), ci(K), P(Wt), P(b))
+            elif L[0] == "discrete":
+                blocks, b = [f32(B) for B in L[1]], f32(L[2])
+                bin_ = np.array([B.shape[1] for B in blocks], np.int32)
+                bout = np.array([B.shape[0] for B in blocks], np.int32)
+                flat = np.concatenate([B.ravel() for B in blocks])
+                lib.orc_net_add_discrete(self.h, ci(len(blocks)), P(bin_), P(bout), P(flat), P(b))
             elif L[0] == "sigmoid":
                 lib.orc_net_add_sigmoid(self.h, ci(L[1]))
             elif L[0] == "softmax":
@@ -202,8 +214,7 @@ class Net:
         return out
 
     def _nout(self):
-        L = self.layers[-1]
-        return L[1].shape[0] if L[0] == "affine" else L[1]
+        return F.layer_dims(self.layers[-1])[1]
 
     def train_bunch(self, X, T, cv=False):
         X = f32(X); T = f32(T)
@@ -220,15 +231,32 @@ class Net:
         lib.orc_net_get_affine(self.h, ci(idx), P(Wt), P(b))
         return Wt, b
 
-    def layer_out(self, idx, rows):
+    def get_layer(self, idx):
+        """Current parameters of layer idx in the `layers` tuple form of tnet_b200.formats."""
         L = self.layers[idx]
-        n = L[1].shape[0] if L[0] == "affine" else L[1]
+        if L[0] == "affine":
+            return ("affine",) + self.get_affine(idx)
+        if L[0] == "shared":
+            Wt = np.empty_like(f32(L[2])); b = np.empty_like(f32(L[3]))
+            lib.orc_net_get_shared(self.h, ci(idx), P(Wt), P(b))
+            return ("shared", L[1], Wt, b)
+        if L[0] == "discrete":
+            flat = np.empty(sum(B.size for B in L[1]), np.float32); b = np.empty_like(f32(L[2]))
+            lib.orc_net_get_discrete(self.h, ci(idx), P(flat), P(b))
+            blocks, pos = [], 0
+            for B in L[1]:
+                blocks.append(flat[pos:pos + B.size].reshape(B.shape).copy())
+                pos += B.size
+            return ("discrete", blocks, b)
+        return L
+
+    def layer_out(self, idx, rows):
+        n = F.layer_dims(self.layers[idx])[1]
         p = lib.orc_net_layer_out(self.h, ci(idx))
         return np.ctypeslib.as_array(p, shape=(rows, n)).copy()
 
     def layer_eout(self, idx, rows):
-        L = self.layers[idx]
-        n = L[1].shape[1] if L[0] == "affine" else L[1]
+        n = F.layer_dims(self.layers[idx])[0]
         p = lib.orc_net_layer_eout(self.h, ci(idx))
         return np.ctypeslib.as_array(p, shape=(rows, n)).copy()
 
@@ -294,6 +322,10 @@ class Rbm:
         self.nhid, self.nvis = Wt.shape
         self.h = C.c_void_p(lib.orc_rbm_new(ci(self.nvis), ci(self.nhid), ci(int(vis_gauss)), ci(int(hid_gauss)),
                                             P(Wt), P(vb), P(hb), cf(lr), cf(mmt), cf(wc), ci(acc_double)))
+
+    def set_sparse(self, cost):
+        """CuRbmSparse: sparsity penalty with the reference's constructor defaults (prior 1e-4, lambda 0.95)."""
+        lib.orc_rbm_set_sparse(self.h, cf(cost))
 
     def cd1(self, pos_vis, z):
         pos_vis = f32(pos_vis); rows = pos_vis.shape[0]

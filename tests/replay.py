@@ -5,12 +5,34 @@ from tnet_b200 import formats as F
 
 
 def fixture_layers(g, prefix="init"):
+    if prefix + "_net" in g:      # newer fixtures keep the whole network file as text
+        return F.read_mlp_text(bytes(g[prefix + "_net"]).decode())
     dims = list(g["dims"])
     layers = []
     for k in range(len(dims) - 1):
         layers.append(("affine", g["%s_Wt%d" % (prefix, k)], g["%s_b%d" % (prefix, k)]))
         layers.append(("softmax" if k == len(dims) - 2 else "sigmoid", int(dims[k + 1])))
     return layers
+
+
+def compare_layer(got, ref, wtol, btol_floor=1e-3):
+    """Parameters of one layer (tuple form of tnet_b200.formats) against another's, e.g. the reference's final network file
+    (6 significant digits, KaldiLib/Matrix.tcc:522-532).  Non-parametric layers compare equal."""
+    assert got[0] == ref[0]
+    if got[0] == "affine":
+        mats, vecs = [(got[1], ref[1])], [(got[2], ref[2])]
+    elif got[0] == "shared":
+        assert got[1] == ref[1]
+        mats, vecs = [(got[2], ref[2])], [(got[3], ref[3])]
+    elif got[0] == "discrete":
+        assert len(got[1]) == len(ref[1])
+        mats, vecs = list(zip(got[1], ref[1])), [(got[2], ref[2])]
+    else:
+        return
+    for W, rW in mats:
+        np.testing.assert_allclose(W, rW, rtol=wtol, atol=wtol * np.abs(rW).max())
+    for b, rb in vecs:
+        np.testing.assert_allclose(b, rb, rtol=wtol, atol=wtol * max(btol_floor, np.abs(rb).max()))
 
 
 def utterances(g):
@@ -62,7 +84,10 @@ def replay_rbm(g, make_rbm, make_cache, srand48):
     ctx, bunch, cache, seed, vis_gauss, hid_gauss = [int(v) for v in g["cfg"]]
     lr, mmt, wc = [float(v) for v in g["hyper"]]
     srand48(seed)
-    rbm = make_rbm(g["init_Wt"], g["init_vb"], g["init_hb"], vis_gauss, hid_gauss, bunch, lr, mmt, wc)
+    extra = {}
+    if "sparse_cost" in g and float(g["sparse_cost"]) >= 0:      # <rbmsparse> fixture
+        extra["sparse_cost"] = float(g["sparse_cost"])
+    rbm = make_rbm(g["init_Wt"], g["init_vb"], g["init_hb"], vis_gauss, hid_gauss, bunch, lr, mmt, wc, **extra)
     cache = (cache // bunch) * bunch
     c = make_cache(cache, bunch)
     it = iter(utterances(g))

@@ -34,6 +34,47 @@ def test_tnetcu_binary_reproduces_reference(case):
             k += 1
 
 
+def _net_cases():
+    import glob
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "*_net_*.npz")))
+
+
+@pytest.mark.parametrize("fixture", _net_cases())
+def test_tnetcu_binary_offset_gemm_layers(fixture):
+    """bin/TNetCu on networks with <sharedlinearity> / <discretelinearity> == the reference trainer that produced the
+    fixture: cpu_* = unmodified CPU TNet (whose rule TNetCu reproduces with --GRADDIVFRM=F --MOMENTUM=0), gpu_* = TNetCu on a B200."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from replay import compare_layer, fixture_layers
+    impl, case = fixture.split("_", 1)
+    g = np.load(os.path.join(GOLD, fixture + ".npz"))
+    with tempfile.TemporaryDirectory() as d:
+        rep, layers, out = MG.run_net(case, MG.NET_CASES[case], "gpu", d, exe=os.path.join(BIN, "TNetCu"), save=False)
+    assert rep["frames"] == int(g["ref_frames"])
+    assert abs(rep["err"] - float(g["ref_err"])) <= 1e-4 * abs(float(g["ref_err"]))
+    assert abs(rep["correct_pct"] - float(g["ref_correct_pct"])) <= 0.2
+    final = fixture_layers(g, "final")
+    assert len(final) == len(layers)
+    for a, b in zip(layers, final):
+        compare_layer(a, b, 2e-4, btol_floor=1e-2)
+
+
+def test_trbmcu_binary_rbmsparse():
+    """bin/TRbmCu accepts an <rbmsparse> layer like the reference (TRbmCu.cc:229) and writes the tag and the sparsity cost back;
+    with the reference's GPU run as fixture (gpu_rbm_sparse_bb.npz, when generated) the result must match it."""
+    case = "rbm_sparse_bb"
+    with tempfile.TemporaryDirectory() as d:
+        rep, LF, out = MG.run_rbm(case, MG.RBM_CASES[case], d, exe=os.path.join(BIN, "TRbmCu"), save=False)
+    assert "===== TRbmCu FINISHED" in out and "RBM::mSparsityCost=" in out
+    assert LF[0] == "rbmsparse" and abs(LF[6] - MG.RBM_CASES[case]["sparse_cost"]) < 1e-9
+    path = os.path.join(GOLD, "gpu_%s.npz" % case)
+    if os.path.exists(path):
+        g = np.load(path)
+        assert rep["frames"] == int(g["ref_frames"])
+        assert abs(rep["err"] - float(g["ref_err"])) <= 2e-4 * abs(float(g["ref_err"]))
+        np.testing.assert_allclose(LF[3], g["final_Wt"], rtol=2e-4, atol=2e-4 * np.abs(g["final_Wt"]).max())
+
+
 def test_trbmcu_binary_reproduces_reference():
     g = np.load(os.path.join(GOLD, "gpu_rbm_gb.npz"))
     with tempfile.TemporaryDirectory() as d:

@@ -10,7 +10,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 import oracle_lib as O
-from replay import fixture_layers, replay_mlp, replay_rbm, rnn_layers, rnn_utterances, utterances
+from replay import compare_layer, fixture_layers, replay_mlp, replay_rbm, rnn_layers, rnn_utterances, utterances
 from tnet_b200 import abi, host
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -97,6 +97,137 @@ def test_one_bunch_layerwise_vs_oracle(dims, bunch, fusion):
     e1, f1, c1 = net.stats()
     e2, f2, c2 = onet.stats()
     assert f1 == f2 and abs(c1 - c2) <= 1 and abs(e1 - e2) <= 2e-5 * abs(e2)
+
+
+NET_GOLD = sorted(glob.glob(os.path.join(GOLD, "*_net_*.npz")))
+
+
+@pytest.mark.parametrize("path", NET_GOLD, ids=[os.path.basename(p)[:-4] for p in NET_GOLD])
+@pytest.mark.parametrize("fusion", [True, False], ids=["fused", "unfused"])
+def test_offset_gemm_layers_epoch_matches_reference_trainers(path, fusion):
+    """SURVEY 8f row 4: networks whose first layer is a <sharedlinearity> / <discretelinearity> (CuMath::OffsetGemm users).  One epoch
+    on the CUDA path == the reference trainer's report and written network (cpu_*: unmodified CPU TNet, gpu_*: TNetCu on a B200)."""
+    g = np.load(path)
+    host.set_math(abi.MATH_3XTF32)
+    net, nb, perms = replay_mlp(g, lambda L: host.Net(L, fusion=fusion), host.Cache, _srand_both)
+    err, frames, correct = net.stats()
+    assert frames == int(g["ref_frames"])
+    assert abs(err - float(g["ref_err"])) <= 1e-4 * abs(float(g["ref_err"]))          # tolerance as for the MLP epochs above
+    ref_correct = round(float(g["ref_correct_pct"]) * frames / 100.0)
+    assert abs(correct - ref_correct) <= max(1, int(0.002 * frames))
+    got, final = net.get_layers(), fixture_layers(g, "final")
+    assert len(got) == len(final)
+    for a, b in zip(got, final):
+        compare_layer(a, b, 2e-4, btol_floor=1e-2)
+
+
+def _offset_nets(r):
+    def w(o, i):
+        return (0.1 * r.standard_normal((o, i))).astype(np.float32)
+
+    def nb(n):
+        return r.uniform(-4.1, -3.9, n).astype(np.float32)
+    top = lambda nh, no: [("sigmoid", nh), ("affine", w(no, nh), np.zeros(no, np.float32)), ("softmax", no)]
+    return {
+        # 13-wide column blocks: every block GEMM starts off a 16-byte boundary -> fp32 FMA kernel
+        "shared_unaligned": [("shared", 5, w(8, 13), nb(8))] + top(40, 10),
+        # 32-wide blocks at 128-byte offsets: the same layer through the tcgen05 kernel
+        "shared_aligned": [("shared", 4, w(64, 32), nb(64))] + top(256, 300),
+        "discrete_unaligned": [("discrete", [w(12, 26), w(20, 39)], nb(32))] + top(32, 10),
+        "discrete_aligned": [("discrete", [w(32, 64), w(96, 32), w(64, 32)], nb(192))] + top(192, 20),
+        # the layer in the middle of a network: its dX and the dX through it are both exercised
+        "shared_middle": [("affine", w(60, 39), nb(60)), ("sigmoid", 60), ("shared", 3, w(16, 20), nb(16))] + top(48, 12),
+        "discrete_middle": [("affine", w(64, 39), nb(64)), ("sigmoid", 64), ("discrete", [w(24, 32), w(8, 32)], nb(32))] + top(32, 12),
+    }
+
+
+@pytest.mark.parametrize("fusion", [True, False], ids=["fused", "unfused"])
+@pytest.mark.parametrize("name", ["shared_unaligned", "shared_aligned", "discrete_unaligned", "discrete_aligned", "shared_middle",
+                                  "discrete_middle"])
+def test_offset_gemm_layers_one_bunch_vs_oracle(name, fusion):
+    """<sharedlinearity> / <discretelinearity> forward, dX and update against the oracle's restatement of cuSharedLinearity.cc /
+    cuDiscreteLinearity.cc (double-accumulated GEMMs), layer by layer, two bunches (momentum), bunch 96."""
+    from tnet_b200 import formats as F
+    r = np.random.default_rng(11)
+    layers = _offset_nets(r)[name]
+    bunch, nin, nout = 96, F.layer_dims(layers[0])[0], F.layer_dims(layers[-1])[1]
+    X = r.standard_normal((bunch, nin)).astype(np.float32)
+    T = np.zeros((bunch, nout), np.float32)
+    T[np.arange(bunch), r.integers(0, nout, bunch)] = 1
+    host.set_math(abi.MATH_3XTF32)
+    net = host.Net(layers, fusion=fusion)
+    onet = O.Net(net.layers, acc_double=1)
+    for n in (net, onet):
+        n.set_hyper(0.2, mmt=0.5, wc=1e-4, gdf=True)
+    for step in range(2):
+        net.train_bunch(X, T)
+        onet.train_bunch(X, T)
+    nl = len(layers)
+    first_upd = min(i for i, L in enumerate(layers) if L[0] in ("affine", "shared", "discrete"))
+    for i in range(nl):
+        if fusion and layers[i][0] == "affine" and i + 1 < nl and layers[i + 1][0] == "sigmoid":
+            continue                # pre-activation is never materialised on the fused path
+        a, b = net.layer_out(i, bunch), onet.layer_out(i, bunch)
+        np.testing.assert_allclose(a, b, rtol=2e-4, atol=2e-5 * max(1.0, np.abs(b).max()), err_msg="output of layer %d" % i)
+    for i in range(first_upd + 1, nl):
+        kind = layers[i][0]
+        if fusion and (kind == "softmax" or (kind == "affine" and layers[i - 1][0] == "sigmoid")):
+            continue                # identity copy / dX+diffsigmoid written straight into the layer below
+        if fusion and kind == "sigmoid" and i + 1 < nl and layers[i + 1][0] == "affine":
+            # the affine above wrote this sigmoid's error output (dX fused with y(1-y)): it must equal the oracle's
+            pass
+        a, b = net.layer_eout(i, bunch), onet.layer_eout(i, bunch)
+        np.testing.assert_allclose(a, b, rtol=1e-3, atol=2e-5 * max(1e-3, np.abs(b).max()), err_msg="error output of layer %d" % i)
+    got = net.get_layers()
+    for i in range(nl):
+        compare_layer(got[i], onet.get_layer(i), 2e-5, btol_floor=1e-2)
+    e1, f1, c1 = net.stats()
+    e2, f2, c2 = onet.stats()
+    assert f1 == f2 and abs(c1 - c2) <= 1 and abs(e1 - e2) <= 2e-5 * abs(e2)
+
+
+def test_offset_gemm_layers_reader_errors(tmp_path):
+    """Error behaviour of the two readers (cuSharedLinearity.cc:98-160, cuDiscreteLinearity.cc:80-141): exceptions -> error status."""
+    bad = str(tmp_path / "bad.nnet")
+    for text in ("<sharedlinearity> 6 6\n0\nm 2 2\n1 2 3 4\nv 2 0 0\n",            # "Bad number of instances"
+                 "<sharedlinearity> 6 5\n2\nm 3 2\n1 2 3 4 5 6\nv 3 0 0 0\n",      # inputs not divisible by the instances
+                 "<sharedlinearity> 6 4\n2\nm 3 3\n1 2 3 4 5 6 7 8 9\nv 3 0 0 0\n",  # block is 3x3, must be 3x2
+                 "<discretelinearity> 4 4\n0\nv 4 0 0 0 0\n",                         # "Bad number of blocks"
+                 "<discretelinearity> 4 4\n2\nm 2 2\n1 2 3 4\nm 2 1\n1 2\nv 4 0 0 0 0\n"):  # blocks cover 3 of 4 inputs
+        open(bad, "w").write(text)
+        with pytest.raises(abi.TnbError):
+            host.Net(path=bad)
+
+
+def test_rbm_sparse_cd1_vs_oracle():
+    """<rbmsparse> (cuRbmSparse.cc:125-168): CD-1 with the sparsity penalty over a few bunches against the oracle's restatement —
+    same Hybrid-Taus states (seeded from the same lrand48 stream), so the Bernoulli samples are bit-identical and the weights
+    differ by GEMM rounding only.  The penalty is made large enough to matter (cost 0.05)."""
+    from test_oracle_golden_rbm_rnn import _Rbm
+    r = np.random.default_rng(23)
+    nvis, nhid, bunch, cost = 39, 24, 32, 0.05
+    Wt = (0.1 * r.standard_normal((nhid, nvis))).astype(np.float32)
+    vb = np.zeros(nvis, np.float32)
+    hb = (r.random(nhid) / 5.0 - 0.1).astype(np.float32)
+    host.set_math(abi.MATH_3XTF32)
+    host.srand48(5)
+    a = host.Rbm(Wt, vb, hb, False, False, bunch, 0.1, 0.5, 2e-4, sparse_cost=cost)
+    O.lib.orc_srand48(5)
+    b = _Rbm(Wt, vb, hb, False, False, bunch, 0.1, 0.5, 2e-4, sparse_cost=cost)
+    O.lib.orc_srand48(5)
+    plain = _Rbm(Wt, vb, hb, False, False, bunch, 0.1, 0.5, 2e-4)       # same samples, no penalty
+    for step in range(6):
+        v = r.random((bunch, nvis)).astype(np.float32)
+        a.cd1(v)
+        b.cd1(v)
+        plain.cd1(v)
+    for k, (x, y, z) in enumerate(zip(a.get(), b.r.get(), plain.r.get())):
+        np.testing.assert_allclose(x, y, rtol=2e-4, atol=2e-5 * max(1e-2, np.abs(y).max()))
+        if k != 1:      # weights and hidden bias carry the penalty: it is not a no-op in this test
+            assert np.abs(y - z).max() > 1e-3 * max(1e-2, np.abs(y).max())
+    ea, fa = a.stats()
+    eb, fb = b.r.stats()
+    assert fa == fb and abs(ea - eb) <= 1e-4 * abs(eb)
 
 
 def test_cache_state_machine_vs_oracle():
@@ -202,7 +333,7 @@ def test_rbm_cd1_matches_reference_trbmcu(path):
 
     class CuRbmAdapter(host.Rbm):
         pass
-    rbm, nb = replay_rbm(g, lambda *a: host.Rbm(*a), host.Cache, host.srand48)
+    rbm, nb = replay_rbm(g, lambda *a, **k: host.Rbm(*a, **k), host.Cache, host.srand48)
     err, frames = rbm.stats()
     assert frames == int(g["ref_frames"])
     assert abs(err - float(g["ref_err"])) <= 2e-4 * abs(float(g["ref_err"]))

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from replay import replay_mlp
+from replay import compare_layer, fixture_layers, replay_mlp
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -22,20 +22,14 @@ def _check(g, acc_double, wtol, etol):
     assert abs(err - float(g["ref_err"])) <= etol * abs(float(g["ref_err"]))
     ref_correct = float(g["ref_correct_pct"]) * frames / 100.0
     assert abs(correct - ref_correct) <= max(1.0, 0.003 * frames)
-    k = 0
+    final = fixture_layers(g, "final")
+    assert len(final) == len(net.layers)
     for i, L in enumerate(net.layers):
-        if L[0] != "affine":
-            continue
-        Wt, b = net.get_affine(i)
-        rW, rb = g["final_Wt%d" % k], g["final_b%d" % k]
-        # reference writes 6 significant digits (KaldiLib/Matrix.tcc:522-532)
-        np.testing.assert_allclose(Wt, rW, rtol=wtol, atol=wtol * np.abs(rW).max())
-        np.testing.assert_allclose(b, rb, rtol=wtol, atol=wtol * max(1e-3, np.abs(rb).max()))
-        k += 1
+        compare_layer(net.get_layer(i), final[i], wtol)
     return correct, ref_correct
 
 
-@pytest.mark.parametrize("case", ["mlp_small", "mlp_norand_wc"])
+@pytest.mark.parametrize("case", ["mlp_small", "mlp_norand_wc", "net_shared"])
 @pytest.mark.parametrize("acc_double", [0, 1])
 def test_oracle_vs_reference_cpu_tnet(case, acc_double):
     g = np.load(os.path.join(GOLD, "cpu_%s.npz" % case))
@@ -43,7 +37,7 @@ def test_oracle_vs_reference_cpu_tnet(case, acc_double):
     assert correct == round(ref_correct)      # frame-accuracy count exact on these fixtures
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "gpu_mlp_*.npz"))) or [None])
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "gpu_mlp_*.npz")) + glob.glob(os.path.join(GOLD, "gpu_net_*.npz"))) or [None])
 def test_oracle_vs_reference_gpu_tnetcu(path):
     if path is None:
         pytest.skip("GPU goldens not generated yet (tests/golden/make_golden.py --impl gpu on a B200)")

@@ -15,8 +15,10 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 class _Rbm:
     """oracle RBM with TRbmCu's generator seeding order."""
 
-    def __init__(self, Wt, vb, hb, vis_gauss, hid_gauss, bunch, lr, mmt, wc):
+    def __init__(self, Wt, vb, hb, vis_gauss, hid_gauss, bunch, lr, mmt, wc, sparse_cost=None):
         self.r = O.Rbm(Wt, vb, hb, vis_gauss, hid_gauss, lr, mmt, wc, acc_double=0)
+        if sparse_cost is not None:
+            self.r.set_sparse(sparse_cost)
         self.z = [np.empty((bunch, Wt.shape[0]), np.uint32) for _ in range(4)]
         O.lib.orc_rand_seed(O.P(self.z[0]), O.P(self.z[1]), O.P(self.z[2]), O.P(self.z[3]), bunch, Wt.shape[0], Wt.shape[0])
 
