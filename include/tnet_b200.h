@@ -305,6 +305,36 @@ int tnb_dp_update(TnbContext *ctx, float *G, float *W, float *corrW, TnbMatrixDi
                   float *corrb, float lr, float mmt, float wc, int grad_div_frm, int n_frames_global);
 int tnb_comm_wait(TnbContext *ctx);
 
+/* ---- the same exchange without NCCL: one kernel per layer over NVLink peer memory (csrc/peer.cu) ------------------------------
+ * One process per GPU on one NVSwitch box.  tnb_peer_map is collective over the ranks of tnb_comm_init: it exports `local` (the base
+ * pointer of a device allocation of this library: tnb_malloc / tnb_malloc_pitch) with CUDA IPC, gathers the ranks' handles through
+ * the communicator and maps the other ranks' allocations into this process; mapped[r] is rank r's buffer as addressable from this
+ * GPU's kernels (mapped[rank] == local).  All ranks call it for the same buffers in the same order. */
+#define TNB_MAX_PEERS 16
+#define TNB_IPC_HANDLE_BYTES 64
+int tnb_peer_map(TnbContext *ctx, void *local, void **mapped /* [world] */);
+int tnb_peer_unmap(TnbContext *ctx, void *const *mapped);
+typedef struct TnbPeerJob_ {
+  float *G[TNB_MAX_PEERS]; /* every rank's [dW ; db] gradient buffer, (rows_pad + 1) rows of pitch dW.stride, as mapped into this process */
+  float *W[TNB_MAX_PEERS]; /* every rank's weights [rows_pad x stride] */
+  float *corrW;            /* this rank's momentum buffer [rows_pad x stride] */
+  float *bias, *corrb;     /* this rank's bias and its momentum buffer [cols] (both NULL: no bias) */
+  TnbMatrixDim dW;         /* logical weight matrix */
+  int rows_pad;            /* multiple of the world size, >= dW.rows; rows beyond dW.rows are zero in G and W */
+  float lr, mmt, wc;
+  int grad_div_frm, n_frames; /* n_frames = frames of the GLOBAL bunch */
+} TnbPeerJob;
+/* One layer's data-parallel update as ONE kernel on the communication stream, behind everything already on the compute stream and
+ * behind `wait_event` (may be NULL): this rank sums its block of rows [rank*rows_pad/world, +rows_pad/world) of all ranks' gradients
+ * through peer loads (rank order 0..world-1), applies CuBiasedLinearity::Update to that block of its corrW, and stores the updated
+ * weights into EVERY rank's W; the bias row is summed and updated by every rank for itself.  Ranks synchronise through flag words in
+ * peer memory at the start (all gradients complete, nobody reads W any more) and at the end (all blocks of this rank's W written)
+ * of the kernel; `done_event` (may be NULL) is recorded behind it.  With one rank it is tnb_sgd_update on the compute stream. */
+int tnb_dp_peer_update(TnbContext *ctx, const TnbPeerJob *job, void *wait_event, void *done_event);
+/* the same kernel for an explicit rank / world / flag blocks (64 zero-initialised words per rank) / sequence number (1, 2, ... per
+ * launch) on a given stream of the context: lets a test play several ranks on one GPU */
+int tnb_dp_peer_update_on(TnbContext *ctx, int stream_id, const TnbPeerJob *job, int rank, int world, unsigned *const *flags, unsigned seq);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,24 @@ static int load_nccl() {
     }                                                                                             \
   } while (0)
 
+int comm_allgather_bytes(TnbContext *ctx, unsigned char *all, size_t n) {
+  TNB_ARG(ctx && all && n > 0, "null");
+  if (ctx->world == 1) return TNB_OK;
+  int rc = load_nccl();
+  if (rc != TNB_OK) return rc;
+  TNB_ARG(ctx->nccl_comm != nullptr, "communicator not initialised");
+  unsigned char *d = nullptr;
+  const size_t total = n * (size_t)ctx->world, mine = n * (size_t)ctx->rank;
+  TNB_CUDA(cudaMalloc((void **)&d, total));
+  TNB_CUDA(cudaMemcpyAsync(d + mine, all + mine, n, cudaMemcpyHostToDevice, ctx->comm_stream));
+  int r = p_AllGather(d + mine, d, n, 0 /* ncclInt8 */, (NcclComm)ctx->nccl_comm, ctx->comm_stream);
+  if (r != 0) { cudaFree(d); TNB_NCCL(r); }
+  TNB_CUDA(cudaMemcpyAsync(all, d, total, cudaMemcpyDeviceToHost, ctx->comm_stream));
+  TNB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+  TNB_CUDA(cudaFree(d));
+  return TNB_OK;
+}
+
 }  // namespace tnb
 
 using namespace tnb;

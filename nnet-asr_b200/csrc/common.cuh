@@ -91,6 +91,9 @@ struct TnbContext_ {
   // data-parallel
   void *nccl_comm = nullptr;
   int rank = 0, world = 1;
+  // peer-memory schedule (peer.cu): every rank's flag block as mapped into this process, and the launch counter
+  unsigned *peer_flags[TNB_MAX_PEERS] = {};
+  unsigned peer_seq = 0;
 };
 
 namespace tnb {
@@ -105,6 +108,8 @@ int launch_sgd_update(TnbContext *ctx, cudaStream_t stream, const float *G, floa
 int ensure_row_scratch(TnbContext *ctx, int rows);
 int ensure_vec_scratch(TnbContext *ctx, int n);
 int ensure_vec_scratch_side(TnbContext *ctx, int n);
+// gathers n bytes per rank through the NCCL communicator: all[rank*n .. +n) in, every rank's bytes out (host memory; synchronous)
+int comm_allgather_bytes(TnbContext *ctx, unsigned char *all, size_t n);
 cudaStream_t stream_of(TnbContext *ctx, int stream_id);  // TNB_STREAM_* -> cudaStream_t (nullptr for an unknown id)
 int get_tmap(TnbContext *ctx, const void *ptr, int rows, int cols, int stride, int box_rows,
              int box_cols, int swizzle32, CUtensorMap *out, int elem_bytes = 4);

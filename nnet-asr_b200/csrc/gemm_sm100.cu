@@ -231,6 +231,10 @@ int launch_gemm_bf16(TnbContext *ctx, char transa, char transb, int M, int N, in
   if (force_bn < 0) { const char *e = getenv("TNB_GEMM_BN"); force_bn = e ? atoi(e) : 0; }
   if (force_cg < 0) { const char *e = getenv("TNB_GEMM_CG"); force_cg = e ? atoi(e) : 0; }
   if (force_split < 0) { const char *e = getenv("TNB_GEMM_SPLIT"); force_split = e ? atoi(e) : 0; }
+  // experiment knob: extra cycles charged to a split-K choice (the model's per-K-block fetch term is pessimistic for bf16 tiles, which
+  // may hide that 256x128 pairs without the accumulator exchange are as fast as split 256x256 ones)
+  static double split_penalty = -1.0;
+  if (split_penalty < 0.0) { const char *e = getenv("TNB_GEMM_BF16_SPLIT_PENALTY"); split_penalty = e ? atof(e) : 0.0; }
   int bn = 128, cg = 1, split = 1;
   double best = 1e300;
   const int cands[3] = {64, 128, 256};
@@ -252,7 +256,7 @@ int launch_gemm_bf16(TnbContext *ctx, char transa, char transb, int M, int N, in
         const long ctas = (long)mt * ((N + c - 1) / c) * sp;
         const long cap = (g * sp == 1) ? ctx->sm_count : cluster_capacity(ctx, g * sp);
         const long waves = (ctas + cap - 1) / cap;
-        const double t = ((num_kb + sp - 1) / sp) * (fetch > mma ? fetch : mma) + 4000.0 + 30.0 * c / sp + (sp == 2 ? 2500.0 + 8.0 * c : 0.0);
+        const double t = ((num_kb + sp - 1) / sp) * (fetch > mma ? fetch : mma) + 4000.0 + 30.0 * c / sp + (sp == 2 ? 2500.0 + 8.0 * c + split_penalty : 0.0);
         const double cost = waves * t;
         if (cost < best * 0.999) { best = cost; bn = c; cg = g; split = sp; }
       }

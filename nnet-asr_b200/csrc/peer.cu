@@ -1,0 +1,276 @@
+// peer.cu — one layer's data-parallel update as ONE kernel over NVLink peer memory.
+//
+// The NCCL schedules of comm.cu spend a layer's exchange on three steps that each sweep the weight-sized arrays: the collective
+// (all-reduce, or reduce-scatter + all-gather), then the update kernel (read G, corr, W; write corr, W).  Here every rank maps
+// the other ranks' gradient and weight buffers into its address space (CUDA IPC, one process per GPU on one NVSwitch box) and a
+// single kernel per layer does, for the block of weight rows this rank owns:
+//     g = sum over ranks of G_r[block]            (peer loads over NVLink, fixed rank order -> deterministic)
+//     corr = g + mmt*corr ; w = W + scale*corr ; w += l2*w        (CuBiasedLinearity::Update, cuBiasedLinearity.cc:55-63)
+//     W_r[block] = w for every rank r                              (peer stores)
+// i.e. reduce-scatter, the reference CPU trainer's "every worker updates its slice" (TNetLib/BiasedLinearity.cc:133-178) and
+// all-gather fused; the summed gradient never exists in memory and the update's HBM traffic is divided by the world size.
+// The bias (one row) is summed and updated redundantly by every rank.
+//
+// Ordering between the ranks uses two flag words per peer in a small flag block that every rank maps from every other rank:
+//   ready[r] = s : rank r has entered its kernel number s — its gradient is complete (stream order) and it no longer reads the
+//                  weights of this layer (its dX GEMM precedes its gradient GEMM);
+//   done[r]  = s : rank r has finished its stores for kernel s (fence.sys before the flag).
+// A kernel starts its loads when all ready flags have reached s and ends when all done flags have: after it, this rank's
+// weights are complete and nobody reads its gradient buffer any more.  All ranks issue the same kernels in the same order on
+// their communication stream (like a collective).  Every wait is bounded (trap, not hang).
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace tnb {
+
+struct PeerArgs {
+  int rank, world;
+  const float *G[TNB_MAX_PEERS];
+  float *W[TNB_MAX_PEERS];
+  unsigned *flags[TNB_MAX_PEERS];  // per rank: [0,16) ready, [16,32) done, [32] arrival counter of the owner's own CTAs
+  float *corr, *bias, *corrb;      // local
+  int cols, stride, shard, rows_pad;
+  float mmt, scale, l2;
+  unsigned seq;
+  long long timeout;  // cycles
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// threads [0, world) of the CTA each poll one flag until it has reached seq (wrap-safe compare), then the CTA proceeds
+__device__ __forceinline__ void wait_flags(const unsigned *f, int world, unsigned seq, long long timeout) {
+  if ((int)threadIdx.x < world) {
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(f + threadIdx.x) - seq) < 0) {
+      if (clock64() - t0 > timeout) __trap();
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float4 ldg_f4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+
+// WORLD > 0: compile-time rank count (all loads of U items issued before the first use); WORLD == 0: any rank count, one item at a time
+template <int WORLD, int U>
+__global__ void __launch_bounds__(512) dp_peer_update_kernel(const __grid_constant__ PeerArgs a) {
+  const int world = WORLD > 0 ? WORLD : a.world;
+  unsigned *my = a.flags[a.rank];
+  if (blockIdx.x == 0 && (int)threadIdx.x < world) st_release_sys(a.flags[threadIdx.x] + a.rank, a.seq);
+  wait_flags(my, world, a.seq, a.timeout);
+
+  const int vcols = (a.cols + 3) >> 2;
+  const long total = (long)a.shard * vcols;
+  const size_t row0 = (size_t)a.rank * a.shard;
+  const long step = (long)gridDim.x * blockDim.x;
+  if (WORLD > 0 && (a.cols & 3) == 0) {
+    for (long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += step * U) {
+      float4 g[U][WORLD > 0 ? WORLD : 1], k[U], w[U];
+      size_t base[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const long i = i0 + u * step;
+        const long ii = i < total ? i : i0;  // clamp: the duplicate's result is not stored
+        base[u] = (row0 + (size_t)(ii / vcols)) * a.stride + ((size_t)(ii % vcols) << 2);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+#pragma unroll
+        for (int r = 0; r < WORLD; r++) g[u][r] = ldg_f4(a.G[r] + base[u]);
+        k[u] = ldg_f4(a.corr + base[u]);
+        w[u] = ldg_f4(a.W[a.rank] + base[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (i0 + u * step >= total) continue;
+        float4 s = g[u][0];
+#pragma unroll
+        for (int r = 1; r < WORLD; r++) { s.x += g[u][r].x; s.y += g[u][r].y; s.z += g[u][r].z; s.w += g[u][r].w; }
+        float4 kk = k[u], ww = w[u];
+        kk.x = s.x + a.mmt * kk.x; kk.y = s.y + a.mmt * kk.y; kk.z = s.z + a.mmt * kk.z; kk.w = s.w + a.mmt * kk.w;
+        ww.x = a.scale * kk.x + ww.x; ww.y = a.scale * kk.y + ww.y; ww.z = a.scale * kk.z + ww.z; ww.w = a.scale * kk.w + ww.w;
+        if (a.l2 != 0.0f) { ww.x = a.l2 * ww.x + ww.x; ww.y = a.l2 * ww.y + ww.y; ww.z = a.l2 * ww.z + ww.z; ww.w = a.l2 * ww.w + ww.w; }
+        *reinterpret_cast<float4 *>(a.corr + base[u]) = kk;
+#pragma unroll
+        for (int r = 0; r < WORLD; r++) *reinterpret_cast<float4 *>(a.W[r] + base[u]) = ww;
+      }
+    }
+  } else {  // any rank count / column count: scalar
+    const long total_s = (long)a.shard * a.cols;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total_s; i += step) {
+      const size_t base = (row0 + (size_t)(i / a.cols)) * a.stride + (size_t)(i % a.cols);
+      float s = a.G[0][base];
+      for (int r = 1; r < world; r++) s += a.G[r][base];
+      const float kk = s + a.mmt * a.corr[base];
+      float ww = a.scale * kk + a.W[a.rank][base];
+      if (a.l2 != 0.0f) ww = a.l2 * ww + ww;
+      a.corr[base] = kk;
+      for (int r = 0; r < world; r++) a.W[r][base] = ww;
+    }
+  }
+  // bias: every rank sums all ranks' bias gradients (row rows_pad of the gradient buffers) in the same order and updates its own copy
+  if (a.bias) {
+    const size_t gb = (size_t)a.rows_pad * a.stride;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.cols; c += (int)step) {
+      float s = a.G[0][gb + c];
+      for (int r = 1; r < world; r++) s += a.G[r][gb + c];
+      const float kk = s + a.mmt * a.corrb[c];
+      a.corrb[c] = kk;
+      a.bias[c] = a.scale * kk + a.bias[c];
+    }
+  }
+
+  // this rank is done when ALL its CTAs are: the last one to arrive publishes the flag and waits for the other ranks
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int last;
+  if (threadIdx.x == 0) last = (atomicAdd(my + 32, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) my[32] = 0;  // for the next launch (which starts after this kernel has ended)
+  __threadfence_system();
+  if ((int)threadIdx.x < world) st_release_sys(a.flags[threadIdx.x] + 16 + a.rank, a.seq);
+  wait_flags(my + 16, world, a.seq, a.timeout);
+}
+
+static int peer_ctas() {
+  // next to the backward GEMMs (128 CTAs that need a whole SM each) only the 20 remaining SMs are free
+  static int n = -1;
+  if (n < 0) { const char *e = getenv("TNB_DP_PEER_CTAS"); n = e ? atoi(e) : 20; if (n < 1) n = 1; }
+  return n;
+}
+static long long peer_timeout_cycles() {
+  static long long t = -1;
+  if (t < 0) { const char *e = getenv("TNB_PEER_TIMEOUT_MS"); t = (long long)(e ? atof(e) : 10000.0) * 2000000LL; }  // ~2 GHz
+  return t;
+}
+
+static int launch_peer_update(TnbContext *ctx, cudaStream_t stream, const TnbPeerJob *job, int rank, int world, unsigned *const *flags,
+                              unsigned seq) {
+  TNB_ARG(ctx && job && flags, "null");
+  TNB_ARG(world >= 1 && world <= TNB_MAX_PEERS && rank >= 0 && rank < world, "rank/world");
+  const TnbMatrixDim d = job->dW;
+  TNB_ARG(d.rows > 0 && d.cols > 0 && d.stride >= d.cols && (d.stride & 3) == 0 && job->n_frames > 0, "dims");
+  TNB_ARG(job->rows_pad >= d.rows && job->rows_pad % world == 0, "rows_pad must be a multiple of the world size, at least dW.rows");
+  TNB_ARG(job->corrW && ((job->bias && job->corrb) || (!job->bias && !job->corrb)), "null");
+  PeerArgs a;
+  memset(&a, 0, sizeof(a));
+  a.rank = rank; a.world = world;
+  for (int r = 0; r < world; r++) {
+    TNB_ARG(job->G[r] && job->W[r] && flags[r], "null peer pointer");
+    TNB_ARG(((uintptr_t)job->G[r] & 15) == 0 && ((uintptr_t)job->W[r] & 15) == 0, "peer buffers must be 16-byte aligned");
+    a.G[r] = job->G[r]; a.W[r] = job->W[r]; a.flags[r] = flags[r];
+  }
+  TNB_ARG(((uintptr_t)job->corrW & 15) == 0, "corrW must be 16-byte aligned");
+  a.corr = job->corrW; a.bias = job->bias; a.corrb = job->corrb;
+  a.cols = d.cols; a.stride = d.stride; a.rows_pad = job->rows_pad; a.shard = job->rows_pad / world;
+  a.mmt = job->mmt;
+  update_scalars(job->lr, job->mmt, job->wc, job->grad_div_frm, job->n_frames, &a.scale, &a.l2);
+  a.seq = seq;
+  a.timeout = peer_timeout_cycles();
+  const long items = (long)a.shard * ((d.cols + 3) / 4);
+  long blocks = (items + 511) / 512;
+  if (blocks > peer_ctas()) blocks = peer_ctas();
+  if (blocks < 1) blocks = 1;
+  const dim3 grid((unsigned)blocks), block(512);
+  switch (world) {
+    case 1: dp_peer_update_kernel<1, 4><<<grid, block, 0, stream>>>(a); break;
+    case 2: dp_peer_update_kernel<2, 4><<<grid, block, 0, stream>>>(a); break;
+    case 4: dp_peer_update_kernel<4, 2><<<grid, block, 0, stream>>>(a); break;
+    case 8: dp_peer_update_kernel<8, 2><<<grid, block, 0, stream>>>(a); break;
+    default: dp_peer_update_kernel<0, 1><<<grid, block, 0, stream>>>(a); break;
+  }
+  TNB_LAUNCHED(ctx);
+  return TNB_OK;
+}
+
+// the per-context flag block, mapped from every rank (collective, first use)
+static int ensure_peer_flags(TnbContext *ctx) {
+  if (ctx->peer_flags[ctx->rank]) return TNB_OK;
+  void *p = nullptr;
+  TNB_CUDA(cudaMalloc(&p, 64 * sizeof(unsigned)));
+  TNB_CUDA(cudaMemset(p, 0, 64 * sizeof(unsigned)));
+  TNB_CUDA(cudaDeviceSynchronize());
+  void *mapped[TNB_MAX_PEERS];
+  int rc = tnb_peer_map(ctx, p, mapped);
+  if (rc != TNB_OK) { cudaFree(p); return rc; }
+  for (int r = 0; r < ctx->world; r++) ctx->peer_flags[r] = (unsigned *)mapped[r];
+  ctx->peer_seq = 0;
+  return TNB_OK;
+}
+
+}  // namespace tnb
+
+using namespace tnb;
+
+extern "C" {
+
+int tnb_peer_map(TnbContext *ctx, void *local, void **mapped) {
+  TNB_ARG(ctx && local && mapped, "null");
+  const int world = ctx->world, rank = ctx->rank;
+  TNB_ARG(world <= TNB_MAX_PEERS, "too many ranks");
+  for (int r = 0; r < world; r++) mapped[r] = nullptr;
+  mapped[rank] = local;
+  if (world == 1) return TNB_OK;
+  TNB_CUDA(cudaSetDevice(ctx->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == TNB_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  std::vector<unsigned char> all((size_t)world * TNB_IPC_HANDLE_BYTES);
+  cudaIpcMemHandle_t h;
+  TNB_CUDA(cudaIpcGetMemHandle(&h, local));
+  memcpy(&all[(size_t)rank * TNB_IPC_HANDLE_BYTES], &h, TNB_IPC_HANDLE_BYTES);
+  int rc = comm_allgather_bytes(ctx, all.data(), TNB_IPC_HANDLE_BYTES);  // the communicator of tnb_comm_init carries the handles
+  if (rc != TNB_OK) return rc;
+  for (int r = 0; r < world; r++) {
+    if (r == rank) continue;
+    cudaIpcMemHandle_t hr;
+    memcpy(&hr, &all[(size_t)r * TNB_IPC_HANDLE_BYTES], TNB_IPC_HANDLE_BYTES);
+    TNB_CUDA(cudaIpcOpenMemHandle(&mapped[r], hr, cudaIpcMemLazyEnablePeerAccess));
+  }
+  return TNB_OK;
+}
+
+int tnb_peer_unmap(TnbContext *ctx, void *const *mapped) {
+  TNB_ARG(ctx && mapped, "null");
+  for (int r = 0; r < ctx->world; r++)
+    if (r != ctx->rank && mapped[r]) cudaIpcCloseMemHandle(mapped[r]);
+  return TNB_OK;
+}
+
+int tnb_dp_peer_update(TnbContext *ctx, const TnbPeerJob *job, void *wait_event, void *done_event) {
+  TNB_ARG(ctx && job, "null");
+  cudaStream_t cs = ctx->world > 1 ? ctx->comm_stream : ctx->main_stream;
+  if (ctx->world > 1) {
+    TNB_ARG(ctx->nccl_comm != nullptr, "communicator not initialised");
+    int rc = ensure_peer_flags(ctx);
+    if (rc != TNB_OK) return rc;
+    TNB_CUDA(cudaEventRecord(ctx->ev_compute, ctx->main_stream));  // the gradient GEMM (and this layer's dX before it) is the producer
+    TNB_CUDA(cudaStreamWaitEvent(cs, ctx->ev_compute, 0));
+    if (wait_event) TNB_CUDA(cudaStreamWaitEvent(cs, (cudaEvent_t)wait_event, 0));
+  } else if (!ctx->peer_flags[0]) {
+    void *p = nullptr;
+    TNB_CUDA(cudaMalloc(&p, 64 * sizeof(unsigned)));
+    TNB_CUDA(cudaMemset(p, 0, 64 * sizeof(unsigned)));
+    ctx->peer_flags[0] = (unsigned *)p;
+    ctx->peer_seq = 0;
+  }
+  int rc = launch_peer_update(ctx, cs, job, ctx->rank, ctx->world, ctx->peer_flags, ++ctx->peer_seq);
+  if (rc != TNB_OK) return rc;
+  if (done_event) TNB_CUDA(cudaEventRecord((cudaEvent_t)done_event, cs));
+  return TNB_OK;
+}
+
+int tnb_dp_peer_update_on(TnbContext *ctx, int stream_id, const TnbPeerJob *job, int rank, int world, unsigned *const *flags, unsigned seq) {
+  TNB_ARG(ctx != nullptr, "null");
+  cudaStream_t s = stream_of(ctx, stream_id);
+  TNB_ARG(s != nullptr, "unknown stream id");
+  return launch_peer_update(ctx, s, job, rank, world, flags, seq);
+}
+
+}  // extern "C"

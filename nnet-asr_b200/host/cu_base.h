@@ -94,9 +94,9 @@ template <typename T> class CuVector;
 template <typename T>
 class CuMatrix {
  public:
-  CuMatrix() : mRows(0), mCols(0), mStride(0), mCap(0), mpCUData(NULL), mpTwin(NULL), mTwinCap(0), mTwinStride(0), mTwinValid(false) {}
+  CuMatrix() : mRows(0), mCols(0), mStride(0), mCap(0), mpCUData(NULL), mpTwin(NULL), mTwinCap(0), mTwinStride(0), mTwinValid(false), mExported(false) {}
   CuMatrix(size_t rows, size_t cols)
-      : mRows(0), mCols(0), mStride(0), mCap(0), mpCUData(NULL), mpTwin(NULL), mTwinCap(0), mTwinStride(0), mTwinValid(false) {
+      : mRows(0), mCols(0), mStride(0), mCap(0), mpCUData(NULL), mpTwin(NULL), mTwinCap(0), mTwinStride(0), mTwinValid(false), mExported(false) {
     Init(rows, cols);
   }
   ~CuMatrix() { Destroy(); }
@@ -136,6 +136,7 @@ class CuMatrix {
     if (stride == 0) stride = 32;
     size_t need = (rows ? rows : 1) * stride;
     if (need > mCap) {
+      if (mExported) Error("CuMatrix::Init would move a buffer that other ranks have mapped (peer-memory data parallel)");
       Destroy();
       void *p = NULL;
       int st = 0;
@@ -154,6 +155,7 @@ class CuMatrix {
   void ReserveRows(size_t rows) {
     const size_t need = rows * mStride;
     if (need <= mCap) return;
+    if (mExported) Error("CuMatrix::ReserveRows would move a buffer that other ranks have mapped (peer-memory data parallel)");
     void *p = NULL;
     int st = 0;
     TNB_CHECK(tnb_malloc_pitch(Cx(), &p, &st, (int)rows, (int)mCols));  // zero-filled
@@ -165,8 +167,12 @@ class CuMatrix {
     mpCUData = (T *)p;
     mCap = need;
   }
+  /// the allocation has been mapped into other processes (tnb_peer_map): freeing it while a peer still has it open is undefined
+  /// (cudaIpcOpenMemHandle), and the peers close at their own pace — it is left to the end of the process instead
+  void MarkExported() { mExported = true; }
   void Destroy() {
-    if (mpCUData) tnb_free(Cx(), mpCUData);
+    if (mpCUData && !mExported) tnb_free(Cx(), mpCUData);
+    mExported = false;
     if (mpTwin) tnb_free(Cx(), mpTwin);
     mpCUData = NULL;
     mpTwin = NULL;
@@ -270,6 +276,7 @@ class CuMatrix {
   mutable uint16_t *mpTwin;
   mutable size_t mTwinCap, mTwinStride;
   mutable bool mTwinValid;
+  bool mExported;
 };
 
 /// Device vector (reference: cuvector.h:14-85)

@@ -143,9 +143,10 @@ class CuBiasedLinearity : public CuUpdatableComponent {
  public:
   CuBiasedLinearity(size_t nInputs, size_t nOutputs, CuComponent *pPred)
       : CuUpdatableComponent(nInputs, nOutputs, pPred), mLinearity(nInputs, nOutputs), mBias(nOutputs),
-        mLinearityCorrection(nInputs, nOutputs), mBiasCorrection(nOutputs), mDpFrames(0), mRowsPad(0), mEvE(NULL), mEvB(NULL), mEvAR(NULL), mEvDone(NULL), mDpPending(false) {}
+        mLinearityCorrection(nInputs, nOutputs), mBiasCorrection(nOutputs), mDpFrames(0), mRowsPad(0), mEvE(NULL), mEvB(NULL), mEvAR(NULL), mEvDone(NULL), mDpPending(false), mPeerMapped(false) {}
   ~CuBiasedLinearity() {
     if (mEvE) { tnb_event_destroy(Cx(), mEvE); tnb_event_destroy(Cx(), mEvB); tnb_event_destroy(Cx(), mEvAR); tnb_event_destroy(Cx(), mEvDone); }
+    if (mPeerMapped) { tnb_peer_unmap(Cx(), mGradPeers); tnb_peer_unmap(Cx(), mWPeers); }
   }
   ComponentType GetType() const { return BIASED_LINEARITY; }
   const char *GetName() const { return "<biasedlinearity>"; }
@@ -280,6 +281,32 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     TNB_CHECK(tnb_event_record(Cx(), mEvDone, TNB_STREAM_AUX2));
     mDpPending = true;
   }
+  /// peer-memory schedule (TNB_DP_MODE=peer): map every rank's gradient buffer and weights into this process.  Collective — every
+  /// rank calls it for its layers in the same order; the buffers must not be reallocated afterwards (Init() with unchanged
+  /// dimensions, CopyFrom() and SetParams() keep them)
+  void PreparePeer() {
+    if (mPeerMapped) return;
+    if (mRowsPad == 0) Error("PreparePeer before PrepareDataParallel");
+    TNB_CHECK(tnb_peer_map(Cx(), mGrad.pCUData(), mGradPeers));
+    TNB_CHECK(tnb_peer_map(Cx(), mLinearity.pCUData(), mWPeers));
+    mGrad.MarkExported();
+    mLinearity.MarkExported();
+    mPeerMapped = true;
+  }
+  /// second half, peer-memory schedule: ONE kernel on the communication stream sums this rank's block of rows over all ranks'
+  /// gradients, updates it and stores the new weights into every rank's matrix (tnb_dp_peer_update)
+  void DataParallelPeerUpdate(int n_frames_global) {
+    if (!mPeerMapped) Error("DataParallelPeerUpdate before PreparePeer");
+    TnbPeerJob j;
+    memset(&j, 0, sizeof(j));
+    for (int r = 0; r < TNB_MAX_PEERS; r++) { j.G[r] = (float *)mGradPeers[r]; j.W[r] = (float *)mWPeers[r]; }
+    (void)mLinearity.pCUData();  // the kernels (this rank's and its peers') rewrite the weights: the bf16 twin goes stale
+    j.corrW = mLinearityCorrection.pCUData(); j.bias = mBias.pCUData(); j.corrb = mBiasCorrection.pCUData();
+    j.dW = mLinearity.Dim(); j.rows_pad = (int)mRowsPad;
+    j.lr = mLearningRate; j.mmt = mMomentum; j.wc = mWeightcost; j.grad_div_frm = mGradDivFrm ? 1 : 0; j.n_frames = n_frames_global;
+    TNB_CHECK(tnb_dp_peer_update(Cx(), &j, mEvB, mEvDone));
+    mDpPending = true;
+  }
   /// pieces of the second half for a GROUP of layers exchanged in one NCCL launch (CuNetwork's deferred layers)
   void *BiasGradientEvent() { return mEvB; }
   void MarkDataParallelUpdateEnqueued() {  // the group's batched update has just been enqueued on the update stream
@@ -356,6 +383,8 @@ class CuBiasedLinearity : public CuUpdatableComponent {
   size_t mRowsPad;
   void *mEvE, *mEvB, *mEvAR, *mEvDone;  ///< data-parallel stream ordering (created on first use)
   mutable bool mDpPending;              ///< an update of this layer is in flight on the side streams
+  bool mPeerMapped;                     ///< peer-memory schedule: the tables below are filled
+  void *mGradPeers[TNB_MAX_PEERS], *mWPeers[TNB_MAX_PEERS];  ///< every rank's mGrad / mLinearity as mapped into this process
 };
 
 // =====================================================================================================
@@ -784,12 +813,12 @@ inline CuObjectiveFunction *CuObjectiveFunction::Factory(ObjFunType type) {
 class CuNetwork {
   typedef std::vector<CuComponent *> LayeredType;
  public:
-  CuNetwork() : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mEvGroup(NULL), mDpGroup(false), mBwdStreams(BwdStreamsDefault()), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false) {
+  CuNetwork() : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mEvGroup(NULL), mDpGroup(false), mBwdStreams(BwdStreamsDefault()), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false), mDpPeer(false) {
     const char *e = getenv("TNB_FUSE");
     if (e && atoi(e) == 0) mFuse = false;
   }
   explicit CuNetwork(std::istream &rIn)
-      : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mEvGroup(NULL), mDpGroup(false), mBwdStreams(BwdStreamsDefault()), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false) {
+      : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mEvGroup(NULL), mDpGroup(false), mBwdStreams(BwdStreamsDefault()), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false), mDpPeer(false) {
     ReadNetwork(rIn);
   }
   ~CuNetwork() {
@@ -821,6 +850,7 @@ class CuNetwork {
     mWorld = world;
     const char *e = getenv("TNB_DP_MODE");
     mDpShard = e && !strcmp(e, "shard");
+    mDpPeer = e && !strcmp(e, "peer") && world > 1;  // all-reduce schedule with the NCCL call + update kernel replaced by one peer-memory kernel
     // default: with L >= 6 updatable layers the top one and the bottom two exchange at once, the middle ones late (measured on
     // 2 B200, config C, ms per bunch: no deferral 1.311, 1:5 1.244, 2:5 1.261, 3:5 1.288, 2:6 1.305);
     // TNB_DP_DEFER=begin:end overrides (0:0 = plain top-to-bottom order)
@@ -838,6 +868,9 @@ class CuNetwork {
     if (d) { int a = 0, b = 0; if (sscanf(d, "%d:%d", &a, &b) == 2) { mDpDeferBegin = a; mDpDeferEnd = b; } }
     for (size_t i = 0; i < mNetComponents.size(); i++)
       if (mNetComponents[i]->GetType() == CuComponent::BIASED_LINEARITY) static_cast<CuBiasedLinearity *>(mNetComponents[i])->PrepareDataParallel(world);
+    if (mDpPeer)
+      for (size_t i = 0; i < mNetComponents.size(); i++)
+        if (mNetComponents[i]->GetType() == CuComponent::BIASED_LINEARITY) static_cast<CuBiasedLinearity *>(mNetComponents[i])->PreparePeer();
   }
 
   /// forward the data to the output (cuNetwork.h:137-165)
@@ -912,6 +945,7 @@ class CuNetwork {
               lin->DataParallelGradient();
               const int k = (int)pending.size();
               if (k >= mDpDeferBegin && k < mDpDeferEnd) deferred.push_back(lin);
+              else if (mDpPeer) lin->DataParallelPeerUpdate((int)lin->GetInput().Rows() * mWorld);
               else lin->DataParallelReduceUpdate((int)lin->GetInput().Rows() * mWorld);
             }
             pending.push_back(lin);
@@ -943,7 +977,9 @@ class CuNetwork {
     for (size_t k = 0; k < side_done.size(); k++) TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_COMPUTE, side_done[k]));
     for (size_t k = 0; k < bias_jobs.size(); k += TNB_MAX_BIAS_JOBS)
       TNB_CHECK(tnb_bias_update_batch(Cx(), &bias_jobs[k], (int)std::min<size_t>(TNB_MAX_BIAS_JOBS, bias_jobs.size() - k)));
-    if (!mDpGroup) {
+    if (mDpPeer) {
+      for (size_t k = deferred.size(); k-- > 0;) deferred[k]->DataParallelPeerUpdate((int)deferred[k]->GetInput().Rows() * mWorld);
+    } else if (!mDpGroup) {
       for (size_t k = deferred.size(); k-- > 0;)  // bottom-most deferred layer first: the order the next forward pass needs them
         deferred[k]->DataParallelReduceUpdate((int)deferred[k]->GetInput().Rows() * mWorld);
     } else if (!deferred.empty()) {
@@ -1085,6 +1121,7 @@ class CuNetwork {
   int mBwdStreams;                 ///< fused single-GPU schedule: 2 = weight-gradient GEMMs on a side stream (TNB_BWD_STREAMS)
   int mDpDeferBegin, mDpDeferEnd;  ///< all-reduce schedule: updatable layers [begin, end), counted from the top, exchange late
   bool mDpShard;  ///< data-parallel schedule: false = all-reduce + batched update (default), true = tnb_dp_update (TNB_DP_MODE=shard)
+  bool mDpPeer;   ///< TNB_DP_MODE=peer: the all-reduce schedule's order with one peer-memory kernel per layer (tnb_dp_peer_update)
 };
 
 // =====================================================================================================

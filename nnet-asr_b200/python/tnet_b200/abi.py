@@ -26,6 +26,16 @@ class ObjStats(C.Structure):
     _fields_ = [("error", C.c_double), ("frames", C.c_longlong), ("correct", C.c_longlong)]
 
 
+MAX_PEERS = 16
+
+
+class PeerJob(C.Structure):
+    """TnbPeerJob of include/tnet_b200.h (one layer's update over peer memory)."""
+    _fields_ = [("G", C.c_void_p * MAX_PEERS), ("W", C.c_void_p * MAX_PEERS), ("corrW", C.c_void_p), ("bias", C.c_void_p),
+                ("corrb", C.c_void_p), ("dW", MatrixDim), ("rows_pad", C.c_int), ("lr", C.c_float), ("mmt", C.c_float),
+                ("wc", C.c_float), ("grad_div_frm", C.c_int), ("n_frames", C.c_int)]
+
+
 class TnbError(RuntimeError):
     pass
 

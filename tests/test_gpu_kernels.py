@@ -217,6 +217,95 @@ def test_affine_grad_plus_sgd_update_equals_fused(ctx):
     np.testing.assert_allclose(c1.download(), c2.download(), rtol=1e-6, atol=1e-7)
 
 
+def _update_scalars(lr, mmt, wc, gdf, rows):
+    """update_scalars() of csrc/elementwise.cu = the float arithmetic of cuBiasedLinearity.cc:44-63"""
+    f = np.float32
+    N = f(rows) if gdf else f(1)
+    N = f(N * f(1.0 / (1.0 - float(f(mmt)))))
+    return f(-f(lr) / N), f(-float(f(lr)) * float(f(wc)) * (1.0 if gdf else rows))
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("rows,cols", [(100, 260), (37, 135)])
+def test_peer_update_kernel_virtual_ranks(ctx, world, rows, cols):
+    """csrc/peer.cu on ONE GPU: `world` virtual ranks (one context = one stream each, own gradient / weight / momentum / flag
+    buffers) run the fused reduce-scatter + update + all-gather kernel concurrently, twice (sequence numbers 1, 2).  Every rank's
+    weights must be the update from the rank-ordered sum of all gradients, identical bit for bit across the ranks; a rank's momentum
+    buffer changes only in its own block of rows.  world 3 takes the generic kernel, 135 columns the scalar path."""
+    r = rng(100 + world)
+    rows_pad = ((rows + world - 1) // world) * world
+    shard = rows_pad // world
+    lr, mmt, wc, gdf, frames = 0.3, 0.5, 1e-3, 1, 64 * world
+    scale, l2 = _update_scalars(lr, mmt, wc, gdf, frames)
+    W0 = np.zeros((rows_pad, cols), np.float32)
+    W0[:rows] = 0.1 * r.standard_normal((rows, cols))
+    K0 = np.zeros_like(W0)
+    K0[:rows] = 0.01 * r.standard_normal((rows, cols))
+    b0 = r.standard_normal(cols).astype(np.float32)
+    kb0 = (0.01 * r.standard_normal(cols)).astype(np.float32)
+    ctxs = [abi.Context(0) for _ in range(world)]
+    Wd = Kd = bd = kbd = Gd = flags = []
+    try:
+        Wd = [abi.DMat.from_numpy(c, W0) for c in ctxs]
+        Kd = [abi.DMat.from_numpy(c, K0) for c in ctxs]
+        bd = [abi.DMat.from_numpy(c, b0) for c in ctxs]
+        kbd = [abi.DMat.from_numpy(c, kb0) for c in ctxs]
+        Gd = [abi.DMat(c, rows_pad + 1, cols) for c in ctxs]
+        flags = [abi.DMat(c, 1, 64, np.uint32) for c in ctxs]          # zero-filled by tnb_malloc_pitch
+        fl = (C.POINTER(C.c_uint) * world)(*[f.p(C.c_uint) for f in flags])
+        Wref, Kref, bref, kbref = W0.copy(), K0.copy(), b0.copy(), kb0.copy()
+        for seq in (1, 2):
+            Gs = []
+            for k in range(world):
+                G = np.zeros((rows_pad + 1, cols), np.float32)
+                G[:rows] = r.standard_normal((rows, cols))
+                G[rows_pad] = r.standard_normal(cols)
+                Gd[k].upload(G)
+                Gs.append(G)
+            for k in range(world):
+                job = abi.PeerJob()
+                for q in range(world):
+                    job.G[q] = Gd[q].ptr.value
+                    job.W[q] = Wd[q].ptr.value
+                job.corrW, job.bias, job.corrb = Kd[k].ptr.value, bd[k].ptr.value, kbd[k].ptr.value
+                job.dW = abi.MatrixDim(rows, cols, Wd[k].stride)
+                job.rows_pad, job.lr, job.mmt, job.wc, job.grad_div_frm, job.n_frames = rows_pad, lr, mmt, wc, gdf, frames
+                abi.check(L.tnb_dp_peer_update_on(ctxs[k].h, C.c_int(0), C.byref(job), C.c_int(k), C.c_int(world), fl, C.c_uint(seq)))
+            for c in ctxs:
+                c.sync()
+            g = Gs[0].copy()
+            for k in range(1, world):
+                g = g + Gs[k]                                            # rank order, float32
+            Kref = (g[:rows_pad] + np.float32(mmt) * Kref).astype(np.float32)
+            Wref = (scale * Kref + Wref).astype(np.float32)
+            Wref = (l2 * Wref + Wref).astype(np.float32)
+            kbref = (g[rows_pad] + np.float32(mmt) * kbref).astype(np.float32)
+            bref = (scale * kbref + bref).astype(np.float32)
+            got = [w.download() for w in Wd]
+            for k in range(1, world):
+                assert np.array_equal(got[k], got[0]), "ranks hold different weights"
+            # fused multiply-adds on the device against separately rounded numpy operations
+            np.testing.assert_allclose(got[0], Wref, rtol=2e-6, atol=2e-7)
+            assert not got[0][rows:].any()
+            for k in range(world):
+                kk = Kd[k].download()
+                blk = slice(k * shard, (k + 1) * shard)
+                np.testing.assert_allclose(kk[blk], Kref[blk], rtol=2e-6, atol=2e-7)
+                np.testing.assert_allclose(bd[k].download()[0], bref, rtol=2e-6, atol=2e-6)
+                np.testing.assert_allclose(kbd[k].download()[0], kbref, rtol=2e-6, atol=2e-6)
+                f = flags[k].download()[0]
+                assert (f[:world] == seq).all() and (f[16:16 + world] == seq).all() and f[32] == 0
+        # a rank's momentum buffer outside its own block is untouched (the peers own those rows)
+        if world > 1:
+            kk = Kd[0].download()
+            assert np.array_equal(kk[shard:], K0[shard:])
+    finally:
+        for m in Wd + Kd + bd + kbd + Gd + flags:
+            m.free()
+        for c in ctxs:
+            c.close()
+
+
 # ------------------------------------------------------------------------------------------------ elementwise
 def _mat(ctx, a):
     return abi.DMat.from_numpy(ctx, a)

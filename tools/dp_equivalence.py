@@ -36,7 +36,8 @@ lab = r.integers(0, dims[-1], (steps, B)).astype(np.int32)
 T = np.zeros((steps, B, dims[-1]), np.float32)
 for s in range(steps):
     T[s, np.arange(B), lab[s]] = 1
-for mode in ("allreduce", "shard"):      # both data-parallel schedules of CuNetwork::Backpropagate (TNB_DP_MODE)
+modes = os.environ.get("DP_EQUIV_MODES", "allreduce,shard,peer").split(",")
+for mode in modes:      # the data-parallel schedules of CuNetwork::Backpropagate (TNB_DP_MODE); "peer" = csrc/peer.cu, no NCCL on the data path
     for mname, math in (("3xtf32", abi.MATH_3XTF32), ("bf16", abi.MATH_BF16)):
         os.environ["TNB_DP_MODE"] = mode
         host.set_math(math)
