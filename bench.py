@@ -331,7 +331,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"3xtf32": "tf32x3", "tf32": "tf32", "bf16": "bf16"}[args.math], "data": "synthetic",
             "config": {"workload": WORKLOAD, "dims": DIMS, "bunch_per_gpu": BUNCH, "global_bunch": BUNCH * world,
-                       "parallelism": "dp%d" % world, "learn_rate": LR, "momentum": MMT, "weightcost": WC,
+                       "parallelism": "dp%d" % world, "dp_schedule": (os.environ.get("TNB_DP_MODE", "peer") if world > 1 else "none"), "learn_rate": LR, "momentum": MMT, "weightcost": WC,
                        "l2_note": "no L2 flush: weights+corrections (224 MB) and activations exceed the 126 MB L2 every step",
                        "flops_per_frame": fpf, "gemm_math": args.math},
             "clocks": clocks,

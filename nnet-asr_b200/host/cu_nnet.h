@@ -850,7 +850,11 @@ class CuNetwork {
     mWorld = world;
     const char *e = getenv("TNB_DP_MODE");
     mDpShard = e && !strcmp(e, "shard");
-    mDpPeer = e && !strcmp(e, "peer") && world > 1;  // all-reduce schedule with the NCCL call + update kernel replaced by one peer-memory kernel
+    // default with more than one rank: the all-reduce schedule's order with the NCCL call + update kernel of every layer replaced by
+    // ONE peer-memory kernel (csrc/peer.cu).  Measured on config C, ms per bunch: 2 B200 1.081 against 1.262 with NCCL all-reduce,
+    // 8 B200 1.152 against 1.493.  TNB_DP_MODE=allreduce|shard select the NCCL schedules.
+    mDpPeer = world > 1 && (!e || !strcmp(e, "peer"));
+    if (e && strcmp(e, "peer") && strcmp(e, "shard") && strcmp(e, "allreduce")) Error(std::string("TNB_DP_MODE must be peer, allreduce or shard, not ") + e);
     // default: with L >= 6 updatable layers the top one and the bottom two exchange at once, the middle ones late (measured on
     // 2 B200, config C, ms per bunch: no deferral 1.311, 1:5 1.244, 2:5 1.261, 3:5 1.288, 2:6 1.305);
     // TNB_DP_DEFER=begin:end overrides (0:0 = plain top-to-bottom order)
@@ -1120,8 +1124,8 @@ class CuNetwork {
   bool mDpGroup;                   ///< deferred layers in one NCCL launch (TNB_DP_GROUP=1; measured slower, off by default)
   int mBwdStreams;                 ///< fused single-GPU schedule: 2 = weight-gradient GEMMs on a side stream (TNB_BWD_STREAMS)
   int mDpDeferBegin, mDpDeferEnd;  ///< all-reduce schedule: updatable layers [begin, end), counted from the top, exchange late
-  bool mDpShard;  ///< data-parallel schedule: false = all-reduce + batched update (default), true = tnb_dp_update (TNB_DP_MODE=shard)
-  bool mDpPeer;   ///< TNB_DP_MODE=peer: the all-reduce schedule's order with one peer-memory kernel per layer (tnb_dp_peer_update)
+  bool mDpShard;  ///< TNB_DP_MODE=shard: reduce-scatter / block update / all-gather per layer with NCCL (tnb_dp_update)
+  bool mDpPeer;   ///< default with several ranks: one peer-memory kernel per layer (tnb_dp_peer_update); both false = NCCL all-reduce + update
 };
 
 // =====================================================================================================

@@ -77,6 +77,7 @@ sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
 import oracle_lib as O
 from tnet_b200 import formats as F
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+schedule = sys.argv[3]
 dist.init_process_group("gloo")
 r = np.random.default_rng(5)
 dims, B = [20, 16, 7], 64
@@ -102,12 +103,39 @@ for step in range(2):
     grads = [(O.gemm("T", "N", 1.0, Xl, e1, 0.0, np.zeros_like(W[0]), 1), e1.astype(np.float64).sum(0).astype(np.float32)),
              (O.gemm("T", "N", 1.0, h, e2, 0.0, np.zeros_like(W[1]), 1), e2.astype(np.float64).sum(0).astype(np.float32))]
     for k, (gW, gb) in enumerate(grads):
-        tW, tb = torch.from_numpy(gW.copy()), torch.from_numpy(gb.copy())
-        dist.all_reduce(tW); dist.all_reduce(tb)
         N = np.float32(B) * np.float32(1.0 / (1.0 - mmt))
-        cW[k] = tW.numpy() + np.float32(mmt) * cW[k]; cb[k] = tb.numpy() + np.float32(mmt) * cb[k]
-        W[k] = W[k] + np.float32(-lr / N) * cW[k]; b[k] = b[k] + np.float32(-lr / N) * cb[k]
-        W[k] = W[k] + np.float32(-lr * wc) * W[k]
+        if schedule == "allreduce":      # NCCL schedule: sum everywhere, every rank updates everything
+            tW, tb = torch.from_numpy(gW.copy()), torch.from_numpy(gb.copy())
+            dist.all_reduce(tW); dist.all_reduce(tb)
+            cW[k] = tW.numpy() + np.float32(mmt) * cW[k]; cb[k] = tb.numpy() + np.float32(mmt) * cb[k]
+            W[k] = W[k] + np.float32(-lr / N) * cW[k]; b[k] = b[k] + np.float32(-lr / N) * cb[k]
+            W[k] = W[k] + np.float32(-lr * wc) * W[k]
+        else:
+            # peer-memory schedule (csrc/peer.cu): rank r owns rows [r*shard, (r+1)*shard) of the zero-padded matrix; it reads that
+            # block of EVERY rank's gradient (all_gather stands in for the peer loads), sums in rank order, updates its block of
+            # corrW and W, and stores the new rows into every rank's W (all_gather of the blocks = the peer stores).  The bias row
+            # is summed in rank order and updated by every rank for itself.
+            nin = gW.shape[0]; pad = -(-nin // world) * world; shard = pad // world
+            Gp = np.zeros((pad, gW.shape[1]), np.float32); Gp[:nin] = gW
+            allG = [torch.zeros(Gp.shape) for _ in range(world)]; dist.all_gather(allG, torch.from_numpy(Gp))
+            allb = [torch.zeros(gb.shape) for _ in range(world)]; dist.all_gather(allb, torch.from_numpy(gb.copy()))
+            blk = slice(rank * shard, (rank + 1) * shard)
+            g = allG[0].numpy()[blk].copy()
+            for q in range(1, world):
+                g = g + allG[q].numpy()[blk]
+            Wp = np.zeros((pad, gW.shape[1]), np.float32); Wp[:nin] = W[k]
+            Kp = np.zeros_like(Wp); Kp[:nin] = cW[k]
+            Kp[blk] = g + np.float32(mmt) * Kp[blk]
+            wnew = Wp[blk] + np.float32(-lr / N) * Kp[blk]
+            wnew = wnew + np.float32(-lr * wc) * wnew
+            blocks = [torch.zeros(wnew.shape) for _ in range(world)]; dist.all_gather(blocks, torch.from_numpy(wnew.astype(np.float32)))
+            W[k] = np.concatenate([t.numpy() for t in blocks])[:nin]
+            cW[k] = Kp[:nin]                 # only this rank's block is current — exactly what the kernel leaves behind
+            sb = allb[0].numpy().copy()
+            for q in range(1, world):
+                sb = sb + allb[q].numpy()
+            cb[k] = sb + np.float32(mmt) * cb[k]
+            b[k] = b[k] + np.float32(-lr / N) * cb[k]
 if rank == 0:
     ref = O.Net(layers, acc_double=1); ref.set_hyper(lr, mmt=mmt, wc=wc, gdf=True)
     ref.train_bunch(X, T); ref.train_bunch(X, T)
@@ -120,15 +148,17 @@ dist.destroy_process_group()
 """
 
 
-def test_data_parallel_arithmetic_two_gloo_ranks(tmp_path):
-    """N>1 semantics on CPU: rows of the bunch split over 2 ranks, per-layer gradient all-reduce (gloo), update with the
-    GLOBAL frame count == the single-process oracle on the whole bunch."""
+@pytest.mark.parametrize("schedule,port", [("allreduce", 29517), ("peer", 29518)])
+def test_data_parallel_arithmetic_two_gloo_ranks(tmp_path, schedule, port):
+    """N>1 semantics on CPU: rows of the bunch split over 2 ranks, then either the per-layer gradient all-reduce + full update (the
+    NCCL schedule) or the peer-memory schedule's block-owner arithmetic (rank-ordered sum of the owner's rows, block update, rows
+    handed to every rank), both with the GLOBAL frame count == the single-process oracle on the whole bunch."""
     script = tmp_path / "dp_worker.py"
     script.write_text(DP_WORKER)
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29517", OMP_NUM_THREADS="1")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29517", str(script), os.path.join(ROOT, "tests"), os.path.join(ROOT, "nnet-asr_b200", "python")],
-                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=300)
+                        "--master-port", str(port), str(script), os.path.join(ROOT, "tests"), os.path.join(ROOT, "nnet-asr_b200", "python"),
+                        schedule], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "DP_OK" in r.stdout, r.stdout[-3000:]
 
 
