@@ -11,7 +11,8 @@
 //     sigmoid, writing the sigmoid component's output directly (the affine pre-activation is never materialised);
 //   * dX of an affine layer whose predecessor is a <sigmoid> multiplies by y(1-y) in the GEMM epilogue;
 //   * the weight gradient GEMM applies momentum / learning rate / L2 in its epilogue (single GPU), or is followed by
-//     an NCCL all-reduce and a fused update kernel (data parallel);
+//     one kernel that sums the ranks' gradients over NVLink peer memory, updates this rank's rows and hands them to every
+//     rank (data parallel; NCCL all-reduce / reduce-scatter schedules selectable);
 //   * <softmax>'s identity backward copy and the output copy of Propagate() are pointer re-wiring, not copies;
 //   * Xent / correct / frames accumulate on the device and are read when Report()/GetError() is called.
 // SetFusion(false) (or TNB_FUSE=0) restores the component-by-component traversal for debugging and parity tests.
@@ -845,7 +846,7 @@ class CuNetwork {
     for (size_t i = 0; i < mNetComponents.size(); i++)
       if (mNetComponents[i]->GetType() == CuComponent::BIASED_LINEARITY) static_cast<CuBiasedLinearity *>(mNetComponents[i])->WaitDataParallel();
   }
-  /// data parallel over `world` ranks: Update() becomes gradient -> all-reduce -> apply (N uses rows*world)
+  /// data parallel over `world` ranks: Update() becomes gradient -> exchange -> apply (N uses rows*world)
   void SetDataParallel(int world) {
     mWorld = world;
     const char *e = getenv("TNB_DP_MODE");
@@ -1123,7 +1124,7 @@ class CuNetwork {
   void *mEvGroup;                  ///< data parallel: behind the grouped all-reduce of the deferred layers
   bool mDpGroup;                   ///< deferred layers in one NCCL launch (TNB_DP_GROUP=1; measured slower, off by default)
   int mBwdStreams;                 ///< fused single-GPU schedule: 2 = weight-gradient GEMMs on a side stream (TNB_BWD_STREAMS)
-  int mDpDeferBegin, mDpDeferEnd;  ///< all-reduce schedule: updatable layers [begin, end), counted from the top, exchange late
+  int mDpDeferBegin, mDpDeferEnd;  ///< peer-memory and all-reduce schedules: updatable layers [begin, end), counted from the top, exchange late
   bool mDpShard;  ///< TNB_DP_MODE=shard: reduce-scatter / block update / all-gather per layer with NCCL (tnb_dp_update)
   bool mDpPeer;   ///< default with several ranks: one peer-memory kernel per layer (tnb_dp_peer_update); both false = NCCL all-reduce + update
 };

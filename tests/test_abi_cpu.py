@@ -44,3 +44,17 @@ def test_matrixdim_layout_matches_reference():
     assert C.sizeof(abi.MatrixDim) == 12
     assert [f[0] for f in abi.MatrixDim._fields_] == ["rows", "cols", "stride"]
     assert C.sizeof(abi.ObjStats) == 24
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of the structs passed by pointer have the C compiler's layout of include/tnet_b200.h."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "tnet_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(TnbPeerJob), offsetof(TnbPeerJob, W), offsetof(TnbPeerJob, dW),'
+                   ' offsetof(TnbPeerJob, n_frames), sizeof(TnbObjStats));return 0;}\n')
+    exe = str(tmp_path / "sz")
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", exe])
+    got = [int(v) for v in subprocess.check_output([exe], text=True).split()]
+    P = abi.PeerJob
+    assert got == [C.sizeof(P), P.W.offset, P.dW.offset, P.n_frames.offset, C.sizeof(abi.ObjStats)]

@@ -53,7 +53,7 @@ def test_oracle_rnn_vs_reference_trecurrentcu():
         rnn.clear()
         for t in range(x.shape[0]):
             h = rnn.propagate(x[t]).reshape(1, H)
-            a = np.empty((1, n_out), np.float32)
+            a = np.zeros((1, n_out), np.float32)     # Init()-zeroed like the component's output: the bias pre-copy computes 0*old
             O.lib.orc_affine_fwd(O.P(h), H, O.P(W), n_out, O.P(bo), O.P(a), n_out, 1, H, n_out, 0)
             y = O.softmax(a)
             tgt = np.zeros((1, n_out), np.float32); tgt[0, lab[t]] = 1

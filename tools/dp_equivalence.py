@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Run under torchrun with WORLD_SIZE ranks (one per GPU): the data-parallel CUDA path (rows of every bunch split over the
-ranks, per-layer NCCL all-reduce of [dW;db], update with the global frame count) must reproduce the single-GPU run of the
-full bunch.  Rank 0 prints DP_EQUIV_OK."""
+ranks, per-layer exchange of [dW;db] — peer-memory kernel, NCCL all-reduce or NCCL reduce-scatter/all-gather — and update with
+the global frame count) must reproduce the single-GPU run of the full bunch.  Rank 0 prints DP_EQUIV_OK.
+DP_EQUIV_MODES=peer,allreduce,shard selects the schedules (default: all three)."""
 import ctypes as C
 import os
 import sys
