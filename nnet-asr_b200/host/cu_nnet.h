@@ -848,6 +848,12 @@ class CuNetwork {
   }
   /// data parallel over `world` ranks: Update() becomes gradient -> exchange -> apply (N uses rows*world)
   void SetDataParallel(int world) {
+    // only <biasedlinearity> has a gradient exchange; any other trainable layer would silently train on its rank's rows alone
+    if (world > 1)
+      for (size_t i = 0; i < mNetComponents.size(); i++)
+        if (mNetComponents[i]->IsUpdatable() && mNetComponents[i]->GetType() != CuComponent::BIASED_LINEARITY)
+          Error(std::string("data-parallel training exchanges the gradients of <biasedlinearity> layers only; the network contains ") +
+                mNetComponents[i]->GetName());
     mWorld = world;
     const char *e = getenv("TNB_DP_MODE");
     mDpShard = e && !strcmp(e, "shard");

@@ -199,6 +199,16 @@ def test_offset_gemm_layers_reader_errors(tmp_path):
             host.Net(path=bad)
 
 
+def test_data_parallel_rejects_layers_without_gradient_exchange():
+    """Only <biasedlinearity> gradients are exchanged between ranks: a network with another trainable layer must be refused in
+    data-parallel mode instead of training every rank on its own rows."""
+    r = np.random.default_rng(1)
+    net = host.Net(_offset_nets(r)["shared_unaligned"])
+    with pytest.raises(abi.TnbError, match="sharedlinearity"):
+        net.set_data_parallel(2)
+    net.set_data_parallel(1)
+
+
 def test_rbm_sparse_cd1_vs_oracle():
     """<rbmsparse> (cuRbmSparse.cc:125-168): CD-1 with the sparsity penalty over a few bunches against the oracle's restatement —
     same Hybrid-Taus states (seeded from the same lrand48 stream), so the Bernoulli samples are bit-identical and the weights
