@@ -301,12 +301,19 @@ def main():
     # One submission is kept in flight: submit bunch k+1 (H2D on the copy stream, step behind it), then collect bunch k (blocks
     # until ITS statistics have been copied back).  Every step's input crosses PCIe inside the timed region and every step's
     # result is read by the host; the copy of bunch k+1 overlaps the step of bunch k, as a loader thread would arrange it.
+    host_t = {"submit": 0.0, "collect": 0.0}   # host time inside the two calls (diagnostic: enqueue cost vs waiting for the GPU)
+
     def e2e_run(n):
         st = None
+        host_t["submit"] = host_t["collect"] = 0.0
         net.submit_bunch_labels(xp, lp, BUNCH)
         for _ in range(n - 1):
+            ta = time.perf_counter()
             net.submit_bunch_labels(xp, lp, BUNCH)
+            tb = time.perf_counter()
             st = net.collect()
+            host_t["submit"] += tb - ta
+            host_t["collect"] += time.perf_counter() - tb
         return net.collect()
 
     e2e_run(3)
@@ -336,7 +343,10 @@ def main():
                        "flops_per_frame": fpf, "gemm_math": args.math},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": BUNCH * DIMS[0] * 4 + BUNCH * 4,
-                    "d2h_bytes_per_step": 24},
+                    "d2h_bytes_per_step": 24,
+                    # rank 0's host time per step inside the two calls: enqueueing a step vs waiting for the previous one's statistics
+                    "host_ms_per_step": {"submit": 1000.0 * host_t["submit"] / max(1, args.steps - 1),
+                                         "collect_wait": 1000.0 * host_t["collect"] / max(1, args.steps - 1)}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": gemm_tflops / pk["bf16_sustained"],
