@@ -43,6 +43,14 @@ MLP_CASES = {
                          lr=1.0, mmt=0.9, wc=0.0, gdf=True, seed=5, randomize=True),
 }
 GPU_ONLY = {"mlp_mmt_wide", "mlp_bigbunch"}
+# option cases (fixtures *_opt_*): per-layer learning-rate factors with a frozen first layer (the backpropagation stopper moves up,
+# cuNetwork.cc:80-135) and cross-validation (forward + objective only, nothing written, TNetCu.cc:437-466 / TNet.cc:344)
+OPT_CASES = {
+    "opt_lrfactors": dict(raw_dim=13, ctx=2, hidden=[24, 20], n_out=12, n_utt=16, n_frames=80, bunch=32, cache=256,
+                          lr=0.01, mmt=0.0, wc=0.0, gdf=False, seed=71, randomize=True, factors="0:1:0.5"),
+    "opt_cv": dict(raw_dim=13, ctx=2, hidden=[24], n_out=12, n_utt=16, n_frames=80, bunch=32, cache=256,
+                   lr=0.01, mmt=0.0, wc=0.0, gdf=False, seed=72, randomize=False, cv=True),
+}
 
 
 def _b(v):
@@ -88,15 +96,25 @@ def run_mlp(case, cfg, impl, workdir, exe=None, save=True):
         cmd += ["--THREADS=1"]
     else:
         cmd += ["--MOMENTUM=" + repr(cfg["mmt"]), "--GRADDIVFRM=" + _b(cfg["gdf"])]
+    if cfg.get("factors"):
+        cmd += ["--LEARNRATEFACTORS=" + cfg["factors"]]
+    if cfg.get("cv"):
+        cmd += ["--CROSSVALIDATE=TRUE"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("reference failed:\n" + res.stdout[-3000:])
     rep = parse_report(res.stdout)
-    out_layers = F.read_mlp(final)
+    if cfg.get("cv"):
+        assert not os.path.exists(final), "a cross-validation run must not write a network"
+        out_layers = layers          # nothing is trained: the fixture's "final" network is the initial one
+    else:
+        out_layers = F.read_mlp(final)
     if not save:
         return rep, out_layers, res.stdout
     names = list(utts.keys())
     data = dict(
+        lr_factors=np.array([float(v) for v in cfg["factors"].split(":")] if cfg.get("factors") else [], dtype=np.float64),
+        cv=np.int64(1 if cfg.get("cv") else 0),
         feats=np.concatenate([utts[n][0] for n in names]), labels=np.concatenate([utts[n][1] for n in names]),
         lengths=np.array([utts[n][0].shape[0] for n in names], dtype=np.int32),
         dims=np.array(dims, dtype=np.int32),
@@ -360,6 +378,10 @@ def main():
             continue
         with tempfile.TemporaryDirectory() as d:
             run_mlp(case, cfg, a.impl, d)
+    for case, cfg in OPT_CASES.items():
+        if want(case) and not (a.impl == "cpu" and cfg.get("factors")):   # the CPU trainer advertises LEARNRATEFACTORS but rejects it
+            with tempfile.TemporaryDirectory() as d:
+                run_mlp(case, cfg, a.impl, d)
     for case, cfg in NET_CASES.items():
         if (a.impl == "cpu" and case in NET_GPU_ONLY) or not want(case):
             continue

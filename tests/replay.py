@@ -57,7 +57,10 @@ def replay_mlp(g, make_net, make_cache, srand48, cv=False):
     ctx, bunch, cache, seed, randomize, gdf = [int(v) for v in g["cfg"]]
     lr, mmt, wc = [float(v) for v in g["hyper"]]
     net = make_net(fixture_layers(g))
-    net.set_hyper(lr, mmt=mmt, wc=wc, gdf=bool(gdf))
+    factors = [float(v) for v in g["lr_factors"]] if "lr_factors" in g and len(g["lr_factors"]) else None
+    net.set_hyper(lr, mmt=mmt, wc=wc, gdf=bool(gdf), factors=factors)
+    if "cv" in g and int(g["cv"]):
+        cv = True
     srand48(seed)
     cache = (cache // bunch) * bunch
     c = make_cache(cache, bunch)

@@ -121,6 +121,25 @@ def test_offset_gemm_layers_epoch_matches_reference_trainers(path, fusion):
         compare_layer(a, b, 2e-4, btol_floor=1e-2)
 
 
+OPT_GOLD = sorted(glob.glob(os.path.join(GOLD, "*_opt_*.npz")))
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round-1 GPU budget was spent: not yet run on a B200")
+@pytest.mark.parametrize("path", OPT_GOLD, ids=[os.path.basename(p)[:-4] for p in OPT_GOLD])
+def test_option_fixtures_match_reference_trainers(path):
+    """Cross-validation (no update, network untouched) and per-layer learning-rate factors with a frozen first layer, against the
+    reference trainers' reports and written networks."""
+    g = np.load(path)
+    host.set_math(abi.MATH_3XTF32)
+    net, nb, perms = replay_mlp(g, lambda L: host.Net(L), host.Cache, _srand_both)
+    err, frames, correct = net.stats()
+    assert frames == int(g["ref_frames"])
+    assert abs(err - float(g["ref_err"])) <= 1e-4 * abs(float(g["ref_err"]))
+    assert abs(correct - round(float(g["ref_correct_pct"]) * frames / 100.0)) <= max(1, int(0.002 * frames))
+    for a, b in zip(net.get_layers(), fixture_layers(g, "final")):
+        compare_layer(a, b, 2e-4, btol_floor=1e-2)
+
+
 def _offset_nets(r):
     def w(o, i):
         return (0.1 * r.standard_normal((o, i))).astype(np.float32)
@@ -206,7 +225,6 @@ def test_data_parallel_rejects_layers_without_gradient_exchange():
     net = host.Net(_offset_nets(r)["shared_unaligned"])
     with pytest.raises(abi.TnbError, match="sharedlinearity"):
         net.set_data_parallel(2)
-    net.set_data_parallel(1)
 
 
 def test_rbm_sparse_cd1_vs_oracle():

@@ -37,6 +37,22 @@ def test_oracle_vs_reference_cpu_tnet(case, acc_double):
     assert correct == round(ref_correct)      # frame-accuracy count exact on these fixtures
 
 
+def test_oracle_cross_validation_vs_reference_cpu_tnet():
+    """--CROSSVALIDATE=TRUE (TNet.cc:344 / TNetCu.cc:437): forward + objective only — same report, network untouched."""
+    g = np.load(os.path.join(GOLD, "cpu_opt_cv.npz"))
+    assert int(g["cv"]) == 1
+    correct, ref_correct = _check(g, 1, wtol=1e-7, etol=2e-5)       # "final" network of the fixture = the initial one
+    assert correct == round(ref_correct)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "gpu_opt_*.npz"))) or [None])
+def test_oracle_options_vs_reference_gpu_tnetcu(path):
+    """per-layer learning-rate factors with a frozen first layer (gpu_opt_lrfactors.npz: only TNetCu takes --LEARNRATEFACTORS)"""
+    if path is None:
+        pytest.skip("generate with tests/golden/make_golden.py --impl gpu --only opt_ on a B200")
+    _check(np.load(path), 0, wtol=5e-5, etol=5e-5)
+
+
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "gpu_mlp_*.npz")) + glob.glob(os.path.join(GOLD, "gpu_net_*.npz"))) or [None])
 def test_oracle_vs_reference_gpu_tnetcu(path):
     if path is None:
