@@ -292,8 +292,11 @@ class FeatureRepository {
     int first = rec.mFirst < 0 ? 0 : rec.mFirst, last = rec.mLast < 0 ? h.mNSamples - 1 : rec.mLast;
     if (first > last || last >= h.mNSamples) { fclose(f); Error(std::string("Frame range out of file: ") + rec.mLogical); }
     const int n = last - first + 1;
-    std::vector<float> buf((size_t)n * dim);
-    fseek(f, 12 + (long)first * h.mSampleSize, SEEK_SET);
+    // The context rows of a frame RANGE come from the file's own neighbouring frames where it has them; only beyond the ends of the
+    // FILE is the first/last frame replicated (Features.cc:1185-1191: from_frame/to_frame move outwards by min(ext, frames available)).
+    const int lo = std::max(0, first - mStartExt), hi = std::min((int)h.mNSamples - 1, last + mEndExt);
+    std::vector<float> buf((size_t)(hi - lo + 1) * dim);
+    fseek(f, 12 + (long)lo * h.mSampleSize, SEEK_SET);
     if (fread(buf.data(), 4, buf.size(), f) != buf.size()) { fclose(f); Error(std::string("Cannot read feature file: '") + rec.mPhysical + "'"); }
     fclose(f);
     if (mSwap) {
@@ -302,9 +305,9 @@ class FeatureRepository {
     }
     rMatrix.Init(n + mStartExt + mEndExt, dim);
     for (int r = 0; r < n + mStartExt + mEndExt; r++) {
-      int src = r - mStartExt;
-      src = src < 0 ? 0 : (src >= n ? n - 1 : src);
-      memcpy(rMatrix.pRowData(r), buf.data() + (size_t)src * dim, sizeof(float) * dim);
+      int src = first - mStartExt + r;  // frame of the file
+      src = src < lo ? lo : (src > hi ? hi : src);
+      memcpy(rMatrix.pRowData(r), buf.data() + (size_t)(src - lo) * dim, sizeof(float) * dim);
     }
     mHeader = h;
     mHeader.mNSamples = n;

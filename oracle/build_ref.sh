@@ -5,6 +5,8 @@
 #   oracle/_ref/TNet          CPU trainer   (src/TNet.cc + KaldiLib + TNetLib)   -> cpu baseline + oracle pin
 #   oracle/_ref/TFeaCat       CPU forward-only tool (src/TFeaCat.cc, same libs)  -> golden for the TFeaCatCu drop-in
 #   oracle/_ref/TNorm         CPU mean/variance estimator (src/TNorm.cc)         -> golden for the TNormCu drop-in
+#   oracle/_ref/RefIoDump     oracle/ref_tools/io_dump.cc (ours) over the reference's FeatureRepository / LabelRepository
+#                             -> golden for the drop-in's HTK / script-file / MLF readers
 #   oracle/_ref/TNetCu        GPU trainer   (src/TNetCu.cc + CuBaseLib + CuTNetLib, legacy cuBLAS) -> golden on B200
 #   oracle/_ref/TRbmCu, TRecurrentCu        same libs
 #
@@ -55,6 +57,11 @@ build_cpu() {
   g++ $CXXF $INC -c "$REF/src/TNorm.cc" -o "$WORK/cpu/TNorm.o"
   g++ -o "$OUT/TNorm" "$WORK/cpu/TNorm.o" "${lobjs[@]}" "$OBLAS" -lpthread -Wl,--disable-new-dtags -Wl,-rpath,"$OBLAS_DIR"
   echo "built $OUT/TNorm"
+  # our dumper over the reference's own HTK / script-file / MLF readers (oracle/ref_tools/io_dump.cc): differential fixture for the
+  # drop-in's front end (nnet-asr_b200/host/io.h)
+  g++ $CXXF $INC -c "$HERE/ref_tools/io_dump.cc" -o "$WORK/cpu/io_dump.o"
+  g++ -o "$OUT/RefIoDump" "$WORK/cpu/io_dump.o" "${lobjs[@]}" "$OBLAS" -lpthread -Wl,--disable-new-dtags -Wl,-rpath,"$OBLAS_DIR"
+  echo "built $OUT/RefIoDump"
 }
 
 build_gpu() {

@@ -1,0 +1,68 @@
+// TEST INFRASTRUCTURE.  Dumps what the reference's OWN front end (src/KaldiLib/Features.cc FeatureRepository, Labels.cc
+// LabelRepository — compiled unmodified by oracle/build_ref.sh) reads from a script file + MLF + label map, in the call order
+// of the trainer's main loop (src/TNetCu.cc:288-300, 376-408): per utterance the extended feature matrix and the per-frame
+// class id of the dense target matrix.  The drop-in's readers (nnet-asr_b200/host/io.h) are compared against this dump by
+// tests/test_host_cpu.py.  Only THIS file is ours; everything it calls is the reference.
+//
+//   io_dump <scp> <mlf> <labelmap> <start_ext> <end_ext> <swap 0|1> <out.bin> [label_dir, e.g. "*/" as the training scripts pass with -L]
+//
+// Output: int32 n_utt, then per utterance: int32 len(logical), bytes logical, int32 rows, int32 cols, int32 sample_period,
+// float32 rows*cols, int32 label_rows, int32 label_rows ids (-1 = all-zero target row, -2 = more than one 1).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "Features.h"
+#include "Labels.h"
+#include "Matrix.h"
+
+using namespace TNet;
+
+static void put32(FILE *f, int v) { fwrite(&v, 4, 1, f); }
+
+int main(int argc, char **argv) {
+  if (argc != 8 && argc != 9) { fprintf(stderr, "usage: io_dump scp mlf labelmap start_ext end_ext swap out.bin\n"); return 2; }
+  const int start_ext = atoi(argv[4]), end_ext = atoi(argv[5]);
+  const bool swap = atoi(argv[6]) != 0;
+  try {
+    FeatureRepository feature_repo;
+    LabelRepository label_repo;
+    feature_repo.Init(swap, start_ext, end_ext, PARAMKIND_ANON, 0, NULL, NULL, NULL, NULL, NULL, NULL);
+    feature_repo.AddFileList(argv[1]);
+    label_repo.Init(argv[2], argv[3], argc == 9 ? argv[8] : NULL, "lab");
+    FILE *out = fopen(argv[7], "wb");
+    if (!out) { perror("out"); return 1; }
+    std::vector<std::string> names;
+    long pos0 = ftell(out);
+    put32(out, 0);
+    int n = 0;
+    for (feature_repo.Rewind(); !feature_repo.EndOfList(); feature_repo.MoveNext(), n++) {
+      Matrix<BaseFloat> feats;
+      feature_repo.ReadFullMatrix(feats);
+      const std::string logical = feature_repo.Current().Logical();
+      put32(out, (int)logical.size());
+      fwrite(logical.data(), 1, logical.size(), out);
+      put32(out, (int)feats.Rows()); put32(out, (int)feats.Cols()); put32(out, (int)feature_repo.CurrentHeader().mSamplePeriod);
+      for (size_t r = 0; r < feats.Rows(); r++) fwrite(feats.pRowData(r), sizeof(float), feats.Cols(), out);
+      const int rows = (int)feats.Rows() - start_ext - end_ext;  // the trainer trims the context rows after the transform
+      Matrix<BaseFloat> labs;
+      label_repo.GenDesiredMatrix(labs, rows, feature_repo.CurrentHeader().mSamplePeriod, logical.c_str());
+      put32(out, (int)labs.Rows());
+      for (size_t r = 0; r < labs.Rows(); r++) {
+        int id = -1;
+        for (size_t c = 0; c < labs.Cols(); c++)
+          if (labs(r, c) != 0.0f) id = (id == -1) ? (int)c : -2;
+        put32(out, id);
+      }
+    }
+    fseek(out, pos0, SEEK_SET);
+    put32(out, n);
+    fclose(out);
+  } catch (std::exception &e) {
+    fprintf(stderr, "io_dump: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

@@ -1,0 +1,56 @@
+// Dumps what the drop-in's front end (nnet-asr_b200/host/io.h: FeatureRepository, LabelRepository) reads from a script file +
+// MLF + label map, in the call order of the trainer's main loop and in the format of oracle/ref_tools/io_dump.cc (the same dump
+// through the reference's own KaldiLib readers).  tests/test_host_cpu.py compares the two byte for byte.  No GPU, no CUDA.
+//
+//   test_feature_io <scp> <mlf> <labelmap> <start_ext> <end_ext> <swap 0|1> <out.bin> [label_dir, e.g. "*/" as the training scripts pass with -L]
+#include <cstdio>
+#include <cstdlib>
+
+#include "io.h"
+
+using namespace TNet;
+
+static void put32(FILE *f, int v) { fwrite(&v, 4, 1, f); }
+
+int main(int argc, char **argv) {
+  if (argc != 8 && argc != 9) { fprintf(stderr, "usage: test_feature_io scp mlf labelmap start_ext end_ext swap out.bin\n"); return 2; }
+  const int start_ext = atoi(argv[4]), end_ext = atoi(argv[5]);
+  const bool swap = atoi(argv[6]) != 0;
+  try {
+    FeatureRepository feature_repo;
+    LabelRepository label_repo;
+    feature_repo.Init(swap, start_ext, end_ext, 0, 0, NULL, NULL, NULL, NULL, NULL, NULL);
+    feature_repo.AddFileList(argv[1]);
+    label_repo.Init(argv[2], argv[3], argc == 9 ? argv[8] : NULL, "lab");
+    FILE *out = fopen(argv[7], "wb");
+    if (!out) { perror("out"); return 1; }
+    put32(out, (int)feature_repo.QueueSize());
+    for (feature_repo.Rewind(); !feature_repo.EndOfList(); feature_repo.MoveNext()) {
+      Matrix<BaseFloat> feats;
+      feature_repo.ReadFullMatrix(feats);
+      const std::string logical = feature_repo.Current().Logical();
+      put32(out, (int)logical.size());
+      fwrite(logical.data(), 1, logical.size(), out);
+      put32(out, (int)feats.Rows()); put32(out, (int)feats.Cols()); put32(out, (int)feature_repo.CurrentHeader().mSamplePeriod);
+      for (size_t r = 0; r < feats.Rows(); r++) fwrite(feats.pRowData(r), sizeof(float), feats.Cols(), out);
+      const int rows = (int)feats.Rows() - start_ext - end_ext;
+      std::vector<int> ids;  // the int32 ids the device expands to one-hot rows (tnb_onehot): -1 = unlabelled frame
+      label_repo.GenLabelIds(ids, rows, feature_repo.CurrentHeader().mSamplePeriod, logical.c_str());
+      BfMatrix dense;        // and the reference's dense form must say the same
+      label_repo.GenDesiredMatrix(dense, rows, feature_repo.CurrentHeader().mSamplePeriod, logical.c_str());
+      put32(out, (int)ids.size());
+      for (size_t r = 0; r < ids.size(); r++) {
+        int id = -1;
+        for (size_t c = 0; c < dense.Cols(); c++)
+          if (dense(r, c) != 0.0f) id = (id == -1) ? (int)c : -2;
+        if (id != ids[r]) { fprintf(stderr, "GenLabelIds and GenDesiredMatrix disagree at frame %zu\n", r); return 1; }
+        put32(out, id);
+      }
+    }
+    fclose(out);
+  } catch (std::exception &e) {
+    fprintf(stderr, "test_feature_io: %s\n", e.what());
+    return 3;
+  }
+  return 0;
+}

@@ -172,3 +172,127 @@ def test_fast_text_reader_writer_matches_ostream_format(tmp_path):
     subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-pthread", "-I", inc, "-o", exe, src])
     r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
     assert r.returncode == 0 and "TEXT_IO_OK" in r.stdout, r.stderr
+
+
+# ------------------------------------------------------------------------------------------------ front end: HTK / script file / MLF readers
+def _io_dataset(d):
+    """A small set that exercises the readers: ragged utterances, plain / logical=physical / logical=physical[first,last] script
+    entries, label times that need the round-half-up division by the sample period, score columns and comments in the MLF, a
+    record longer than its utterance (truncated frames), little- and big-endian reads decided by the caller."""
+    r = np.random.default_rng(17)
+    utts = F.gen_utterances(5, 40, 7, 6, r)
+    paths = F.write_dataset(d, utts, 6, 2)
+    names = list(utts.keys())
+    fea = dict(zip(names, paths["files"]))
+    entries = [fea[names[0]],                                              # plain physical name
+               "alias_b.fea=" + fea[names[1]],                             # logical=physical
+               "seg_c.fea=" + fea[names[2]] + "[3,17]",                    # a frame range of a longer file
+               fea[names[3]],
+               "some/dir/alias_e.fea=" + fea[names[4]] + "[0,%d]" % (utts[names[4]][0].shape[0] - 1)]
+    scp = os.path.join(d, "mixed.scp")
+    open(scp, "w").write("\n".join(entries) + "\n\n")
+    tags = ["s%d" % i for i in range(6)]
+    P = 100000
+    with open(os.path.join(d, "mixed.mlf"), "w") as f:
+        f.write("#!MLF!#\n")
+        lab = {n: utts[n][1] for n in names}
+
+        def rec(key, ids, jitter=0, extra=""):
+            f.write('"*/%s.lab"\n' % key)
+            start = 0
+            for t in range(1, len(ids) + 1):
+                if t == len(ids) or ids[t] != ids[start]:
+                    # boundaries off by less than half a frame must round to the same frame index
+                    b = start * P + (jitter if start else 0)
+                    e = t * P + (jitter if t < len(ids) else 0)
+                    f.write("%d %d %s%s\n" % (b, e, tags[int(ids[start])], extra))
+                    start = t
+            f.write(".\n")
+        rec(names[0], lab[names[0]])
+        rec("alias_b", lab[names[1]], jitter=-40000)
+        rec("seg_c", lab[names[2]][3:18], jitter=+49999, extra=" -12.5 word")
+        rec(names[3], np.concatenate([lab[names[3]], lab[names[3]][-1:].repeat(30)]))    # runs past the end of the features
+        rec("alias_e", lab[names[4]])
+    return scp, os.path.join(d, "mixed.mlf"), paths["labelmap"]
+
+
+def _parse_io_dump(path):
+    b = open(path, "rb").read()
+    pos = 0
+
+    def i32():
+        nonlocal pos
+        v = int(np.frombuffer(b, "<i4", 1, pos)[0]); pos += 4
+        return v
+    out = []
+    for _ in range(i32()):
+        n = i32(); name = b[pos:pos + n].decode(); pos += n
+        rows, cols, period = i32(), i32(), i32()
+        x = np.frombuffer(b, "<f4", rows * cols, pos).reshape(rows, cols).copy(); pos += 4 * rows * cols
+        m = i32()
+        ids = np.frombuffer(b, "<i4", m, pos).copy(); pos += 4 * m
+        out.append((name, period, x, ids))
+    assert pos == len(b)
+    return out
+
+
+@pytest.mark.parametrize("ext", [(0, 0), (2, 2), (4, 1)])
+def test_feature_and_label_readers_match_the_reference_front_end(tmp_path, ext):
+    """nnet-asr_b200/host/io.h (FeatureRepository: script-file entries, byte order, STARTFRMEXT/ENDFRMEXT replication; LabelRepository:
+    MLF records by logical base name, time -> frame rounding, truncation) against the reference's own KaldiLib readers driven in
+    the trainer's call order (oracle/ref_tools/io_dump.cc -> oracle/_ref/RefIoDump), and against the committed dump of that tool."""
+    d = str(tmp_path)
+    scp, mlf, lmap = _io_dataset(d)
+    exe = str(tmp_path / "test_feature_io")
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "nnet-asr_b200", "host"), "-I",
+                           os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_feature_io.cc")])
+    mine = str(tmp_path / "mine.bin")
+    subprocess.check_call([exe, scp, mlf, lmap, str(ext[0]), str(ext[1]), "1", mine, "*/"])     # -L "*/" -X lab, as the scripts run it
+    got = _parse_io_dump(mine)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "cpu_io_dump.npz"))
+    key = "e%d_%d" % ext
+    assert [g[0].replace(d, "<D>") for g in got] == [str(s) for s in gold[key + "_names"]]
+    np.testing.assert_array_equal(np.concatenate([g[2].ravel() for g in got]), gold[key + "_feats"])
+    np.testing.assert_array_equal(np.concatenate([g[3] for g in got]), gold[key + "_ids"])
+    np.testing.assert_array_equal(np.array([g[2].shape[0] for g in got]), gold[key + "_rows"])
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "RefIoDump")
+    if os.path.exists(ref_exe):                 # the build container: the reference's readers, live, on the same files
+        ref = str(tmp_path / "ref.bin")
+        subprocess.check_call([ref_exe, scp, mlf, lmap, str(ext[0]), str(ext[1]), "1", ref, "*/"])
+        assert open(ref, "rb").read() == open(mine, "rb").read()
+
+
+@pytest.mark.parametrize("case", ["missing_record", "unknown_tag", "frame_assigned_twice", "range_outside_file", "ok"])
+def test_feature_and_label_reader_errors_match_the_reference(tmp_path, case):
+    """Malformed inputs must fail where the reference's readers fail (Labels.cc:55-57,124-145; Features.cc:1193-1195) — and the
+    well-formed control must pass in both."""
+    d = str(tmp_path)
+    r = np.random.default_rng(3)
+    x = r.standard_normal((20, 5)).astype(np.float32)
+    fea = os.path.join(d, "a.fea")
+    F.write_htk(fea, x)
+    open(os.path.join(d, "map"), "w").write("s0\ns1\n")
+    rec = '"*/a.lab"\n0 1000000 s0\n1000000 2000000 s1\n.\n'
+    entry = fea
+    if case == "missing_record":
+        rec = rec.replace("a.lab", "b.lab")
+    elif case == "unknown_tag":
+        rec = rec.replace("s1", "s7")
+    elif case == "frame_assigned_twice":
+        rec = rec.replace("1000000 2000000", "900000 2000000")      # frame 9 belongs to both segments after rounding
+    elif case == "range_outside_file":
+        entry = "a.fea=" + fea + "[5,25]"
+    open(os.path.join(d, "a.scp"), "w").write(entry + "\n")
+    open(os.path.join(d, "a.mlf"), "w").write("#!MLF!#\n" + rec)
+    exe = str(tmp_path / "test_feature_io")
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "nnet-asr_b200", "host"), "-I",
+                           os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_feature_io.cc")])
+    args = [os.path.join(d, "a.scp"), os.path.join(d, "a.mlf"), os.path.join(d, "map"), "1", "1", "1"]
+    mine = subprocess.run([exe] + args + [os.path.join(d, "mine.bin"), "*/"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert (mine.returncode == 0) == (case == "ok"), mine.stderr[-500:]
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "RefIoDump")
+    if os.path.exists(ref_exe):
+        ref = subprocess.run([ref_exe] + args + [os.path.join(d, "ref.bin"), "*/"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert (ref.returncode == 0) == (mine.returncode == 0), (ref.returncode, mine.returncode, ref.stderr[-300:], mine.stderr[-300:])
+        if case == "ok":
+            assert open(os.path.join(d, "ref.bin"), "rb").read() == open(os.path.join(d, "mine.bin"), "rb").read()
