@@ -14,6 +14,7 @@
 #include <stdint.h>
 #include <strings.h>
 
+#include <iomanip>
 #include <map>
 
 #include "tnet_base.h"
@@ -189,10 +190,12 @@ class UserInterface {
       }
     }
   }
+  /// same layout as the reference's dump (UserInterface.cc:645-654): "# " marks a parameter nothing has read yet
   void PrintConfig(std::ostream &out) {
     out << "Configuration Parameters[" << mMap.size() << "]\n";
     for (std::map<std::string, ValueRecord>::iterator it = mMap.begin(); it != mMap.end(); ++it)
-      out << (it->second.mRead ? " " : "#") << it->first << " = " << it->second.mValue << "   # -" << it->second.mOption << "\n";
+      out << (it->second.mRead ? "  " : "# ") << std::setw(35) << std::left << it->first << " = " << std::setw(30) << std::left
+          << it->second.mValue << " # -" << it->second.mOption << std::endl;
   }
 
  private:

@@ -5,6 +5,7 @@
 //   test_feature_io <scp> <mlf> <labelmap> <start_ext> <end_ext> <swap 0|1> <out.bin> [label_dir, e.g. "*/" as the training scripts pass with -L]
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "io.h"
 
@@ -13,6 +14,13 @@ using namespace TNet;
 static void put32(FILE *f, int v) { fwrite(&v, 4, 1, f); }
 
 int main(int argc, char **argv) {
+  // second mode: <tool> --htkname <in> <dir|-> <ext|->  prints MakeHtkFileName(in, dir, ext) ("-" = NULL argument)
+  if (argc == 5 && !strcmp(argv[1], "--htkname")) {
+    char out[4096];
+    MakeHtkFileName(out, argv[2], strcmp(argv[3], "-") ? argv[3] : NULL, strcmp(argv[4], "-") ? argv[4] : NULL);
+    printf("%s\n", out);
+    return 0;
+  }
   if (argc != 8 && argc != 9) { fprintf(stderr, "usage: test_feature_io scp mlf labelmap start_ext end_ext swap out.bin\n"); return 2; }
   const int start_ext = atoi(argv[4]), end_ext = atoi(argv[5]);
   const bool swap = atoi(argv[6]) != 0;
