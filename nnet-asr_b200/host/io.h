@@ -290,7 +290,8 @@ class FeatureRepository {
     memcpy(&h.mNSamples, hb, 4); memcpy(&h.mSamplePeriod, hb + 4, 4); memcpy(&h.mSampleSize, hb + 8, 2); memcpy(&h.mSampleKind, hb + 10, 2);
     if (mSwap) { h.mNSamples = Swap32(h.mNSamples); h.mSamplePeriod = Swap32(h.mSamplePeriod); h.mSampleSize = (int16_t)Swap16((uint16_t)h.mSampleSize); h.mSampleKind = Swap16(h.mSampleKind); }
     if (h.mSampleKind & 02000) { fclose(f); Error(std::string("Compressed (_C) HTK files are not built into the B200 hot path: ") + rec.mPhysical); }
-    if (h.mNSamples <= 0 || h.mSampleSize <= 0 || h.mSampleSize % 4 != 0) { fclose(f); Error(std::string("Invalid HTK header in feature file: '") + rec.mPhysical + "'"); }
+    // the reference's header check (Features.cc:522-528) also bounds the sample period: a wrong byte order shows up here
+    if (h.mSamplePeriod < 0 || h.mSamplePeriod > 100000 || h.mNSamples <= 0 || h.mSampleSize <= 0 || h.mSampleSize % 4 != 0) { fclose(f); Error(std::string("Invalid HTK header in feature file: '") + rec.mPhysical + "'"); }
     const int dim = h.mSampleSize / 4;
     int first = rec.mFirst < 0 ? 0 : rec.mFirst, last = rec.mLast < 0 ? h.mNSamples - 1 : rec.mLast;
     if (first > last || last >= h.mNSamples) { fclose(f); Error(std::string("Frame range out of file: ") + rec.mLogical); }

@@ -23,6 +23,29 @@ using namespace TNet;
 static void put32(FILE *f, int v) { fwrite(&v, 4, 1, f); }
 
 int main(int argc, char **argv) {
+  // third mode: <tool> --rewrite <scp entry> <start_ext> <end_ext> <swap 0|1> <out.htk>  reads one script-file entry and writes it
+  // back the way TFeaCat does (TFeaCat.cc:262 / main_TFeaCatCu.cc: WriteFeatureMatrix, USER kind, the source's sample period)
+  if (argc == 7 && !strcmp(argv[1], "--rewrite")) {
+    try {
+      FeatureRepository repo;
+      repo.Init(atoi(argv[5]) != 0, atoi(argv[3]), atoi(argv[4]), PARAMKIND_ANON, 0, NULL, NULL, NULL, NULL, NULL, NULL);
+      const char *list = "/tmp/.io_dump_entry";
+      std::string tmp = std::string(argv[6]) + ".scp";
+      FILE *f = fopen(tmp.c_str(), "w");
+      fprintf(f, "%s\n", argv[2]);
+      fclose(f);
+      (void)list;
+      repo.AddFileList(tmp.c_str());
+      repo.Rewind();
+      Matrix<BaseFloat> m;
+      repo.ReadFullMatrix(m);
+      repo.WriteFeatureMatrix(m, argv[6], PARAMKIND_USER, repo.CurrentHeader().mSamplePeriod);
+    } catch (std::exception &e) {
+      fprintf(stderr, "%s\n", e.what());
+      return 1;
+    }
+    return 0;
+  }
   // second mode: <tool> --htkname <in> <dir|-> <ext|->  prints MakeHtkFileName(in, dir, ext) ("-" = NULL argument)
   if (argc == 5 && !strcmp(argv[1], "--htkname")) {
     char out[4096];

@@ -344,3 +344,35 @@ def test_make_htk_file_name_like_the_reference(tmp_path):
         assert got == want, (args, got, want)
         if os.path.exists(ref_exe):
             assert subprocess.check_output([ref_exe, "--htkname"] + list(args), text=True).rstrip("\n") == got, args
+
+
+def test_htk_writer_and_header_checks_like_the_reference(tmp_path):
+    """FeatureRepository::WriteFeatureMatrix as TFeaCat uses it (TFeaCat.cc:262): a script-file entry read with context rows and
+    written back must give the reference's bytes (header: frame count, source sample period, size, USER kind; big-endian data);
+    headers the reference rejects (Features.cc:522-528: sample period outside [0, 100000] — also what a wrong byte order looks like)
+    must be rejected."""
+    exe = str(tmp_path / "test_feature_io")
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "nnet-asr_b200", "host"), "-I",
+                           os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_feature_io.cc")])
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "RefIoDump")
+    r = np.random.default_rng(1)
+    x = r.standard_normal((12, 5)).astype(np.float32)
+    fea, bad = str(tmp_path / "a.fea"), str(tmp_path / "bad.fea")
+    F.write_htk(fea, x, samp_period=62500)
+    F.write_htk(bad, x, samp_period=123400)
+    import struct
+    for entry, lo, hi in ((fea, 0, 11), ("z.fea=" + fea + "[2,7]", 2, 7)):
+        for se, ee in ((0, 0), (3, 2)):
+            out = str(tmp_path / "mine.htk")
+            subprocess.check_call([exe, "--rewrite", entry, str(se), str(ee), "1", out])
+            rows = np.clip(np.arange(lo - se, hi + ee + 1), 0, 11)
+            want = struct.pack(">iihh", len(rows), 62500, 20, 9) + x[rows].astype(">f4").tobytes()
+            assert open(out, "rb").read() == want
+            if os.path.exists(ref_exe):
+                ref = str(tmp_path / "ref.htk")
+                subprocess.check_call([ref_exe, "--rewrite", entry, str(se), str(ee), "1", ref])
+                assert open(ref, "rb").read() == want
+    for tool in [exe] + ([ref_exe] if os.path.exists(ref_exe) else []):
+        for args in ((bad, "1"), (fea, "0")):       # period 123400 ; little-endian read of a big-endian file
+            rc = subprocess.run([tool, "--rewrite", args[0], "0", "0", args[1], str(tmp_path / "x.htk")], stderr=subprocess.PIPE).returncode
+            assert rc != 0, (tool, args)
