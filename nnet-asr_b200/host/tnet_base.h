@@ -23,6 +23,8 @@
 #include <stdexcept>
 #include <string>
 #include <algorithm>
+#include <type_traits>
+#include <limits>
 #include <thread>
 #include <vector>
 
@@ -127,7 +129,7 @@ typedef Vector<BaseFloat> BfVector;
 // ---- text format -------------------------------------------------------------------------------------
 // Same text as the reference (KaldiLib/Matrix.tcc:522-600, Vector.tcc:527-571: `ostream << float` at the default precision of 6
 // = printf's %g), produced and parsed fast enough that a 28M-weight network does not dominate a short run: numbers are
-// scanned straight from the stream buffer with strtod semantics (also "inf"/"nan"), large matrices are formatted row block by
+// scanned straight from the stream buffer (strtod on the tokens `istream >> float` would accept), large matrices are formatted row block by
 // row block on several threads and written in order.
 template <typename T>
 inline bool ReadNumber(std::istream &in, T &v) {
@@ -142,10 +144,19 @@ inline bool ReadNumber(std::istream &in, T &v) {
     ch = sb->snextc();
   }
   tok[n] = '\0';
+  // what `istream >> float` takes, as the reference reads its files (Matrix.tcc:556-566): decimal digits, sign, point, exponent.
+  // "nan" / "inf" (which `ostream << float` writes for a diverged network), hexadecimal floats and values beyond the float range
+  // fail there, so they fail here: a network that the reference refuses to load is not loaded silently.
+  for (int i = 0; i < n; i++) {
+    const char c = tok[i];
+    if (!((c >= '0' && c <= '9') || c == '+' || c == '-' || c == '.' || c == 'e' || c == 'E')) return false;
+  }
   char *end = 0;
   double d = std::strtod(tok, &end);
   if (end == tok || *end != '\0') return false;
-  v = (T)d;
+  const T f = (T)d;
+  if (std::is_floating_point<T>::value && std::isinf((double)f)) return false;  // beyond the range after rounding to T
+  v = f;
   return true;
 }
 

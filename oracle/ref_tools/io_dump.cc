@@ -11,18 +11,42 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <string>
 #include <vector>
 
 #include "Features.h"
 #include "Labels.h"
 #include "Matrix.h"
+#include "Vector.h"
 
 using namespace TNet;
 
 static void put32(FILE *f, int v) { fwrite(&v, 4, 1, f); }
 
 int main(int argc, char **argv) {
+  // fourth mode: <tool> --readmv <text file> <out.bin>  reads a matrix then a vector with the text operators of the network files
+  // (Matrix.tcc:575-600, Vector.tcc:527-547) and dumps int32 rows, cols, float32 values, int32 dim, float32 values
+  if (argc == 4 && !strcmp(argv[1], "--readmv")) {
+    try {
+      std::ifstream in(argv[2]);
+      Matrix<BaseFloat> m;
+      Vector<BaseFloat> v;
+      in >> m;
+      in >> v;
+      FILE *f = fopen(argv[3], "wb");
+      int r = (int)m.Rows(), c = (int)m.Cols(), d = (int)v.Dim();
+      fwrite(&r, 4, 1, f); fwrite(&c, 4, 1, f);
+      for (int i = 0; i < r; i++) fwrite(m.pRowData(i), sizeof(float), c, f);
+      fwrite(&d, 4, 1, f);
+      fwrite(v.pData(), sizeof(float), d, f);
+      fclose(f);
+    } catch (std::exception &e) {
+      fprintf(stderr, "%s\n", e.what());
+      return 1;
+    }
+    return 0;
+  }
   // third mode: <tool> --rewrite <scp entry> <start_ext> <end_ext> <swap 0|1> <out.htk>  reads one script-file entry and writes it
   // back the way TFeaCat does (TFeaCat.cc:262 / main_TFeaCatCu.cc: WriteFeatureMatrix, USER kind, the source's sample period)
   if (argc == 7 && !strcmp(argv[1], "--rewrite")) {

@@ -376,3 +376,36 @@ def test_htk_writer_and_header_checks_like_the_reference(tmp_path):
         for args in ((bad, "1"), (fea, "0")):       # period 123400 ; little-endian read of a big-endian file
             rc = subprocess.run([tool, "--rewrite", args[0], "0", "0", args[1], str(tmp_path / "x.htk")], stderr=subprocess.PIPE).returncode
             assert rc != 0, (tool, args)
+
+
+def test_matrix_vector_text_parsing_like_the_reference(tmp_path):
+    """The text operators the network files are read with (tnet_base.h) against the reference's (Matrix.tcc:575-600,
+    Vector.tcc:527-547, i.e. `istream >> float`): same values for every syntax the reference accepts, refusal where it refuses
+    ("nan"/"inf" of a diverged network, hexadecimal floats, values beyond the float range, truncated or malformed matrices)."""
+    exe = str(tmp_path / "test_feature_io")
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "nnet-asr_b200", "host"), "-I",
+                           os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_feature_io.cc")])
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "RefIoDump")
+    f32 = lambda *v: np.array(v, np.float32).tobytes()
+    i32 = lambda *v: np.array(v, np.int32).tobytes()
+    cases = {   # text -> expected dump (None = must be refused)
+        "m 2 3\n1 2 3 \n4 5 6 \nv 2  7 8 \n": i32(2, 3) + f32(1, 2, 3, 4, 5, 6) + i32(2) + f32(7, 8),
+        "\n\n  m 2 2\n1e-3   -2.5E+2\n\t.5 +7.\n\n v 3 1 2\n3\n": i32(2, 2) + f32(1e-3, -250, .5, 7) + i32(3) + f32(1, 2, 3),
+        "m 1 4 1 2 3 4 v 1 9": i32(1, 4) + f32(1, 2, 3, 4) + i32(1) + f32(9),
+        "m 1 3 -0 1e-42 3.4028235e38 v 1 1e-50": i32(1, 3) + f32(-0.0, 1e-42, 3.4028235e38) + i32(1) + f32(0),
+        "m 0 0\nv 0 \n": i32(0, 0) + i32(0),
+        "m 1 2 0.1234567890123456789 16777217 v 1 0.30000001192092896": i32(1, 2) + f32(0.1234567890123456789, 16777217) + i32(1) + f32(0.3),
+        "m 1 2 1e39 -1e39 v 1 0": None, "m 2 2 1 2 3 v 2 1 2": None, "m 1 2 nan 1 v 1 0": None, "m 1 2 inf 1 v 1 0": None,
+        "m 1 2 0x10 1 v 1 0": None, "m -1 2 v 1 0": None, "m 1 2 1,2 v 1 0": None,
+    }
+    for txt, want in cases.items():
+        src, out = str(tmp_path / "in.txt"), str(tmp_path / "out.bin")
+        open(src, "w").write(txt)
+        for tool in [exe] + ([ref_exe] if os.path.exists(ref_exe) else []):
+            if os.path.exists(out):
+                os.unlink(out)
+            rc = subprocess.run([tool, "--readmv", src, out], stderr=subprocess.PIPE).returncode
+            if want is None:
+                assert rc != 0, (tool, txt)
+            else:
+                assert rc == 0 and open(out, "rb").read() == want, (tool, txt)
