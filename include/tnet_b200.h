@@ -99,6 +99,8 @@ int tnb_memcpy2d(TnbContext *ctx, void *dst, size_t dpitch_bytes, const void *sr
 int tnb_memcpy(TnbContext *ctx, void *dst, const void *src, size_t bytes, int kind);
 int tnb_host_alloc(void **ptr, size_t bytes); /* pinned host memory */
 /* ---- CUDA graphs: record a launch-bound sequence of calls once, replay it (TRecurrentCu: ~115 small kernels per frame).
+ * No counterpart in the reference, which launches every kernel synchronously (cuSafeCall + cudaThreadSynchronize,
+ * src/CuBaseLib/cucommon.h:13-22; per-frame sequence: cuRecurrent.cc:16-153).
  * Between begin and end every call on the compute stream is captured instead of executed; do not allocate, synchronise or copy
  * to/from pageable host memory there (run the sequence once eagerly first so that every buffer and scratch exists). */
 int tnb_graph_begin(TnbContext *ctx);
@@ -218,10 +220,10 @@ typedef struct TnbBiasJob_ {
   float lr, mmt;
   int grad_div_frm, n_frames_global;
 } TnbBiasJob;
-int tnb_bias_update_batch(TnbContext *ctx, const TnbBiasJob *jobs, int n);
+int tnb_bias_update_batch(TnbContext *ctx, const TnbBiasJob *jobs, int n); /* cuBiasedLinearity.cc:56-59 for n layers */
 /* the same on another stream of the context, with its own reduction scratch (may run next to compute-stream column sums) */
 int tnb_bias_update_batch_on(TnbContext *ctx, int stream_id, const TnbBiasJob *jobs, int n);
-/* the same update given an already summed gradient (after the NCCL allreduce):
+/* the same update (cuBiasedLinearity.cc:55-63) given an already summed gradient (after the NCCL allreduce):
  *   corrW = G + mmt*corrW ; ... as above.  gb/bias/corrb may be NULL together. */
 int tnb_sgd_update(TnbContext *ctx, const float *G, float *W, float *corrW, TnbMatrixDim dW, const float *gb, float *bias,
                    float *corrb, float lr, float mmt, float wc, int grad_div_frm, int n_frames);
@@ -231,7 +233,8 @@ int tnb_sgd_update(TnbContext *ctx, const float *G, float *W, float *corrW, TnbM
  * path avoids that conversion by keeping a bf16 twin next to each fp32 matrix a GEMM reads: the three fused layer ops below
  * READ twins (X16, W16, E16: row-major bf16 bit patterns, pitch in elements, 16-byte aligned, pitch a multiple of 8) and WRITE
  * the twin of what they produce (Y16, Eprev16, W16; may be NULL) from the same fp32 value they store.  Arithmetic and fp32
- * results are identical to the fp32-array entry points in bf16 mode. */
+ * results are identical to the fp32-array entry points in bf16 mode; the reference code they stand for is the same
+ * (cuBiasedLinearity.cc:11-16 forward, :20-25 dX, :44-64 update; cuActivation.cc:9-22 sigmoid / diff-sigmoid). */
 int tnb_to_bf16(TnbContext *ctx, uint16_t *dst, int dst_stride, const float *src, TnbMatrixDim d); /* dst = bf16_rn(src); pad columns zeroed */
 int tnb_affine_fwd_bf16(TnbContext *ctx, const uint16_t *X16, int ldx16, TnbMatrixDim dX, const uint16_t *W16, int ldw16,
                         TnbMatrixDim dW, const float *bias, float *Y, TnbMatrixDim dY, uint16_t *Y16, int ldy16, int act);
@@ -245,7 +248,7 @@ int tnb_affine_update_bf16(TnbContext *ctx, const uint16_t *X16, int ldx16, TnbM
                            const float *E, TnbMatrixDim dE, float *W, TnbMatrixDim dW, uint16_t *W16, int ldw16, float *bias,
                            float *corrW, float *corrb, float lr, float mmt, float wc, int grad_div_frm, int n_frames_global);
 
-/* tnb_sgd_update for several layers in one launch (the data-parallel step applies them after the last all-reduce); W16/ldw16:
+/* tnb_sgd_update (cuBiasedLinearity.cc:55-63) for several layers in one launch (the data-parallel step applies them after the last all-reduce); W16/ldw16:
  * optional bf16 twin of W to refresh (NULL otherwise). */
 typedef struct TnbSgdJob_ {
   const float *G;
