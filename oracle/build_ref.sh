@@ -7,6 +7,8 @@
 #   oracle/_ref/TNorm         CPU mean/variance estimator (src/TNorm.cc)         -> golden for the TNormCu drop-in
 #   oracle/_ref/RefIoDump     oracle/ref_tools/io_dump.cc (ours) over the reference's FeatureRepository / LabelRepository
 #                             -> golden for the drop-in's HTK / script-file / MLF readers
+#   oracle/_ref/RefCacheDump  oracle/ref_tools/cache_dump.cc (ours) over the reference's CPU frame cache (TNetLib/Cache.cc)
+#                             -> bit-exact golden for the oracle's cache (fill, leftovers, permutation, bunches, discards)
 #   oracle/_ref/TNetCu        GPU trainer   (src/TNetCu.cc + CuBaseLib + CuTNetLib, legacy cuBLAS) -> golden on B200
 #   oracle/_ref/TRbmCu, TRecurrentCu        same libs
 #
@@ -62,6 +64,10 @@ build_cpu() {
   g++ $CXXF $INC -c "$HERE/ref_tools/io_dump.cc" -o "$WORK/cpu/io_dump.o"
   g++ -o "$OUT/RefIoDump" "$WORK/cpu/io_dump.o" "${lobjs[@]}" "$OBLAS" -lpthread -Wl,--disable-new-dtags -Wl,-rpath,"$OBLAS_DIR"
   echo "built $OUT/RefIoDump"
+  # our driver over the reference's CPU frame cache (oracle/ref_tools/cache_dump.cc): bit-exact fixture for the oracle's cache
+  g++ $CXXF $INC -c "$HERE/ref_tools/cache_dump.cc" -o "$WORK/cpu/cache_dump.o"
+  g++ -o "$OUT/RefCacheDump" "$WORK/cpu/cache_dump.o" "${lobjs[@]}" "$OBLAS" -lpthread -Wl,--disable-new-dtags -Wl,-rpath,"$OBLAS_DIR"
+  echo "built $OUT/RefCacheDump"
 }
 
 build_gpu() {

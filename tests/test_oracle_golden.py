@@ -94,3 +94,68 @@ def test_tnorm_restatement_vs_reference_cpu_tnorm():
     var = second / frames - mean * mean
     np.testing.assert_allclose(-mean, g["ref_bias"], rtol=1e-5, atol=1e-6)      # the tool prints 6 significant digits
     np.testing.assert_allclose(1.0 / np.sqrt(var), g["ref_window"], rtol=1e-5)
+
+
+CACHE_CASES = {
+    # name: (cachesize, bunchsize, seed, randomize, lens) — ragged utterances, leftovers carried into the next fill, a partial last
+    # fill, utterances longer than the free space, a discarded tail; the leftover never exceeds the cache (the reference asserts)
+    "ragged_rand": (192, 32, 77, 1, [50, 7, 130, 64, 1, 99, 150, 12, 45, 33, 170]),
+    "norand": (128, 64, 5, 0, [100, 100, 30, 64, 2, 60]),
+    "exact_fit": (96, 32, 9, 1, [32, 64, 96, 16, 16, 64]),
+    "tiny_bunch": (40, 8, 123, 1, [3, 5, 8, 13, 21, 34, 2, 1, 39]),
+}
+
+
+def _cache_inputs(name):
+    cachesize, bunch, seed, rnd, lens = CACHE_CASES[name]
+    r = np.random.default_rng(len(name) + seed)
+    fdim, ddim = 11, 5
+    seqs = [(r.standard_normal((n, fdim)).astype(np.float32), r.standard_normal((n, ddim)).astype(np.float32)) for n in lens]
+    return cachesize, bunch, seed, rnd, fdim, ddim, seqs
+
+
+def _oracle_cache_run(name):
+    cachesize, bunch, seed, rnd, fdim, ddim, seqs = _cache_inputs(name)
+    O.lib.orc_srand48(seed)
+    c = O.Cache(cachesize, bunch)
+    out, i = [], 0
+    while i < len(seqs):
+        while not c.full() and i < len(seqs):
+            c.add(*seqs[i]); i += 1
+        if rnd:
+            c.randomize()
+        while not c.empty():
+            out.append(c.get_bunch())
+    return out, c.discarded()
+
+
+@pytest.mark.parametrize("name", sorted(CACHE_CASES))
+def test_oracle_cache_vs_reference_cpu_cache(name, tmp_path):
+    """The oracle's frame cache (orc_cache_*: fill, leftover carry-over, random_shuffle + lrand48 permutation, bunch slicing, discarded
+    tail) against the reference's own CPU cache (TNetLib/Cache.cc, the same state machine as cuCache.cc) driven by
+    oracle/ref_tools/cache_dump.cc: every bunch bit for bit — committed dump, and live where oracle/_ref/RefCacheDump exists."""
+    got, disc = _oracle_cache_run(name)
+    flat = np.concatenate([np.concatenate([f.ravel(), d.ravel()]) for f, d in got]) if got else np.zeros(0, np.float32)
+    gold = np.load(os.path.join(GOLD, "cpu_cache_dump.npz"))
+    assert int(gold[name + "_nb"]) == len(got) and int(gold[name + "_discarded"]) == disc
+    assert np.array_equal(flat.view(np.uint32), gold[name + "_data"].view(np.uint32))
+    exe = os.path.join(os.path.dirname(GOLD), "..", "oracle", "_ref", "RefCacheDump")
+    if os.path.exists(exe):
+        nb, data, rdisc = run_reference_cache(exe, name, str(tmp_path))
+        assert nb == len(got) and rdisc == disc and np.array_equal(data.view(np.uint32), flat.view(np.uint32))
+
+
+def run_reference_cache(exe, name, d):
+    import subprocess
+    cachesize, bunch, seed, rnd, fdim, ddim, seqs = _cache_inputs(name)
+    src, out = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+    with open(src, "wb") as f:
+        f.write(np.array([cachesize, bunch, seed, rnd, fdim, ddim, len(seqs)], np.int32).tobytes())
+        for F_, D_ in seqs:
+            f.write(np.array([F_.shape[0]], np.int32).tobytes() + F_.tobytes() + D_.tobytes())
+    subprocess.check_call([exe, src, out])
+    b = open(out, "rb").read()
+    nb = int(np.frombuffer(b, np.int32, 1)[0])
+    data = np.frombuffer(b, np.float32, nb * bunch * (fdim + ddim), 4).copy()
+    disc = int(np.frombuffer(b, np.int32, 1, 4 + 4 * data.size)[0])
+    return nb, data, disc
