@@ -15,7 +15,7 @@ case "${1:-one}" in
     python -m pytest tests -m gpu -q -rxX > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
     tail -5 gpurun_out/pytest_gpu.log
     ncu --set full --clock-control none --import-source on -k regex:dp_peer_update_kernel -c 8 -o gpurun_out/peer_virtual \
-        python -m pytest tests/test_gpu_kernels.py -q -k "peer and 8-100-260" > gpurun_out/ncu_peer.log 2>&1
+        python -m pytest tests/test_gpu_kernels.py -q -k "peer and 100-260-8" > gpurun_out/ncu_peer.log 2>&1
     python bench.py --steps 50 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
     ;;
   two)
