@@ -245,8 +245,28 @@ def main():
 
     net = host.Net(dims=DIMS, seed=1)
     net.set_hyper(LR, mmt=MMT, wc=WC, gdf=True)
+    dp_schedule = "none"
     if world > 1:
-        net.set_data_parallel(world)
+        dp_schedule = os.environ.get("TNB_DP_MODE", "peer")
+        ok = 1
+        try:
+            net.set_data_parallel(world)
+        except abi.TnbError as e:
+            ok = 0
+            sys.stderr.write("[bench] rank %d: data-parallel set-up (%s) failed: %s\n" % (rank, dp_schedule, e))
+        tt = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+        if int(tt.item()) == 0:
+            if dp_schedule != "peer":
+                raise SystemExit("data-parallel set-up failed")
+            # the peer-memory schedule needs CUDA IPC between the ranks' processes; where that is not available the NCCL schedule
+            # still is — say so loudly and in the JSON line instead of losing the measurement
+            sys.stderr.write("[bench] falling back to TNB_DP_MODE=allreduce (NCCL) on all ranks\n")
+            os.environ["TNB_DP_MODE"] = "allreduce"
+            dp_schedule = "allreduce (peer-memory set-up failed)"
+            net = host.Net(dims=DIMS, seed=1)
+            net.set_hyper(LR, mmt=MMT, wc=WC, gdf=True)
+            net.set_data_parallel(world)
 
     rng = np.random.default_rng(20240607 + rank)
     rows = RESIDENT_BUNCHES * BUNCH
@@ -338,7 +358,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"3xtf32": "tf32x3", "tf32": "tf32", "bf16": "bf16"}[args.math], "data": "synthetic",
             "config": {"workload": WORKLOAD, "dims": DIMS, "bunch_per_gpu": BUNCH, "global_bunch": BUNCH * world,
-                       "parallelism": "dp%d" % world, "dp_schedule": (os.environ.get("TNB_DP_MODE", "peer") if world > 1 else "none"), "learn_rate": LR, "momentum": MMT, "weightcost": WC,
+                       "parallelism": "dp%d" % world, "dp_schedule": dp_schedule, "learn_rate": LR, "momentum": MMT, "weightcost": WC,
                        "l2_note": "no L2 flush: weights+corrections (224 MB) and activations exceed the 126 MB L2 every step",
                        "flops_per_frame": fpf, "gemm_math": args.math},
             "clocks": clocks,
