@@ -414,7 +414,7 @@ class LabelRepository {
   }
   size_t NOutputs() const { return mLabelMap.size(); }
 
-  /// per-frame class ids (-1 = unlabelled); times are divided by sourceRate with round-half-up (Labels.cc:111-112)
+  /// per-frame class ids; times are divided by sourceRate with round-half-up (Labels.cc:111-112); an unlabelled frame is an error
   void GenLabelIds(std::vector<int> &ids, size_t nFrames, size_t sourceRate, const char *pFeatureLogical) {
     if (nFrames < 1) KALDI_ERR << "Number of frames:" << nFrames << " is lower than 1!!!\n" << pFeatureLogical;
     std::map<std::string, std::vector<std::string> >::iterator rec = mRecords.find(BaseKey(pFeatureLogical));
@@ -445,6 +445,15 @@ class LabelRepository {
         ids[fr] = it->second;
       }
     }
+    // every frame must carry a target: the reference refuses an all-zero row of the desired matrix (Labels.cc:161-173; its test
+    // `!sum == 1.0` is true exactly when the row sum is 0)
+    for (size_t i = 0; i < nFrames; i++)
+      if (ids[i] < 0) {
+        std::ostringstream os;
+        os << "Desired vector sum isn't 1.0, " << " file: " << BaseKey(pFeatureLogical) << "." << mExt << " row: " << i << " nframes: " << nFrames
+           << " sum: 0\n";
+        Error(os.str());
+      }
     if (trunc_frames > 10) {
       std::ostringstream os;
       os << "Truncated frames: " << trunc_frames << " Check sourcerate in features and validity of labels\n";

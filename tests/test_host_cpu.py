@@ -197,16 +197,17 @@ def _io_dataset(d):
         f.write("#!MLF!#\n")
         lab = {n: utts[n][1] for n in names}
 
-        def rec(key, ids, jitter=0, extra=""):
+        def rec(key, ids, jitter=0, extra="", skip=-1):
             f.write('"*/%s.lab"\n' % key)
-            start = 0
+            start, seg = 0, 0
             for t in range(1, len(ids) + 1):
                 if t == len(ids) or ids[t] != ids[start]:
                     # boundaries off by less than half a frame must round to the same frame index
                     b = start * P + (jitter if start else 0)
                     e = t * P + (jitter if t < len(ids) else 0)
-                    f.write("%d %d %s%s\n" % (b, e, tags[int(ids[start])], extra))
-                    start = t
+                    if seg != skip:
+                        f.write("%d %d %s%s\n" % (b, e, tags[int(ids[start])], extra))
+                    start, seg = t, seg + 1
             f.write(".\n")
         rec(names[0], lab[names[0]])
         rec("alias_b", lab[names[1]], jitter=-40000)
@@ -262,7 +263,7 @@ def test_feature_and_label_readers_match_the_reference_front_end(tmp_path, ext):
         assert open(ref, "rb").read() == open(mine, "rb").read()
 
 
-@pytest.mark.parametrize("case", ["missing_record", "unknown_tag", "frame_assigned_twice", "range_outside_file", "ok"])
+@pytest.mark.parametrize("case", ["missing_record", "unknown_tag", "frame_assigned_twice", "unlabelled_frames", "range_outside_file", "ok"])
 def test_feature_and_label_reader_errors_match_the_reference(tmp_path, case):
     """Malformed inputs must fail where the reference's readers fail (Labels.cc:55-57,124-145; Features.cc:1193-1195) — and the
     well-formed control must pass in both."""
@@ -280,6 +281,8 @@ def test_feature_and_label_reader_errors_match_the_reference(tmp_path, case):
         rec = rec.replace("s1", "s7")
     elif case == "frame_assigned_twice":
         rec = rec.replace("1000000 2000000", "900000 2000000")      # frame 9 belongs to both segments after rounding
+    elif case == "unlabelled_frames":
+        rec = rec.replace("0 1000000 s0\n", "0 700000 s0\n")               # frames 7..9 carry no target ("Desired vector sum isn't 1.0")
     elif case == "range_outside_file":
         entry = "a.fea=" + fea + "[5,25]"
     open(os.path.join(d, "a.scp"), "w").write(entry + "\n")
