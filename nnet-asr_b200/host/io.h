@@ -403,6 +403,8 @@ class LabelRepository {
         if (line[0] == '"') {
           size_t q = line.rfind('"');
           key = BaseKey(line.substr(1, q > 0 ? q - 1 : std::string::npos));
+          // a name defined twice: the FIRST definition is the one the reference's MLF index finds (MlfStream.tcc:356-372)
+          if (mRecords.find(key) != mRecords.end()) key = std::string("\x01duplicate ") + key;
           mRecords[key].clear();
           in_rec = true;
         }

@@ -175,6 +175,15 @@ def test_fast_text_reader_writer_matches_ostream_format(tmp_path):
 
 
 # ------------------------------------------------------------------------------------------------ front end: HTK / script file / MLF readers
+
+@pytest.fixture(scope="module")
+def feature_io_exe(tmp_path_factory):
+    """tests/cpp/test_feature_io.cc (the drop-in's readers behind the dump format of oracle/ref_tools/io_dump.cc), compiled once"""
+    exe = str(tmp_path_factory.mktemp("feature_io") / "test_feature_io")
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "nnet-asr_b200", "host"), "-I",
+                           os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_feature_io.cc")])
+    return exe
+
 def _io_dataset(d):
     """A small set that exercises the readers: ragged utterances, plain / logical=physical / logical=physical[first,last] script
     entries, label times that need the round-half-up division by the sample period, score columns and comments in the MLF, a
@@ -238,15 +247,13 @@ def _parse_io_dump(path):
 
 
 @pytest.mark.parametrize("ext", [(0, 0), (2, 2), (4, 1)])
-def test_feature_and_label_readers_match_the_reference_front_end(tmp_path, ext):
+def test_feature_and_label_readers_match_the_reference_front_end(tmp_path, ext, feature_io_exe):
     """nnet-asr_b200/host/io.h (FeatureRepository: script-file entries, byte order, STARTFRMEXT/ENDFRMEXT replication; LabelRepository:
     MLF records by logical base name, time -> frame rounding, truncation) against the reference's own KaldiLib readers driven in
     the trainer's call order (oracle/ref_tools/io_dump.cc -> oracle/_ref/RefIoDump), and against the committed dump of that tool."""
     d = str(tmp_path)
     scp, mlf, lmap = _io_dataset(d)
-    exe = str(tmp_path / "test_feature_io")
-    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "nnet-asr_b200", "host"), "-I",
-                           os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_feature_io.cc")])
+    exe = feature_io_exe
     mine = str(tmp_path / "mine.bin")
     subprocess.check_call([exe, scp, mlf, lmap, str(ext[0]), str(ext[1]), "1", mine, "*/"])     # -L "*/" -X lab, as the scripts run it
     got = _parse_io_dump(mine)
@@ -264,7 +271,7 @@ def test_feature_and_label_readers_match_the_reference_front_end(tmp_path, ext):
 
 
 @pytest.mark.parametrize("case", ["missing_record", "unknown_tag", "frame_assigned_twice", "unlabelled_frames", "range_outside_file", "ok"])
-def test_feature_and_label_reader_errors_match_the_reference(tmp_path, case):
+def test_feature_and_label_reader_errors_match_the_reference(tmp_path, case, feature_io_exe):
     """Malformed inputs must fail where the reference's readers fail (Labels.cc:55-57,124-145; Features.cc:1193-1195) — and the
     well-formed control must pass in both."""
     d = str(tmp_path)
@@ -287,9 +294,7 @@ def test_feature_and_label_reader_errors_match_the_reference(tmp_path, case):
         entry = "a.fea=" + fea + "[5,25]"
     open(os.path.join(d, "a.scp"), "w").write(entry + "\n")
     open(os.path.join(d, "a.mlf"), "w").write("#!MLF!#\n" + rec)
-    exe = str(tmp_path / "test_feature_io")
-    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "nnet-asr_b200", "host"), "-I",
-                           os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_feature_io.cc")])
+    exe = feature_io_exe
     args = [os.path.join(d, "a.scp"), os.path.join(d, "a.mlf"), os.path.join(d, "map"), "1", "1", "1"]
     mine = subprocess.run([exe] + args + [os.path.join(d, "mine.bin"), "*/"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert (mine.returncode == 0) == (case == "ok"), mine.stderr[-500:]
@@ -332,12 +337,10 @@ def test_config_file_and_option_dump_like_the_reference(tmp_path):
         assert norm(_config_block(ref.stdout)) == norm(block)
 
 
-def test_make_htk_file_name_like_the_reference(tmp_path):
+def test_make_htk_file_name_like_the_reference(tmp_path, feature_io_exe):
     """MakeHtkFileName (Common.cc:118-175: output names from -M/-o, label names from -L/-X, TFeaCat's -l/-y): directory, extension
     and the `/./` marker that keeps a sub-path — expected strings from the reference's function, compared live where it is built."""
-    exe = str(tmp_path / "test_feature_io")
-    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "nnet-asr_b200", "host"), "-I",
-                           os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_feature_io.cc")])
+    exe = feature_io_exe
     cases = [(("a/b/c.fea", "out", "lab"), "out/c.lab"), (("a/b/c.fea", "-", "lab"), "a/b/c.lab"), (("a/b/c.fea", "out", "-"), "out/c.fea"),
              (("x/./sub/c.d.fea", "out", "ext"), "out/sub/c.d.ext"), (("c", "-", "-"), "c"), (("-", "out", "lab"), "-"),
              (("a/b/c.fea", "", "lab"), "c.lab"), (("a.b/c", "o", "e"), "o/c.e"), (("/abs/dir/name.x.y", "*", "lab"), "*/name.x.lab")]
@@ -349,14 +352,12 @@ def test_make_htk_file_name_like_the_reference(tmp_path):
             assert subprocess.check_output([ref_exe, "--htkname"] + list(args), text=True).rstrip("\n") == got, args
 
 
-def test_htk_writer_and_header_checks_like_the_reference(tmp_path):
+def test_htk_writer_and_header_checks_like_the_reference(tmp_path, feature_io_exe):
     """FeatureRepository::WriteFeatureMatrix as TFeaCat uses it (TFeaCat.cc:262): a script-file entry read with context rows and
     written back must give the reference's bytes (header: frame count, source sample period, size, USER kind; big-endian data);
     headers the reference rejects (Features.cc:522-528: sample period outside [0, 100000] — also what a wrong byte order looks like)
     must be rejected."""
-    exe = str(tmp_path / "test_feature_io")
-    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "nnet-asr_b200", "host"), "-I",
-                           os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_feature_io.cc")])
+    exe = feature_io_exe
     ref_exe = os.path.join(ROOT, "oracle", "_ref", "RefIoDump")
     r = np.random.default_rng(1)
     x = r.standard_normal((12, 5)).astype(np.float32)
@@ -381,13 +382,11 @@ def test_htk_writer_and_header_checks_like_the_reference(tmp_path):
             assert rc != 0, (tool, args)
 
 
-def test_matrix_vector_text_parsing_like_the_reference(tmp_path):
+def test_matrix_vector_text_parsing_like_the_reference(tmp_path, feature_io_exe):
     """The text operators the network files are read with (tnet_base.h) against the reference's (Matrix.tcc:575-600,
     Vector.tcc:527-547, i.e. `istream >> float`): same values for every syntax the reference accepts, refusal where it refuses
     ("nan"/"inf" of a diverged network, hexadecimal floats, values beyond the float range, truncated or malformed matrices)."""
-    exe = str(tmp_path / "test_feature_io")
-    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "nnet-asr_b200", "host"), "-I",
-                           os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_feature_io.cc")])
+    exe = feature_io_exe
     ref_exe = os.path.join(ROOT, "oracle", "_ref", "RefIoDump")
     f32 = lambda *v: np.array(v, np.float32).tobytes()
     i32 = lambda *v: np.array(v, np.int32).tobytes()
@@ -412,3 +411,49 @@ def test_matrix_vector_text_parsing_like_the_reference(tmp_path):
                 assert rc != 0, (tool, txt)
             else:
                 assert rc == 0 and open(out, "rb").read() == want, (tool, txt)
+
+
+_MLF_REC = '"*/a.lab"\n0 1000000 s0\n1000000 2000000 s1\n.\n'
+_FRONT_END_VARIANTS = {   # name: (overrides, expected to be accepted)
+    "no_mlf_header": (dict(mlf=_MLF_REC), True),
+    "crlf": (dict(mlf=("#!MLF!#\n" + _MLF_REC).replace("\n", "\r\n")), True),
+    "map_extra_cols": (dict(map="s0 extra\ns1\n"), True),
+    "trailing_spaces": (dict(mlf='#!MLF!#\n"*/a.lab"  \n0 1000000 s0  \n1000000 2000000 s1\t\n.\n'), True),
+    "name_defined_twice": (dict(mlf="#!MLF!#\n" + _MLF_REC + '"*/a.lab"\n0 1000000 s1\n1000000 2000000 s0\n.\n'), True),   # first wins
+    "scp_blank_and_spaces": (dict(scp="\n  {fea}  \n\n"), True),
+    "scp_range_single": (dict(scp="a.fea={fea}[4,4]\n", mlf='#!MLF!#\n"*/a.lab"\n0 100000 s1\n.\n'), True),
+    "negative_time": (dict(mlf='#!MLF!#\n"*/a.lab"\n-5 1000000 s0\n1000000 2000000 s1\n.\n'), True),
+    "comment_in_record": (dict(mlf='#!MLF!#\n"*/a.lab"\n# c\n0 1000000 s0\n1000000 2000000 s1\n.\n'), True),
+    "missing_final_dot": (dict(mlf='#!MLF!#\n"*/a.lab"\n0 1000000 s0\n1000000 2000000 s1\n'), True),
+    "label_without_times": (dict(mlf='#!MLF!#\n"*/a.lab"\ns0\n.\n'), False),
+    "label_with_start_only": (dict(mlf='#!MLF!#\n"*/a.lab"\n0 s0\n.\n'), False),
+    "float_times": (dict(mlf='#!MLF!#\n"*/a.lab"\n0.0 1000000.0 s0\n1000000 2000000 s1\n.\n'), False),
+    "scp_missing_file": (dict(scp="{dir}/nofile.fea\n"), False),
+    "scp_range_reversed": (dict(scp="a.fea={fea}[7,3]\n"), False),
+    "duplicate_tag_in_map": (dict(map="s0\ns1\ns0\n"), False),
+    "empty_map": (dict(map=""), False),
+}
+
+
+@pytest.mark.parametrize("name", sorted(_FRONT_END_VARIANTS))
+def test_front_end_input_variants_like_the_reference(tmp_path, name, feature_io_exe):
+    """Spellings of script files, MLFs and label maps that occur in practice: accepted and refused alike by the drop-in's readers and
+    by the reference's (live where oracle/_ref/RefIoDump exists), and read to the same bytes when accepted."""
+    over, accepted = _FRONT_END_VARIANTS[name]
+    d = str(tmp_path)
+    x = np.random.default_rng(3).standard_normal((20, 5)).astype(np.float32)
+    fea = os.path.join(d, "a.fea")
+    F.write_htk(fea, x)
+    open(os.path.join(d, "a.scp"), "w").write(over.get("scp", "{fea}\n").format(fea=fea, dir=d))
+    open(os.path.join(d, "a.mlf"), "w", newline="").write(over.get("mlf", "#!MLF!#\n" + _MLF_REC))
+    open(os.path.join(d, "map"), "w").write(over.get("map", "s0\ns1\n"))
+    exe = feature_io_exe
+    args = [os.path.join(d, "a.scp"), os.path.join(d, "a.mlf"), os.path.join(d, "map"), "1", "1", "1"]
+    mine = subprocess.run([exe] + args + [os.path.join(d, "mine.bin"), "*/"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert (mine.returncode == 0) == accepted, mine.stderr[-400:]
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "RefIoDump")
+    if os.path.exists(ref_exe):
+        ref = subprocess.run([ref_exe] + args + [os.path.join(d, "ref.bin"), "*/"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert (ref.returncode == 0) == accepted, ref.stderr[-400:]
+        if accepted:
+            assert open(os.path.join(d, "ref.bin"), "rb").read() == open(os.path.join(d, "mine.bin"), "rb").read()
