@@ -308,7 +308,10 @@ def test_feature_and_label_reader_errors_match_the_reference(tmp_path, case, fea
 
 def _config_block(txt):
     lines = txt.splitlines()
-    i = [k for k, l in enumerate(lines) if l.startswith("Configuration Parameters[")][0]
+    at = [k for k, l in enumerate(lines) if l.startswith("Configuration Parameters[")]
+    if not at:
+        return None                 # the command line was refused before the dump
+    i = at[0]
     n = int(lines[i].split("[")[1].split("]")[0])
     return lines[i:i + 1 + n]
 
@@ -330,11 +333,19 @@ def test_config_file_and_option_dump_like_the_reference(tmp_path):
     assert "  %-35s = %-30s # -C" % ("TNET:SEED", "7") in block
     ref_exe = os.path.join(ROOT, "oracle", "_ref", "TNet")
     if os.path.exists(ref_exe):
-        ref = subprocess.run([ref_exe] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         # "# " marks parameters not read yet at the time of the dump; the two mains read theirs in a different order, so the marker
         # column is compared after normalisation and everything else verbatim
         norm = lambda ls: [l[2:] if l[:2] in ("  ", "# ") else l for l in ls]
-        assert norm(_config_block(ref.stdout)) == norm(block)
+        more = [["-D", "--learningrate=0.5", "-H", "x"], ["-D", "-n", "1", "-n", "2", "-H", "x"], ["-D", "-T", "3", "-H", "x"],
+                ["-D", "--BUNCHSIZE", "64", "-H", "x"], ["-D", "-c", "-H", "x"], ["-D", "--CROSSVALIDATE=t", "-H", "x"],
+                ["-D", "-H", "x", "-S", "a.scp", "extra1", "extra2"], ["-D", "--TNET:SEED=5", "-H", "x"], ["-D", "-A", "-V", "-H", "x"]]
+        for a in [args] + more:
+            ref = subprocess.run([ref_exe] + a, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            got = subprocess.run([os.path.join(BIN, "TNetCu")] + a, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            rb, gb = _config_block(ref.stdout), _config_block(got.stdout)
+            assert (rb is None) == (gb is None), a
+            assert rb is None or norm(rb) == norm(gb), a
+            assert (ref.returncode != 0) and (got.returncode != 0)
 
 
 def test_make_htk_file_name_like_the_reference(tmp_path, feature_io_exe):
