@@ -7,7 +7,7 @@
 #include "main_common.h"
 
 using namespace TNet;
-#define SNAME "TNORMCU"
+#define SNAME "TNORM"
 
 int main(int argc, char *argv[]) try {
   const char *p_option_string =

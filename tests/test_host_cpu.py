@@ -468,3 +468,26 @@ def test_front_end_input_variants_like_the_reference(tmp_path, name, feature_io_
         assert (ref.returncode == 0) == accepted, ref.stderr[-400:]
         if accepted:
             assert open(os.path.join(d, "ref.bin"), "rb").read() == open(os.path.join(d, "mine.bin"), "rb").read()
+
+
+@pytest.mark.parametrize("mine,ref,lines", [
+    ("TFeaCatCu", "TFeaCat", [["-D", "-H", "x", "-l", "outdir", "-y", "post", "-S", "a.scp"], ["-D", "-H", "x", "--LOGPOSTERIOR=TRUE"],
+                              ["-D", "-H", "x", "-T", "1", "--STARTFRMEXT=3", "--ENDFRMEXT=3"]]),
+    ("TNormCu", "TNorm", [["-D", "-H", "x", "--TARGETMMF=out.t"], ["-D", "-H", "x", "-T", "1", "--STARTFRMEXT=3", "--ENDFRMEXT=3"],
+                          ["-D", "-H", "x", "-S", "a.scp", "--NATURALREADORDER=T"]]),
+])
+def test_tool_option_maps_like_the_reference(mine, ref, lines):
+    """The forward-only and normalisation tools name their parameters like the reference's (module prefix, short-option mapping): the
+    -D dump of the drop-in equals the reference CPU tool's for the same command line (the GPU tools share SNAME and option map with
+    their CPU twins: TFeaCat.cc:40 / TFeaCatCu.cc:43, TNorm.cc:46 / TNormCu.cc:47).  Live comparison where oracle/_ref exists."""
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", ref)
+    norm = lambda ls: [l[2:] if l[:2] in ("  ", "# ") else l for l in ls]
+    for a in lines:
+        got = subprocess.run([os.path.join(BIN, mine)] + a, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        gb = _config_block(got.stdout)
+        assert gb is not None and got.returncode != 0, a
+        prefix = {"TFeaCatCu": "TFEACAT:", "TNormCu": "TNORM:"}[mine]
+        assert all(l[2:].startswith(prefix) for l in gb[1:]), gb
+        if os.path.exists(ref_exe):
+            r = subprocess.run([ref_exe] + a, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            assert norm(_config_block(r.stdout)) == norm(gb), a
