@@ -141,6 +141,7 @@ NET_CASES = {
                          cache=512, lr=0.6, mmt=0.5, wc=1e-4, gdf=True, seed=63, randomize=True),
 }
 NET_GPU_ONLY = {"net_shared_mmt", "net_discrete"}
+LAST_FINAL_TEXT = None
 
 
 def build_net(cfg, rng):
@@ -180,6 +181,8 @@ def run_net(case, cfg, impl, workdir, exe=None, save=True):
     if res.returncode != 0:
         raise RuntimeError("reference failed:\n" + res.stdout[-3000:])
     rep = parse_report(res.stdout)
+    global LAST_FINAL_TEXT
+    LAST_FINAL_TEXT = open(final).read()       # the written network file as text (tests compare its layout with the reference's)
     if not save:
         return rep, F.read_mlp(final), res.stdout
     names = list(utts.keys())

@@ -59,6 +59,22 @@ def test_tnetcu_binary_offset_gemm_layers(fixture):
         compare_layer(a, b, 2e-4, btol_floor=1e-2)
 
 
+@pytest.mark.xfail(strict=False, reason="added after the round-1 GPU budget was spent: not yet run on a B200")
+@pytest.mark.parametrize("fixture", [f for f in _net_cases() if f.startswith("gpu_")])
+def test_written_network_file_has_the_reference_layout(fixture):
+    """The network file bin/TNetCu writes has, token for token, the layout of the file the reference TNetCu wrote for the same run
+    (tags, dimensions, block counts, `m rows cols` / `v dim` headers, line structure) — only the numbers may differ in their last
+    printed digit."""
+    import re
+    impl, case = fixture.split("_", 1)
+    g = np.load(os.path.join(GOLD, fixture + ".npz"))
+    with tempfile.TemporaryDirectory() as d:
+        MG.run_net(case, MG.NET_CASES[case], "gpu", d, exe=os.path.join(BIN, "TNetCu"), save=False)
+    mask = lambda t: [re.sub(r"-?\d[\d.e+-]*", "#", l) if not l.startswith(("<", "m ", "v ")) else re.sub(r"(?<=\d) +-?[\d.].*", " #...", l)
+                      for l in t.split("\n")]
+    assert mask(MG.LAST_FINAL_TEXT) == mask(bytes(g["final_net"]).decode())
+
+
 def test_trbmcu_binary_rbmsparse():
     """bin/TRbmCu accepts an <rbmsparse> layer like the reference (TRbmCu.cc:229) and writes the tag and the sparsity cost back;
     with the reference's GPU run as fixture (gpu_rbm_sparse_bb.npz, when generated) the result must match it."""
