@@ -114,7 +114,7 @@ class Matrix {
     for (size_t i = 0; i < d_.size(); i++)
       if (std::isnan((double)d_[i]) || std::isinf((double)d_[i])) {
         std::ostringstream os;
-        os << "Invalid value: " << d_[i] << " in matrix " << name << " at row " << i / (c_ ? c_ : 1) << " col " << i % (c_ ? c_ : 1);
+        os << "Invalid value: " << d_[i] << " in matrix row: " << i / (c_ ? c_ : 1) << " col: " << i % (c_ ? c_ : 1) << " file: " << name;  // Matrix.h:238-251
         Error(os.str());
       }
   }
