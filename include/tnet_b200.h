@@ -47,7 +47,8 @@ enum {
   TNB_ERR_CUDA = 1,     /* CUDA runtime/driver error; text via tnb_last_error() */
   TNB_ERR_ARG = 2,      /* bad dimension / alignment / null pointer */
   TNB_ERR_UNSUPPORTED = 3,
-  TNB_ERR_NCCL = 4
+  TNB_ERR_NCCL = 4,
+  TNB_ERR_COMM = 5      /* a data-parallel rank gave up waiting for a peer (peer-memory schedule); text says which */
 };
 
 /* GEMM arithmetic (north_star: "fp32-equivalent via 3xTF32 as the default, bf16 reported separately") */
@@ -337,6 +338,15 @@ int tnb_dp_peer_update(TnbContext *ctx, const TnbPeerJob *job, void *wait_event,
 /* the same kernel for an explicit rank / world / flag blocks (64 zero-initialised words per rank) / sequence number (1, 2, ... per
  * launch) on a given stream of the context: lets a test play several ranks on one GPU */
 int tnb_dp_peer_update_on(TnbContext *ctx, int stream_id, const TnbPeerJob *job, int rank, int world, unsigned *const *flags, unsigned seq);
+/* ALL `world` ranks of one layer's exchange as ONE cooperative grid on this context's GPU (jobs[r] = rank r's job; CTAs
+ * [r*c, (r+1)*c) play rank r, c = min(ctas_per_rank or the default, what is co-resident)): the way to run the multi-rank kernel on
+ * a single GPU — separate launches that wait for each other's flags are not guaranteed to be co-resident.  Synchronous; returns
+ * TNB_ERR_COMM if a rank's wait ran out of time. */
+int tnb_dp_peer_update_virtual(TnbContext *ctx, const TnbPeerJob *jobs, int world, unsigned *const *flags, unsigned seq, int ctas_per_rank);
+/* TNB_OK, or TNB_ERR_COMM with a message naming the rank and flag a peer-memory kernel of this context gave up waiting for (a wait
+ * that exceeds TNB_PEER_TIMEOUT_MS ends the kernel without touching the weights and without poisoning the CUDA context; 0 = no
+ * limit).  Synchronises nothing itself: call it after tnb_ctx_sync / an event wait.  tnb_ctx_sync calls it. */
+int tnb_peer_status(TnbContext *ctx);
 
 #ifdef __cplusplus
 }

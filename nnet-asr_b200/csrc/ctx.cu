@@ -245,7 +245,7 @@ int tnb_ctx_sync(TnbContext *ctx) {
   TNB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
   TNB_CUDA(cudaStreamSynchronize(ctx->aux_stream));
   TNB_CUDA(cudaStreamSynchronize(ctx->aux2_stream));
-  return TNB_OK;
+  return ctx->peer_flags[ctx->rank] ? tnb_peer_status(ctx) : TNB_OK;  // a peer-memory kernel that gave up waiting says so here
 }
 int tnb_ctx_free_memory(TnbContext *ctx, size_t *fr, size_t *tot) {
   TNB_ARG(ctx && fr && tot, "null");

@@ -17,7 +17,14 @@
 //   done[r]  = s : rank r has finished its stores for kernel s (fence.sys before the flag).
 // A kernel starts its loads when all ready flags have reached s and ends when all done flags have: after it, this rank's
 // weights are complete and nobody reads its gradient buffer any more.  All ranks issue the same kernels in the same order on
-// their communication stream (like a collective).  Every wait is bounded (trap, not hang).
+// their communication stream (like a collective).  Every wait is bounded: a rank that waits longer than TNB_PEER_TIMEOUT_MS
+// (default 10 s; 0 = no limit) writes {phase, peer it was waiting for, sequence number} into word 33 of its own flag block and
+// leaves the kernel WITHOUT touching the weights; the CUDA context stays usable and tnb_peer_status / tnb_ctx_sync report which
+// rank stalled (a __trap() here would poison every rank's context for a rank that was merely late, e.g. in file I/O).
+//
+// On ONE GPU several ranks must not be played as separate launches that wait for each other (nothing guarantees that they are
+// co-resident): dp_peer_update_virtual_kernel runs all ranks' work as ONE cooperative grid (tnb_dp_peer_update_virtual), which is
+// what the tests and the ncu capture of this kernel use.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -28,12 +35,12 @@ struct PeerArgs {
   int rank, world;
   const float *G[TNB_MAX_PEERS];
   float *W[TNB_MAX_PEERS];
-  unsigned *flags[TNB_MAX_PEERS];  // per rank: [0,16) ready, [16,32) done, [32] arrival counter of the owner's own CTAs
+  unsigned *flags[TNB_MAX_PEERS];  // per rank: [0,16) ready, [16,32) done, [32] arrival counter of the owner's own CTAs, [33] error word
   float *corr, *bias, *corrb;      // local
   int cols, stride, shard, rows_pad;
   float mmt, scale, l2;
   unsigned seq;
-  long long timeout;  // cycles
+  long long timeout;  // cycles; 0 = wait for ever
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
@@ -44,34 +51,43 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// threads [0, world) of the CTA each poll one flag until it has reached seq (wrap-safe compare), then the CTA proceeds
-__device__ __forceinline__ void wait_flags(const unsigned *f, int world, unsigned seq, long long timeout) {
+// threads [0, world) of the CTA each poll one flag until it has reached seq (wrap-safe compare).  Returns false for the whole CTA
+// when a wait ran out of time; the error word of this rank's flag block then says what it was waiting for.
+__device__ __forceinline__ bool wait_flags(unsigned *my, int off, int world, unsigned seq, long long timeout) {
+  int bad = 0;
   if ((int)threadIdx.x < world) {
     const long long t0 = clock64();
-    while ((int)(ld_acquire_sys(f + threadIdx.x) - seq) < 0) {
-      if (clock64() - t0 > timeout) __trap();
+    while ((int)(ld_acquire_sys(my + off + threadIdx.x) - seq) < 0) {
+      if (timeout > 0 && clock64() - t0 > timeout) {
+        // 0x80000000 | phase (0 = ready, 1 = done) << 24 | peer << 16 | low 16 bits of the sequence number
+        atomicCAS(my + 33, 0u, 0x80000000u | ((unsigned)(off ? 1 : 0) << 24) | ((unsigned)threadIdx.x << 16) | (seq & 0xFFFFu));
+        bad = 1;
+        break;
+      }
       __nanosleep(100);
     }
   }
-  __syncthreads();
+  return __syncthreads_or(bad) == 0;
 }
 
 __device__ __forceinline__ float4 ldg_f4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 
 // WORLD > 0: compile-time rank count (all loads of U items issued before the first use); WORLD == 0: any rank count, one item at a time
+// bid / nblk: this CTA's index among the CTAs working for rank a.rank and their number (the grid of dp_peer_update_kernel; one
+// slice of the grid of dp_peer_update_virtual_kernel)
 template <int WORLD, int U>
-__global__ void __launch_bounds__(512) dp_peer_update_kernel(const __grid_constant__ PeerArgs a) {
+__device__ __forceinline__ void peer_update_body(const PeerArgs &a, const int bid, const int nblk) {
   const int world = WORLD > 0 ? WORLD : a.world;
   unsigned *my = a.flags[a.rank];
-  if (blockIdx.x == 0 && (int)threadIdx.x < world) st_release_sys(a.flags[threadIdx.x] + a.rank, a.seq);
-  wait_flags(my, world, a.seq, a.timeout);
+  if (bid == 0 && (int)threadIdx.x < world) st_release_sys(a.flags[threadIdx.x] + a.rank, a.seq);
+  if (!wait_flags(my, 0, world, a.seq, a.timeout)) return;
 
   const int vcols = (a.cols + 3) >> 2;
   const long total = (long)a.shard * vcols;
   const size_t row0 = (size_t)a.rank * a.shard;
-  const long step = (long)gridDim.x * blockDim.x;
+  const long step = (long)nblk * blockDim.x;
   if (WORLD > 0 && (a.cols & 3) == 0) {
-    for (long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += step * U) {
+    for (long i0 = (long)bid * blockDim.x + threadIdx.x; i0 < total; i0 += step * U) {
       float4 g[U][WORLD > 0 ? WORLD : 1], k[U], w[U];
       size_t base[U];
 #pragma unroll
@@ -104,7 +120,7 @@ __global__ void __launch_bounds__(512) dp_peer_update_kernel(const __grid_consta
     }
   } else {  // any rank count / column count: scalar
     const long total_s = (long)a.shard * a.cols;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total_s; i += step) {
+    for (long i = (long)bid * blockDim.x + threadIdx.x; i < total_s; i += step) {
       const size_t base = (row0 + (size_t)(i / a.cols)) * a.stride + (size_t)(i % a.cols);
       float s = a.G[0][base];
       for (int r = 1; r < world; r++) s += a.G[r][base];
@@ -118,7 +134,7 @@ __global__ void __launch_bounds__(512) dp_peer_update_kernel(const __grid_consta
   // bias: every rank sums all ranks' bias gradients (row rows_pad of the gradient buffers) in the same order and updates its own copy
   if (a.bias) {
     const size_t gb = (size_t)a.rows_pad * a.stride;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.cols; c += (int)step) {
+    for (int c = bid * blockDim.x + threadIdx.x; c < a.cols; c += (int)step) {
       float s = a.G[0][gb + c];
       for (int r = 1; r < world; r++) s += a.G[r][gb + c];
       const float kk = s + a.mmt * a.corrb[c];
@@ -131,13 +147,29 @@ __global__ void __launch_bounds__(512) dp_peer_update_kernel(const __grid_consta
   __threadfence_system();
   __syncthreads();
   __shared__ int last;
-  if (threadIdx.x == 0) last = (atomicAdd(my + 32, 1u) == gridDim.x - 1) ? 1 : 0;
+  if (threadIdx.x == 0) last = (atomicAdd(my + 32, 1u) == (unsigned)nblk - 1) ? 1 : 0;
   __syncthreads();
   if (!last) return;
   if (threadIdx.x == 0) my[32] = 0;  // for the next launch (which starts after this kernel has ended)
   __threadfence_system();
   if ((int)threadIdx.x < world) st_release_sys(a.flags[threadIdx.x] + 16 + a.rank, a.seq);
-  wait_flags(my + 16, world, a.seq, a.timeout);
+  wait_flags(my, 16, world, a.seq, a.timeout);
+}
+
+template <int WORLD, int U>
+__global__ void __launch_bounds__(512) dp_peer_update_kernel(const __grid_constant__ PeerArgs a) {
+  peer_update_body<WORLD, U>(a, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// All ranks of a layer's exchange as ONE grid on one GPU (tests, ncu): CTAs [v*ctas, (v+1)*ctas) play rank v with args[v].  Launched
+// cooperatively, so that every CTA is resident while the slices wait for each other's flags.
+template <int WORLD, int U>
+__global__ void __launch_bounds__(512) dp_peer_update_virtual_kernel(const PeerArgs *__restrict__ args, int ctas) {
+  __shared__ PeerArgs a;
+  const int v = (int)blockIdx.x / ctas;
+  for (int i = threadIdx.x; i < (int)(sizeof(PeerArgs) / 4); i += blockDim.x) ((unsigned *)&a)[i] = ((const unsigned *)(args + v))[i];
+  __syncthreads();
+  peer_update_body<WORLD, U>(a, (int)blockIdx.x - v * ctas, ctas);
 }
 
 static int peer_ctas() {
@@ -148,19 +180,24 @@ static int peer_ctas() {
 }
 static long long peer_timeout_cycles() {
   static long long t = -1;
-  if (t < 0) { const char *e = getenv("TNB_PEER_TIMEOUT_MS"); t = (long long)(e ? atof(e) : 10000.0) * 2000000LL; }  // ~2 GHz
+  if (t < 0) {  // milliseconds -> cycles at ~2 GHz, evaluated in double (0.5 ms is 1e6 cycles, not 0); 0 or less: no limit
+    const char *e = getenv("TNB_PEER_TIMEOUT_MS");
+    const double ms = e ? atof(e) : 10000.0;
+    t = ms > 0.0 ? (long long)(ms * 2.0e6) : 0;
+    if (ms > 0.0 && t < 1) t = 1;
+  }
   return t;
 }
 
-static int launch_peer_update(TnbContext *ctx, cudaStream_t stream, const TnbPeerJob *job, int rank, int world, unsigned *const *flags,
-                              unsigned seq) {
-  TNB_ARG(ctx && job && flags, "null");
+// argument block of one rank's kernel from its job description
+static int fill_peer_args(const TnbPeerJob *job, int rank, int world, unsigned *const *flags, unsigned seq, PeerArgs *out, long *blocks) {
+  TNB_ARG(job && flags, "null");
   TNB_ARG(world >= 1 && world <= TNB_MAX_PEERS && rank >= 0 && rank < world, "rank/world");
   const TnbMatrixDim d = job->dW;
   TNB_ARG(d.rows > 0 && d.cols > 0 && d.stride >= d.cols && (d.stride & 3) == 0 && job->n_frames > 0, "dims");
   TNB_ARG(job->rows_pad >= d.rows && job->rows_pad % world == 0, "rows_pad must be a multiple of the world size, at least dW.rows");
   TNB_ARG(job->corrW && ((job->bias && job->corrb) || (!job->bias && !job->corrb)), "null");
-  PeerArgs a;
+  PeerArgs &a = *out;
   memset(&a, 0, sizeof(a));
   a.rank = rank; a.world = world;
   for (int r = 0; r < world; r++) {
@@ -176,9 +213,20 @@ static int launch_peer_update(TnbContext *ctx, cudaStream_t stream, const TnbPee
   a.seq = seq;
   a.timeout = peer_timeout_cycles();
   const long items = (long)a.shard * ((d.cols + 3) / 4);
-  long blocks = (items + 511) / 512;
-  if (blocks > peer_ctas()) blocks = peer_ctas();
-  if (blocks < 1) blocks = 1;
+  long nb = (items + 511) / 512;
+  if (nb > peer_ctas()) nb = peer_ctas();
+  if (nb < 1) nb = 1;
+  *blocks = nb;
+  return TNB_OK;
+}
+
+static int launch_peer_update(TnbContext *ctx, cudaStream_t stream, const TnbPeerJob *job, int rank, int world, unsigned *const *flags,
+                              unsigned seq) {
+  TNB_ARG(ctx != nullptr, "null");
+  PeerArgs a;
+  long blocks = 1;
+  int rc = fill_peer_args(job, rank, world, flags, seq, &a, &blocks);
+  if (rc != TNB_OK) return rc;
   const dim3 grid((unsigned)blocks), block(512);
   switch (world) {
     case 1: dp_peer_update_kernel<1, 4><<<grid, block, 0, stream>>>(a); break;
@@ -189,6 +237,13 @@ static int launch_peer_update(TnbContext *ctx, cudaStream_t stream, const TnbPee
   }
   TNB_LAUNCHED(ctx);
   return TNB_OK;
+}
+
+// decode the error word a timed-out wait left in a rank's flag block (0 = none)
+static void describe_peer_error(unsigned w, int rank, char *buf, size_t n) {
+  snprintf(buf, n, "rank %d: peer-memory update kernel %u (low 16 bits of its sequence number) gave up waiting for rank %u's %s flag "
+           "(TNB_PEER_TIMEOUT_MS): the ranks did not issue the same sequence of updates, or that rank is stalled",
+           rank, w & 0xFFFFu, (w >> 16) & 0xFFu, ((w >> 24) & 1u) ? "done" : "ready");
 }
 
 // the per-context flag block, mapped from every rank (collective, first use)
@@ -271,6 +326,68 @@ int tnb_dp_peer_update_on(TnbContext *ctx, int stream_id, const TnbPeerJob *job,
   cudaStream_t s = stream_of(ctx, stream_id);
   TNB_ARG(s != nullptr, "unknown stream id");
   return launch_peer_update(ctx, s, job, rank, world, flags, seq);
+}
+
+int tnb_dp_peer_update_virtual(TnbContext *ctx, const TnbPeerJob *jobs, int world, unsigned *const *flags, unsigned seq, int ctas_per_rank) {
+  TNB_ARG(ctx && jobs && flags, "null");
+  TNB_ARG(world >= 1 && world <= TNB_MAX_PEERS, "world");
+  std::vector<PeerArgs> args((size_t)world);
+  long blocks = 1;
+  for (int r = 0; r < world; r++) {
+    long nb = 1;
+    int rc = fill_peer_args(&jobs[r], r, world, flags, seq, &args[(size_t)r], &nb);
+    if (rc != TNB_OK) return rc;
+    if (r == 0) blocks = nb;
+    TNB_ARG(nb == blocks, "the ranks' jobs must describe the same layer");
+  }
+  if (ctas_per_rank > 0 && ctas_per_rank < blocks) blocks = ctas_per_rank;
+  while (blocks > 1 && blocks * world > ctx->sm_count) blocks--;  // one CTA per SM is always co-resident
+  PeerArgs *dargs = nullptr;
+  TNB_CUDA(cudaMalloc(&dargs, sizeof(PeerArgs) * (size_t)world));
+  cudaError_t e = cudaMemcpyAsync(dargs, args.data(), sizeof(PeerArgs) * (size_t)world, cudaMemcpyHostToDevice, ctx->stream);
+  int ctas = (int)blocks;
+  void *kargs[2] = {(void *)&dargs, (void *)&ctas};
+  const dim3 grid((unsigned)(blocks * world)), block(512);
+  if (e == cudaSuccess) {
+    switch (world) {
+      case 1: e = cudaLaunchCooperativeKernel((const void *)dp_peer_update_virtual_kernel<1, 4>, grid, block, kargs, 0, ctx->stream); break;
+      case 2: e = cudaLaunchCooperativeKernel((const void *)dp_peer_update_virtual_kernel<2, 4>, grid, block, kargs, 0, ctx->stream); break;
+      case 4: e = cudaLaunchCooperativeKernel((const void *)dp_peer_update_virtual_kernel<4, 2>, grid, block, kargs, 0, ctx->stream); break;
+      case 8: e = cudaLaunchCooperativeKernel((const void *)dp_peer_update_virtual_kernel<8, 2>, grid, block, kargs, 0, ctx->stream); break;
+      default: e = cudaLaunchCooperativeKernel((const void *)dp_peer_update_virtual_kernel<0, 1>, grid, block, kargs, 0, ctx->stream); break;
+    }
+  }
+  if (e == cudaSuccess) { ctx->launches++; e = cudaStreamSynchronize(ctx->stream); }
+  cudaFree(dargs);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("virtual peer update: CUDA error %d (%s)", (int)e, cudaGetErrorString(e));
+    return TNB_ERR_CUDA;
+  }
+  for (int r = 0; r < world; r++) {
+    unsigned w = 0;
+    TNB_CUDA(cudaMemcpy(&w, flags[r] + 33, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    if (w) {
+      char buf[320];
+      describe_peer_error(w, r, buf, sizeof(buf));
+      set_error("%s", buf);
+      return TNB_ERR_COMM;
+    }
+  }
+  return TNB_OK;
+}
+
+int tnb_peer_status(TnbContext *ctx) {
+  TNB_ARG(ctx != nullptr, "null");
+  unsigned *my = ctx->peer_flags[ctx->rank];
+  if (!my) return TNB_OK;
+  unsigned w = 0;
+  TNB_CUDA(cudaMemcpy(&w, my + 33, sizeof(unsigned), cudaMemcpyDeviceToHost));
+  if (!w) return TNB_OK;
+  char buf[320];
+  describe_peer_error(w, ctx->rank, buf, sizeof(buf));
+  set_error("%s", buf);
+  return TNB_ERR_COMM;
 }
 
 }  // extern "C"

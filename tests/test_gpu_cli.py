@@ -59,7 +59,6 @@ def test_tnetcu_binary_offset_gemm_layers(fixture):
         compare_layer(a, b, 2e-4, btol_floor=1e-2)
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round-1 GPU budget was spent: not yet run on a B200")
 @pytest.mark.parametrize("fixture", [f for f in _net_cases() if f.startswith("gpu_")])
 def test_written_network_file_has_the_reference_layout(fixture):
     """The network file bin/TNetCu writes has, token for token, the layout of the file the reference TNetCu wrote for the same run

@@ -1,6 +1,7 @@
 """Kernel-level parity: every C-ABI compute entry point of libtnetb200.so against oracle/tnet_oracle.c on the same
 seeded inputs.  Integer / index work is bit-exact; floating point is held to the tolerance written at each test."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -10,6 +11,7 @@ pytestmark = pytest.mark.gpu
 import oracle_lib as O
 from tnet_b200 import abi
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 L = None
 
 
@@ -228,10 +230,11 @@ def _update_scalars(lr, mmt, wc, gdf, rows):
 @pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
 @pytest.mark.parametrize("rows,cols", [(100, 260), (37, 135)])
 def test_peer_update_kernel_virtual_ranks(ctx, world, rows, cols):
-    """csrc/peer.cu on ONE GPU: `world` virtual ranks (one context = one stream each, own gradient / weight / momentum / flag
-    buffers) run the fused reduce-scatter + update + all-gather kernel concurrently, twice (sequence numbers 1, 2).  Every rank's
-    weights must be the update from the rank-ordered sum of all gradients, identical bit for bit across the ranks; a rank's momentum
-    buffer changes only in its own block of rows.  world 3 takes the generic kernel, 135 columns the scalar path."""
+    """csrc/peer.cu on ONE GPU: `world` virtual ranks (own gradient / weight / momentum / flag buffers) run the fused reduce-scatter +
+    update + all-gather kernel as ONE cooperative grid (tnb_dp_peer_update_virtual: separate launches that wait for each other are
+    not guaranteed to be co-resident), twice (sequence numbers 1, 2).  Every rank's weights must be the update from the rank-ordered
+    sum of all gradients, identical bit for bit across the ranks; a rank's momentum buffer changes only in its own block of rows.
+    world 3 takes the generic kernel, 135 columns the scalar path."""
     r = rng(100 + world)
     rows_pad = ((rows + world - 1) // world) * world
     shard = rows_pad // world
@@ -243,7 +246,7 @@ def test_peer_update_kernel_virtual_ranks(ctx, world, rows, cols):
     K0[:rows] = 0.01 * r.standard_normal((rows, cols))
     b0 = r.standard_normal(cols).astype(np.float32)
     kb0 = (0.01 * r.standard_normal(cols)).astype(np.float32)
-    ctxs = [abi.Context(0) for _ in range(world)]
+    ctxs = [ctx] * world
     Wd = Kd = bd = kbd = Gd = flags = []
     try:
         Wd = [abi.DMat.from_numpy(c, W0) for c in ctxs]
@@ -262,17 +265,17 @@ def test_peer_update_kernel_virtual_ranks(ctx, world, rows, cols):
                 G[rows_pad] = r.standard_normal(cols)
                 Gd[k].upload(G)
                 Gs.append(G)
+            jobs = (abi.PeerJob * world)()
             for k in range(world):
-                job = abi.PeerJob()
+                job = jobs[k]
                 for q in range(world):
                     job.G[q] = Gd[q].ptr.value
                     job.W[q] = Wd[q].ptr.value
                 job.corrW, job.bias, job.corrb = Kd[k].ptr.value, bd[k].ptr.value, kbd[k].ptr.value
                 job.dW = abi.MatrixDim(rows, cols, Wd[k].stride)
                 job.rows_pad, job.lr, job.mmt, job.wc, job.grad_div_frm, job.n_frames = rows_pad, lr, mmt, wc, gdf, frames
-                abi.check(L.tnb_dp_peer_update_on(ctxs[k].h, C.c_int(0), C.byref(job), C.c_int(k), C.c_int(world), fl, C.c_uint(seq)))
-            for c in ctxs:
-                c.sync()
+            abi.check(L.tnb_dp_peer_update_virtual(ctx.h, jobs, C.c_int(world), fl, C.c_uint(seq), C.c_int(0)))
+            ctx.sync()
             g = Gs[0].copy()
             for k in range(1, world):
                 g = g + Gs[k]                                            # rank order, float32
@@ -302,8 +305,37 @@ def test_peer_update_kernel_virtual_ranks(ctx, world, rows, cols):
     finally:
         for m in Wd + Kd + bd + kbd + Gd + flags:
             m.free()
-        for c in ctxs:
-            c.close()
+
+
+def test_peer_update_timeout_is_reported_not_fatal(ctx):
+    """A rank whose peer never shows up (here: rank 0 of a 2-rank exchange launched alone) must give up after TNB_PEER_TIMEOUT_MS,
+    leave the weights untouched, say which rank it waited for — and leave the CUDA context usable (no __trap)."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import ctypes as C, numpy as np, sys
+        sys.path.insert(0, %r)
+        from tnet_b200 import abi
+        L = abi.lib(); ctx = abi.Context(0)
+        W0 = np.ones((8, 32), np.float32)
+        W = [abi.DMat.from_numpy(ctx, W0) for _ in range(2)]; G = [abi.DMat(ctx, 9, 32) for _ in range(2)]
+        K = abi.DMat(ctx, 8, 32); fl = [abi.DMat(ctx, 1, 64, np.uint32) for _ in range(2)]
+        flp = (C.POINTER(C.c_uint) * 2)(*[f.p(C.c_uint) for f in fl])
+        job = abi.PeerJob()
+        for q in range(2):
+            job.G[q] = G[q].ptr.value; job.W[q] = W[q].ptr.value
+        job.corrW = K.ptr.value; job.dW = abi.MatrixDim(8, 32, W[0].stride)
+        job.rows_pad, job.lr, job.mmt, job.wc, job.grad_div_frm, job.n_frames = 8, 0.1, 0.0, 0.0, 1, 8
+        abi.check(L.tnb_dp_peer_update_on(ctx.h, C.c_int(0), C.byref(job), C.c_int(0), C.c_int(2), flp, C.c_uint(1)))
+        abi.check(L.tnb_ctx_sync(ctx.h))                 # no peer flag block registered in this context: plain sync succeeds
+        w = fl[0].download()[0][33]
+        assert w >> 31 == 1 and (w >> 16) & 0xFF == 1 and (w >> 24) & 1 == 0 and w & 0xFFFF == 1, hex(w)
+        assert np.array_equal(W[0].download(), W0)       # nothing was updated
+        x = abi.DMat.from_numpy(ctx, W0); assert np.array_equal(x.download(), W0)   # the context still works
+        print("TIMEOUT_REPORTED")
+    """ % os.path.join(ROOT, "nnet-asr_b200", "python"))
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120,
+                       env=dict(os.environ, TNB_PEER_TIMEOUT_MS="0.5"))
+    assert r.returncode == 0 and "TIMEOUT_REPORTED" in r.stdout, r.stdout[-2000:]
 
 
 # ------------------------------------------------------------------------------------------------ elementwise

@@ -124,7 +124,6 @@ def test_offset_gemm_layers_epoch_matches_reference_trainers(path, fusion):
 OPT_GOLD = sorted(glob.glob(os.path.join(GOLD, "*_opt_*.npz")))
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round-1 GPU budget was spent: not yet run on a B200")
 @pytest.mark.parametrize("path", OPT_GOLD, ids=[os.path.basename(p)[:-4] for p in OPT_GOLD])
 def test_option_fixtures_match_reference_trainers(path):
     """Cross-validation (no update, network untouched) and per-layer learning-rate factors with a frozen first layer, against the

@@ -19,8 +19,12 @@ r = np.random.default_rng(0)
 out = []
 
 
+ITERS_SCALE = float(os.environ.get("TNB_BENCH_ITERS_SCALE", "1"))   # < 1 for short runs under ncu
+
+
 def timeit(name, nbytes, fns, iters=40):
     """fns: list of closures over rotating buffer sets"""
+    iters = max(1, int(iters * ITERS_SCALE))
     for f in fns:
         f()
     ctx.sync()
