@@ -125,15 +125,26 @@ def write_reference_dataset(d, n_frames, utt_len=256, seed=20240607):
     return paths
 
 
-def run_reference_tnet(paths, d, threads, n_utts_scp=None):
+def reference_cachesize(threads, utt_len):
+    """The CPU trainer gives every worker thread its own cache of (CACHESIZE / threads / (BUNCHSIZE / threads)) * (BUNCHSIZE / threads)
+    rows (TNetLib/Platform.h:159-160) and refuses segments longer than half of it (TNetLib/Cache.cc:66-72): size the total so that
+    each thread's share holds four of its bunch slices AND four utterances, whatever the core count of the box."""
+    per_thread_bunch = max(1, BUNCH // threads)
+    per_thread = max(4 * per_thread_bunch, 4 * utt_len)
+    per_thread = ((per_thread + per_thread_bunch - 1) // per_thread_bunch) * per_thread_bunch
+    return per_thread * threads
+
+
+def run_reference_tnet(paths, d, threads, n_utts_scp=None, utt_len=256):
     exe = os.path.join(ROOT, "oracle", "_ref", "TNet")
+    cachesize = reference_cachesize(threads, utt_len)
     scp = paths["scp"]
     if n_utts_scp is not None:
         scp = os.path.join(d, "sub_%d.scp" % n_utts_scp)
         open(scp, "w").write("\n".join(paths["files"][:n_utts_scp]) + "\n")
     cmd = [exe, "-H", paths["net"], "-I", paths["mlf"], "-L", "*/", "-X", "lab", "-S", scp, "-m", paths["labelmap"],
            "-n", repr(LR / BUNCH),      # the CPU trainer has no 1/N: the schedulers divide lr by the bunch size (SURVEY A.3)
-           "--TARGETMMF=" + os.path.join(d, "out.nnet"), "--BUNCHSIZE=%d" % BUNCH, "--CACHESIZE=%d" % (BUNCH * 4),
+           "--TARGETMMF=" + os.path.join(d, "out.nnet"), "--BUNCHSIZE=%d" % BUNCH, "--CACHESIZE=%d" % cachesize,
            "--RANDOMIZE=TRUE", "--SEED=123", "--FEATURETRANSFORM=" + paths["transform"], "--STARTFRMEXT=%d" % CTX,
            "--ENDFRMEXT=%d" % CTX, "--WEIGHTCOST=%g" % WC, "--THREADS=%d" % threads]
     env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")
@@ -153,9 +164,11 @@ def cpu_reference_throughput(bunches_a, bunches_b, threads=None):
     if not os.path.exists(exe):
         raise RuntimeError("oracle/_ref/TNet is not built (run __graft_entry__.build() where /root/reference exists)")
     ncpu = os.cpu_count() or 1
+    if threads is None and os.environ.get("TNB_REF_THREADS"):
+        threads = int(os.environ["TNB_REF_THREADS"])      # testing: e.g. 32 threads on a smaller box
     if threads is None:
         threads = 1
-        while threads * 2 <= min(ncpu, 32):
+        while threads * 2 <= min(ncpu, 32) and BUNCH % (threads * 2) == 0:
             threads *= 2
     utt_len = 256
     d = tempfile.mkdtemp(prefix="tnet_cpu_")
@@ -163,8 +176,8 @@ def cpu_reference_throughput(bunches_a, bunches_b, threads=None):
         need = max(bunches_a, bunches_b) * BUNCH
         paths = write_reference_dataset(d, need, utt_len)
         per = BUNCH // utt_len
-        ta, fa = run_reference_tnet(paths, d, threads, bunches_a * per)
-        tb, fb = run_reference_tnet(paths, d, threads, bunches_b * per)
+        ta, fa = run_reference_tnet(paths, d, threads, bunches_a * per, utt_len)
+        tb, fb = run_reference_tnet(paths, d, threads, bunches_b * per, utt_len)
     finally:
         shutil.rmtree(d, ignore_errors=True)
     if fb <= fa or tb <= ta:
@@ -198,6 +211,19 @@ def reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ this repo's arm
+def ncu_traffic(math):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant GEMM from the committed ncu --set full capture
+    (profiles/ncu_traffic.json, written by tools/summarize_ncu.py from the .ncu-rep of the same bench command); None without one."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    try:
+        d = json.load(open(p)).get(math)
+        return (d["dram_bytes_per_launch"], d.get("source")) if d else (None, None)
+    except Exception:
+        return None, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -205,11 +231,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--math", default="3xtf32", choices=["3xtf32", "tf32", "bf16"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 1024 frames per GPU (global bunch 1024*N); strong: the 1024-frame bunch partitioned over the GPUs")
+    ap.add_argument("--windows", type=int, default=5, help="timed windows of --steps bunches; the median is reported")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the bf16-mode and other-scaling sub-objects and the peak probe")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
     args.warmup = max(args.warmup, 3)
+    args.windows = max(args.windows, 1)
     # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner does) go to stderr instead
     sys.stdout.flush()
     json_fd = os.dup(1)
@@ -229,7 +260,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     host.select_gpu(local)
-    host.set_math({"3xtf32": abi.MATH_3XTF32, "tf32": abi.MATH_TF32, "bf16": abi.MATH_BF16}[args.math])
+    MATH = {"3xtf32": abi.MATH_3XTF32, "tf32": abi.MATH_TF32, "bf16": abi.MATH_BF16}
     L, H = abi.lib(), host.hlib()
     ctx = host.ctx_handle()
 
@@ -243,38 +274,8 @@ def main():
         idbuf = (C.c_ubyte * 128)(*t.cpu().tolist())
         abi.check(L.tnb_comm_init(ctx, idbuf, C.c_int(rank), C.c_int(world)))
 
-    net = host.Net(dims=DIMS, seed=1)
-    net.set_hyper(LR, mmt=MMT, wc=WC, gdf=True)
-    dp_schedule = "none"
-    if world > 1:
-        dp_schedule = os.environ.get("TNB_DP_MODE", "peer")
-        ok = 1
-        try:
-            net.set_data_parallel(world)
-        except abi.TnbError as e:
-            ok = 0
-            sys.stderr.write("[bench] rank %d: data-parallel set-up (%s) failed: %s\n" % (rank, dp_schedule, e))
-        tt = torch.tensor([ok], dtype=torch.int32, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MIN)
-        if int(tt.item()) == 0:
-            if dp_schedule != "peer":
-                raise SystemExit("data-parallel set-up failed")
-            # the peer-memory schedule needs CUDA IPC between the ranks' processes; where that is not available the NCCL schedule
-            # still is — say so loudly and in the JSON line instead of losing the measurement
-            sys.stderr.write("[bench] falling back to TNB_DP_MODE=allreduce (NCCL) on all ranks\n")
-            os.environ["TNB_DP_MODE"] = "allreduce"
-            dp_schedule = "allreduce (peer-memory set-up failed)"
-            net = host.Net(dims=DIMS, seed=1)
-            net.set_hyper(LR, mmt=MMT, wc=WC, gdf=True)
-            net.set_data_parallel(world)
-
-    rng = np.random.default_rng(20240607 + rank)
-    rows = RESIDENT_BUNCHES * BUNCH
-    X = rng.standard_normal((rows, DIMS[0])).astype(np.float32)
-    lab = rng.integers(0, DIMS[-1], rows).astype(np.int32)
-    net.load_resident(X, lab)
-
     stream = torch.cuda.ExternalStream(host_stream(L, ctx), device=torch.device("cuda", local))
+    dp_state = {"schedule": "none"}
 
     def barrier():
         host.sync()
@@ -282,40 +283,106 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing ----
+    def allmax(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def make_net(math, scaling):
+        """network + resident synthetic set for one (math mode, scaling) arm.  weak: every rank draws its own 1024-frame bunches;
+        strong: ONE global set (same seed everywhere), rank g owns rows [g*B/G, (g+1)*B/G) of every 1024-frame bunch
+        (the reference CPU trainer's bunchsize_/num_thr, TNetLib/Platform.h:159)."""
+        host.set_math(MATH[math])
+        net = host.Net(dims=DIMS, seed=1)
+        net.set_hyper(LR, mmt=MMT, wc=WC, gdf=True)
+        if world > 1:
+            dp_state["schedule"] = os.environ.get("TNB_DP_MODE", "peer")
+            ok = 1
+            try:
+                net.set_data_parallel(world)
+            except abi.TnbError as e:
+                ok = 0
+                sys.stderr.write("[bench] rank %d: data-parallel set-up (%s) failed: %s\n" % (rank, dp_state["schedule"], e))
+            tt = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+            if int(tt.item()) == 0:
+                if dp_state["schedule"] != "peer":
+                    raise SystemExit("data-parallel set-up failed")
+                # the peer-memory schedule needs CUDA IPC between the ranks' processes; where that is not available the NCCL
+                # schedule still is — say so loudly and in the JSON line instead of losing the measurement
+                sys.stderr.write("[bench] falling back to TNB_DP_MODE=allreduce (NCCL) on all ranks\n")
+                os.environ["TNB_DP_MODE"] = "allreduce"
+                dp_state["schedule"] = "allreduce (peer-memory set-up failed)"
+                net = host.Net(dims=DIMS, seed=1)
+                net.set_hyper(LR, mmt=MMT, wc=WC, gdf=True)
+                net.set_data_parallel(world)
+        if scaling == "weak" or world == 1:
+            bunch = BUNCH
+            rng = np.random.default_rng(20240607 + rank)
+            X = rng.standard_normal((RESIDENT_BUNCHES * bunch, DIMS[0])).astype(np.float32)
+            lab = rng.integers(0, DIMS[-1], RESIDENT_BUNCHES * bunch).astype(np.int32)
+        else:
+            if BUNCH % world:
+                raise SystemExit("strong scaling needs the bunch (%d) to divide by the GPU count" % BUNCH)
+            bunch = BUNCH // world
+            rng = np.random.default_rng(20240607)
+            Xg = rng.standard_normal((RESIDENT_BUNCHES, BUNCH, DIMS[0])).astype(np.float32)
+            labg = rng.integers(0, DIMS[-1], (RESIDENT_BUNCHES, BUNCH)).astype(np.int32)
+            X = np.ascontiguousarray(Xg[:, rank * bunch:(rank + 1) * bunch]).reshape(-1, DIMS[0])
+            lab = np.ascontiguousarray(labg[:, rank * bunch:(rank + 1) * bunch]).reshape(-1)
+        net.load_resident(X, lab)
+        return net, bunch, X, lab
+
+    def timed_windows(net, bunch, n_windows):
+        """n_windows x (args.steps bunches bracketed by barrier + synchronize, CUDA events on the library's stream, max over ranks)"""
+        net.train_resident(bunch, 0, args.warmup)
+        barrier()
+        out, first, launches = [], args.warmup, 0
+        for _ in range(n_windows):
+            l0 = host.launches()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            net.train_resident(bunch, first, args.steps)
+            e1.record(stream)
+            barrier()
+            out.append(allmax(e0.elapsed_time(e1)))
+            launches = host.launches() - l0
+            first += args.steps
+        return out, launches, first
+
+    def median(v):
+        v = sorted(v)
+        return v[len(v) // 2] if len(v) % 2 else 0.5 * (v[len(v) // 2 - 1] + v[len(v) // 2])
+
+    def gemm_pass(net, bunch, first):
+        # roofline pass: K steps with a CUDA event pair around every GEMM launch (tnb_ctx_profile_*).  Kept out of the timed windows
+        # because an event record between two kernels removes their programmatic-dependent-launch overlap.
+        abi.check(L.tnb_ctx_profile_begin(ctx))
+        net.train_resident(bunch, first, args.steps)
+        barrier()
+        gms, gl, gfl = C.c_double(), C.c_ulonglong(), C.c_double()
+        abi.check(L.tnb_ctx_profile_end(ctx, C.byref(gms), C.byref(gl), C.byref(gfl)))
+        return gms.value, int(gl.value), gfl.value
+
+    # ================================================================== headline arm
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()             # clocks are sampled from the warm-up to the end of the timed region
-    net.train_resident(BUNCH, 0, args.warmup)
-    barrier()
-    l0 = host.launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    net.train_resident(BUNCH, args.warmup, args.steps)
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = host.launches() - l0
-    # roofline pass: the same K steps again with a CUDA event pair around every GEMM launch (tnb_ctx_profile_*).  Kept out of
-    # the region `value` is timed on because an event record between two kernels disables their programmatic dependent launch.
-    abi.check(L.tnb_ctx_profile_begin(ctx))
-    net.train_resident(BUNCH, args.warmup + args.steps, args.steps)
-    barrier()
-    gms, gl, gfl = C.c_double(), C.c_ulonglong(), C.c_double()
-    abi.check(L.tnb_ctx_profile_end(ctx, C.byref(gms), C.byref(gl), C.byref(gfl)))
+        sampler.start()             # clocks are sampled from the warm-up to the end of the timed windows
+    net, bunch, X, lab = make_net(args.math, args.scaling)
+    win_ms, launches, first = timed_windows(net, bunch, args.windows)
     clocks = sampler.stop() if rank == 0 else {}
-    if world > 1:
-        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
-    frames = args.steps * BUNCH * world
+    ms = median(win_ms)
+    gms, gl, gfl = gemm_pass(net, bunch, first)
+    frames = args.steps * bunch * world
     value = frames / (ms / 1000.0)
 
     # ---- end to end: pinned host buffers in, statistics out, every step ----
-    xb = torch.empty((BUNCH, DIMS[0]), dtype=torch.float32).pin_memory()
-    lb = torch.empty((BUNCH,), dtype=torch.int32).pin_memory()
-    xb.copy_(torch.from_numpy(X[:BUNCH]))
-    lb.copy_(torch.from_numpy(lab[:BUNCH]))
+    xb = torch.empty((bunch, DIMS[0]), dtype=torch.float32).pin_memory()
+    lb = torch.empty((bunch,), dtype=torch.int32).pin_memory()
+    xb.copy_(torch.from_numpy(X[:bunch]))
+    lb.copy_(torch.from_numpy(lab[:bunch]))
     xp, lp = C.cast(xb.data_ptr(), C.POINTER(C.c_float)), C.cast(lb.data_ptr(), C.POINTER(C.c_int))
 
     # One submission is kept in flight: submit bunch k+1 (H2D on the copy stream, step behind it), then collect bunch k (blocks
@@ -324,64 +391,120 @@ def main():
     host_t = {"submit": 0.0, "collect": 0.0}   # host time inside the two calls (diagnostic: enqueue cost vs waiting for the GPU)
 
     def e2e_run(n):
-        st = None
         host_t["submit"] = host_t["collect"] = 0.0
-        net.submit_bunch_labels(xp, lp, BUNCH)
+        net.submit_bunch_labels(xp, lp, bunch)
         for _ in range(n - 1):
             ta = time.perf_counter()
-            net.submit_bunch_labels(xp, lp, BUNCH)
+            net.submit_bunch_labels(xp, lp, bunch)
             tb = time.perf_counter()
-            st = net.collect()
+            net.collect()
             host_t["submit"] += tb - ta
             host_t["collect"] += time.perf_counter() - tb
         return net.collect()
 
     e2e_run(3)
-    barrier()
-    t0 = time.perf_counter()
-    st = e2e_run(args.steps)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
-    e2e_value = frames / e2e_s
+    e2e_s, st = [], None
+    for _ in range(min(3, args.windows)):
+        barrier()
+        t0 = time.perf_counter()
+        st = e2e_run(args.steps)
+        barrier()
+        e2e_s.append(allmax(time.perf_counter() - t0))
+    e2e_value = frames / median(e2e_s)
+    net.close()
+
+    # ================================================================== the other arms, reported inside the same line
+    extras = {}
+    if not args.no_extras:
+        def side_arm(math, scaling):
+            n2, b2, _, _ = make_net(math, scaling)
+            w2, l2, f2 = timed_windows(n2, b2, max(3, min(args.windows, 5)))
+            g2 = gemm_pass(n2, b2, f2)
+            n2.close()
+            return b2, median(w2), w2, l2, g2
+        if args.math == "3xtf32":
+            b2, m2, w2, l2, g2 = side_arm("bf16", args.scaling)
+            extras["bf16"] = (b2, m2, w2, l2, g2)
+        if world > 1:
+            other = "strong" if args.scaling == "weak" else "weak"
+            b2, m2, w2, l2, g2 = side_arm(args.math, other)
+            extras[other] = (b2, m2, w2, l2, g2)
+        host.set_math(MATH[args.math])
+
+    # ---- measured dense peaks of THIS box (library GEMM as a yardstick; nothing in the product calls it) ----
+    peaks_live = None
+    if rank == 0 and not args.no_extras:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from tf32_peak import probe_dense_peak
+            peaks_live = {"tf32": probe_dense_peak("tf32", sustain_s=1.5), "bf16": probe_dense_peak("bf16", sustain_s=1.5)}
+        except Exception as e:  # the probe is a yardstick: its failure must not lose the measurement
+            sys.stderr.write("[bench] dense-peak probe failed: %s\n" % e)
 
     if rank == 0:
         pk = measured_peaks()
         fpf = flops_per_frame(DIMS)
-        gemm_tflops = (gfl.value / (gms.value / 1000.0)) / 1e12 if gms.value > 0 else 0.0
-        passes = 3 if args.math == "3xtf32" else 1
+
+        def roof(math, gms_, gl_, gfl_, ms_step, bunch_):
+            gemm_tflops = (gfl_ / (gms_ / 1000.0)) / 1e12 if gms_ > 0 else 0.0
+            passes = 3 if math == "3xtf32" else 1
+            traffic, tsrc = ncu_traffic(math)
+            r = {"bound": "tensor", "achieved": gemm_tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                 "frac": gemm_tflops / pk["bf16_sustained"], "traffic": traffic, "traffic_source": tsrc,
+                 "kernel": "tcgen05 GEMM launches of K steps, one CUDA event pair per launch (no PDL overlap in this pass)",
+                 "gemm_ms_per_step": gms_ / args.steps, "gemm_launches": gl_, "issued_tflops": gemm_tflops * passes,
+                 "peak_source": pk["source"] + " (bf16 sustained)",
+                 # whole step (every kernel, PDL overlap included) as algorithmic flops per second, per GPU
+                 "step_tflops": fpf * bunch_ / (ms_step / 1000.0) / 1e12,
+                 "step_frac": fpf * bunch_ / (ms_step / 1000.0) / 1e12 / pk["bf16_sustained"]}
+            if peaks_live and math != "bf16":
+                tpk = peaks_live["tf32"]
+                r["tf32_peak_measured"] = {"burst_tflops": tpk["burst_tflops"], "sustained_tflops": tpk["sustained_tflops"],
+                                           "how": "torch.matmul fp32 %d^3 with TF32 allowed: best of 10 and back to back 1.5 s, this run" % tpk["n"]}
+                # issued tf32 flops against the MEASURED tf32 peak: the burst figure for the kernel timed alone in the event pass
+                r["frac_issued_of_measured_tf32_burst"] = gemm_tflops * passes / tpk["burst_tflops"]
+                r["step_frac_issued_of_measured_tf32_sustained"] = r["step_tflops"] * passes / tpk["sustained_tflops"]
+            if peaks_live and math == "bf16":
+                r["bf16_peak_this_run"] = {"burst_tflops": peaks_live["bf16"]["burst_tflops"], "sustained_tflops": peaks_live["bf16"]["sustained_tflops"]}
+            return r
+
         line = {
             "metric": "training_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
             "vs_baseline": None, "dtype": {"3xtf32": "tf32x3", "tf32": "tf32", "bf16": "bf16"}[args.math], "data": "synthetic",
-            "config": {"workload": WORKLOAD, "dims": DIMS, "bunch_per_gpu": BUNCH, "global_bunch": BUNCH * world,
-                       "parallelism": "dp%d" % world, "dp_schedule": dp_schedule, "learn_rate": LR, "momentum": MMT, "weightcost": WC,
+            "config": {"workload": WORKLOAD, "dims": DIMS, "bunch_per_gpu": bunch, "global_bunch": bunch * world,
+                       "parallelism": "dp%d" % world, "dp_schedule": dp_state["schedule"], "learn_rate": LR, "momentum": MMT, "weightcost": WC,
                        "l2_note": "no L2 flush: weights+corrections (224 MB) and activations exceed the 126 MB L2 every step",
+                       "timed_region": "K x (row window of the resident set, int labels -> one-hot, forward, softmax+xent+accuracy, backward, "
+                                       "update); the cache shuffle and the splice run once per cache fill and are outside it (~5 us per bunch amortised)",
+                       "windows_ms": win_ms, "windows": "median of %d windows of %d bunches" % (len(win_ms), args.steps),
+                       "scaling_note": "weak = 1024 frames per GPU; strong = the 1024-frame bunch partitioned, rows [g*B/G,(g+1)*B/G) per GPU. "
+                                       "The 85 % efficiency target is read on the weak curve: at a fixed 1024-frame global bunch the 112 MB fp32 "
+                                       "gradient exchange per bunch exceeds the per-GPU compute at 8 GPUs by construction (SURVEY 8e); the "
+                                       "strong curve is reported beside it",
                        "flops_per_frame": fpf, "gemm_math": args.math},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": BUNCH * DIMS[0] * 4 + BUNCH * 4,
-                    "d2h_bytes_per_step": 24,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": bunch * DIMS[0] * 4 + bunch * 4,
+                    "d2h_bytes_per_step": 24, "windows_s": e2e_s,
                     # rank 0's host time per step inside the two calls: enqueueing a step vs waiting for the previous one's statistics
                     "host_ms_per_step": {"submit": 1000.0 * host_t["submit"] / max(1, args.steps - 1),
                                          "collect_wait": 1000.0 * host_t["collect"] / max(1, args.steps - 1)}},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": gemm_tflops / pk["bf16_sustained"],
-                         # dram__bytes_read+write of ONE 1024x2048x2048 forward launch (ncu --set full, profiles/r01_ncu_fwd.md and
-                         # r01_ncu_fwd_bf16.md); algorithmic bytes of that launch: X 8.4 MB + W 16.8 MB read in fp32 (half in bf16),
-                         # Y 8.4 MB written (stays in L2)
-                         "traffic": 12.63e6 if args.math == "bf16" else 25.22e6,
-                         "kernel": "gemm_tcgen05_kernel (every GEMM launch of K steps, one CUDA event pair per launch)",
-                         "gemm_ms_per_step": gms.value / args.steps, "gemm_launches": int(gl.value),
-                         "issued_tflops": gemm_tflops * passes,
-                         "frac_issued_of_mode_peak": gemm_tflops * passes / (pk["bf16_sustained"] / (1.0 if args.math == "bf16" else 2.0)),
-                         "peak_source": pk["source"] + "; tf32 dense peak taken as bf16/2",
-                         "step_tflops": fpf * value / world / 1e12},
+            "roofline": roof(args.math, gms, gl, gfl, ms / args.steps, bunch),
             "final_stats": {"xent_per_frame": st[0] / max(1, st[1]), "frames": st[1]},
         }
+        for k, (b2, m2, w2, l2, g2) in extras.items():
+            math2 = "bf16" if k == "bf16" else args.math
+            obj = {"value": args.steps * b2 * world / (m2 / 1000.0), "unit": "frames/s", "ms_per_step": m2 / args.steps,
+                   "bunch_per_gpu": b2, "global_bunch": b2 * world, "windows_ms": w2, "gpu_launches": int(l2),
+                   "roofline": roof(math2, g2[0], g2[1], g2[2], m2 / args.steps, b2)}
+            if k == "bf16":
+                obj["dtype"] = "bf16"
+                obj["note"] = "north_star's bf16 mode, reported separately: bf16 operands (resident twins), fp32 accumulation, fp32 master weights"
+                line["bf16"] = obj
+            else:
+                obj["scaling"] = k
+                line[k + "_scaling"] = obj
         if world == 1 and not args.no_cpu_baseline:
             try:
                 fps, threads, sample = cpu_reference_throughput(2, 10)
@@ -391,6 +514,7 @@ def main():
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
+        barrier()
         abi.check(L.tnb_comm_destroy(ctx))
         dist.destroy_process_group()
     return 0

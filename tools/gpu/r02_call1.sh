@@ -13,7 +13,7 @@ TNB_BENCH_ITERS_SCALE=0.1 python tools/bench_kernels.py > $O/hbm_kernels_plain.t
 TNB_BENCH_ITERS_SCALE=0.1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum,sm__warps_active.avg.pct_of_peak_sustained_active \
   --clock-control none --csv --log-file $O/hbm_kernels_ncu.csv python tools/bench_kernels.py > $O/hbm_kernels_ncu.log 2>&1
 echo "ncu hbm rc=$?"
-python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "peer" > $O/peer_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:dp_peer_update_kernel -c 6 -o $O/peer_virtual \
-    python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "peer" > $O/ncu_peer.log 2>&1
-echo "ncu peer rc=$?"
+python tools/peer_virtual_bench.py > $O/peer_virtual_bench.txt 2>&1 &&
+PEER_BENCH_WORLDS=8 PEER_BENCH_ITERS=1 ncu --set full --clock-control none --import-source on -k regex:dp_peer_update_virtual -s 2 -c 1 -o $O/peer_virtual \
+    python tools/peer_virtual_bench.py > $O/ncu_peer.log 2>&1
+echo "ncu peer rc=$?"; cat $O/peer_virtual_bench.txt
