@@ -249,6 +249,54 @@ int tnb_affine_update_bf16(TnbContext *ctx, const uint16_t *X16, int ldx16, TnbM
                            const float *E, TnbMatrixDim dE, float *W, TnbMatrixDim dW, uint16_t *W16, int ldw16, float *bias,
                            float *corrW, float *corrb, float lr, float mmt, float wc, int grad_div_frm, int n_frames_global);
 
+/* ---- several independent GEMMs (each with its fused epilogue) as ONE persistent launch (csrc/gemm_multi.cu) -----------------------
+ * In CuNetwork::Backpropagate (cuNetwork.h:170-194) the input-gradient GEMM of layer l (cuBiasedLinearity.cc:24) and the
+ * weight-gradient + update GEMMs of the layers above it (cuBiasedLinearity.cc:44-64) do not depend on each other: the reference
+ * issues them one cublasSgemm after the other, each leaving most of the chip idle at a 1024-frame bunch.  A job is one such GEMM
+ * C = epilogue(op(A) * op(B)) cut into 256 x 256 output tiles; tnb_gemm_batch runs all tiles of the `must` jobs plus as many tiles
+ * of the `pool` jobs (in order; tile_first / tile_count of a pool job record its progress and are updated) as fit without
+ * lengthening the launch — everything left in the pool when there is no `must` job.  Results per element are those of the single
+ * GEMM entry points (same mainloop, same epilogue arithmetic).  The caller orders conflicting jobs: a pool job that updates W in
+ * place must not share a launch with a job that reads W.  3xTF32 and bf16 modes (bf16: the twins A16 / B16 are read). */
+enum { TNB_EPI_STORE = 0, TNB_EPI_FWD = 1, TNB_EPI_DX = 2, TNB_EPI_UPDATE = 3 };
+typedef struct TnbGemmJob_ {
+  int transa, transb;                 /* 0: op(X) = X, 1: op(X) = X^T — operands row-major as CuMatrix::Gemm receives them (cumatrix.tcc:335-370) */
+  int m, n, k;
+  const float *A; int lda;
+  const float *B; int ldb;
+  const uint16_t *A16; int lda16;     /* bf16 twins of A and B (TNB_MATH_BF16) */
+  const uint16_t *B16; int ldb16;
+  int epilogue;                       /* TNB_EPI_*: which fused layer op this is (selects the specialised epilogue; STORE = any combination) */
+  float alpha, beta;                  /* out = alpha*acc + beta*C_old (+ bias) (sigmoid) (.* y(1-y)) */
+  float *C; int ldc;
+  const float *bias; int act;
+  const float *mulY; int ldy;
+  float *W; int ldw; float w_scale, w_l2;   /* fused SGD: W += w_scale*out ; W += w_l2*W */
+  uint16_t *C16; int ldc16;           /* optional bf16 twins of the stored output / the updated weights */
+  uint16_t *W16; int ldw16;
+  int tile_first, tile_count;         /* tiles [tile_first, tile_first + tile_count) of the row-major 256 x 256 tile grid still to run */
+} TnbGemmJob;
+/* the three layer ops as jobs (same arguments as tnb_affine_bwd_dx / tnb_affine_update / tnb_affine_grad; the bias halves of the
+ * update stay with tnb_bias_update_batch).  tile_count is set to the job's number of tiles. */
+int tnb_job_affine_bwd_dx(TnbGemmJob *job, const float *E, TnbMatrixDim dE, const float *W, TnbMatrixDim dW, const float *Yprev,
+                          TnbMatrixDim dYprev, float *Eprev, TnbMatrixDim dEprev);
+int tnb_job_affine_update(TnbGemmJob *job, const float *X, TnbMatrixDim dX, const float *E, TnbMatrixDim dE, float *W, TnbMatrixDim dW,
+                          float *corrW, float lr, float mmt, float wc, int grad_div_frm, int n_frames_global);
+int tnb_job_affine_grad(TnbGemmJob *job, const float *X, TnbMatrixDim dX, const float *E, TnbMatrixDim dE, float *G, TnbMatrixDim dG);
+/* bf16 mode: the twins the job reads (A16, B16) and keeps current (C16, W16; may be NULL) */
+int tnb_job_set_twins(TnbGemmJob *job, const uint16_t *A16, int lda16, const uint16_t *B16, int ldb16, uint16_t *C16, int ldc16,
+                      uint16_t *W16, int ldw16);
+int tnb_gemm_job_tiles(const TnbGemmJob *job);
+/* 1 if the job suits the batch kernel in the context's math mode (operand alignment; output and contraction at least a tile wide:
+ * smaller GEMMs are better served by the tile shapes of the single-GEMM path), else 0 */
+int tnb_gemm_batch_ok(TnbContext *ctx, const TnbGemmJob *job);
+int tnb_gemm_batch(TnbContext *ctx, const TnbGemmJob *must, int n_must, TnbGemmJob *pool, int n_pool);
+/* CTA pairs (2 SMs each) a batch launch may occupy; 0 = all that can be co-resident (74 on a B200).  Fewer leaves SMs to kernels
+ * that run beside the batch, e.g. the data-parallel gradient exchange. */
+int tnb_gemm_batch_set_pairs(TnbContext *ctx, int pairs);
+/* developer aid (TNB_BATCH_TRACE=1): clock64() stamps [pair][64] of the last tnb_gemm_batch launch (slots: csrc/gemm_multi.cu) */
+int tnb_gemm_batch_trace_read(TnbContext *ctx, long long *out);
+
 /* tnb_sgd_update (cuBiasedLinearity.cc:55-63) for several layers in one launch (the data-parallel step applies them after the last all-reduce); W16/ldw16:
  * optional bf16 twin of W to refresh (NULL otherwise). */
 typedef struct TnbSgdJob_ {

@@ -40,6 +40,12 @@ int tnh_net_write(TnhNet *net, const char *network_file);
 int tnh_net_set_hyper(TnhNet *net, float learn_rate, const char *learn_rate_factors /*NULL or "a:b:c"*/, float momentum,
                       float weightcost, int grad_div_frm);
 int tnh_net_set_fusion(TnhNet *net, int on);
+/* 0: every GEMM of the backward pass in its own launch (the round-1 schedule); 1 (default): independent ones share persistent
+ * launches (tnb_gemm_batch) */
+int tnh_net_set_batching(TnhNet *net, int on);
+/* parameters of a <biasedlinearity> layer as held on the device, without the text round trip: W [nin x nout] row-major (the file
+ * stores its transpose, cuBiasedLinearity.cc:70-78) and bias [nout]; either pointer may be NULL.  *nin / *nout return the dimensions. */
+int tnh_net_get_affine(TnhNet *net, int layer, float *W_host, float *bias_host, int *nin, int *nout);
 int tnh_net_set_data_parallel(TnhNet *net, int world);
 int tnh_net_dims(TnhNet *net, int *n_inputs, int *n_outputs, int *n_layers);
 int tnh_net_propagate(TnhNet *net, const float *x_host, int rows, float *out_host);

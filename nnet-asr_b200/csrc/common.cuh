@@ -47,6 +47,16 @@ void set_error(const char *fmt, ...);
     }                                                                                          \
   } while (0)
 
+// tnb_gemm_batch (gemm_multi.cu): the cached plan of one launch
+struct MgPlan {
+  std::vector<int> src;          // GEMM slot -> index into must[] (i < n_must) or n_must + index into pool[]
+  std::vector<int> pool_taken;   // tiles taken from each pool job
+  void *dlist = nullptr;         // device copy of the per-pair tile lists [used_pairs][ipp] (int4)
+  int used_pairs = 0, ipp = 0;
+  long makespan = 0;
+  double flops = 0.0;
+};
+
 struct TmapKey {
   const void *ptr;
   int rows, cols, stride, box_rows, box_cols, swizzle32;
@@ -70,6 +80,9 @@ struct TnbContext_ {
   bool capturing = false;                   // between tnb_graph_begin and tnb_graph_end
   unsigned long long capture_base = 0;      // launch counter at tnb_graph_begin
   std::map<tnb::TmapKey, CUtensorMap> tmaps;  // TMA descriptors keyed by (ptr, dims, box)
+  std::map<std::vector<int>, tnb::MgPlan> mg_plans;  // tnb_gemm_batch: launch plans keyed by the jobs' shapes and tile ranges
+  int mg_pairs_limit = 0;                       // tnb_gemm_batch_set_pairs: CTA pairs a batch launch may use (0 = all that are co-resident)
+  void *mg_trace = nullptr;                     // TNB_BATCH_TRACE=1: per-pair clock stamps of the last tnb_gemm_batch launch
   // scratch for deterministic per-row -> stats reductions
   float *row_scratch = nullptr;
   int *row_match = nullptr;

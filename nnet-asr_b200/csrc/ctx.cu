@@ -218,6 +218,8 @@ int tnb_ctx_destroy(TnbContext *ctx) {
   cudaStreamDestroy(ctx->aux_stream);
   cudaStreamDestroy(ctx->aux2_stream);
   if (ctx->vec_scratch_side) cudaFree(ctx->vec_scratch_side);
+  for (auto &kv : ctx->mg_plans) if (kv.second.dlist) cudaFree(kv.second.dlist);
+  if (ctx->mg_trace) cudaFree(ctx->mg_trace);
   delete ctx;
   return TNB_OK;
 }

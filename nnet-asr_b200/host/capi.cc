@@ -167,6 +167,18 @@ int tnh_net_set_hyper(TnhNet *h, float lr, const char *factors, float mmt, float
   TNH_CATCH
 }
 int tnh_net_set_fusion(TnhNet *h, int on) { TNH_TRY h->net.SetFusion(on != 0); TNH_CATCH }
+int tnh_net_set_batching(TnhNet *h, int on) { TNH_TRY h->net.SetBatching(on != 0); TNH_CATCH }
+int tnh_net_get_affine(TnhNet *h, int layer, float *W_host, float *bias_host, int *nin, int *nout) {
+  TNH_TRY
+  if (layer < 0 || layer >= h->net.Layers()) Error("layer index");
+  if (h->net.Layer(layer).GetType() != CuComponent::BIASED_LINEARITY) Error("layer is not a <biasedlinearity>");
+  CuBiasedLinearity &lin = static_cast<CuBiasedLinearity &>(h->net.Layer(layer));
+  if (nin) *nin = (int)lin.GetNInputs();
+  if (nout) *nout = (int)lin.GetNOutputs();
+  if (W_host) download(lin.Linearity(), W_host, (int)lin.GetNInputs(), (int)lin.GetNOutputs());
+  if (bias_host) TNB_CHECK(tnb_memcpy(Cx(), bias_host, lin.Bias().pCUData(), sizeof(float) * lin.GetNOutputs(), 1));
+  TNH_CATCH
+}
 int tnh_net_set_data_parallel(TnhNet *h, int world) { TNH_TRY h->net.SetDataParallel(world); TNH_CATCH }
 int tnh_net_dims(TnhNet *h, int *nin, int *nout, int *nl) {
   TNH_TRY

@@ -217,6 +217,44 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     TNB_CHECK(tnb_affine_update(Cx(), X.pCUData(), X.Dim(), E.pCUData(), E.Dim(), mLinearity.pCUData(), mLinearity.Dim(), bias,
                                 mLinearityCorrection.pCUData(), corrb, mLearningRate, mMomentum, mWeightcost, mGradDivFrm ? 1 : 0, 0));
   }
+  // ---- the same two GEMMs as JOBS of a batched launch (tnb_gemm_batch: independent GEMMs of the backward pass share one grid) ----
+  /// dX (+ diff-sigmoid of the <sigmoid> below when pYprev != NULL) as a job; false if the batch kernel does not take the shape
+  bool MakeBackpropJob(const CuMatrix<BaseFloat> &E, const CuMatrix<BaseFloat> *pYprev, CuMatrix<BaseFloat> &Eprev, TnbGemmJob *pJob) {
+    WaitDataParallel();
+    const CuMatrix<BaseFloat> &W = mLinearity;
+    TnbMatrixDim none = {0, 0, 0};
+    TNB_CHECK(tnb_job_affine_bwd_dx(pJob, E.pCUData(), E.Dim(), W.pCUData(), W.Dim(), pYprev ? pYprev->pCUData() : NULL,
+                                    pYprev ? pYprev->Dim() : none, Eprev.pCUData(), Eprev.Dim()));
+    if (Bf16()) {
+      const uint16_t *e16 = E.Twin(), *w16 = W.Twin();
+      uint16_t *ep16 = Eprev.TwinForWrite();  // (allocates on first use: take it BEFORE TwinStride() is read in the argument list below)
+      TNB_CHECK(tnb_job_set_twins(pJob, e16, E.TwinStride(), w16, W.TwinStride(), ep16, Eprev.TwinStride(), NULL, 0));
+    }
+    if (tnb_gemm_batch_ok(Cx(), pJob)) return true;
+    if (Bf16()) (void)Eprev.pCUData();  // not taken: the twin was not written after all
+    return false;
+  }
+  /// the weight half of Update() as a job (the bias half goes to *pDeferredBias as in Update(TnbBiasJob *)); false if not batchable
+  bool MakeUpdateJob(TnbGemmJob *pJob, TnbBiasJob *pDeferredBias) {
+    WaitDataParallel();
+    const CuMatrix<BaseFloat> &X = GetInput(), &E = GetErrorInput();
+    const CuMatrix<BaseFloat> &Wc = mLinearity;
+    TNB_CHECK(tnb_job_affine_update(pJob, X.pCUData(), X.Dim(), E.pCUData(), E.Dim(), const_cast<float *>(Wc.pCUData()), Wc.Dim(),
+                                    const_cast<float *>(static_cast<const CuMatrix<BaseFloat> &>(mLinearityCorrection).pCUData()), mLearningRate,
+                                    mMomentum, mWeightcost, mGradDivFrm ? 1 : 0, 0));
+    if (Bf16()) {
+      const uint16_t *x16 = X.Twin(), *e16 = E.Twin();
+      uint16_t *w16 = const_cast<uint16_t *>(Wc.Twin());  // allocate (and fill on first use); the epilogue keeps it current from here on
+      TNB_CHECK(tnb_job_set_twins(pJob, x16, X.TwinStride(), e16, E.TwinStride(), NULL, 0, w16, Wc.TwinStride()));
+    }
+    if (!tnb_gemm_batch_ok(Cx(), pJob)) return false;
+    (void)mLinearityCorrection.pCUData();  // both are rewritten by the job ...
+    (void)mLinearity.pCUData();
+    if (Bf16()) (void)mLinearity.TwinForWrite();  // ... and the epilogue writes the weights' twin from the value it stores
+    TnbBiasJob j = {E.pCUData(), E.Dim(), mBias.pCUData(), mBiasCorrection.pCUData(), mLearningRate, mMomentum, mGradDivFrm ? 1 : 0, 0};
+    *pDeferredBias = j;
+    return true;
+  }
   // ---- data-parallel halves of Update(): local gradient, (all-reduce by the network), apply ----
   /// rows of the weight matrix rounded up to a multiple of the world size: the ranks own equal blocks of rows in the update
   void PrepareDataParallel(int world) {
@@ -814,12 +852,12 @@ inline CuObjectiveFunction *CuObjectiveFunction::Factory(ObjFunType type) {
 class CuNetwork {
   typedef std::vector<CuComponent *> LayeredType;
  public:
-  CuNetwork() : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mEvGroup(NULL), mDpGroup(false), mBwdStreams(BwdStreamsDefault()), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false), mDpPeer(false) {
+  CuNetwork() : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mBatch(BatchDefault()), mWorld(1), mEvGroup(NULL), mDpGroup(false), mBwdStreams(BwdStreamsDefault()), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false), mDpPeer(false) {
     const char *e = getenv("TNB_FUSE");
     if (e && atoi(e) == 0) mFuse = false;
   }
   explicit CuNetwork(std::istream &rIn)
-      : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mWorld(1), mEvGroup(NULL), mDpGroup(false), mBwdStreams(BwdStreamsDefault()), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false), mDpPeer(false) {
+      : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mBatch(BatchDefault()), mWorld(1), mEvGroup(NULL), mDpGroup(false), mBwdStreams(BwdStreamsDefault()), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false), mDpPeer(false) {
     ReadNetwork(rIn);
   }
   ~CuNetwork() {
@@ -839,6 +877,8 @@ class CuNetwork {
   CuComponent &Layer(int i) { return *mNetComponents[i]; }
 
   static int BwdStreamsDefault() { const char *e = getenv("TNB_BWD_STREAMS"); return e ? atoi(e) : 1; }
+  static bool BatchDefault() { const char *e = getenv("TNB_GEMM_BATCH"); return !(e && atoi(e) == 0); }
+  void SetBatching(bool on) { mBatch = on; }
   void SetFusion(bool on) { mFuse = on; }
   /// order the compute stream behind every outstanding data-parallel update (stream order only; callers that time or end a
   /// run of bunches use it so that the last bunch's exchange is inside what they measure)
@@ -915,11 +955,35 @@ class CuNetwork {
     std::vector<CuBiasedLinearity *> deferred; // data parallel, all-reduce schedule: layers whose exchange is issued after the lowest layer's
     std::vector<void *> side_done;             // fused schedule on two streams: one event per layer, behind its update GEMM
     std::vector<TnbBiasJob> bias_jobs;         // fused schedule: bias halves of the updates, applied together after the last layer
+    int sig_done_by_batch = -1;                // batched schedule: index of the <sigmoid> whose backward the last dX job included
+    // Batched schedule (single GPU, fused): the dX GEMM of a layer shares ONE persistent launch with tiles of the weight-gradient
+    // GEMMs of the layers ABOVE it (tnb_gemm_batch).  A layer's update job enters the pool only after its own dX has been
+    // launched (the update rewrites W in place, dX reads it); what is left in the pool runs in a last launch.
+    std::vector<TnbGemmJob> pool;
+    const bool batch = mFuse && mBatch && mWorld == 1 && mBwdStreams != 2;
     for (int i = n - 1; i >= 0; i--) {
       CuComponent *c = mNetComponents[i];
       if (c != mpPropagErrorStopper) {
         bool done = false;
-        if (mFuse) {
+        if (batch && c->GetType() == CuComponent::BIASED_LINEARITY) {
+          // dX of this layer as a job, with the diff-sigmoid of a <sigmoid> right below fused as in the unbatched schedule
+          CuBiasedLinearity *lin = static_cast<CuBiasedLinearity *>(c);
+          const bool sig_below = i > 0 && mNetComponents[i - 1]->GetType() == CuComponent::SIGMOID && mNetComponents[i - 1] != mpPropagErrorStopper;
+          CuMatrix<BaseFloat> &eprev = sig_below ? mNetComponents[i - 1]->MutableErrorOutput() : c->MutableErrorOutput();
+          eprev.Init(c->GetErrorInput().Rows(), c->GetNInputs());
+          TnbGemmJob job;
+          // alone in a launch, a GEMM with fewer tiles than half the pairs is better off on the split-K tiles of the single-GEMM path
+          const bool pool_has_work = !pool.empty();
+          if (lin->MakeBackpropJob(c->GetErrorInput(), sig_below ? &mNetComponents[i - 1]->GetOutput() : NULL, eprev, &job) &&
+              (pool_has_work || tnb_gemm_job_tiles(&job) >= 48)) {
+            TNB_CHECK(tnb_gemm_batch(Cx(), &job, 1, pool.empty() ? NULL : &pool[0], (int)pool.size()));
+            while (!pool.empty() && pool.front().tile_count == 0) pool.erase(pool.begin());
+            done = true;
+            if (sig_below) sig_done_by_batch = i - 1;
+          }
+        }
+        if (!done && batch && c->GetType() == CuComponent::SIGMOID && i == sig_done_by_batch) done = true;
+        if (!done && mFuse) {
           // <softmax> backward is the identity: hand globerr to the layer below instead of copying it
           if (c->GetType() == CuComponent::SOFTMAX && i > 0) {
             mNetComponents[i - 1]->SetErrorInput(c->GetErrorInput());
@@ -963,7 +1027,10 @@ class CuNetwork {
           } else if (mFuse && c->GetType() == CuComponent::BIASED_LINEARITY) {
             bias_jobs.push_back(TnbBiasJob());
             CuBiasedLinearity *lin = static_cast<CuBiasedLinearity *>(c);
-            if (mBwdStreams == 2) {
+            TnbGemmJob ujob;
+            if (batch && (int)pool.size() < 4 && lin->MakeUpdateJob(&ujob, &bias_jobs.back())) {
+              pool.push_back(ujob);  // runs next to the dX GEMMs of the layers below (or in the closing launch)
+            } else if (mBwdStreams == 2) {
               // the weight-gradient GEMM (+ fused update) of this layer only needs E and X, which exist: it runs on a side stream next
               // to the dX GEMMs of the layers below (their CTAs fill the SMs the other kernel leaves free or has finished with)
               void *ev_dx = NULL, *ev_upd = NULL;
@@ -985,6 +1052,7 @@ class CuNetwork {
       }
       if (mpPropagErrorStopper == c) break;
     }
+    if (!pool.empty()) TNB_CHECK(tnb_gemm_batch(Cx(), NULL, 0, &pool[0], (int)pool.size()));  // closing launch: every update still in the pool
     for (size_t k = 0; k < side_done.size(); k++) TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_COMPUTE, side_done[k]));
     for (size_t k = 0; k < bias_jobs.size(); k += TNB_MAX_BIAS_JOBS)
       TNB_CHECK(tnb_bias_update_batch(Cx(), &bias_jobs[k], (int)std::min<size_t>(TNB_MAX_BIAS_JOBS, bias_jobs.size() - k)));
@@ -1126,6 +1194,7 @@ class CuNetwork {
   const char *mpLearnRateFactors;
   const char *mpTempBasisDir;
   bool mFuse;
+  bool mBatch;                     ///< fused schedule: independent backward GEMMs share persistent launches (tnb_gemm_batch; TNB_GEMM_BATCH=0 disables)
   int mWorld;
   void *mEvGroup;                  ///< data parallel: behind the grouped all-reduce of the deferred layers
   bool mDpGroup;                   ///< deferred layers in one NCCL launch (TNB_DP_GROUP=1; measured slower, off by default)

@@ -36,6 +36,21 @@ class PeerJob(C.Structure):
                 ("wc", C.c_float), ("grad_div_frm", C.c_int), ("n_frames", C.c_int)]
 
 
+EPI_STORE, EPI_FWD, EPI_DX, EPI_UPDATE = 0, 1, 2, 3
+
+
+class GemmJob(C.Structure):
+    """TnbGemmJob of include/tnet_b200.h (one GEMM + fused epilogue of a tnb_gemm_batch launch)."""
+    _fields_ = [("transa", C.c_int), ("transb", C.c_int), ("m", C.c_int), ("n", C.c_int), ("k", C.c_int),
+                ("A", C.c_void_p), ("lda", C.c_int), ("B", C.c_void_p), ("ldb", C.c_int),
+                ("A16", C.c_void_p), ("lda16", C.c_int), ("B16", C.c_void_p), ("ldb16", C.c_int),
+                ("epilogue", C.c_int), ("alpha", C.c_float), ("beta", C.c_float),
+                ("C", C.c_void_p), ("ldc", C.c_int), ("bias", C.c_void_p), ("act", C.c_int),
+                ("mulY", C.c_void_p), ("ldy", C.c_int), ("W", C.c_void_p), ("ldw", C.c_int), ("w_scale", C.c_float), ("w_l2", C.c_float),
+                ("C16", C.c_void_p), ("ldc16", C.c_int), ("W16", C.c_void_p), ("ldw16", C.c_int),
+                ("tile_first", C.c_int), ("tile_count", C.c_int)]
+
+
 class TnbError(RuntimeError):
     pass
 

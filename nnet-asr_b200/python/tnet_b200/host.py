@@ -106,6 +106,18 @@ class Net:
         fs = None if factors is None else ":".join(repr(float(x)) for x in factors).encode()
         hcheck(hlib().tnh_net_set_hyper(self.h, C.c_float(lr), fs, C.c_float(mmt), C.c_float(wc), C.c_int(int(gdf))))
 
+    def set_batching(self, on):
+        hcheck(hlib().tnh_net_set_batching(self.h, C.c_int(int(on))))
+
+    def get_affine_raw(self, idx):
+        """(W^T [nout x nin], bias) of layer idx straight from the device (no text round trip, full fp32 precision)"""
+        nin, nout = C.c_int(), C.c_int()
+        hcheck(hlib().tnh_net_get_affine(self.h, C.c_int(idx), None, None, C.byref(nin), C.byref(nout)))
+        W = np.empty((nin.value, nout.value), np.float32)
+        b = np.empty(nout.value, np.float32)
+        hcheck(hlib().tnh_net_get_affine(self.h, C.c_int(idx), P(W), P(b), None, None))
+        return np.ascontiguousarray(W.T), b
+
     def set_data_parallel(self, world):
         hcheck(hlib().tnh_net_set_data_parallel(self.h, C.c_int(world)))
 

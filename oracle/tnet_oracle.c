@@ -344,6 +344,42 @@ void orc_gemm(char transa, char transb, int m, int n, int k, float alpha, const 
               const float *B, int ldb, float beta, float *C, int ldc, int acc_double) {
   int ta = (transa == 'T' || transa == 't');
   int tb = (transb == 'T' || transb == 't');
+  if (!tb) {
+    /* op(B) = B is [k x n] row-major: walk it row by row with one accumulator per output column.  Every C[i][j] still sums its
+     * products in the order p = 0..k-1 (one sequential chain per element), so the result is the plain triple loop's bit for bit;
+     * only the memory access pattern differs (the full-size parity cases of tests/ finish in seconds instead of minutes). */
+#pragma omp parallel
+    {
+      double *accd = acc_double ? (double *)malloc(sizeof(double) * (size_t)n) : NULL;
+      float *accf = acc_double ? NULL : (float *)malloc(sizeof(float) * (size_t)n);
+#pragma omp for schedule(static)
+      for (int i = 0; i < m; i++) {
+        if (acc_double) {
+          for (int j = 0; j < n; j++) accd[j] = 0.0;
+          for (int p = 0; p < k; p++) {
+            const double a = (double)(ta ? A[IDX(p, i, lda)] : A[IDX(i, p, lda)]);
+            const float *brow = B + (size_t)p * (size_t)ldb;
+            for (int j = 0; j < n; j++) accd[j] += a * (double)brow[j];
+          }
+        } else {
+          for (int j = 0; j < n; j++) accf[j] = 0.0f;
+          for (int p = 0; p < k; p++) {
+            const float a = ta ? A[IDX(p, i, lda)] : A[IDX(i, p, lda)];
+            const float *brow = B + (size_t)p * (size_t)ldb;
+            for (int j = 0; j < n; j++) accf[j] = fmaf(a, brow[j], accf[j]);
+          }
+        }
+        for (int j = 0; j < n; j++) {
+          float r = acc_double ? (float)accd[j] : accf[j];
+          float old = (beta == 0.0f) ? 0.0f : beta * C[IDX(i, j, ldc)];
+          C[IDX(i, j, ldc)] = alpha * r + old;
+        }
+      }
+      free(accd);
+      free(accf);
+    }
+    return;
+  }
 #pragma omp parallel for schedule(static)
   for (int i = 0; i < m; i++) {
     for (int j = 0; j < n; j++) {
@@ -352,7 +388,7 @@ void orc_gemm(char transa, char transb, int m, int n, int k, float alpha, const 
         double acc = 0.0;
         for (int p = 0; p < k; p++) {
           float a = ta ? A[IDX(p, i, lda)] : A[IDX(i, p, lda)];
-          float b = tb ? B[IDX(j, p, ldb)] : B[IDX(p, j, ldb)];
+          float b = B[IDX(j, p, ldb)];
           acc += (double)a * (double)b;
         }
         r = (float)acc;
@@ -360,7 +396,7 @@ void orc_gemm(char transa, char transb, int m, int n, int k, float alpha, const 
         float acc = 0.0f;
         for (int p = 0; p < k; p++) {
           float a = ta ? A[IDX(p, i, lda)] : A[IDX(i, p, lda)];
-          float b = tb ? B[IDX(j, p, ldb)] : B[IDX(p, j, ldb)];
+          float b = B[IDX(j, p, ldb)];
           acc = fmaf(a, b, acc);
         }
         r = acc;

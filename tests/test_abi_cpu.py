@@ -51,10 +51,13 @@ def test_struct_layouts_match_the_header(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "tnet_b200.h"\n'
-                   'int main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(TnbPeerJob), offsetof(TnbPeerJob, W), offsetof(TnbPeerJob, dW),'
-                   ' offsetof(TnbPeerJob, n_frames), sizeof(TnbObjStats));return 0;}\n')
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(TnbPeerJob), offsetof(TnbPeerJob, W), offsetof(TnbPeerJob, dW),'
+                   ' offsetof(TnbPeerJob, n_frames), sizeof(TnbObjStats), sizeof(TnbGemmJob), offsetof(TnbGemmJob, A16), offsetof(TnbGemmJob, C),'
+                   ' offsetof(TnbGemmJob, w_scale), offsetof(TnbGemmJob, tile_first));return 0;}\n')
     exe = str(tmp_path / "sz")
     subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", exe])
     got = [int(v) for v in subprocess.check_output([exe], text=True).split()]
     P = abi.PeerJob
-    assert got == [C.sizeof(P), P.W.offset, P.dW.offset, P.n_frames.offset, C.sizeof(abi.ObjStats)]
+    J = abi.GemmJob
+    assert got == [C.sizeof(P), P.W.offset, P.dW.offset, P.n_frames.offset, C.sizeof(abi.ObjStats),
+                   C.sizeof(J), J.A16.offset, J.C.offset, J.w_scale.offset, J.tile_first.offset]

@@ -48,6 +48,9 @@ GEMM_SHAPES = [
     ("N", "N", 1, 7, 5),           # degenerate tiny
     ("T", "T", 130, 70, 45),       # the 4th operand-major combination
     ("N", "N", 128, 64, 32),       # exactly one tile, BN=64
+    ("N", "N", 1024, 2048, 2048),  # config C hidden layer, forward: the 256 x 256 split-K pair tiles that carry 80 % of the bench
+    ("N", "T", 1024, 2048, 2048),  # config C hidden layer, dX
+    ("T", "N", 2048, 2048, 1024),  # config C hidden layer, dW
 ]
 
 
@@ -74,7 +77,7 @@ def test_gemm_3xtf32_vs_oracle(ctx, ta, tb, M, N, K):
     assert err.max() < tol3x(K), err.max()
 
 
-@pytest.mark.parametrize("ta,tb,M,N,K", GEMM_SHAPES[:5] + GEMM_SHAPES[8:])
+@pytest.mark.parametrize("ta,tb,M,N,K", GEMM_SHAPES[:5] + GEMM_SHAPES[8:11])
 def test_gemm_tf32_vs_oracle(ctx, ta, tb, M, N, K):
     got, ref, scale = _gemm_case(ctx, ta, tb, M, N, K, abi.MATH_TF32)
     err = np.abs(got.astype(np.float64) - ref) / (scale + 1e-30)
@@ -194,6 +197,110 @@ def test_affine_update_vs_oracle(ctx, rows, nin, nout, mmt, wc, gdf):
     np.testing.assert_allclose(dW.download(), W2, rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(dcb.download()[0], cb2, rtol=1e-5, atol=1e-5 * np.abs(cb2).max())
     np.testing.assert_allclose(db.download()[0], b2, rtol=1e-5, atol=1e-6)
+
+
+def _batch_case(ctx, math, seed):
+    """Three independent GEMMs of a backward pass as jobs: dX with diff-sigmoid (NT), a momentum/L2 weight update (TN) and a plain
+    gradient (TN), with ragged edges in every direction (M = 429 + tail tile, N = 3000 = 11*256 + 184, K = 1000 = 31*32 + 8)."""
+    r = rng(seed)
+    rows, nin, nout = 1000, 429, 3000
+    E = (0.1 * r.standard_normal((rows, nout))).astype(np.float32)
+    W = (0.1 * r.standard_normal((nin, nout))).astype(np.float32)
+    Yp = r.random((rows, nin)).astype(np.float32)
+    X2 = r.standard_normal((rows, 429)).astype(np.float32)         # a second layer: [429 x 3000] weights (second row tile ragged)
+    W2 = (0.1 * r.standard_normal((429, nout))).astype(np.float32)
+    cW2 = (0.01 * r.standard_normal((429, nout))).astype(np.float32)
+    X3 = r.standard_normal((rows, 300)).astype(np.float32)         # a third layer: plain gradient [300 x 3000]
+    return dict(rows=rows, nin=nin, nout=nout, E=E, W=W, Yp=Yp, X2=X2, W2=W2, cW2=cW2, X3=X3)
+
+
+_round_bf16 = abi.bf16_round
+
+
+@pytest.mark.parametrize("math", ["3xtf32", "bf16"])
+@pytest.mark.parametrize("split_over_launches", [False, True])
+def test_gemm_batch_vs_oracle(ctx, math, split_over_launches):
+    """tnb_gemm_batch (csrc/gemm_multi.cu): several independent GEMMs with different operand majors and fused epilogues in ONE
+    persistent launch, against the oracle GEMM (double accumulation) + the reference's epilogue arithmetic.  With
+    split_over_launches the update and dX jobs sit in the POOL next to a mandatory gradient job and are finished by a closing
+    launch (tile_first / tile_count progress), which is how CuNetwork::Backpropagate uses it."""
+    d = _batch_case(ctx, math, 31)
+    bf = math == "bf16"
+    ctx.set_math(abi.MATH_BF16 if bf else abi.MATH_3XTF32)
+    rows, nin, nout = d["rows"], d["nin"], d["nout"]
+    lr, mmt, wc = 0.05, 0.5, 1e-3
+    try:
+        mats = {k: abi.DMat.from_numpy(ctx, d[k]) for k in ("E", "W", "Yp", "X2", "W2", "cW2", "X3")}
+        Ep, G3 = abi.DMat(ctx, rows, nin), abi.DMat(ctx, 300, nout)
+        jobs = (abi.GemmJob * 3)()
+        none = abi.MatrixDim(0, 0, 0)
+        abi.check(L.tnb_job_affine_bwd_dx(C.byref(jobs[0]), mats["E"].p(), mats["E"].dim, mats["W"].p(), mats["W"].dim, mats["Yp"].p(), mats["Yp"].dim,
+                                          Ep.p(), Ep.dim))
+        abi.check(L.tnb_job_affine_update(C.byref(jobs[1]), mats["X2"].p(), mats["X2"].dim, mats["E"].p(), mats["E"].dim, mats["W2"].p(), mats["W2"].dim,
+                                          mats["cW2"].p(), C.c_float(lr), C.c_float(mmt), C.c_float(wc), C.c_int(1), C.c_int(0)))
+        abi.check(L.tnb_job_affine_grad(C.byref(jobs[2]), mats["X3"].p(), mats["X3"].dim, mats["E"].p(), mats["E"].dim, G3.p(), G3.dim))
+        assert [jobs[i].tile_count for i in range(3)] == [4 * 2, 2 * 12, 2 * 12]   # ceil(m/256) x ceil(n/256)
+        tw = {}
+        if bf:
+            for k in ("E", "W", "X2", "X3"):
+                t = abi.DMat16(ctx, mats[k].rows, mats[k].cols)
+                abi.check(L.tnb_to_bf16(ctx.h, t.p(), C.c_int(t.stride), mats[k].p(), mats[k].dim))
+                tw[k] = t
+            tw["Ep"] = abi.DMat16(ctx, rows, nin)
+            tw["W2"] = abi.DMat16(ctx, 429, nout)
+            abi.check(L.tnb_job_set_twins(C.byref(jobs[0]), tw["E"].p(), C.c_int(tw["E"].stride), tw["W"].p(), C.c_int(tw["W"].stride), tw["Ep"].p(),
+                                          C.c_int(tw["Ep"].stride), None, C.c_int(0)))
+            abi.check(L.tnb_job_set_twins(C.byref(jobs[1]), tw["X2"].p(), C.c_int(tw["X2"].stride), tw["E"].p(), C.c_int(tw["E"].stride), None, C.c_int(0),
+                                          tw["W2"].p(), C.c_int(tw["W2"].stride)))
+            abi.check(L.tnb_job_set_twins(C.byref(jobs[2]), tw["X3"].p(), C.c_int(tw["X3"].stride), tw["E"].p(), C.c_int(tw["E"].stride), None, C.c_int(0),
+                                          None, C.c_int(0)))
+        for i in range(3):
+            assert L.tnb_gemm_batch_ok(ctx.h, C.byref(jobs[i])) == 1
+        l0 = ctx.launches()
+        if not split_over_launches:
+            abi.check(L.tnb_gemm_batch(ctx.h, jobs, C.c_int(3), None, C.c_int(0)))
+            assert ctx.launches() - l0 == 1
+        else:
+            # mandatory: the dX job (8 long tiles) on 16 pairs; pool: the update and gradient jobs (24 tiles each).  Only part of the
+            # pool fits next to the mandatory tiles; the closing launch runs the rest.
+            abi.check(L.tnb_gemm_batch_set_pairs(ctx.h, C.c_int(16)))
+            pool = (abi.GemmJob * 2)(jobs[1], jobs[2])
+            abi.check(L.tnb_gemm_batch(ctx.h, C.byref(jobs[0]), C.c_int(1), pool, C.c_int(2)))
+            left = pool[0].tile_count + pool[1].tile_count
+            assert 0 < left < 48, "part of the pool must run next to the mandatory job on 16 pairs (%d tiles left)" % left
+            assert all(pool[i].tile_first + pool[i].tile_count == 24 for i in range(2))
+            abi.check(L.tnb_gemm_batch(ctx.h, None, C.c_int(0), pool, C.c_int(2)))
+            assert pool[0].tile_count == 0 and pool[1].tile_count == 0 and pool[0].tile_first == 24 and pool[1].tile_first == 24
+            abi.check(L.tnb_gemm_batch_set_pairs(ctx.h, C.c_int(0)))
+            assert ctx.launches() - l0 == 2
+        ctx.sync()
+        q = _round_bf16 if bf else (lambda a: a)
+        E, W, Yp, X2, W2, cW2, X3 = (d[k] for k in ("E", "W", "Yp", "X2", "W2", "cW2", "X3"))
+        # dX .* y(1-y)
+        # tolerance of the plain GEMM tests: tol3x(K) relative to sum_k |a||b| (the tensor core's fp32 accumulation grows like sqrt(K))
+        def close(got, ref, A_, B_, K, extra=0.0, factor=1.0, what=""):
+            scale = np.abs(A_).astype(np.float64) @ np.abs(B_).astype(np.float64) * factor + extra
+            err = np.abs(got.astype(np.float64) - ref) / (scale + 1e-30)
+            assert err.max() < tol3x(K), (what, err.max())
+        # dX .* y(1-y)
+        pre = O.gemm("N", "T", 1.0, q(E), q(W), 0.0, np.zeros((rows, nin), np.float32), acc_double=1)
+        close(Ep.download(), O.diff_sigmoid(pre, Yp), q(E), q(W).T, nout, factor=(Yp * (1.0 - Yp)).astype(np.float64), what="dX")
+        # gradient
+        g3 = O.gemm("T", "N", 1.0, q(X3), q(E), 0.0, np.zeros((300, nout), np.float32), acc_double=1)
+        close(G3.download(), g3, q(X3).T, q(E), rows, what="gradient")
+        # update: corr = X^T E + mmt*corr ; W += scale*corr ; W += l2*W  (cuBiasedLinearity.cc:44-64)
+        scale, l2 = _update_scalars(lr, mmt, wc, 1, rows)
+        corr = O.gemm("T", "N", 1.0, q(X2), q(E), mmt, cW2, acc_double=1)
+        close(mats["cW2"].download(), corr, q(X2).T, q(E), rows, extra=mmt * np.abs(cW2), what="momentum buffer")
+        Wn = (scale * corr + W2).astype(np.float32)
+        Wn = (l2 * Wn + Wn).astype(np.float32)
+        np.testing.assert_allclose(mats["W2"].download(), Wn, rtol=1e-5, atol=2e-6)
+        if bf:  # the twins the epilogues keep current are the round-to-nearest-even of the fp32 values stored beside them
+            assert np.array_equal(tw["Ep"].download(), _round_bf16(Ep.download()))
+            assert np.array_equal(tw["W2"].download(), _round_bf16(mats["W2"].download()))
+    finally:
+        L.tnb_gemm_batch_set_pairs(ctx.h, C.c_int(0))
+        ctx.set_math(abi.MATH_3XTF32)
 
 
 def test_affine_grad_plus_sgd_update_equals_fused(ctx):

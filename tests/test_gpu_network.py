@@ -99,6 +99,62 @@ def test_one_bunch_layerwise_vs_oracle(dims, bunch, fusion):
     assert f1 == f2 and abs(c1 - c2) <= 1 and abs(e1 - e2) <= 2e-5 * abs(e2)
 
 
+@pytest.mark.parametrize("batching", [True, False], ids=["batched", "unbatched"])
+def test_config_c_one_bunch_layerwise_vs_oracle(batching):
+    """BASELINE configs[2] at FULL size — 429-2048x6-3000, bunch 1024, lr 0.008 / momentum 0.5 / weightcost 1e-6 as bench.py runs it —
+    one training bunch through CuNetwork (the tile shapes, split-K pairs and batched persistent launches the bench uses) against
+    the oracle with double accumulation: every layer's activations, the error signals above the stopper, the updated weights and
+    biases of all seven layers, cross-entropy and the frame-accuracy count.  Tolerances are those of the small cases above
+    (3xTF32 GEMM vs double-accumulated oracle).  Parameters go to the oracle straight from the device (tnh_net_get_affine)."""
+    dims, bunch = [429, 2048, 2048, 2048, 2048, 2048, 2048, 3000], 1024
+    r = np.random.default_rng(2024)
+    host.set_math(abi.MATH_3XTF32)
+    net = host.Net(dims=dims, seed=7)
+    net.set_batching(batching)
+    nl = 2 * (len(dims) - 1)
+    layers = []
+    for i in range(0, nl, 2):
+        Wt, b = net.get_affine_raw(i)
+        layers.append(("affine", Wt, b))
+        layers.append(("softmax" if i == nl - 2 else "sigmoid", dims[i // 2 + 1]))
+    X = r.standard_normal((bunch, dims[0])).astype(np.float32)
+    lab = r.integers(0, dims[-1], bunch)
+    T = np.zeros((bunch, dims[-1]), np.float32)
+    T[np.arange(bunch), lab] = 1
+    onet = O.Net(layers, acc_double=1)
+    for n in (net, onet):
+        n.set_hyper(0.008, mmt=0.5, wc=1e-6, gdf=True)
+        n.train_bunch(X, T)
+    net.layers = layers
+    for i in range(nl):
+        if layers[i][0] == "affine" and i + 1 < nl and layers[i + 1][0] == "sigmoid":
+            continue                # pre-activation is never materialised on the fused path
+        a, b = net.layer_out(i, bunch), onet.layer_out(i, bunch)
+        np.testing.assert_allclose(a, b, rtol=2e-4, atol=2e-5 * max(1.0, np.abs(b).max()), err_msg="output of layer %d" % i)
+    np.testing.assert_allclose(net.err(bunch), onet.err(bunch), rtol=1e-3, atol=1e-6)
+    for i in range(2, nl):
+        kind = layers[i][0]
+        if kind == "softmax" or (kind == "affine" and layers[i - 1][0] == "sigmoid"):
+            continue                # identity copy / dX+diffsigmoid written straight into the layer below
+        a, b = net.layer_eout(i, bunch), onet.layer_eout(i, bunch)
+        np.testing.assert_allclose(a, b, rtol=1e-3, atol=2e-5 * max(1e-3, np.abs(b).max()), err_msg="error output of layer %d" % i)
+    for i in range(0, nl, 2):
+        Wt, b = net.get_affine_raw(i)
+        oWt, ob = onet.get_affine(i)
+        # the update of one bunch moves a weight by ~1e-6: compare the MOVEMENT, not only the weight (whose 2e-5 tolerance would hide it)
+        dW, odW = Wt - layers[i][1], oWt - layers[i][1]
+        # (both sides round W + dW to fp32 independently: two ulps of the largest weight on top of the GEMM tolerance)
+        np.testing.assert_allclose(dW, odW, rtol=1e-3, atol=2e-5 * np.abs(odW).max() + 2 * np.spacing(np.abs(oWt).max()),
+                                   err_msg="weight update of layer %d" % i)
+        np.testing.assert_allclose(b - layers[i][2], ob - layers[i][2], rtol=1e-3,
+                                   atol=2e-5 * np.abs(ob - layers[i][2]).max() + 2 * np.spacing(max(1e-3, np.abs(ob).max())),
+                                   err_msg="bias update of layer %d" % i)
+    e1, f1, c1 = net.stats()
+    e2, f2, c2 = onet.stats()
+    assert f1 == f2 == bunch and abs(c1 - c2) <= 1 and abs(e1 - e2) <= 2e-5 * abs(e2)
+    net.close()
+
+
 NET_GOLD = sorted(glob.glob(os.path.join(GOLD, "*_net_*.npz")))
 
 
