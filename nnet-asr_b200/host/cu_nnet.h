@@ -852,12 +852,12 @@ inline CuObjectiveFunction *CuObjectiveFunction::Factory(ObjFunType type) {
 class CuNetwork {
   typedef std::vector<CuComponent *> LayeredType;
  public:
-  CuNetwork() : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mBatch(BatchDefault()), mWorld(1), mEvGroup(NULL), mDpGroup(false), mBwdStreams(BwdStreamsDefault()), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false), mDpPeer(false) {
+  CuNetwork() : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mBatch(BatchDefault()), mBatchPolicy(BatchPolicyDefault()), mBatchFlushTiles(BatchFlushDefault()), mWorld(1), mEvGroup(NULL), mDpGroup(false), mBwdStreams(BwdStreamsDefault()), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false), mDpPeer(false) {
     const char *e = getenv("TNB_FUSE");
     if (e && atoi(e) == 0) mFuse = false;
   }
   explicit CuNetwork(std::istream &rIn)
-      : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mBatch(BatchDefault()), mWorld(1), mEvGroup(NULL), mDpGroup(false), mBwdStreams(BwdStreamsDefault()), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false), mDpPeer(false) {
+      : mpPropagErrorStopper(NULL), mGlobLearnRate(0.0), mpLearnRateFactors(NULL), mpTempBasisDir(NULL), mFuse(true), mBatch(BatchDefault()), mBatchPolicy(BatchPolicyDefault()), mBatchFlushTiles(BatchFlushDefault()), mWorld(1), mEvGroup(NULL), mDpGroup(false), mBwdStreams(BwdStreamsDefault()), mDpDeferBegin(0), mDpDeferEnd(0), mDpShard(false), mDpPeer(false) {
     ReadNetwork(rIn);
   }
   ~CuNetwork() {
@@ -877,8 +877,13 @@ class CuNetwork {
   CuComponent &Layer(int i) { return *mNetComponents[i]; }
 
   static int BwdStreamsDefault() { const char *e = getenv("TNB_BWD_STREAMS"); return e ? atoi(e) : 1; }
-  static bool BatchDefault() { const char *e = getenv("TNB_GEMM_BATCH"); return !(e && atoi(e) == 0); }
-  void SetBatching(bool on) { mBatch = on; }
+  /// -1 = by measurement (profiles/r02_batch_kernel.md): on in bf16 mode (0.465 against 0.474 ms per bunch on config C), off in 3xTF32, whose
+  /// mainloop already saturates the shared-memory port, so that an epilogue running under it slows both (0.988 against 0.944 ms)
+  static int BatchDefault() { const char *e = getenv("TNB_GEMM_BATCH"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }
+  void SetBatching(bool on) { mBatch = on ? 1 : 0; }
+  static int BatchPolicyDefault() { const char *e = getenv("TNB_BATCH_POLICY"); return e ? atoi(e) : 1; }
+  static int BatchFlushDefault() { const char *e = getenv("TNB_BATCH_FLUSH_TILES"); return e ? atoi(e) : 148; }
+  void SetBatchPolicy(int p) { mBatchPolicy = p; }
   void SetFusion(bool on) { mFuse = on; }
   /// order the compute stream behind every outstanding data-parallel update (stream order only; callers that time or end a
   /// run of bunches use it so that the last bunch's exchange is inside what they measure)
@@ -959,13 +964,16 @@ class CuNetwork {
     // Batched schedule (single GPU, fused): the dX GEMM of a layer shares ONE persistent launch with tiles of the weight-gradient
     // GEMMs of the layers ABOVE it (tnb_gemm_batch).  A layer's update job enters the pool only after its own dX has been
     // launched (the update rewrites W in place, dX reads it); what is left in the pool runs in a last launch.
+    // mBatchPolicy 2: the dX chain keeps its own split-K launches (it is the critical path and wants all SMs); only the weight
+    // updates are pooled, and the pool runs as launches of two tiles per CTA pair whenever that many have accumulated.
     std::vector<TnbGemmJob> pool;
-    const bool batch = mFuse && mBatch && mWorld == 1 && mBwdStreams != 2;
+    const bool batch = mFuse && (mBatch == 1 || (mBatch < 0 && CuBiasedLinearity::Bf16())) && mWorld == 1 && mBwdStreams != 2;
+    const bool batch_dx = batch && mBatchPolicy == 1;
     for (int i = n - 1; i >= 0; i--) {
       CuComponent *c = mNetComponents[i];
       if (c != mpPropagErrorStopper) {
         bool done = false;
-        if (batch && c->GetType() == CuComponent::BIASED_LINEARITY) {
+        if (batch_dx && c->GetType() == CuComponent::BIASED_LINEARITY) {
           // dX of this layer as a job, with the diff-sigmoid of a <sigmoid> right below fused as in the unbatched schedule
           CuBiasedLinearity *lin = static_cast<CuBiasedLinearity *>(c);
           const bool sig_below = i > 0 && mNetComponents[i - 1]->GetType() == CuComponent::SIGMOID && mNetComponents[i - 1] != mpPropagErrorStopper;
@@ -1030,6 +1038,14 @@ class CuNetwork {
             TnbGemmJob ujob;
             if (batch && (int)pool.size() < 4 && lin->MakeUpdateJob(&ujob, &bias_jobs.back())) {
               pool.push_back(ujob);  // runs next to the dX GEMMs of the layers below (or in the closing launch)
+              if (!batch_dx) {       // policy 2: a full launch (two tiles on every pair) as soon as the pool holds one
+                int tiles = 0;
+                for (size_t k = 0; k < pool.size(); k++) tiles += pool[k].tile_count;
+                if (tiles >= mBatchFlushTiles || (int)pool.size() >= 4) {
+                  TNB_CHECK(tnb_gemm_batch(Cx(), NULL, 0, &pool[0], (int)pool.size()));
+                  pool.clear();
+                }
+              }
             } else if (mBwdStreams == 2) {
               // the weight-gradient GEMM (+ fused update) of this layer only needs E and X, which exist: it runs on a side stream next
               // to the dX GEMMs of the layers below (their CTAs fill the SMs the other kernel leaves free or has finished with)
@@ -1194,7 +1210,9 @@ class CuNetwork {
   const char *mpLearnRateFactors;
   const char *mpTempBasisDir;
   bool mFuse;
-  bool mBatch;                     ///< fused schedule: independent backward GEMMs share persistent launches (tnb_gemm_batch; TNB_GEMM_BATCH=0 disables)
+  int mBatch;                      ///< fused schedule: independent backward GEMMs share persistent launches (tnb_gemm_batch; TNB_GEMM_BATCH=0 disables)
+  int mBatchPolicy;                ///< 1: dX jobs share launches with pooled updates; 2: dX on its own split-K launches, updates pooled into full launches
+  int mBatchFlushTiles;            ///< policy 2: pool size (tiles) that triggers a launch
   int mWorld;
   void *mEvGroup;                  ///< data parallel: behind the grouped all-reduce of the deferred layers
   bool mDpGroup;                   ///< deferred layers in one NCCL launch (TNB_DP_GROUP=1; measured slower, off by default)
