@@ -327,10 +327,19 @@ typedef struct TnbObjStats_ {
 int tnb_softmax_xent(TnbContext *ctx, const float *A, const float *T, float *Y, float *Err, TnbMatrixDim d, TnbObjStats *stats);
 /* CuCrossEntropy::Evaluate on an existing softmax output */
 int tnb_xent_eval(TnbContext *ctx, const float *Y, const float *T, float *Err, TnbMatrixDim d, TnbObjStats *stats);
+/* The same two with the targets given as ONE CLASS ID PER ROW (labels[r * label_stride], int32) instead of a dense matrix — what
+ * the reference builds its one-hot rows from (KaldiLib/Labels.cc:66,156).  The one-hot row is generated in registers, so the 4*cols
+ * bytes per frame of the target read (12 kB at 3000 classes) and the dense matrix itself disappear; results are bit-identical to
+ * the dense form on the one-hot matrix of the same ids.  An id outside [0, cols) stands for an all-zero target row. */
+int tnb_softmax_xent_labels(TnbContext *ctx, const float *A, const int *labels, int label_stride, float *Y, float *Err, TnbMatrixDim d,
+                            TnbObjStats *stats);
+int tnb_xent_eval_labels(TnbContext *ctx, const float *Y, const int *labels, int label_stride, float *Err, TnbMatrixDim d, TnbObjStats *stats);
 /* CuMeanSquareError::Evaluate (cuObjectiveFunction.cc:26-46; no 1/2 factor) */
 int tnb_mse_eval(TnbContext *ctx, const float *Y, const float *T, float *Err, TnbMatrixDim d, TnbObjStats *stats);
 /* dense one-hot targets from class ids (Labels.cc:66,156 builds them on the host): T[r, lab[r]] = 1 else 0 */
 int tnb_onehot(TnbContext *ctx, float *T, const int *labels, TnbMatrixDim d);
+/* the same with the ids label_stride ints apart (the [frames x 1] label column CuCache keeps: stride = its pitch) */
+int tnb_onehot_strided(TnbContext *ctx, float *T, const int *labels, int label_stride, TnbMatrixDim d);
 
 /* ---- data-parallel exchange (no counterpart in the reference GPU path; mirrors the CPU trainer's
  *      gradient reduce, TNetLib/Platform.h:300-335, BiasedLinearity.cc:90-178) ------------------------ */
@@ -356,6 +365,14 @@ int tnb_allreduce_sum_multi(TnbContext *ctx, float *const *bufs, const size_t *c
 int tnb_dp_update(TnbContext *ctx, float *G, float *W, float *corrW, TnbMatrixDim dW, int rows_pad, float *gb, float *bias,
                   float *corrb, float lr, float mmt, float wc, int grad_div_frm, int n_frames_global);
 int tnb_comm_wait(TnbContext *ctx);
+/* Ranks as THREADS of one process, one GPU each (bin/TNetCu --GPUS=N): the group object is shared by the threads; each calls
+ * tnb_comm_init_local with its context and rank (collective: returns when all have).  Peer access is enabled between the group's
+ * GPUs, so the peer-memory schedule below works on plain device pointers (no NCCL, no CUDA IPC).  The NCCL schedules
+ * (tnb_allreduce_sum*, tnb_dp_update) need tnb_comm_init instead. */
+typedef struct TnbLocalGroup_ TnbLocalGroup;
+int tnb_local_group_create(TnbLocalGroup **out, int world);
+int tnb_local_group_destroy(TnbLocalGroup *group);
+int tnb_comm_init_local(TnbContext *ctx, TnbLocalGroup *group, int rank);
 
 /* ---- the same exchange without NCCL: one kernel per layer over NVLink peer memory (csrc/peer.cu) ------------------------------
  * One process per GPU on one NVSwitch box.  tnb_peer_map is collective over the ranks of tnb_comm_init: it exports `local` (the base

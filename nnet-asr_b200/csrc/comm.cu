@@ -11,7 +11,22 @@
 #include <dlfcn.h>
 #include <stdlib.h>
 
+#include <condition_variable>
+#include <mutex>
+
 #include "common.cuh"
+
+// ---- ranks as THREADS of one process (bin/TNetCu --GPUS=N): no NCCL, no CUDA IPC.  The ranks exchange bytes through a shared host
+// buffer behind a generation barrier; with peer access enabled every rank's device pointers are valid on every other rank's GPU.
+struct TnbLocalGroup_ {
+  int world = 0;
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0;
+  unsigned long generation = 0;
+  std::vector<unsigned char> gather;  // [world][n] of the exchange in flight
+  int devices[TNB_MAX_PEERS];
+};
 
 namespace tnb {
 
@@ -60,9 +75,31 @@ static int load_nccl() {
     }                                                                                             \
   } while (0)
 
+// all ranks of a local group meet here; the last one to arrive releases the others
+static void local_barrier(TnbLocalGroup_ *g, std::unique_lock<std::mutex> &lk) {
+  const unsigned long gen = g->generation;
+  if (++g->arrived == g->world) {
+    g->arrived = 0;
+    g->generation++;
+    g->cv.notify_all();
+  } else {
+    g->cv.wait(lk, [&] { return g->generation != gen; });
+  }
+}
+
 int comm_allgather_bytes(TnbContext *ctx, unsigned char *all, size_t n) {
   TNB_ARG(ctx && all && n > 0, "null");
   if (ctx->world == 1) return TNB_OK;
+  if (ctx->local_group) {
+    TnbLocalGroup_ *g = (TnbLocalGroup_ *)ctx->local_group;
+    std::unique_lock<std::mutex> lk(g->mu);
+    if (g->gather.size() != n * (size_t)g->world) g->gather.assign(n * (size_t)g->world, 0);
+    memcpy(&g->gather[n * (size_t)ctx->rank], all + n * (size_t)ctx->rank, n);
+    local_barrier(g, lk);               // everybody has written its slice
+    memcpy(all, g->gather.data(), n * (size_t)g->world);
+    local_barrier(g, lk);               // everybody has read: the buffer may be reused
+    return TNB_OK;
+  }
   int rc = load_nccl();
   if (rc != TNB_OK) return rc;
   TNB_ARG(ctx->nccl_comm != nullptr, "communicator not initialised");
@@ -115,8 +152,53 @@ int tnb_comm_init(TnbContext *ctx, const unsigned char id[TNB_NCCL_ID_BYTES], in
   return TNB_OK;
 }
 
+int tnb_local_group_create(TnbLocalGroup **out, int world) {
+  TNB_ARG(out && world >= 1 && world <= TNB_MAX_PEERS, "world");
+  TnbLocalGroup_ *g = new TnbLocalGroup_();
+  g->world = world;
+  for (int i = 0; i < TNB_MAX_PEERS; i++) g->devices[i] = -1;
+  *out = g;
+  return TNB_OK;
+}
+
+int tnb_local_group_destroy(TnbLocalGroup *g) {
+  delete g;
+  return TNB_OK;
+}
+
+int tnb_comm_init_local(TnbContext *ctx, TnbLocalGroup *g, int rank) {
+  TNB_ARG(ctx && g, "null");
+  TNB_ARG(rank >= 0 && rank < g->world, "rank");
+  TNB_ARG(ctx->nccl_comm == nullptr && ctx->local_group == nullptr, "the context already has a communicator");
+  ctx->local_group = g;
+  ctx->rank = rank;
+  ctx->world = g->world;
+  if (g->world == 1) return TNB_OK;
+  // every rank learns every rank's device, then enables peer access to the others (NVLink / NVSwitch on an HGX box)
+  std::vector<unsigned char> all(sizeof(int) * (size_t)g->world);
+  memcpy(&all[sizeof(int) * (size_t)rank], &ctx->device, sizeof(int));
+  int rc = comm_allgather_bytes(ctx, all.data(), sizeof(int));
+  if (rc != TNB_OK) return rc;
+  TNB_CUDA(cudaSetDevice(ctx->device));
+  for (int r = 0; r < g->world; r++) {
+    int dev;
+    memcpy(&dev, &all[sizeof(int) * (size_t)r], sizeof(int));
+    g->devices[r] = dev;
+    if (r == rank) continue;
+    if (dev == ctx->device) { set_error("local ranks %d and %d share GPU %d: kernels of different ranks wait for each other and need a GPU each", rank, r, dev); return TNB_ERR_ARG; }
+    int can = 0;
+    TNB_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, dev));
+    if (!can) { set_error("GPU %d cannot access GPU %d directly (no peer access)", ctx->device, dev); return TNB_ERR_UNSUPPORTED; }
+    cudaError_t e = cudaDeviceEnablePeerAccess(dev, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) TNB_CUDA(e);
+    cudaGetLastError();
+  }
+  return TNB_OK;
+}
+
 int tnb_comm_destroy(TnbContext *ctx) {
   TNB_ARG(ctx, "null");
+  ctx->local_group = nullptr;
   if (ctx->nccl_comm && p_CommDestroy) {
     cudaStreamSynchronize(ctx->comm_stream);
     p_CommDestroy((NcclComm)ctx->nccl_comm);

@@ -103,6 +103,7 @@ struct TnbContext_ {
   double prof_flops = 0.0;
   // data-parallel
   void *nccl_comm = nullptr;
+  void *local_group = nullptr;   // tnb_comm_init_local: the ranks are threads of this process (TnbLocalGroup)
   int rank = 0, world = 1;
   // peer-memory schedule (peer.cu): every rank's flag block as mapped into this process, and the launch counter
   unsigned *peer_flags[TNB_MAX_PEERS] = {};

@@ -335,11 +335,23 @@ __global__ void __launch_bounds__(256) rearrange_kernel(float *__restrict__ y, c
   }
 }
 
-__global__ void __launch_bounds__(256) onehot_kernel(float *__restrict__ T, const int *__restrict__ lab, int rows, int cols,
+// 16-byte stores where the row allows it (pitches are multiples of 32 floats; the pad columns of a row are never read as data)
+__global__ void __launch_bounds__(256) onehot_kernel(float *__restrict__ T, const int *__restrict__ lab, int lstride, int rows, int cols,
                                                      int stride) {
+  const bool vec = ((uintptr_t)T & 15) == 0 && (stride & 3) == 0;
   for (int r = blockIdx.x; r < rows; r += gridDim.x) {
-    const int l = lab[r];
-    for (int i = threadIdx.x; i < cols; i += blockDim.x) T[(size_t)r * stride + i] = (i == l) ? 1.0f : 0.0f;
+    const int l = lab[(size_t)r * lstride];
+    float *t = T + (size_t)r * stride;
+    if (vec) {
+      const int nq = cols >> 2;
+      for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+        const int c = q << 2;
+        ((float4 *)t)[q] = make_float4(c == l ? 1.0f : 0.0f, c + 1 == l ? 1.0f : 0.0f, c + 2 == l ? 1.0f : 0.0f, c + 3 == l ? 1.0f : 0.0f);
+      }
+      for (int i = (nq << 2) + threadIdx.x; i < cols; i += blockDim.x) t[i] = (i == l) ? 1.0f : 0.0f;
+    } else {
+      for (int i = threadIdx.x; i < cols; i += blockDim.x) t[i] = (i == l) ? 1.0f : 0.0f;
+    }
   }
 }
 
@@ -642,15 +654,16 @@ int tnb_randomize(TnbContext *ctx, float *y, const float *x, const int *copy_fro
   TNB_LAUNCHED(ctx);
   return TNB_OK;
 }
-int tnb_onehot(TnbContext *ctx, float *T, const int *labels, TnbMatrixDim d) {
-  TNB_ARG(ctx && T && labels, "null");
+int tnb_onehot_strided(TnbContext *ctx, float *T, const int *labels, int label_stride, TnbMatrixDim d) {
+  TNB_ARG(ctx && T && labels && label_stride >= 1, "null");
   DIMCHK(d);
   if (d.rows == 0 || d.cols == 0) return TNB_OK;
   int blocks = d.rows < ctx->sm_count * 8 ? d.rows : ctx->sm_count * 8;
-  onehot_kernel<<<blocks, 256, 0, ctx->stream>>>(T, labels, d.rows, d.cols, d.stride);
+  onehot_kernel<<<blocks, 256, 0, ctx->stream>>>(T, labels, label_stride, d.rows, d.cols, d.stride);
   TNB_LAUNCHED(ctx);
   return TNB_OK;
 }
+int tnb_onehot(TnbContext *ctx, float *T, const int *labels, TnbMatrixDim d) { return tnb_onehot_strided(ctx, T, labels, 1, d); }
 
 int tnb_rand(TnbContext *ctx, float *mat, unsigned *z1, unsigned *z2, unsigned *z3, unsigned *z4, TnbMatrixDim d) {
   return launch_rand<0>(ctx, mat, nullptr, 0.0f, z1, z2, z3, z4, d);

@@ -94,8 +94,12 @@ __device__ __forceinline__ int block_argmax_tree(const float *val, int *idx, int
 // MODE 0: softmax only (Y = softmax(A))
 // MODE 1: fused softmax + xent (A = activations; Y optional)
 // MODE 2: xent on given Y (A = Y input, no softmax)
+// Targets are either a dense matrix T (the reference's interface) or, when T == NULL, one class id per row (labels[r*lstride]):
+// the row of T is then the one-hot vector of that id, generated in registers — every value the kernel computes with is the one it
+// would have loaded, so both forms give the same bits (an id outside [0, cols) stands for an all-zero row).
 template <int MODE>
 __global__ void __launch_bounds__(ROW_THREADS) row_objective_kernel(const float *__restrict__ A, const float *__restrict__ T,
+                                                                    const int *__restrict__ labels, int lstride,
                                                                     float *__restrict__ Y, float *__restrict__ Err, int rows,
                                                                     int cols, int stride, float *__restrict__ row_xent,
                                                                     int *__restrict__ row_match) {
@@ -106,6 +110,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_objective_kernel(const float 
   const bool staged = cols <= ROW_SMEM_FLOATS;
   for (int r = blockIdx.x; r < rows; r += gridDim.x) {
     const float *a = A + (size_t)r * stride;
+    const int lab = (MODE != 0 && !T) ? labels[(size_t)r * lstride] : -1;
     // ---- load row, max ----
     float mx = -1e20f;
     for (int c = threadIdx.x; c < cols; c += ROW_THREADS) {
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_objective_kernel(const float 
       }
       if (MODE != 2 && Y) Y[(size_t)r * stride + c] = y;
       if (MODE != 0) {
-        float t = T[(size_t)r * stride + c];
+        float t = T ? T[(size_t)r * stride + c] : (c == lab ? 1.0f : 0.0f);
         Err[(size_t)r * stride + c] = y - t;
         float ly = logf(y < FLT_MIN ? FLT_MIN : y);
         xe += ly * t;
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_objective_kernel(const float 
       } else {
         __syncthreads();
         out_id = block_argmax_tree(srow, sidx, cols);  // srow holds y
-        for (int c = threadIdx.x; c < cols; c += ROW_THREADS) srow[c] = T[(size_t)r * stride + c];
+        for (int c = threadIdx.x; c < cols; c += ROW_THREADS) srow[c] = T ? T[(size_t)r * stride + c] : (c == lab ? 1.0f : 0.0f);
         __syncthreads();
         des_id = block_argmax_tree(srow, sidx, cols);
       }
@@ -179,6 +184,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_objective_kernel(const float 
 constexpr int ROW_VEC_MAX = 4;
 template <int MODE>
 __global__ void __launch_bounds__(ROW_THREADS) row_softmax_xent_wide_kernel(const float *__restrict__ A, const float *__restrict__ T,
+                                                                            const int *__restrict__ labels, int lstride,
                                                                             float *__restrict__ Y, float *__restrict__ Err, int rows,
                                                                             int cols, int stride, float *__restrict__ row_xent,
                                                                             int *__restrict__ row_match) {
@@ -188,11 +194,18 @@ __global__ void __launch_bounds__(ROW_THREADS) row_softmax_xent_wide_kernel(cons
   for (int r = blockIdx.x; r < rows; r += gridDim.x) {
     const float4 *a4 = (const float4 *)(A + (size_t)r * stride);
     const float4 *t4 = (const float4 *)(T + (size_t)r * stride);
+    const int lab = (MODE == 1 && !T) ? labels[(size_t)r * lstride] : -1;
     float4 av[ROW_VEC_MAX], tv[ROW_VEC_MAX];
 #pragma unroll
     for (int i = 0; i < ROW_VEC_MAX; i++) {
       const int qd = threadIdx.x + i * ROW_THREADS;
-      if (qd < nq) { av[i] = a4[qd]; if (MODE == 1) tv[i] = t4[qd]; }
+      if (qd < nq) {
+        av[i] = a4[qd];
+        if (MODE == 1) {
+          if (T) tv[i] = t4[qd];
+          else { const int c = qd << 2; tv[i] = make_float4(c == lab ? 1.0f : 0.0f, c + 1 == lab ? 1.0f : 0.0f, c + 2 == lab ? 1.0f : 0.0f, c + 3 == lab ? 1.0f : 0.0f); }
+        }
+      }
     }
     float mx = -1e20f;
 #pragma unroll
@@ -320,10 +333,11 @@ __global__ void __launch_bounds__(256) stats_fold_kernel(const float *__restrict
 
 template <int MODE>
 static int launch_row_objective(TnbContext *ctx, const float *A, const float *T, float *Y, float *Err, TnbMatrixDim d,
-                                TnbObjStats *stats) {
+                                TnbObjStats *stats, const int *labels = nullptr, int lstride = 1) {
   TNB_ARG(ctx && A, "null");
   TNB_ARG(d.rows >= 0 && d.cols > 0 && d.stride >= d.cols, "dims");
-  if (MODE != 0) TNB_ARG(T && Err && stats, "null");
+  if (MODE != 0) TNB_ARG((T || labels) && Err && stats, "null");
+  if (labels) TNB_ARG(!T && lstride >= 1, "either a dense target matrix or class ids");
   if (MODE == 0) TNB_ARG(Y, "null");
   if (MODE == 1 && d.cols > ROW_SMEM_FLOATS) TNB_ARG(Y, "rows wider than 8192 need the Y buffer");
   if (d.rows == 0) return TNB_OK;
@@ -333,10 +347,10 @@ static int launch_row_objective(TnbContext *ctx, const float *A, const float *T,
   const bool wide = MODE != 2 && d.cols > 256 && d.cols <= 4 * ROW_VEC_MAX * ROW_THREADS && (d.cols & 3) == 0 && (d.stride & 3) == 0 &&
                     ((uintptr_t)A & 15) == 0 && ((uintptr_t)T & 15) == 0 && ((uintptr_t)Err & 15) == 0 && (!Y || ((uintptr_t)Y & 15) == 0);
   if (wide)
-    row_softmax_xent_wide_kernel<(MODE == 0 ? 0 : 1)><<<blocks, ROW_THREADS, 0, ctx->stream>>>(A, T, Y, Err, d.rows, d.cols, d.stride, ctx->row_scratch,
-                                                                          ctx->row_match);
+    row_softmax_xent_wide_kernel<(MODE == 0 ? 0 : 1)><<<blocks, ROW_THREADS, 0, ctx->stream>>>(A, T, labels, lstride, Y, Err, d.rows, d.cols, d.stride,
+                                                                                              ctx->row_scratch, ctx->row_match);
   else
-    row_objective_kernel<MODE><<<blocks, ROW_THREADS, 0, ctx->stream>>>(A, T, Y, Err, d.rows, d.cols, d.stride, ctx->row_scratch,
+    row_objective_kernel<MODE><<<blocks, ROW_THREADS, 0, ctx->stream>>>(A, T, labels, lstride, Y, Err, d.rows, d.cols, d.stride, ctx->row_scratch,
                                                                          ctx->row_match);
   TNB_LAUNCHED(ctx);
   if (MODE != 0) {
@@ -360,6 +374,15 @@ int tnb_softmax_xent(TnbContext *ctx, const float *A, const float *T, float *Y, 
 }
 int tnb_xent_eval(TnbContext *ctx, const float *Y, const float *T, float *Err, TnbMatrixDim d, TnbObjStats *stats) {
   return launch_row_objective<2>(ctx, Y, T, nullptr, Err, d, stats);
+}
+int tnb_softmax_xent_labels(TnbContext *ctx, const float *A, const int *labels, int label_stride, float *Y, float *Err, TnbMatrixDim d,
+                            TnbObjStats *stats) {
+  TNB_ARG(labels != nullptr, "null");
+  return launch_row_objective<1>(ctx, A, nullptr, Y, Err, d, stats, labels, label_stride);
+}
+int tnb_xent_eval_labels(TnbContext *ctx, const float *Y, const int *labels, int label_stride, float *Err, TnbMatrixDim d, TnbObjStats *stats) {
+  TNB_ARG(labels != nullptr, "null");
+  return launch_row_objective<2>(ctx, Y, nullptr, nullptr, Err, d, stats, labels, label_stride);
 }
 int tnb_mse_eval(TnbContext *ctx, const float *Y, const float *T, float *Err, TnbMatrixDim d, TnbObjStats *stats) {
   TNB_ARG(ctx && Y && T && Err && stats, "null");

@@ -275,6 +275,15 @@ int tnb_peer_map(TnbContext *ctx, void *local, void **mapped) {
   mapped[rank] = local;
   if (world == 1) return TNB_OK;
   TNB_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->local_group) {
+    // ranks are threads of this process with peer access enabled (tnb_comm_init_local): a rank's device pointer is valid as it is
+    std::vector<unsigned char> ptrs((size_t)world * sizeof(void *));
+    memcpy(&ptrs[(size_t)rank * sizeof(void *)], &local, sizeof(void *));
+    int rcl = comm_allgather_bytes(ctx, ptrs.data(), sizeof(void *));
+    if (rcl != TNB_OK) return rcl;
+    for (int r = 0; r < world; r++) memcpy(&mapped[r], &ptrs[(size_t)r * sizeof(void *)], sizeof(void *));
+    return TNB_OK;
+  }
   static_assert(sizeof(cudaIpcMemHandle_t) == TNB_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
   std::vector<unsigned char> all((size_t)world * TNB_IPC_HANDLE_BYTES);
   cudaIpcMemHandle_t h;
@@ -293,6 +302,7 @@ int tnb_peer_map(TnbContext *ctx, void *local, void **mapped) {
 
 int tnb_peer_unmap(TnbContext *ctx, void *const *mapped) {
   TNB_ARG(ctx && mapped, "null");
+  if (ctx->local_group) return TNB_OK;  // plain peer pointers: nothing was opened
   for (int r = 0; r < ctx->world; r++)
     if (r != ctx->rank && mapped[r]) cudaIpcCloseMemHandle(mapped[r]);
   return TNB_OK;
@@ -302,7 +312,7 @@ int tnb_dp_peer_update(TnbContext *ctx, const TnbPeerJob *job, void *wait_event,
   TNB_ARG(ctx && job, "null");
   cudaStream_t cs = ctx->world > 1 ? ctx->comm_stream : ctx->main_stream;
   if (ctx->world > 1) {
-    TNB_ARG(ctx->nccl_comm != nullptr, "communicator not initialised");
+    TNB_ARG(ctx->nccl_comm != nullptr || ctx->local_group != nullptr, "communicator not initialised");
     int rc = ensure_peer_flags(ctx);
     if (rc != TNB_OK) return rc;
     TNB_CUDA(cudaEventRecord(ctx->ev_compute, ctx->main_stream));  // the gradient GEMM (and this layer's dX before it) is the producer

@@ -55,6 +55,19 @@ struct TnhNet_ {
     net.PropagateEvaluate(feats, labs, *obj, globerr);
     if (!cv) net.Backpropagate(globerr);
   }
+  /// the same step with the targets as class ids on the device (`stride` ints apart): no one-hot matrix exists anywhere.
+  /// Objectives other than cross-entropy need the dense targets and get them expanded here.
+  void StepIds(const CuMatrix<BaseFloat> &x, const int *ids, int stride, bool cv) {
+    CuCrossEntropy *xent = dynamic_cast<CuCrossEntropy *>(obj);
+    if (xent) {
+      net.PropagateEvaluateIds(x, ids, stride, *xent, globerr);
+    } else {
+      labs.Init(x.Rows(), net.GetNOutputs());
+      TNB_CHECK(tnb_onehot_strided(Cx(), labs.pCUData(), ids, stride, labs.Dim()));
+      net.PropagateEvaluate(x, labs, *obj, globerr);
+    }
+    if (!cv) net.Backpropagate(globerr);
+  }
 };
 
 struct TnhCache_ {
@@ -205,9 +218,7 @@ int tnh_net_train_bunch_labels(TnhNet *h, const float *x, const int *lab, int ro
   upload(h->feats, x, rows, (int)h->net.GetNInputs());
   h->labels.Init(rows);
   TNB_CHECK(tnb_memcpy(Cx(), h->labels.pCUData(), lab, sizeof(int) * (size_t)rows, 0));
-  h->labs.Init(rows, h->net.GetNOutputs());
-  TNB_CHECK(tnb_onehot(Cx(), h->labs.pCUData(), h->labels.pCUData(), h->labs.Dim()));
-  h->Step(cv != 0);
+  h->StepIds(h->feats, h->labels.pCUData(), 1, cv != 0);
   TNH_CATCH
 }
 int tnh_net_submit_bunch_labels(TnhNet *h, const float *x, const int *lab, int rows, int cv) {
@@ -235,10 +246,7 @@ int tnh_net_submit_bunch_labels(TnhNet *h, const float *x, const int *lab, int r
   TNB_CHECK(tnb_memcpy_on(Cx(), TNB_STREAM_COPY, s.labels.pCUData(), lab, sizeof(int) * (size_t)rows, 0));
   TNB_CHECK(tnb_event_record(Cx(), s.ready, TNB_STREAM_COPY));
   TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_COMPUTE, s.ready));
-  h->labs.Init(rows, h->net.GetNOutputs());
-  TNB_CHECK(tnb_onehot(Cx(), h->labs.pCUData(), s.labels.pCUData(), h->labs.Dim()));
-  h->net.PropagateEvaluate(s.feats, h->labs, *h->obj, h->globerr);
-  if (!cv) h->net.Backpropagate(h->globerr);
+  h->StepIds(s.feats, s.labels.pCUData(), 1, cv != 0);
   TNB_CHECK(tnb_event_record(Cx(), s.used, TNB_STREAM_COMPUTE));
   TNB_CHECK(tnb_memcpy_on(Cx(), TNB_STREAM_COMPUTE, s.stats_host, h->obj->DeviceStats(), sizeof(TnbObjStats), 1));
   TNB_CHECK(tnb_event_record(Cx(), s.done, TNB_STREAM_COMPUTE));
@@ -287,12 +295,10 @@ int tnh_net_train_resident(TnhNet *h, int bunch, int first, int n, int cv) {
   const int total = (int)h->res_feats.Rows() / bunch;
   if (total <= 0) Error("resident set smaller than one bunch");
   h->feats.Init(bunch, h->net.GetNInputs());
-  h->labs.Init(bunch, h->net.GetNOutputs());
   for (int b = 0; b < n; b++) {
     const size_t r0 = (size_t)((first + b) % total) * bunch;
-    h->feats.CopyRows(bunch, r0, h->res_feats, 0);  // CuCache::GetBunch's D2D row window
-    TNB_CHECK(tnb_onehot(Cx(), h->labs.pCUData(), h->res_labels.pCUData() + r0, h->labs.Dim()));
-    h->Step(cv != 0);
+    h->feats.CopyRows(bunch, r0, h->res_feats, 0);  // CuCache::GetBunch's D2D row window; the ids of the window are read in place
+    h->StepIds(h->feats, h->res_labels.pCUData() + r0, 1, cv != 0);
   }
   h->net.WaitDataParallel();  // the last bunch's exchange belongs to this call (stream order; the host does not block)
   TNH_CATCH

@@ -27,10 +27,20 @@ namespace TNet {
     }                                                                                            \
   } while (0)
 
-/// Process-wide device singleton (reference: cudevice.h:15-73).  Lazily creates the TnbContext.
+/// The device singleton of the reference (cudevice.h:15-73), one PER THREAD: a thread that never starts another one sees exactly the
+/// reference's process-wide object; the loader thread and the per-GPU worker threads of bin/TNetCu each get their own context (own
+/// streams, own GPU) behind the same Cx().  Lazily creates the TnbContext.
 class CuDevice {
  public:
-  static CuDevice &Instantiate() { static CuDevice dev; return dev; }
+  static CuDevice &Instantiate() { static thread_local CuDevice dev; return dev; }
+  /// a new thread starts from the arithmetic mode (and, unless gpu_id >= 0, the GPU) of the thread that created it
+  void InheritFrom(CuDevice &parent, int gpu_id = -1) {
+    mMath = parent.Math();
+    int dev = gpu_id;
+    if (dev < 0) TNB_CHECK(tnb_ctx_device(parent.Ctx(), &dev));
+    SelectGPU(dev);
+  }
+  int Device() { int d = -1; TNB_CHECK(tnb_ctx_device(Ctx(), &d)); return d; }
   ~CuDevice() {
     if (mVerbose && mCtx) PrintProfile();
     if (mCtx) tnb_ctx_destroy(mCtx);
@@ -170,6 +180,12 @@ class CuMatrix {
   /// the allocation has been mapped into other processes (tnb_peer_map): freeing it while a peer still has it open is undefined
   /// (cudaIpcOpenMemHandle), and the peers close at their own pace — it is left to the end of the process instead
   void MarkExported() { mExported = true; }
+  /// exchange the buffers of two matrices (no device work)
+  void Swap(CuMatrix<T> &o) {
+    std::swap(mRows, o.mRows); std::swap(mCols, o.mCols); std::swap(mStride, o.mStride); std::swap(mCap, o.mCap);
+    std::swap(mpCUData, o.mpCUData); std::swap(mpTwin, o.mpTwin); std::swap(mTwinCap, o.mTwinCap); std::swap(mTwinStride, o.mTwinStride);
+    std::swap(mTwinValid, o.mTwinValid); std::swap(mExported, o.mExported);
+  }
   void Destroy() {
     if (mpCUData && !mExported) tnb_free(Cx(), mpCUData);
     mExported = false;

@@ -827,6 +827,36 @@ class CuCrossEntropy : public CuObjectiveFunction {
     rNetError.Init(rAct.Rows(), rAct.Cols());
     TNB_CHECK(tnb_softmax_xent(Cx(), rAct.pCUData(), rDesired.pCUData(), rSoftmaxOut.pCUData(), rNetError.pCUData(), rAct.Dim(), mpStats));
   }
+  /// Targets as ONE CLASS ID PER FRAME: rLabels is a [rows x 1] matrix whose 4-byte elements hold int32 ids (the form CuCache keeps
+  /// them in when it is fed ids: 128 bytes per frame of pitch instead of 4 * nOutputs).  Same results, bit for bit, as Evaluate on the
+  /// one-hot matrix of those ids (tnb_xent_eval_labels).
+  void EvaluateLabels(const CuMatrix<BaseFloat> &rNetOutput, const CuMatrix<BaseFloat> &rLabels, CuMatrix<BaseFloat> &rNetError) {
+    if (rLabels.Cols() != 1 || rLabels.Rows() != rNetOutput.Rows()) Error("EvaluateLabels: the labels must be a [frames x 1] matrix of class ids");
+    EvaluateIds(rNetOutput, (const int *)rLabels.pCUData(), (int)rLabels.Stride(), rNetError);
+  }
+  void EvaluateFromActivationsLabels(const CuMatrix<BaseFloat> &rAct, const CuMatrix<BaseFloat> &rLabels, CuMatrix<BaseFloat> &rSoftmaxOut,
+                                     CuMatrix<BaseFloat> &rNetError) {
+    if (rLabels.Cols() != 1 || rLabels.Rows() != rAct.Rows()) Error("EvaluateFromActivationsLabels: the labels must be a [frames x 1] matrix of class ids");
+    EvaluateFromActivationsIds(rAct, (const int *)rLabels.pCUData(), (int)rLabels.Stride(), rSoftmaxOut, rNetError);
+  }
+  /// the same on a device array of ids, `stride` ints apart (1 = packed), one per row of the network output
+  void EvaluateIds(const CuMatrix<BaseFloat> &rNetOutput, const int *pIds, int stride, CuMatrix<BaseFloat> &rNetError) {
+    rNetError.Init(rNetOutput.Rows(), rNetOutput.Cols());
+    TNB_CHECK(tnb_xent_eval_labels(Cx(), rNetOutput.pCUData(), pIds, stride, rNetError.pCUData(), rNetOutput.Dim(), mpStats));
+  }
+  void EvaluateFromActivationsIds(const CuMatrix<BaseFloat> &rAct, const int *pIds, int stride, CuMatrix<BaseFloat> &rSoftmaxOut,
+                                  CuMatrix<BaseFloat> &rNetError) {
+    rSoftmaxOut.Init(rAct.Rows(), rAct.Cols());
+    rNetError.Init(rAct.Rows(), rAct.Cols());
+    TNB_CHECK(tnb_softmax_xent_labels(Cx(), rAct.pCUData(), pIds, stride, rSoftmaxOut.pCUData(), rNetError.pCUData(), rAct.Dim(), mpStats));
+  }
+  /// [frames x 1] label matrix from a vector of ids (a strided device-to-device copy; the bits of the ints are kept)
+  static void LabelsFromIds(const CuVector<int> &rIds, size_t first, size_t rows, CuMatrix<BaseFloat> &rLabels) {
+    if (first + rows > rIds.Dim()) Error("LabelsFromIds: range");
+    rLabels.Init(rows, 1);
+    if (rows == 0) return;
+    TNB_CHECK(tnb_memcpy2d(Cx(), rLabels.pCUData(), rLabels.Stride() * sizeof(BaseFloat), rIds.pCUData() + first, sizeof(int), sizeof(int), rows, 2));
+  }
   /// byte-compatible with cuObjectiveFunction.h:132-144 (tools/train/training_scheduler.sh greps it)
   std::string Report() {
     TnbObjStats st = Read();
@@ -948,6 +978,24 @@ class CuNetwork {
       if (n == 0) Error("PropagateEvaluate on an empty network");
       ForwardTo(in, n);
       obj.Evaluate(mNetComponents.back()->GetOutput(), desired, globerr);
+    }
+  }
+
+  /// PropagateEvaluate with class ids ([frames x 1] matrix of int32 bits, see CuCrossEntropy::EvaluateLabels) instead of dense targets
+  void PropagateEvaluateLabels(const CuMatrix<BaseFloat> &in, const CuMatrix<BaseFloat> &labels, CuCrossEntropy &xent, CuMatrix<BaseFloat> &globerr) {
+    if (labels.Cols() != 1 || labels.Rows() != in.Rows()) Error("PropagateEvaluateLabels: the labels must be a [frames x 1] matrix of class ids");
+    PropagateEvaluateIds(in, (const int *)labels.pCUData(), (int)labels.Stride(), xent, globerr);
+  }
+  /// ... or a device array of ids `stride` ints apart (1 = packed), one per row of `in`
+  void PropagateEvaluateIds(const CuMatrix<BaseFloat> &in, const int *pIds, int stride, CuCrossEntropy &xent, CuMatrix<BaseFloat> &globerr) {
+    size_t n = mNetComponents.size();
+    if (n == 0) Error("PropagateEvaluate on an empty network");
+    if (mFuse && n >= 2 && mNetComponents[n - 1]->GetType() == CuComponent::SOFTMAX) {
+      ForwardTo(in, n - 1);
+      xent.EvaluateFromActivationsIds(mNetComponents[n - 2]->GetOutput(), pIds, stride, mNetComponents[n - 1]->MutableOutput(), globerr);
+    } else {
+      ForwardTo(in, n);
+      xent.EvaluateIds(mNetComponents.back()->GetOutput(), pIds, stride, globerr);
     }
   }
 
@@ -1237,6 +1285,14 @@ class CuCache {
   void AddData(const CuMatrix<BaseFloat> &rFeatures, const CuMatrix<BaseFloat> &rDesired);
   void Randomize();
   void GetBunch(CuMatrix<BaseFloat> &rFeatures, CuMatrix<BaseFloat> &rDesired);
+  /// hand the rows that did not fit into this fill to `dst` (the cache object of the NEXT fill): two cache objects filled
+  /// alternately then hold exactly what the reference's single cache holds fill after fill (cuCache.cc:60-76,102-108)
+  void MoveLeftoverTo(CuCache &dst) {
+    dst.mFeaturesLeftover.Swap(mFeaturesLeftover);
+    dst.mDesiredLeftover.Swap(mDesiredLeftover);
+    mFeaturesLeftover.Destroy();
+    mDesiredLeftover.Destroy();
+  }
   bool Full() { return (mState == FULL); }
   bool Empty() { return (mState == EMPTY || mIntakePos < mBunchsize); }
   int Discarded() { return mDiscarded; }

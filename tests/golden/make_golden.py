@@ -76,7 +76,7 @@ def pack_layers(prefix, layers, out):
             k += 1
 
 
-def run_mlp(case, cfg, impl, workdir, exe=None, save=True):
+def run_mlp(case, cfg, impl, workdir, exe=None, save=True, extra=None):
     rng = np.random.default_rng(cfg["seed"] + 1000)
     utts = F.gen_utterances(cfg["n_utt"], cfg["n_frames"], cfg["raw_dim"], cfg["n_out"], rng)
     paths = F.write_dataset(workdir, utts, cfg["n_out"], cfg["ctx"])
@@ -100,6 +100,8 @@ def run_mlp(case, cfg, impl, workdir, exe=None, save=True):
         cmd += ["--LEARNRATEFACTORS=" + cfg["factors"]]
     if cfg.get("cv"):
         cmd += ["--CROSSVALIDATE=TRUE"]
+    if extra:
+        cmd += list(extra)      # flags of the drop-in that the reference does not have (--GPUS, --LOADER, ...)
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("reference failed:\n" + res.stdout[-3000:])

@@ -34,6 +34,50 @@ def test_tnetcu_binary_reproduces_reference(case):
             k += 1
 
 
+@pytest.mark.parametrize("case", ["mlp_small", "mlp_mmt_wide"])
+def test_tnetcu_loader_thread_changes_nothing(case):
+    """The loader thread (cache k filled while cache 1-k trains) against --LOADER=FALSE (read, then train, as the
+    reference's loop does): same report line and the same network file, byte for byte — same fills, same leftovers, same lrand48 order."""
+    outs = []
+    for flag in ("--LOADER=TRUE", "--LOADER=FALSE"):
+        with tempfile.TemporaryDirectory() as d:
+            rep, layers, out = MG.run_mlp(case, MG.MLP_CASES[case], "gpu", d, exe=os.path.join(BIN, "TNetCu"), save=False, extra=[flag])
+            outs.append((rep, layers))
+    assert outs[0][0] == outs[1][0]
+    for a, b in zip(outs[0][1], outs[1][1]):
+        if a[0] == "affine":
+            assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+@pytest.mark.parametrize("case", ["mlp_mmt_wide", "mlp_bigbunch"])
+def test_tnetcu_two_gpus_reproduce_one(case):
+    """bin/TNetCu --GPUS=2 (ONE cache and ONE permutation, GPU g trains rows [g*B/2, (g+1)*B/2) of every bunch, gradients
+    summed and the update applied over NVLink peer memory with N = the whole bunch) against the single-GPU run AND the reference
+    TNetCu's golden: same frames, cross-entropy, accuracy and weights."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    g = np.load(os.path.join(GOLD, "gpu_%s.npz" % case))
+    res = []
+    for flag in ("--GPUS=1", "--GPUS=2"):
+        with tempfile.TemporaryDirectory() as d:
+            rep, layers, out = MG.run_mlp(case, MG.MLP_CASES[case], "gpu", d, exe=os.path.join(BIN, "TNetCu"), save=False, extra=[flag])
+            res.append((rep, layers, out))
+    assert "Data parallel: 2 GPUs" in res[1][2]
+    r1, r2 = res[0][0], res[1][0]
+    assert r1["frames"] == r2["frames"] == int(g["ref_frames"])
+    assert abs(r1["err"] - r2["err"]) <= 2e-6 * abs(r1["err"])          # partial sums of the two halves of a bunch instead of one sum
+    assert abs(r2["err"] - float(g["ref_err"])) <= 1e-4 * abs(float(g["ref_err"]))
+    assert abs(r1["correct_pct"] - r2["correct_pct"]) <= 0.05 and abs(r2["correct_pct"] - float(g["ref_correct_pct"])) <= 0.2
+    k = 0
+    for a, b in zip(res[0][1], res[1][1]):
+        if a[0] == "affine":
+            np.testing.assert_allclose(b[1], a[1], rtol=2e-5, atol=2e-5 * np.abs(a[1]).max())
+            rW = g["final_Wt%d" % k]
+            np.testing.assert_allclose(b[1], rW, rtol=2e-4, atol=2e-4 * np.abs(rW).max())
+            k += 1
+
+
 def _net_cases():
     import glob
     return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLD, "*_net_*.npz")))

@@ -445,6 +445,48 @@ def test_peer_update_timeout_is_reported_not_fatal(ctx):
     assert r.returncode == 0 and "TIMEOUT_REPORTED" in r.stdout, r.stdout[-2000:]
 
 
+@pytest.mark.parametrize("rows,cols", [(64, 10), (33, 135), (100, 256), (128, 300), (1024, 3000), (16, 5000), (7, 9001)])
+def test_objective_with_class_ids_is_bit_identical_to_dense_targets(ctx, rows, cols):
+    """tnb_softmax_xent_labels / tnb_xent_eval_labels (targets as one class id per frame, what Labels.cc:66,156 builds its one-hot rows
+    from) against the dense-target entry points on the one-hot matrix of the same ids: softmax output, error signal, cross-entropy
+    sum and frame-accuracy count must agree BIT FOR BIT, for every kernel path (tree arg-max <= 256 columns, register-resident wide
+    rows, staged and unstaged generic rows) and for ids kept `stride` ints apart (the [frames x 1] column of the cache)."""
+    r = rng(rows * 7 + cols)
+    A = (3.0 * r.standard_normal((rows, cols))).astype(np.float32)
+    lab = r.integers(0, cols, rows).astype(np.int32)
+    A[0, :] = 0.0                                   # a row of ties: first-maximum / index-tree rule decides the accuracy flag
+    lab[0] = min(3, cols - 1)
+    T = np.zeros((rows, cols), np.float32)
+    T[np.arange(rows), lab] = 1
+    dA, dT = abi.DMat.from_numpy(ctx, A), abi.DMat.from_numpy(ctx, T)
+    labcol = abi.DMat.from_numpy(ctx, lab.reshape(-1, 1))          # [rows x 1] int column, pitch 32
+    labvec = abi.DMat.from_numpy(ctx, lab.reshape(1, -1))
+    outs = []
+    for mode in ("dense", "ids_strided", "ids_packed"):
+        Y, E = abi.DMat(ctx, rows, cols), abi.DMat(ctx, rows, cols)
+        st = abi.DStats(ctx)
+        if mode == "dense":
+            abi.check(L.tnb_softmax_xent(ctx.h, dA.p(), dT.p(), Y.p(), E.p(), dA.dim, st.p()))
+        elif mode == "ids_strided":
+            abi.check(L.tnb_softmax_xent_labels(ctx.h, dA.p(), labcol.p(C.c_int), C.c_int(labcol.stride), Y.p(), E.p(), dA.dim, st.p()))
+        else:
+            abi.check(L.tnb_softmax_xent_labels(ctx.h, dA.p(), labvec.p(C.c_int), C.c_int(1), Y.p(), E.p(), dA.dim, st.p()))
+        # xent on the given softmax output (the unfused CuCrossEntropy::Evaluate) through the same two forms
+        E2 = abi.DMat(ctx, rows, cols)
+        st2 = abi.DStats(ctx)
+        if mode == "dense":
+            abi.check(L.tnb_xent_eval(ctx.h, Y.p(), dT.p(), E2.p(), dA.dim, st2.p()))
+        else:
+            lp, ls = (labcol.p(C.c_int), labcol.stride) if mode == "ids_strided" else (labvec.p(C.c_int), 1)
+            abi.check(L.tnb_xent_eval_labels(ctx.h, Y.p(), lp, C.c_int(ls), E2.p(), dA.dim, st2.p()))
+        outs.append((Y.download(), E.download(), st.read(), E2.download(), st2.read()))
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1]) and np.array_equal(o[3], outs[0][3])
+        assert o[2] == outs[0][2] and o[4] == outs[0][4]
+    # and the dense form is the oracle's (the existing parity test): a spot check on the frame count
+    assert outs[0][2][1] == rows
+
+
 # ------------------------------------------------------------------------------------------------ elementwise
 def _mat(ctx, a):
     return abi.DMat.from_numpy(ctx, a)
