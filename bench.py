@@ -183,7 +183,7 @@ def cpu_reference_throughput(bunches_a, bunches_b, threads=None):
     if fb <= fa or tb <= ta:
         raise RuntimeError("reference runs did not scale: %s frames in %.1fs vs %s in %.1fs" % (fa, ta, fb, tb))
     fps = (fb - fa) / (tb - ta)
-    return fps, threads, "reference TNet --THREADS=%d, slope between %d and %d frames of config C (%.1fs, %.1fs wall)" % (
+    return fps, threads, "reference TNet --THREADS=%d, slope between %d and %d frames of the workload (%.1fs, %.1fs wall)" % (
         threads, fa, fb, ta, tb)
 
 
@@ -191,9 +191,10 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps = max(1, min(args.steps, 12))     # bounded sample: each CPU step is one 1024-frame bunch
+    steps = max(1, min(args.steps, 12))     # bounded sample: each CPU step is one bunch (1024 frames in config C)
     try:
-        fps, threads, sample = cpu_reference_throughput(2, 2 + steps)
+        # the small configs train a bunch in a few milliseconds on the host: longer runs, so that every worker thread sees data
+        fps, threads, sample = cpu_reference_throughput(2, 2 + steps) if args.config == "C" else cpu_reference_throughput(40, 40 + 20 * steps)
     except Exception as e:  # the oracle always exists; a failure here is an error, not "unavailable"
         print(json.dumps({"impl": "reference", "error": str(e)[:300]}))
         return 1
@@ -201,12 +202,148 @@ def reference_arm(args):
         "impl": "reference", "metric": "training_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": 2, "ms_per_step": 1000.0 * BUNCH / fps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "bunch": BUNCH, "note": "CPU reference trains ONE 1024-frame bunch per step on host cores"},
+        "config": {"workload": WORKLOAD, "bunch": BUNCH, "note": "CPU reference trains ONE %d-frame bunch per step on host cores" % BUNCH},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ the other BASELINE configs
+CONFIGS = {
+    # name: dims, bunch, splice context, momentum, workload text (BASELINE.json configs[0..4])
+    "A": ([351, 1024, 135], 256, 4, 0.0, "examples/01test-shape MLP3 351-1024-135, bunch 256 (BASELINE configs[0])"),
+    "B": ([351, 2048, 135], 256, 4, 0.5, "MLP3 newbob TIMIT-shape 351-2048-135, bunch 256, momentum (BASELINE configs[1])"),
+    "C": (None, None, None, None, None),
+}
+
+
+def select_config(name):
+    global DIMS, BUNCH, CTX, MMT, WORKLOAD
+    if name in ("A", "B"):
+        DIMS, BUNCH, CTX, MMT, WORKLOAD = CONFIGS[name]
+
+
+def bench_rbm_rnn(args):
+    """BASELINE configs[3] (D: TRbmCu CD-1, Gaussian-Bernoulli 429 x 2048, bunch 128) and configs[4] (E: TRecurrentCu 351+1024 -> 1024 -> 135,
+    BPTT 20): frames/s through the C handles of libtnetb200_host.so, the oracle port timed beside it on a bounded sample."""
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    import torch
+    from tnet_b200 import abi, host
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    torch.cuda.set_device(0)
+    host.select_gpu(0)
+    host.set_math({"3xtf32": abi.MATH_3XTF32, "tf32": abi.MATH_TF32, "bf16": abi.MATH_BF16}[args.math])
+    L, ctx = abi.lib(), host.ctx_handle()
+    stream = torch.cuda.ExternalStream(host_stream(L, ctx), device=torch.device("cuda", 0))
+    r = np.random.default_rng(20240607)
+    pk = measured_peaks()
+    sampler = ClockSampler(0)
+    sampler.start()
+
+    def windows(fn, n):
+        out = []
+        for _ in range(n):
+            host.sync(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            host.sync(); torch.cuda.synchronize()
+            out.append(e0.elapsed_time(e1))
+        return out
+
+    if args.config == "D":
+        nvis, nhid, bunch = 429, 2048, 128
+        Wt = (0.1 * r.standard_normal((nhid, nvis))).astype(np.float32)
+        rbm = host.Rbm(Wt, np.zeros(nvis, np.float32), np.zeros(nhid, np.float32), True, False, bunch, 0.001, 0.5, 2e-4)
+        steps = max(args.steps, 50)
+        X = r.standard_normal((steps * bunch, nvis)).astype(np.float32)
+        cache = host.Cache(steps * bunch, bunch)
+
+        def fill():
+            cache.add(X, np.zeros((X.shape[0], 1), np.float32))
+        for _ in range(max(1, args.warmup // 3)):
+            fill(); rbm.cd1_from_cache(cache)
+        ms = []
+        l0 = 0
+        for _ in range(args.windows):
+            fill()                                   # host -> device upload of the window's frames: outside the timed region
+            l0 = host.launches()
+            ms += windows(lambda: rbm.cd1_from_cache(cache), 1)
+            l0 = host.launches() - l0
+        t = sorted(ms)[len(ms) // 2]
+        frames = steps * bunch
+        value = frames / (t / 1000.0)
+        # end to end: every bunch uploaded from host memory inside the timed region (tnh_rbm_cd1_bunch: upload, step, synchronise)
+        t0 = time.perf_counter()
+        for b in range(steps):
+            rbm.cd1(X[b * bunch:(b + 1) * bunch])
+        e2e = frames / (time.perf_counter() - t0)
+        fpf = 10 * nvis * nhid
+        # oracle port on a bounded sample
+        orbm = O.Rbm(Wt, np.zeros(nvis, np.float32), np.zeros(nhid, np.float32), True, False, 0.001, 0.5, 2e-4)
+        z = [r.integers(129, 2 ** 31, (bunch, nhid)).astype(np.uint32) for _ in range(4)]
+        t0 = time.perf_counter()
+        nb = 0
+        while time.perf_counter() - t0 < 10.0:
+            orbm.cd1(X[:bunch], z); nb += 1
+        cpu = nb * bunch / (time.perf_counter() - t0)
+        work = "TRbmCu CD-1, Gaussian-Bernoulli RBM 429 x 2048, bunch 128, lr 0.001 / momentum 0.5 / weightcost 2e-4 (BASELINE configs[3])"
+        cfg = {"workload": work, "bunch": bunch, "flops_per_frame": fpf, "windows_ms": ms, "gemm_math": args.math,
+               "timed_region": "K x (propagate, sample, reconstruct, propagate, fused CD-1 update, MSE) from a device-resident cache"}
+        e2e_obj = {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": bunch * nvis * 4, "d2h_bytes_per_step": 0}
+        sample = "oracle port (oracle/tnet_oracle.c, OpenMP GEMM), %d CD-1 bunches of 128 frames" % nb
+    else:
+        nin, H, nout, bptt, T = 351, 1024, 135, 20, 1000
+        Wr = (0.1 * r.standard_normal((H, nin + H))).astype(np.float32)
+        Wo = (0.1 * r.standard_normal((nout, H))).astype(np.float32)
+        layers = [("recurrent", Wr, np.zeros(H, np.float32), nin), ("affine", Wo, np.zeros(nout, np.float32)), ("softmax", nout)]
+        rnn = host.Rnn(layers, bptt, 0.001)
+        X = r.standard_normal((T, nin)).astype(np.float32)
+        lab = r.integers(0, nout, T).astype(np.int32)
+        rnn.train_utterance(X[:200], lab[:200])
+        ms = []
+        l0 = 0
+        for _ in range(min(3, args.windows)):
+            l0 = host.launches()
+            ms += windows(lambda: rnn.train_utterance(X, lab), 1)
+            l0 = host.launches() - l0
+        t = sorted(ms)[len(ms) // 2]
+        frames, steps, bunch = T, T, 1
+        value = frames / (t / 1000.0)
+        e2e = value                                  # train_utterance already takes host buffers (1.4 MB upload inside the timed call)
+        fpf = 2 * (nin + H) * H * (2 + bptt) + 4 * H * nout   # forward GEMV + BPTT chain GEMVs + rank-1 updates + output layer
+        # oracle port on a bounded sample: frames of the same layer through orc_rnn_propagate / orc_rnn_update
+        ornn = O.Rnn(Wr, np.zeros(H, np.float32), nin, bptt, 0.001)
+        t0 = time.perf_counter()
+        nf = 0
+        while time.perf_counter() - t0 < 10.0 and nf < T:
+            ornn.propagate(X[nf]); ornn.update(np.full(H, 1e-3, np.float32)); nf += 1
+        cpu = nf / (time.perf_counter() - t0)
+        work = "TRecurrentCu simple recurrent layer 351+1024 -> 1024 -> 135 softmax, BPTT 20, one 1000-frame utterance (BASELINE configs[4])"
+        cfg = {"workload": work, "bunch": 1, "flops_per_frame": fpf, "windows_ms": ms, "gemm_math": "fp32 (GEMV / rank-1 kernels)",
+               "timed_region": "one utterance, frame by frame (forward, cross-entropy, truncated BPTT update), per-frame sequence replayed as a CUDA graph"}
+        e2e_obj = {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": (nin + 1) * 4, "d2h_bytes_per_step": 0}
+        sample = "oracle port (recurrent layer only: orc_rnn_propagate + orc_rnn_update), %d frames" % nf
+    clocks = sampler.stop()
+    achieved = fpf * value / 1e12
+    line = {"metric": "training_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": 1, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": t / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.config == "E" else {"3xtf32": "tf32x3", "tf32": "tf32", "bf16": "bf16"}[args.math], "data": "synthetic",
+            "config": cfg, "clocks": clocks, "e2e": e2e_obj, "gpu_launches": int(l0),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+                         "traffic": None, "peak_source": pk["source"] + " (bf16 sustained)",
+                         "note": "whole step (every kernel) as algorithmic flops per second; config %s is %s" % (
+                             args.config, "launch/latency-bound at bunch 128 (a 429 x 2048 layer)" if args.config == "D" else
+                             "frame-serial by construction (the weights change every frame): frames/s is the figure of merit")},
+            "cpu_baseline": {"value": cpu, "unit": "frames/s", "cores": os.cpu_count() if args.config == "D" else 1, "kind": "port", "sample": sample}}
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     return 0
 
 
@@ -236,9 +373,15 @@ def main():
     ap.add_argument("--windows", type=int, default=5, help="timed windows of --steps bunches; the median is reported")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the bf16-mode and other-scaling sub-objects and the peak probe")
+    ap.add_argument("--config", default="C", choices=["A", "B", "C", "D", "E"],
+                    help="BASELINE.json configs[0..4]; C (the configuration the metric is quoted on) is the default and the only multi-GPU one")
     args = ap.parse_args()
+    select_config(args.config)
     if args.impl == "reference":
         return reference_arm(args)
+    if args.config in ("D", "E"):
+        args.warmup = max(args.warmup, 3)
+        return bench_rbm_rnn(args)
     args.warmup = max(args.warmup, 3)
     args.windows = max(args.windows, 1)
     # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner does) go to stderr instead
@@ -474,7 +617,8 @@ def main():
             "vs_baseline": None, "dtype": {"3xtf32": "tf32x3", "tf32": "tf32", "bf16": "bf16"}[args.math], "data": "synthetic",
             "config": {"workload": WORKLOAD, "dims": DIMS, "bunch_per_gpu": bunch, "global_bunch": bunch * world,
                        "parallelism": "dp%d" % world, "dp_schedule": dp_state["schedule"], "learn_rate": LR, "momentum": MMT, "weightcost": WC,
-                       "l2_note": "no L2 flush: weights+corrections (224 MB) and activations exceed the 126 MB L2 every step",
+                       "l2_note": ("no L2 flush: weights+corrections (224 MB) and activations exceed the 126 MB L2 every step" if args.config == "C" else
+                                   "no L2 flush: the model (2-4 MB) is L2-resident by nature; the 16 resident bunches rotate"),
                        "timed_region": "K x (row window of the resident set, int labels -> one-hot, forward, softmax+xent+accuracy, backward, "
                                        "update); the cache shuffle and the splice run once per cache fill and are outside it (~5 us per bunch amortised)",
                        "windows_ms": win_ms, "windows": "median of %d windows of %d bunches" % (len(win_ms), args.steps),
@@ -507,7 +651,7 @@ def main():
                 line[k + "_scaling"] = obj
         if world == 1 and not args.no_cpu_baseline:
             try:
-                fps, threads, sample = cpu_reference_throughput(2, 10)
+                fps, threads, sample = cpu_reference_throughput(2, 10) if args.config == "C" else cpu_reference_throughput(40, 240)
                 line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "reference", "sample": sample}
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % str(e)[:200]}

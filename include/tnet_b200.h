@@ -297,6 +297,16 @@ int tnb_gemm_batch_set_pairs(TnbContext *ctx, int pairs);
 /* developer aid (TNB_BATCH_TRACE=1): clock64() stamps [pair][64] of the last tnb_gemm_batch launch (slots: csrc/gemm_multi.cu) */
 int tnb_gemm_batch_trace_read(TnbContext *ctx, long long *out);
 
+/* CuRbm::RbmUpdate, the CD-1 update of TRbmCu (cuRbm.cc:131-174), for the weights and both biases: the reference issues two GEMMs,
+ * two weight-sized AddScaled sweeps, four column sums and two vector adds; here the second GEMM's epilogue does the sweeps
+ * (corrW += -lr*wc*W ; W += corrW on the tile it has just produced) and one kernel per bias does its two column sums and updates:
+ *   corrW = mmt*corrW + (lr/N) * (pos_vis^T pos_hid - neg_vis^T neg_hid) - lr*wc*W ;  W += corrW
+ *   corr_b = mmt*corr_b + (lr/N) * (colsum(pos) - colsum(neg)) ;  b += corr_b          (visible and hidden)
+ * in the reference's operation order.  N = rows of the bunch. */
+int tnb_rbm_cd1_update(TnbContext *ctx, const float *pos_vis, const float *neg_vis, TnbMatrixDim dV, const float *pos_hid, const float *neg_hid,
+                       TnbMatrixDim dH, float *W, TnbMatrixDim dW, float *corrW, float *vis_bias, float *corr_vb, float *hid_bias, float *corr_hb,
+                       float lr, float mmt, float wc);
+
 /* tnb_sgd_update (cuBiasedLinearity.cc:55-63) for several layers in one launch (the data-parallel step applies them after the last all-reduce); W16/ldw16:
  * optional bf16 twin of W to refresh (NULL otherwise). */
 typedef struct TnbSgdJob_ {

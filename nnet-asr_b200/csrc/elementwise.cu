@@ -733,6 +733,62 @@ int tnb_affine_update(TnbContext *ctx, const float *X, TnbMatrixDim dX, const fl
   return launch_colsum_update(ctx, 1.0f, E, mmt, corrb, dE.rows, dE.cols, dE.stride, bias, scale);
 }
 
+// ---- CuRbm::RbmUpdate (cuRbm.cc:131-174) ---------------------------------------------------------------------------------------
+// One thread per column: the two serial double-precision column sums of the reference's _add_col_sum (cukernels.cu:155-167, the path
+// AddColSum takes for more than 256 columns or more than 512 rows), then the three vector updates, in the reference's order:
+//   corr = (-a)*colsum(neg) + mmt*corr ; corr = a*colsum(pos) + corr ; bias = corr + bias
+__global__ void __launch_bounds__(128) rbm_bias_kernel(const float *__restrict__ pos, const float *__restrict__ neg, int rows, int cols, int stride,
+                                                       float *__restrict__ bias, float *__restrict__ corr, float a, float mmt) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double sp = 0.0, sn = 0.0;
+  for (int r = 0; r < rows; r++) {
+    sp += pos[(size_t)r * stride + c];
+    sn += neg[(size_t)r * stride + c];
+  }
+  float k = corr[c];
+  k = (float)((double)(-a) * sn + (double)(mmt * k));
+  k = (float)((double)a * sp + (double)(1.0f * k));
+  corr[c] = k;
+  bias[c] = 1.0f * k + 1.0f * bias[c];
+}
+
+int tnb_rbm_cd1_update(TnbContext *ctx, const float *pos_vis, const float *neg_vis, TnbMatrixDim dV, const float *pos_hid, const float *neg_hid,
+                       TnbMatrixDim dH, float *W, TnbMatrixDim dW, float *corrW, float *vis_bias, float *corr_vb, float *hid_bias, float *corr_hb,
+                       float lr, float mmt, float wc) {
+  TNB_ARG(ctx && pos_vis && neg_vis && pos_hid && neg_hid && W && corrW && vis_bias && corr_vb && hid_bias && corr_hb, "null");
+  TNB_ARG(dV.rows == dH.rows && dV.rows > 0 && dW.rows == dV.cols && dW.cols == dH.cols, "dimension mismatch");
+  const float a = lr / (float)dV.rows;  // the reference evaluates lr/N in float (cuRbm.cc:140)
+  // corrW = -a * neg_vis^T neg_hid + mmt*corrW                       (cuRbm.cc:143)
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.C = corrW; ep.ldc = dW.stride; ep.alpha = -a; ep.beta = mmt;
+  int rc = launch_gemm(ctx, 'T', 'N', dV.cols, dH.cols, dV.rows, neg_vis, dV.stride, neg_hid, dH.stride, ep);
+  if (rc != TNB_OK) return rc;
+  // corrW = +a * pos_vis^T pos_hid + corrW ; corrW += -lr*wc*W ; W += corrW      (cuRbm.cc:144-146: one GEMM with the two sweeps in its epilogue)
+  ep.alpha = a; ep.beta = 1.0f;
+  ep.W = W; ep.ldw = dW.stride; ep.w_scale = 1.0f; ep.w_l2 = 0.0f; ep.c_wdecay = -lr * wc;
+  rc = launch_gemm(ctx, 'T', 'N', dV.cols, dH.cols, dV.rows, pos_vis, dV.stride, pos_hid, dH.stride, ep);
+  if (rc != TNB_OK) return rc;
+  // the two biases (cuRbm.cc:148-154)
+  const float *pp[2] = {pos_vis, pos_hid}, *nn[2] = {neg_vis, neg_hid};
+  const TnbMatrixDim dd[2] = {dV, dH};
+  float *bb[2] = {vis_bias, hid_bias}, *kk[2] = {corr_vb, corr_hb};
+  for (int i = 0; i < 2; i++) {
+    if (dd[i].rows > 512 || dd[i].cols > 256) {
+      rbm_bias_kernel<<<(dd[i].cols + 127) / 128, 128, 0, ctx->stream>>>(pp[i], nn[i], dd[i].rows, dd[i].cols, dd[i].stride, bb[i], kk[i], a, mmt);
+      TNB_LAUNCHED(ctx);
+    } else {  // small shapes take the reference's float tree reduction: the 1:1 entry points reproduce it
+      TnbMatrixDim dv = {1, dd[i].cols, dd[i].cols};
+      rc = tnb_add_col_sum(ctx, -a, nn[i], mmt, kk[i], dd[i]);
+      if (rc == TNB_OK) rc = tnb_add_col_sum(ctx, a, pp[i], 1.0f, kk[i], dd[i]);
+      if (rc == TNB_OK) rc = tnb_add_scaled(ctx, 1.0f, kk[i], 1.0f, bb[i], dv);
+      if (rc != TNB_OK) return rc;
+    }
+  }
+  return TNB_OK;
+}
+
 int tnb_bias_update_batch(TnbContext *ctx, const TnbBiasJob *jobs, int n) { return tnb_bias_update_batch_on(ctx, TNB_STREAM_COMPUTE, jobs, n); }
 
 int tnb_bias_update_batch_on(TnbContext *ctx, int stream_id, const TnbBiasJob *jobs, int n) {

@@ -12,6 +12,7 @@ struct EpiParams {
   const float *mulY; int ldy;   // out *= y*(1-y)              (CuSigmoid::BackpropagateFnc)
   float *W; int ldw;            // fused SGD: W += w_scale*out ; W += w_l2*W
   float w_scale, w_l2;
+  float c_wdecay;               // generic epilogue only: out += c_wdecay * W_old before the store and the W update (CD-1: corr += -lr*wc*W)
   uint16_t *C16; int ldc16;     // optional bf16 copy of the stored output (TNB_MATH_BF16 shadows)
   uint16_t *W16; int ldw16;     // optional bf16 copy of the updated weights
   int mode;                     // EPI_*: which specialised epilogue the fused entry point asks for (EPI_GENERIC = any combination)

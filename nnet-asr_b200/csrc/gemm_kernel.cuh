@@ -577,11 +577,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #ifdef TNB_GEMM_TRACE
               if (ep.alpha == -77.0f) { asm volatile("" ::"f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)); continue; }  // probe: epilogue without its stores
 #endif
+              float4 *wp = (float4 *)(ep.W + (size_t)row * ep.ldw + n);
+              float4 w = make_float4(0, 0, 0, 0);
+              if (ep.W) {
+                w = *wp;
+                if (ep.c_wdecay != 0.0f) { o.x = ep.c_wdecay * w.x + o.x; o.y = ep.c_wdecay * w.y + o.y; o.z = ep.c_wdecay * w.z + o.z; o.w = ep.c_wdecay * w.w + o.w; }
+              }
               *(float4 *)(ep.C + crow + n) = o;
               if (ep.C16) st16(ep.C16, ep.ldc16, row, n, o);
               if (ep.W) {
-                float4 *wp = (float4 *)(ep.W + (size_t)row * ep.ldw + n);
-                float4 w = *wp;
                 w.x = ep.w_scale * o.x + w.x; w.y = ep.w_scale * o.y + w.y;
                 w.z = ep.w_scale * o.z + w.z; w.w = ep.w_scale * o.w + w.w;
                 if (ep.w_l2 != 0.0f) {
@@ -608,6 +612,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             float bs = ep.bias ? ep.bias[n + t] : 0.0f;
             float yv = ep.mulY ? ep.mulY[(size_t)row * ep.ldy + n + t] : 0.0f;
             float o = epi_one(ep, acc[t], cold, bs, yv);
+            if (ep.W && ep.c_wdecay != 0.0f) o = ep.c_wdecay * ep.W[(size_t)row * ep.ldw + n + t] + o;
             ep.C[crow + n + t] = o;
             if (ep.C16) ep.C16[(size_t)row * ep.ldc16 + n + t] = __bfloat16_as_ushort(__float2bfloat16_rn(o));
             if (ep.W) {

@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float *__restrict_
       float bv = ep.bias ? ep.bias[n] : 0.0f;
       float yv = ep.mulY ? ep.mulY[(size_t)row * ep.ldy + n] : 0.0f;
       float o = epi_one(ep, acc[i][j], cold, bv, yv);
+      if (ep.W && ep.c_wdecay != 0.0f) o = ep.c_wdecay * ep.W[(size_t)row * ep.ldw + n] + o;
       ep.C[ci] = o;
       if (ep.W) {
         float *wp = ep.W + (size_t)row * ep.ldw + n;

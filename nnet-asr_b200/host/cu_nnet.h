@@ -618,17 +618,11 @@ class CuRbm : public CuRbmBase {
     if (!(pos_vis.Rows() == pos_hid.Rows() && pos_vis.Rows() == neg_vis.Rows() && pos_vis.Rows() == neg_hid.Rows() &&
           pos_vis.Cols() == neg_vis.Cols() && pos_hid.Cols() == neg_hid.Cols() && pos_vis.Cols() == mNInputs && pos_hid.Cols() == mNOutputs))
       Error("RbmUpdate: non-matching dimensions");
-    BaseFloat N = static_cast<BaseFloat>(pos_vis.Rows());
-    mVisHidCorrection.Gemm('T', 'N', -mLearningRate / N, neg_vis, neg_hid, mMomentum);
-    mVisHidCorrection.Gemm('T', 'N', +mLearningRate / N, pos_vis, pos_hid, 1.0);
-    mVisHidCorrection.AddScaled(-mLearningRate * mWeightcost, mVisHid, 1.0);
-    mVisHid.AddScaled(1.0, mVisHidCorrection, 1.0);
-    mVisBiasCorrection.AddColSum(-mLearningRate / N, neg_vis, mMomentum);
-    mVisBiasCorrection.AddColSum(+mLearningRate / N, pos_vis, 1.0);
-    mVisBias.AddScaled(1.0, mVisBiasCorrection, 1.0);
-    mHidBiasCorrection.AddColSum(-mLearningRate / N, neg_hid, mMomentum);
-    mHidBiasCorrection.AddColSum(+mLearningRate / N, pos_hid, 1.0);
-    mHidBias.AddScaled(1.0, mHidBiasCorrection, 1.0);
+    // weights and both biases through one fused entry point: the second statistics GEMM applies the weight-cost and the weight
+    // update in its epilogue, one kernel per bias does its column sums and updates (tnb_rbm_cd1_update has the formulas)
+    TNB_CHECK(tnb_rbm_cd1_update(Cx(), pos_vis.pCUData(), neg_vis.pCUData(), pos_vis.Dim(), pos_hid.pCUData(), neg_hid.pCUData(), pos_hid.Dim(),
+                                 mVisHid.pCUData(), mVisHid.Dim(), mVisHidCorrection.pCUData(), mVisBias.pCUData(), mVisBiasCorrection.pCUData(),
+                                 mHidBias.pCUData(), mHidBiasCorrection.pCUData(), mLearningRate, mMomentum, mWeightcost));
   }
   void ReadFromStream(std::istream &rIn) {
     std::string str;
