@@ -152,6 +152,16 @@ __global__ void __launch_bounds__(256) colsum_partial_batch_kernel(const __grid_
   const bool vec = ((stride & 3) == 0) && (((uintptr_t)mat & 15) == 0) && (c + 3 < cols);
   if (vec) {
     int r = r0 + ry;
+    for (; r + 24 < r1; r += 32) {  // four independent 16-byte loads in flight per thread
+      const float4 a = *(const float4 *)(mat + (size_t)r * stride + c);
+      const float4 bb = *(const float4 *)(mat + (size_t)(r + 8) * stride + c);
+      const float4 cc4 = *(const float4 *)(mat + (size_t)(r + 16) * stride + c);
+      const float4 dd = *(const float4 *)(mat + (size_t)(r + 24) * stride + c);
+      s0 += a.x; s1 += a.y; s2 += a.z; s3 += a.w;
+      t0 += bb.x; t1 += bb.y; t2 += bb.z; t3 += bb.w;
+      s0 += cc4.x; s1 += cc4.y; s2 += cc4.z; s3 += cc4.w;
+      t0 += dd.x; t1 += dd.y; t2 += dd.z; t3 += dd.w;
+    }
     for (; r + 8 < r1; r += 16) {
       const float4 a = *(const float4 *)(mat + (size_t)r * stride + c);
       const float4 bb = *(const float4 *)(mat + (size_t)(r + 8) * stride + c);
@@ -807,7 +817,7 @@ int tnb_bias_update_batch_on(TnbContext *ctx, int stream_id, const TnbBiasJob *j
     TNB_ARG(q.E && q.corrb, "null");
     TNB_ARG(q.dE.rows >= 0 && q.dE.cols >= 0 && q.dE.stride >= q.dE.cols, "dims");
     const int cb = (q.dE.cols + 127) / 128;
-    int S = (2 * ctx->sm_count + cb * n - 1) / (cb * n);  // ~2 CTAs per SM over the whole batch
+    int S = (6 * ctx->sm_count + cb * n - 1) / (cb * n);  // ~6 CTAs of 256 threads per SM over the whole batch (the kernel is latency-bound)
     if (S > (q.dE.rows + 31) / 32) S = (q.dE.rows + 31) / 32;
     if (S < 1) S = 1;
     float scale, l2;

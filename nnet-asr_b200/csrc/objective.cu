@@ -237,8 +237,10 @@ __global__ void __launch_bounds__(ROW_THREADS) row_softmax_xent_wide_kernel(cons
         e.x = y.x - tv[i].x; e.y = y.y - tv[i].y; e.z = y.z - tv[i].z; e.w = y.w - tv[i].w;
         if (Y) ((float4 *)(Y + (size_t)r * stride))[qd] = y;
         ((float4 *)(Err + (size_t)r * stride))[qd] = e;
-        xe += logf(y.x < FLT_MIN ? FLT_MIN : y.x) * tv[i].x; xe += logf(y.y < FLT_MIN ? FLT_MIN : y.y) * tv[i].y;
-        xe += logf(y.z < FLT_MIN ? FLT_MIN : y.z) * tv[i].z; xe += logf(y.w < FLT_MIN ? FLT_MIN : y.w) * tv[i].w;
+        if (T || (lab >> 2) == qd) {  // class ids: only the label's quad has a non-zero target (the others would add +-0)
+          xe += logf(y.x < FLT_MIN ? FLT_MIN : y.x) * tv[i].x; xe += logf(y.y < FLT_MIN ? FLT_MIN : y.y) * tv[i].y;
+          xe += logf(y.z < FLT_MIN ? FLT_MIN : y.z) * tv[i].z; xe += logf(y.w < FLT_MIN ? FLT_MIN : y.w) * tv[i].w;
+        }
         const int c = qd << 2;
         ay = am_merge(ay, am_make(y.x, c)); ay = am_merge(ay, am_make(y.y, c + 1));
         ay = am_merge(ay, am_make(y.z, c + 2)); ay = am_merge(ay, am_make(y.w, c + 3));
