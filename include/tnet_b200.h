@@ -402,7 +402,15 @@ typedef struct TnbPeerJob_ {
   int rows_pad;            /* multiple of the world size, >= dW.rows; rows beyond dW.rows are zero in G and W */
   float lr, mmt, wc;
   int grad_div_frm, n_frames; /* n_frames = frames of the GLOBAL bunch */
+  int pushed;              /* 1: the ranks' gradients were PUSHED into the owners' staging slices by tnb_affine_grad_scatter: G[rank] is
+                            * [world slices of rows_pad/world rows ; this rank's bias gradient row] and is summed from local memory */
 } TnbPeerJob;
+/* GEMM -> reduce-scatter in one kernel: the gradient GEMM of a data-parallel rank (cuBiasedLinearity.cc:55 without the update) whose
+ * epilogue stores row block o of dW = X^T E into slice `rank` of rank o's staging buffer Gpeers[o] (peer memory, as returned by
+ * tnb_peer_map for the ranks' gradient buffers: [(rows_pad + 1) x dG.stride] each), tile by tile while the MMAs of the next tile run
+ * on the other SMs.  X16 / E16: bf16 twins (TNB_MATH_BF16) or NULL.  Pair with TnbPeerJob.pushed = 1. */
+int tnb_affine_grad_scatter(TnbContext *ctx, const float *X, TnbMatrixDim dX, const float *E, TnbMatrixDim dE, const uint16_t *X16, int ldx16,
+                            const uint16_t *E16, int lde16, float *const *Gpeers, int world, int rank, TnbMatrixDim dG, int rows_pad);
 /* One layer's data-parallel update as ONE kernel on the communication stream, behind everything already on the compute stream and
  * behind `wait_event` (may be NULL): this rank sums its block of rows [rank*rows_pad/world, +rows_pad/world) of all ranks' gradients
  * through peer loads (rank order 0..world-1), applies CuBiasedLinearity::Update to that block of its corrW, and stores the updated

@@ -725,6 +725,27 @@ int tnb_affine_grad(TnbContext *ctx, const float *X, TnbMatrixDim dX, const floa
   return TNB_OK;
 }
 
+// The data-parallel gradient GEMM with the reduce-scatter fused into its epilogue: G = X^T E is not written to this rank's memory
+// but, row block by row block, straight into the staging slice the OWNING rank keeps for this rank (peer stores over NVLink, 128-byte
+// segments from the transposed epilogue tile).  The owner's update kernel (tnb_dp_peer_update with job.pushed = 1) then sums its
+// `world` slices from LOCAL memory.  Gpeers[o] = rank o's staging buffer [(world*shard + 1) x stride] as mapped into this process
+// (tnb_peer_map); shard = rows_pad / world.  X16 / E16: the bf16 twins in TNB_MATH_BF16 (NULL otherwise).
+int tnb_affine_grad_scatter(TnbContext *ctx, const float *X, TnbMatrixDim dX, const float *E, TnbMatrixDim dE, const uint16_t *X16, int ldx16,
+                            const uint16_t *E16, int lde16, float *const *Gpeers, int world, int rank, TnbMatrixDim dG, int rows_pad) {
+  TNB_ARG(ctx && X && E && Gpeers, "null");
+  TNB_ARG(world >= 1 && world <= TNB_MAX_PEERS && rank >= 0 && rank < world, "rank/world");
+  TNB_ARG(dX.rows == dE.rows && dG.rows == dX.cols && dG.cols == dE.cols, "dimension mismatch");
+  TNB_ARG(rows_pad >= dG.rows && rows_pad % world == 0, "rows_pad must be a multiple of the world size, at least dG.rows");
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  for (int r = 0; r < world; r++) { TNB_ARG(Gpeers[r] != nullptr && ((uintptr_t)Gpeers[r] & 15) == 0, "peer staging buffer"); ep.scat[r] = Gpeers[r]; }
+  ep.scat_shard = rows_pad / world; ep.scat_rank = rank;
+  ep.C = Gpeers[rank]; ep.ldc = dG.stride; ep.alpha = 1.0f; ep.beta = 0.0f;
+  if (ctx->math_mode == TNB_MATH_BF16 && X16 && E16)
+    return launch_gemm_bf16(ctx, 'T', 'N', dX.cols, dE.cols, dX.rows, X16, ldx16, E16, lde16, ep);
+  return launch_gemm(ctx, 'T', 'N', dX.cols, dE.cols, dX.rows, X, dX.stride, E, dE.stride, ep);
+}
+
 int tnb_affine_update(TnbContext *ctx, const float *X, TnbMatrixDim dX, const float *E, TnbMatrixDim dE, float *W, TnbMatrixDim dW,
                       float *bias, float *corrW, float *corrb, float lr, float mmt, float wc, int gdf, int n_frames_global) {
   TNB_ARG(ctx && X && E && W && corrW && ((bias && corrb) || (!bias && !corrb)), "null");

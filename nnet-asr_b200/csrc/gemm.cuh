@@ -15,6 +15,10 @@ struct EpiParams {
   float c_wdecay;               // generic epilogue only: out += c_wdecay * W_old before the store and the W update (CD-1: corr += -lr*wc*W)
   uint16_t *C16; int ldc16;     // optional bf16 copy of the stored output (TNB_MATH_BF16 shadows)
   uint16_t *W16; int ldw16;     // optional bf16 copy of the updated weights
+  // generic epilogue only (data-parallel gradient GEMM): row i of the output goes to scat[i / scat_shard], at row
+  // scat_rank * scat_shard + i % scat_shard — the block owner's staging slice for this rank (peer memory); scat_shard == 0: plain C
+  float *scat[TNB_MAX_PEERS];
+  int scat_shard, scat_rank;
   int mode;                     // EPI_*: which specialised epilogue the fused entry point asks for (EPI_GENERIC = any combination)
 };
 

@@ -565,9 +565,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int row = row0 + 4 * k;
             const float4 a4 = acc_at(k);
             if (row < M) {
-              const size_t crow = (size_t)row * (size_t)ep.ldc;
+              size_t crow = (size_t)row * (size_t)ep.ldc;
+              float *cbase = ep.C;
+              if (ep.scat_shard > 0) {  // data-parallel gradient: straight into the owning rank's staging slice (peer stores over NVLink)
+                const int own = row / ep.scat_shard;
+                cbase = ep.scat[own];
+                crow = (size_t)(ep.scat_rank * ep.scat_shard + (row - own * ep.scat_shard)) * (size_t)ep.ldc;
+              }
               float4 cold = make_float4(0, 0, 0, 0), yv = make_float4(0, 0, 0, 0);
-              if (ep.beta != 0.0f) cold = *(const float4 *)(ep.C + crow + n);
+              if (ep.beta != 0.0f) cold = *(const float4 *)(cbase + crow + n);
               if (ep.mulY) yv = *(const float4 *)(ep.mulY + (size_t)row * ep.ldy + n);
               float4 o;
               o.x = epi_one(ep, a4.x, cold.x, bv.x, yv.x);
@@ -583,7 +589,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 w = *wp;
                 if (ep.c_wdecay != 0.0f) { o.x = ep.c_wdecay * w.x + o.x; o.y = ep.c_wdecay * w.y + o.y; o.z = ep.c_wdecay * w.z + o.z; o.w = ep.c_wdecay * w.w + o.w; }
               }
-              *(float4 *)(ep.C + crow + n) = o;
+              *(float4 *)(cbase + crow + n) = o;
               if (ep.C16) st16(ep.C16, ep.ldc16, row, n, o);
               if (ep.W) {
                 w.x = ep.w_scale * o.x + w.x; w.y = ep.w_scale * o.y + w.y;
@@ -606,14 +612,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const float4 a4 = acc_at(k);
           if (row >= M) continue;
           const float acc[4] = {a4.x, a4.y, a4.z, a4.w};
-          const size_t crow = (size_t)row * (size_t)ep.ldc;
+          size_t crow = (size_t)row * (size_t)ep.ldc;
+          float *cbase = ep.C;
+          if (ep.scat_shard > 0) {
+            const int own = row / ep.scat_shard;
+            cbase = ep.scat[own];
+            crow = (size_t)(ep.scat_rank * ep.scat_shard + (row - own * ep.scat_shard)) * (size_t)ep.ldc;
+          }
           for (int t = 0; t < 4 && n + t < N; t++) {
-            float cold = (ep.beta != 0.0f) ? ep.C[crow + n + t] : 0.0f;
+            float cold = (ep.beta != 0.0f) ? cbase[crow + n + t] : 0.0f;
             float bs = ep.bias ? ep.bias[n + t] : 0.0f;
             float yv = ep.mulY ? ep.mulY[(size_t)row * ep.ldy + n + t] : 0.0f;
             float o = epi_one(ep, acc[t], cold, bs, yv);
             if (ep.W && ep.c_wdecay != 0.0f) o = ep.c_wdecay * ep.W[(size_t)row * ep.ldw + n + t] + o;
-            ep.C[crow + n + t] = o;
+            cbase[crow + n + t] = o;
             if (ep.C16) ep.C16[(size_t)row * ep.ldc16 + n + t] = __bfloat16_as_ushort(__float2bfloat16_rn(o));
             if (ep.W) {
               float *wp = ep.W + (size_t)row * ep.ldw + n + t;

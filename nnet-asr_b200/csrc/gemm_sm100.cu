@@ -70,12 +70,18 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float *__restrict_
       int n = n0 + tx * 4 + j;
       if (n >= N) continue;
       size_t ci = (size_t)row * ep.ldc + n;
-      float cold = (ep.beta != 0.0f) ? ep.C[ci] : 0.0f;
+      float *cb = ep.C;
+      if (ep.scat_shard > 0) {
+        const int own = row / ep.scat_shard;
+        cb = ep.scat[own];
+        ci = (size_t)(ep.scat_rank * ep.scat_shard + (row - own * ep.scat_shard)) * ep.ldc + n;
+      }
+      float cold = (ep.beta != 0.0f) ? cb[ci] : 0.0f;
       float bv = ep.bias ? ep.bias[n] : 0.0f;
       float yv = ep.mulY ? ep.mulY[(size_t)row * ep.ldy + n] : 0.0f;
       float o = epi_one(ep, acc[i][j], cold, bv, yv);
       if (ep.W && ep.c_wdecay != 0.0f) o = ep.c_wdecay * ep.W[(size_t)row * ep.ldw + n] + o;
-      ep.C[ci] = o;
+      cb[ci] = o;
       if (ep.W) {
         float *wp = ep.W + (size_t)row * ep.ldw + n;
         float w = ep.w_scale * o + *wp;

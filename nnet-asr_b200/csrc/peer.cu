@@ -39,6 +39,7 @@ struct PeerArgs {
   float *corr, *bias, *corrb;      // local
   int cols, stride, shard, rows_pad;
   float mmt, scale, l2;
+  int pushed;        // the gradients were pushed into the owners' staging slices (tnb_affine_grad_scatter): G[rank] holds `world` local slices
   unsigned seq;
   long long timeout;  // cycles; 0 = wait for ever
 };
@@ -99,7 +100,8 @@ __device__ __forceinline__ void peer_update_body(const PeerArgs &a, const int bi
 #pragma unroll
       for (int u = 0; u < U; u++) {
 #pragma unroll
-        for (int r = 0; r < WORLD; r++) g[u][r] = ldg_f4(a.G[r] + base[u]);
+        for (int r = 0; r < WORLD; r++)  // pushed: slice r of this rank's own staging buffer (local HBM); else rank r's buffer (NVLink)
+          g[u][r] = a.pushed ? ldg_f4(a.G[a.rank] + (base[u] - row0 * a.stride) + (size_t)r * a.shard * a.stride) : ldg_f4(a.G[r] + base[u]);
         k[u] = ldg_f4(a.corr + base[u]);
         w[u] = ldg_f4(a.W[a.rank] + base[u]);
       }
@@ -122,8 +124,9 @@ __device__ __forceinline__ void peer_update_body(const PeerArgs &a, const int bi
     const long total_s = (long)a.shard * a.cols;
     for (long i = (long)bid * blockDim.x + threadIdx.x; i < total_s; i += step) {
       const size_t base = (row0 + (size_t)(i / a.cols)) * a.stride + (size_t)(i % a.cols);
-      float s = a.G[0][base];
-      for (int r = 1; r < world; r++) s += a.G[r][base];
+      const size_t lbase = base - row0 * a.stride;  // position inside a staging slice
+      float s = a.pushed ? a.G[a.rank][lbase] : a.G[0][base];
+      for (int r = 1; r < world; r++) s += a.pushed ? a.G[a.rank][lbase + (size_t)r * a.shard * a.stride] : a.G[r][base];
       const float kk = s + a.mmt * a.corr[base];
       float ww = a.scale * kk + a.W[a.rank][base];
       if (a.l2 != 0.0f) ww = a.l2 * ww + ww;
@@ -209,6 +212,7 @@ static int fill_peer_args(const TnbPeerJob *job, int rank, int world, unsigned *
   a.corr = job->corrW; a.bias = job->bias; a.corrb = job->corrb;
   a.cols = d.cols; a.stride = d.stride; a.rows_pad = job->rows_pad; a.shard = job->rows_pad / world;
   a.mmt = job->mmt;
+  a.pushed = job->pushed ? 1 : 0;
   update_scalars(job->lr, job->mmt, job->wc, job->grad_div_frm, job->n_frames, &a.scale, &a.l2);
   a.seq = seq;
   a.timeout = peer_timeout_cycles();

@@ -307,8 +307,21 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     TnbBiasJob bj = {E.pCUData(), E.Dim(), NULL, mGrad.pCURowData(mRowsPad), 0.0f, 0.0f, 0, 0};  // gradient only
     TNB_CHECK(tnb_bias_update_batch_on(Cx(), TNB_STREAM_AUX, &bj, 1));
     TNB_CHECK(tnb_event_record(Cx(), mEvB, TNB_STREAM_AUX));
-    ComputeGradient(false);
+    if (mPeerMapped && DpPush()) {
+      // GEMM -> reduce-scatter in one kernel: the tiles of dW go straight to the owning ranks' staging slices over NVLink
+      const CuMatrix<BaseFloat> &X = GetInput();
+      int rank = 0, world = 1;
+      TNB_CHECK(tnb_comm_world(Cx(), &rank, &world));
+      const bool bf = Bf16();
+      const uint16_t *x16 = bf ? X.Twin() : NULL, *e16 = bf ? E.Twin() : NULL;
+      TNB_CHECK(tnb_affine_grad_scatter(Cx(), X.pCUData(), X.Dim(), E.pCUData(), E.Dim(), x16, bf ? X.TwinStride() : 0, e16, bf ? E.TwinStride() : 0,
+                                        (float *const *)mGradPeers, world, rank, mLinearity.Dim(), (int)mRowsPad));
+    } else {
+      ComputeGradient(false);
+    }
   }
+  /// TNB_DP_PUSH=0: the owner pulls the ranks' gradient blocks with peer loads instead (the round-1 schedule)
+  static bool DpPush() { static int v = -1; if (v < 0) { const char *e = getenv("TNB_DP_PUSH"); v = (e && atoi(e) == 0) ? 0 : 1; } return v != 0; }
   /// second half: the all-reduce of [dW ; db] on the communication stream behind both, the update on a second side stream behind
   /// the all-reduce.  Nothing waits for it here: whoever touches the parameters next does (WaitDataParallel), which lets the
   /// exchange of this bunch run into the forward pass of the next one.
@@ -343,6 +356,7 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     j.corrW = mLinearityCorrection.pCUData(); j.bias = mBias.pCUData(); j.corrb = mBiasCorrection.pCUData();
     j.dW = mLinearity.Dim(); j.rows_pad = (int)mRowsPad;
     j.lr = mLearningRate; j.mmt = mMomentum; j.wc = mWeightcost; j.grad_div_frm = mGradDivFrm ? 1 : 0; j.n_frames = n_frames_global;
+    j.pushed = DpPush() ? 1 : 0;
     TNB_CHECK(tnb_dp_peer_update(Cx(), &j, mEvB, mEvDone));
     mDpPending = true;
   }

@@ -33,7 +33,7 @@ class PeerJob(C.Structure):
     """TnbPeerJob of include/tnet_b200.h (one layer's update over peer memory)."""
     _fields_ = [("G", C.c_void_p * MAX_PEERS), ("W", C.c_void_p * MAX_PEERS), ("corrW", C.c_void_p), ("bias", C.c_void_p),
                 ("corrb", C.c_void_p), ("dW", MatrixDim), ("rows_pad", C.c_int), ("lr", C.c_float), ("mmt", C.c_float),
-                ("wc", C.c_float), ("grad_div_frm", C.c_int), ("n_frames", C.c_int)]
+                ("wc", C.c_float), ("grad_div_frm", C.c_int), ("n_frames", C.c_int), ("pushed", C.c_int)]
 
 
 EPI_STORE, EPI_FWD, EPI_DX, EPI_UPDATE = 0, 1, 2, 3

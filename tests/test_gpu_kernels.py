@@ -414,6 +414,70 @@ def test_peer_update_kernel_virtual_ranks(ctx, world, rows, cols):
             m.free()
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("math", ["3xtf32", "bf16"])
+def test_gradient_gemm_with_fused_reduce_scatter_virtual_ranks(ctx, world, math):
+    """GEMM -> reduce-scatter -> update -> all-gather on ONE GPU with virtual ranks: every rank's gradient GEMM (tnb_affine_grad_scatter)
+    stores row block o of X_r^T E_r into slice r of rank o's staging buffer, then ONE cooperative grid runs all ranks' update kernels
+    with job.pushed = 1 (local sums of the slices, CuBiasedLinearity::Update on the owned rows, rows stored into every rank's weights).
+    Every rank must end with the weights of a single-GPU update on the concatenated bunch (oracle GEMM on the same operands)."""
+    r = rng(300 + world)
+    bf = math == "bf16"
+    ctx.set_math(abi.MATH_BF16 if bf else abi.MATH_3XTF32)
+    rows, nin, nout = 96, 300, 260                      # per-rank frames; nin not a multiple of the world size -> padded rows
+    rows_pad = ((nin + world - 1) // world) * world
+    lr, mmt, wc, frames = 0.3, 0.5, 1e-3, rows * world
+    scale, l2 = _update_scalars(lr, mmt, wc, 1, frames)
+    q = abi.bf16_round if bf else (lambda a: a)
+    W0 = np.zeros((rows_pad, nout), np.float32)
+    W0[:nin] = 0.1 * r.standard_normal((nin, nout))
+    try:
+        Xs = [r.standard_normal((rows, nin)).astype(np.float32) for _ in range(world)]
+        Es = [(0.1 * r.standard_normal((rows, nout))).astype(np.float32) for _ in range(world)]
+        Wd = [abi.DMat.from_numpy(ctx, W0) for _ in range(world)]
+        Kd = [abi.DMat(ctx, rows_pad, nout) for _ in range(world)]
+        Gd = [abi.DMat(ctx, rows_pad + 1, nout) for _ in range(world)]
+        flags = [abi.DMat(ctx, 1, 64, np.uint32) for _ in range(world)]
+        fl = (C.POINTER(C.c_uint) * world)(*[f.p(C.c_uint) for f in flags])
+        gp = (C.POINTER(C.c_float) * world)(*[g.p() for g in Gd])
+        for k in range(world):
+            dX, dE = abi.DMat.from_numpy(ctx, Xs[k]), abi.DMat.from_numpy(ctx, Es[k])
+            x16 = e16 = None
+            lx = le = 0
+            if bf:
+                X16, E16 = abi.DMat16.from_fp32(ctx, dX), abi.DMat16.from_fp32(ctx, dE)
+                x16, e16, lx, le = X16.p(), E16.p(), X16.stride, E16.stride
+            abi.check(L.tnb_affine_grad_scatter(ctx.h, dX.p(), dX.dim, dE.p(), dE.dim, x16, C.c_int(lx), e16, C.c_int(le), gp, C.c_int(world),
+                                                C.c_int(k), abi.MatrixDim(nin, nout, Wd[k].stride), C.c_int(rows_pad)))
+        ctx.sync()
+        jobs = (abi.PeerJob * world)()
+        for k in range(world):
+            for p_ in range(world):
+                jobs[k].G[p_] = Gd[p_].ptr.value
+                jobs[k].W[p_] = Wd[p_].ptr.value
+            jobs[k].corrW = Kd[k].ptr.value
+            jobs[k].dW = abi.MatrixDim(nin, nout, Wd[k].stride)
+            jobs[k].rows_pad, jobs[k].lr, jobs[k].mmt, jobs[k].wc, jobs[k].grad_div_frm, jobs[k].n_frames = rows_pad, lr, mmt, wc, 1, frames
+            jobs[k].pushed = 1
+        abi.check(L.tnb_dp_peer_update_virtual(ctx.h, jobs, C.c_int(world), fl, C.c_uint(1), C.c_int(0)))
+        ctx.sync()
+        g = np.zeros((nin, nout), np.float64)
+        scale_abs = np.zeros((nin, nout), np.float64)
+        for k in range(world):
+            g += O.gemm("T", "N", 1.0, q(Xs[k]), q(Es[k]), 0.0, np.zeros((nin, nout), np.float32), acc_double=1).astype(np.float64)
+            scale_abs += np.abs(q(Xs[k])).T.astype(np.float64) @ np.abs(q(Es[k])).astype(np.float64)
+        Wref = W0[:nin].astype(np.float64) + float(scale) * g
+        Wref = Wref + float(l2) * Wref
+        got = [w.download() for w in Wd]
+        for k in range(1, world):
+            assert np.array_equal(got[k], got[0]), "ranks hold different weights"
+        err = np.abs(got[0][:nin].astype(np.float64) - Wref) / (abs(float(scale)) * scale_abs * tol3x(rows) + 1e-7)
+        assert err.max() < 1.0, err.max()
+        assert not got[0][nin:].any()
+    finally:
+        ctx.set_math(abi.MATH_3XTF32)
+
+
 def test_peer_update_timeout_is_reported_not_fatal(ctx):
     """A rank whose peer never shows up (here: rank 0 of a 2-rank exchange launched alone) must give up after TNB_PEER_TIMEOUT_MS,
     leave the weights untouched, say which rank it waited for — and leave the CUDA context usable (no __trap)."""

@@ -1,0 +1,14 @@
+#!/usr/bin/env bash
+set -u
+export MASTER_ADDR=127.0.0.1
+N=${1:-8}
+mkdir -p gpurun_out/r02
+O=gpurun_out/r02
+run() { name=$1; shift
+  env "$@" timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29590 bench.py --gpus $N --steps 50 --warmup 5 --windows 3 --no-extras > $O/bench_n${N}_$name.json 2> $O/bench_n${N}_$name.err
+  python -c "import json;d=json.load(open('$O/bench_n${N}_$name.json'));print('N=$N $name value %.0f ms %.4f e2e %.0f'%(d['value'],d['ms_per_step'],d['e2e']['value']))" || tail -3 $O/bench_n${N}_$name.err
+}
+run push1 TNB_DP_PUSH=1
+run push0 TNB_DP_PUSH=0
+run push1_c32 TNB_DP_PUSH=1 TNB_DP_PEER_CTAS=32
+run push1_c12 TNB_DP_PUSH=1 TNB_DP_PEER_CTAS=12
