@@ -153,6 +153,49 @@ def test_trecurrentcu_binary_reproduces_reference():
     np.testing.assert_allclose(LF[0][1], g["final_Wr"], rtol=3e-4, atol=3e-4 * np.abs(g["final_Wr"]).max())
 
 
+REF_BIN = os.path.join(ROOT, "oracle", "_ref")
+
+
+def test_config_d_full_size_dropin_vs_live_reference_trbmcu():
+    """BASELINE configs[3] at FULL size — Gaussian-Bernoulli RBM 429 (39 x 11 spliced) x 2048, bunch 128, lr 0.001 / momentum 0.5 /
+    weightcost 2e-4 — bin/TRbmCu against the UNMODIFIED reference TRbmCu (oracle/_ref, built by oracle/build_ref.sh) run on the same
+    files on this GPU: same frames, reconstruction error and final weights (the Hybrid-Taus streams are bit-identical, so both
+    binaries sample the same hidden states up to probabilities that fall within a rounding error of the uniform draw)."""
+    ref = os.path.join(REF_BIN, "TRbmCu")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/TRbmCu is not built")
+    cfg = dict(raw_dim=39, ctx=5, nhid=2048, vistype="gauss", hidtype="bern", n_utt=16, n_frames=300, bunch=128, cache=2048,
+               lr=0.001, mmt=0.5, wc=2e-4, seed=41)
+    res = []
+    for exe in (ref, os.path.join(BIN, "TRbmCu")):
+        with tempfile.TemporaryDirectory() as d:
+            res.append(MG.run_rbm("config_d", cfg, d, exe=exe, save=False))
+    (r_ref, L_ref, _), (r_our, L_our, _) = res
+    assert r_ref["frames"] == r_our["frames"] and r_our["frames"] >= 25 * 128
+    assert abs(r_our["err"] - r_ref["err"]) <= 2e-4 * abs(r_ref["err"])
+    np.testing.assert_allclose(L_our[3], L_ref[3], rtol=2e-4, atol=2e-4 * np.abs(L_ref[3]).max())     # weights
+    np.testing.assert_allclose(L_our[5], L_ref[5], rtol=2e-4, atol=2e-4 * max(1e-2, np.abs(L_ref[5]).max()))   # hidden bias
+
+
+def test_config_e_full_size_dropin_vs_live_reference_trecurrentcu():
+    """BASELINE configs[4] at FULL size — recurrent layer 351 (39 x 9) + 1024 -> 1024, BPTT 20, 135-way softmax — bin/TRecurrentCu
+    against the unmodified reference TRecurrentCu on the same files on this GPU (tolerances of the small golden)."""
+    ref = os.path.join(REF_BIN, "TRecurrentCu")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/TRecurrentCu is not built")
+    cfg = dict(raw_dim=39, ctx=4, nhid=1024, n_out=135, n_utt=2, n_frames=120, bptt=20, lr=0.01, seed=43)
+    res = []
+    for exe in (ref, os.path.join(BIN, "TRecurrentCu")):
+        with tempfile.TemporaryDirectory() as d:
+            res.append(MG.run_rnn("config_e", cfg, d, exe=exe, save=False))
+    (r_ref, L_ref, _), (r_our, L_our, _) = res
+    assert r_ref["frames"] == r_our["frames"]
+    assert abs(r_our["err"] - r_ref["err"]) <= 2e-4 * abs(r_ref["err"])
+    assert abs(r_our["correct_pct"] - r_ref["correct_pct"]) <= 0.5
+    np.testing.assert_allclose(L_our[0][1], L_ref[0][1], rtol=3e-4, atol=3e-4 * np.abs(L_ref[0][1]).max())   # recurrent weights
+    np.testing.assert_allclose(L_our[1][1], L_ref[1][1], rtol=3e-4, atol=3e-4 * np.abs(L_ref[1][1]).max())   # output layer
+
+
 @pytest.mark.parametrize("case", ["feacat_post", "feacat_logpost"])
 def test_tfeacatcu_binary_reproduces_reference(case):
     """bin/TFeaCatCu with the reference's command line on the files the golden was produced from == the features the unmodified

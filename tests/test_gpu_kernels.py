@@ -478,6 +478,103 @@ def test_gradient_gemm_with_fused_reduce_scatter_virtual_ranks(ctx, world, math)
         ctx.set_math(abi.MATH_3XTF32)
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_whole_data_parallel_step_with_virtual_ranks_equals_single_rank_step(ctx, world):
+    """N-rank equivalence on ONE GPU: a whole training step of a 429-512-384-300 network (three <biasedlinearity> layers, sigmoid /
+    sigmoid / softmax) run as `world` virtual ranks — every rank forward, objective (class ids) and backward on its rows
+    [g*B/N, (g+1)*B/N) of the bunch, gradient GEMMs with the fused reduce-scatter into the owners' staging slices, bias gradients,
+    then per layer ONE cooperative grid playing all ranks' peer-memory update kernels — against the single-rank step on the whole
+    bunch (fused update GEMMs).  Every rank must hold the single-rank step's weights and biases (summation-order tolerance) and the
+    ranks' cross-entropy / accuracy counters must add up to the single rank's."""
+    r = rng(500 + world)
+    dims, B = [429, 512, 384, 300], 256
+    lr, mmt, wc = 0.2, 0.5, 1e-4
+    ctx.set_math(abi.MATH_3XTF32)
+    Ws = [(0.1 * r.standard_normal((dims[i], dims[i + 1]))).astype(np.float32) for i in range(3)]
+    bs = [(0.1 * r.standard_normal(dims[i + 1])).astype(np.float32) for i in range(3)]
+    X = r.standard_normal((B, dims[0])).astype(np.float32)
+    lab = r.integers(0, dims[-1], B).astype(np.int32)
+    none = abi.MatrixDim(0, 0, 0)
+
+    def fwd_bwd(Xd, labd, W, b, rows):
+        """forward + objective + dX chain of one rank; returns activations and errors per layer (inputs of the gradient GEMMs)"""
+        acts, errs = [Xd], [None] * 3
+        for i in range(3):
+            Y = abi.DMat(ctx, rows, dims[i + 1])
+            abi.check(L.tnb_affine_fwd(ctx.h, acts[i].p(), acts[i].dim, W[i].p(), W[i].dim, b[i].p(), Y.p(), Y.dim,
+                                       C.c_int(abi.ACT_SIGMOID if i < 2 else abi.ACT_NONE)))
+            acts.append(Y)
+        Ysm, E = abi.DMat(ctx, rows, dims[3]), abi.DMat(ctx, rows, dims[3])
+        st = abi.DStats(ctx)
+        abi.check(L.tnb_softmax_xent_labels(ctx.h, acts[3].p(), labd.p(C.c_int), C.c_int(1), Ysm.p(), E.p(), E.dim, st.p()))
+        errs[2] = E
+        for i in (2, 1):
+            Ep = abi.DMat(ctx, rows, dims[i])
+            abi.check(L.tnb_affine_bwd_dx(ctx.h, errs[i].p(), errs[i].dim, W[i].p(), W[i].dim, acts[i].p(), acts[i].dim, Ep.p(), Ep.dim))
+            errs[i - 1] = Ep
+        return acts, errs, st
+
+    # ---- single rank, whole bunch, fused update GEMMs
+    W1 = [abi.DMat.from_numpy(ctx, w) for w in Ws]
+    b1 = [abi.DMat.from_numpy(ctx, v) for v in bs]
+    K1 = [abi.DMat(ctx, dims[i], dims[i + 1]) for i in range(3)]
+    kb1 = [abi.DMat(ctx, 1, dims[i + 1]) for i in range(3)]
+    acts, errs, st1 = fwd_bwd(abi.DMat.from_numpy(ctx, X), abi.DMat.from_numpy(ctx, lab.reshape(1, -1)), W1, b1, B)
+    for i in range(3):
+        abi.check(L.tnb_affine_update(ctx.h, acts[i].p(), acts[i].dim, errs[i].p(), errs[i].dim, W1[i].p(), W1[i].dim, b1[i].p(), K1[i].p(),
+                                      kb1[i].p(), C.c_float(lr), C.c_float(mmt), C.c_float(wc), C.c_int(1), C.c_int(0)))
+    ctx.sync()
+    ref_stats = st1.read()
+    # ---- `world` virtual ranks
+    rows = B // world
+    pads = [((dims[i] + world - 1) // world) * world for i in range(3)]
+    Wr = [[abi.DMat.from_numpy(ctx, np.vstack([Ws[i], np.zeros((pads[i] - dims[i], dims[i + 1]), np.float32)])) for i in range(3)] for _ in range(world)]
+    br = [[abi.DMat.from_numpy(ctx, v) for v in bs] for _ in range(world)]
+    Kr = [[abi.DMat(ctx, pads[i], dims[i + 1]) for i in range(3)] for _ in range(world)]
+    kbr = [[abi.DMat(ctx, 1, dims[i + 1]) for i in range(3)] for _ in range(world)]
+    Gr = [[abi.DMat(ctx, pads[i] + 1, dims[i + 1]) for i in range(3)] for _ in range(world)]
+    flags = [abi.DMat(ctx, 1, 64, np.uint32) for _ in range(world)]
+    fl = (C.POINTER(C.c_uint) * world)(*[f.p(C.c_uint) for f in flags])
+    tot = [0.0, 0, 0]
+    for g in range(world):
+        Xg = abi.DMat.from_numpy(ctx, X[g * rows:(g + 1) * rows])
+        lg = abi.DMat.from_numpy(ctx, lab[g * rows:(g + 1) * rows].reshape(1, -1))
+        Wg = [abi.DMat.from_numpy(ctx, Ws[i]) for i in range(3)]           # forward / dX read the logical [nin x nout] weights
+        acts, errs, stg = fwd_bwd(Xg, lg, Wg, br[g], rows)
+        for i in range(3):
+            gp = (C.POINTER(C.c_float) * world)(*[Gr[q][i].p() for q in range(world)])
+            abi.check(L.tnb_affine_grad_scatter(ctx.h, acts[i].p(), acts[i].dim, errs[i].p(), errs[i].dim, None, C.c_int(0), None, C.c_int(0), gp,
+                                                C.c_int(world), C.c_int(g), abi.MatrixDim(dims[i], dims[i + 1], Wr[g][i].stride), C.c_int(pads[i])))
+            brow = C.cast(C.c_void_p(Gr[g][i].ptr.value + 4 * pads[i] * Gr[g][i].stride), C.POINTER(C.c_float))
+            abi.check(L.tnb_add_col_sum(ctx.h, C.c_float(1.0), errs[i].p(), C.c_float(0.0), brow, errs[i].dim))
+        ctx.sync()
+        e, f, c = stg.read()
+        tot[0] += e; tot[1] += f; tot[2] += c
+    for i in range(3):
+        jobs = (abi.PeerJob * world)()
+        for g in range(world):
+            for q in range(world):
+                jobs[g].G[q] = Gr[q][i].ptr.value
+                jobs[g].W[q] = Wr[q][i].ptr.value
+            jobs[g].corrW, jobs[g].bias, jobs[g].corrb = Kr[g][i].ptr.value, br[g][i].ptr.value, kbr[g][i].ptr.value
+            jobs[g].dW = abi.MatrixDim(dims[i], dims[i + 1], Wr[g][i].stride)
+            jobs[g].rows_pad, jobs[g].lr, jobs[g].mmt, jobs[g].wc, jobs[g].grad_div_frm, jobs[g].n_frames = pads[i], lr, mmt, wc, 1, B
+            jobs[g].pushed = 1
+        abi.check(L.tnb_dp_peer_update_virtual(ctx.h, jobs, C.c_int(world), fl, C.c_uint(i + 1), C.c_int(0)))
+    ctx.sync()
+    assert tot[1] == ref_stats[1] == B and tot[2] == ref_stats[2]
+    assert abs(tot[0] - ref_stats[0]) <= 1e-5 * abs(ref_stats[0])
+    for i in range(3):
+        w_ref, b_ref = W1[i].download(), b1[i].download()[0]
+        moved = np.abs(w_ref - Ws[i]).max()
+        for g in range(world):
+            w = Wr[g][i].download()
+            np.testing.assert_allclose(w[:dims[i]] - Ws[i], w_ref - Ws[i], rtol=1e-4, atol=2e-5 * moved + 2 * np.spacing(np.abs(w_ref).max()),
+                                       err_msg="layer %d rank %d" % (i, g))
+            assert not w[dims[i]:].any()
+            np.testing.assert_allclose(br[g][i].download()[0], b_ref, rtol=1e-5, atol=1e-6)
+
+
 def test_peer_update_timeout_is_reported_not_fatal(ctx):
     """A rank whose peer never shows up (here: rank 0 of a 2-rank exchange launched alone) must give up after TNB_PEER_TIMEOUT_MS,
     leave the weights untouched, say which rank it waited for — and leave the CUDA context usable (no __trap)."""
