@@ -517,6 +517,28 @@ def main():
     win_ms, launches, first = timed_windows(net, bunch, args.windows)
     clocks = sampler.stop() if rank == 0 else {}
     ms = median(win_ms)
+    if world > 1 and os.environ.get("TNB_DP_TRACE"):
+        # debugging: %globaltimer stamps of the last peer-memory update kernels of this rank (csrc/peer.cu), one line per launch
+        buf, seq = (C.c_longlong * 384)(), (C.c_uint * 2)()
+        if L.tnb_peer_trace_read(ctx, buf, seq) == 0:
+            n_upd = len(DIMS) - 1
+            ev = []
+            for s_ in range(seq[0] - 3 * n_upd + 1, seq[0] + 1):
+                r_ = [buf[(s_ % 64) * 4 + k] for k in range(4)]
+                ev.append((r_[0], "kernel entry | wait ready %6.1f | own rows %6.1f | wait done %6.1f | exit %10.1f", r_))
+            for s_ in range(max(0, seq[1] - 3 * n_upd), seq[1]):
+                r_ = [buf[256 + (s_ % 64) * 2 + k] for k in range(2)]
+                ev.append((r_[0], "push start   | copies %6.1f", r_))
+            ev.sort(key=lambda e_: e_[0])
+            t0 = ev[0][0]
+            txt = ["[dp trace] rank %d: peer-memory kernels and copy-engine pushes of the last 3 bunches, us" % rank]
+            for t_, fmt, r_ in ev:
+                if len(r_) == 4:
+                    line = fmt % ((r_[1] - r_[0]) / 1e3, (r_[2] - r_[1]) / 1e3, (r_[3] - r_[2]) / 1e3, (r_[3] - t0) / 1e3)
+                else:
+                    line = fmt % ((r_[1] - r_[0]) / 1e3)
+                txt.append("[dp trace] r%d %9.1f %s" % (rank, (t_ - t0) / 1e3, line))
+            sys.stderr.write("\n".join(txt) + "\n")
     gms, gl, gfl = gemm_pass(net, bunch, first)
     frames = args.steps * bunch * world
     value = frames / (ms / 1000.0)

@@ -418,6 +418,15 @@ int tnb_affine_grad_scatter(TnbContext *ctx, const float *X, TnbMatrixDim dX, co
  * peer memory at the start (all gradients complete, nobody reads W any more) and at the end (all blocks of this rank's W written)
  * of the kernel; `done_event` (may be NULL) is recorded behind it.  With one rank it is tnb_sgd_update on the compute stream. */
 int tnb_dp_peer_update(TnbContext *ctx, const TnbPeerJob *job, void *wait_event, void *done_event);
+/* The same kernel on the communication stream behind the given events only (nothing is recorded on the compute stream, so that
+ * consecutive GEMMs there keep their programmatic-dependent-launch overlap); several ranks only. */
+int tnb_dp_peer_update_after(TnbContext *ctx, const TnbPeerJob *job, void *const *wait_events, int n_wait, void *done_event);
+/* Gradient push by the copy engines instead of by the GEMM epilogue: block o (rows [o*rows_pad/world, (o+1)*rows_pad/world)) of
+ * this rank's full gradient G [rows_pad x dG.stride] goes to slice `rank` of rank o's staging buffer Gpeers[o] (tnb_peer_map of the
+ * ranks' [(rows_pad + 1) x dG.stride] buffers), as `world` device-to-device copies on stream `stream_id` behind `wait_event`;
+ * `done_event` is recorded behind them.  No SM is involved and the gradient GEMM's epilogue stores stay local. */
+int tnb_peer_push_blocks(TnbContext *ctx, int stream_id, const float *G, float *const *Gpeers, int world, int rank, TnbMatrixDim dG,
+                         int rows_pad, void *wait_event, void *done_event);
 /* the same kernel for an explicit rank / world / flag blocks (64 zero-initialised words per rank) / sequence number (1, 2, ... per
  * launch) on a given stream of the context: lets a test play several ranks on one GPU */
 int tnb_dp_peer_update_on(TnbContext *ctx, int stream_id, const TnbPeerJob *job, int rank, int world, unsigned *const *flags, unsigned seq);
@@ -430,6 +439,10 @@ int tnb_dp_peer_update_virtual(TnbContext *ctx, const TnbPeerJob *jobs, int worl
  * that exceeds TNB_PEER_TIMEOUT_MS ends the kernel without touching the weights and without poisoning the CUDA context; 0 = no
  * limit).  Synchronises nothing itself: call it after tnb_ctx_sync / an event wait.  tnb_ctx_sync calls it. */
 int tnb_peer_status(TnbContext *ctx);
+/* Debugging (TNB_DP_TRACE=1): %globaltimer stamps (ns).  out[0..255]: this context's last 64 peer-memory kernels, slot = sequence
+ * number % 64: {entry, all ranks ready, CTA 0's rows done, all ranks done}; out[256..383]: the last 64 tnb_peer_push_blocks calls,
+ * slot = call counter % 64: {copies start, copies done}; seq[0] = sequence number of the latest kernel, seq[1] = number of push calls. */
+int tnb_peer_trace_read(TnbContext *ctx, long long *out /* [384] */, unsigned *seq /* [2] */);
 
 #ifdef __cplusplus
 }

@@ -95,6 +95,9 @@ struct TnbContext_ {
   // bf16 copies of fp32 GEMM operands for the generic entry points in TNB_MATH_BF16 (slot 0 = A, 1 = B)
   uint16_t *bf16_scratch[2] = {nullptr, nullptr};
   size_t bf16_cap[2] = {0, 0};
+  // split-K GEMMs: accumulator exchange buffers, one per stream that has launched one (gemm_kernel.cuh)
+  struct Xchg { cudaStream_t stream; float *ptr; size_t cap; };
+  std::vector<Xchg> xchg;
   // GEMM profiling (tnb_ctx_profile_begin/end)
   bool profiling = false;
   bool pdl = true;  // programmatic dependent launch between consecutive GEMMs (TNB_PDL=0 disables)
@@ -108,6 +111,8 @@ struct TnbContext_ {
   // peer-memory schedule (peer.cu): every rank's flag block as mapped into this process, and the launch counter
   unsigned *peer_flags[TNB_MAX_PEERS] = {};
   unsigned peer_seq = 0;
+  unsigned push_seq = 0;   // tnb_peer_push_blocks calls (trace slots)
+  void *peer_trace = nullptr;   // TNB_DP_TRACE=1: %globaltimer stamps of the last 64 peer-memory kernels (tnb_peer_trace_read)
 };
 
 namespace tnb {

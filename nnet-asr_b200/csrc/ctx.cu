@@ -136,6 +136,25 @@ int bf16_scratch(TnbContext *ctx, int slot, const float *src, int rows, int cols
   return launch_to_bf16(ctx, *out, st, src, rows, cols, stride);
 }
 
+int xchg_buffer(TnbContext *ctx, cudaStream_t stream, size_t bytes, float **out) {
+  *out = nullptr;
+  static int use_dsmem = -1;
+  if (use_dsmem < 0) { const char *e = getenv("TNB_GEMM_XCHG"); use_dsmem = (e && !strcmp(e, "dsmem")) ? 1 : 0; }
+  if (use_dsmem) return TNB_OK;
+  TnbContext::Xchg *x = nullptr;
+  for (auto &e : ctx->xchg) if (e.stream == stream) x = &e;
+  if (!x) { ctx->xchg.push_back(TnbContext::Xchg{stream, nullptr, 0}); x = &ctx->xchg.back(); }
+  if (bytes > x->cap) {
+    if (ctx->capturing) return TNB_OK;  // no allocation inside a stream capture: this launch exchanges through DSMEM
+    if (x->ptr) { TNB_CUDA(cudaStreamSynchronize(stream)); cudaFree(x->ptr); x->ptr = nullptr; x->cap = 0; }
+    const size_t want = bytes < ((size_t)10 << 20) ? ((size_t)10 << 20) : bytes;  // 148 CTAs x 64 KB fit the first allocation
+    TNB_CUDA(cudaMalloc(&x->ptr, want));
+    x->cap = want;
+  }
+  *out = x->ptr;
+  return TNB_OK;
+}
+
 }  // namespace tnb
 
 using namespace tnb;
@@ -209,6 +228,7 @@ int tnb_ctx_destroy(TnbContext *ctx) {
   if (ctx->row_match) cudaFree(ctx->row_match);
   if (ctx->vec_scratch) cudaFree(ctx->vec_scratch);
   for (int i = 0; i < 2; i++) if (ctx->bf16_scratch[i]) cudaFree(ctx->bf16_scratch[i]);
+  for (auto &e : ctx->xchg) if (e.ptr) cudaFree(e.ptr);
   for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_compute);
   cudaEventDestroy(ctx->ev_comm);
@@ -220,6 +240,7 @@ int tnb_ctx_destroy(TnbContext *ctx) {
   if (ctx->vec_scratch_side) cudaFree(ctx->vec_scratch_side);
   for (auto &kv : ctx->mg_plans) if (kv.second.dlist) cudaFree(kv.second.dlist);
   if (ctx->mg_trace) cudaFree(ctx->mg_trace);
+  if (ctx->peer_trace) cudaFree(ctx->peer_trace);
   delete ctx;
   return TNB_OK;
 }

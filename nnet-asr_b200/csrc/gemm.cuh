@@ -19,6 +19,7 @@ struct EpiParams {
   // scat_rank * scat_shard + i % scat_shard — the block owner's staging slice for this rank (peer memory); scat_shard == 0: plain C
   float *scat[TNB_MAX_PEERS];
   int scat_shard, scat_rank;
+  float *xchg;                  // split-K kernels: L2 exchange buffer of the launch (set by the launcher; NULL = exchange through DSMEM)
   int mode;                     // EPI_*: which specialised epilogue the fused entry point asks for (EPI_GENERIC = any combination)
 };
 
@@ -71,6 +72,9 @@ int launch_gemm_bf16(TnbContext *ctx, char transa, char transb, int M, int N, in
                      const uint16_t *B, int ldb, const EpiParams &ep);
 // A16 = bf16_rn(A) for a [rows x cols] fp32 matrix (elementwise.cu)
 int launch_to_bf16(TnbContext *ctx, uint16_t *dst, int dst_stride, const float *src, int rows, int cols, int src_stride);
+// split-K accumulator exchange buffer of the stream the launch goes to (ctx-owned, grown on demand; *out = NULL when it cannot be
+// provided — inside a graph capture before the first allocation — and the kernel then exchanges through DSMEM)
+int xchg_buffer(TnbContext *ctx, cudaStream_t stream, size_t bytes, float **out);
 // ctx-owned bf16 scratch copies of fp32 operands (generic entry points in TNB_MATH_BF16): slot 0 / 1
 int bf16_scratch(TnbContext *ctx, int slot, const float *src, int rows, int cols, int stride, uint16_t **out, int *out_stride);
 

@@ -451,7 +451,39 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     if (threadIdx.x == 64) { DBG_TS(1, 2); DBG_CTA(1); }
   }
-  if (SPLIT == 2) {
+  // split-K: which of this warp's chunks of the exchanged half (chunk ci <-> slot (ci - chalf) / XSTEP of the warp's exchange area)
+  constexpr int XSTEP = CONV_WARPS / 4;
+  constexpr int XITERS = (HALFC + XSTEP - 1) / XSTEP;
+  const float4 *xmine = nullptr;       // this CTA's slot of the L2 exchange buffer: what the partner pair has left for it
+  if (SPLIT == 2 && ep.xchg) {
+    // Accumulator exchange THROUGH L2 (default): every epilogue thread stores the 32-column TMEM rows of the half the OTHER pair
+    // finishes into the partner CTA's slot, in the register layout tcgen05.ld produced them in ([warp][chunk][j][lane] float4: a warp
+    // instruction covers 512 contiguous bytes); the partner thread at the same (warp, lane) — same TMEM lanes, same rows — reads them
+    // back the same way and adds them to its own accumulator before the transpose.  One cluster barrier (release / acquire at cluster
+    // scope) orders the stores before the loads.  Distributed shared memory moves 17-21 B/clk per SM; L2 takes the 64 KB of a CTA at
+    // the rate of its ordinary stores, and the read-back overlaps the epilogue (measured: profiles/r02_split_exchange.md).
+    const size_t slot_f4 = (size_t)CONV_WARPS * XITERS * 8 * 32;
+    const size_t cta = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    xmine = (const float4 *)ep.xchg + cta * slot_f4;
+    if (threadIdx.x == 64) DBG_TS(7, 0);
+    if (warp >= 2) {
+      float4 *xdst = (float4 *)ep.xchg + (cta ^ 2u) * slot_f4 + (size_t)(warp - 2) * XITERS * 256 + lane;
+#pragma unroll 1
+      for (int ci = chalf, it = 0; ci < HALFC; ci += XSTEP, it++) {
+        const int c = (1 - (int)split) * HALFC + ci;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          __stcg(xdst + (it * 8 + j) * 32, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                                      __uint_as_float(v[4 * j + 3])));
+      }
+    }
+    if (threadIdx.x == 64) DBG_TS(7, 2);
+    cluster_sync_all();  // release (my stores) / acquire (the partner's) at cluster scope
+    if (threadIdx.x == 64) DBG_TS(7, 3);
+  } else if (SPLIT == 2) {
+    // exchange through distributed shared memory (TNB_GEMM_XCHG=dsmem; the first version, kept for A/B measurements)
     if (threadIdx.x == 64) DBG_TS(7, 0);
     cluster_sync_all();  // every pair of the cluster has finished its MMAs: all four CTAs' stage buffers are free
     if (threadIdx.x == 64) DBG_TS(7, 1);
@@ -480,6 +512,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int ci = chalf; ci < nchunks; ci += CONV_WARPS / 4) {
       const int c = (SPLIT == 2) ? (int)split * HALFC + ci : ci;
       if (n0 + c * 32 >= N) break;
+      float4 px[8];  // split-K through L2: the partner pair's sums for this chunk
+      if (SPLIT == 2 && xmine) {
+        const float4 *xsrc = xmine + ((size_t)(warp - 2) * XITERS + (ci - chalf) / XSTEP) * 256 + lane;
+#pragma unroll
+        for (int j = 0; j < 8; j++) px[j] = __ldcg(xsrc + j * 32);
+      }
       if (ci != chalf) prefetch_chunk(ci);
       if (threadIdx.x == 64) DBG_TS(6, 4 * (ci / 2) + 0);
       const int n = chunk_col(ci);
@@ -490,17 +528,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
       if (threadIdx.x == 64) DBG_TS(6, 4 * (ci / 2) + 1);
       float4 *srow = (float4 *)(scratch + lane * 36);
+      if (SPLIT == 2 && xmine) {
+        // own K half + the partner's (a + b is commutative: both halves of the tile agree bit for bit)
 #pragma unroll
-      for (int j = 0; j < 8; j++)
-        srow[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                              __uint_as_float(v[4 * j + 3]));
+        for (int j = 0; j < 8; j++)
+          srow[j] = make_float4(__uint_as_float(v[4 * j]) + px[j].x, __uint_as_float(v[4 * j + 1]) + px[j].y, __uint_as_float(v[4 * j + 2]) + px[j].z,
+                                __uint_as_float(v[4 * j + 3]) + px[j].w);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          srow[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                __uint_as_float(v[4 * j + 3]));
+      }
       __syncwarp();
       if (threadIdx.x == 64) DBG_TS(6, 4 * (ci / 2) + 2);
       // accumulator value (both K halves when split) of this lane's 4 columns in row r8 + 4k
       auto acc_at = [&](int k) {
         const int r = r8 + 4 * k;
         float4 a4 = *(const float4 *)(scratch + r * 36 + cg4);
-        if (SPLIT == 2) {  // other K half, computed by the partner pair (a + b is commutative: both halves of the tile agree)
+        if (SPLIT == 2 && !xmine) {  // other K half, received through distributed shared memory
           const float4 p4 = *(const float4 *)(recv + (q * 32 + r) * RS + ci * 32 + cg4);
           a4.x += p4.x; a4.y += p4.y; a4.z += p4.z; a4.w += p4.w;
         }
@@ -696,7 +742,15 @@ static int launch_tc(TnbContext *ctx, const CUtensorMap &tmA, const CUtensorMap 
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;
   }
-  TNB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, M, N, K, ep));
+  EpiParams epl = ep;
+  epl.xchg = nullptr;
+  if (SPLIT == 2) {
+    // one slot per CTA: [8 warps][chunks per warp][8][32] float4 (see the kernel's exchange step)
+    constexpr size_t SLOT = (size_t)CONV_WARPS * (((BN / 64) + CONV_WARPS / 4 - 1) / (CONV_WARPS / 4)) * 8 * 32 * 16;
+    const int rc = xchg_buffer(ctx, ctx->stream, (size_t)cfg.gridDim.x * cfg.gridDim.y * SLOT, &epl.xchg);
+    if (rc != TNB_OK) return rc;
+  }
+  TNB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, M, N, K, epl));
   if (e1) TNB_CUDA(cudaEventRecord(e1, ctx->stream));
   TNB_LAUNCHED(ctx);
   return TNB_OK;

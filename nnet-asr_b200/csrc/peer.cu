@@ -42,7 +42,16 @@ struct PeerArgs {
   int pushed;        // the gradients were pushed into the owners' staging slices (tnb_affine_grad_scatter): G[rank] holds `world` local slices
   unsigned seq;
   long long timeout;  // cycles; 0 = wait for ever
+  long long *trace;   // TNB_DP_TRACE=1: [64 launches][4] %globaltimer stamps of CTA 0 (entry, all ranks ready, own rows done) and of the last CTA (all ranks done)
 };
+
+__device__ __forceinline__ void peer_stamp(const PeerArgs &a, int slot) {
+  if (a.trace && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.trace[(a.seq & 63u) * 4 + slot] = t;
+  }
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -80,8 +89,10 @@ template <int WORLD, int U>
 __device__ __forceinline__ void peer_update_body(const PeerArgs &a, const int bid, const int nblk) {
   const int world = WORLD > 0 ? WORLD : a.world;
   unsigned *my = a.flags[a.rank];
+  if (bid == 0) peer_stamp(a, 0);
   if (bid == 0 && (int)threadIdx.x < world) st_release_sys(a.flags[threadIdx.x] + a.rank, a.seq);
   if (!wait_flags(my, 0, world, a.seq, a.timeout)) return;
+  if (bid == 0) peer_stamp(a, 1);
 
   const int vcols = (a.cols + 3) >> 2;
   const long total = (long)a.shard * vcols;
@@ -146,6 +157,7 @@ __device__ __forceinline__ void peer_update_body(const PeerArgs &a, const int bi
     }
   }
 
+  if (bid == 0) peer_stamp(a, 2);
   // this rank is done when ALL its CTAs are: the last one to arrive publishes the flag and waits for the other ranks
   __threadfence_system();
   __syncthreads();
@@ -157,6 +169,14 @@ __device__ __forceinline__ void peer_update_body(const PeerArgs &a, const int bi
   __threadfence_system();
   if ((int)threadIdx.x < world) st_release_sys(a.flags[threadIdx.x] + 16 + a.rank, a.seq);
   wait_flags(my, 16, world, a.seq, a.timeout);
+  peer_stamp(a, 3);
+}
+
+// TNB_DP_TRACE=1: a one-thread kernel that leaves %globaltimer in *p (stream-ordered marker around the copy engines' pushes)
+__global__ void peer_stamp_kernel(long long *p) {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *p = t;
 }
 
 template <int WORLD, int U>
@@ -216,11 +236,23 @@ static int fill_peer_args(const TnbPeerJob *job, int rank, int world, unsigned *
   update_scalars(job->lr, job->mmt, job->wc, job->grad_div_frm, job->n_frames, &a.scale, &a.l2);
   a.seq = seq;
   a.timeout = peer_timeout_cycles();
+  a.trace = nullptr;
   const long items = (long)a.shard * ((d.cols + 3) / 4);
   long nb = (items + 511) / 512;
   if (nb > peer_ctas()) nb = peer_ctas();
   if (nb < 1) nb = 1;
   *blocks = nb;
+  return TNB_OK;
+}
+
+// TNB_DP_TRACE=1: [64][4] stamps of the update kernels, then [64][2] stamps around the pushes (slot = push counter % 64)
+static int peer_trace_buffer(TnbContext *ctx) {
+  static int want_trace = -1;
+  if (want_trace < 0) { const char *e = getenv("TNB_DP_TRACE"); want_trace = (e && atoi(e) != 0) ? 1 : 0; }
+  if (want_trace && !ctx->capturing && !ctx->peer_trace) {
+    TNB_CUDA(cudaMalloc(&ctx->peer_trace, sizeof(long long) * 384));
+    TNB_CUDA(cudaMemset(ctx->peer_trace, 0, sizeof(long long) * 384));
+  }
   return TNB_OK;
 }
 
@@ -231,6 +263,8 @@ static int launch_peer_update(TnbContext *ctx, cudaStream_t stream, const TnbPee
   long blocks = 1;
   int rc = fill_peer_args(job, rank, world, flags, seq, &a, &blocks);
   if (rc != TNB_OK) return rc;
+  if (peer_trace_buffer(ctx) != TNB_OK) return TNB_ERR_CUDA;
+  a.trace = (long long *)ctx->peer_trace;
   const dim3 grid((unsigned)blocks), block(512);
   switch (world) {
     case 1: dp_peer_update_kernel<1, 4><<<grid, block, 0, stream>>>(a); break;
@@ -335,6 +369,44 @@ int tnb_dp_peer_update(TnbContext *ctx, const TnbPeerJob *job, void *wait_event,
   return TNB_OK;
 }
 
+int tnb_dp_peer_update_after(TnbContext *ctx, const TnbPeerJob *job, void *const *wait_events, int n_wait, void *done_event) {
+  TNB_ARG(ctx && job && (wait_events || n_wait == 0) && n_wait >= 0, "null");
+  TNB_ARG(ctx->world > 1, "tnb_dp_peer_update_after is the multi-rank entry point (tnb_dp_peer_update covers one rank)");
+  TNB_ARG(ctx->nccl_comm != nullptr || ctx->local_group != nullptr, "communicator not initialised");
+  cudaStream_t cs = ctx->comm_stream;
+  int rc = ensure_peer_flags(ctx);
+  if (rc != TNB_OK) return rc;
+  for (int i = 0; i < n_wait; i++)
+    if (wait_events[i]) TNB_CUDA(cudaStreamWaitEvent(cs, (cudaEvent_t)wait_events[i], 0));
+  rc = launch_peer_update(ctx, cs, job, ctx->rank, ctx->world, ctx->peer_flags, ++ctx->peer_seq);
+  if (rc != TNB_OK) return rc;
+  if (done_event) TNB_CUDA(cudaEventRecord((cudaEvent_t)done_event, cs));
+  return TNB_OK;
+}
+
+int tnb_peer_push_blocks(TnbContext *ctx, int stream_id, const float *G, float *const *Gpeers, int world, int rank, TnbMatrixDim dG,
+                         int rows_pad, void *wait_event, void *done_event) {
+  TNB_ARG(ctx && G && Gpeers, "null");
+  TNB_ARG(world >= 1 && world <= TNB_MAX_PEERS && rank >= 0 && rank < world, "rank/world");
+  TNB_ARG(dG.rows > 0 && dG.cols > 0 && dG.stride >= dG.cols && rows_pad >= dG.rows && rows_pad % world == 0, "dims");
+  cudaStream_t s = stream_of(ctx, stream_id);
+  TNB_ARG(s != nullptr, "unknown stream id");
+  if (wait_event) TNB_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)wait_event, 0));
+  if (peer_trace_buffer(ctx) != TNB_OK) return TNB_ERR_CUDA;
+  long long *tr = ctx->peer_trace ? (long long *)ctx->peer_trace + 256 + (ctx->push_seq++ & 63u) * 2 : nullptr;
+  if (tr) peer_stamp_kernel<<<1, 1, 0, s>>>(tr);
+  const size_t shard = (size_t)(rows_pad / world), block = shard * (size_t)dG.stride;  // floats: whole rows, hence contiguous
+  // the farthest-first order spreads the ranks' copies over different destinations at any one time (rank r starts with r + 1)
+  for (int k = 1; k <= world; k++) {
+    const int o = (rank + k) % world;
+    TNB_ARG(Gpeers[o] != nullptr, "null peer pointer");
+    TNB_CUDA(cudaMemcpyAsync(Gpeers[o] + (size_t)rank * block, G + (size_t)o * block, block * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  if (tr) peer_stamp_kernel<<<1, 1, 0, s>>>(tr + 1);
+  if (done_event) TNB_CUDA(cudaEventRecord((cudaEvent_t)done_event, s));
+  return TNB_OK;
+}
+
 int tnb_dp_peer_update_on(TnbContext *ctx, int stream_id, const TnbPeerJob *job, int rank, int world, unsigned *const *flags, unsigned seq) {
   TNB_ARG(ctx != nullptr, "null");
   cudaStream_t s = stream_of(ctx, stream_id);
@@ -388,6 +460,16 @@ int tnb_dp_peer_update_virtual(TnbContext *ctx, const TnbPeerJob *jobs, int worl
       return TNB_ERR_COMM;
     }
   }
+  return TNB_OK;
+}
+
+int tnb_peer_trace_read(TnbContext *ctx, long long *out /* [64][4] + [64][2] */, unsigned *seq /* [2] */) {
+  TNB_ARG(ctx && out && seq, "null");
+  TNB_ARG(ctx->peer_trace != nullptr, "no trace: set TNB_DP_TRACE=1 before the first peer-memory update");
+  TNB_CUDA(cudaDeviceSynchronize());
+  TNB_CUDA(cudaMemcpy(out, ctx->peer_trace, sizeof(long long) * 384, cudaMemcpyDeviceToHost));
+  seq[0] = ctx->peer_seq;
+  seq[1] = ctx->push_seq;
   return TNB_OK;
 }
 

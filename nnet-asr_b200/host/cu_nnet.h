@@ -144,9 +144,10 @@ class CuBiasedLinearity : public CuUpdatableComponent {
  public:
   CuBiasedLinearity(size_t nInputs, size_t nOutputs, CuComponent *pPred)
       : CuUpdatableComponent(nInputs, nOutputs, pPred), mLinearity(nInputs, nOutputs), mBias(nOutputs),
-        mLinearityCorrection(nInputs, nOutputs), mBiasCorrection(nOutputs), mDpFrames(0), mRowsPad(0), mEvE(NULL), mEvB(NULL), mEvAR(NULL), mEvDone(NULL), mDpPending(false), mPeerMapped(false) {}
+        mLinearityCorrection(nInputs, nOutputs), mBiasCorrection(nOutputs), mDpFrames(0), mRowsPad(0), mEvE(NULL), mEvB(NULL), mEvAR(NULL), mEvDone(NULL), mEvG(NULL), mEvPush(NULL), mDpPending(false), mPeerMapped(false) {}
   ~CuBiasedLinearity() {
     if (mEvE) { tnb_event_destroy(Cx(), mEvE); tnb_event_destroy(Cx(), mEvB); tnb_event_destroy(Cx(), mEvAR); tnb_event_destroy(Cx(), mEvDone); }
+    if (mEvG) { tnb_event_destroy(Cx(), mEvG); tnb_event_destroy(Cx(), mEvPush); }
     if (mPeerMapped) { tnb_peer_unmap(Cx(), mGradPeers); tnb_peer_unmap(Cx(), mWPeers); }
   }
   ComponentType GetType() const { return BIASED_LINEARITY; }
@@ -295,19 +296,27 @@ class CuBiasedLinearity : public CuUpdatableComponent {
   }
   /// all-reduce schedule, one layer, first half: the bias gradient (column sums of E) on a side stream, the weight gradient
   /// GEMM on the compute stream.  Only the GEMM stays on the compute stream's critical path.
-  void DataParallelGradient() {
+  /// evEReady: an event of the compute stream behind which this layer's error input is complete (the gradient event of the layer
+  /// above, CuNetwork::Backpropagate); NULL = record one now.  Peer-memory schedule: the only event recorded on the compute stream
+  /// per layer is mEvG behind the gradient GEMM, so the dX GEMM -> gradient GEMM pair keeps its programmatic-dependent-launch overlap.
+  void DataParallelGradient(void *evEReady = NULL) {
     if (mRowsPad == 0) PrepareDataParallel(1);
     if (!mEvE) {
       TNB_CHECK(tnb_event_create(Cx(), &mEvE)); TNB_CHECK(tnb_event_create(Cx(), &mEvB));
       TNB_CHECK(tnb_event_create(Cx(), &mEvAR)); TNB_CHECK(tnb_event_create(Cx(), &mEvDone));
     }
+    if (!mEvG) { TNB_CHECK(tnb_event_create(Cx(), &mEvG)); TNB_CHECK(tnb_event_create(Cx(), &mEvPush)); }
     const CuMatrix<BaseFloat> &E = GetErrorInput();
-    TNB_CHECK(tnb_event_record(Cx(), mEvE, TNB_STREAM_COMPUTE));        // E (and the previous bunch's use of the buffers) is done
-    TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_AUX, mEvE));
+    if (!evEReady) {
+      TNB_CHECK(tnb_event_record(Cx(), mEvE, TNB_STREAM_COMPUTE));      // E (and the previous bunch's use of the buffers) is done
+      evEReady = mEvE;
+    }
+    TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_AUX, evEReady));
     TnbBiasJob bj = {E.pCUData(), E.Dim(), NULL, mGrad.pCURowData(mRowsPad), 0.0f, 0.0f, 0, 0};  // gradient only
     TNB_CHECK(tnb_bias_update_batch_on(Cx(), TNB_STREAM_AUX, &bj, 1));
     TNB_CHECK(tnb_event_record(Cx(), mEvB, TNB_STREAM_AUX));
-    if (mPeerMapped && DpPush()) {
+    const int push = mPeerMapped ? DpPush() : 0;
+    if (push == 1) {
       // GEMM -> reduce-scatter in one kernel: the tiles of dW go straight to the owning ranks' staging slices over NVLink
       const CuMatrix<BaseFloat> &X = GetInput();
       int rank = 0, world = 1;
@@ -316,12 +325,31 @@ class CuBiasedLinearity : public CuUpdatableComponent {
       const uint16_t *x16 = bf ? X.Twin() : NULL, *e16 = bf ? E.Twin() : NULL;
       TNB_CHECK(tnb_affine_grad_scatter(Cx(), X.pCUData(), X.Dim(), E.pCUData(), E.Dim(), x16, bf ? X.TwinStride() : 0, e16, bf ? E.TwinStride() : 0,
                                         (float *const *)mGradPeers, world, rank, mLinearity.Dim(), (int)mRowsPad));
+    } else if (push == 2) {
+      // the GEMM keeps its stores local (mGradLocal); the copy engines carry the row blocks to their owners' staging slices on a
+      // side stream while the compute stream goes on with the next layer's GEMMs (no SM waits for NVLink)
+      const CuMatrix<BaseFloat> &X = GetInput();
+      TnbMatrixDim dG = mLinearity.Dim();
+      if (Bf16()) TNB_CHECK(tnb_affine_grad_bf16(Cx(), X.Twin(), X.TwinStride(), X.Dim(), E.Twin(), E.TwinStride(), E.pCUData(), E.Dim(), mGradLocal.pCUData(), dG, NULL));
+      else TNB_CHECK(tnb_affine_grad(Cx(), X.pCUData(), X.Dim(), E.pCUData(), E.Dim(), mGradLocal.pCUData(), dG, NULL));
     } else {
       ComputeGradient(false);
     }
+    if (mPeerMapped) {
+      TNB_CHECK(tnb_event_record(Cx(), mEvG, TNB_STREAM_COMPUTE));
+      if (push == 2) {
+        int rank = 0, world = 1;
+        TNB_CHECK(tnb_comm_world(Cx(), &rank, &world));
+        TNB_CHECK(tnb_peer_push_blocks(Cx(), TNB_STREAM_AUX2, mGradLocal.pCUData(), (float *const *)mGradPeers, world, rank, mLinearity.Dim(), (int)mRowsPad,
+                                       mEvG, mEvPush));
+      }
+    }
   }
-  /// TNB_DP_PUSH=0: the owner pulls the ranks' gradient blocks with peer loads instead (the round-1 schedule)
-  static bool DpPush() { static int v = -1; if (v < 0) { const char *e = getenv("TNB_DP_PUSH"); v = (e && atoi(e) == 0) ? 0 : 1; } return v != 0; }
+  /// the event behind this layer's gradient GEMM on the compute stream (peer-memory schedule), NULL otherwise
+  void *GradientEvent() { return mPeerMapped ? mEvG : NULL; }
+  /// TNB_DP_PUSH: how a rank's gradient blocks reach their owners in the peer-memory schedule — 2 (default): copy engines behind a
+  /// local gradient GEMM; 1: peer stores of the gradient GEMM's epilogue; 0: the owner's update kernel pulls them with peer loads
+  static int DpPush() { static int v = -1; if (v < 0) { const char *e = getenv("TNB_DP_PUSH"); v = e ? atoi(e) : 2; if (v < 0 || v > 2) v = 2; } return v; }
   /// second half: the all-reduce of [dW ; db] on the communication stream behind both, the update on a second side stream behind
   /// the all-reduce.  Nothing waits for it here: whoever touches the parameters next does (WaitDataParallel), which lets the
   /// exchange of this bunch run into the forward pass of the next one.
@@ -343,6 +371,7 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     TNB_CHECK(tnb_peer_map(Cx(), mLinearity.pCUData(), mWPeers));
     mGrad.MarkExported();
     mLinearity.MarkExported();
+    if (DpPush() == 2) mGradLocal.Init(mRowsPad, mNOutputs);  // padded rows stay zero
     mPeerMapped = true;
   }
   /// second half, peer-memory schedule: ONE kernel on the communication stream sums this rank's block of rows over all ranks'
@@ -357,7 +386,8 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     j.dW = mLinearity.Dim(); j.rows_pad = (int)mRowsPad;
     j.lr = mLearningRate; j.mmt = mMomentum; j.wc = mWeightcost; j.grad_div_frm = mGradDivFrm ? 1 : 0; j.n_frames = n_frames_global;
     j.pushed = DpPush() ? 1 : 0;
-    TNB_CHECK(tnb_dp_peer_update(Cx(), &j, mEvB, mEvDone));
+    void *waits[2] = {DpPush() == 2 ? mEvPush : mEvG, mEvB};  // the gradient (pushed, or complete where it is) and the bias gradient
+    TNB_CHECK(tnb_dp_peer_update_after(Cx(), &j, waits, 2, mEvDone));
     mDpPending = true;
   }
   /// pieces of the second half for a GROUP of layers exchanged in one NCCL launch (CuNetwork's deferred layers)
@@ -432,9 +462,11 @@ class CuBiasedLinearity : public CuUpdatableComponent {
   CuMatrix<BaseFloat> mLinearityCorrection;
   CuVector<BaseFloat> mBiasCorrection;
   CuMatrix<BaseFloat> mGrad;  ///< data-parallel only: [dW ; db]
+  CuMatrix<BaseFloat> mGradLocal;  ///< peer-memory schedule with copy-engine pushes: this rank's full dW before its row blocks travel to their owners' mGrad
   int mDpFrames;
   size_t mRowsPad;
   void *mEvE, *mEvB, *mEvAR, *mEvDone;  ///< data-parallel stream ordering (created on first use)
+  void *mEvG, *mEvPush;                 ///< peer-memory schedule: behind the gradient GEMM (compute stream) / behind the copy engines' pushes
   mutable bool mDpPending;              ///< an update of this layer is in flight on the side streams
   bool mPeerMapped;                     ///< peer-memory schedule: the tables below are filled
   void *mGradPeers[TNB_MAX_PEERS], *mWPeers[TNB_MAX_PEERS];  ///< every rank's mGrad / mLinearity as mapped into this process
@@ -1017,6 +1049,7 @@ class CuNetwork {
     std::vector<void *> side_done;             // fused schedule on two streams: one event per layer, behind its update GEMM
     std::vector<TnbBiasJob> bias_jobs;         // fused schedule: bias halves of the updates, applied together after the last layer
     int sig_done_by_batch = -1;                // batched schedule: index of the <sigmoid> whose backward the last dX job included
+    void *dp_prev_grad_event = NULL;           // peer-memory schedule: event behind the gradient GEMM of the updatable layer above (its dX precedes it: this layer's error is complete)
     // Batched schedule (single GPU, fused): the dX GEMM of a layer shares ONE persistent launch with tiles of the weight-gradient
     // GEMMs of the layers ABOVE it (tnb_gemm_batch).  A layer's update job enters the pool only after its own dX has been
     // launched (the update rewrites W in place, dX reads it); what is left in the pool runs in a last launch.
@@ -1067,7 +1100,10 @@ class CuNetwork {
               mNetComponents[i + 1] != mpPropagErrorStopper)
             done = true;
         }
-        if (!done) c->Backpropagate();
+        if (!done) {
+          c->Backpropagate();
+          if (c->GetType() != CuComponent::BIASED_LINEARITY) dp_prev_grad_event = NULL;  // this kernel, not the gradient GEMM above, completes the error below
+        }
       }
       if (c->IsUpdatable()) {
         CuUpdatableComponent &rComp = dynamic_cast<CuUpdatableComponent &>(*c);
@@ -1081,7 +1117,8 @@ class CuNetwork {
               // layer's gradient, which the next forward pass needs FIRST, is the last one to exist: the middle layers'
               // exchanges are therefore issued after the lowest layers', in forward order, and run into the next bunch's
               // forward pass (every layer's forward waits only for its own update, CuBiasedLinearity::WaitDataParallel).
-              lin->DataParallelGradient();
+              lin->DataParallelGradient(dp_prev_grad_event);
+              dp_prev_grad_event = lin->GradientEvent();
               const int k = (int)pending.size();
               if (k >= mDpDeferBegin && k < mDpDeferEnd) deferred.push_back(lin);
               else if (mDpPeer) lin->DataParallelPeerUpdate((int)lin->GetInput().Rows() * mWorld);
