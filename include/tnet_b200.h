@@ -333,7 +333,9 @@ typedef struct TnbObjStats_ {
   long long correct; /* rows with argmax(y)==argmax(t) (xent only) */
 } TnbObjStats;
 /* CuSoftmax::PropagateFnc + CuCrossEntropy::Evaluate fused (cuActivation.cc:26-31, cuObjectiveFunction.cc:48-84):
- *   Y = softmax(A) (Y may be NULL), Err = Y - T, stats += {xent, rows, correct}.  `stats` is a DEVICE pointer. */
+ *   Y = softmax(A) (Y may be NULL), Err = Y - T, stats += {xent, rows, correct}.  `stats` is a DEVICE pointer.
+ *   ONE TnbMatrixDim describes A, T, Y and Err: all four have d.rows rows and d.stride floats of pitch (the callers check, as the
+ *   host mirror's CheckTargetLayout does; the same holds for tnb_xent_eval and tnb_mse_eval). */
 int tnb_softmax_xent(TnbContext *ctx, const float *A, const float *T, float *Y, float *Err, TnbMatrixDim d, TnbObjStats *stats);
 /* CuCrossEntropy::Evaluate on an existing softmax output */
 int tnb_xent_eval(TnbContext *ctx, const float *Y, const float *T, float *Err, TnbMatrixDim d, TnbObjStats *stats);

@@ -828,12 +828,24 @@ class CuObjectiveFunction {
   TnbObjStats *mpStats;  ///< device-resident accumulators
 };
 
+/// the objective kernels index the targets with the network output's rows and pitch (one TnbMatrixDim for both): refuse a target
+/// matrix of another shape or pitch instead of reading it out of bounds
+inline void CheckTargetLayout(const CuMatrix<BaseFloat> &rOut, const CuMatrix<BaseFloat> &rDesired) {
+  if (rDesired.Rows() != rOut.Rows() || rDesired.Stride() != rOut.Stride()) {
+    std::ostringstream os;
+    os << "Non-matching dimensions of network output with training targets!!! Netoutput rows:" << rOut.Rows() << " pitch:" << rOut.Stride()
+       << " Targets rows:" << rDesired.Rows() << " pitch:" << rDesired.Stride();
+    Error(os.str());
+  }
+}
+
 class CuMeanSquareError : public CuObjectiveFunction {
  public:
   ObjFunType GetTypeId() { return MEAN_SQUARE_ERROR; }
   const char *GetTypeLabel() { return "<mean_square_error>"; }
   void Evaluate(const CuMatrix<BaseFloat> &rNetOutput, const CuMatrix<BaseFloat> &rDesired, CuMatrix<BaseFloat> &rNetError) {
     if (rDesired.Cols() != rNetOutput.Cols() || rDesired.Rows() != rNetOutput.Rows()) Error("Non-matching dimensions of network output with training targets!!!");
+    CheckTargetLayout(rNetOutput, rDesired);
     rNetError.Init(rNetOutput.Rows(), rNetOutput.Cols());
     TNB_CHECK(tnb_mse_eval(Cx(), rNetOutput.pCUData(), rDesired.pCUData(), rNetError.pCUData(), rNetOutput.Dim(), mpStats));
   }
@@ -856,6 +868,7 @@ class CuCrossEntropy : public CuObjectiveFunction {
          << " Targets:" << rDesired.Cols();
       Error(os.str());
     }
+    CheckTargetLayout(rNetOutput, rDesired);
     rNetError.Init(rNetOutput.Rows(), rNetOutput.Cols());
     TNB_CHECK(tnb_xent_eval(Cx(), rNetOutput.pCUData(), rDesired.pCUData(), rNetError.pCUData(), rNetOutput.Dim(), mpStats));
   }
@@ -863,6 +876,7 @@ class CuCrossEntropy : public CuObjectiveFunction {
   void EvaluateFromActivations(const CuMatrix<BaseFloat> &rAct, const CuMatrix<BaseFloat> &rDesired, CuMatrix<BaseFloat> &rSoftmaxOut,
                                CuMatrix<BaseFloat> &rNetError) {
     if (rDesired.Cols() != rAct.Cols()) Error("Non-matching dimensions of network output with training targets!!!");
+    CheckTargetLayout(rAct, rDesired);
     rSoftmaxOut.Init(rAct.Rows(), rAct.Cols());
     rNetError.Init(rAct.Rows(), rAct.Cols());
     TNB_CHECK(tnb_softmax_xent(Cx(), rAct.pCUData(), rDesired.pCUData(), rSoftmaxOut.pCUData(), rNetError.pCUData(), rAct.Dim(), mpStats));

@@ -16,6 +16,7 @@
 
 #include <iomanip>
 #include <map>
+#include <set>
 
 #include "tnet_base.h"
 
@@ -179,16 +180,10 @@ class UserInterface {
       throw std::runtime_error(std::string("TRUE or FALSE expected for ") + name + " but found '" + val + "'");
     return false;
   }
-  /// unknown / unused command line parameters are an error (TNetCu.cc:261)
+  /// every command line parameter nothing has read is an error (UserInterface.cc:657-667), short options included
   void CheckCommandLineParamUse() {
-    for (std::map<std::string, ValueRecord>::iterator it = mMap.begin(); it != mMap.end(); ++it) {
-      if (!it->second.mRead && it->second.mOption != 'C') {
-        std::string what = it->second.mOption == '-' ? std::string("Unexpected command line parameter ") + it->first
-                                                     : std::string("Ignoring option '-") + it->second.mOption + "'";
-        if (it->second.mOption == '-') throw std::runtime_error(what);
-        Warning(what);
-      }
-    }
+    for (std::map<std::string, ValueRecord>::iterator it = mMap.begin(); it != mMap.end(); ++it)
+      if (!it->second.mRead && it->second.mOption != 'C') throw std::runtime_error(std::string("Unexpected command line parameter ") + it->first);
   }
   /// same layout as the reference's dump (UserInterface.cc:645-654): "# " marks a parameter nothing has read yet
   void PrintConfig(std::ostream &out) {
@@ -249,15 +244,13 @@ class FeatureRepository {
     const std::string &Logical() const { return mLogical; }
     const std::string &Physical() const { return mPhysical; }
   };
-  FeatureRepository() : mSwap(true), mStartExt(0), mEndExt(0), mTrace(0), mPos(0) { memset(&mHeader, 0, sizeof(mHeader)); }
+  FeatureRepository() : mSwap(true), mStartExt(0), mEndExt(0), mTargetKind(-1), mTrace(0), mPos(0) { memset(&mHeader, 0, sizeof(mHeader)); }
 
   void Init(bool swap, int extLeft, int extRight, int targetKind, int derivOrder, int *pDerivWinLen, const char *pCmnPath, const char *pCmnMask,
             const char *pCvnPath, const char *pCvnMask, const char *pCvgFile) {
-    (void)pDerivWinLen; (void)pCmnPath; (void)pCvnPath;
+    (void)pDerivWinLen; (void)pCmnPath; (void)pCvnPath; (void)derivOrder;
     mSwap = swap; mStartExt = extLeft; mEndExt = extRight;
-    if (derivOrder > 0 || (targetKind & 0x3F00 & ~0)) {
-      if (derivOrder > 0) Error("TARGETKIND with derivatives (_D/_A/_T) is not built into the B200 hot path");
-    }
+    mTargetKind = targetKind;  // checked against every file's own kind: this reader converts nothing (CheckKind)
     if (pCmnMask || pCvnMask || pCvgFile) Error("CMEAN/VARSCALE normalisation files are not built into the B200 hot path (use a <bias>/<window> transform)");
   }
   void Trace(int t) { mTrace = t; }
@@ -292,6 +285,13 @@ class FeatureRepository {
     if (h.mSampleKind & 02000) { fclose(f); Error(std::string("Compressed (_C) HTK files are not built into the B200 hot path: ") + rec.mPhysical); }
     // the reference's header check (Features.cc:522-528) also bounds the sample period: a wrong byte order shows up here
     if (h.mSamplePeriod < 0 || h.mSamplePeriod > 100000 || h.mNSamples <= 0 || h.mSampleSize <= 0 || h.mSampleSize % 4 != 0) { fclose(f); Error(std::string("Invalid HTK header in feature file: '") + rec.mPhysical + "'"); }
+    if (!KindOk(h.mSampleKind)) {
+      fclose(f);
+      char buf[256];
+      snprintf(buf, sizeof(buf), "Cannot convert parameter kind 0%o of '%s' to TARGETKIND 0%o: kind conversions (_Z mean normalisation, _E/_0/_N energy "
+               "columns, _D/_A/_T derivatives) are not built into the B200 hot path", (unsigned)h.mSampleKind, rec.mPhysical.c_str(), (unsigned)mTargetKind);
+      Error(buf);
+    }
     const int dim = h.mSampleSize / 4;
     int first = rec.mFirst < 0 ? 0 : rec.mFirst, last = rec.mLast < 0 ? h.mNSamples - 1 : rec.mLast;
     if (first > last || last >= h.mNSamples) { fclose(f); Error(std::string("Frame range out of file: ") + rec.mLogical); }
@@ -338,6 +338,18 @@ class FeatureRepository {
     if (!ok) Error(std::string("Cannot write to file:") + filename);
     return ok;
   }
+  /// The reference converts a file's parameter kind to TARGETKIND (Features.cc:1120-1178: per-utterance mean normalisation for _Z,
+  /// energy columns added or stripped, derivatives appended).  This reader converts nothing, so it accepts exactly the cases where the
+  /// reference's conversion is the identity — TARGETKIND=ANON (the file's own kind), or the same base kind (or an ANON base on either
+  /// side) with the same E/N/D/A/Z/0/T qualifiers — and refuses every other combination instead of training on different features.
+  bool KindOk(int fileKind) const {
+    const int conv = 0100 | 0200 | 0400 | 01000 | 04000 | 020000 | 0100000;
+    const int anon_here = 077, anon_htk = 12;   // ReadParmKind's ANON / the value in HTK headers
+    if (mTargetKind < 0 || mTargetKind == anon_here) return true;
+    const int tb = mTargetKind & 077, fb = fileKind & 077;
+    if (tb != anon_here && tb != anon_htk && fb != anon_htk && tb != fb) return false;
+    return (mTargetKind & conv) == (fileKind & conv);
+  }
   static int ReadParmKind(const char *str, bool) {
     static const char *names[] = {"WAVEFORM", "LPC", "LPREFC", "LPCEPSTRA", "LPDELCEP", "IREFC", "MFCC", "FBANK", "MELSPEC", "USER", "DISCRETE", "PLP", "ANON"};
     std::string s(str);
@@ -377,7 +389,7 @@ class FeatureRepository {
     return r;
   }
   bool mSwap;
-  int mStartExt, mEndExt, mTrace;
+  int mStartExt, mEndExt, mTargetKind, mTrace;
   std::vector<FileRecord> mFiles;
   size_t mPos;
   HtkHeader mHeader;
@@ -386,31 +398,34 @@ class FeatureRepository {
 // ------------------------------------------------------------------------------------------ LabelRepository
 class LabelRepository {
  public:
-  LabelRepository() : mTrace(0) {}
+  LabelRepository() : mHasDir(false), mHasExt(false), mTrace(0) {}
   void Trace(int t) { mTrace = t; }
+  /// pLabelDir / pLabelExt (SOURCETRANSCDIR / SOURCETRANSCEXT) build the label file name of an utterance from its logical feature
+  /// name exactly as the reference does (MakeHtkFileName, Labels.cc:52); that name is then looked up among the MLF's record names
+  /// with the reference's rules (MlfStream.cc:40-270): names without wildcards after their first character are hashed — an exact
+  /// name, or "*" + the name's tail from one of its '/' (longest tail first) — the others ('*', '?', '%' inside) are patterns tried in
+  /// file order; the first definition of a name wins.
   void Init(const char *pLabelMlfFile, const char *pOutputLabelMapFile, const char *pLabelDir, const char *pLabelExt) {
-    (void)pLabelDir;
-    mExt = pLabelExt ? pLabelExt : "lab";
+    mHasDir = pLabelDir != NULL;
+    mDir = pLabelDir ? pLabelDir : "";
+    mHasExt = pLabelExt != NULL;
+    mExt = pLabelExt ? pLabelExt : "";
     ReadOutputLabelMap(pOutputLabelMapFile);
     std::ifstream in(pLabelMlfFile);
     if (!in.good()) Error(std::string("Cannot open Label MLF file: ") + pLabelMlfFile);
-    std::string line, key;
-    bool in_rec = false;
+    std::string line;
+    std::vector<std::string> *body = NULL;
     while (std::getline(in, line)) {
       if (!line.empty() && line[line.size() - 1] == '\r') line.erase(line.size() - 1);
-      if (!in_rec) {
+      if (!body) {
         if (line.empty() || line[0] == '#') continue;
         if (line[0] == '"') {
           size_t q = line.rfind('"');
-          key = BaseKey(line.substr(1, q > 0 ? q - 1 : std::string::npos));
-          // a name defined twice: the FIRST definition is the one the reference's MLF index finds (MlfStream.tcc:356-372)
-          if (mRecords.find(key) != mRecords.end()) key = std::string("\x01duplicate ") + key;
-          mRecords[key].clear();
-          in_rec = true;
+          body = Insert(line.substr(1, q > 0 ? q - 1 : std::string::npos));
         }
       } else {
-        if (line == ".") { in_rec = false; continue; }
-        mRecords[key].push_back(line);
+        if (line == ".") { body = NULL; continue; }
+        body->push_back(line);
       }
     }
   }
@@ -419,12 +434,13 @@ class LabelRepository {
   /// per-frame class ids; times are divided by sourceRate with round-half-up (Labels.cc:111-112); an unlabelled frame is an error
   void GenLabelIds(std::vector<int> &ids, size_t nFrames, size_t sourceRate, const char *pFeatureLogical) {
     if (nFrames < 1) KALDI_ERR << "Number of frames:" << nFrames << " is lower than 1!!!\n" << pFeatureLogical;
-    std::map<std::string, std::vector<std::string> >::iterator rec = mRecords.find(BaseKey(pFeatureLogical));
-    if (rec == mRecords.end()) Error(std::string("Cannot open label MLF record: ") + BaseKey(pFeatureLogical) + "." + mExt);
+    const std::string label_file = LabelFileName(pFeatureLogical);
+    const std::vector<std::string> *rec = Find(label_file);
+    if (!rec) Error(std::string("Cannot open label MLF record: ") + label_file);
     ids.assign(nFrames, -1);
     size_t trunc_frames = 0;
-    for (size_t l = 0; l < rec->second.size(); l++) {
-      const std::string &line = rec->second[l];
+    for (size_t l = 0; l < rec->size(); l++) {
+      const std::string &line = (*rec)[l];
       if (line.empty() || line[0] == '#') continue;
       std::istringstream iss(line);
       unsigned long long beg, end;
@@ -452,7 +468,7 @@ class LabelRepository {
     for (size_t i = 0; i < nFrames; i++)
       if (ids[i] < 0) {
         std::ostringstream os;
-        os << "Desired vector sum isn't 1.0, " << " file: " << BaseKey(pFeatureLogical) << "." << mExt << " row: " << i << " nframes: " << nFrames
+        os << "Desired vector sum isn't 1.0, " << " file: " << label_file << " row: " << i << " nframes: " << nFrames
            << " sum: 0\n";
         Error(os.str());
       }
@@ -483,15 +499,81 @@ class LabelRepository {
     }
     if (mLabelMap.empty()) Error(std::string("Empty OutputLabelMapFile: ") + file);
   }
-  /// records are matched on the file's base name without directory and extension ("*/utt.lab" patterns)
-  static std::string BaseKey(const std::string &name) {
-    size_t sl = name.rfind('/');
-    std::string b = sl == std::string::npos ? name : name.substr(sl + 1);
-    size_t dot = b.rfind('.');
-    if (dot != std::string::npos) b.erase(dot);
-    return b;
+  std::string LabelFileName(const char *pFeatureLogical) const {
+    std::vector<char> buf(strlen(pFeatureLogical) + mDir.size() + mExt.size() + 8);
+    MakeHtkFileName(&buf[0], pFeatureLogical, mHasDir ? mDir.c_str() : NULL, mHasExt ? mExt.c_str() : NULL);
+    return std::string(&buf[0]);
   }
-  std::map<std::string, std::vector<std::string> > mRecords;
+  struct Record { std::vector<std::string> mLines; size_t mListLimit; };
+  static size_t DirDepth(const std::string &p) { size_t d = 0; for (size_t i = 0; i < p.size(); i++) d += (p[i] == '/' || p[i] == '\\'); return d; }
+  /// glob match of the reference's ProcessMask (StkMatch.cc:453-493): "*/" is put before a pattern that does not start with '*', "/"
+  /// before a name that does not start with '/'; '*' = any run of characters, '?' and '%' = any one character
+  static bool Glob(const char *p, const char *t) {
+    for (; *p; p++, t++) {
+      if (*p == '*') {
+        while (*p == '*') p++;
+        if (!*p) return true;
+        for (; *t; t++) if (Glob(p, t)) return true;
+        return false;
+      }
+      if (!*t) return false;
+      if (*p == '[') Error("character classes ([...]) in MLF record names are not built into the B200 hot path");
+      if (*p != '?' && *p != '%' && *p != *t) return false;
+    }
+    return !*t;
+  }
+  static bool MaskMatch(const std::string &name, const std::string &pattern) {
+    const std::string p = pattern[0] != '*' ? "*/" + pattern : pattern, t = name[0] != '/' ? "/" + name : name;
+    return Glob(p.c_str(), t.c_str());
+  }
+  const Record *FindInHash(const std::string &name) const {
+    std::map<std::string, Record>::const_iterator it;
+    // deepest stored depth first: the exact name (depth "infinity"), then '*' + the tail of the name from its d-th '/' from the right
+    for (std::set<size_t>::const_reverse_iterator d = mDepths.rbegin(); d != mDepths.rend(); ++d) {
+      if (*d == (size_t)-1) {
+        if ((it = mHash.find(name)) != mHash.end()) return &it->second;
+        continue;
+      }
+      size_t pos = name.size();
+      bool ok = true;
+      if (*d == 0) pos = 0;
+      else
+        for (size_t i = 0; i < *d && ok; i++) {
+          if (pos == 0) { ok = false; break; }
+          pos = name.find_last_of("/\\", pos - 1);
+          if (pos == std::string::npos) ok = false;
+        }
+      if (!ok) continue;
+      if ((it = mHash.find("*" + name.substr(pos))) != mHash.end()) return &it->second;
+    }
+    return NULL;
+  }
+  const std::vector<std::string> *Find(const std::string &name) const {
+    const Record *h = FindInHash(name);
+    const size_t limit = h ? h->mListLimit : mList.size();   // a hashed name yields to the patterns defined BEFORE it only
+    for (size_t i = 0; i < limit; i++)
+      if (MaskMatch(name, mList[i].first)) return &mList[i].second.mLines;
+    return h ? &h->mLines : NULL;
+  }
+  /// returns where the record's lines go (a scratch record when an earlier definition already covers the name)
+  std::vector<std::string> *Insert(const std::string &name) {
+    if (name.empty()) Error("Empty record name in the label MLF");
+    Record r;
+    r.mListLimit = mList.size();
+    if (name.find_first_of("*?%", 1) == std::string::npos) {
+      mDepths.insert(name[0] == '*' ? DirDepth(name) : (size_t)-1);
+      if (Find(name)) { mShadowed.mLines.clear(); return &mShadowed.mLines; }   // MlfStream.cc:76-86: the more general / earlier definition stays
+      return &(mHash[name] = r).mLines;
+    }
+    mList.push_back(std::make_pair(name, r));
+    return &mList.back().second.mLines;
+  }
+  std::map<std::string, Record> mHash;
+  std::vector<std::pair<std::string, Record> > mList;
+  std::set<size_t> mDepths;
+  Record mShadowed;
+  std::string mDir;
+  bool mHasDir, mHasExt;
   std::map<std::string, int> mLabelMap;
   std::string mExt;
   int mTrace;

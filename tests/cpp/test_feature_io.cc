@@ -42,7 +42,7 @@ int main(int argc, char **argv) {
   if (argc == 7 && !strcmp(argv[1], "--rewrite")) {
     try {
       FeatureRepository repo;
-      repo.Init(atoi(argv[5]) != 0, atoi(argv[3]), atoi(argv[4]), 0, 0, NULL, NULL, NULL, NULL, NULL, NULL);
+      repo.Init(atoi(argv[5]) != 0, atoi(argv[3]), atoi(argv[4]), FeatureRepository::ReadParmKind(getenv("TEST_TARGETKIND") ? getenv("TEST_TARGETKIND") : "ANON", false), 0, NULL, NULL, NULL, NULL, NULL, NULL);
       const char *list = "/tmp/.io_dump_entry";
       std::string tmp = std::string(argv[6]) + ".scp";
       FILE *f = fopen(tmp.c_str(), "w");
@@ -73,7 +73,7 @@ int main(int argc, char **argv) {
   try {
     FeatureRepository feature_repo;
     LabelRepository label_repo;
-    feature_repo.Init(swap, start_ext, end_ext, 0, 0, NULL, NULL, NULL, NULL, NULL, NULL);
+    feature_repo.Init(swap, start_ext, end_ext, FeatureRepository::ReadParmKind(getenv("TEST_TARGETKIND") ? getenv("TEST_TARGETKIND") : "ANON", false), 0, NULL, NULL, NULL, NULL, NULL, NULL);
     feature_repo.AddFileList(argv[1]);
     label_repo.Init(argv[2], argv[3], argc == 9 ? argv[8] : NULL, "lab");
     FILE *out = fopen(argv[7], "wb");

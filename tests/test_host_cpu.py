@@ -306,6 +306,86 @@ def test_feature_and_label_reader_errors_match_the_reference(tmp_path, case, fea
             assert open(os.path.join(d, "ref.bin"), "rb").read() == open(os.path.join(d, "mine.bin"), "rb").read()
 
 
+@pytest.mark.parametrize("case", ["same_base_two_dirs", "exact_with_label_dir", "star_depth_two", "question_mark_pattern", "first_definition_wins",
+                                  "pattern_before_hashed_name", "bare_name_vs_star_pattern", "no_match_in_other_dir"])
+def test_mlf_record_lookup_rules_match_the_reference(tmp_path, case, feature_io_exe):
+    """Which MLF record an utterance gets (SOURCETRANSCDIR / SOURCETRANSCEXT applied to the logical feature name, then the reference's
+    record index: exact names and '*/tail' names hashed, other wildcards in file order, first definition wins — MlfStream.cc:40-270,
+    Labels.cc:52) — differential against the reference's own readers; the expected ids are also stated here."""
+    d = str(tmp_path)
+    r = np.random.default_rng(5)
+    open(os.path.join(d, "map"), "w").write("s0\ns1\ns2\n")
+    feas = []
+    for k in range(2):
+        fea = os.path.join(d, "f%d.fea" % k)
+        F.write_htk(fea, r.standard_normal((6, 4)).astype(np.float32))
+        feas.append(fea)
+    rec = lambda name, tag: '"%s"\n0 600000 %s\n.\n' % (name, tag)
+    ldir, expect = None, None
+    if case == "same_base_two_dirs":          # ids follow the directory of the logical name, not just its base name
+        scp = ["a/utt.fea=" + feas[0], "b/utt.fea=" + feas[1]]
+        mlf = rec("b/utt.lab", "s2") + rec("a/utt.lab", "s1")
+        expect = [1, 2]
+    elif case == "exact_with_label_dir":      # -L labs/x: the directory replaces the logical name's
+        scp = ["a/utt.fea=" + feas[0], "b/other.fea=" + feas[1]]
+        mlf = rec("labs/x/utt.lab", "s1") + rec("labs/x/other.lab", "s2")
+        ldir, expect = "labs/x", [1, 2]
+    elif case == "star_depth_two":            # '*' + the tail from the second '/' from the right
+        scp = ["top/a/utt.fea=" + feas[0], "top/b/utt.fea=" + feas[1]]
+        mlf = rec("*/a/utt.lab", "s0") + rec("*/b/utt.lab", "s2")
+        expect = [0, 2]
+    elif case == "question_mark_pattern":
+        scp = ["utt1_x.fea=" + feas[0], "utt2_x.fea=" + feas[1]]
+        mlf = rec("*/utt?_x.lab", "s1")
+        expect = [1, 1]
+    elif case == "first_definition_wins":
+        scp = ["x/utt.fea=" + feas[0], "x/w.fea=" + feas[1]]
+        mlf = rec("*/utt.lab", "s2") + rec("*/utt.lab", "s0") + rec("*/w.lab", "s1")
+        expect = [2, 1]
+    elif case == "pattern_before_hashed_name":    # a wildcard pattern defined before a hashed name that it also matches takes the utterance
+        scp = ["x/utt.fea=" + feas[0], "x/w.fea=" + feas[1]]
+        mlf = rec("*/u?t.lab", "s1") + rec("*/utt.lab", "s2") + rec("*/w.lab", "s0")
+        expect = [1, 0]
+    elif case == "bare_name_vs_star_pattern":     # the hashed "*/utt.lab" is looked up as '*' + the tail from a '/': a name without one finds nothing
+        scp = ["utt.fea=" + feas[0]]
+        mlf = rec("*/utt.lab", "s1")
+    else:                                      # an exact name in another directory does not match
+        scp = ["a/utt.fea=" + feas[0]]
+        mlf = rec("b/utt.lab", "s1")
+    open(os.path.join(d, "a.scp"), "w").write("\n".join(scp) + "\n")
+    open(os.path.join(d, "a.mlf"), "w").write("#!MLF!#\n" + mlf)
+    args = [os.path.join(d, "a.scp"), os.path.join(d, "a.mlf"), os.path.join(d, "map"), "0", "0", "1"]
+    tail = [ldir] if ldir is not None else []
+    mine = subprocess.run([feature_io_exe] + args + [os.path.join(d, "mine.bin")] + tail, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert (mine.returncode == 0) == (expect is not None), mine.stderr[-500:]
+    if expect is not None:
+        got = _parse_io_dump(os.path.join(d, "mine.bin"))
+        assert [int(g[3][0]) for g in got] == expect and all((g[3] == g[3][0]).all() for g in got)
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "RefIoDump")
+    if os.path.exists(ref_exe):
+        ref = subprocess.run([ref_exe] + args + [os.path.join(d, "ref.bin")] + tail, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert (ref.returncode == 0) == (mine.returncode == 0), (ref.returncode, mine.returncode, ref.stderr[-300:], mine.stderr[-300:])
+        if expect is not None:
+            assert open(os.path.join(d, "ref.bin"), "rb").read() == open(os.path.join(d, "mine.bin"), "rb").read()
+
+
+@pytest.mark.parametrize("kind,ok", [("ANON", True), ("USER", True), ("USER_Z", False), ("MFCC", False), ("USER_D_A", False), ("ANON_Z", False)])
+def test_target_kind_that_needs_a_conversion_is_refused(tmp_path, kind, ok, feature_io_exe):
+    """The reader converts nothing: TARGETKIND must be ANON or describe the file as it is (the cases where the reference's conversion,
+    Features.cc:1120-1178, is the identity); _Z / energy / derivative requests and other base kinds fail instead of being ignored."""
+    d = str(tmp_path)
+    fea = os.path.join(d, "a.fea")
+    F.write_htk(fea, np.random.default_rng(7).standard_normal((6, 4)).astype(np.float32))      # kind USER (9)
+    open(os.path.join(d, "map"), "w").write("s0\n")
+    open(os.path.join(d, "a.scp"), "w").write(fea + "\n")
+    open(os.path.join(d, "a.mlf"), "w").write('#!MLF!#\n"*/a.lab"\n0 600000 s0\n.\n')
+    r = subprocess.run([feature_io_exe, os.path.join(d, "a.scp"), os.path.join(d, "a.mlf"), os.path.join(d, "map"), "0", "0", "1", os.path.join(d, "o.bin"), "*/"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=dict(os.environ, TEST_TARGETKIND=kind))
+    assert (r.returncode == 0) == ok, r.stderr[-400:]
+    if not ok:
+        assert b"Cannot convert parameter kind" in r.stderr
+
+
 def _config_block(txt):
     lines = txt.splitlines()
     at = [k for k, l in enumerate(lines) if l.startswith("Configuration Parameters[")]
