@@ -112,6 +112,8 @@ struct TnbContext_ {
   unsigned *peer_flags[TNB_MAX_PEERS] = {};
   unsigned peer_seq = 0;
   unsigned push_seq = 0;   // tnb_peer_push_blocks calls (trace slots)
+  cudaStream_t push_streams[TNB_MAX_PEERS] = {};  // tnb_peer_push_blocks: one stream (one copy engine at a time) per destination rank
+  cudaEvent_t push_events[TNB_MAX_PEERS] = {};
   void *peer_trace = nullptr;   // TNB_DP_TRACE=1: %globaltimer stamps of the last 64 peer-memory kernels (tnb_peer_trace_read)
 };
 

@@ -241,6 +241,10 @@ int tnb_ctx_destroy(TnbContext *ctx) {
   for (auto &kv : ctx->mg_plans) if (kv.second.dlist) cudaFree(kv.second.dlist);
   if (ctx->mg_trace) cudaFree(ctx->mg_trace);
   if (ctx->peer_trace) cudaFree(ctx->peer_trace);
+  for (int i = 0; i < TNB_MAX_PEERS; i++) {
+    if (ctx->push_streams[i]) cudaStreamDestroy(ctx->push_streams[i]);
+    if (ctx->push_events[i]) cudaEventDestroy(ctx->push_events[i]);
+  }
   delete ctx;
   return TNB_OK;
 }

@@ -184,6 +184,16 @@ __global__ void __launch_bounds__(512) dp_peer_update_kernel(const __grid_consta
   peer_update_body<WORLD, U>(a, (int)blockIdx.x, (int)gridDim.x);
 }
 
+// "Spread" shape (TNB_DP_PEER_SPREAD=1; measured equal or slightly slower than the shape above at 4 GPUs): one SMALL CTA per SM — 128 threads, at most 64 registers, no shared memory — so that a
+// CTA of this kernel fits NEXT TO a GEMM CTA on the same SM (the GEMMs take 320 threads x <= 168 registers, ~200 KB of shared memory and
+// the SM's TMEM; they leave ~10 K registers and all the issue slots their waiting warps do not use).  The 20 x 512-thread shape above
+// needs SMs of its own: a GEMM grid that arrives while it runs finds 128 SMs instead of 148, which a 4-CTA-cluster launch does not
+// always fit in one wave (measured: the forward GEMMs next to the deferred exchanges ran 20 % slower, profiles/r02_dp_timeline.md).
+template <int WORLD>
+__global__ void __launch_bounds__(128, 8) dp_peer_update_spread_kernel(const __grid_constant__ PeerArgs a) {
+  peer_update_body<WORLD, 1>(a, (int)blockIdx.x, (int)gridDim.x);
+}
+
 // All ranks of a layer's exchange as ONE grid on one GPU (tests, ncu): CTAs [v*ctas, (v+1)*ctas) play rank v with args[v].  Launched
 // cooperatively, so that every CTA is resident while the slices wait for each other's flags.
 template <int WORLD, int U>
@@ -265,6 +275,20 @@ static int launch_peer_update(TnbContext *ctx, cudaStream_t stream, const TnbPee
   if (rc != TNB_OK) return rc;
   if (peer_trace_buffer(ctx) != TNB_OK) return TNB_ERR_CUDA;
   a.trace = (long long *)ctx->peer_trace;
+  static int spread = -1;
+  if (spread < 0) { const char *e = getenv("TNB_DP_PEER_SPREAD"); spread = e ? atoi(e) : 0; }
+  if (spread && world > 1 && (world == 2 || world == 4 || world == 8)) {
+    const long items = (long)a.shard * ((a.cols + 3) / 4);
+    long nb = spread > 1 ? spread : ctx->sm_count;   // TNB_DP_PEER_SPREAD=n (> 1): n CTAs instead of one per SM
+    if (nb > (items + 127) / 128) nb = (items + 127) / 128;
+    if (nb < 1) nb = 1;
+    const dim3 grid((unsigned)nb), block(128);
+    if (world == 2) dp_peer_update_spread_kernel<2><<<grid, block, 0, stream>>>(a);
+    else if (world == 4) dp_peer_update_spread_kernel<4><<<grid, block, 0, stream>>>(a);
+    else dp_peer_update_spread_kernel<8><<<grid, block, 0, stream>>>(a);
+    TNB_LAUNCHED(ctx);
+    return TNB_OK;
+  }
   const dim3 grid((unsigned)blocks), block(512);
   switch (world) {
     case 1: dp_peer_update_kernel<1, 4><<<grid, block, 0, stream>>>(a); break;
@@ -396,11 +420,27 @@ int tnb_peer_push_blocks(TnbContext *ctx, int stream_id, const float *G, float *
   long long *tr = ctx->peer_trace ? (long long *)ctx->peer_trace + 256 + (ctx->push_seq++ & 63u) * 2 : nullptr;
   if (tr) peer_stamp_kernel<<<1, 1, 0, s>>>(tr);
   const size_t shard = (size_t)(rows_pad / world), block = shard * (size_t)dG.stride;  // floats: whole rows, hence contiguous
-  // the farthest-first order spreads the ranks' copies over different destinations at any one time (rank r starts with r + 1)
+  // One stream per destination: copies to different ranks run on different copy engines at the same time (one stream alone moves a
+  // 4 MB block at 150-250 GB/s, measured: profiles/r02_dp_timeline.md).  TNB_DP_PUSH_STREAMS=0: all copies on `s`, one after the other.
+  static int fan = -1;
+  if (fan < 0) { const char *e = getenv("TNB_DP_PUSH_STREAMS"); fan = (e && atoi(e) == 0) ? 0 : 1; }
   for (int k = 1; k <= world; k++) {
-    const int o = (rank + k) % world;
+    const int o = (rank + k) % world;  // rank r starts with r + 1: the ranks' copies go to different destinations at any one time
     TNB_ARG(Gpeers[o] != nullptr, "null peer pointer");
-    TNB_CUDA(cudaMemcpyAsync(Gpeers[o] + (size_t)rank * block, G + (size_t)o * block, block * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    cudaStream_t cs = s;
+    if (fan && o != rank && !ctx->capturing) {
+      if (!ctx->push_streams[o]) {
+        TNB_CUDA(cudaStreamCreateWithFlags(&ctx->push_streams[o], cudaStreamNonBlocking));
+        TNB_CUDA(cudaEventCreateWithFlags(&ctx->push_events[o], cudaEventDisableTiming));
+      }
+      cs = ctx->push_streams[o];
+      if (wait_event) TNB_CUDA(cudaStreamWaitEvent(cs, (cudaEvent_t)wait_event, 0));
+    }
+    TNB_CUDA(cudaMemcpyAsync(Gpeers[o] + (size_t)rank * block, G + (size_t)o * block, block * sizeof(float), cudaMemcpyDeviceToDevice, cs));
+    if (cs != s) {
+      TNB_CUDA(cudaEventRecord(ctx->push_events[o], cs));
+      TNB_CUDA(cudaStreamWaitEvent(s, ctx->push_events[o], 0));
+    }
   }
   if (tr) peer_stamp_kernel<<<1, 1, 0, s>>>(tr + 1);
   if (done_event) TNB_CUDA(cudaEventRecord((cudaEvent_t)done_event, s));

@@ -144,7 +144,7 @@ class CuBiasedLinearity : public CuUpdatableComponent {
  public:
   CuBiasedLinearity(size_t nInputs, size_t nOutputs, CuComponent *pPred)
       : CuUpdatableComponent(nInputs, nOutputs, pPred), mLinearity(nInputs, nOutputs), mBias(nOutputs),
-        mLinearityCorrection(nInputs, nOutputs), mBiasCorrection(nOutputs), mDpFrames(0), mRowsPad(0), mEvE(NULL), mEvB(NULL), mEvAR(NULL), mEvDone(NULL), mEvG(NULL), mEvPush(NULL), mDpPending(false), mPeerMapped(false) {}
+        mLinearityCorrection(nInputs, nOutputs), mBiasCorrection(nOutputs), mDpFrames(0), mRowsPad(0), mEvE(NULL), mEvB(NULL), mEvAR(NULL), mEvDone(NULL), mEvG(NULL), mEvPush(NULL), mPushMode(-1), mDpPending(false), mPeerMapped(false) {}
   ~CuBiasedLinearity() {
     if (mEvE) { tnb_event_destroy(Cx(), mEvE); tnb_event_destroy(Cx(), mEvB); tnb_event_destroy(Cx(), mEvAR); tnb_event_destroy(Cx(), mEvDone); }
     if (mEvG) { tnb_event_destroy(Cx(), mEvG); tnb_event_destroy(Cx(), mEvPush); }
@@ -315,7 +315,7 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     TnbBiasJob bj = {E.pCUData(), E.Dim(), NULL, mGrad.pCURowData(mRowsPad), 0.0f, 0.0f, 0, 0};  // gradient only
     TNB_CHECK(tnb_bias_update_batch_on(Cx(), TNB_STREAM_AUX, &bj, 1));
     TNB_CHECK(tnb_event_record(Cx(), mEvB, TNB_STREAM_AUX));
-    const int push = mPeerMapped ? DpPush() : 0;
+    const int push = mPeerMapped ? PushMode() : 0;
     if (push == 1) {
       // GEMM -> reduce-scatter in one kernel: the tiles of dW go straight to the owning ranks' staging slices over NVLink
       const CuMatrix<BaseFloat> &X = GetInput();
@@ -345,6 +345,10 @@ class CuBiasedLinearity : public CuUpdatableComponent {
       }
     }
   }
+  /// this layer's way of moving its gradient blocks (TNB_DP_PUSH values); CuNetwork gives the lowest layers, whose exchange is the
+  /// exposed tail of the step, the GEMM-epilogue push (no copy-engine latency between the GEMM and the update kernel)
+  int PushMode() const { return mPushMode >= 0 ? mPushMode : DpPush(); }
+  void SetPushMode(int m) { if (mPeerMapped) Error("SetPushMode after PreparePeer"); mPushMode = m; }
   /// the event behind this layer's gradient GEMM on the compute stream (peer-memory schedule), NULL otherwise
   void *GradientEvent() { return mPeerMapped ? mEvG : NULL; }
   /// TNB_DP_PUSH: how a rank's gradient blocks reach their owners in the peer-memory schedule — 2 (default): copy engines behind a
@@ -371,7 +375,7 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     TNB_CHECK(tnb_peer_map(Cx(), mLinearity.pCUData(), mWPeers));
     mGrad.MarkExported();
     mLinearity.MarkExported();
-    if (DpPush() == 2) mGradLocal.Init(mRowsPad, mNOutputs);  // padded rows stay zero
+    if (PushMode() == 2) mGradLocal.Init(mRowsPad, mNOutputs);  // padded rows stay zero
     mPeerMapped = true;
   }
   /// second half, peer-memory schedule: ONE kernel on the communication stream sums this rank's block of rows over all ranks'
@@ -385,8 +389,8 @@ class CuBiasedLinearity : public CuUpdatableComponent {
     j.corrW = mLinearityCorrection.pCUData(); j.bias = mBias.pCUData(); j.corrb = mBiasCorrection.pCUData();
     j.dW = mLinearity.Dim(); j.rows_pad = (int)mRowsPad;
     j.lr = mLearningRate; j.mmt = mMomentum; j.wc = mWeightcost; j.grad_div_frm = mGradDivFrm ? 1 : 0; j.n_frames = n_frames_global;
-    j.pushed = DpPush() ? 1 : 0;
-    void *waits[2] = {DpPush() == 2 ? mEvPush : mEvG, mEvB};  // the gradient (pushed, or complete where it is) and the bias gradient
+    j.pushed = PushMode() ? 1 : 0;
+    void *waits[2] = {PushMode() == 2 ? mEvPush : mEvG, mEvB};  // the gradient (pushed, or complete where it is) and the bias gradient
     TNB_CHECK(tnb_dp_peer_update_after(Cx(), &j, waits, 2, mEvDone));
     mDpPending = true;
   }
@@ -467,6 +471,7 @@ class CuBiasedLinearity : public CuUpdatableComponent {
   size_t mRowsPad;
   void *mEvE, *mEvB, *mEvAR, *mEvDone;  ///< data-parallel stream ordering (created on first use)
   void *mEvG, *mEvPush;                 ///< peer-memory schedule: behind the gradient GEMM (compute stream) / behind the copy engines' pushes
+  int mPushMode;                        ///< -1 = DpPush()
   mutable bool mDpPending;              ///< an update of this layer is in flight on the side streams
   bool mPeerMapped;                     ///< peer-memory schedule: the tables below are filled
   void *mGradPeers[TNB_MAX_PEERS], *mWPeers[TNB_MAX_PEERS];  ///< every rank's mGrad / mLinearity as mapped into this process
@@ -1008,9 +1013,20 @@ class CuNetwork {
     if (d) { int a = 0, b = 0; if (sscanf(d, "%d:%d", &a, &b) == 2) { mDpDeferBegin = a; mDpDeferEnd = b; } }
     for (size_t i = 0; i < mNetComponents.size(); i++)
       if (mNetComponents[i]->GetType() == CuComponent::BIASED_LINEARITY) static_cast<CuBiasedLinearity *>(mNetComponents[i])->PrepareDataParallel(world);
-    if (mDpPeer)
+    if (mDpPeer) {
+      // TNB_DP_PUSH_TAIL=n (default 2): the n lowest layers push from the GEMM epilogue when the others use the copy engines
+      int tail = 2;
+      const char *t = getenv("TNB_DP_PUSH_TAIL");
+      if (t) tail = atoi(t);
+      for (size_t i = 0; i < mNetComponents.size() && tail > 0; i++)
+        if (mNetComponents[i]->GetType() == CuComponent::BIASED_LINEARITY) {
+          CuBiasedLinearity *lin = static_cast<CuBiasedLinearity *>(mNetComponents[i]);
+          if (lin->PushMode() == 2) lin->SetPushMode(1);
+          tail--;
+        }
       for (size_t i = 0; i < mNetComponents.size(); i++)
         if (mNetComponents[i]->GetType() == CuComponent::BIASED_LINEARITY) static_cast<CuBiasedLinearity *>(mNetComponents[i])->PreparePeer();
+    }
   }
 
   /// forward the data to the output (cuNetwork.h:137-165)
