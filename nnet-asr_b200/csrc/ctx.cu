@@ -241,6 +241,7 @@ int tnb_ctx_destroy(TnbContext *ctx) {
   for (auto &kv : ctx->mg_plans) if (kv.second.dlist) cudaFree(kv.second.dlist);
   if (ctx->mg_trace) cudaFree(ctx->mg_trace);
   if (ctx->peer_trace) cudaFree(ctx->peer_trace);
+  if (ctx->done_stream) { cudaStreamDestroy(ctx->done_stream); cudaEventDestroy(ctx->ev_done_fork); }
   for (int i = 0; i < TNB_MAX_PEERS; i++) {
     if (ctx->push_streams[i]) cudaStreamDestroy(ctx->push_streams[i]);
     if (ctx->push_events[i]) cudaEventDestroy(ctx->push_events[i]);
@@ -272,6 +273,9 @@ int tnb_ctx_sync(TnbContext *ctx) {
   TNB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
   TNB_CUDA(cudaStreamSynchronize(ctx->aux_stream));
   TNB_CUDA(cudaStreamSynchronize(ctx->aux2_stream));
+  if (ctx->done_stream) TNB_CUDA(cudaStreamSynchronize(ctx->done_stream));
+  for (int i = 0; i < TNB_MAX_PEERS; i++)
+    if (ctx->push_streams[i]) TNB_CUDA(cudaStreamSynchronize(ctx->push_streams[i]));
   return ctx->peer_flags[ctx->rank] ? tnb_peer_status(ctx) : TNB_OK;  // a peer-memory kernel that gave up waiting says so here
 }
 int tnb_ctx_free_memory(TnbContext *ctx, size_t *fr, size_t *tot) {

@@ -42,6 +42,7 @@ struct PeerArgs {
   int pushed;        // the gradients were pushed into the owners' staging slices (tnb_affine_grad_scatter): G[rank] holds `world` local slices
   unsigned seq;
   long long timeout;  // cycles; 0 = wait for ever
+  int defer_done;     // leave once this rank's done flag is published: a dp_peer_wait_done_kernel on another stream waits for the other ranks'
   long long *trace;   // TNB_DP_TRACE=1: [64 launches][4] %globaltimer stamps of CTA 0 (entry, all ranks ready, own rows done) and of the last CTA (all ranks done)
 };
 
@@ -168,8 +169,15 @@ __device__ __forceinline__ void peer_update_body(const PeerArgs &a, const int bi
   if (threadIdx.x == 0) my[32] = 0;  // for the next launch (which starts after this kernel has ended)
   __threadfence_system();
   if ((int)threadIdx.x < world) st_release_sys(a.flags[threadIdx.x] + 16 + a.rank, a.seq);
-  wait_flags(my, 16, world, a.seq, a.timeout);
+  if (!a.defer_done) wait_flags(my, 16, world, a.seq, a.timeout);
   peer_stamp(a, 3);
+}
+
+// The second half of a kernel launched with defer_done: one warp that waits until every rank's done flag has reached `seq` (all
+// blocks of this rank's weights have been written, nobody reads its gradient buffer any more).  It runs on its own stream, so the
+// communication stream goes on with the next layer's kernel instead of idling through a cross-GPU round trip per layer.
+__global__ void __launch_bounds__(32) dp_peer_wait_done_kernel(unsigned *my, int world, unsigned seq, long long timeout) {
+  wait_flags(my, 16, world, seq, timeout);
 }
 
 // TNB_DP_TRACE=1: a one-thread kernel that leaves %globaltimer in *p (stream-ordered marker around the copy engines' pushes)
@@ -267,7 +275,7 @@ static int peer_trace_buffer(TnbContext *ctx) {
 }
 
 static int launch_peer_update(TnbContext *ctx, cudaStream_t stream, const TnbPeerJob *job, int rank, int world, unsigned *const *flags,
-                              unsigned seq) {
+                              unsigned seq, int defer_done = 0) {
   TNB_ARG(ctx != nullptr, "null");
   PeerArgs a;
   long blocks = 1;
@@ -275,6 +283,7 @@ static int launch_peer_update(TnbContext *ctx, cudaStream_t stream, const TnbPee
   if (rc != TNB_OK) return rc;
   if (peer_trace_buffer(ctx) != TNB_OK) return TNB_ERR_CUDA;
   a.trace = (long long *)ctx->peer_trace;
+  a.defer_done = defer_done;
   static int spread = -1;
   if (spread < 0) { const char *e = getenv("TNB_DP_PEER_SPREAD"); spread = e ? atoi(e) : 0; }
   if (spread && world > 1 && (world == 2 || world == 4 || world == 8)) {
@@ -402,9 +411,27 @@ int tnb_dp_peer_update_after(TnbContext *ctx, const TnbPeerJob *job, void *const
   if (rc != TNB_OK) return rc;
   for (int i = 0; i < n_wait; i++)
     if (wait_events[i]) TNB_CUDA(cudaStreamWaitEvent(cs, (cudaEvent_t)wait_events[i], 0));
-  rc = launch_peer_update(ctx, cs, job, ctx->rank, ctx->world, ctx->peer_flags, ++ctx->peer_seq);
+  static int split_done = -1;
+  // TNB_DP_SPLIT_DONE=1: the wait for the other ranks' done flags as a separate one-warp kernel on its own stream.  Measured SLOWER at
+  // 4 GPUs (1.063 against 1.040 ms per bunch): what a kernel spends after its own rows is mostly the tail of its own CTAs, and two
+  // layers' kernels running at once slow each other down.  Off by default.
+  if (split_done < 0) { const char *e = getenv("TNB_DP_SPLIT_DONE"); split_done = (e && atoi(e) != 0) ? 1 : 0; }
+  const bool split = split_done && !ctx->capturing;
+  rc = launch_peer_update(ctx, cs, job, ctx->rank, ctx->world, ctx->peer_flags, ++ctx->peer_seq, split ? 1 : 0);
   if (rc != TNB_OK) return rc;
-  if (done_event) TNB_CUDA(cudaEventRecord((cudaEvent_t)done_event, cs));
+  if (!split) {
+    if (done_event) TNB_CUDA(cudaEventRecord((cudaEvent_t)done_event, cs));
+    return TNB_OK;
+  }
+  if (!ctx->done_stream) {
+    TNB_CUDA(cudaStreamCreateWithFlags(&ctx->done_stream, cudaStreamNonBlocking));
+    TNB_CUDA(cudaEventCreateWithFlags(&ctx->ev_done_fork, cudaEventDisableTiming));
+  }
+  TNB_CUDA(cudaEventRecord(ctx->ev_done_fork, cs));
+  TNB_CUDA(cudaStreamWaitEvent(ctx->done_stream, ctx->ev_done_fork, 0));
+  dp_peer_wait_done_kernel<<<1, 32, 0, ctx->done_stream>>>(ctx->peer_flags[ctx->rank], ctx->world, ctx->peer_seq, peer_timeout_cycles());
+  TNB_LAUNCHED(ctx);
+  if (done_event) TNB_CUDA(cudaEventRecord((cudaEvent_t)done_event, ctx->done_stream));
   return TNB_OK;
 }
 
