@@ -426,7 +426,9 @@ int tnb_dp_peer_update_after(TnbContext *ctx, const TnbPeerJob *job, void *const
 /* Gradient push by the copy engines instead of by the GEMM epilogue: block o (rows [o*rows_pad/world, (o+1)*rows_pad/world)) of
  * this rank's full gradient G [rows_pad x dG.stride] goes to slice `rank` of rank o's staging buffer Gpeers[o] (tnb_peer_map of the
  * ranks' [(rows_pad + 1) x dG.stride] buffers), as `world` device-to-device copies on stream `stream_id` behind `wait_event`;
- * `done_event` is recorded behind them.  No SM is involved and the gradient GEMM's epilogue stores stay local. */
+ * `done_event` is recorded behind them.  The copies are ordered behind everything enqueued on `stream_id` before the call (they may
+ * run on per-destination streams of the context, which fork from and join `stream_id`).  No SM is involved and the gradient GEMM's
+ * epilogue stores stay local. */
 int tnb_peer_push_blocks(TnbContext *ctx, int stream_id, const float *G, float *const *Gpeers, int world, int rank, TnbMatrixDim dG,
                          int rows_pad, void *wait_event, void *done_event);
 /* the same kernel for an explicit rank / world / flag blocks (64 zero-initialised words per rank) / sequence number (1, 2, ... per

@@ -114,6 +114,7 @@ struct TnbContext_ {
   unsigned push_seq = 0;   // tnb_peer_push_blocks calls (trace slots)
   cudaStream_t push_streams[TNB_MAX_PEERS] = {};  // tnb_peer_push_blocks: one stream (one copy engine at a time) per destination rank
   cudaEvent_t push_events[TNB_MAX_PEERS] = {};
+  cudaEvent_t ev_push_fork = nullptr;
   cudaStream_t done_stream = nullptr;   // tnb_dp_peer_update_after: the kernels that wait for the other ranks' done flags
   cudaEvent_t ev_done_fork = nullptr;
   void *peer_trace = nullptr;   // TNB_DP_TRACE=1: %globaltimer stamps of the last 64 peer-memory kernels (tnb_peer_trace_read)

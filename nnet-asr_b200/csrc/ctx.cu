@@ -242,6 +242,7 @@ int tnb_ctx_destroy(TnbContext *ctx) {
   if (ctx->mg_trace) cudaFree(ctx->mg_trace);
   if (ctx->peer_trace) cudaFree(ctx->peer_trace);
   if (ctx->done_stream) { cudaStreamDestroy(ctx->done_stream); cudaEventDestroy(ctx->ev_done_fork); }
+  if (ctx->ev_push_fork) cudaEventDestroy(ctx->ev_push_fork);
   for (int i = 0; i < TNB_MAX_PEERS; i++) {
     if (ctx->push_streams[i]) cudaStreamDestroy(ctx->push_streams[i]);
     if (ctx->push_events[i]) cudaEventDestroy(ctx->push_events[i]);

@@ -451,6 +451,7 @@ int tnb_peer_push_blocks(TnbContext *ctx, int stream_id, const float *G, float *
   // 4 MB block at 150-250 GB/s, measured: profiles/r02_dp_timeline.md).  TNB_DP_PUSH_STREAMS=0: all copies on `s`, one after the other.
   static int fan = -1;
   if (fan < 0) { const char *e = getenv("TNB_DP_PUSH_STREAMS"); fan = (e && atoi(e) == 0) ? 0 : 1; }
+  bool forked = false;
   for (int k = 1; k <= world; k++) {
     const int o = (rank + k) % world;  // rank r starts with r + 1: the ranks' copies go to different destinations at any one time
     TNB_ARG(Gpeers[o] != nullptr, "null peer pointer");
@@ -461,7 +462,12 @@ int tnb_peer_push_blocks(TnbContext *ctx, int stream_id, const float *G, float *
         TNB_CUDA(cudaEventCreateWithFlags(&ctx->push_events[o], cudaEventDisableTiming));
       }
       cs = ctx->push_streams[o];
-      if (wait_event) TNB_CUDA(cudaStreamWaitEvent(cs, (cudaEvent_t)wait_event, 0));
+      if (!forked) {  // the destination streams start where `s` stands now (behind wait_event and everything enqueued on `s` before)
+        if (!ctx->ev_push_fork) TNB_CUDA(cudaEventCreateWithFlags(&ctx->ev_push_fork, cudaEventDisableTiming));
+        TNB_CUDA(cudaEventRecord(ctx->ev_push_fork, s));
+        forked = true;
+      }
+      TNB_CUDA(cudaStreamWaitEvent(cs, ctx->ev_push_fork, 0));
     }
     TNB_CUDA(cudaMemcpyAsync(Gpeers[o] + (size_t)rank * block, G + (size_t)o * block, block * sizeof(float), cudaMemcpyDeviceToDevice, cs));
     if (cs != s) {

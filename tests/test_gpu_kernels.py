@@ -478,14 +478,17 @@ def test_gradient_gemm_with_fused_reduce_scatter_virtual_ranks(ctx, world, math)
         ctx.set_math(abi.MATH_3XTF32)
 
 
+@pytest.mark.parametrize("push", ["epilogue", "copy_engine"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_whole_data_parallel_step_with_virtual_ranks_equals_single_rank_step(ctx, world):
+def test_whole_data_parallel_step_with_virtual_ranks_equals_single_rank_step(ctx, world, push):
     """N-rank equivalence on ONE GPU: a whole training step of a 429-512-384-300 network (three <biasedlinearity> layers, sigmoid /
     sigmoid / softmax) run as `world` virtual ranks — every rank forward, objective (class ids) and backward on its rows
     [g*B/N, (g+1)*B/N) of the bunch, gradient GEMMs with the fused reduce-scatter into the owners' staging slices, bias gradients,
     then per layer ONE cooperative grid playing all ranks' peer-memory update kernels — against the single-rank step on the whole
     bunch (fused update GEMMs).  Every rank must hold the single-rank step's weights and biases (summation-order tolerance) and the
-    ranks' cross-entropy / accuracy counters must add up to the single rank's."""
+    ranks' cross-entropy / accuracy counters must add up to the single rank's.  push = "epilogue": tnb_affine_grad_scatter (peer
+    stores of the GEMM epilogue); "copy_engine": tnb_affine_grad into the rank's own full gradient, then tnb_peer_push_blocks (the
+    default of the upper layers with several GPUs)."""
     r = rng(500 + world)
     dims, B = [429, 512, 384, 300], 256
     lr, mmt, wc = 0.2, 0.5, 1e-4
@@ -543,8 +546,15 @@ def test_whole_data_parallel_step_with_virtual_ranks_equals_single_rank_step(ctx
         acts, errs, stg = fwd_bwd(Xg, lg, Wg, br[g], rows)
         for i in range(3):
             gp = (C.POINTER(C.c_float) * world)(*[Gr[q][i].p() for q in range(world)])
-            abi.check(L.tnb_affine_grad_scatter(ctx.h, acts[i].p(), acts[i].dim, errs[i].p(), errs[i].dim, None, C.c_int(0), None, C.c_int(0), gp,
-                                                C.c_int(world), C.c_int(g), abi.MatrixDim(dims[i], dims[i + 1], Wr[g][i].stride), C.c_int(pads[i])))
+            dG = abi.MatrixDim(dims[i], dims[i + 1], Wr[g][i].stride)
+            if push == "epilogue":
+                abi.check(L.tnb_affine_grad_scatter(ctx.h, acts[i].p(), acts[i].dim, errs[i].p(), errs[i].dim, None, C.c_int(0), None, C.c_int(0), gp,
+                                                    C.c_int(world), C.c_int(g), dG, C.c_int(pads[i])))
+            else:
+                Gloc = abi.DMat(ctx, pads[i], dims[i + 1])                     # zero-filled: the padded rows stay zero
+                assert Gloc.stride == Wr[g][i].stride
+                abi.check(L.tnb_affine_grad(ctx.h, acts[i].p(), acts[i].dim, errs[i].p(), errs[i].dim, Gloc.p(), dG, None))
+                abi.check(L.tnb_peer_push_blocks(ctx.h, C.c_int(0), Gloc.p(), gp, C.c_int(world), C.c_int(g), dG, C.c_int(pads[i]), None, None))
             brow = C.cast(C.c_void_p(Gr[g][i].ptr.value + 4 * pads[i] * Gr[g][i].stride), C.POINTER(C.c_float))
             abi.check(L.tnb_add_col_sum(ctx.h, C.c_float(1.0), errs[i].p(), C.c_float(0.0), brow, errs[i].dim))
         ctx.sync()
