@@ -8,12 +8,12 @@ Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 
 bunch 1024 PER GPU, synthetic N(0,1) features and uniform labels, random-init weights (W~0.1*N(0,1), hidden bias
 U[-4.1,-3.9]), learning rate 0.008 / momentum 0.5 / weightcost 1e-6, GRADDIVFRM on.  A step = one bunch: CuCache::GetBunch
 row window, forward, fused softmax+cross-entropy+accuracy, backward, momentum/L2 update.  Data parallel: every rank owns
-its rows of the (N x 1024)-frame global bunch, per-layer [dW|db] is summed with NCCL, N in the update rule is the global
+its rows of the (N x 1024)-frame global bunch, per-layer [dW|db] is summed over NVLink peer memory (csrc/peer.cu), N in the update rule is the global
 frame count ("scaling": "weak").
 
 One JSON line on stdout (rank 0).  `value` = frames/s with the training set resident in HBM; `e2e` = the same through
 the host-buffer entry points (pinned host features + int labels copied H2D every step, statistics read back D2H every
-step, one submission kept in flight so that the copy of the next bunch overlaps the current step); `roofline` = algorithmic GEMM flops / CUDA-event time of the tcgen05 GEMM launches of a second pass over the same K steps (an
+step, one submission kept in flight (three with several ranks) so that the copy of the next bunch overlaps the current step); `roofline` = algorithmic GEMM flops / CUDA-event time of the tcgen05 GEMM launches of a second pass over the same K steps (an
 event pair around every launch; separate from the pass `value` is timed on, where consecutive GEMMs overlap by PDL);
 `cpu_baseline` = the reference CPU trainer on a bounded sample of the same workload (rank 0, N=1 only).
 """
@@ -555,17 +555,26 @@ def main():
     # result is read by the host; the copy of bunch k+1 overlaps the step of bunch k, as a loader thread would arrange it.
     host_t = {"submit": 0.0, "collect": 0.0}   # host time inside the two calls (diagnostic: enqueue cost vs waiting for the GPU)
 
+    # submissions kept in flight behind the one being collected: one is enough on a single GPU; with several ranks a host thread
+    # that is late by a fraction of a millisecond would otherwise stall its GPU and, at the next exchange, every other rank's
+    E2E_DEPTH = 1 if world == 1 else 3
+
     def e2e_run(n):
         host_t["submit"] = host_t["collect"] = 0.0
-        net.submit_bunch_labels(xp, lp, bunch)
-        for _ in range(n - 1):
+        ahead = min(E2E_DEPTH, n)
+        for _ in range(ahead):
+            net.submit_bunch_labels(xp, lp, bunch)
+        st_ = None
+        for _ in range(n - ahead):
             ta = time.perf_counter()
             net.submit_bunch_labels(xp, lp, bunch)
             tb = time.perf_counter()
-            net.collect()
+            st_ = net.collect()
             host_t["submit"] += tb - ta
             host_t["collect"] += time.perf_counter() - tb
-        return net.collect()
+        for _ in range(ahead):
+            st_ = net.collect()
+        return st_
 
     e2e_run(3)
     e2e_s, st = [], None
@@ -651,10 +660,10 @@ def main():
                        "flops_per_frame": fpf, "gemm_math": args.math},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": bunch * DIMS[0] * 4 + bunch * 4,
-                    "d2h_bytes_per_step": 24, "windows_s": e2e_s,
+                    "d2h_bytes_per_step": 24, "windows_s": e2e_s, "submissions_in_flight": E2E_DEPTH,
                     # rank 0's host time per step inside the two calls: enqueueing a step vs waiting for the previous one's statistics
-                    "host_ms_per_step": {"submit": 1000.0 * host_t["submit"] / max(1, args.steps - 1),
-                                         "collect_wait": 1000.0 * host_t["collect"] / max(1, args.steps - 1)}},
+                    "host_ms_per_step": {"submit": 1000.0 * host_t["submit"] / max(1, args.steps - E2E_DEPTH),
+                                         "collect_wait": 1000.0 * host_t["collect"] / max(1, args.steps - E2E_DEPTH)}},
             "gpu_launches": int(launches),
             "roofline": roof(args.math, gms, gl, gfl, ms / args.steps, bunch),
             "final_stats": {"xent_per_frame": st[0] / max(1, st[1]), "frames": st[1]},

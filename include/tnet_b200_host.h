@@ -55,10 +55,11 @@ int tnh_net_train_bunch(TnhNet *net, const float *x_host, const float *t_host, i
 int tnh_net_train_bunch_labels(TnhNet *net, const float *x_host, const int *labels_host, int rows, int cross_validate);
 int tnh_net_stats(TnhNet *net, double *error, long long *frames, long long *correct);
 /* Pipelined form of the pair above, for a host that feeds bunches from PINNED memory (what TNetCu's reader thread would do):
- * submit() enqueues the H2D copy of this bunch on the copy stream into one of two device buffers, the training step behind it on
+ * submit() enqueues the H2D copy of this bunch on the copy stream into one of four device buffers (at most four submissions in flight), the training step behind it on
  * the compute stream, and an asynchronous D2H copy of the running objective statistics; it returns without waiting.
  * collect() blocks until the OLDEST uncollected submission has finished and returns the statistics as of that bunch.  With one
- * submission kept in flight (submit k+1, then collect k) the copy of bunch k+1 overlaps the step of bunch k.  x_host/labels_host
+ * submission kept in flight (submit k+1, then collect k) the copy of bunch k+1 overlaps the step of bunch k; keeping more in flight
+ * absorbs host-side jitter (bench.py keeps three with several ranks, where a late rank stalls all of them).  x_host/labels_host
  * must stay unchanged until the submission has been collected. */
 int tnh_net_submit_bunch_labels(TnhNet *net, const float *x_host_pinned, const int *labels_host_pinned, int rows, int cross_validate);
 int tnh_net_collect(TnhNet *net, double *error, long long *frames, long long *correct);

@@ -34,19 +34,21 @@ struct TnhNet_ {
   // resident training set
   CuMatrix<BaseFloat> res_feats;
   CuVector<int> res_labels;
-  // pipelined submission (tnh_net_submit_bunch_labels / tnh_net_collect): two input slots
+  // pipelined submission (tnh_net_submit_bunch_labels / tnh_net_collect): NSLOT input slots (as many submissions may be in flight)
+  enum { NSLOT = 4 };
   struct Slot {
     CuMatrix<BaseFloat> feats;
+    CuMatrix<BaseFloat> stage;  // the bunch as it lies in host memory ([rows x nin] without a pitch, stored as ONE row): target of the H2D copy
     CuVector<int> labels;
     void *ready, *used, *done;  // H2D landed (copy stream) / step no longer reads the slot / statistics copied back
     TnbObjStats *stats_host;    // pinned
     Slot() : ready(NULL), used(NULL), done(NULL), stats_host(NULL) {}
-  } slot[2];
+  } slot[NSLOT];
   unsigned long long submitted, collected;
   TnhNet_() : obj(NULL), submitted(0), collected(0) {}
   ~TnhNet_() {
     delete obj;
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < NSLOT; i++) {
       if (slot[i].ready) { tnb_event_destroy(Cx(), slot[i].ready); tnb_event_destroy(Cx(), slot[i].used); tnb_event_destroy(Cx(), slot[i].done); }
       if (slot[i].stats_host) tnb_host_free(slot[i].stats_host);
     }
@@ -223,8 +225,8 @@ int tnh_net_train_bunch_labels(TnhNet *h, const float *x, const int *lab, int ro
 }
 int tnh_net_submit_bunch_labels(TnhNet *h, const float *x, const int *lab, int rows, int cv) {
   TNH_TRY
-  if (h->submitted - h->collected >= 2) Error("two submissions are already in flight: collect one first");
-  TnhNet_::Slot &s = h->slot[h->submitted & 1];
+  if (h->submitted - h->collected >= TnhNet_::NSLOT) Error("four submissions are already in flight: collect one first");
+  TnhNet_::Slot &s = h->slot[h->submitted % TnhNet_::NSLOT];
   const int nin = (int)h->net.GetNInputs();
   if (!s.ready) {
     TNB_CHECK(tnb_event_create(Cx(), &s.ready));
@@ -237,26 +239,41 @@ int tnh_net_submit_bunch_labels(TnhNet *h, const float *x, const int *lab, int r
   }
   if ((int)s.feats.Rows() != rows || (int)s.feats.Cols() != nin) {
     s.feats.Init(rows, nin);   // (re)allocation and zero-fill run on the compute stream: the copy must not overtake them
+    s.stage.Init(1, (size_t)rows * nin);
     s.labels.Init(rows);
     TNB_CHECK(tnb_event_record(Cx(), s.used, TNB_STREAM_COMPUTE));
   }
-  TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_COPY, s.used));  // the step that last read this slot (two submissions ago) is done
-  TNB_CHECK(tnb_memcpy2d_on(Cx(), TNB_STREAM_COPY, s.feats.pCUData(), s.feats.Stride() * sizeof(float), x, (size_t)nin * sizeof(float),
-                            (size_t)nin * sizeof(float), rows, 0));
+  static int dbg = -1;   // TNH_E2E_DEBUG (timing experiments only): 1 = no H2D copy, 2 = no statistics read-back, 4 = statistics on the copy stream
+  if (dbg < 0) { const char *e = getenv("TNH_E2E_DEBUG"); dbg = e ? atoi(e) : 0; }
+  TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_COPY, s.used));  // the step that last read this slot (NSLOT submissions ago) is done
+  // ONE contiguous H2D copy (a copy engine at PCIe rate), then the pitched layout on the device at the start of the step.  A pitched
+  // H2D copy (cudaMemcpy2DAsync, 1716-byte rows into a 1792-byte pitch for 429 inputs) cost 0.14 ms per bunch as soon as the
+  // peer-memory kernels of a data-parallel step occupied the SMs the GEMMs leave free (profiles/r02_dp_timeline.md).
+  if (!(dbg & 1))
+  TNB_CHECK(tnb_memcpy_on(Cx(), TNB_STREAM_COPY, s.stage.pCUData(), x, (size_t)rows * nin * sizeof(float), 0));
+  if (!(dbg & 1))
   TNB_CHECK(tnb_memcpy_on(Cx(), TNB_STREAM_COPY, s.labels.pCUData(), lab, sizeof(int) * (size_t)rows, 0));
   TNB_CHECK(tnb_event_record(Cx(), s.ready, TNB_STREAM_COPY));
   TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_COMPUTE, s.ready));
+  TNB_CHECK(tnb_memcpy2d_on(Cx(), TNB_STREAM_COMPUTE, s.feats.pCUData(), s.feats.Stride() * sizeof(float), s.stage.pCUData(), (size_t)nin * sizeof(float),
+                            (size_t)nin * sizeof(float), rows, 2));
   h->StepIds(s.feats, s.labels.pCUData(), 1, cv != 0);
   TNB_CHECK(tnb_event_record(Cx(), s.used, TNB_STREAM_COMPUTE));
-  TNB_CHECK(tnb_memcpy_on(Cx(), TNB_STREAM_COMPUTE, s.stats_host, h->obj->DeviceStats(), sizeof(TnbObjStats), 1));
-  TNB_CHECK(tnb_event_record(Cx(), s.done, TNB_STREAM_COMPUTE));
+  if (dbg & 4) {
+    TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_COPY, s.used));
+    TNB_CHECK(tnb_memcpy_on(Cx(), TNB_STREAM_COPY, s.stats_host, h->obj->DeviceStats(), sizeof(TnbObjStats), 1));
+    TNB_CHECK(tnb_event_record(Cx(), s.done, TNB_STREAM_COPY));
+  } else {
+    if (!(dbg & 2)) TNB_CHECK(tnb_memcpy_on(Cx(), TNB_STREAM_COMPUTE, s.stats_host, h->obj->DeviceStats(), sizeof(TnbObjStats), 1));
+    TNB_CHECK(tnb_event_record(Cx(), s.done, TNB_STREAM_COMPUTE));
+  }
   h->submitted++;
   TNH_CATCH
 }
 int tnh_net_collect(TnhNet *h, double *e, long long *f, long long *c) {
   TNH_TRY
   if (h->collected >= h->submitted) Error("nothing in flight");
-  TnhNet_::Slot &s = h->slot[h->collected & 1];
+  TnhNet_::Slot &s = h->slot[h->collected % TnhNet_::NSLOT];
   TNB_CHECK(tnb_event_sync(Cx(), s.done));
   *e = s.stats_host->error; *f = s.stats_host->frames; *c = s.stats_host->correct;
   h->collected++;
