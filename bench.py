@@ -596,13 +596,26 @@ def main():
             g2 = gemm_pass(n2, b2, f2)
             n2.close()
             return b2, median(w2), w2, l2, g2
+
+        def try_side_arm(key, math, scaling):
+            # a sub-object that fails must not lose the headline measurement: it is dropped (on every rank) and named on stderr
+            res, ok = None, 1
+            try:
+                res = side_arm(math, scaling)
+            except Exception as e:
+                ok = 0
+                sys.stderr.write("[bench] rank %d: the %s arm failed and is left out of the line: %s\n" % (rank, key, e))
+            if world > 1:
+                tt = torch.tensor([ok], dtype=torch.int32, device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+                ok = int(tt.item())
+            if ok:
+                extras[key] = res
         if args.math == "3xtf32":
-            b2, m2, w2, l2, g2 = side_arm("bf16", args.scaling)
-            extras["bf16"] = (b2, m2, w2, l2, g2)
+            try_side_arm("bf16", "bf16", args.scaling)
         if world > 1:
             other = "strong" if args.scaling == "weak" else "weak"
-            b2, m2, w2, l2, g2 = side_arm(args.math, other)
-            extras[other] = (b2, m2, w2, l2, g2)
+            try_side_arm(other, args.math, other)
         host.set_math(MATH[args.math])
 
     # ---- measured dense peaks of THIS box (library GEMM as a yardstick; nothing in the product calls it) ----
