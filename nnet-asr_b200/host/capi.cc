@@ -243,15 +243,11 @@ int tnh_net_submit_bunch_labels(TnhNet *h, const float *x, const int *lab, int r
     s.labels.Init(rows);
     TNB_CHECK(tnb_event_record(Cx(), s.used, TNB_STREAM_COMPUTE));
   }
-  static int dbg = -1;   // TNH_E2E_DEBUG (timing experiments only): 1 = no H2D copy, 2 = no statistics read-back, 4 = statistics on the copy stream
-  if (dbg < 0) { const char *e = getenv("TNH_E2E_DEBUG"); dbg = e ? atoi(e) : 0; }
   TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_COPY, s.used));  // the step that last read this slot (NSLOT submissions ago) is done
   // ONE contiguous H2D copy (a copy engine at PCIe rate), then the pitched layout on the device at the start of the step.  A pitched
   // H2D copy (cudaMemcpy2DAsync, 1716-byte rows into a 1792-byte pitch for 429 inputs) cost 0.14 ms per bunch as soon as the
   // peer-memory kernels of a data-parallel step occupied the SMs the GEMMs leave free (profiles/r02_dp_timeline.md).
-  if (!(dbg & 1))
   TNB_CHECK(tnb_memcpy_on(Cx(), TNB_STREAM_COPY, s.stage.pCUData(), x, (size_t)rows * nin * sizeof(float), 0));
-  if (!(dbg & 1))
   TNB_CHECK(tnb_memcpy_on(Cx(), TNB_STREAM_COPY, s.labels.pCUData(), lab, sizeof(int) * (size_t)rows, 0));
   TNB_CHECK(tnb_event_record(Cx(), s.ready, TNB_STREAM_COPY));
   TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_COMPUTE, s.ready));
@@ -259,14 +255,8 @@ int tnh_net_submit_bunch_labels(TnhNet *h, const float *x, const int *lab, int r
                             (size_t)nin * sizeof(float), rows, 2));
   h->StepIds(s.feats, s.labels.pCUData(), 1, cv != 0);
   TNB_CHECK(tnb_event_record(Cx(), s.used, TNB_STREAM_COMPUTE));
-  if (dbg & 4) {
-    TNB_CHECK(tnb_stream_wait_event(Cx(), TNB_STREAM_COPY, s.used));
-    TNB_CHECK(tnb_memcpy_on(Cx(), TNB_STREAM_COPY, s.stats_host, h->obj->DeviceStats(), sizeof(TnbObjStats), 1));
-    TNB_CHECK(tnb_event_record(Cx(), s.done, TNB_STREAM_COPY));
-  } else {
-    if (!(dbg & 2)) TNB_CHECK(tnb_memcpy_on(Cx(), TNB_STREAM_COMPUTE, s.stats_host, h->obj->DeviceStats(), sizeof(TnbObjStats), 1));
-    TNB_CHECK(tnb_event_record(Cx(), s.done, TNB_STREAM_COMPUTE));
-  }
+  TNB_CHECK(tnb_memcpy_on(Cx(), TNB_STREAM_COMPUTE, s.stats_host, h->obj->DeviceStats(), sizeof(TnbObjStats), 1));
+  TNB_CHECK(tnb_event_record(Cx(), s.done, TNB_STREAM_COMPUTE));
   h->submitted++;
   TNH_CATCH
 }
