@@ -244,14 +244,24 @@ class FeatureRepository {
     const std::string &Logical() const { return mLogical; }
     const std::string &Physical() const { return mPhysical; }
   };
-  FeatureRepository() : mSwap(true), mStartExt(0), mEndExt(0), mTargetKind(-1), mTrace(0), mPos(0) { memset(&mHeader, 0, sizeof(mHeader)); }
+  FeatureRepository() : mSwap(true), mStartExt(0), mEndExt(0), mTargetKind(12), mDerivOrder(-1), mHasCmn(false), mHasCvn(false), mHasCvg(false), mTrace(0), mPos(0) {
+    memset(&mHeader, 0, sizeof(mHeader));
+  }
 
+  /// Arguments as FeatureRepository::Init of the reference (Features.h): targetKind from ReadParmKind; derivOrder < 0 = whatever the
+  /// first file has; pDerivWinLen = derivOrder window lengths (DELTAWINDOW / ACCWINDOW / THIRDWINDOW or DERIVWINDOWS); the CMN / CVN
+  /// path + mask pairs select one normalisation file per utterance, pCvgFile is one global variance-scale file.
   void Init(bool swap, int extLeft, int extRight, int targetKind, int derivOrder, int *pDerivWinLen, const char *pCmnPath, const char *pCmnMask,
             const char *pCvnPath, const char *pCvnMask, const char *pCvgFile) {
-    (void)pDerivWinLen; (void)pCmnPath; (void)pCvnPath; (void)derivOrder;
     mSwap = swap; mStartExt = extLeft; mEndExt = extRight;
-    mTargetKind = targetKind;  // checked against every file's own kind: this reader converts nothing (CheckKind)
-    if (pCmnMask || pCvnMask || pCvgFile) Error("CMEAN/VARSCALE normalisation files are not built into the B200 hot path (use a <bias>/<window> transform)");
+    mTargetKind = targetKind;
+    mDerivOrder = derivOrder;
+    mDerivWin.clear();
+    for (int i = 0; pDerivWinLen && i < derivOrder; i++) mDerivWin.push_back(pDerivWinLen[i]);
+    mHasCmn = pCmnPath && pCmnMask; mHasCvn = pCvnPath && pCvnMask; mHasCvg = pCvgFile != NULL;
+    mCmnPath = pCmnPath ? pCmnPath : ""; mCmnMask = pCmnMask ? pCmnMask : "";
+    mCvnPath = pCvnPath ? pCvnPath : ""; mCvnMask = pCvnMask ? pCvnMask : "";
+    mCvgFile = pCvgFile ? pCvgFile : "";
   }
   void Trace(int t) { mTrace = t; }
   void AddFile(const std::string &entry) { mFiles.push_back(ParseEntry(entry)); }
@@ -272,7 +282,12 @@ class FeatureRepository {
   const FileRecord &Current() const { return mFiles[mPos]; }
   const HtkHeader &CurrentHeader() const { return mHeader; }
 
-  /// read the current file; STARTFRMEXT/ENDFRMEXT rows replicate the first/last frame
+  /// Read the current script-file entry the way the reference does (Features.cc:1025-1440, restated): open, header (and the scale /
+  /// bias vectors of a compressed file), resolve TARGETKIND against the file's own kind, take the requested frames plus the
+  /// STARTFRMEXT / ENDFRMEXT context (file's own neighbours first, then the edge frame replicated), drop energy columns and derivative
+  /// blocks the target does not want, per-utterance mean normalisation (_Z), derivatives the file lacks, then the CMN / CVN / global
+  /// variance files.  All arithmetic in float and in the reference's order, so the matrices are bit-identical (differential tests
+  /// against the reference's own reader: tests/test_host_cpu.py).
   void ReadFullMatrix(Matrix<BaseFloat> &rMatrix) {
     const FileRecord &rec = Current();
     FILE *f = fopen(rec.mPhysical.c_str(), "rb");
@@ -282,40 +297,148 @@ class FeatureRepository {
     HtkHeader h;
     memcpy(&h.mNSamples, hb, 4); memcpy(&h.mSamplePeriod, hb + 4, 4); memcpy(&h.mSampleSize, hb + 8, 2); memcpy(&h.mSampleKind, hb + 10, 2);
     if (mSwap) { h.mNSamples = Swap32(h.mNSamples); h.mSamplePeriod = Swap32(h.mSamplePeriod); h.mSampleSize = (int16_t)Swap16((uint16_t)h.mSampleSize); h.mSampleKind = Swap16(h.mSampleKind); }
-    if (h.mSampleKind & 02000) { fclose(f); Error(std::string("Compressed (_C) HTK files are not built into the B200 hot path: ") + rec.mPhysical); }
     // the reference's header check (Features.cc:522-528) also bounds the sample period: a wrong byte order shows up here
-    if (h.mSamplePeriod < 0 || h.mSamplePeriod > 100000 || h.mNSamples <= 0 || h.mSampleSize <= 0 || h.mSampleSize % 4 != 0) { fclose(f); Error(std::string("Invalid HTK header in feature file: '") + rec.mPhysical + "'"); }
-    if (!KindOk(h.mSampleKind)) {
+    if (h.mSamplePeriod < 0 || h.mSamplePeriod > 100000 || h.mNSamples < 0 || h.mSampleSize <= 0) { fclose(f); Error(std::string("Invalid HTK header in feature file: '") + rec.mPhysical + "'"); }
+    const bool comp = (h.mSampleKind & K_C) != 0;
+    std::vector<float> scale, bias;   // compressed files: x = (int16 + bias) / scale per column, both vectors behind the header
+    long data_off = 12;
+    if (comp) {
+      const size_t nc = (size_t)h.mSampleSize / 2;
+      scale.resize(nc); bias.resize(nc);
+      if (fread(scale.data(), 4, nc, f) != nc || fread(bias.data(), 4, nc, f) != nc) { fclose(f); Error(std::string("Cannot read feature file: '") + rec.mPhysical + "'"); }
+      if (mSwap) { SwapFloats(scale); SwapFloats(bias); }
+      h.mNSamples -= 4;   // the two float vectors count as four 16-bit "samples"
+      data_off += (long)nc * 8;
+    }
+    int kind = h.mSampleKind & ~K_C;
+    // ---- what the file has / what is wanted
+    const int sd = (kind & K_T) ? 3 : (kind & K_A) ? 2 : (kind & K_D) ? 1 : 0;
+    const int sE = (kind & K_E) != 0, s0 = (kind & K_0) != 0, sN = ((kind & K_N) != 0) * (sE + s0);
+    // TARGETKIND ANON adopts the FIRST file's kind for the rest of the run, as the reference's member does (Features.cc:1135-1143)
+    if (mTargetKind == K_ANON) mTargetKind = kind;
+    else if ((mTargetKind & 077) == K_ANON) mTargetKind = (mTargetKind & ~077) | (kind & 077);
+    const int tk = mTargetKind;
+    const int tE = (tk & K_E) != 0, t0 = (tk & K_0) != 0, tN = ((tk & K_N) != 0) * (tE + t0);
+    const int csize = comp ? 2 : 4;
+    int coefs = (h.mSampleSize / csize + sN) / (sd + 1) - sE - s0;   // static coefficients without the energy columns
+    const int src_vec = (coefs + sE + s0) * (sd + 1) - sN;
+    if (src_vec * csize != h.mSampleSize) { fclose(f); Error(std::string("Invalid HTK header in feature file: '") + rec.mPhysical + "' mSampleSize do not match with parmKind"); }
+    if (mDerivOrder < 0) mDerivOrder = sd;
+    const int dord = mDerivOrder;
+    if ((!sE && tE) || (!s0 && t0) || (sN && !tN) || (tN && !tE && !t0) || (tN && !dord) || (sN && !sd && dord) ||
+        ((kind & 077) != (tk & 077) && (kind & 077) != K_ANON)) {
       fclose(f);
-      char buf[256];
-      snprintf(buf, sizeof(buf), "Cannot convert parameter kind 0%o of '%s' to TARGETKIND 0%o: kind conversions (_Z mean normalisation, _E/_0/_N energy "
-               "columns, _D/_A/_T derivatives) are not built into the B200 hot path", (unsigned)h.mSampleKind, rec.mPhysical.c_str(), (unsigned)mTargetKind);
-      Error(buf);
+      Error(std::string("Cannot convert ") + ParmKind2Str(kind) + " to " + ParmKind2Str(tk));
     }
-    const int dim = h.mSampleSize / 4;
+    if ((int)mDerivWin.size() < dord && dord > sd) { fclose(f); Error("TARGETKIND asks for derivatives but no window lengths were given (DELTAWINDOW / ACCWINDOW / THIRDWINDOW / DERIVWINDOWS)"); }
+    // two combinations index one element BEFORE a feature row in the reference (Features.cc:1289, 1317 with trg_N > 0): refuse them
+    const bool sentence_cmn = !mHasCmn && !(kind & K_Z) && (tk & K_Z);
+    if (tN && (sentence_cmn || (sd == 0 && dord > 0))) {
+      fclose(f);
+      Error(std::string("Cannot convert ") + ParmKind2Str(kind) + " to " + ParmKind2Str(tk) + ": suppressing the absolute energy (_N) together with "
+            "mean normalisation or with derivatives computed from the static coefficients is undefined in the reference (it indexes outside the feature row)");
+    }
+    const int lo_ord = std::min(sd, dord);
+    const int trg_vec = (coefs + tE + t0) * (dord + 1) - tN;
+    // ---- frames: the requested range, extended by the file's own neighbours, then by replication
     int first = rec.mFirst < 0 ? 0 : rec.mFirst, last = rec.mLast < 0 ? h.mNSamples - 1 : rec.mLast;
-    if (first > last || last >= h.mNSamples) { fclose(f); Error(std::string("Frame range out of file: ") + rec.mLogical); }
-    const int n = last - first + 1;
-    // The context rows of a frame RANGE come from the file's own neighbouring frames where it has them; only beyond the ends of the
-    // FILE is the first/last frame replicated (Features.cc:1185-1191: from_frame/to_frame move outwards by min(ext, frames available)).
-    const int lo = std::max(0, first - mStartExt), hi = std::min((int)h.mNSamples - 1, last + mEndExt);
-    std::vector<float> buf((size_t)(hi - lo + 1) * dim);
-    fseek(f, 12 + (long)lo * h.mSampleSize, SEEK_SET);
-    if (fread(buf.data(), 4, buf.size(), f) != buf.size()) { fclose(f); Error(std::string("Cannot read feature file: '") + rec.mPhysical + "'"); }
+    int ext_left = mStartExt, ext_right = mEndExt;
+    { const int i = std::min(first, mStartExt); first -= i; ext_left -= i; }
+    { const int i = std::min(h.mNSamples - last - 1, mEndExt); last += i; ext_right -= i; }
+    if (first > last || first >= h.mNSamples || last < 0 || last >= h.mNSamples) { fclose(f); Error(std::string("Invalid frame range for feature file: '") + rec.mPhysical + "'"); }
+    const int nread = last - first + 1, tot = nread + ext_left + ext_right;
+    std::vector<float> raw((size_t)nread * src_vec);
+    fseek(f, data_off + (long)first * h.mSampleSize, SEEK_SET);
+    bool ok;
+    if (comp) {
+      std::vector<int16_t> q(raw.size());
+      ok = fread(q.data(), 2, q.size(), f) == q.size();
+      for (size_t i = 0; ok && i < q.size(); i++) {
+        const int16_t v = mSwap ? (int16_t)Swap16((uint16_t)q[i]) : q[i];
+        const size_t c = i % (size_t)src_vec;
+        raw[i] = ((float)v + bias[c]) / scale[c];
+      }
+    } else {
+      ok = fread(raw.data(), 4, raw.size(), f) == raw.size();
+      if (ok && mSwap) SwapFloats(raw);
+    }
     fclose(f);
-    if (mSwap) {
-      uint32_t *u = reinterpret_cast<uint32_t *>(buf.data());
-      for (size_t i = 0; i < buf.size(); i++) u[i] = (uint32_t)Swap32((int32_t)u[i]);
+    if (!ok) Error(std::string("Cannot read feature file: '") + rec.mPhysical + "'");
+    rMatrix.Init(tot, trg_vec);
+    // ---- copy what the target keeps: block 0 = statics (+ _0, _E unless the absolute energy is suppressed), blocks 1.. = derivatives
+    for (int i = 0; i < nread; i++) {
+      const float *src = raw.data() + (size_t)i * src_vec;
+      float *dst = rMatrix.pRowData(i + ext_left);
+      memcpy(dst, src, sizeof(float) * coefs); src += coefs; dst += coefs;
+      if (s0 && !sN) { if (t0 && !tN) *dst++ = *src; src++; }
+      if (sE && !sN) { if (tE && !tN) *dst++ = *src; src++; }
+      for (int b = 0; b < sd; b++) {
+        if (b < lo_ord) { memcpy(dst, src, sizeof(float) * coefs); dst += coefs; }
+        src += coefs;
+        if (s0) { if (b < lo_ord && t0) *dst++ = *src; src++; }
+        if (sE) { if (b < lo_ord && tE) *dst++ = *src; src++; }
+      }
     }
-    rMatrix.Init(n + mStartExt + mEndExt, dim);
-    for (int r = 0; r < n + mStartExt + mEndExt; r++) {
-      int src = first - mStartExt + r;  // frame of the file
-      src = src < lo ? lo : (src > hi ? hi : src);
-      memcpy(rMatrix.pRowData(r), buf.data() + (size_t)(src - lo) * dim, sizeof(float) * dim);
+    coefs += t0 + tE;   // from here on a block is `coefs` wide (block 0: coefs - tN)
+    const size_t have = (size_t)(coefs * (1 + lo_ord) - tN);
+    for (int i = 0; i < ext_left; i++) memcpy(rMatrix.pRowData(i), rMatrix.pRowData(ext_left), sizeof(float) * have);
+    for (int i = tot - ext_right; i < tot; i++) memcpy(rMatrix.pRowData(i), rMatrix.pRowData(tot - ext_right - 1), sizeof(float) * have);
+    // ---- sentence mean normalisation of the static block (float sums in frame order, Features.cc:1281-1300)
+    if (sentence_cmn) {
+      for (int j = 0; j < coefs; j++) {
+        float norm = 0.0f;
+        for (int i = 0; i < tot; i++) norm += rMatrix.pRowData(i)[j];
+        norm /= tot;
+        for (int i = 0; i < tot; i++) rMatrix.pRowData(i)[j] -= norm;
+      }
     }
+    // ---- derivatives the file does not carry: regression over +-winLen frames of the block below, edges clamped (Features.cc:1302-1343)
+    for (int d = sd; d < dord; d++) {
+      const int win = mDerivWin[d];
+      float norm = 0.0f;
+      for (int k = 1; k <= win; k++) norm += 2 * k * k;
+      for (int i = 0; i < tot; i++) {
+        for (int j = 0; j < coefs; j++) {
+          const int col = d * coefs - tN + j;
+          float acc = 0.0f;
+          for (int k = 1; k <= win; k++)
+            acc += k * (rMatrix.pRowData(i + std::min(tot - 1 - i, k))[col] - rMatrix.pRowData(i - std::min(i, k))[col]);
+          rMatrix.pRowData(i)[col + coefs] = acc / norm;
+        }
+      }
+    }
+    h.mNSamples = tot;
+    h.mSampleSize = (int16_t)(trg_vec * 4);
+    kind = tk & ~(K_D | K_A | K_T);
+    // ---- normalisation files
+    if (mHasCmn) {
+      std::string name;
+      MaskCapture(rec.mLogical, mCmnMask, name);
+      if (name.empty()) Error("CMN Matching failed");
+      std::vector<float> v;
+      ReadCepsNormFile(mCmnPath + "/" + name, kind & ~K_Z, 0, coefs, v);
+      for (int i = 0; i < tot; i++)
+        for (int j = tN; j < coefs; j++) rMatrix.pRowData(i)[j - tN] -= v[j];
+    }
+    kind |= dord == 3 ? (K_D | K_A | K_T) : dord == 2 ? (K_D | K_A) : dord == 1 ? K_D : 0;
+    if (mHasCvn) {
+      std::string name;
+      MaskCapture(rec.mLogical, mCvnMask, name);
+      std::vector<float> v;
+      ReadCepsNormFile(mCvnPath + "/" + name, kind, 1, trg_vec, v);
+      for (int i = 0; i < tot; i++)
+        for (int j = tN; j < trg_vec; j++) rMatrix.pRowData(i)[j - tN] *= v[j];
+    }
+    if (mHasCvg) {
+      std::vector<float> v;
+      ReadCepsNormFile(mCvgFile, -1, 2, trg_vec, v);
+      for (int i = 0; i < tot; i++)
+        for (int j = tN; j < trg_vec; j++) rMatrix.pRowData(i)[j - tN] *= v[j];
+    }
+    h.mSampleKind = (uint16_t)kind;
     mHeader = h;
-    mHeader.mNSamples = n;
-    if (mTrace & 1) std::cout << "[" << rec.mLogical << " " << n << "frm]" << std::flush;
+    mHeader.mNSamples = tot - mStartExt - mEndExt;   // frames without the context rows (what the trainers' progress lines count)
+    if (mTrace & 1) std::cout << "[" << rec.mLogical << " " << mHeader.mNSamples << "frm]" << std::flush;
   }
   /// write an uncompressed HTK parameter file in the byte order the reader was configured with (Features.cc:485-495,1481-1550)
   bool WriteFeatureMatrix(const Matrix<BaseFloat> &rMatrix, const std::string &filename, int targetKind, int samplePeriod) {
@@ -338,17 +461,19 @@ class FeatureRepository {
     if (!ok) Error(std::string("Cannot write to file:") + filename);
     return ok;
   }
-  /// The reference converts a file's parameter kind to TARGETKIND (Features.cc:1120-1178: per-utterance mean normalisation for _Z,
-  /// energy columns added or stripped, derivatives appended).  This reader converts nothing, so it accepts exactly the cases where the
-  /// reference's conversion is the identity — TARGETKIND=ANON (the file's own kind), or the same base kind (or an ANON base on either
-  /// side) with the same E/N/D/A/Z/0/T qualifiers — and refuses every other combination instead of training on different features.
-  bool KindOk(int fileKind) const {
-    const int conv = 0100 | 0200 | 0400 | 01000 | 04000 | 020000 | 0100000;
-    const int anon_here = 077, anon_htk = 12;   // ReadParmKind's ANON / the value in HTK headers
-    if (mTargetKind < 0 || mTargetKind == anon_here) return true;
-    const int tb = mTargetKind & 077, fb = fileKind & 077;
-    if (tb != anon_here && tb != anon_htk && fb != anon_htk && tb != fb) return false;
-    return (mTargetKind & conv) == (fileKind & conv);
+  enum { K_E = 0100, K_N = 0200, K_D = 0400, K_A = 01000, K_C = 02000, K_Z = 04000, K_K = 010000, K_0 = 020000, K_V = 040000, K_T = 0100000, K_ANON = 12 };
+  static const char *const *KindNames() {
+    static const char *names[] = {"WAVEFORM", "LPC", "LPREFC", "LPCEPSTRA", "LPDELCEP", "IREFC", "MFCC", "FBANK", "MELSPEC", "USER", "DISCRETE", "PLP", "ANON"};
+    return names;
+  }
+  /// "MFCC_E_D_A" from a kind word (base name, then the qualifiers in the reference's order E N D A C Z K 0 V T, Features.cc ParmKind2Str)
+  static std::string ParmKind2Str(int kind) {
+    const int base = kind & 077;
+    std::string out = base <= 12 ? KindNames()[base] : "UNKNOWN";
+    static const struct { int bit; const char *q; } quals[] = {{K_E, "_E"}, {K_N, "_N"}, {K_D, "_D"}, {K_A, "_A"}, {K_C, "_C"}, {K_Z, "_Z"}, {K_K, "_K"}, {K_0, "_0"}, {K_V, "_V"}, {K_T, "_T"}};
+    for (size_t i = 0; i < sizeof(quals) / sizeof(quals[0]); i++)
+      if (kind & quals[i].bit) out += quals[i].q;
+    return out;
   }
   static int ReadParmKind(const char *str, bool) {
     static const char *names[] = {"WAVEFORM", "LPC", "LPREFC", "LPCEPSTRA", "LPDELCEP", "IREFC", "MFCC", "FBANK", "MELSPEC", "USER", "DISCRETE", "PLP", "ANON"};
@@ -357,7 +482,7 @@ class FeatureRepository {
     std::string base = s.substr(0, us);
     int kind = -1;
     for (int i = 0; i < 13; i++)
-      if (!strcasecmp(base.c_str(), names[i])) kind = i == 12 ? 0x3F : i;
+      if (!strcasecmp(base.c_str(), names[i])) kind = i;
     if (kind < 0) return -1;
     while (us != std::string::npos) {
       size_t nx = s.find('_', us + 1);
@@ -371,6 +496,71 @@ class FeatureRepository {
   }
 
  private:
+  void SwapFloats(std::vector<float> &v) const {
+    uint32_t *u = reinterpret_cast<uint32_t *>(v.data());
+    for (size_t i = 0; i < v.size(); i++) u[i] = (uint32_t)Swap32((int32_t)u[i]);
+  }
+  /// the characters a mask's '%' match in a name, concatenated (the reference's ProcessMask, StkMatch.cc:453-493: "*/" before a mask
+  /// that does not start with '*', "/" before a name that does not start with '/'); false / empty when the mask does not match
+  static bool CaptureGlob(const char *p, const char *t, std::string &cap) {
+    for (; *p; p++, t++) {
+      if (*p == '*') {
+        while (*p == '*') p++;
+        if (!*p) return true;
+        for (; *t; t++) {
+          const size_t keep = cap.size();
+          if (CaptureGlob(p, t, cap)) return true;
+          cap.resize(keep);
+        }
+        return false;
+      }
+      if (!*t) return false;
+      if (*p == '[') Error("character classes ([...]) in file-name masks are not built into the B200 hot path");
+      if (*p == '%') cap.push_back(*t);
+      else if (*p != '?' && *p != *t) return false;
+    }
+    return !*t;
+  }
+  static bool MaskCapture(const std::string &name, const std::string &mask, std::string &cap) {
+    const std::string p = (mask.empty() || mask[0] != '*') ? "*/" + mask : mask, t = (name.empty() || name[0] != '/') ? "/" + name : name;
+    cap.clear();
+    if (CaptureGlob(p.c_str(), t.c_str(), cap)) return true;
+    cap.clear();
+    return false;
+  }
+  /// "<CEPSNORM> <KIND>  <MEAN|VARIANCE> n  v1 .. vn" (type 0 mean, 1 variance -> 1/sqrt) or "<VARSCALE> n  v1 .. vn" (type 2 -> sqrt);
+  /// the kind and the count must be what the features have at that point (Features.cc:97-179)
+  static void ReadCepsNormFile(const std::string &file, int kind, int type, int n, std::vector<float> &out) {
+    const char *tag = type == 0 ? "MEAN" : type == 1 ? "VARIANCE" : "VARSCALE", *what = type == 0 ? "CMN" : type == 1 ? "CVN" : "VarScale";
+    FILE *fp = fopen(file.c_str(), "r");
+    if (!fp) Error(std::string("Cannot open ") + what + " pFileName: '" + file + "'");
+    char s1[80], s2[80];
+    int cnt = 0;
+    bool ok = true;
+    if (type != 2) {
+      ok = fscanf(fp, " <%64[^>]> <%64[^>]>", s1, s2) == 2 && !strcasecmp(s1, "CEPSNORM") && ReadParmKind(s2, false) == kind;
+    }
+    ok = ok && fscanf(fp, " <%64[^>]> %d", s1, &cnt) == 2 && !strcasecmp(s1, tag) && cnt == n;
+    if (!ok) {
+      fclose(fp);
+      Error((type == 2 ? std::string("") : "<CEPSNORM> <" + ParmKind2Str(kind) + ">") + " <" + tag + " ... expected in " + what + " file " + file);
+    }
+    out.resize(n);
+    for (int i = 0; i < n; i++) {
+      if (fscanf(fp, " %f", &out[i]) != 1) {
+        std::string msg;
+        if (fscanf(fp, "%64s", s2) == 1) msg = std::string("Decimal number expected but '") + s2 + "' found in " + what + " file " + file;
+        else if (feof(fp)) msg = std::string("Unexpected end of ") + what + " file " + file;
+        else msg = std::string("Cannot read ") + what + " file " + file;
+        fclose(fp);
+        Error(msg);
+      }
+      if (type == 1) out[i] = (float)(1 / sqrt(out[i]));
+      else if (type == 2) out[i] = (float)sqrt(out[i]);
+    }
+    if (fscanf(fp, "%64s", s2) == 1) { fclose(fp); Error(std::string("End of file expected but '") + s2 + "' found in " + what + " file " + file); }
+    fclose(fp);
+  }
   static int32_t Swap32(int32_t v) { uint32_t u = (uint32_t)v; return (int32_t)((u >> 24) | ((u >> 8) & 0xFF00) | ((u << 8) & 0xFF0000) | (u << 24)); }
   static uint16_t Swap16(uint16_t v) { return (uint16_t)((v >> 8) | (v << 8)); }
   static FileRecord ParseEntry(const std::string &e) {
@@ -389,7 +579,11 @@ class FeatureRepository {
     return r;
   }
   bool mSwap;
-  int mStartExt, mEndExt, mTargetKind, mTrace;
+  int mStartExt, mEndExt, mTargetKind, mDerivOrder;
+  std::vector<int> mDerivWin;
+  bool mHasCmn, mHasCvn, mHasCvg;
+  std::string mCmnPath, mCmnMask, mCvnPath, mCvnMask, mCvgFile;
+  int mTrace;
   std::vector<FileRecord> mFiles;
   size_t mPos;
   HtkHeader mHeader;

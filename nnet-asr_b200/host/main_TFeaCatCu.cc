@@ -58,7 +58,7 @@ int main(int argc, char *argv[]) try {
   } else {
     Error("Source MMF must be specified [-H]");
   }
-  feature_repo.Init(fp.swap_features, fp.start_frm_ext, fp.end_frm_ext, fp.target_kind, fp.deriv_order, NULL, NULL, fp.cmn_mask, NULL, fp.cvn_mask, fp.cvg_file);
+  InitFeatureRepository(feature_repo, fp);
   if (NULL != p_script) feature_repo.AddFileList(p_script);
   if (feature_repo.QueueSize() <= 0) KALDI_ERR << "No input features specified,\n" << " try [-S SCP] or positional argument";
 

@@ -26,6 +26,7 @@
 
 #include "cu_nnet.h"
 #include "io.h"
+#include "main_common.h"
 
 using namespace TNet;
 
@@ -131,20 +132,8 @@ int main(int argc, char *argv[]) try {
   int args_parsed = ui.ParseOptions(argc, argv, p_option_string, SNAME);
 
   // ---- option retrieval (defaults: TNetCu.cc:192-248) ----
-  bool swap_features = !ui.GetBool(SNAME ":NATURALREADORDER", IsBigEndian());
-  int start_frm_ext = ui.GetInt(SNAME ":STARTFRMEXT", 0);
-  int end_frm_ext = ui.GetInt(SNAME ":ENDFRMEXT", 0);
-  const char *cmn_mask = ui.GetStr(SNAME ":CMEANMASK", NULL);
-  ui.GetStr(SNAME ":CMEANDIR", NULL);
-  const char *cvn_mask = ui.GetStr(SNAME ":VARSCALEMASK", NULL);
-  ui.GetStr(SNAME ":VARSCALEDIR", NULL);
-  const char *cvg_file = ui.GetStr(SNAME ":VARSCALEFN", NULL);
-  const char *target_kind_str = ui.GetStr(SNAME ":TARGETKIND", "ANON");
-  int target_kind = FeatureRepository::ReadParmKind(target_kind_str, false);
-  if (target_kind == -1) throw std::runtime_error(std::string("Invalid TARGETKIND = '") + target_kind_str + "'");
-  int deriv_order = (target_kind & 0100000) ? 3 : (target_kind & 01000) ? 2 : (target_kind & 0400) ? 1 : 0;
-  ui.GetInt(SNAME ":DELTAWINDOW", 2); ui.GetInt(SNAME ":ACCWINDOW", 2); ui.GetInt(SNAME ":THIRDWINDOW", 2);
-  ui.GetStr(SNAME ":DERIVWINDOWS", NULL);
+  FeatureParams fp = GetFeatureParams(ui, SNAME);   // STARTFRMEXT .. DERIVWINDOWS (UserInterface.cc:361-462)
+  const int start_frm_ext = fp.start_frm_ext, end_frm_ext = fp.end_frm_ext;
 
   const char *p_source_mmf_file = ui.GetStr(SNAME ":SOURCEMMF", NULL);
   const char *p_input_transform = ui.GetStr(SNAME ":FEATURETRANSFORM", NULL);
@@ -204,7 +193,7 @@ int main(int argc, char *argv[]) try {
     Error("Source MMF must be specified [-H]");
   }
 
-  feature_repo.Init(swap_features, start_frm_ext, end_frm_ext, target_kind, deriv_order, NULL, NULL, cmn_mask, NULL, cvn_mask, cvg_file);
+  InitFeatureRepository(feature_repo, fp);
   feature_repo.Trace(trace);
   if (NULL != p_script) feature_repo.AddFileList(p_script);
   else Warning("WARNING: The script file is missing [-S]");

@@ -45,7 +45,7 @@ int main(int argc, char *argv[]) try {
     Error("Source MMF must be specified [-H]");
   }
   if (NULL == p_targetmmf) Error("forgot to specify --TARGETMMF argument");
-  features.Init(fp.swap_features, fp.start_frm_ext, fp.end_frm_ext, fp.target_kind, fp.deriv_order, NULL, NULL, fp.cmn_mask, NULL, fp.cvn_mask, fp.cvg_file);
+  InitFeatureRepository(features, fp);
   if (NULL != p_script) features.AddFileList(p_script);
   else Warning("WARNING: The script file is missing [-S]");
 

@@ -56,7 +56,7 @@ int main(int argc, char *argv[]) try {
     Error(std::string("Layer must be RBM") + p_source_mmf_file);
   CuRbmBase &rbm = dynamic_cast<CuRbmBase &>(network.Layer(0));
 
-  feature_repo.Init(fp.swap_features, fp.start_frm_ext, fp.end_frm_ext, fp.target_kind, fp.deriv_order, NULL, NULL, fp.cmn_mask, NULL, fp.cvn_mask, fp.cvg_file);
+  InitFeatureRepository(feature_repo, fp);
   if (NULL != p_script) feature_repo.AddFileList(p_script);
   else Warning("WARNING: The script file is missing [-S]");
   feature_repo.Trace(trace);

@@ -67,7 +67,7 @@ int main(int argc, char *argv[]) try {
   if (NULL != p_input_transform) transform_network.ReadNetwork(p_input_transform);
   if (NULL != p_source_mmf_file) network.ReadNetwork(p_source_mmf_file);
   else Error("Source MMF must be specified [-H]");
-  feature_repo.Init(fp.swap_features, fp.start_frm_ext, fp.end_frm_ext, fp.target_kind, fp.deriv_order, NULL, NULL, fp.cmn_mask, NULL, fp.cvn_mask, fp.cvg_file);
+  InitFeatureRepository(feature_repo, fp);
   if (NULL != p_script) feature_repo.AddFileList(p_script);
   else Warning("WARNING: The script file is missing [-S]");
   if (NULL == p_source_mlf_file) Error("Source mlf file file is missing [-I]");

@@ -13,7 +13,13 @@ namespace TNet {
 struct FeatureParams {
   bool swap_features;
   int start_frm_ext, end_frm_ext, target_kind, deriv_order;
+  std::vector<int> deriv_win;       // window lengths of the derivatives (empty = none given)
+  bool has_cmn_path, has_cvn_path;  // a mask was given: the path is "<dir>/" (or "" without a directory), as the reference builds it
+  std::string cmn_path, cvn_path;
   const char *cmn_mask, *cvn_mask, *cvg_file;
+  int *DerivWin() { return deriv_win.empty() ? NULL : &deriv_win[0]; }
+  const char *CmnPath() const { return has_cmn_path ? cmn_path.c_str() : NULL; }
+  const char *CvnPath() const { return has_cvn_path ? cvn_path.c_str() : NULL; }
 };
 
 inline FeatureParams GetFeatureParams(UserInterface &ui, const char *sname) {
@@ -22,20 +28,54 @@ inline FeatureParams GetFeatureParams(UserInterface &ui, const char *sname) {
   p.swap_features = !ui.GetBool((s + ":NATURALREADORDER").c_str(), IsBigEndian());
   p.start_frm_ext = ui.GetInt((s + ":STARTFRMEXT").c_str(), 0);
   p.end_frm_ext = ui.GetInt((s + ":ENDFRMEXT").c_str(), 0);
+  const char *cmn_dir = ui.GetStr((s + ":CMEANDIR").c_str(), NULL);
   p.cmn_mask = ui.GetStr((s + ":CMEANMASK").c_str(), NULL);
-  ui.GetStr((s + ":CMEANDIR").c_str(), NULL);
+  p.has_cmn_path = p.cmn_mask != NULL;
+  if (p.has_cmn_path && cmn_dir) p.cmn_path = std::string(cmn_dir) + "/";
+  const char *cvn_dir = ui.GetStr((s + ":VARSCALEDIR").c_str(), NULL);
   p.cvn_mask = ui.GetStr((s + ":VARSCALEMASK").c_str(), NULL);
-  ui.GetStr((s + ":VARSCALEDIR").c_str(), NULL);
+  p.has_cvn_path = p.cvn_mask != NULL;
+  if (p.has_cvn_path && cvn_dir) p.cvn_path = std::string(cvn_dir) + "/";
   p.cvg_file = ui.GetStr((s + ":VARSCALEFN").c_str(), NULL);
   const char *tk = ui.GetStr((s + ":TARGETKIND").c_str(), "ANON");
   p.target_kind = FeatureRepository::ReadParmKind(tk, false);
   if (p.target_kind == -1) throw std::runtime_error(std::string("Invalid TARGETKIND = '") + tk + "'");
+  // DERIVWINDOWS ("2_2_2") sets the number of derivatives and their windows and leaves the three single-window parameters unread
+  // (UserInterface.cc:421-443); otherwise the order comes from TARGETKIND's _D/_A/_T and the windows from DELTAWINDOW / ACCWINDOW /
+  // THIRDWINDOW (default 2); a plain ANON target takes whatever the first file has (order -1)
+  const char *dw = ui.GetStr((s + ":DERIVWINDOWS").c_str(), NULL);
+  if (dw) {
+    std::string str(dw);
+    size_t pos = 0;
+    while ((pos = str.find_first_not_of(" \t_", pos)) != std::string::npos) {
+      size_t end = str.find_first_of(" \t_", pos);
+      const std::string tok = str.substr(pos, end == std::string::npos ? std::string::npos : end - pos);
+      char *ep;
+      long v = strtol(tok.c_str(), &ep, 0);
+      if (tok.empty() || *ep) throw std::runtime_error("Integers separated by '_' expected for parameter DERIVWINDOWS");
+      p.deriv_win.push_back((int)v);
+      pos = end == std::string::npos ? str.size() : end;
+    }
+    p.deriv_order = (int)p.deriv_win.size();
+    return p;
+  }
   p.deriv_order = (p.target_kind & 0100000) ? 3 : (p.target_kind & 01000) ? 2 : (p.target_kind & 0400) ? 1 : 0;
-  ui.GetInt((s + ":DELTAWINDOW").c_str(), 2);
-  ui.GetInt((s + ":ACCWINDOW").c_str(), 2);
-  ui.GetInt((s + ":THIRDWINDOW").c_str(), 2);
-  ui.GetStr((s + ":DERIVWINDOWS").c_str(), NULL);
+  if (p.deriv_order || p.target_kind != 12 /* ANON */) {
+    p.deriv_win.push_back(ui.GetInt((s + ":DELTAWINDOW").c_str(), 2));
+    p.deriv_win.push_back(ui.GetInt((s + ":ACCWINDOW").c_str(), 2));
+    p.deriv_win.push_back(ui.GetInt((s + ":THIRDWINDOW").c_str(), 2));
+    return p;
+  }
+  p.deriv_order = -1;
   return p;
+}
+
+/// FeatureRepository::Init with the parameters above (the trainers' call, TNetCu.cc:288-296)
+inline void InitFeatureRepository(FeatureRepository &repo, FeatureParams &fp) {
+  // the repository copies `deriv_order` window lengths: with DELTAWINDOW / ACCWINDOW / THIRDWINDOW all three exist whatever the order
+  std::vector<int> wins = fp.deriv_win;
+  repo.Init(fp.swap_features, fp.start_frm_ext, fp.end_frm_ext, fp.target_kind, fp.deriv_order, wins.empty() ? NULL : &wins[0], fp.CmnPath(), fp.cmn_mask,
+            fp.CvnPath(), fp.cvn_mask, fp.cvg_file);
 }
 
 inline void SelectMath(UserInterface &ui, const char *sname) {

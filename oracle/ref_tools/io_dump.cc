@@ -25,6 +25,56 @@ using namespace TNet;
 static void put32(FILE *f, int v) { fwrite(&v, 4, 1, f); }
 
 int main(int argc, char **argv) {
+  // fifth mode: <tool> --fea <scp> <start_ext> <end_ext> <swap 0|1> <out.bin>  features only, with the feature-side parameters the
+  // trainers read (UserInterface::GetFeatureParams) taken from the environment: FEA_TARGETKIND, FEA_DERIVWINDOWS ("2_2"), FEA_DELTAWINDOW,
+  // FEA_ACCWINDOW, FEA_THIRDWINDOW, FEA_CMNDIR, FEA_CMNMASK, FEA_CVNDIR, FEA_CVNMASK, FEA_CVGFILE.  Dump: int32 n, then per entry
+  // int32 rows, cols, header kind, sample period, float32 rows*cols.
+  if (argc == 7 && !strcmp(argv[1], "--fea")) {
+    try {
+      const char *tk = getenv("FEA_TARGETKIND") ? getenv("FEA_TARGETKIND") : "ANON";
+      const int kind = FeatureRepository::ReadParmKind(tk, false);
+      if (kind == -1) { fprintf(stderr, "Invalid TARGETKIND\n"); return 1; }
+      int order, wins[8], *pw = wins;
+      if (getenv("FEA_DERIVWINDOWS")) {
+        order = 0;
+        std::string s(getenv("FEA_DERIVWINDOWS"));
+        for (size_t p = 0; (p = s.find_first_not_of("_", p)) != std::string::npos && order < 8;) {
+          size_t e = s.find('_', p);
+          wins[order++] = atoi(s.substr(p, e == std::string::npos ? std::string::npos : e - p).c_str());
+          p = e == std::string::npos ? s.size() : e;
+        }
+      } else {
+        order = (kind & 0100000) ? 3 : (kind & 01000) ? 2 : (kind & 0400) ? 1 : 0;
+        if (order || kind != 12) {
+          wins[0] = getenv("FEA_DELTAWINDOW") ? atoi(getenv("FEA_DELTAWINDOW")) : 2;
+          wins[1] = getenv("FEA_ACCWINDOW") ? atoi(getenv("FEA_ACCWINDOW")) : 2;
+          wins[2] = getenv("FEA_THIRDWINDOW") ? atoi(getenv("FEA_THIRDWINDOW")) : 2;
+        } else { order = -1; pw = NULL; }
+      }
+      std::string cmn_path, cvn_path;
+      const char *cmn_mask = getenv("FEA_CMNMASK"), *cvn_mask = getenv("FEA_CVNMASK");
+      if (cmn_mask && getenv("FEA_CMNDIR")) cmn_path = std::string(getenv("FEA_CMNDIR")) + "/";
+      if (cvn_mask && getenv("FEA_CVNDIR")) cvn_path = std::string(getenv("FEA_CVNDIR")) + "/";
+      FeatureRepository repo;
+      repo.Init(atoi(argv[5]) != 0, atoi(argv[3]), atoi(argv[4]), kind, order, pw, cmn_mask ? cmn_path.c_str() : NULL, cmn_mask,
+                cvn_mask ? cvn_path.c_str() : NULL, cvn_mask, getenv("FEA_CVGFILE"));
+      repo.AddFileList(argv[2]);
+      FILE *out = fopen(argv[6], "wb");
+      if (!out) { perror("out"); return 1; }
+      put32(out, (int)repo.QueueSize());
+      for (repo.Rewind(); !repo.EndOfList(); repo.MoveNext()) {
+        Matrix<BaseFloat> m;
+        repo.ReadFullMatrix(m);
+        put32(out, (int)m.Rows()); put32(out, (int)m.Cols()); put32(out, (int)(repo.CurrentHeader().mSampleKind & 0xFFFF)); put32(out, (int)repo.CurrentHeader().mSamplePeriod);
+        for (size_t r = 0; r < m.Rows(); r++) fwrite(m.pRowData(r), sizeof(float), m.Cols(), out);
+      }
+      fclose(out);
+    } catch (std::exception &e) {
+      fprintf(stderr, "%s\n", e.what());
+      return 1;
+    }
+    return 0;
+  }
   // fourth mode: <tool> --readmv <text file> <out.bin>  reads a matrix then a vector with the text operators of the network files
   // (Matrix.tcc:575-600, Vector.tcc:527-547) and dumps int32 rows, cols, float32 values, int32 dim, float32 values
   if (argc == 4 && !strcmp(argv[1], "--readmv")) {

@@ -369,10 +369,10 @@ def test_mlf_record_lookup_rules_match_the_reference(tmp_path, case, feature_io_
             assert open(os.path.join(d, "ref.bin"), "rb").read() == open(os.path.join(d, "mine.bin"), "rb").read()
 
 
-@pytest.mark.parametrize("kind,ok", [("ANON", True), ("USER", True), ("USER_Z", False), ("MFCC", False), ("USER_D_A", False), ("ANON_Z", False)])
-def test_target_kind_that_needs_a_conversion_is_refused(tmp_path, kind, ok, feature_io_exe):
-    """The reader converts nothing: TARGETKIND must be ANON or describe the file as it is (the cases where the reference's conversion,
-    Features.cc:1120-1178, is the identity); _Z / energy / derivative requests and other base kinds fail instead of being ignored."""
+@pytest.mark.parametrize("kind,ok", [("ANON", True), ("USER", True), ("USER_Z", True), ("MFCC", False), ("USER_E", False), ("ANON_Z", True)])
+def test_target_kind_is_applied_or_refused_as_in_the_reference(tmp_path, kind, ok, feature_io_exe):
+    """TARGETKIND through the trainers' reading path: conversions the reference can do are done (here _Z), the others fail with its
+    message ("Cannot convert ...", Features.cc:1164-1178) instead of being ignored."""
     d = str(tmp_path)
     fea = os.path.join(d, "a.fea")
     F.write_htk(fea, np.random.default_rng(7).standard_normal((6, 4)).astype(np.float32))      # kind USER (9)
@@ -383,7 +383,150 @@ def test_target_kind_that_needs_a_conversion_is_refused(tmp_path, kind, ok, feat
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=dict(os.environ, TEST_TARGETKIND=kind))
     assert (r.returncode == 0) == ok, r.stderr[-400:]
     if not ok:
-        assert b"Cannot convert parameter kind" in r.stderr
+        assert b"Cannot convert USER to " in r.stderr
+
+
+# HTK parameter-kind words (Features.h:46-70)
+_K = dict(MFCC=6, USER=9, PLP=11, E=0o100, N=0o200, D=0o400, A=0o1000, C=0o2000, Z=0o4000, K=0o10000, O=0o20000, T=0o100000)
+
+
+def _write_htk_raw(path, x, kind, compressed=False, big_endian=True, period=100000):
+    """HTK parameter file of any kind; compressed = 16-bit samples with the per-column scale A and bias B behind the header
+    (x = (s + B) / A; the two float vectors count as 4 extra 'samples' in the header)."""
+    import struct
+    x = np.asarray(x, np.float32)
+    n, d = x.shape
+    e = ">" if big_endian else "<"
+    with open(path, "wb") as f:
+        if not compressed:
+            f.write(struct.pack(e + "iihH", n, period, 4 * d, kind))
+            f.write(x.astype(e + "f4").tobytes())
+        else:
+            hi, lo = x.max(0).astype(np.float64), x.min(0).astype(np.float64)
+            span = np.where(hi > lo, hi - lo, 1.0)
+            A = (2 * 32767.0 / span).astype(np.float32)
+            B = ((hi + lo) * 32767.0 / span).astype(np.float32)
+            q = np.clip(np.rint(x.astype(np.float64) * A - B), -32767, 32767).astype(np.int16)
+            f.write(struct.pack(e + "iihH", n + 4, period, 2 * d, kind | _K["C"]))
+            f.write(A.astype(e + "f4").tobytes())
+            f.write(B.astype(e + "f4").tobytes())
+            f.write(q.astype(e + "i2").tobytes())
+
+
+def _ceps_file(path, tag, values, kind_str=None):
+    with open(path, "w") as f:
+        if kind_str is not None:
+            f.write("<CEPSNORM> <%s>\n" % kind_str)
+        f.write("<%s> %d\n" % (tag, len(values)))
+        f.write(" ".join("%.6e" % v for v in values) + "\n")
+
+
+_FEA_CASES = {
+    # name: (source kind word, static coefs, file derivative order, has _E, has _0, compressed, environment, expected to succeed)
+    "user_plain": ("USER", 7, 0, 0, 0, False, {}, True),
+    "user_compressed": ("USER", 7, 0, 0, 0, True, {}, True),
+    "mfcc_e_d_a_as_is": ("MFCC", 12, 2, 1, 0, False, {"FEA_TARGETKIND": "MFCC_E_D_A"}, True),
+    "mfcc_e_d_a_keep_statics": ("MFCC", 12, 2, 1, 0, False, {"FEA_TARGETKIND": "MFCC_E"}, True),
+    "mfcc_e_d_a_drop_energy": ("MFCC", 12, 2, 1, 0, False, {"FEA_TARGETKIND": "MFCC_D"}, True),
+    "mfcc_e_d_a_third_derivative": ("MFCC", 12, 2, 1, 0, False, {"FEA_TARGETKIND": "MFCC_E_D_A_T", "FEA_THIRDWINDOW": "3"}, True),
+    "mfcc_e_d_a_sentence_cmn": ("MFCC", 12, 2, 1, 0, True, {"FEA_TARGETKIND": "MFCC_E_D_A_Z"}, True),
+    "mfcc_0_compute_d_a": ("MFCC", 12, 0, 0, 1, False, {"FEA_TARGETKIND": "MFCC_0_D_A", "FEA_DELTAWINDOW": "3", "FEA_ACCWINDOW": "1"}, True),
+    "mfcc_0_derivwindows": ("MFCC", 12, 0, 0, 1, True, {"FEA_TARGETKIND": "MFCC_0", "FEA_DERIVWINDOWS": "2_3"}, True),
+    "anon_z_d": ("PLP", 9, 0, 1, 1, False, {"FEA_TARGETKIND": "ANON_E_0_D_Z"}, True),
+    "mfcc_e_d_suppress_abs_energy": ("MFCC", 12, 1, 1, 0, False, {"FEA_TARGETKIND": "MFCC_E_D_N"}, True),
+    "cmn_cvn_cvg_files": ("MFCC", 12, 1, 1, 0, False, {"FEA_TARGETKIND": "MFCC_E_D_A", "norm_files": "1"}, True),
+    "other_base_kind": ("MFCC", 12, 0, 0, 0, False, {"FEA_TARGETKIND": "PLP"}, False),
+    "energy_the_file_lacks": ("MFCC", 12, 0, 0, 0, False, {"FEA_TARGETKIND": "MFCC_E"}, False),
+    "cmn_file_of_another_kind": ("MFCC", 12, 1, 1, 0, False, {"FEA_TARGETKIND": "MFCC_E_D", "norm_files": "wrong_kind"}, False),
+}
+
+
+@pytest.mark.parametrize("ext", [(0, 0), (3, 2)])
+@pytest.mark.parametrize("case", sorted(_FEA_CASES))
+def test_feature_kind_conversions_match_the_reference_reader(tmp_path, case, ext, feature_io_exe):
+    """FeatureRepository::ReadFullMatrix with everything the reference's reader does between the file and the trainer (Features.cc:
+    1025-1440): compressed files, TARGETKIND conversions (energy columns and derivative blocks dropped, _Z sentence mean normalisation,
+    missing derivatives computed with DELTAWINDOW / ACCWINDOW / THIRDWINDOW / DERIVWINDOWS), CMEANDIR+CMEANMASK / VARSCALEDIR+
+    VARSCALEMASK / VARSCALEFN files, frame ranges and context rows — byte for byte against the reference's own reader where it is
+    built (oracle/_ref/RefIoDump), and against properties stated here everywhere."""
+    base, nc, sd, has_e, has_0, comp, env, ok = _FEA_CASES[case]
+    d = str(tmp_path)
+    r = np.random.default_rng(abs(hash(case)) % 1000)
+    width = (nc + has_e + has_0) * (sd + 1)
+    kind = _K[base] | (_K["E"] if has_e else 0) | (_K["O"] if has_0 else 0) | (_K["D"] if sd >= 1 else 0) | (_K["A"] if sd >= 2 else 0)
+    names = ["spk1_a", "spk1_b", "spk2_a"]
+    data = {}
+    for k, nm in enumerate(names):
+        data[nm] = (r.standard_normal((25 + 7 * k, width)) * 3 + r.standard_normal(width)).astype(np.float32)
+        _write_htk_raw(os.path.join(d, nm + ".fea"), data[nm], kind, compressed=comp)
+    # logical names without the temporary directory: the masks below must find the speaker in them, not in a path component
+    scp = ["lg/spk1_a.fea=" + os.path.join(d, "spk1_a.fea"), "lg/spk1_b.fea=" + os.path.join(d, "spk1_b.fea") + "[4,20]",
+           "spk2_a.fea=" + os.path.join(d, "spk2_a.fea") + "[0,9]"]
+    open(os.path.join(d, "a.scp"), "w").write("\n".join(scp) + "\n")
+    env = dict(env)
+    nf = env.pop("norm_files", None)
+    if nf:
+        os.makedirs(os.path.join(d, "cmn")), os.makedirs(os.path.join(d, "cvn"))
+        tk = env["FEA_TARGETKIND"]
+        n_static = nc + has_e + has_0
+        n_all = n_static * (tk.count("_D") + tk.count("_A") + tk.count("_T") + 1)
+        static_kind = "MFCC_E" if nf != "wrong_kind" else "MFCC_0"
+        for spk in ("spk1", "spk2"):
+            _ceps_file(os.path.join(d, "cmn", spk), "MEAN", r.standard_normal(n_static), static_kind)
+            _ceps_file(os.path.join(d, "cvn", spk), "VARIANCE", r.random(n_all) + 0.5, tk)
+        _ceps_file(os.path.join(d, "cvg"), "VARSCALE", r.random(n_all) + 0.5)
+        env.update(FEA_CMNDIR=os.path.join(d, "cmn"), FEA_CMNMASK="%%%%_*", FEA_CVNDIR=os.path.join(d, "cvn"), FEA_CVNMASK="%%%%_*.fea",
+                   FEA_CVGFILE=os.path.join(d, "cvg"))
+    args = ["--fea", os.path.join(d, "a.scp"), str(ext[0]), str(ext[1]), "1"]
+    mine = subprocess.run([feature_io_exe] + args + [os.path.join(d, "mine.bin")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=dict(os.environ, **env))
+    assert (mine.returncode == 0) == ok, mine.stderr[-500:]
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "RefIoDump")
+    if os.path.exists(ref_exe):
+        ref = subprocess.run([ref_exe] + args + [os.path.join(d, "ref.bin")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=dict(os.environ, **env))
+        assert (ref.returncode == 0) == ok, ref.stderr[-500:]
+        if ok:
+            assert open(os.path.join(d, "ref.bin"), "rb").read() == open(os.path.join(d, "mine.bin"), "rb").read()
+    if not ok:
+        return
+    b = open(os.path.join(d, "mine.bin"), "rb").read()
+    pos, mats = 4, []
+    assert int(np.frombuffer(b, "<i4", 1, 0)[0]) == 3
+    for _ in range(3):
+        rows, cols, knd, per = (int(v) for v in np.frombuffer(b, "<i4", 4, pos)); pos += 16
+        mats.append((knd, np.frombuffer(b, "<f4", rows * cols, pos).reshape(rows, cols))); pos += 4 * rows * cols
+    assert pos == len(b)
+    assert [m.shape[0] for _, m in mats] == [25 + ext[0] + ext[1], 17 + ext[0] + ext[1], 10 + ext[0] + ext[1]]
+    tol = 2e-3 if comp else 0.0
+    if case in ("user_plain", "user_compressed", "mfcc_e_d_a_as_is"):
+        np.testing.assert_allclose(mats[0][1][ext[0]:ext[0] + 25], data["spk1_a"], rtol=0, atol=tol * 12)
+        lo = max(0, 4 - ext[0])                  # a range takes its context from the file's own frames where it has them
+        np.testing.assert_allclose(mats[1][1][ext[0] - (4 - lo):ext[0] + 17], data["spk1_b"][lo:21], rtol=0, atol=tol * 12)
+    if case == "mfcc_e_d_a_keep_statics":
+        np.testing.assert_array_equal(mats[0][1][ext[0]:ext[0] + 25], data["spk1_a"][:, :13])
+    if case == "mfcc_e_d_a_drop_energy":
+        np.testing.assert_array_equal(mats[0][1][ext[0]:ext[0] + 25], np.hstack([data["spk1_a"][:, 0:12], data["spk1_a"][:, 13:25]]))
+    if case == "mfcc_e_d_a_sentence_cmn":
+        assert np.abs(mats[0][1][:, :13].mean(0)).max() < 1e-4 and mats[0][0] & _K["Z"]
+    if case == "mfcc_0_compute_d_a":
+        m = mats[0][1]
+        assert m.shape[1] == 39
+        i = m.shape[0] // 2                      # an interior frame: delta = sum_k k (x[i+k] - x[i-k]) / (2 sum k^2), window 3
+        want = sum(k * (m[i + k, :13] - m[i - k, :13]) for k in (1, 2, 3)) / 28.0
+        np.testing.assert_allclose(m[i, 13:26], want, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(m[i, 26:39], (m[i + 1, 13:26] - m[i - 1, 13:26]) / 2.0, rtol=1e-5, atol=1e-6)
+
+
+def test_feature_kind_conversions_the_reference_leaves_undefined_are_refused(tmp_path, feature_io_exe):
+    """_N (absolute energy suppressed) together with sentence mean normalisation, or with first derivatives computed from the statics,
+    makes the reference index one element before a feature row (Features.cc:1289,1317): the reader refuses instead."""
+    d = str(tmp_path)
+    x = np.random.default_rng(2).standard_normal((12, 13)).astype(np.float32)
+    _write_htk_raw(os.path.join(d, "a.fea"), x, _K["MFCC"] | _K["E"])
+    open(os.path.join(d, "a.scp"), "w").write(os.path.join(d, "a.fea") + "\n")
+    for tk in ("MFCC_E_D_N", "MFCC_E_D_N_Z"):
+        r = subprocess.run([feature_io_exe, "--fea", os.path.join(d, "a.scp"), "0", "0", "1", os.path.join(d, "o.bin")], stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, env=dict(os.environ, FEA_TARGETKIND=tk))
+        assert r.returncode != 0 and b"undefined in the reference" in r.stderr, r.stderr[-300:]
 
 
 def _config_block(txt):
