@@ -228,6 +228,30 @@ inline void MakeHtkFileName(char *pOut, const char *inFileName, const char *out_
   strcpy(pOut, out.c_str());
 }
 
+/// A whole HTK parameter file as a float matrix, big-endian on disk whatever NATURALREADORDER says — Matrix::LoadHTK of the reference
+/// (Matrix.tcc:188-246), which the trainers use for target matrices with MLFTRANSC=FALSE (TNetCu.cc:402-407)
+inline void LoadHtkMatrix(const char *pFileName, Matrix<BaseFloat> &rOut) {
+  FILE *f = fopen(pFileName, "rb");
+  if (!f) Error(std::string("Cannot open target matrix file: '") + pFileName + "'");
+  unsigned char hb[12];
+  if (fread(hb, 1, 12, f) != 12) { fclose(f); Error(std::string("Invalid HTK header in target matrix file: '") + pFileName + "'"); }
+  const int32_t n = (int32_t)((uint32_t)hb[0] << 24 | (uint32_t)hb[1] << 16 | (uint32_t)hb[2] << 8 | (uint32_t)hb[3]);
+  const int size = (int16_t)((uint16_t)hb[8] << 8 | (uint16_t)hb[9]);
+  if (n <= 0 || size <= 0 || size % 4 != 0) { fclose(f); Error(std::string("Invalid HTK header in target matrix file: '") + pFileName + "'"); }
+  const int cols = size / 4;
+  rOut.Init(n, cols);
+  std::vector<unsigned char> row((size_t)size);
+  for (int r = 0; r < n; r++) {
+    if (fread(row.data(), 1, row.size(), f) != row.size()) { fclose(f); Error(std::string("Cannot read target matrix file: '") + pFileName + "'"); }
+    float *dst = rOut.pRowData(r);
+    for (int c = 0; c < cols; c++) {
+      const uint32_t u = (uint32_t)row[4 * c] << 24 | (uint32_t)row[4 * c + 1] << 16 | (uint32_t)row[4 * c + 2] << 8 | (uint32_t)row[4 * c + 3];
+      memcpy(dst + c, &u, 4);
+    }
+  }
+  fclose(f);
+}
+
 // ------------------------------------------------------------------------------------------ FeatureRepository
 struct HtkHeader {
   int32_t mNSamples;

@@ -204,13 +204,12 @@ int main(int argc, char *argv[]) try {
     if (trace & 1) TraceLog(std::string("Indexing labels: ") + p_source_mlf_file);
     label_repo.Init(p_source_mlf_file, p_output_label_map, p_src_lbl_dir, p_src_lbl_ext);
     label_repo.Trace(trace);
-  } else {
-    Error("MLFTRANSC=FALSE (targets from HTK matrix files) is not built into the B200 hot path");
   }
 
   CuObjectiveFunction *p_obj_function = CuObjectiveFunction::Factory(obj_fun_id);
   CuCrossEntropy *p_xent = dynamic_cast<CuCrossEntropy *>(p_obj_function);
-  const bool id_targets = p_xent != NULL;  // cross-entropy takes class ids; MSE needs the dense rows
+  // cross-entropy on MLF labels takes class ids; MSE, and targets read as matrices (MLFTRANSC=FALSE), need the dense rows
+  const bool id_targets = p_xent != NULL && mlf_transc;
   network.SetLearnRate(learning_rate, learning_rate_factors);
   network.SetMomentum(momentum);
   network.SetWeightcost(weightcost);
@@ -338,6 +337,21 @@ int main(int argc, char *argv[]) try {
       feats_trim.Init(rows, feats_expanded.Cols());
       feats_trim.CopyRows(rows, start_frm_ext, feats_expanded, 0);
       t_part.End(); time_xform += t_part.Val(); t_part.Start();
+      if (!mlf_transc) {
+        // targets are an HTK matrix file next to (or named after) the features (TNetCu.cc:402-413)
+        std::vector<char> lbl_file(strlen(feature_repo.Current().Logical().c_str()) + (p_src_lbl_dir ? strlen(p_src_lbl_dir) : 0) +
+                                   (p_src_lbl_ext ? strlen(p_src_lbl_ext) : 0) + 8);
+        MakeHtkFileName(&lbl_file[0], feature_repo.Current().Logical().c_str(), p_src_lbl_dir, p_src_lbl_ext);
+        Matrix<BaseFloat> labs_host;
+        LoadHtkMatrix(&lbl_file[0], labs_host);
+        t_part.End(); time_labels += t_part.Val(); t_part.Start();
+        labs_cu.CopyFrom(labs_host);
+        if ((int)labs_cu.Rows() != rows) Error(std::string("Nonmatching number number of input/target examples") + feature_repo.Current().Logical());
+        c.AddData(feats_trim, labs_cu);
+        t_part.End(); time_cache += t_part.Val();
+        feature_repo.MoveNext();
+        continue;
+      }
       // labels: class ids go to the device (4 bytes per frame instead of 4*nOutputs) ...
       std::vector<int> ids;
       label_repo.GenLabelIds(ids, rows, feature_repo.CurrentHeader().mSamplePeriod, feature_repo.Current().Logical().c_str());

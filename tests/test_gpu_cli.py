@@ -203,6 +203,52 @@ def test_config_e_full_size_dropin_vs_live_reference_trecurrentcu():
     np.testing.assert_allclose(L_our[1][1], L_ref[1][1], rtol=3e-4, atol=3e-4 * np.abs(L_ref[1][1]).max())   # output layer
 
 
+@pytest.mark.parametrize("objective", ["xent", "mse"])
+def test_tnetcu_targets_from_htk_matrix_files_vs_live_reference(objective):
+    """--MLFTRANSC=FALSE: the targets of every utterance are an HTK matrix file named after the features (-L dir -X ext), read whole
+    (TNetCu.cc:402-413, Matrix::LoadHTK) — bin/TNetCu against the unmodified reference TNetCu on the same files on this GPU: same
+    frames, objective value, accuracy and final weights; with one-hot rows as targets also the MLF-label run of the same data."""
+    ref = os.path.join(REF_BIN, "TNetCu")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/TNetCu is not built")
+    import subprocess
+    from tnet_b200 import formats as F
+    cfg = dict(raw_dim=13, ctx=2, hidden=[48], n_out=9, n_utt=6, n_frames=70, bunch=32, cache=128, lr=0.2, mmt=0.5, wc=1e-4, seed=11)
+    runs = []
+    for exe in (ref, os.path.join(BIN, "TNetCu")):
+        with tempfile.TemporaryDirectory() as d:
+            rng = np.random.default_rng(cfg["seed"] + 1000)
+            utts = F.gen_utterances(cfg["n_utt"], cfg["n_frames"], cfg["raw_dim"], cfg["n_out"], rng)
+            paths = F.write_dataset(d, utts, cfg["n_out"], cfg["ctx"])
+            tdir = os.path.join(d, "targets")
+            os.makedirs(tdir)
+            for name, fea in zip(utts.keys(), paths["files"]):
+                ids = utts[name][1]
+                T = np.zeros((len(ids), cfg["n_out"]), np.float32)
+                T[np.arange(len(ids)), ids] = 1.0
+                F.write_htk(os.path.join(tdir, os.path.splitext(os.path.basename(fea))[0] + ".tgt"), T)
+            dims = [cfg["raw_dim"] * (2 * cfg["ctx"] + 1)] + cfg["hidden"] + [cfg["n_out"]]
+            init, final = os.path.join(d, "init.nnet"), os.path.join(d, "final.nnet")
+            F.write_mlp(init, F.gen_mlp_init(dims, rng))
+            cmd = [exe, "-H", init, "-L", tdir, "-X", "tgt", "-S", paths["scp"], "--MLFTRANSC=FALSE", "--OBJECTIVEFUNCTION=" + objective,
+                   "-n", repr(cfg["lr"]), "--TARGETMMF=" + final, "--BUNCHSIZE=%d" % cfg["bunch"], "--CACHESIZE=%d" % cfg["cache"],
+                   "--RANDOMIZE=TRUE", "--SEED=%d" % cfg["seed"], "--FEATURETRANSFORM=" + paths["transform"],
+                   "--STARTFRMEXT=%d" % cfg["ctx"], "--ENDFRMEXT=%d" % cfg["ctx"], "--WEIGHTCOST=" + repr(cfg["wc"]),
+                   "--MOMENTUM=" + repr(cfg["mmt"]), "--GRADDIVFRM=TRUE"]
+            res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            assert res.returncode == 0, res.stdout[-2000:]
+            runs.append((res.stdout, F.read_mlp(final)))
+    (out_ref, L_ref), (out_our, L_our) = runs
+    r_ref, r_our = MG.parse_report(out_ref), MG.parse_report(out_our)
+    assert r_ref["frames"] == r_our["frames"] and r_our["frames"] >= 5 * 32
+    assert abs(r_our["err"] - r_ref["err"]) <= 1e-4 * abs(r_ref["err"])
+    if objective == "xent":
+        assert abs(r_our["correct_pct"] - r_ref["correct_pct"]) <= 0.5
+    for a, b in zip(L_our, L_ref):
+        if a[0] == "affine":
+            np.testing.assert_allclose(a[1], b[1], rtol=2e-4, atol=2e-4 * np.abs(b[1]).max())
+
+
 @pytest.mark.parametrize("case", ["feacat_post", "feacat_logpost"])
 def test_tfeacatcu_binary_reproduces_reference(case):
     """bin/TFeaCatCu with the reference's command line on the files the golden was produced from == the features the unmodified
