@@ -12,7 +12,8 @@
 //     two cache objects hold, fill after fill, exactly what the reference's single cache holds, and the shuffles draw lrand48() in the
 //     same order (only the loader calls it);
 //   * the cache keeps ONE CLASS ID per frame (a [rows x 1] column) instead of a dense one-hot row (Labels.cc:66,156 / cuCache.cc:124-153):
-//     at 3000 classes a fill of 131 072 frames moves 0.26 GB instead of 3.4 GB, and the objective kernel needs no target read;
+//     at 3000 classes a fill of 131 072 frames moves 0.26 GB instead of 3.4 GB, and the objective kernel needs no target read
+//     (dense rows remain for the MSE objective and for MLFTRANSC=FALSE, where the targets are HTK matrix files);
 //   * --GPUS=N: ONE cache and ONE permutation (bit-identical to the single-GPU run); GPU g trains rows [g*B/N, (g+1)*B/N) of every
 //     bunch (the reference CPU trainer's bunchsize_/num_thr, TNetLib/Platform.h:159) in its own thread; the gradients are summed and
 //     the update applied by the peer-memory kernel (csrc/peer.cu) with N = the whole bunch, so the weights equal the single-GPU run's.
