@@ -66,6 +66,41 @@ int main(int argc, char **argv) {
     }
     return 0;
   }
+  // sixth mode: <tool> --readlayers <network file> <out.bin>  walks a network file the way the component factory does (tag, sizes,
+  // then for <biasedlinearity> the transposed weight matrix and the bias vector through the text operators) and dumps, per affine
+  // layer, int32 rows, cols, float32 matrix, int32 dim, float32 vector: the stream must stand exactly behind every matrix it has read
+  if (argc == 4 && !strcmp(argv[1], "--readlayers")) {
+    try {
+      std::ifstream in(argv[2]);
+      FILE *f = fopen(argv[3], "wb");
+      std::string tag;
+      while (in >> tag) {
+        long a = -1, b = -1;
+        in >> a >> b;
+        if (in.fail()) { fprintf(stderr, "sizes behind %s\n", tag.c_str()); return 1; }
+        if (tag == "<biasedlinearity>") {
+          Matrix<BaseFloat> m;
+          Vector<BaseFloat> v;
+          in >> m;
+          in >> v;
+          int r = (int)m.Rows(), c = (int)m.Cols(), d = (int)v.Dim();
+          if (r != a || c != b || d != a) { fprintf(stderr, "layer sizes\n"); return 1; }
+          fwrite(&r, 4, 1, f); fwrite(&c, 4, 1, f);
+          for (int i = 0; i < r; i++) fwrite(m.pRowData(i), sizeof(float), c, f);
+          fwrite(&d, 4, 1, f);
+          fwrite(v.pData(), sizeof(float), d, f);
+        } else if (tag != "<sigmoid>" && tag != "<softmax>") {
+          fprintf(stderr, "unexpected tag %s\n", tag.c_str());
+          return 1;
+        }
+      }
+      fclose(f);
+    } catch (std::exception &e) {
+      fprintf(stderr, "%s\n", e.what());
+      return 1;
+    }
+    return 0;
+  }
   // fourth mode: <tool> --readmv <text file> <out.bin>  reads a matrix then a vector with the text operators of the network files
   // (Matrix.tcc:575-600, Vector.tcc:527-547) and dumps int32 rows, cols, float32 values, int32 dim, float32 values
   if (argc == 4 && !strcmp(argv[1], "--readmv")) {
