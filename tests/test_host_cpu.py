@@ -1,6 +1,7 @@
 """CPU-side tests of the host logic that needs no device: option grammar of the drop-in binaries (they must fail before
 touching the GPU), the text formats, and the data-parallel arithmetic (2 gloo ranks against the single-process oracle)."""
 import os
+import re
 import subprocess
 import sys
 
@@ -561,7 +562,12 @@ def test_config_file_and_option_dump_like_the_reference(tmp_path):
         norm = lambda ls: [l[2:] if l[:2] in ("  ", "# ") else l for l in ls]
         more = [["-D", "--learningrate=0.5", "-H", "x"], ["-D", "-n", "1", "-n", "2", "-H", "x"], ["-D", "-T", "3", "-H", "x"],
                 ["-D", "--BUNCHSIZE", "64", "-H", "x"], ["-D", "-c", "-H", "x"], ["-D", "--CROSSVALIDATE=t", "-H", "x"],
-                ["-D", "-H", "x", "-S", "a.scp", "extra1", "extra2"], ["-D", "--TNET:SEED=5", "-H", "x"], ["-D", "-A", "-V", "-H", "x"]]
+                ["-D", "-H", "x", "-S", "a.scp", "extra1", "extra2"], ["-D", "--TNET:SEED=5", "-H", "x"], ["-D", "-A", "-V", "-H", "x"],
+                # the feature-side parameters (UserInterface::GetFeatureParams)
+                ["-D", "--TARGETKIND=MFCC_E_D_A", "--DELTAWINDOW=3", "--ACCWINDOW=1", "-H", "x"],
+                ["-D", "--TARGETKIND=MFCC_0", "--DERIVWINDOWS=2", "-H", "x"],   # (with "2_3" the reference's strtok leaves a NUL in the value it dumps)
+                ["-D", "--CMEANDIR=/a", "--CMEANMASK=%%%_*", "--VARSCALEDIR=/b", "--VARSCALEMASK=%%%_*", "--VARSCALEFN=/c", "-H", "x"],
+                ["-D", "--STARTFRMEXT=3", "--ENDFRMEXT=4", "--NATURALREADORDER=T", "-H", "x"]]
         for a in [args] + more:
             ref = subprocess.run([ref_exe] + a, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             got = subprocess.run([os.path.join(BIN, "TNetCu")] + a, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -569,6 +575,16 @@ def test_config_file_and_option_dump_like_the_reference(tmp_path):
             assert (rb is None) == (gb is None), a
             assert rb is None or norm(rb) == norm(gb), a
             assert (ref.returncode != 0) and (got.returncode != 0)
+        # which parameters count as read decides what "Unexpected command line parameter" names: the single-window parameters are
+        # read only when TARGETKIND is not plain ANON, and not at all next to DERIVWINDOWS (UserInterface.cc:421-460)
+        unexpected = lambda txt: sorted(set(re.findall(r"Unexpected command line parameter (\S+)", txt)))
+        for a, want in [(["--DELTAWINDOW=3", "-H", "x"], ["TNET:DELTAWINDOW"]),
+                        (["--TARGETKIND=MFCC_D", "--DELTAWINDOW=3", "-H", "x"], []),
+                        (["--TARGETKIND=MFCC_D", "--DERIVWINDOWS=2", "--DELTAWINDOW=3", "-H", "x"], ["TNET:DELTAWINDOW"]),
+                        (["--TARGETKIND=USER", "--THIRDWINDOW=3", "-H", "x"], [])]:
+            ref = subprocess.run([ref_exe] + a, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            got = subprocess.run([os.path.join(BIN, "TNetCu")] + a, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            assert unexpected(ref.stdout)[:1] == want[:1] and unexpected(got.stdout)[:1] == want[:1], (a, ref.stdout[-300:], got.stdout[-300:])
 
 
 def test_make_htk_file_name_like_the_reference(tmp_path, feature_io_exe):
