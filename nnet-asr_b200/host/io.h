@@ -289,14 +289,24 @@ class FeatureRepository {
   }
   void Trace(int t) { mTrace = t; }
   void AddFile(const std::string &entry) { mFiles.push_back(ParseEntry(entry)); }
+  /// pFileName = one script file or several separated by commas (a comma behind a backslash does not separate; blanks around a name
+  /// are dropped; an empty name fails like a file that cannot be opened); an entry is a white-space separated token of the file, so a
+  /// line may hold several (Features.cc:390-429, Tokenizer.cc)
   void AddFileList(const char *pFileName) {
-    std::ifstream in(pFileName);
-    if (!in.good()) Error(std::string("Cannot open script file ") + pFileName);
-    std::string line;
-    while (std::getline(in, line)) {
-      size_t b = line.find_first_not_of(" \t\r"), e = line.find_last_not_of(" \t\r");
-      if (b == std::string::npos) continue;
-      AddFile(line.substr(b, e - b + 1));
+    const std::string list(pFileName);
+    size_t old_pos = 0, search = 0;
+    while (old_pos != std::string::npos) {
+      const size_t cur = list.find(',', search);
+      if (cur != 0 && cur != std::string::npos && list[cur - 1] == '\\') { search = cur + 1; continue; }
+      std::string name = list.substr(old_pos, cur == std::string::npos ? std::string::npos : cur - old_pos);
+      old_pos = cur == std::string::npos ? cur : cur + 1;
+      search = old_pos;
+      const size_t b = name.find_first_not_of(" \t\r\n"), e = name.find_last_not_of(" \t\r\n");
+      name = b == std::string::npos ? std::string() : name.substr(b, e - b + 1);
+      std::ifstream in(name.c_str());
+      if (name.empty() || !in.good()) Error(std::string("Cannot not open list file ") + name);
+      std::string entry;
+      while (in >> entry) AddFile(entry);
     }
   }
   size_t QueueSize() const { return mFiles.size(); }

@@ -705,6 +705,34 @@ def test_large_matrix_text_is_read_in_parallel_like_the_reference(tmp_path, case
         assert all(o == want for o in outs)
 
 
+@pytest.mark.parametrize("case", ["two_lists", "several_entries_per_line", "blanks_around_names", "trailing_comma", "missing_list"])
+def test_script_file_lists_like_the_reference(tmp_path, case, feature_io_exe):
+    """-S takes one script file or several separated by commas, and an entry is a white-space separated token (several per line are
+    several entries) — FeatureRepository::AddFileList, Features.cc:390-429 — against the reference's own reader."""
+    d = str(tmp_path)
+    r = np.random.default_rng(6)
+    feas = []
+    for k in range(4):
+        fea = os.path.join(d, "f%d.fea" % k)
+        F.write_htk(fea, r.standard_normal((5 + k, 3)).astype(np.float32))
+        feas.append(fea)
+    a, b = os.path.join(d, "a.scp"), os.path.join(d, "b.scp")
+    open(a, "w").write(feas[0] + "\n" + feas[1] + "\n")
+    open(b, "w").write(feas[2] + "   " + feas[3] + "\n" if case == "several_entries_per_line" else feas[2] + "\n" + feas[3] + "\n")
+    arg, ok, n = {"two_lists": (a + "," + b, True, 4), "several_entries_per_line": (b, True, 2), "blanks_around_names": (" " + a + " , " + b + " ", True, 4),
+                  "trailing_comma": (a + ",", False, 0), "missing_list": (a + "," + os.path.join(d, "none.scp"), False, 0)}[case]
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "RefIoDump")
+    outs = []
+    for tool in [feature_io_exe] + ([ref_exe] if os.path.exists(ref_exe) else []):
+        out = os.path.join(d, os.path.basename(tool) + ".bin")
+        rc = subprocess.run([tool, "--fea", arg, "0", "0", "1", out], stdout=subprocess.PIPE, stderr=subprocess.PIPE).returncode
+        assert (rc == 0) == ok, (tool, case)
+        if ok:
+            outs.append(open(out, "rb").read())
+    if ok:
+        assert int(np.frombuffer(outs[0], "<i4", 1, 0)[0]) == n and all(o == outs[0] for o in outs)
+
+
 def test_network_file_with_large_layers_is_walked_like_the_python_parser(tmp_path, feature_io_exe):
     """A three-layer network file whose matrices take the parallel text reader (two of them) and the one-by-one reader (one), walked
     tag by tag as the component factory does: every matrix and vector must come out as the Python parser reads them, i.e. the stream
