@@ -1,36 +1,31 @@
 #!/usr/bin/env bash
-# What the next GPU session should run first, as three gpurun calls.  Each block writes into gpurun_out/.
+# What a new GPU session should run first.  Each block writes into gpurun_out/next/.
 #
-#   1 GPU :  gpurun --timeout 600 -- 'bash tools/next_gpu_checks.sh one'
-#   2 GPUs:  gpurun --gpus 2 --timeout 600 -- 'bash tools/next_gpu_checks.sh two'
-#   4 GPUs:  gpurun --gpus 4 --timeout 400 -- 'bash tools/next_gpu_checks.sh four'
+#   1 GPU :  gpurun --timeout 900 -- 'bash tools/next_gpu_checks.sh one'
+#   N GPUs:  gpurun --gpus N --timeout 600 -- 'bash tools/next_gpu_checks.sh many N'      (N = 2, 4 or 8)
 set -u
-mkdir -p gpurun_out
+O=gpurun_out/next
+mkdir -p $O
+export MASTER_ADDR=127.0.0.1
 case "${1:-one}" in
   one)
-    # GPU goldens that need the reference TNetCu (learning-rate factors), then the whole GPU suite incl. the tests added after
-    # round 1's last full run, then an ncu capture of the peer-memory kernel driven by virtual ranks on one device
-    python tests/golden/make_golden.py --impl gpu --only opt_ --out gpurun_out/golden > gpurun_out/make_golden_opt.log 2>&1
-    cp gpurun_out/golden/*.npz tests/golden/ 2>/dev/null
-    python -m pytest tests -m gpu -q -rxX > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-    tail -5 gpurun_out/pytest_gpu.log
-    ncu --set full --clock-control none --import-source on -k regex:dp_peer_update_kernel -c 8 -o gpurun_out/peer_virtual \
-        python -m pytest tests/test_gpu_kernels.py -q -k "peer and 100-260-8" > gpurun_out/ncu_peer.log 2>&1
-    python bench.py --steps 50 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+    # the whole GPU suite, the smoke entry point, the default bench line (3xTF32 headline + bf16 sub-object + CPU baseline), and
+    # the launch list of one bunch under ncu (only after the same command has run cleanly without it)
+    python -m pytest tests -m gpu -q -rxXs > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest_gpu.log
+    python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/smoke.log
+    python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; echo "bench rc=$?"
+    python bench.py --steps 2 --warmup 3 --windows 1 --no-extras --no-cpu-baseline > $O/bench_small.json 2> $O/bench_small.err &&
+    ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv \
+        --log-file $O/launches.csv python bench.py --steps 2 --warmup 3 --windows 1 --no-extras --no-cpu-baseline > $O/ncu_launches.log 2>&1
     ;;
-  two)
-    export MASTER_ADDR=127.0.0.1
-    python -m pytest tests/test_gpu_multi.py -m gpu -q > gpurun_out/pytest_multi.log 2>&1; tail -3 gpurun_out/pytest_multi.log
-    python tools/symm_probe.py > /dev/null 2>&1 || true
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29571 tools/symm_probe.py \
-        > gpurun_out/symm_probe_n2.txt 2>&1
-    python tools/dp_sweep.py --gpus 2 --modes peer,allreduce --ctas 12,20,32 --out gpurun_out/dp_sweep_n2.jsonl | tee gpurun_out/dp_sweep_n2.txt
-    python tools/dp_sweep.py --gpus 2 --math bf16 --modes peer,allreduce --ctas 20 --out gpurun_out/dp_sweep_n2_bf16.jsonl | tee gpurun_out/dp_sweep_n2_bf16.txt
-    ;;
-  four)
-    export MASTER_ADDR=127.0.0.1
-    DP_EQUIV_MODES=peer python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29572 \
-        tools/dp_equivalence.py > gpurun_out/dp_equiv_n4.log 2>&1; grep -E "dp ok|DP_EQUIV" gpurun_out/dp_equiv_n4.log
-    python tools/dp_sweep.py --gpus 4 --modes peer,allreduce --ctas 20 --out gpurun_out/dp_sweep_n4.jsonl | tee gpurun_out/dp_sweep_n4.txt
+  many)
+    N=${2:-2}
+    # N-rank equivalence (every schedule, both math modes), the 2-GPU tests of the suite, the default bench line as the driver launches
+    # it, and the same with the data-parallel step's timeline on stderr (TNB_DP_TRACE=1: peer-memory kernels and copy-engine pushes)
+    python -m pytest tests/test_gpu_multi.py tests/test_gpu_cli.py -m gpu -q -k "two_gpu or two_gpus" > $O/pytest_multi.log 2>&1; tail -2 $O/pytest_multi.log
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29571 bench.py --gpus $N --steps 50 --warmup 5 \
+        > $O/bench_n$N.json 2> $O/bench_n$N.err; echo "bench rc=$?"
+    TNB_DP_TRACE=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29572 bench.py --gpus $N --steps 50 \
+        --warmup 5 --windows 3 --no-extras > $O/bench_n${N}_trace.json 2> $O/bench_n${N}_trace.err; grep "dp trace\] r0" $O/bench_n${N}_trace.err | tail -24
     ;;
 esac
