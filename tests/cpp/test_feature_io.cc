@@ -115,7 +115,7 @@ int main(int argc, char **argv) {
       fwrite(&r, 4, 1, f); fwrite(&c, 4, 1, f);
       for (int i = 0; i < r; i++) fwrite(m.pRowData(i), sizeof(float), c, f);
       fwrite(&d, 4, 1, f);
-      fwrite(v.pData(), sizeof(float), d, f);
+      if (d > 0) fwrite(v.pData(), sizeof(float), d, f);
       fclose(f);
     } catch (std::exception &e) {
       fprintf(stderr, "%s\n", e.what());

@@ -181,7 +181,9 @@ def test_fast_text_reader_writer_matches_ostream_format(tmp_path):
 def feature_io_exe(tmp_path_factory):
     """tests/cpp/test_feature_io.cc (the drop-in's readers behind the dump format of oracle/ref_tools/io_dump.cc), compiled once"""
     exe = str(tmp_path_factory.mktemp("feature_io") / "test_feature_io")
-    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "nnet-asr_b200", "host"), "-I",
+    # TNB_TEST_SANITIZE=1: the same tests with AddressSanitizer + UBSan under the readers (developer switch)
+    san = ["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-g"] if os.environ.get("TNB_TEST_SANITIZE") else []
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-pthread"] + san + ["-I", os.path.join(ROOT, "nnet-asr_b200", "host"), "-I",
                            os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_feature_io.cc")])
     return exe
 
