@@ -660,7 +660,12 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
             "vs_baseline": None, "dtype": {"3xtf32": "tf32x3", "tf32": "tf32", "bf16": "bf16"}[args.math], "data": "synthetic",
             "config": {"workload": WORKLOAD, "dims": DIMS, "bunch_per_gpu": bunch, "global_bunch": bunch * world,
-                       "parallelism": "dp%d" % world, "dp_schedule": dp_state["schedule"], "learn_rate": LR, "momentum": MMT, "weightcost": WC,
+                       "parallelism": "dp%d" % world, "dp_schedule": dp_state["schedule"],
+                       "dp_gradient_transport": (None if world == 1 or not str(dp_state["schedule"]).startswith("peer") else
+                                                 {"0": "owner pulls (peer loads)", "1": "GEMM-epilogue peer stores, every layer",
+                                                  "2": "fp32, copy engines for the upper layers + GEMM-epilogue peer stores for the %s lowest"
+                                                       % os.environ.get("TNB_DP_PUSH_TAIL", "2")}.get(os.environ.get("TNB_DP_PUSH", "2"), "?")),
+                       "learn_rate": LR, "momentum": MMT, "weightcost": WC,
                        "l2_note": ("no L2 flush: weights+corrections (224 MB) and activations exceed the 126 MB L2 every step" if args.config == "C" else
                                    "no L2 flush: the model (2-4 MB) is L2-resident by nature; the 16 resident bunches rotate"),
                        "timed_region": "K x (row window of the resident set, int labels -> one-hot, forward, softmax+xent+accuracy, backward, "
